@@ -1,0 +1,23 @@
+"""B200-native Mamba-TasNet separator forward (drop-in for ``Mamba-TasNet/modules`` of shangfuu/avse_challenge).
+
+Public surface:
+    Encoder, MaskNet, Decoder, MambaBlocksSequential, Block, Mamba   -- reference-named nn.Module drop-ins
+    MambaTasNetSeparator                                              -- fused compute_forward equivalent
+    SeparatorEngine                                                   -- the kernel plan itself
+    CONFIGS / HParams / init_state_dicts                              -- the four shipped configurations
+The compute path is ``libmtn_b200.so`` (C ABI in ``include/mtn_b200.h``); importing this package does not
+load it, calling any op without it raises.
+"""
+from .hparams import CONFIGS, HParams, init_state_dicts  # noqa: F401
+from .synth import synth_mixture, si_snr, pit_si_snr  # noqa: F401
+
+
+def __getattr__(name):
+    if name in ("Encoder", "MaskNet", "Decoder", "MambaBlocksSequential", "Block", "Mamba", "MambaTasNetSeparator",
+                "RMSNorm", "ChannelwiseLayerNorm"):
+        from . import modules
+        return getattr(modules, name)
+    if name == "SeparatorEngine":
+        from .engine import SeparatorEngine
+        return SeparatorEngine
+    raise AttributeError(name)

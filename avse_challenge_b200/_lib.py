@@ -1,0 +1,87 @@
+"""ctypes binding of ``libmtn_b200.so`` (the C ABI declared in ``include/mtn_b200.h``).
+
+There is no fallback: if the library is missing, or an entry point fails, this raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmtn_b200.so")
+
+EPI_STORE, EPI_INPROJ, EPI_MASK, EPI_RELU = 0, 1, 2, 3
+
+EXPORTS = [
+    "mtn_encoder_cln_fwd", "mtn_gemm_fwd", "mtn_add_rmsnorm_fwd", "mtn_conv_silu_fwd", "mtn_scan_fwd",
+    "mtn_decoder_fwd", "mtn_cln_fwd", "mtn_split_planes", "mtn_last_error_string", "mtn_abi_version",
+]
+
+
+class GemmArgs(Structure):
+    _fields_ = [
+        ("a", c_void_p), ("w", c_void_p), ("out", c_void_p), ("aux", c_void_p),
+        ("M", c_int), ("N", c_int), ("K", c_int), ("a_rows", c_int),
+        ("lda", c_int), ("ldo", c_int), ("ld_aux", c_int),
+        ("planes", c_int), ("groups", c_int), ("out_group_stride", c_int),
+        ("epilogue", c_int), ("epi_param", c_int), ("out_bf16", c_int), ("max_ctas", c_int),
+    ]
+
+
+class ScanArgs(Structure):
+    _fields_ = [
+        ("u", c_void_p), ("dbl", c_void_p), ("z", c_void_p), ("w_dt", c_void_p), ("dt_bias", c_void_p),
+        ("A2", c_void_p), ("Dskip", c_void_p), ("y", c_void_p), ("h_in", c_void_p), ("h_out", c_void_p),
+        ("batch", c_int), ("L", c_int), ("di", c_int), ("R", c_int), ("n_dbl", c_int), ("ld_dbl", c_int),
+        ("ldz", c_int), ("z_col0", c_int), ("planes", c_int), ("z_bf16", c_int), ("dir_mask", c_int),
+    ]
+
+
+class MtnError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load the CUDA library; raise loudly when it has not been built (no CPU / eager fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MtnError(
+            f"{LIB_PATH} not found: build it with `python -m avse_challenge_b200.build` "
+            "(nvcc, sm_100a). There is no fallback implementation.")
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.mtn_last_error_string.restype = c_char_p
+    lib.mtn_last_error_string.argtypes = []
+    lib.mtn_abi_version.restype = c_int
+    lib.mtn_encoder_cln_fwd.argtypes = [c_void_p] * 6 + [c_int] * 5 + [c_float, c_void_p]
+    lib.mtn_gemm_fwd.argtypes = [POINTER(GemmArgs), c_void_p]
+    lib.mtn_add_rmsnorm_fwd.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_float,
+                                        c_void_p]
+    lib.mtn_conv_silu_fwd.argtypes = [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                      c_void_p]
+    lib.mtn_scan_fwd.argtypes = [POINTER(ScanArgs), c_void_p]
+    lib.mtn_decoder_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]
+    lib.mtn_cln_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p]
+    lib.mtn_split_planes.argtypes = [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p]
+    for name in EXPORTS:
+        fn = getattr(lib, name, None)
+        if fn is not None and name not in ("mtn_last_error_string", "mtn_abi_version"):
+            fn.restype = c_int
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = load().mtn_last_error_string().decode("utf-8", "replace")
+        raise MtnError(f"{what} failed (rc={rc}): {msg}")
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or None)."""
+    return None if t is None else t.data_ptr()

@@ -1,0 +1,539 @@
+// HBM-bound streaming kernels of the Mamba-TasNet path (sm_100a): waveform encoder + channel LayerNorm,
+// residual add + RMSNorm, bidirectional depthwise causal conv + SiLU, overlap-add decoder, plane packing.
+// All activations channel-last; all global accesses are warp-contiguous (>= 64 B per warp instruction,
+// 128-bit per lane where the row length allows).
+#include "mtn_ptx.cuh"
+#include "mtn_host.h"
+
+namespace mtn {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <int P>
+__device__ __forceinline__ void store_planes1(__nv_bfloat16* base, size_t plane_stride, size_t off, float v) {
+    if (P == 2) {
+        __nv_bfloat16 hi, lo;
+        split_bf16(v, hi, lo);
+        base[off] = hi;
+        base[plane_stride + off] = lo;
+    } else {
+        base[off] = __float2bfloat16_rn(v);
+    }
+}
+
+template <int P>
+__device__ __forceinline__ void store_planes4(__nv_bfloat16* base, size_t plane_stride, size_t off, float4 v) {
+    __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
+    if (P == 2) {
+        split_bf16(v.x, h0, l0);
+        split_bf16(v.y, h1, l1);
+        split_bf16(v.z, h2, l2);
+        split_bf16(v.w, h3, l3);
+    } else {
+        h0 = __float2bfloat16_rn(v.x);
+        h1 = __float2bfloat16_rn(v.y);
+        h2 = __float2bfloat16_rn(v.z);
+        h3 = __float2bfloat16_rn(v.w);
+    }
+    __nv_bfloat162 a = __halves2bfloat162(h0, h1), b = __halves2bfloat162(h2, h3);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&a);
+    pk.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(base + off) = pk;
+    if (P == 2) {
+        __nv_bfloat162 c = __halves2bfloat162(l0, l1), d = __halves2bfloat162(l2, l3);
+        pk.x = *reinterpret_cast<uint32_t*>(&c);
+        pk.y = *reinterpret_cast<uint32_t*>(&d);
+        *reinterpret_cast<uint2*>(base + plane_stride + off) = pk;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Encoder (Conv1d 1->N, k=16, s=8, no bias, ReLU) + ChannelwiseLayerNorm.  One warp per frame.
+// Reference: speechbrain dual_path.Encoder == baseline/avse2/model.py:14-24; cLN call
+// Mamba-TasNet/modules/mamba_masknet.py:118 (biased variance, eps 1e-8).
+// ------------------------------------------------------------------------------------------------
+template <int P, int NJ>  // NJ = N / 32 channels per lane
+__global__ void __launch_bounds__(256)
+encoder_cln_kernel(const float* __restrict__ mix, const float* __restrict__ w_enc, const float* __restrict__ gamma,
+                   const float* __restrict__ beta, float* __restrict__ mix_w, __nv_bfloat16* __restrict__ yn, int batch,
+                   int T, int L, float eps) {
+    constexpr int N = NJ * 32;
+    extern __shared__ float s_w[];  // [16][N] transposed filter bank
+    for (int i = threadIdx.x; i < 16 * N; i += blockDim.x) {
+        const int n = i / 16, k = i % 16;
+        s_w[k * N + n] = w_enc[i];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    const size_t tokens = size_t(batch) * L;
+    const size_t plane_stride = tokens * N;
+    float g[NJ], bt[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+        g[j] = gamma[lane + 32 * j];
+        bt[j] = beta[lane + 32 * j];
+    }
+    for (size_t tok = size_t(blockIdx.x) * warps_per_block + (threadIdx.x >> 5); tok < tokens;
+         tok += size_t(gridDim.x) * warps_per_block) {
+        const int b = int(tok / L), l = int(tok % L);
+        const float4* xp = reinterpret_cast<const float4*>(mix + size_t(b) * T + size_t(l) * 8);
+        float x[16];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 f = __ldg(xp + q);
+            x[4 * q] = f.x;
+            x[4 * q + 1] = f.y;
+            x[4 * q + 2] = f.z;
+            x[4 * q + 3] = f.w;
+        }
+        float v[NJ];
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            float acc = 0.f;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) acc = fmaf(s_w[k * N + lane + 32 * j], x[k], acc);
+            v[j] = fmaxf(acc, 0.f);
+            s += v[j];
+        }
+        const float mean = warp_sum(s) * (1.0f / N);
+        float sq = 0.f;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            const float d = v[j] - mean;
+            sq = fmaf(d, d, sq);
+        }
+        const float rstd = rsqrtf(warp_sum(sq) * (1.0f / N) + eps);
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            const size_t off = tok * N + lane + 32 * j;
+            mix_w[off] = v[j];
+            store_planes1<P>(yn, plane_stride, off, fmaf(g[j] * (v[j] - mean), rstd, bt[j]));
+        }
+    }
+}
+
+// ChannelwiseLayerNorm alone (stand-alone MaskNet module on an external mix_w).  One warp per token.
+template <int P, int NJ>
+__global__ void __launch_bounds__(256)
+cln_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+           __nv_bfloat16* __restrict__ yn, int M, float eps) {
+    constexpr int N = NJ * 32;
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    const size_t plane_stride = size_t(M) * N;
+    for (int tok = blockIdx.x * warps_per_block + (threadIdx.x >> 5); tok < M; tok += gridDim.x * warps_per_block) {
+        float v[NJ];
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            v[j] = x[size_t(tok) * N + lane + 32 * j];
+            s += v[j];
+        }
+        const float mean = warp_sum(s) * (1.0f / N);
+        float sq = 0.f;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            const float d = v[j] - mean;
+            sq = fmaf(d, d, sq);
+        }
+        const float rstd = rsqrtf(warp_sum(sq) * (1.0f / N) + eps);
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            const int n = lane + 32 * j;
+            store_planes1<P>(yn, plane_stride, size_t(tok) * N + n, fmaf(gamma[n] * (v[j] - mean), rstd, beta[n]));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Residual add + RMSNorm -> bf16 planes.  One warp per token, 128-bit accesses.
+// Reference: Block.forward Mamba-TasNet/modules/mamba/bimamba.py:446-447; final add + norm_f
+// modules/mamba_blocks.py:196-197; RMSNorm math = mamba-ssm rms_norm_ref (fp32, eps 1e-5).
+// ------------------------------------------------------------------------------------------------
+template <int P, int NV, bool VEC>  // VEC: NV float4 per lane (D = 128*NV); else NV floats per lane (D = 32*NV)
+__global__ void __launch_bounds__(256)
+add_rmsnorm_kernel(const float* __restrict__ h, float* __restrict__ res, int res_valid, const float* __restrict__ g,
+                   __nv_bfloat16* __restrict__ xn, int M, float eps) {
+    constexpr int D = VEC ? 128 * NV : 32 * NV;
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    const size_t plane_stride = size_t(M) * D;
+    for (int tok = blockIdx.x * warps_per_block + (threadIdx.x >> 5); tok < M; tok += gridDim.x * warps_per_block) {
+        const size_t base = size_t(tok) * D;
+        if (VEC) {
+            float4 r[NV];
+            float sq = 0.f;
+#pragma unroll
+            for (int j = 0; j < NV; ++j) {
+                const size_t off = base + 128 * j + 4 * lane;
+                float4 a = h ? *reinterpret_cast<const float4*>(h + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (res_valid) {
+                    const float4 b = *reinterpret_cast<const float4*>(res + off);
+                    a.x += b.x;
+                    a.y += b.y;
+                    a.z += b.z;
+                    a.w += b.w;
+                }
+                r[j] = a;
+                sq += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
+            }
+            const float rstd = rsqrtf(warp_sum(sq) * (1.0f / D) + eps);
+#pragma unroll
+            for (int j = 0; j < NV; ++j) {
+                const size_t off = base + 128 * j + 4 * lane;
+                if (h) *reinterpret_cast<float4*>(res + off) = r[j];
+                const float4 gg = *reinterpret_cast<const float4*>(g + 128 * j + 4 * lane);
+                float4 o;
+                o.x = r[j].x * rstd * gg.x;
+                o.y = r[j].y * rstd * gg.y;
+                o.z = r[j].z * rstd * gg.z;
+                o.w = r[j].w * rstd * gg.w;
+                store_planes4<P>(xn, plane_stride, off, o);
+            }
+        } else {
+            float r[NV];
+            float sq = 0.f;
+#pragma unroll
+            for (int j = 0; j < NV; ++j) {
+                const size_t off = base + 32 * j + lane;
+                float a = h ? h[off] : 0.f;
+                if (res_valid) a += res[off];
+                r[j] = a;
+                sq = fmaf(a, a, sq);
+            }
+            const float rstd = rsqrtf(warp_sum(sq) * (1.0f / D) + eps);
+#pragma unroll
+            for (int j = 0; j < NV; ++j) {
+                const size_t off = base + 32 * j + lane;
+                if (h) res[off] = r[j];
+                store_planes1<P>(xn, plane_stride, off, r[j] * rstd * g[32 * j + lane]);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Depthwise causal conv (width 4) + bias + SiLU, forward AND time-reversed direction in one pass over xs.
+// Reference: causal_conv1d_cuda.causal_conv1d_fwd call, Mamba-TasNet/modules/mamba/selective_scan_interface.py:182;
+// the backward direction runs the same op on xz.flip(-1) (modules/mamba/bimamba.py:237), i.e. anti-causal taps.
+// Thread = 4 channels, walks TT consecutive frames with a 7-row register window.
+// ------------------------------------------------------------------------------------------------
+template <typename XT>
+__device__ __forceinline__ float4 load_x4(const XT* p);
+template <>
+__device__ __forceinline__ float4 load_x4<float>(const float* p) {
+    return *reinterpret_cast<const float4*>(p);
+}
+template <>
+__device__ __forceinline__ float4 load_x4<__nv_bfloat16>(const __nv_bfloat16* p) {
+    const uint2 raw = *reinterpret_cast<const uint2*>(p);
+    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&raw.x);
+    const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&raw.y);
+    const float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+    return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
+
+constexpr int CONV_TT = 32;
+
+template <int P, typename XT>
+__global__ void __launch_bounds__(256)
+conv_silu_kernel(const XT* __restrict__ xz, int ldxz, const float* __restrict__ conv_w, const float* __restrict__ conv_b,
+                 __nv_bfloat16* __restrict__ u, int batch, int L, int di) {
+    const int c = (blockIdx.z * blockDim.x + threadIdx.x) * 4;
+    if (c >= di) return;
+    const int b = blockIdx.y;
+    const int t0 = blockIdx.x * CONV_TT;
+    const int t1 = min(t0 + CONV_TT, L);
+    const size_t M = size_t(batch) * L;
+    const size_t plane_stride = M * 2 * di;
+    float4 wf[4], wb[4];  // wf[k] = tap k for channels c..c+3
+    {
+        float tf[4][4], tb[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float4 a = *reinterpret_cast<const float4*>(conv_w + size_t(c + i) * 4);
+            const float4 bq = *reinterpret_cast<const float4*>(conv_w + size_t(di + c + i) * 4);
+            tf[i][0] = a.x; tf[i][1] = a.y; tf[i][2] = a.z; tf[i][3] = a.w;
+            tb[i][0] = bq.x; tb[i][1] = bq.y; tb[i][2] = bq.z; tb[i][3] = bq.w;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            wf[k] = make_float4(tf[0][k], tf[1][k], tf[2][k], tf[3][k]);
+            wb[k] = make_float4(tb[0][k], tb[1][k], tb[2][k], tb[3][k]);
+        }
+    }
+    const float4 bf = *reinterpret_cast<const float4*>(conv_b + c);
+    const float4 bb = *reinterpret_cast<const float4*>(conv_b + di + c);
+    const XT* xbase = xz + size_t(b) * L * ldxz + c;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto ld = [&](int t) -> float4 { return (t >= 0 && t < L) ? load_x4<XT>(xbase + size_t(t) * ldxz) : zero; };
+    // window w[i] = x[t - 3 + i], i = 0..6
+    float4 w0 = ld(t0 - 3), w1 = ld(t0 - 2), w2 = ld(t0 - 1), w3 = ld(t0), w4 = ld(t0 + 1), w5 = ld(t0 + 2), w6;
+    for (int t = t0; t < t1; t += 4) {
+        float4 nx[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) nx[i] = ld(t + 3 + i);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            w6 = nx[i];
+            if (t + i < t1) {
+                float4 f, r;
+                f.x = fmaf(wf[0].x, w0.x, fmaf(wf[1].x, w1.x, fmaf(wf[2].x, w2.x, fmaf(wf[3].x, w3.x, bf.x))));
+                f.y = fmaf(wf[0].y, w0.y, fmaf(wf[1].y, w1.y, fmaf(wf[2].y, w2.y, fmaf(wf[3].y, w3.y, bf.y))));
+                f.z = fmaf(wf[0].z, w0.z, fmaf(wf[1].z, w1.z, fmaf(wf[2].z, w2.z, fmaf(wf[3].z, w3.z, bf.z))));
+                f.w = fmaf(wf[0].w, w0.w, fmaf(wf[1].w, w1.w, fmaf(wf[2].w, w2.w, fmaf(wf[3].w, w3.w, bf.w))));
+                // time-reversed direction: tap k multiplies x[t + 3 - k]
+                r.x = fmaf(wb[0].x, w6.x, fmaf(wb[1].x, w5.x, fmaf(wb[2].x, w4.x, fmaf(wb[3].x, w3.x, bb.x))));
+                r.y = fmaf(wb[0].y, w6.y, fmaf(wb[1].y, w5.y, fmaf(wb[2].y, w4.y, fmaf(wb[3].y, w3.y, bb.y))));
+                r.z = fmaf(wb[0].z, w6.z, fmaf(wb[1].z, w5.z, fmaf(wb[2].z, w4.z, fmaf(wb[3].z, w3.z, bb.z))));
+                r.w = fmaf(wb[0].w, w6.w, fmaf(wb[1].w, w5.w, fmaf(wb[2].w, w4.w, fmaf(wb[3].w, w3.w, bb.w))));
+                f = make_float4(silu_f(f.x), silu_f(f.y), silu_f(f.z), silu_f(f.w));
+                r = make_float4(silu_f(r.x), silu_f(r.y), silu_f(r.z), silu_f(r.w));
+                const size_t off = (size_t(b) * L + (t + i)) * (2 * di) + c;
+                store_planes4<P>(u, plane_stride, off, f);
+                store_planes4<P>(u, plane_stride, off + di, r);
+            }
+            w0 = w1; w1 = w2; w2 = w3; w3 = w4; w4 = w5; w5 = w6;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Decoder: ConvTranspose1d(N -> 1, k=16, s=8, no bias) per speaker = frame GEMV + overlap-add.
+// Reference: speechbrain dual_path.Decoder == baseline/avse2/model.py:27-37; speaker loop, cat and
+// pad/trim Mamba-TasNet/train_wsj0mix.py:95-109.
+// ------------------------------------------------------------------------------------------------
+constexpr int DEC_WLD = 20;  // padded filter row (16 taps + 4): conflict-free float4 reads
+
+template <int NJ>
+__global__ void __launch_bounds__(256)
+decoder_frames_kernel(const float* __restrict__ sep, const float* __restrict__ w_dec, float* __restrict__ frames,
+                      size_t items) {
+    constexpr int N = NJ * 32;
+    extern __shared__ float s_w[];  // [N][DEC_WLD]
+    for (int i = threadIdx.x; i < N * 16; i += blockDim.x) s_w[(i / 16) * DEC_WLD + (i % 16)] = w_dec[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    // one warp per (token, speaker)
+    for (size_t item = size_t(blockIdx.x) * warps_per_block + (threadIdx.x >> 5); item < items;
+         item += size_t(gridDim.x) * warps_per_block) {
+        const float* row = sep + item * N;  // sep[token][s*N + n] -> contiguous in (token, s)
+        float acc[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) acc[k] = 0.f;
+#pragma unroll 2
+        for (int j = 0; j < NJ; ++j) {
+            const int n = lane + 32 * j;
+            const float v = row[n];
+            const float4* wp = reinterpret_cast<const float4*>(&s_w[n * DEC_WLD]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 w = wp[q];
+                acc[4 * q] = fmaf(v, w.x, acc[4 * q]);
+                acc[4 * q + 1] = fmaf(v, w.y, acc[4 * q + 1]);
+                acc[4 * q + 2] = fmaf(v, w.z, acc[4 * q + 2]);
+                acc[4 * q + 3] = fmaf(v, w.w, acc[4 * q + 3]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) acc[k] = warp_sum(acc[k]);
+        if (lane < 16) {
+            float mine = 0.f;
+#pragma unroll
+            for (int k = 0; k < 16; ++k)
+                if (lane == k) mine = acc[k];
+            frames[item * 16 + lane] = mine;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+decoder_ola_kernel(const float* __restrict__ frames, float* __restrict__ est, int batch, int T, int L, int S) {
+    const size_t total = size_t(batch) * T * S;
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+        const int s = int(i % S);
+        const size_t bt = i / S;
+        const int t = int(bt % T);
+        const int b = int(bt / T);
+        const int l1 = t >> 3, k = t & 7;
+        float v = 0.f;
+        if (l1 < L) v += frames[((size_t(b) * L + l1) * S + s) * 16 + k];
+        if (l1 >= 1 && l1 - 1 < L) v += frames[((size_t(b) * L + l1 - 1) * S + s) * 16 + 8 + k];
+        est[i] = v;
+    }
+}
+
+template <int P>
+__global__ void __launch_bounds__(256)
+split_planes_kernel(const float* __restrict__ src, int ld, __nv_bfloat16* __restrict__ dst, int rows, int cols) {
+    const size_t total = size_t(rows) * cols;
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+        const size_t r = i / cols, c = i % cols;
+        store_planes1<P>(dst, total, i, src[r * ld + c]);
+    }
+}
+
+static int grid_for(size_t items, int per_block, int waves = 8) {
+    size_t need = (items + per_block - 1) / per_block;
+    size_t cap = size_t(num_sms()) * waves;
+    size_t g = need < cap ? need : cap;
+    return g < 1 ? 1 : int(g);
+}
+
+}  // namespace mtn
+
+using namespace mtn;
+
+extern "C" int mtn_encoder_cln_fwd(const float* mix, const float* w_enc, const float* gamma, const float* beta,
+                                   float* mix_w, void* yn_planes, int batch, int T, int L, int N, int planes, float eps,
+                                   mtn_stream_t stream) {
+    MTN_REQUIRE(mix && w_enc && gamma && beta && mix_w && yn_planes, "encoder: null pointer");
+    MTN_REQUIRE(batch > 0 && T >= 16 && L == (T - 16) / 8 + 1, "encoder: bad shape batch=%d T=%d L=%d", batch, T, L);
+    MTN_REQUIRE(T % 4 == 0 && (reinterpret_cast<uintptr_t>(mix) & 15) == 0,
+                "encoder: T must be a multiple of 4 and mix 16-byte aligned (128-bit frame loads)");
+    MTN_REQUIRE(planes == 1 || planes == 2, "encoder: planes=%d", planes);
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const size_t tokens = size_t(batch) * L;
+    const int grid = grid_for(tokens, 8, 4);
+    const size_t smem = size_t(16) * N * sizeof(float);
+#define MTN_ENC(PP, NJ)                                                                                          \
+    do {                                                                                                         \
+        auto k = encoder_cln_kernel<PP, NJ>;                                                                     \
+        if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+        k<<<grid, 256, smem, s>>>(mix, w_enc, gamma, beta, mix_w, reinterpret_cast<__nv_bfloat16*>(yn_planes),  \
+                                  batch, T, L, eps);                                                             \
+    } while (0)
+#define MTN_ENC_N(PP)                                                         \
+    switch (N) {                                                              \
+        case 64: MTN_ENC(PP, 2); break;                                       \
+        case 128: MTN_ENC(PP, 4); break;                                      \
+        case 256: MTN_ENC(PP, 8); break;                                      \
+        case 512: MTN_ENC(PP, 16); break;                                     \
+        default: set_error("encoder: unsupported N=%d", N); return MTN_EINVAL; \
+    }
+    if (planes == 2) { MTN_ENC_N(2) } else { MTN_ENC_N(1) }
+#undef MTN_ENC_N
+#undef MTN_ENC
+    MTN_CUDA_LAUNCH_CHECK("encoder_cln");
+    return MTN_OK;
+}
+
+extern "C" int mtn_cln_fwd(const float* x, const float* gamma, const float* beta, void* yn_planes, int M, int N,
+                           int planes, float eps, mtn_stream_t stream) {
+    MTN_REQUIRE(x && gamma && beta && yn_planes && M > 0, "cln: bad arguments");
+    MTN_REQUIRE(planes == 1 || planes == 2, "cln: planes=%d", planes);
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const int grid = grid_for(size_t(M), 8, 8);
+    __nv_bfloat16* yn = reinterpret_cast<__nv_bfloat16*>(yn_planes);
+#define MTN_CLN(PP, NJ) cln_kernel<PP, NJ><<<grid, 256, 0, s>>>(x, gamma, beta, yn, M, eps)
+#define MTN_CLN_N(PP)                                                     \
+    switch (N) {                                                          \
+        case 64: MTN_CLN(PP, 2); break;                                   \
+        case 128: MTN_CLN(PP, 4); break;                                  \
+        case 256: MTN_CLN(PP, 8); break;                                  \
+        case 512: MTN_CLN(PP, 16); break;                                 \
+        default: set_error("cln: unsupported N=%d", N); return MTN_EINVAL; \
+    }
+    if (planes == 2) { MTN_CLN_N(2) } else { MTN_CLN_N(1) }
+#undef MTN_CLN_N
+#undef MTN_CLN
+    MTN_CUDA_LAUNCH_CHECK("cln");
+    return MTN_OK;
+}
+
+extern "C" int mtn_add_rmsnorm_fwd(const float* h, float* res, int res_valid, const float* g, void* xn_planes, int M,
+                                   int D, int planes, float eps, mtn_stream_t stream) {
+    MTN_REQUIRE(res && g && xn_planes, "add_rmsnorm: null pointer");
+    MTN_REQUIRE(h || res_valid, "add_rmsnorm: need h or a valid residual");
+    MTN_REQUIRE(M > 0 && planes >= 1 && planes <= 2, "add_rmsnorm: bad M=%d planes=%d", M, planes);
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const int grid = grid_for(size_t(M), 8, 8);
+    __nv_bfloat16* xn = reinterpret_cast<__nv_bfloat16*>(xn_planes);
+#define MTN_RMS(PP, NV, VEC) add_rmsnorm_kernel<PP, NV, VEC><<<grid, 256, 0, s>>>(h, res, res_valid, g, xn, M, eps)
+#define MTN_RMS_D(PP)                                                             \
+    switch (D) {                                                                  \
+        case 64: MTN_RMS(PP, 2, false); break;                                    \
+        case 128: MTN_RMS(PP, 1, true); break;                                    \
+        case 256: MTN_RMS(PP, 2, true); break;                                    \
+        case 512: MTN_RMS(PP, 4, true); break;                                    \
+        default: set_error("add_rmsnorm: unsupported D=%d", D); return MTN_EINVAL; \
+    }
+    if (planes == 2) { MTN_RMS_D(2) } else { MTN_RMS_D(1) }
+#undef MTN_RMS_D
+#undef MTN_RMS
+    MTN_CUDA_LAUNCH_CHECK("add_rmsnorm");
+    return MTN_OK;
+}
+
+extern "C" int mtn_conv_silu_fwd(const void* xz, int ldxz, int xz_bf16, const float* conv_w, const float* conv_b,
+                                 void* u_planes, int batch, int L, int di, int planes, mtn_stream_t stream) {
+    MTN_REQUIRE(xz && conv_w && conv_b && u_planes, "conv_silu: null pointer");
+    MTN_REQUIRE(batch > 0 && L > 0 && di > 0 && di % 4 == 0 && ldxz % 4 == 0, "conv_silu: bad shape");
+    MTN_REQUIRE(planes == 1 || planes == 2, "conv_silu: planes=%d", planes);
+    MTN_REQUIRE(batch <= 65535, "conv_silu: batch too large for grid.y");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const int threads_needed = di / 4;
+    const int block = threads_needed >= 256 ? 256 : ((threads_needed + 31) / 32) * 32;
+    dim3 grid((L + CONV_TT - 1) / CONV_TT, batch, (threads_needed + block - 1) / block);
+    __nv_bfloat16* u = reinterpret_cast<__nv_bfloat16*>(u_planes);
+    if (xz_bf16) {
+        const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(xz);
+        if (planes == 2) conv_silu_kernel<2, __nv_bfloat16><<<grid, block, 0, s>>>(x, ldxz, conv_w, conv_b, u, batch, L, di);
+        else conv_silu_kernel<1, __nv_bfloat16><<<grid, block, 0, s>>>(x, ldxz, conv_w, conv_b, u, batch, L, di);
+    } else {
+        const float* x = reinterpret_cast<const float*>(xz);
+        if (planes == 2) conv_silu_kernel<2, float><<<grid, block, 0, s>>>(x, ldxz, conv_w, conv_b, u, batch, L, di);
+        else conv_silu_kernel<1, float><<<grid, block, 0, s>>>(x, ldxz, conv_w, conv_b, u, batch, L, di);
+    }
+    MTN_CUDA_LAUNCH_CHECK("conv_silu");
+    return MTN_OK;
+}
+
+extern "C" int mtn_decoder_fwd(const float* sep, const float* w_dec, float* frames, float* est, int batch, int T, int L,
+                               int N, int n_spk, mtn_stream_t stream) {
+    MTN_REQUIRE(sep && w_dec && frames && est, "decoder: null pointer");
+    MTN_REQUIRE(batch > 0 && T > 0 && L > 0 && n_spk >= 1, "decoder: bad shape");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const size_t tokens = size_t(batch) * L;
+    const int grid = grid_for(tokens * n_spk, 8, 4);
+    const size_t smem = size_t(N) * DEC_WLD * sizeof(float);
+#define MTN_DEC(NJ)                                                                                            \
+    do {                                                                                                       \
+        auto k = decoder_frames_kernel<NJ>;                                                                    \
+        if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        k<<<grid, 256, smem, s>>>(sep, w_dec, frames, tokens * n_spk);                                                \
+    } while (0)
+    switch (N) {
+        case 64: MTN_DEC(2); break;
+        case 128: MTN_DEC(4); break;
+        case 256: MTN_DEC(8); break;
+        case 512: MTN_DEC(16); break;
+        default: set_error("decoder: unsupported N=%d", N); return MTN_EINVAL;
+    }
+#undef MTN_DEC
+    MTN_CUDA_LAUNCH_CHECK("decoder_frames");
+    decoder_ola_kernel<<<grid_for(size_t(batch) * T * n_spk, 256, 8), 256, 0, s>>>(frames, est, batch, T, L, n_spk);
+    MTN_CUDA_LAUNCH_CHECK("decoder_ola");
+    return MTN_OK;
+}
+
+extern "C" int mtn_split_planes(const float* src, int ld, void* dst_planes, int rows, int cols, int planes,
+                                mtn_stream_t stream) {
+    MTN_REQUIRE(src && dst_planes && rows > 0 && cols > 0 && ld >= cols, "split_planes: bad arguments");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const int grid = grid_for(size_t(rows) * cols, 256, 8);
+    __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(dst_planes);
+    if (planes == 2) split_planes_kernel<2><<<grid, 256, 0, s>>>(src, ld, d, rows, cols);
+    else if (planes == 1) split_planes_kernel<1><<<grid, 256, 0, s>>>(src, ld, d, rows, cols);
+    else { set_error("split_planes: planes=%d", planes); return MTN_EINVAL; }
+    MTN_CUDA_LAUNCH_CHECK("split_planes");
+    return MTN_OK;
+}

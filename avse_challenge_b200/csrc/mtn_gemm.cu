@@ -1,0 +1,369 @@
+// Dense contractions of the Mamba-TasNet path on tcgen05 tensor cores (sm_100a).
+//
+//   out[M, N] = epilogue( A[M, K] * W[N, K]^T )        (x groups)
+//
+// Replaces cuBLAS/cuDNN calls of the reference: in_proj (modules/mamba/bimamba.py:192-196), x_proj
+// (modules/mamba/selective_scan_interface.py:186), out_proj (bimamba.py:253), bottleneck / mask 1x1 convs
+// (modules/mamba_masknet.py:121,123).
+//
+// Design (B200-first, not a cuBLAS wrapper):
+//  * A and W live in HBM as bf16 "planes".  P = 2 is the fp32-accurate mode: value = hi + lo and the kernel issues
+//    three tcgen05.mma per K-step (hi*hi + lo*hi + hi*lo) into one fp32 TMEM accumulator -- ~2^-17 operand
+//    precision at the HBM traffic of plain fp32, with no in-kernel conversion pass.  P = 1 is bf16 mode.
+//  * Persistent, warp-specialised CTA (one per SM): warp 0 = TMA producer (128B-swizzled boxes straight into the
+//    UMMA canonical K-major layout), warp 1 = single-thread tcgen05.mma issuer, warps 2-5 = epilogue.  Two TMEM
+//    accumulators so the epilogue of tile i overlaps the MMAs of tile i+1.
+//  * These GEMMs are HBM-bound (K <= 1024, output-write dominated), so the epilogue is the part that matters:
+//    TMEM -> registers -> per-warp padded smem transpose -> fully coalesced 128-bit global stores, with the
+//    SiLU(z) gate / relu(mask)*mix_w fused in.
+#include "mtn_ptx.cuh"
+#include "mtn_host.h"
+
+namespace mtn {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
+constexpr int STG_LD = 36;  // floats per staging row (32 + 4 pad: conflict-free 128-bit accesses)
+
+struct GemmParams {
+    void* out;
+    const float* aux;
+    int M, N, K;
+    int ldo, ld_aux;
+    int groups, out_group_stride;
+    int epi_param;
+    int tiles_m, tiles_n;
+};
+
+template <int P, int BN>
+struct GemmCfg {
+    static constexpr int A_BYTES = BM * BK * 2;
+    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = P * (A_BYTES + B_BYTES);
+    static constexpr int STAGING_BYTES = 4 * 32 * STG_LD * 4;
+    static constexpr int BAR_BYTES = 256;
+    static constexpr int BUDGET = 227 * 1024 - 1024 - STAGING_BYTES - BAR_BYTES;
+    static constexpr int STAGES_RAW = BUDGET / STAGE_BYTES;
+    static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
+    static constexpr int ACC_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+    static constexpr int TMEM_COLS = 2 * ACC_COLS;
+    static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + STAGING_BYTES + BAR_BYTES;
+    static_assert(STAGES >= 2, "need at least a double-buffered operand pipeline");
+    static_assert(B_BYTES % 1024 == 0, "B tile must keep 1024B alignment for SWIZZLE_128B");
+};
+
+template <int P, int BN, int EPI, bool OUT_BF16>
+__global__ void __launch_bounds__(192, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                    const GemmParams p) {
+    using Cfg = GemmCfg<P, BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    float* staging = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::STAGING_BYTES);
+    uint64_t* empty_bar = full_bar + Cfg::STAGES;
+    uint64_t* tfull_bar = empty_bar + Cfg::STAGES;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&mapA);
+        tma_prefetch_desc(&mapB);
+        for (int s = 0; s < Cfg::STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tfull_bar[a], 1);
+            mbar_init(&tempty_bar[a], 4);  // one arrive per epilogue warp
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int kblocks = p.K / BK;
+    const int tiles_per_group = p.tiles_m * p.tiles_n;
+    const int total_tiles = tiles_per_group * p.groups;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer (one thread)
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int g = tile / tiles_per_group;
+                const int r = tile - g * tiles_per_group;
+                const int mt = r / p.tiles_n;
+                const int nt = r - mt * p.tiles_n;
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                    uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+                    uint8_t* sb = sa + P * Cfg::A_BYTES;
+#pragma unroll
+                    for (int pl = 0; pl < P; ++pl) {
+                        tma_load_3d(sa + pl * Cfg::A_BYTES, &mapA, &full_bar[stage], g * p.K + kb * BK, mt * BM, pl);
+                        tma_load_3d(sb + pl * Cfg::B_BYTES, &mapB, &full_bar[stage], kb * BK, g * p.N + nt * BN, pl);
+                    }
+                    if (++stage == Cfg::STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer (one thread)
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_COLS;
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                    const uint32_t sb = sa + P * Cfg::A_BYTES;
+#pragma unroll
+                    for (int kk = 0; kk < BK / 16; ++kk) {
+                        const uint64_t a_hi = make_smem_desc_sw128(sa + kk * 32);
+                        const uint64_t b_hi = make_smem_desc_sw128(sb + kk * 32);
+                        tc_mma_bf16(d_tmem, a_hi, b_hi, idesc, (kb | kk) != 0 ? 1u : 0u);
+                        if (P == 2) {
+                            const uint64_t a_lo = make_smem_desc_sw128(sa + Cfg::A_BYTES + kk * 32);
+                            const uint64_t b_lo = make_smem_desc_sw128(sb + Cfg::B_BYTES + kk * 32);
+                            tc_mma_bf16(d_tmem, a_lo, b_hi, idesc, 1u);
+                            tc_mma_bf16(d_tmem, a_hi, b_lo, idesc, 1u);
+                        }
+                    }
+                    tc_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+                    if (++stage == Cfg::STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                tc_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+            }
+        }
+        __syncwarp();
+    } else {
+        // ------------------------------------------------------------ epilogue warps (2..5)
+        const int q = warp & 3;  // TMEM lane quarter this warp may read
+        float* stg = staging + (warp - 2) * 32 * STG_LD;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int g = tile / tiles_per_group;
+            const int r = tile - g * tiles_per_group;
+            const int mt = r / p.tiles_n;
+            const int nt = r - mt * p.tiles_n;
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t t_base = tmem_base + acc * Cfg::ACC_COLS + (uint32_t(q * 32) << 16);
+            const int row0 = mt * BM + q * 32;
+#pragma unroll
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                constexpr int dummy = 0;
+                (void)dummy;
+                const int width = (BN - c0) >= 32 ? 32 : 16;
+                uint32_t v[32];
+                {
+                    uint32_t(&v0)[16] = *reinterpret_cast<uint32_t(*)[16]>(&v[0]);
+                    tmem_ld_x16(t_base + c0, v0);
+                    if (width == 32) {
+                        uint32_t(&v1)[16] = *reinterpret_cast<uint32_t(*)[16]>(&v[16]);
+                        tmem_ld_x16(t_base + c0 + 16, v1);
+                    }
+                }
+                tmem_ld_wait();
+                if (c0 + 32 >= BN) {
+                    // last TMEM read of this accumulator: hand it back to the MMA warp early
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                }
+                // registers (thread = row) -> padded smem
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (j * 4 < width) {
+                        float4 f = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                               __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                        *reinterpret_cast<float4*>(&stg[lane * STG_LD + 4 * j]) = f;
+                    }
+                }
+                __syncwarp();
+                // smem -> global, row-contiguous: (width/4) lanes cover one row segment
+                const int lanes_per_row = width / 4;           // 8 or 4
+                const int rows_per_it = 32 / lanes_per_row;    // 4 or 8
+                const int rsub = lane / lanes_per_row;
+                const int c4 = lane % lanes_per_row;
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    if (it * rows_per_it < 32) {
+                        const int rr = it * rows_per_it + rsub;
+                        const int grow = row0 + rr;
+                        const int gcol = nt * BN + c0 + c4 * 4;  // column within the group's N
+                        float4 f = *reinterpret_cast<const float4*>(&stg[rr * STG_LD + c4 * 4]);
+                        if (grow < p.M) {
+                            if (EPI == MTN_EPI_INPROJ) {
+                                if (gcol >= p.epi_param) {
+                                    f.x = silu_f(f.x);
+                                    f.y = silu_f(f.y);
+                                    f.z = silu_f(f.z);
+                                    f.w = silu_f(f.w);
+                                }
+                            } else if (EPI == MTN_EPI_RELU) {
+                                f.x = fmaxf(f.x, 0.f);
+                                f.y = fmaxf(f.y, 0.f);
+                                f.z = fmaxf(f.z, 0.f);
+                                f.w = fmaxf(f.w, 0.f);
+                            } else if (EPI == MTN_EPI_MASK) {
+                                const float4 a = *reinterpret_cast<const float4*>(
+                                    p.aux + size_t(grow) * p.ld_aux + (gcol % p.epi_param));
+                                f.x = fmaxf(f.x, 0.f) * a.x;
+                                f.y = fmaxf(f.y, 0.f) * a.y;
+                                f.z = fmaxf(f.z, 0.f) * a.z;
+                                f.w = fmaxf(f.w, 0.f) * a.w;
+                            }
+                            const size_t off = size_t(grow) * p.ldo + size_t(g) * p.out_group_stride + gcol;
+                            if (OUT_BF16) {
+                                __nv_bfloat162 lo2 = __floats2bfloat162_rn(f.x, f.y);
+                                __nv_bfloat162 hi2 = __floats2bfloat162_rn(f.z, f.w);
+                                uint2 pk;
+                                pk.x = *reinterpret_cast<uint32_t*>(&lo2);
+                                pk.y = *reinterpret_cast<uint32_t*>(&hi2);
+                                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off) = pk;
+                            } else {
+                                *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off) = f;
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+template <int P, int BN, int EPI, bool OUT_BF16>
+static int launch_gemm(const mtn_gemm_args* a, cudaStream_t stream) {
+    using Cfg = GemmCfg<P, BN>;
+    CUtensorMap mapA, mapB;
+    {
+        uint64_t dims[3] = {(uint64_t)a->lda, (uint64_t)a->a_rows, (uint64_t)P};
+        uint64_t str[2] = {(uint64_t)a->lda * 2, (uint64_t)a->a_rows * a->lda * 2};
+        uint32_t box[3] = {BK, BM, 1};
+        if (!encode_tmap(&mapA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, a->a, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B))
+            return MTN_ECUDA;
+    }
+    {
+        uint64_t rows = (uint64_t)a->groups * a->N;
+        uint64_t dims[3] = {(uint64_t)a->K, rows, (uint64_t)P};
+        uint64_t str[2] = {(uint64_t)a->K * 2, rows * a->K * 2};
+        uint32_t box[3] = {BK, BN, 1};
+        if (!encode_tmap(&mapB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, a->w, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B))
+            return MTN_ECUDA;
+    }
+    GemmParams p;
+    p.out = a->out;
+    p.aux = reinterpret_cast<const float*>(a->aux);
+    p.M = a->M;
+    p.N = a->N;
+    p.K = a->K;
+    p.ldo = a->ldo;
+    p.ld_aux = a->ld_aux;
+    p.groups = a->groups;
+    p.out_group_stride = a->out_group_stride;
+    p.epi_param = a->epi_param;
+    p.tiles_m = (a->M + BM - 1) / BM;
+    p.tiles_n = a->N / BN;
+    auto kern = gemm_tcgen05_kernel<P, BN, EPI, OUT_BF16>;
+    static bool attr_set = false;  // per template instantiation
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        if (e != cudaSuccess) {
+            set_error("gemm: cudaFuncSetAttribute(%d B smem) failed: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
+            return MTN_ECUDA;
+        }
+        attr_set = true;
+    }
+    int total = p.tiles_m * p.tiles_n * p.groups;
+    int cap = a->max_ctas > 0 ? a->max_ctas : num_sms();
+    int grid = total < cap ? total : cap;
+    kern<<<grid, 192, Cfg::SMEM_BYTES, stream>>>(mapA, mapB, p);
+    MTN_CUDA_LAUNCH_CHECK("gemm");
+    return MTN_OK;
+}
+
+template <int P, int BN>
+static int dispatch_epi(const mtn_gemm_args* a, cudaStream_t s) {
+    if (a->epilogue == MTN_EPI_STORE && !a->out_bf16) return launch_gemm<P, BN, MTN_EPI_STORE, false>(a, s);
+    if (BN >= 128) {
+        if (a->epilogue == MTN_EPI_INPROJ && !a->out_bf16) return launch_gemm<P, BN, MTN_EPI_INPROJ, false>(a, s);
+        if (a->epilogue == MTN_EPI_INPROJ && a->out_bf16) return launch_gemm<P, BN, MTN_EPI_INPROJ, true>(a, s);
+        if (a->epilogue == MTN_EPI_MASK && !a->out_bf16) return launch_gemm<P, BN, MTN_EPI_MASK, false>(a, s);
+        if (a->epilogue == MTN_EPI_RELU && !a->out_bf16) return launch_gemm<P, BN, MTN_EPI_RELU, false>(a, s);
+    }
+    set_error("gemm: unsupported epilogue %d / out_bf16 %d for N tile %d", a->epilogue, a->out_bf16, BN);
+    return MTN_EINVAL;
+}
+
+template <int P>
+static int dispatch_bn(const mtn_gemm_args* a, cudaStream_t s) {
+    const int N = a->N;
+    if (N % 256 == 0) return dispatch_epi<P, 256>(a, s);
+    if (N % 128 == 0) return dispatch_epi<P, 128>(a, s);
+    if (N == 64) return dispatch_epi<P, 64>(a, s);
+    if (N == 48) return dispatch_epi<P, 48>(a, s);
+    set_error("gemm: unsupported N=%d (need 48, 64 or a multiple of 128)", N);
+    return MTN_EINVAL;
+}
+
+}  // namespace mtn
+
+extern "C" int mtn_gemm_fwd(const mtn_gemm_args* a, mtn_stream_t stream) {
+    using namespace mtn;
+    MTN_REQUIRE(a && a->a && a->w && a->out, "gemm: null pointer");
+    MTN_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0 && a->groups >= 1, "gemm: bad shape M=%d N=%d K=%d groups=%d", a->M,
+                a->N, a->K, a->groups);
+    MTN_REQUIRE(a->K % BK == 0, "gemm: K=%d must be a multiple of %d", a->K, BK);
+    MTN_REQUIRE(a->lda % 8 == 0 && a->lda >= a->groups * a->K, "gemm: lda=%d invalid", a->lda);
+    MTN_REQUIRE(a->a_rows >= a->M, "gemm: a_rows=%d < M=%d", a->a_rows, a->M);
+    MTN_REQUIRE(a->ldo % 4 == 0 && a->out_group_stride % 4 == 0, "gemm: ldo/out_group_stride must be multiples of 4");
+    MTN_REQUIRE((reinterpret_cast<uintptr_t>(a->a) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->w) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(a->out) & 15) == 0,
+                "gemm: pointers must be 16-byte aligned");
+    if (a->epilogue == MTN_EPI_MASK)
+        MTN_REQUIRE(a->aux && a->epi_param > 0 && a->epi_param % 4 == 0 && a->ld_aux % 4 == 0,
+                    "gemm: mask epilogue needs aux / enc_dim");
+    if (a->epilogue == MTN_EPI_INPROJ) MTN_REQUIRE(a->epi_param % 4 == 0, "gemm: inproj split must be a multiple of 4");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (a->planes == 2) return dispatch_bn<2>(a, s);
+    if (a->planes == 1) return dispatch_bn<1>(a, s);
+    set_error("gemm: planes=%d (must be 1 or 2)", a->planes);
+    return MTN_EINVAL;
+}

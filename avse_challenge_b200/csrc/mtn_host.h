@@ -1,0 +1,36 @@
+// Host-side helpers shared by the C-ABI translation units: error reporting, TMA descriptors.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/mtn_b200.h"
+
+namespace mtn {
+
+void set_error(const char* fmt, ...);
+int num_sms();
+
+// cuTensorMapEncodeTiled through the runtime's driver-entry-point query (no -lcuda link).
+// dims/strides innermost first; strides in BYTES for dims 1..rank-1.
+bool encode_tmap(CUtensorMap* map, CUtensorMapDataType dtype, int rank, const void* base, const uint64_t* dims,
+                 const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swizzle);
+
+#define MTN_REQUIRE(cond, ...)           \
+    do {                                 \
+        if (!(cond)) {                   \
+            mtn::set_error(__VA_ARGS__); \
+            return MTN_EINVAL;           \
+        }                                \
+    } while (0)
+
+#define MTN_CUDA_LAUNCH_CHECK(what)                                                \
+    do {                                                                           \
+        cudaError_t e__ = cudaGetLastError();                                      \
+        if (e__ != cudaSuccess) {                                                  \
+            mtn::set_error("%s: launch failed: %s", what, cudaGetErrorString(e__)); \
+            return MTN_ECUDA;                                                      \
+        }                                                                          \
+    } while (0)
+
+}  // namespace mtn

@@ -1,0 +1,192 @@
+"""Fused forward plan of the Mamba-TasNet separator on one B200.
+
+``SeparatorEngine`` owns (a) the weights repacked for the kernels (bf16 hi/lo planes, stacked
+per-direction tensors, ``A2 = -exp(A_log) * log2(e)``), (b) per-shape activation workspaces and
+(c) an optional whole-forward CUDA graph.  ``forward(mix)`` is the B200 replacement of
+``Separation.compute_forward`` (``Mamba-TasNet/train_wsj0mix.py:86-111``): ~5 kernels per Mamba layer,
+every activation channel-last, nothing executed by torch except buffer allocation.
+
+Per layer (reference call stack SURVEY.md 3.1):
+    add_rmsnorm   res += h ; xn = RMSNorm(res) * g              (bimamba.py:446-447)
+    gemm(in_proj) xz = xn @ W_in^T ; z-half stored as silu(z)   (bimamba.py:192-196, ssi.py:155)
+    conv_silu     u_f, u_b = silu(conv1d(xs)) both directions   (ssi.py:182, bimamba.py:237)
+    gemm(x_proj)  [dt|B|C]_f, [dt|B|C]_b (2 groups)             (ssi.py:186)
+    scan          dt_proj + softplus + recurrence + D-skip + gate, x0.5, both directions (ssi.py:187,218-220)
+    gemm(out_proj) h = [y_f | y_b] @ [W_out | W_out]^T          (bimamba.py:253)
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib, ops
+from .hparams import HParams
+from .ops import LOG2E, n_dbl_for
+
+MODES = {"fp32": dict(planes=2, xz_bf16=False), "bf16": dict(planes=1, xz_bf16=True)}
+
+
+class PackedWeights:
+    """Kernel-ready copies of the reference parameters (state_dict keys of SURVEY.md App. B)."""
+
+    def __init__(self, hp: HParams, sds: dict, device, mode: str):
+        P = MODES[mode]["planes"]
+        self.hp, self.mode, self.P = hp, mode, P
+        f32 = lambda t: t.detach().to(device=device, dtype=torch.float32).contiguous()
+        m = sds["masknet"]
+        N, D, di, R = hp.enc_dim, hp.d_model, hp.d_inner, hp.dt_rank
+        nd = n_dbl_for(R)
+        self.n_dbl = nd
+        self.w_enc = f32(sds["encoder"]["conv1d.weight"]).reshape(N, hp.kernel_size)
+        self.w_dec = f32(sds["decoder"]["weight"]).reshape(N, hp.kernel_size)
+        self.gamma = f32(m["layer_norm.gamma"]).reshape(N)
+        self.beta = f32(m["layer_norm.beta"]).reshape(N)
+        self.w_bot = ops.split_planes(f32(m["bottleneck_conv1x1.conv.weight"]).reshape(D, N), P)
+        self.w_mask = ops.split_planes(f32(m["mask_conv1x1.conv.weight"]).reshape(hp.n_spk * N, D), P)
+        self.norm_f = f32(m["mamba_net.norm_f.weight"])
+        self.layers = []
+        for i in range(hp.n_mamba):
+            p = f"mamba_net.layers.{i}."
+            lw = {}
+            lw["norm"] = f32(m[p + "norm.weight"])
+            lw["w_in"] = ops.split_planes(f32(m[p + "mixer.in_proj.weight"]), P)            # [P, 2di, D]
+            lw["conv_w"] = torch.stack([f32(m[p + "mixer.conv1d.weight"]).reshape(di, hp.d_conv),
+                                        f32(m[p + "mixer.conv1d_b.weight"]).reshape(di, hp.d_conv)]).contiguous()
+            lw["conv_b"] = torch.stack([f32(m[p + "mixer.conv1d.bias"]), f32(m[p + "mixer.conv1d_b.bias"])]).contiguous()
+            wx = torch.zeros((2 * nd, di), dtype=torch.float32, device=device)              # rows padded R+32 -> nd
+            wx[: R + 32] = f32(m[p + "mixer.x_proj.weight"])
+            wx[nd: nd + R + 32] = f32(m[p + "mixer.x_proj_b.weight"])
+            lw["w_x"] = ops.split_planes(wx, P)                                             # [P, 2*nd, di]
+            lw["w_dt"] = torch.stack([f32(m[p + "mixer.dt_proj.weight"]), f32(m[p + "mixer.dt_proj_b.weight"])]).contiguous()
+            lw["dt_bias"] = torch.stack([f32(m[p + "mixer.dt_proj.bias"]), f32(m[p + "mixer.dt_proj_b.bias"])]).contiguous()
+            A = torch.stack([-torch.exp(f32(m[p + "mixer.A_log"])), -torch.exp(f32(m[p + "mixer.A_b_log"]))])
+            lw["A2"] = (A * LOG2E).contiguous()                                             # [2, di, 16]
+            lw["D"] = torch.stack([f32(m[p + "mixer.D"]), f32(m[p + "mixer.D_b"])]).contiguous()
+            w_out = f32(m[p + "mixer.out_proj.weight"])                                     # [D, di]
+            lw["w_out"] = ops.split_planes(torch.cat([w_out, w_out], dim=1).contiguous(), P)  # [P, D, 2di]
+            self.layers.append(lw)
+
+
+class Workspace:
+    """Activation buffers for one (batch, T) shape; reused across layers and calls."""
+
+    def __init__(self, hp: HParams, batch: int, T: int, device, mode: str):
+        P = MODES[mode]["planes"]
+        xz_dt = torch.bfloat16 if MODES[mode]["xz_bf16"] else torch.float32
+        L = hp.frames(T)
+        M = batch * L
+        N, D, di = hp.enc_dim, hp.d_model, hp.d_inner
+        nd = n_dbl_for(hp.dt_rank)
+        e = lambda shape, dt: torch.empty(shape, dtype=dt, device=device)
+        self.batch, self.T, self.L, self.M = batch, T, L, M
+        self.mix = e((batch, T), torch.float32)
+        self.mix_w = e((M, N), torch.float32)
+        self.yn = e((P, M, N), torch.bfloat16)
+        self.h = e((M, D), torch.float32)
+        self.res = e((M, D), torch.float32)
+        self.xn = e((P, M, D), torch.bfloat16)
+        self.xz = e((M, 2 * di), xz_dt)
+        self.u = e((P, M, 2 * di), torch.bfloat16)
+        self.dbl = e((M, 2 * nd), torch.float32)
+        self.y = e((P, M, 2 * di), torch.bfloat16)
+        self.sep = e((M, hp.n_spk * N), torch.float32)
+        self.frames = e((M, hp.n_spk, 16), torch.float32)
+        self.est = e((batch, T, hp.n_spk), torch.float32)
+
+    def nbytes(self):
+        return sum(t.numel() * t.element_size() for t in vars(self).values() if isinstance(t, torch.Tensor))
+
+
+class SeparatorEngine:
+    """mix [B, T] fp32 (CUDA) -> est_source [B, T, n_spk] fp32, all in hand-written sm_100a kernels."""
+
+    def __init__(self, hp: HParams, sds: dict, device="cuda", mode: str = "fp32", use_graph: bool = True):
+        if mode not in MODES:
+            raise ValueError(f"mode must be one of {list(MODES)}")
+        if not torch.cuda.is_available():
+            raise _lib.MtnError("SeparatorEngine needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        _lib.load()
+        self.hp, self.mode, self.device = hp, mode, torch.device(device)
+        self.use_graph = use_graph
+        with torch.cuda.device(self.device):
+            self.w = PackedWeights(hp, sds, self.device, mode)
+        self._ws = {}
+        self._graphs = {}
+        self.launches_per_forward = 2 + 1 + hp.n_mamba * 6 + 2 + 2  # enc, bottleneck, layers, norm_f+mask, decoder(2)
+
+    # ------------------------------------------------------------------ building blocks
+    def workspace(self, batch, T) -> Workspace:
+        key = (batch, T)
+        if key not in self._ws:
+            self._ws[key] = Workspace(self.hp, batch, T, self.device, self.mode)
+        return self._ws[key]
+
+    def _layer(self, ws: Workspace, lw: dict, first: bool, taps=None):
+        hp, P = self.hp, self.w.P
+        D, di, R, nd, M = hp.d_model, hp.d_inner, hp.dt_rank, self.w.n_dbl, ws.M
+        ops.add_rmsnorm(ws.h, ws.res, not first, lw["norm"], P, xn=ws.xn)
+        ops.gemm(ws.xn, lw["w_in"], M, 2 * di, D, out=ws.xz, epilogue=_lib.EPI_INPROJ, epi_param=di,
+                 out_bf16=ws.xz.dtype == torch.bfloat16)
+        ops.conv_silu(ws.xz, lw["conv_w"], lw["conv_b"], ws.batch, ws.L, di, P, u=ws.u)
+        ops.gemm(ws.u, lw["w_x"], M, nd, di, out=ws.dbl, groups=2, out_group_stride=nd)
+        ops.scan(ws.u, ws.dbl, ws.xz, di, lw["w_dt"], lw["dt_bias"], lw["A2"], lw["D"], ws.batch, ws.L, di, R, y=ws.y)
+        ops.gemm(ws.y, lw["w_out"], M, D, 2 * di, out=ws.h)
+        if taps is not None:
+            taps.append(ws.h.clone())
+
+    def _run(self, ws: Workspace, taps=None):
+        hp, w, P = self.hp, self.w, self.w.P
+        N, D, M = hp.enc_dim, hp.d_model, ws.M
+        ops.encoder_cln(ws.mix, w.w_enc, w.gamma, w.beta, P, mix_w=ws.mix_w, yn=ws.yn)
+        ops.gemm(ws.yn, w.w_bot, M, D, N, out=ws.h)
+        for i, lw in enumerate(w.layers):
+            self._layer(ws, lw, first=(i == 0), taps=taps)
+        ops.add_rmsnorm(ws.h, ws.res, True, w.norm_f, P, xn=ws.xn)
+        ops.gemm(ws.xn, w.w_mask, M, hp.n_spk * N, D, out=ws.sep, epilogue=_lib.EPI_MASK, epi_param=N, aux=ws.mix_w)
+        ops.decoder(ws.sep, w.w_dec, ws.batch, ws.T, ws.L, N, hp.n_spk, est=ws.est, frames=ws.frames)
+        return ws.est
+
+    # ------------------------------------------------------------------ public API
+    @torch.no_grad()
+    def forward(self, mix: torch.Tensor, taps=None) -> torch.Tensor:
+        """``mix`` [B, T] fp32 on this engine's device.  Returns a fresh ``[B, T, n_spk]`` tensor."""
+        if mix.dim() != 2 or mix.dtype != torch.float32 or not mix.is_cuda:
+            raise _lib.MtnError("forward expects a CUDA fp32 tensor of shape [batch, T]")
+        B, T = mix.shape
+        if T % 8 != 0 or T < 16:
+            raise _lib.MtnError(f"T={T}: need T >= 16 and T % 8 == 0 (stride-8 framing with 128-bit loads)")
+        ws = self.workspace(B, T)
+        ws.mix.copy_(mix, non_blocking=True)
+        if taps is not None or not self.use_graph:
+            return self._run(ws, taps).clone()
+        key = (B, T)
+        g = self._graphs.get(key)
+        if g is None:
+            self._run(ws)  # eager warm-up: sets function attributes, validates shapes before capture
+            torch.cuda.current_stream().synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._run(ws)
+            self._graphs[key] = g
+        g.replay()
+        return ws.est.clone()
+
+    __call__ = forward
+
+    def forward_into_workspace(self, batch: int, T: int):
+        """Run (graph replay when enabled) on whatever is already in ``workspace(batch, T).mix``; returns the
+        workspace's ``est`` buffer without copying.  Used by the benchmark's device-resident timing."""
+        ws = self.workspace(batch, T)
+        key = (batch, T)
+        if self.use_graph:
+            g = self._graphs.get(key)
+            if g is None:
+                self._run(ws)
+                torch.cuda.current_stream().synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._run(ws)
+                self._graphs[key] = g
+            g.replay()
+        else:
+            self._run(ws)
+        return ws.est

@@ -1,0 +1,280 @@
+"""``nn.Module`` drop-ins for the reference's Mamba-TasNet modules, backed by the sm_100a kernels.
+
+Constructor signatures, parameter names/shapes (``state_dict`` keys) and call
+conventions mirror the reference, so its checkpoints load with ``strict=True`` and
+``Separation.compute_forward`` (``Mamba-TasNet/train_wsj0mix.py:86-111``) runs unchanged on them:
+
+    Encoder(kernel_size, out_channels)      speechbrain dual_path.Encoder (yaml mambatasnet_S.yaml:131-133)
+    MaskNet(enc_dim, bot_dim, ...)          modules/mamba_masknet.py:46-64
+    Decoder(in_channels, out_channels, kernel_size, stride, bias)   dual_path.Decoder (yaml :151-156)
+    MambaBlocksSequential / Block / Mamba   modules/mamba_blocks.py:108-123, modules/mamba/bimamba.py:410-412,40-61
+
+Inference only (``torch.no_grad``); options the kernels do not implement raise at construction --
+there is no silent fallback.  The fast path a user should call is ``MambaTasNetSeparator`` (one fused
+plan, CUDA graph); the stand-alone module ``forward``s exist for drop-in compatibility and use the same
+kernels with reference layouts ([B, N, L] in / out).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+
+from . import _lib, ops
+from .engine import SeparatorEngine
+from .hparams import HParams
+
+
+def _unsupported(what):
+    raise NotImplementedError(f"{what} is not implemented by the B200 kernels (no fallback path exists)")
+
+
+class RMSNorm(nn.Module):
+    """Parameter container for mamba-ssm's RMSNorm (``weight [D]``, no bias, eps 1e-5)."""
+
+    def __init__(self, hidden_size, eps=1e-5):
+        super().__init__()
+        self.eps = eps
+        self.weight = nn.Parameter(torch.ones(hidden_size))
+
+
+class ChannelwiseLayerNorm(nn.Module):
+    """Parameter container for speechbrain's cLN (``gamma``/``beta`` ``[1,1,N]``, eps 1e-8)."""
+
+    def __init__(self, channel_size):
+        super().__init__()
+        self.gamma = nn.Parameter(torch.ones(1, 1, channel_size))
+        self.beta = nn.Parameter(torch.zeros(1, 1, channel_size))
+
+
+class _SBConv1d(nn.Module):
+    """speechbrain ``nnet.CNN.Conv1d`` (k=1, no bias): parameter lives at ``conv.weight [out, in, 1]``."""
+
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.conv = nn.Conv1d(in_channels, out_channels, 1, bias=False)
+
+
+class Mamba(nn.Module):
+    """Bidirectional ("v2") Mamba mixer parameters (``modules/mamba/bimamba.py:40-174``)."""
+
+    def __init__(self, d_model, d_state=16, d_conv=4, expand=2, dt_rank="auto", conv_bias=True, bias=False,
+                 layer_idx=None, bimamba_type="v2", if_devide_out=True, init_layer_scale=None, **_ignored):
+        super().__init__()
+        if bimamba_type != "v2":
+            _unsupported(f"bimamba_type={bimamba_type!r}")
+        if d_state != 16 or d_conv != 4:
+            _unsupported(f"d_state={d_state}, d_conv={d_conv} (kernels are specialised for 16 / 4)")
+        if bias or not conv_bias or not if_devide_out or init_layer_scale is not None:
+            _unsupported("bias=True / conv_bias=False / if_devide_out=False / init_layer_scale")
+        self.d_model, self.d_state, self.d_conv, self.expand = d_model, d_state, d_conv, expand
+        self.d_inner = int(expand * d_model)
+        self.dt_rank = math.ceil(d_model / 16) if dt_rank == "auto" else dt_rank
+        self.layer_idx = layer_idx
+        di, R = self.d_inner, self.dt_rank
+        self.in_proj = nn.Linear(d_model, 2 * di, bias=False)
+        self.conv1d = nn.Conv1d(di, di, d_conv, groups=di, padding=d_conv - 1, bias=True)
+        self.x_proj = nn.Linear(di, R + 2 * d_state, bias=False)
+        self.dt_proj = nn.Linear(R, di, bias=True)
+        A_log = torch.log(torch.arange(1, d_state + 1, dtype=torch.float32)).repeat(di, 1)
+        self.A_log = nn.Parameter(A_log.clone())
+        self.D = nn.Parameter(torch.ones(di))
+        self.A_b_log = nn.Parameter(A_log.clone())
+        self.conv1d_b = nn.Conv1d(di, di, d_conv, groups=di, padding=d_conv - 1, bias=True)
+        self.x_proj_b = nn.Linear(di, R + 2 * d_state, bias=False)
+        self.dt_proj_b = nn.Linear(R, di, bias=True)
+        self.D_b = nn.Parameter(torch.ones(di))
+        self.out_proj = nn.Linear(di, d_model, bias=False)
+
+
+class Block(nn.Module):
+    """Add -> RMSNorm -> Mixer (``modules/mamba/bimamba.py:409-462``); parameters only."""
+
+    def __init__(self, dim, mixer_cls, norm_cls=RMSNorm, fused_add_norm=False, residual_in_fp32=False):
+        super().__init__()
+        self.mixer = mixer_cls(dim)
+        self.norm = norm_cls(dim)
+
+
+class MambaBlocksSequential(nn.Module):
+    """``modules/mamba_blocks.py:87-212`` (parameters + init); forward runs inside the fused engine."""
+
+    def __init__(self, n_mamba, bidirectional=False, d_model=256, d_state=16, expand=2, d_conv=4, dt_rank="auto",
+                 conv_bias=True, bias=False, fused_add_norm=True, rms_norm=False, norm_epsilon=1e-5,
+                 initializer_cfg=None, residual_in_fp32=False):
+        super().__init__()
+        if not bidirectional:
+            _unsupported("bidirectional=False (external mamba_ssm.Mamba)")
+        if not rms_norm:
+            _unsupported("rms_norm=False (nn.LayerNorm blocks)")
+        if norm_epsilon != 1e-5:
+            _unsupported("norm_epsilon != 1e-5")
+        # fused_add_norm only selects between two mathematically identical reference code paths
+        # (mamba_blocks.py:195-210); residual_in_fp32: the residual stream here is always fp32.
+        self.n_mamba = n_mamba
+        mk = lambda i: Block(d_model, lambda d: Mamba(d, d_state=d_state, d_conv=d_conv, expand=expand, dt_rank=dt_rank,
+                                                      conv_bias=conv_bias, bias=bias, layer_idx=i, bimamba_type="v2"))
+        self.layers = nn.Sequential(*[mk(i) for i in range(n_mamba)])
+        self.norm_f = RMSNorm(d_model, eps=norm_epsilon)
+        with torch.no_grad():  # out_proj rescale, mamba_blocks.py:76-84
+            for blk in self.layers:
+                nn.init.kaiming_uniform_(blk.mixer.out_proj.weight, a=math.sqrt(5))
+                blk.mixer.out_proj.weight /= math.sqrt(n_mamba)
+                for dtp in (blk.mixer.dt_proj, blk.mixer.dt_proj_b):  # bimamba.py:101-118
+                    R = dtp.weight.shape[1]
+                    nn.init.uniform_(dtp.weight, -R ** -0.5, R ** -0.5)
+                    dt = torch.exp(torch.rand(dtp.bias.shape[0]) * (math.log(0.1) - math.log(1e-3)) + math.log(1e-3)).clamp(min=1e-4)
+                    dtp.bias.copy_(dt + torch.log(-torch.expm1(-dt)))
+
+
+class _EngineOwner(nn.Module):
+    """Shared machinery: lazily build a ``SeparatorEngine`` from the current parameters."""
+
+    def _invalidate(self):
+        self.__dict__["_engine_cache"] = {}
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        super()._load_from_state_dict(*args, **kwargs)
+        self._invalidate()
+
+    def _apply(self, fn, *a, **k):
+        out = super()._apply(fn, *a, **k)
+        self._invalidate()
+        return out
+
+
+class Encoder(nn.Module):
+    """``relu(conv1d(mix, k=16, s=8))``: [B, T] -> [B, N, L] (view of the kernel's channel-last buffer)."""
+
+    def __init__(self, kernel_size=16, out_channels=256, in_channels=1):
+        super().__init__()
+        if kernel_size != 16 or in_channels != 1:
+            _unsupported("Encoder kernel_size != 16 or in_channels != 1")
+        self.conv1d = nn.Conv1d(in_channels, out_channels, kernel_size, stride=kernel_size // 2, bias=False)
+        self.in_channels = in_channels
+
+    @torch.no_grad()
+    def forward(self, x):
+        N = self.conv1d.weight.shape[0]
+        dev = x.device
+        ones = torch.ones(N, device=dev)
+        zeros = torch.zeros(N, device=dev)
+        mix_w, _ = ops.encoder_cln(x.contiguous().float(), self.conv1d.weight.detach().reshape(N, 16).contiguous(),
+                                   ones, zeros, 1)
+        B, T = x.shape
+        return mix_w.view(B, -1, N).transpose(1, 2)
+
+
+class Decoder(nn.ConvTranspose1d):
+    """``ConvTranspose1d(N -> 1, k=16, s=8, no bias)``: [B, N, L] -> [B, (L-1)*8+16]."""
+
+    def __init__(self, in_channels, out_channels=1, kernel_size=16, stride=8, bias=False, **kw):
+        if out_channels != 1 or kernel_size != 16 or stride != 8 or bias:
+            _unsupported("Decoder with out_channels != 1 / kernel 16 / stride 8 / bias")
+        super().__init__(in_channels, out_channels, kernel_size, stride=stride, bias=False)
+
+    @torch.no_grad()
+    def forward(self, x):
+        if x.dim() != 3:
+            raise RuntimeError(f"Decoder expects [B, N, L], got {tuple(x.shape)}")
+        B, N, L = x.shape
+        sep = x.transpose(1, 2).contiguous().float().view(B * L, N)
+        T_est = (L - 1) * 8 + 16
+        est = ops.decoder(sep, self.weight.detach().reshape(N, 16).contiguous(), B, T_est, L, N, n_spk=1)
+        est = est.view(B, T_est)
+        return est.squeeze(0) if B == 1 else est  # reference squeezes singleton dims (avse2/model.py:33-36)
+
+
+class MaskNet(_EngineOwner):
+    """``modules/mamba_masknet.py:13-139``: [B, N, L] -> est_mask [n_spk, B, N, L] (ReLU mask)."""
+
+    def __init__(self, enc_dim, bot_dim, n_spk=2, norm_type="gLN", causal=False, mask_nonlinear="relu", n_mamba=16,
+                 bidirectional=True, d_model=256, d_state=16, expand=2, d_conv=4, fused_add_norm=False, rms_norm=True,
+                 residual_in_fp32=False, mode="fp32"):
+        super().__init__()
+        if mask_nonlinear != "relu":
+            _unsupported(f"mask_nonlinear={mask_nonlinear!r}")
+        if n_spk != 2:
+            _unsupported(f"n_spk={n_spk}")
+        if bot_dim != d_model:
+            _unsupported("bot_dim != d_model")
+        self.n_spk, self.mask_nonlinear, self.mode = n_spk, mask_nonlinear, mode
+        self.layer_norm = ChannelwiseLayerNorm(enc_dim)
+        self.bottleneck_conv1x1 = _SBConv1d(enc_dim, bot_dim)
+        self.mamba_net = MambaBlocksSequential(n_mamba=n_mamba, bidirectional=bidirectional, d_model=d_model,
+                                               d_state=d_state, expand=expand, d_conv=d_conv,
+                                               fused_add_norm=fused_add_norm, rms_norm=rms_norm,
+                                               residual_in_fp32=residual_in_fp32, conv_bias=True, bias=False)
+        self.mask_conv1x1 = _SBConv1d(bot_dim, n_spk * enc_dim)
+        self.hp = HParams("custom", enc_dim, d_model, n_mamba, d_state=d_state, expand=expand, d_conv=d_conv, n_spk=n_spk)
+        self._invalidate()
+
+    def engine(self, encoder_sd=None, decoder_sd=None, mode=None, use_graph=True) -> SeparatorEngine:
+        mode = mode or self.mode
+        key = (mode, use_graph, id(encoder_sd), id(decoder_sd))
+        cache = self.__dict__.setdefault("_engine_cache", {})
+        if key not in cache:
+            dev = self.layer_norm.gamma.device
+            N = self.hp.enc_dim
+            enc = encoder_sd or {"conv1d.weight": torch.zeros(N, 1, 16)}
+            dec = decoder_sd or {"weight": torch.zeros(N, 1, 16)}
+            cache[key] = SeparatorEngine(self.hp, {"encoder": enc, "masknet": self.state_dict(), "decoder": dec},
+                                         device=dev, mode=mode, use_graph=use_graph)
+        return cache[key]
+
+    @torch.no_grad()
+    def forward(self, mixture_w):
+        B, N, L = mixture_w.shape
+        eng = self.engine(use_graph=False)
+        hp, w, P = eng.hp, eng.w, eng.w.P
+        x = mixture_w.transpose(1, 2).contiguous().float().view(B * L, N)
+        ws = eng.workspace(B, (L - 1) * 8 + 16)
+        ops.cln(x, w.gamma, w.beta, P, yn=ws.yn)
+        ops.gemm(ws.yn, w.w_bot, ws.M, hp.d_model, N, out=ws.h)
+        for i, lw in enumerate(w.layers):
+            eng._layer(ws, lw, first=(i == 0))
+        ops.add_rmsnorm(ws.h, ws.res, True, w.norm_f, P, xn=ws.xn)
+        score = ops.gemm(ws.xn, w.w_mask, ws.M, hp.n_spk * N, hp.d_model, epilogue=_lib.EPI_RELU)
+        return score.view(B, L, hp.n_spk, N).permute(2, 0, 3, 1)  # mamba_masknet.py:126-131
+
+
+class MambaTasNetSeparator(_EngineOwner):
+    """Fused ``Encoder -> MaskNet -> mask * mix_w -> Decoder -> pad/trim`` == ``compute_forward``
+    (``Mamba-TasNet/train_wsj0mix.py:86-111``); ``forward(mix [B, T]) -> est_source [B, T, n_spk]``."""
+
+    def __init__(self, encoder: Encoder, masknet: MaskNet, decoder: Decoder, mode="fp32", use_graph=True):
+        super().__init__()
+        self.encoder, self.masknet, self.decoder = encoder, masknet, decoder
+        self.mode, self.use_graph = mode, use_graph
+        self._invalidate()
+
+    @classmethod
+    def from_hparams(cls, hp: HParams, mode="fp32", use_graph=True):
+        enc = Encoder(hp.kernel_size, hp.enc_dim)
+        mask = MaskNet(hp.enc_dim, hp.d_model, n_spk=hp.n_spk, n_mamba=hp.n_mamba, d_model=hp.d_model,
+                       d_state=hp.d_state, expand=hp.expand, d_conv=hp.d_conv, mode=mode)
+        dec = Decoder(hp.enc_dim, 1, hp.kernel_size, hp.stride, bias=False)
+        return cls(enc, mask, dec, mode=mode, use_graph=use_graph)
+
+    def load_reference_state_dicts(self, sds: dict, strict=True):
+        """``sds = {"encoder": ..., "masknet": ..., "decoder": ...}`` as saved by the reference's checkpointer
+        (``inference.ipynb`` cell 1)."""
+        self.encoder.load_state_dict(sds["encoder"], strict=strict)
+        self.masknet.load_state_dict(sds["masknet"], strict=strict)
+        self.decoder.load_state_dict(sds["decoder"], strict=strict)
+        self._invalidate()
+        return self
+
+    def engine(self) -> SeparatorEngine:
+        cache = self.__dict__.setdefault("_engine_cache", {})
+        if "e" not in cache:
+            dev = self.masknet.layer_norm.gamma.device
+            sds = {"encoder": self.encoder.state_dict(), "masknet": self.masknet.state_dict(),
+                   "decoder": self.decoder.state_dict()}
+            cache["e"] = SeparatorEngine(self.masknet.hp, sds, device=dev, mode=self.mode, use_graph=self.use_graph)
+        return cache["e"]
+
+    @torch.no_grad()
+    def forward(self, mix):
+        return self.engine().forward(mix)

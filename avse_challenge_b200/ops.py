@@ -1,0 +1,135 @@
+"""Thin torch-tensor wrappers over the C ABI (one function per ``mtn_*`` entry point).
+
+These exist for the parity tests and for ``engine.py``; they allocate outputs with torch's caching
+allocator, pass raw device pointers + the current CUDA stream, and raise on any error.  PyTorch is
+plumbing only (memory + streams); every computation below runs in ``libmtn_b200.so``.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import _lib
+from ._lib import GemmArgs, ScanArgs, check, ptr
+
+LOG2E = 1.4426950408889634
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _req_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.MtnError("mtn ops need CUDA tensors (there is no CPU path)")
+
+
+def n_dbl_for(dt_rank: int) -> int:
+    """Padded width of one direction's [dt | B | C] row: 48 for R <= 16, 64 for R = 32."""
+    w = dt_rank + 32
+    return 48 if w <= 48 else 64
+
+
+def split_planes(x: torch.Tensor, planes: int) -> torch.Tensor:
+    """fp32 [rows, cols] -> bf16 [planes, rows, cols] (hi / lo split when planes == 2)."""
+    _req_cuda(x)
+    assert x.dim() == 2 and x.dtype == torch.float32 and x.stride(1) == 1
+    out = torch.empty((planes, x.shape[0], x.shape[1]), dtype=torch.bfloat16, device=x.device)
+    check(_lib.load().mtn_split_planes(ptr(x), x.stride(0), ptr(out), x.shape[0], x.shape[1], planes, _stream()),
+          "mtn_split_planes")
+    return out
+
+
+def planes_to_float(p: torch.Tensor) -> torch.Tensor:
+    """Test helper: reconstruct fp32 from planes (sum over the plane axis)."""
+    return p.float().sum(dim=0)
+
+
+def encoder_cln(mix, w_enc, gamma, beta, planes, eps=1e-8, mix_w=None, yn=None):
+    _req_cuda(mix, w_enc)
+    B, T = mix.shape
+    N = w_enc.shape[0]
+    L = (T - 16) // 8 + 1
+    if mix_w is None:
+        mix_w = torch.empty((B * L, N), dtype=torch.float32, device=mix.device)
+    if yn is None:
+        yn = torch.empty((planes, B * L, N), dtype=torch.bfloat16, device=mix.device)
+    check(_lib.load().mtn_encoder_cln_fwd(ptr(mix), ptr(w_enc), ptr(gamma), ptr(beta), ptr(mix_w), ptr(yn), B, T, L, N,
+                                          planes, eps, _stream()), "mtn_encoder_cln_fwd")
+    return mix_w, yn
+
+
+def cln(x, gamma, beta, planes, eps=1e-8, yn=None):
+    _req_cuda(x)
+    M, N = x.shape
+    if yn is None:
+        yn = torch.empty((planes, M, N), dtype=torch.bfloat16, device=x.device)
+    check(_lib.load().mtn_cln_fwd(ptr(x), ptr(gamma), ptr(beta), ptr(yn), M, N, planes, eps, _stream()), "mtn_cln_fwd")
+    return yn
+
+
+def gemm(a_planes, w_planes, M, N, K, *, out=None, groups=1, out_group_stride=0, epilogue=_lib.EPI_STORE,
+         epi_param=0, aux=None, out_bf16=False, ldo=None, max_ctas=0):
+    """out[M, groups x N] = epilogue(A[M, K_g] @ W_g[N, K]^T); A planes [P, rows, lda], W planes [P, groups*N, K]."""
+    _req_cuda(a_planes, w_planes)
+    P, a_rows, lda = a_planes.shape
+    assert w_planes.shape == (P, groups * N, K), (tuple(w_planes.shape), (P, groups * N, K))
+    if out is None:
+        width = N if groups == 1 else out_group_stride * groups
+        out = torch.empty((M, width), dtype=torch.bfloat16 if out_bf16 else torch.float32, device=a_planes.device)
+    args = GemmArgs(a=ptr(a_planes), w=ptr(w_planes), out=ptr(out), aux=ptr(aux), M=M, N=N, K=K, a_rows=a_rows,
+                    lda=lda, ldo=ldo if ldo is not None else out.stride(0),
+                    ld_aux=aux.stride(0) if aux is not None else 0, planes=P, groups=groups,
+                    out_group_stride=out_group_stride, epilogue=epilogue, epi_param=epi_param,
+                    out_bf16=int(out_bf16), max_ctas=max_ctas)
+    check(_lib.load().mtn_gemm_fwd(args, _stream()), "mtn_gemm_fwd")
+    return out
+
+
+def add_rmsnorm(h, res, res_valid, g, planes, eps=1e-5, xn=None):
+    _req_cuda(res, g)
+    M, D = res.shape
+    if xn is None:
+        xn = torch.empty((planes, M, D), dtype=torch.bfloat16, device=res.device)
+    check(_lib.load().mtn_add_rmsnorm_fwd(ptr(h), ptr(res), int(res_valid), ptr(g), ptr(xn), M, D, planes, eps,
+                                          _stream()), "mtn_add_rmsnorm_fwd")
+    return xn
+
+
+def conv_silu(xz, conv_w, conv_b, batch, L, di, planes, u=None):
+    """xz [M, >= di] (fp32 or bf16; xs = first di columns) -> u planes [P, M, 2*di]."""
+    _req_cuda(xz, conv_w, conv_b)
+    M = batch * L
+    if u is None:
+        u = torch.empty((planes, M, 2 * di), dtype=torch.bfloat16, device=xz.device)
+    check(_lib.load().mtn_conv_silu_fwd(ptr(xz), xz.stride(0), int(xz.dtype == torch.bfloat16), ptr(conv_w),
+                                        ptr(conv_b), ptr(u), batch, L, di, planes, _stream()), "mtn_conv_silu_fwd")
+    return u
+
+
+def scan(u, dbl, z, z_col0, w_dt, dt_bias, A2, Dskip, batch, L, di, R, *, y=None, h_in=None, h_out=None, dir_mask=3):
+    """Both-direction selective scan; see ``mtn_scan_args`` in include/mtn_b200.h."""
+    _req_cuda(u, dbl, z)
+    P = u.shape[0]
+    nd = n_dbl_for(R)
+    if y is None:
+        y = torch.empty_like(u)
+    args = ScanArgs(u=ptr(u), dbl=ptr(dbl), z=ptr(z), w_dt=ptr(w_dt), dt_bias=ptr(dt_bias), A2=ptr(A2),
+                    Dskip=ptr(Dskip), y=ptr(y), h_in=ptr(h_in), h_out=ptr(h_out), batch=batch, L=L, di=di, R=R,
+                    n_dbl=nd, ld_dbl=dbl.stride(0), ldz=z.stride(0), z_col0=z_col0, planes=P,
+                    z_bf16=int(z.dtype == torch.bfloat16), dir_mask=dir_mask)
+    check(_lib.load().mtn_scan_fwd(args, _stream()), "mtn_scan_fwd")
+    return y
+
+
+def decoder(sep, w_dec, batch, T, L, N, n_spk=2, est=None, frames=None):
+    _req_cuda(sep, w_dec)
+    if frames is None:
+        frames = torch.empty((batch * L, n_spk, 16), dtype=torch.float32, device=sep.device)
+    if est is None:
+        est = torch.empty((batch, T, n_spk), dtype=torch.float32, device=sep.device)
+    check(_lib.load().mtn_decoder_fwd(ptr(sep), ptr(w_dec), ptr(frames), ptr(est), batch, T, L, N, n_spk, _stream()),
+          "mtn_decoder_fwd")
+    return est

@@ -1,0 +1,127 @@
+/* mtn_b200.h -- C ABI of the B200-native Mamba-TasNet separator forward.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.
+ * Every entry point launches hand-written sm_100a kernels on the caller's stream and returns
+ * immediately (stream-ordered, re-entrant, CUDA-graph capturable).  The caller owns every
+ * buffer; the library allocates nothing and keeps no state besides the last error string.
+ * Return value: 0 on success, negative MTN_E* on error (never throws, never exits, never
+ * falls back to another implementation).
+ *
+ * What each entry replaces in the reference (paths relative to /root/reference):
+ *   mtn_encoder_cln_fwd  speechbrain dual_path.Encoder.forward (== baseline/avse2/model.py:14-24,
+ *                        called Mamba-TasNet/train_wsj0mix.py:89) + ChannelwiseLayerNorm
+ *                        (Mamba-TasNet/modules/mamba_masknet.py:118)
+ *   mtn_gemm_fwd         every dense contraction of the path: bottleneck / mask 1x1 convs
+ *                        (mamba_masknet.py:121,123), in_proj (modules/mamba/bimamba.py:192-196),
+ *                        x_proj (modules/mamba/selective_scan_interface.py:186), out_proj
+ *                        (bimamba.py:253); epilogues fuse SiLU(z) (ssi.py:155) and
+ *                        relu(mask)*mix_w (mamba_masknet.py:136 + train_wsj0mix.py:91-92)
+ *   mtn_add_rmsnorm_fwd  Block.forward add + RMSNorm (bimamba.py:446-447) and the final
+ *                        add + norm_f (modules/mamba_blocks.py:196-197)
+ *   mtn_conv_silu_fwd    causal_conv1d_cuda.causal_conv1d_fwd (ssi.py:182), both directions
+ *                        (the reference runs the 2nd on xz.flip(-1), bimamba.py:237)
+ *   mtn_scan_fwd         dt_proj GEMM (ssi.py:187) + selective_scan_cuda.fwd (ssi.py:218-220,
+ *                        oracle selective_scan_ref ssi.py:91-157), both directions, incl. the 0.5
+ *                        averaging of bimamba.py:253; optional initial/final state for the
+ *                        sequence-parallel mode
+ *   mtn_cln_fwd          ChannelwiseLayerNorm alone (mamba_masknet.py:118) for the stand-alone MaskNet module
+ *   mtn_decoder_fwd      speechbrain dual_path.Decoder (== baseline/avse2/model.py:27-37), both
+ *                        speakers, cat + pad/trim (train_wsj0mix.py:95-109)
+ *
+ * Layout conventions: every activation is channel-last [tokens = batch*frames, channels].
+ * "planes" P: a GEMM A-operand tensor is stored as P bf16 planes [P][rows][ld]:
+ *   P = 2 ("fp32 mode"): value = hi + lo (split-bf16; the GEMM computes hi*hi + lo*hi + hi*lo in
+ *          fp32 TMEM accumulators: ~2^-17 relative operand error), P = 1 ("bf16 mode"): plain bf16.
+ */
+#ifndef MTN_B200_H
+#define MTN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MTN_OK 0
+#define MTN_EINVAL (-1)  /* bad shape / alignment / unsupported option */
+#define MTN_ECUDA (-2)   /* CUDA runtime or driver error; see mtn_last_error_string() */
+
+typedef void* mtn_stream_t; /* cudaStream_t */
+
+enum { MTN_EPI_STORE = 0, MTN_EPI_INPROJ = 1, MTN_EPI_MASK = 2, MTN_EPI_RELU = 3 };
+
+typedef struct {
+    const void* a;       /* bf16 [planes][a_rows][lda]; group g reads columns [g*K, (g+1)*K) */
+    const void* w;       /* bf16 [planes][groups*N][K]  (row-major, K contiguous) */
+    void* out;           /* fp32 (or bf16 if out_bf16) [M][ldo]; group g writes columns g*out_group_stride + [0,N) */
+    const void* aux;     /* MTN_EPI_MASK: mix_w fp32 [M][ld_aux]; else NULL */
+    int M, N, K;         /* per-group problem; N % 16 == 0, N <= 256 or N % 256 == 0 or N % 128 == 0; K % 64 == 0 */
+    int a_rows;          /* rows allocated per A plane (>= M) */
+    int lda, ldo, ld_aux;
+    int planes;          /* 1 or 2 */
+    int groups;          /* >= 1 */
+    int out_group_stride;
+    int epilogue;        /* MTN_EPI_* */
+    int epi_param;       /* INPROJ: first column that gets SiLU; MASK: enc_dim (aux column = col % enc_dim) */
+    int out_bf16;        /* 0: fp32 output, 1: bf16 output */
+    int max_ctas;        /* 0 = one persistent CTA per SM */
+} mtn_gemm_args;
+
+typedef struct {
+    const void* u;        /* bf16 [planes][M][2*di]: conv output, direction d at columns [d*di, (d+1)*di) */
+    const float* dbl;     /* fp32 [M][ld_dbl]: direction d at columns d*n_dbl + [dt(R) | B(16) | C(16)] */
+    const void* z;        /* silu(z), fp32 (or bf16 if z_bf16) [M][ldz], columns z_col0 + [0, di) */
+    const float* w_dt;    /* [2][di][R] */
+    const float* dt_bias; /* [2][di] */
+    const float* A2;      /* [2][di][16] = -exp(A_log) * log2(e) */
+    const float* Dskip;   /* [2][di] */
+    void* y;              /* bf16 [planes][M][2*di]: 0.5 * (scan + D*u) * silu(z), same column convention as u */
+    const float* h_in;    /* nullable: fp32 [2][batch][di][16] initial state per direction */
+    float* h_out;         /* nullable: fp32 [2][batch][di][16] final state per direction */
+    int batch, L, di, R, n_dbl, ld_dbl, ldz, z_col0;
+    int planes;           /* 1 or 2 */
+    int z_bf16;
+    int dir_mask;         /* bit0 forward, bit1 backward (3 = both in one launch) */
+} mtn_scan_args;
+
+/* mix [batch][T] fp32 -> mix_w [batch*L][N] fp32 = relu(conv1d(k=16,s=8)); yn planes = cLN(mix_w) */
+int mtn_encoder_cln_fwd(const float* mix, const float* w_enc /*[N][16]*/, const float* gamma, const float* beta,
+                        float* mix_w, void* yn_planes, int batch, int T, int L, int N, int planes, float eps,
+                        mtn_stream_t stream);
+
+int mtn_gemm_fwd(const mtn_gemm_args* args, mtn_stream_t stream);
+
+/* res = (h ? h : 0) + (res_valid ? res : 0); xn planes = res * rsqrt(mean(res^2)+eps) * g.
+ * h fp32 [M][D] (nullable), res fp32 [M][D] in/out. */
+int mtn_add_rmsnorm_fwd(const float* h, float* res, int res_valid, const float* g, void* xn_planes, int M, int D,
+                        int planes, float eps, mtn_stream_t stream);
+
+/* xs = xz[:, 0:di] (fp32 or bf16, row stride ldxz) -> u planes [P][M][2*di]:
+ * u_fwd[t] = silu(b + sum_k w[k]*xs[t-3+k]),  u_bwd[t] = silu(b' + sum_k w'[k]*xs[t+3-k]), zero padded per
+ * utterance.  conv_w [2][di][4], conv_b [2][di]. */
+int mtn_conv_silu_fwd(const void* xz, int ldxz, int xz_bf16, const float* conv_w, const float* conv_b, void* u_planes,
+                      int batch, int L, int di, int planes, mtn_stream_t stream);
+
+int mtn_scan_fwd(const mtn_scan_args* args, mtn_stream_t stream);
+
+/* sep fp32 [batch*L][n_spk*N] (speaker-major channels) -> est [batch][T][n_spk] fp32:
+ * est[b, 8l+k, s] = sum over frames/taps of sum_n w_dec[n][k] * sep[b,l,s*N+n]; zero-padded / trimmed to T.
+ * frames: scratch fp32 [batch*L][n_spk][16]. */
+int mtn_decoder_fwd(const float* sep, const float* w_dec /*[N][16]*/, float* frames, float* est, int batch, int T, int L,
+                    int N, int n_spk, mtn_stream_t stream);
+
+/* ChannelwiseLayerNorm alone (MaskNet called on an externally produced mix_w): x fp32 [M][N] -> yn planes */
+int mtn_cln_fwd(const float* x, const float* gamma, const float* beta, void* yn_planes, int M, int N, int planes,
+                float eps, mtn_stream_t stream);
+
+/* fp32 [rows][cols] (row stride ld) -> bf16 planes [planes][rows][cols] (weight packing helper) */
+int mtn_split_planes(const float* src, int ld, void* dst_planes, int rows, int cols, int planes, mtn_stream_t stream);
+
+const char* mtn_last_error_string(void);
+int mtn_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MTN_B200_H */

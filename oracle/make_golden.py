@@ -1,0 +1,101 @@
+"""TEST INFRASTRUCTURE ONLY -- mint golden vectors from the REAL reference (build container only).
+
+Runs the reference's own modules (imported from ``/root/reference`` under ``oracle/ref_shims.py``)
+on seeded inputs and stores inputs, weights and outputs as small ``.npz`` fixtures under
+``tests/golden/``.  The reference ships no tests or golden vectors for this path (SURVEY.md
+section 4), so these files are what pins both the oracle restatement and the CUDA path.
+
+    python -m oracle.make_golden
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_shims  # noqa: E402
+from avse_challenge_b200.hparams import CONFIGS, init_state_dicts  # noqa: E402
+from avse_challenge_b200.synth import synth_mixture  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def _np(sd, prefix):
+    return {f"{prefix}/{k}": v.detach().numpy() for k, v in sd.items()}
+
+
+def golden_scan():
+    """``selective_scan_ref`` itself (``modules/mamba/selective_scan_interface.py:91-157``) in the
+    reference's own [B, D, L] layout, with and without z / delta_bias / softplus."""
+    ref = ref_shims.load_reference()
+    g = torch.Generator().manual_seed(1234)
+    B, D, L, N = 2, 24, 157, 16
+    u = torch.randn(B, D, L, generator=g)
+    delta = torch.randn(B, D, L, generator=g) * 0.5 - 3.0
+    A = -torch.exp(torch.randn(D, N, generator=g) * 0.5 + 0.5)
+    Bm = torch.randn(B, N, L, generator=g)
+    Cm = torch.randn(B, N, L, generator=g)
+    Dv = torch.randn(D, generator=g)
+    z = torch.randn(B, D, L, generator=g)
+    bias = torch.randn(D, generator=g) * 0.3
+    out, last = ref.selective_scan_ref(u, delta, A, Bm, Cm, Dv, z, bias, True, True)
+    out_nz, _ = ref.selective_scan_ref(u, delta, A, Bm, Cm, Dv, None, bias, True, True)
+    # flipped-input call, exactly how bimamba.py:237 drives the backward direction
+    out_b = ref.selective_scan_ref(u.flip(-1), delta.flip(-1), A, Bm.flip(-1), Cm.flip(-1), Dv,
+                                   z.flip(-1), bias, True).flip(-1)
+    np.savez_compressed(os.path.join(OUT, "scan_ref.npz"), u=u.numpy(), delta=delta.numpy(), A=A.numpy(),
+                        B=Bm.numpy(), C=Cm.numpy(), D=Dv.numpy(), z=z.numpy(), bias=bias.numpy(),
+                        out=out.numpy(), last_state=last.numpy(), out_nogate=out_nz.numpy(),
+                        out_reverse=out_b.numpy())
+
+
+def golden_forward(name, T, batch, seed, tag, own_init):
+    hp = CONFIGS[name]
+    ref = ref_shims.load_reference()
+    enc, mask, dec = ref_shims.build_reference_model(hp.as_dict(), seed=seed)
+    if own_init:  # perturbed ("trained-like") weights, loaded strict into the reference modules
+        sds = init_state_dicts(hp, seed)
+        enc.load_state_dict(sds["encoder"], strict=True)
+        mask.load_state_dict(sds["masknet"], strict=True)
+        dec.load_state_dict(sds["decoder"], strict=True)
+    mix, src = synth_mixture(batch, T, hp.sample_rate, seed=seed)
+    taps = {}
+
+    def hook(key):
+        def fn(_m, _i, o):
+            taps[key] = (o[0] if isinstance(o, tuple) else o).detach().numpy()
+        return fn
+
+    mask.mamba_net.layers[0].mixer.register_forward_hook(hook("mixer0_out"))
+    mask.mamba_net.register_forward_hook(hook("stack_out"))
+    mask.bottleneck_conv1x1.register_forward_hook(hook("bottleneck_out"))
+    with torch.no_grad():
+        mix_w = enc(mix)
+        est_mask = mask(mix_w)
+        est = ref.compute_forward(enc, mask, dec, mix)
+    arrs = {"mix": mix.numpy(), "src": src.numpy(), "est": est.numpy(), "mix_w": mix_w.numpy(),
+            "est_mask": est_mask.numpy(), "T": np.int64(T), "batch": np.int64(batch)}
+    arrs.update({f"tap/{k}": v for k, v in taps.items()})
+    arrs.update(_np(enc.state_dict(), "encoder"))
+    arrs.update(_np(mask.state_dict(), "masknet"))
+    arrs.update(_np(dec.state_dict(), "decoder"))
+    np.savez_compressed(os.path.join(OUT, f"forward_{tag}.npz"), **arrs)
+    print(tag, "est rms", float(est.pow(2).mean().sqrt()), "file",
+          os.path.getsize(os.path.join(OUT, f"forward_{tag}.npz")) // 1024, "KiB")
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(os.cpu_count())
+    golden_scan()
+    golden_forward("tiny", T=2000, batch=2, seed=1234, tag="tiny_refinit", own_init=False)
+    golden_forward("tiny", T=1003, batch=3, seed=77, tag="tiny_trained", own_init=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,196 @@
+"""TEST INFRASTRUCTURE ONLY -- import the REAL reference modules under leaf shims.
+
+The reference's hot path (``/root/reference/Mamba-TasNet/modules``) hard-imports
+third-party packages that are not installed here (``causal_conv1d``,
+``causal_conv1d_cuda``, ``selective_scan_cuda``, ``mamba_ssm``, ``speechbrain``;
+see ``modules/mamba/selective_scan_interface.py:14-16``,
+``modules/mamba_masknet.py:3-8``, ``modules/mamba_blocks.py:12-17``).  This module
+registers minimal stand-ins for exactly those *leaves* in ``sys.modules`` so that
+the reference's own ``MaskNet`` / ``MambaBlocksSequential`` / ``Block`` / bi-``Mamba``
+/ ``MambaInnerFnNoOutProj`` / ``selective_scan_ref`` code runs unmodified on CPU.
+
+Leaf semantics (each is the documented behaviour of the pinned third-party
+version, ``Mamba-TasNet/requirement.txt:7-11``):
+
+* ``causal_conv1d_cuda.causal_conv1d_fwd(x, w, b, seq_idx, silu)``
+  = depthwise causal conv (left zero pad ``width-1``) + bias + optional SiLU;
+  same arithmetic the reference uses in its non-CUDA branch
+  (``modules/mamba/bimamba.py:279``).
+* ``selective_scan_cuda.fwd(...)`` -> routed to the reference's own
+  ``selective_scan_ref`` (``modules/mamba/selective_scan_interface.py:91-157``).
+* ``mamba_ssm.ops.triton.layernorm.RMSNorm``: ``x * rsqrt(mean(x^2) + eps) * w``
+  in fp32 (mamba-ssm 1.1.3.post1 ``rms_norm_ref``).
+* ``speechbrain.lobes.models.conv_tasnet.ChannelwiseLayerNorm``: per-token
+  mean/var over channels (biased), ``gamma*(y-mean)/sqrt(var+1e-8)+beta``,
+  params ``gamma``/``beta`` of shape ``[1,1,N]`` (speechbrain 1.0.0).
+* ``speechbrain.nnet.CNN.Conv1d``: channel-last wrapper around ``nn.Conv1d``
+  stored as child ``conv`` (state_dict key ``conv.weight``).
+
+This file can only work where ``/root/reference`` exists (the build container).
+"""
+from __future__ import annotations
+
+import os
+import sys
+import types
+import warnings
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+REFERENCE_ROOT = os.environ.get("MTN_REFERENCE_ROOT", "/root/reference")
+_MT_ROOT = os.path.join(REFERENCE_ROOT, "Mamba-TasNet")
+
+
+def reference_available() -> bool:
+    return os.path.isdir(os.path.join(_MT_ROOT, "modules"))
+
+
+# --------------------------------------------------------------------------- leaves
+def _causal_conv1d_fwd(x, weight, bias, seq_idx, silu):
+    # x [B, D, L]; weight [D, W]
+    d, w = weight.shape
+    y = F.conv1d(x, weight[:, None, :], bias, padding=w - 1, groups=d)[..., : x.shape[-1]]
+    return F.silu(y) if silu else y
+
+
+class _RMSNorm(nn.Module):
+    def __init__(self, hidden_size, eps=1e-5, device=None, dtype=None):
+        super().__init__()
+        self.eps = eps
+        self.weight = nn.Parameter(torch.ones(hidden_size, device=device, dtype=dtype))
+        self.register_parameter("bias", None)
+
+    def forward(self, x):
+        xf = x.float()
+        y = xf * torch.rsqrt(xf.pow(2).mean(dim=-1, keepdim=True) + self.eps) * self.weight.float()
+        return y.to(x.dtype)
+
+
+class _ChannelwiseLayerNorm(nn.Module):
+    def __init__(self, channel_size):
+        super().__init__()
+        self.gamma = nn.Parameter(torch.ones(1, 1, channel_size))
+        self.beta = nn.Parameter(torch.zeros(1, 1, channel_size))
+
+    def forward(self, y):
+        mean = torch.mean(y, dim=2, keepdim=True)
+        var = torch.var(y, dim=2, keepdim=True, unbiased=False)
+        return self.gamma * (y - mean) / torch.pow(var + 1e-8, 0.5) + self.beta
+
+
+class _SBConv1d(nn.Module):
+    """speechbrain.nnet.CNN.Conv1d restricted to what MaskNet uses (k=1, no bias)."""
+
+    def __init__(self, out_channels, kernel_size, in_channels=None, bias=True, **kw):
+        super().__init__()
+        assert kernel_size == 1
+        self.conv = nn.Conv1d(in_channels, out_channels, kernel_size, bias=bias)
+
+    def forward(self, x):  # [B, L, C] -> [B, L, C_out]
+        return self.conv(x.transpose(1, -1)).transpose(1, -1)
+
+
+_loaded = None
+
+
+def load_reference():
+    """Return a namespace with the reference's own classes/functions (CPU-runnable)."""
+    global _loaded
+    if _loaded is not None:
+        return _loaded
+    if not reference_available():
+        raise RuntimeError(f"reference tree not found under {REFERENCE_ROOT}")
+    warnings.filterwarnings("ignore", category=FutureWarning)
+
+    def mod(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+        return m
+
+    mod("causal_conv1d", causal_conv1d_fn=None, causal_conv1d_update=None)
+    mod("causal_conv1d_cuda", causal_conv1d_fwd=_causal_conv1d_fwd)
+    ssc = mod("selective_scan_cuda")
+    mod("mamba_ssm", Mamba=None)
+    mod("mamba_ssm.ops")
+    mod("mamba_ssm.ops.triton")
+    mod("mamba_ssm.ops.triton.layernorm", RMSNorm=_RMSNorm, layer_norm_fn=None, rms_norm_fn=None)
+    sb = mod("speechbrain")
+    sb.nnet = mod("speechbrain.nnet")
+    sb.nnet.CNN = mod("speechbrain.nnet.CNN", Conv1d=_SBConv1d)
+    mod("speechbrain.lobes")
+    mod("speechbrain.lobes.models")
+    mod("speechbrain.lobes.models.conv_tasnet", ChannelwiseLayerNorm=_ChannelwiseLayerNorm)
+
+    sys.dont_write_bytecode = True  # reference tree is read-only
+    if _MT_ROOT not in sys.path:
+        sys.path.insert(0, _MT_ROOT)
+    from modules.mamba import selective_scan_interface as ssi  # noqa: E402
+
+    def _fwd(u, delta, A, B, C, D, z, delta_bias, delta_softplus):
+        out_z = ssi.selective_scan_ref(u, delta, A, B, C, D, z, delta_bias, delta_softplus)
+        return out_z, torch.empty(0), out_z
+
+    ssc.fwd = _fwd
+    from modules.mamba_masknet import MaskNet  # noqa: E402
+    from modules.mamba_blocks import MambaBlocksSequential  # noqa: E402
+    from modules.mamba.bimamba import Mamba as BiMamba, Block  # noqa: E402
+
+    class RefEncoder(nn.Module):
+        """speechbrain dual_path.Encoder == baseline/avse2/model.py:14-24 (in-repo twin)."""
+
+        def __init__(self, kernel_size=16, out_channels=256, in_channels=1):
+            super().__init__()
+            self.conv1d = nn.Conv1d(in_channels, out_channels, kernel_size,
+                                    stride=kernel_size // 2, groups=1, bias=False)
+
+        def forward(self, x):
+            return F.relu(self.conv1d(x.unsqueeze(1)))
+
+    class RefDecoder(nn.ConvTranspose1d):
+        """speechbrain dual_path.Decoder == baseline/avse2/model.py:27-37."""
+
+        def forward(self, x):
+            x = super().forward(x)
+            return torch.squeeze(x, dim=1) if torch.squeeze(x).dim() == 1 else torch.squeeze(x)
+
+    def compute_forward(encoder, masknet, decoder, mix, num_spks=2):
+        """Line-for-line behaviour of Separation.compute_forward
+        (Mamba-TasNet/train_wsj0mix.py:86-111), calling the modules passed in."""
+        mix_w = encoder(mix)
+        est_mask = masknet(mix_w)
+        mix_w = torch.stack([mix_w] * num_spks)
+        sep_h = mix_w * est_mask
+        est_source = torch.cat([decoder(sep_h[i]).unsqueeze(-1) for i in range(num_spks)], dim=-1)
+        if est_source.dim() == 2:  # batch 1 got squeezed by the decoder
+            est_source = est_source.unsqueeze(0)
+        t_origin, t_est = mix.size(1), est_source.size(1)
+        if t_origin > t_est:
+            est_source = F.pad(est_source, (0, 0, 0, t_origin - t_est))
+        else:
+            est_source = est_source[:, :t_origin, :]
+        return est_source
+
+    _loaded = types.SimpleNamespace(
+        MaskNet=MaskNet, MambaBlocksSequential=MambaBlocksSequential, BiMamba=BiMamba, Block=Block,
+        selective_scan_ref=ssi.selective_scan_ref, Encoder=RefEncoder, Decoder=RefDecoder,
+        compute_forward=compute_forward, ssi=ssi,
+    )
+    return _loaded
+
+
+def build_reference_model(hp, seed=1234):
+    """Construct reference Encoder/MaskNet/Decoder with the reference's own init under a seed.
+
+    ``hp`` needs: enc_dim, d_model, n_mamba, kernel_size."""
+    ref = load_reference()
+    torch.manual_seed(seed)
+    enc = ref.Encoder(kernel_size=hp["kernel_size"], out_channels=hp["enc_dim"])
+    mask = ref.MaskNet(enc_dim=hp["enc_dim"], bot_dim=hp["d_model"], n_spk=2, n_mamba=hp["n_mamba"],
+                       bidirectional=True, d_model=hp["d_model"], d_state=16, expand=2, d_conv=4,
+                       fused_add_norm=False, rms_norm=True, residual_in_fp32=False)
+    dec = ref.Decoder(in_channels=hp["enc_dim"], out_channels=1, kernel_size=hp["kernel_size"],
+                      stride=hp["kernel_size"] // 2, bias=False)
+    return enc.eval(), mask.eval(), dec.eval()

@@ -1,0 +1,236 @@
+"""TEST INFRASTRUCTURE ONLY -- torch-CPU restatement of the reference Mamba-TasNet forward.
+
+Channel-last (``[B, L, C]``) restatement of the math in SURVEY.md App. A.  It is the checker
+for the CUDA path and the reported CPU baseline; the product never imports it.
+Pinned against the real reference (imported under ``oracle/ref_shims.py``) by
+``tests/test_oracle.py`` via ``tests/golden/*.npz``.
+
+All parameters are taken from state_dicts with the reference's key names.
+Citations are relative to ``/root/reference``.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CLIB = None
+
+
+# ----------------------------------------------------------------------------- C scan (optional)
+def build_c_oracle(force: bool = False) -> str:
+    """Compile ``oracle/selscan_ref.c`` -> ``oracle/_build/libselscan_ref.so`` (gcc, OpenMP)."""
+    out_dir = os.path.join(_HERE, "_build")
+    os.makedirs(out_dir, exist_ok=True)
+    so = os.path.join(out_dir, "libselscan_ref.so")
+    src = os.path.join(_HERE, "selscan_ref.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-fopenmp", "-fno-fast-math",
+                               "-o", so, src, "-lm"])
+    return so
+
+
+def _clib():
+    global _CLIB
+    if _CLIB is None:
+        lib = ctypes.CDLL(build_c_oracle())
+        lib.selscan_ref_f32.restype = None
+        lib.selscan_ref_f32.argtypes = [ctypes.c_void_p] * 10 + [ctypes.c_int] * 5 + [ctypes.c_void_p] * 2
+        _CLIB = lib
+    return _CLIB
+
+
+# ----------------------------------------------------------------------------- GEMM rounding model
+_GEMM_MODE = "fp32"
+
+
+def set_gemm_mode(mode: str):
+    """Rounding model applied to BOTH operands of every dense contraction of the path:
+    "fp32" (reference), "bf16" (one bf16 plane), "bf16x3" (hi+lo bf16 planes, 3 products --
+    what the CUDA fp32 mode computes), "tf32" (round-to-nearest 10-bit mantissa)."""
+    global _GEMM_MODE
+    assert mode in ("fp32", "bf16", "bf16x3", "tf32")
+    _GEMM_MODE = mode
+
+
+def _planes(x):
+    hi = x.to(torch.bfloat16).to(x.dtype)
+    lo = (x - hi).to(torch.bfloat16).to(x.dtype)
+    return hi, lo
+
+
+def _mm(x, w):
+    """``x @ w.T`` under the selected operand-rounding model (accumulation stays fp32/fp64)."""
+    if _GEMM_MODE == "fp32":
+        return x @ w.t()
+    if _GEMM_MODE == "bf16":
+        return x.to(torch.bfloat16).to(x.dtype) @ w.to(torch.bfloat16).to(w.dtype).t()
+    if _GEMM_MODE == "tf32":
+        r = lambda t: ((t.float().view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32).to(t.dtype)
+        return r(x) @ r(w).t()
+    xh, xl = _planes(x)
+    wh, wl = _planes(w)
+    return xh @ wh.t() + (xl @ wh.t() + xh @ wl.t())
+
+
+# ----------------------------------------------------------------------------- pieces
+def encoder_fwd(mix, w_enc):
+    """``relu(conv1d(mix[:,None,:], W[N,1,K], stride K//2))`` -> ``[B, L, N]``.
+    speechbrain ``dual_path.Encoder`` == ``baseline/avse2/model.py:14-24``."""
+    k = w_enc.shape[-1]
+    return F.relu(F.conv1d(mix.unsqueeze(1), w_enc, stride=k // 2)).transpose(1, 2).contiguous()
+
+
+def cln_fwd(y, gamma, beta, eps=1e-8):
+    """ChannelwiseLayerNorm over the channel axis, biased variance, eps 1e-8
+    (speechbrain ``conv_tasnet.ChannelwiseLayerNorm``; ctor ``modules/mamba_masknet.py:73``)."""
+    mean = y.mean(dim=-1, keepdim=True)
+    var = y.var(dim=-1, keepdim=True, unbiased=False)
+    return gamma.reshape(-1) * (y - mean) / torch.sqrt(var + eps) + beta.reshape(-1)
+
+
+def rmsnorm_fwd(x, w, eps=1e-5):
+    """``x * rsqrt(mean(x^2)+eps) * w`` (mamba-ssm RMSNorm; eps ``modules/mamba_blocks.py:120``)."""
+    return x * torch.rsqrt(x.pow(2).mean(dim=-1, keepdim=True) + eps) * w
+
+
+def causal_conv_silu(xs, w, b, reverse=False):
+    """Depthwise causal conv (width 4) + bias + SiLU on ``[B, L, di]``.
+    ``causal_conv1d_fwd`` call site ``modules/mamba/selective_scan_interface.py:182``; the backward
+    direction is the same op on the time-flipped sequence (``modules/mamba/bimamba.py:237``)."""
+    x = xs.transpose(1, 2)
+    if reverse:
+        x = x.flip(-1)
+    di, _, width = w.shape
+    y = F.silu(F.conv1d(x, w, b, padding=width - 1, groups=di)[..., : x.shape[-1]])
+    if reverse:
+        y = y.flip(-1)
+    return y.transpose(1, 2).contiguous()
+
+
+def selective_scan(u, delta_pre, A, Bm, Cm, D, z, delta_bias, reverse=False, h_in=None,
+                   impl="auto", gate=True):
+    """Selective-scan recurrence, channel-last.
+
+    u, delta_pre, z: ``[B, L, di]``; Bm, Cm: ``[B, L, Ns]``; A ``[di, Ns]``; D, delta_bias ``[di]``.
+    Follows ``selective_scan_ref`` (``modules/mamba/selective_scan_interface.py:91-157``):
+    ``delta = softplus(delta_pre + bias)`` (:110-112), ``h = exp(delta*A)*h + delta*B*u`` (:126-139),
+    ``y = <h, C> + D*u`` (:144,:153), ``out = y * silu(z)`` (:155).  ``reverse`` runs t = L-1..0
+    (the reference flips the inputs instead, ``bimamba.py:237,253``).  ``h_in``/returned
+    ``h_last`` ``[B, di, Ns]`` are the chunk-carry extension needed for sequence-parallel mode
+    (the reference starts from zeros, :124, and can return the last state, :147-148).
+
+    impl: "torch" = per-step Python loop like the reference; "c" = oracle/selscan_ref.c;
+    "auto" = "c" for fp32 when it builds, else "torch".
+    Returns ``(out [B, L, di], h_last [B, di, Ns])``.
+    """
+    Bsz, L, di = u.shape
+    Ns = A.shape[1]
+    if impl == "auto":
+        impl = "c" if u.dtype == torch.float32 else "torch"
+    if impl == "c":
+        lib = _clib()
+        f = lambda t: np.ascontiguousarray(t.detach().to(torch.float32).numpy())
+        un, dn, An, Bn, Cn, Dn, bn = f(u), f(delta_pre), f(A), f(Bm), f(Cm), f(D), f(delta_bias)
+        zn = f(z) if (gate and z is not None) else None
+        hn = f(h_in) if h_in is not None else None
+        out = np.empty_like(un)
+        hl = np.empty((Bsz, di, Ns), dtype=np.float32)
+        p = lambda a: a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
+        lib.selscan_ref_f32(p(un), p(dn), p(An), p(Bn), p(Cn), p(Dn), p(zn), p(bn), p(hn), p(out),
+                            Bsz, L, di, Ns, int(bool(reverse)), p(hl), None)
+        return torch.from_numpy(out), torch.from_numpy(hl)
+    delta = F.softplus(delta_pre + delta_bias)                           # :110-112
+    h = torch.zeros(Bsz, di, Ns, dtype=u.dtype) if h_in is None else h_in.clone()
+    ys = [None] * L
+    order = range(L - 1, -1, -1) if reverse else range(L)
+    for t in order:                                                       # :138-151
+        dA = torch.exp(delta[:, t, :, None] * A)                          # :126
+        dBu = delta[:, t, :, None] * Bm[:, t, None, :] * u[:, t, :, None]  # :131
+        h = dA * h + dBu                                                  # :139
+        ys[t] = torch.einsum("bdn,bn->bd", h, Cm[:, t])                   # :144
+    y = torch.stack(ys, dim=1) + u * D                                    # :152-153
+    if gate and z is not None:
+        y = y * F.silu(z)                                                 # :155
+    return y, h
+
+
+def mixer_fwd(x, sd, prefix, scan_impl="auto"):
+    """Bidirectional ("v2") Mamba mixer (``modules/mamba/bimamba.py:176-253`` +
+    ``MambaInnerFnNoOutProj.forward`` ``selective_scan_interface.py:164-229``), ``[B,L,D]->[B,L,D]``."""
+    p = prefix
+    W_in = sd[p + "in_proj.weight"]
+    di = W_in.shape[0] // 2
+    xz = _mm(x, W_in)                                                       # bimamba.py:192-196
+    xs, z = xz[..., :di], xz[..., di:]                                     # ssi.py:180 (x first, z last)
+    outs = []
+    for sfx, rev in (("", False), ("_b", True)):
+        conv_w, conv_b = sd[p + f"conv1d{sfx}.weight"], sd[p + f"conv1d{sfx}.bias"]
+        W_x, W_dt, b_dt = sd[p + f"x_proj{sfx}.weight"], sd[p + f"dt_proj{sfx}.weight"], sd[p + f"dt_proj{sfx}.bias"]
+        A = -torch.exp(sd[p + ("A_log" if not rev else "A_b_log")].float())   # bimamba.py:200,222
+        D = sd[p + ("D" if not rev else "D_b")].float()
+        R = W_dt.shape[1]
+        Ns = A.shape[1]
+        u = causal_conv_silu(xs, conv_w, conv_b, reverse=rev)             # ssi.py:182
+        dbl = _mm(u, W_x)                                                  # ssi.py:186
+        delta_pre = dbl[..., :R] @ W_dt.t()                                # ssi.py:187 (bias NOT added here)
+        Bm, Cm = dbl[..., R:R + Ns], dbl[..., R + Ns:]                     # ssi.py:193,205
+        y, _ = selective_scan(u, delta_pre, A.to(u.dtype), Bm, Cm, D.to(u.dtype), z,
+                              b_dt.to(u.dtype), reverse=rev, impl=scan_impl)  # ssi.py:218-220
+        outs.append(y)
+    return _mm(0.5 * outs[0] + 0.5 * outs[1], sd[p + "out_proj.weight"])  # bimamba.py:253
+
+
+def mamba_stack_fwd(h, sd, n_mamba, prefix="mamba_net.", scan_impl="auto", taps=None):
+    """``MambaBlocksSequential.forward`` non-fused branch (``modules/mamba_blocks.py:186-197``)
+    over ``Block.forward`` (``modules/mamba/bimamba.py:445-462``): Add -> RMSNorm -> Mixer."""
+    residual = None
+    for i in range(n_mamba):
+        p = f"{prefix}layers.{i}."
+        residual = h if residual is None else h + residual                # bimamba.py:446
+        hn = rmsnorm_fwd(residual, sd[p + "norm.weight"])                  # bimamba.py:447
+        h = mixer_fwd(hn, sd, p + "mixer.", scan_impl)                     # bimamba.py:461
+        if taps is not None:
+            taps.append(h)
+    residual = h + residual if residual is not None else h                 # mamba_blocks.py:196
+    return rmsnorm_fwd(residual, sd[prefix + "norm_f.weight"])             # mamba_blocks.py:197
+
+
+def masknet_fwd(mix_w, sd, n_mamba, n_spk=2, scan_impl="auto", taps=None):
+    """``MaskNet.forward`` (``modules/mamba_masknet.py:101-139``) on channel-last ``mix_w [B,L,N]``;
+    returns the mask ``[n_spk, B, L, N]`` (channel index ``s*N + n``, :126-131; ReLU :136)."""
+    B, L, N = mix_w.shape
+    y = cln_fwd(mix_w, sd["layer_norm.gamma"], sd["layer_norm.beta"])      # :118
+    y = _mm(y, sd["bottleneck_conv1x1.conv.weight"][:, :, 0])             # :121
+    y = mamba_stack_fwd(y, sd, n_mamba, scan_impl=scan_impl, taps=taps)    # :122
+    score = _mm(y, sd["mask_conv1x1.conv.weight"][:, :, 0])               # :123
+    return F.relu(score.reshape(B, L, n_spk, N).permute(2, 0, 1, 3))       # :126-136
+
+
+def decoder_fwd(sep_h, w_dec):
+    """``conv_transpose1d(sep_h, W[N,1,K], stride K//2)`` on channel-last ``[B,L,N]`` -> ``[B,T_est]``
+    (speechbrain ``dual_path.Decoder`` == ``baseline/avse2/model.py:27-37``)."""
+    k = w_dec.shape[-1]
+    return F.conv_transpose1d(sep_h.transpose(1, 2), w_dec, stride=k // 2)[:, 0, :]
+
+
+def separate(mix, sds, n_mamba, n_spk=2, scan_impl="auto", taps=None):
+    """``Separation.compute_forward`` (``Mamba-TasNet/train_wsj0mix.py:86-111``): ``[B,T] -> [B,T,n_spk]``."""
+    mix_w = encoder_fwd(mix, sds["encoder"]["conv1d.weight"])              # :89
+    mask = masknet_fwd(mix_w, sds["masknet"], n_mamba, n_spk, scan_impl, taps)  # :90
+    est = torch.stack([decoder_fwd(mix_w * mask[s], sds["decoder"]["weight"]) for s in range(n_spk)],
+                      dim=-1)                                              # :91-101
+    T, T_est = mix.shape[1], est.shape[1]
+    if T > T_est:                                                          # :104-109
+        est = F.pad(est, (0, 0, 0, T - T_est))
+    else:
+        est = est[:, :T, :]
+    if taps is not None:
+        taps.append(mix_w)
+        taps.append(mask)
+    return est

@@ -1,0 +1,313 @@
+"""GPU (-m gpu): parity of every C-ABI entry point and of the end-to-end separator against the CPU oracle
+(oracle/restate.py) and the golden vectors minted from the real reference.  Everything here calls through
+libmtn_b200.so; nothing reads /root/reference.
+
+Tolerances (north_star): fp32 mode  max|est - ref| <= 1e-3 * rms(ref)  and  |dSI-SNR| <= 0.01 dB.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from avse_challenge_b200 import CONFIGS, init_state_dicts, synth_mixture, pit_si_snr, si_snr
+from avse_challenge_b200 import _lib, ops, modules
+from avse_challenge_b200.engine import SeparatorEngine
+from oracle import restate
+from tests.helpers import load_golden_forward, rel_max, hp_from_sds
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def _planes_value(p):
+    return p.float().sum(0).cpu()
+
+
+# --------------------------------------------------------------------------- planes
+def test_split_planes_precision():
+    x = torch.randn(300, 200, generator=torch.Generator().manual_seed(0)) * 3
+    p2 = ops.split_planes(x.to(DEV), 2)
+    assert ((_planes_value(p2) - x).abs() / x.abs().clamp(min=1e-20)).max() < 2 ** -15
+    p1 = ops.split_planes(x.to(DEV), 1)
+    assert torch.equal(p1[0].cpu(), x.to(torch.bfloat16))
+
+
+# --------------------------------------------------------------------------- tcgen05 GEMM
+@pytest.mark.parametrize("M,N,K,P,groups", [
+    (300, 48, 128, 2, 2), (300, 64, 256, 2, 2), (129, 128, 64, 2, 1), (1000, 256, 256, 2, 1),
+    (517, 512, 128, 2, 1), (260, 1024, 256, 1, 1), (4099, 256, 1024, 2, 1), (300, 64, 64, 1, 1),
+    (40000, 1024, 256, 2, 1),
+])
+def test_gemm_store(M, N, K, P, groups):
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn(M, groups * K, generator=g)
+    w = torch.randn(groups * N, K, generator=g) / K ** 0.5
+    ap, wp = ops.split_planes(a.to(DEV), P), ops.split_planes(w.to(DEV), P)
+    out = ops.gemm(ap, wp, M, N, K, groups=groups, out_group_stride=N if groups > 1 else 0)
+    torch.cuda.synchronize()
+    av, wv = _planes_value(ap).double(), _planes_value(wp).double()
+    ref = torch.cat([av[:, gi * K:(gi + 1) * K] @ wv[gi * N:(gi + 1) * N].t() for gi in range(groups)], dim=1)
+    tol = 2e-5 if P == 2 else 1e-6  # P=2 drops the lo*lo term (2^-18); P=1 is exact up to fp32 accumulation
+    assert rel_max(out.cpu(), ref) < tol
+    # and against the un-rounded fp32 operands: the split-bf16 scheme is fp32-class
+    if P == 2:
+        ref32 = torch.cat([a.double()[:, gi * K:(gi + 1) * K] @ w.double()[gi * N:(gi + 1) * N].t()
+                           for gi in range(groups)], dim=1)
+        assert rel_max(out.cpu(), ref32) < 5e-5
+
+
+def test_gemm_epilogues():
+    g = torch.Generator().manual_seed(7)
+    M, K, di, enc = 391, 128, 128, 128
+    a = torch.randn(M, K, generator=g)
+    w = torch.randn(2 * di, K, generator=g) / K ** 0.5
+    ap, wp = ops.split_planes(a.to(DEV), 2), ops.split_planes(w.to(DEV), 2)
+    ref = (_planes_value(ap).double() @ _planes_value(wp).double().t())
+    # in_proj: SiLU on the z half, fp32 and bf16 outputs
+    exp = ref.clone()
+    exp[:, di:] = torch.nn.functional.silu(exp[:, di:])
+    out = ops.gemm(ap, wp, M, 2 * di, K, epilogue=_lib.EPI_INPROJ, epi_param=di)
+    assert rel_max(out.cpu(), exp) < 2e-5
+    outb = ops.gemm(ap, wp, M, 2 * di, K, epilogue=_lib.EPI_INPROJ, epi_param=di, out_bf16=True)
+    assert outb.dtype == torch.bfloat16 and rel_max(outb.float().cpu(), exp) < 2 ** -7
+    # relu
+    out = ops.gemm(ap, wp, M, 2 * di, K, epilogue=_lib.EPI_RELU)
+    assert rel_max(out.cpu(), ref.clamp(min=0)) < 2e-5
+    # relu(mask) * mix_w, speaker-major columns
+    mixw = torch.rand(M, enc, generator=g)
+    out = ops.gemm(ap, wp, M, 2 * enc, K, epilogue=_lib.EPI_MASK, epi_param=enc, aux=mixw.to(DEV))
+    exp = ref.clamp(min=0) * torch.cat([mixw, mixw], 1).double()
+    assert rel_max(out.cpu(), exp) < 2e-5
+
+
+def test_gemm_rejects_bad_shapes():
+    ap = torch.zeros(2, 128, 64, dtype=torch.bfloat16, device=DEV)
+    wp = torch.zeros(2, 40, 64, dtype=torch.bfloat16, device=DEV)
+    with pytest.raises(_lib.MtnError):
+        ops.gemm(ap, wp, 128, 40, 64)  # N = 40 unsupported
+
+
+# --------------------------------------------------------------------------- streaming kernels
+@pytest.mark.parametrize("N", [64, 128, 256, 512])
+def test_encoder_cln(N):
+    g = torch.Generator().manual_seed(N)
+    B, T = 3, 1600
+    mix = torch.randn(B, T, generator=g) * 0.1
+    w = torch.randn(N, 1, 16, generator=g) * 0.25
+    gamma, beta = torch.randn(N, generator=g), torch.randn(N, generator=g)
+    mix_w, yn = ops.encoder_cln(mix.to(DEV), w.reshape(N, 16).to(DEV), gamma.to(DEV), beta.to(DEV), 2)
+    ref_w = restate.encoder_fwd(mix, w)
+    ref_y = restate.cln_fwd(ref_w, gamma, beta)
+    assert rel_max(mix_w.cpu().view_as(ref_w), ref_w) < 1e-5
+    assert rel_max(_planes_value(yn).view_as(ref_y), ref_y) < 5e-5
+    yn2 = ops.cln(mix_w, gamma.to(DEV), beta.to(DEV), 2)
+    assert rel_max(_planes_value(yn2).view_as(ref_y), ref_y) < 5e-5
+
+
+@pytest.mark.parametrize("D", [64, 128, 256, 512])
+def test_add_rmsnorm(D):
+    g = torch.Generator().manual_seed(D)
+    M = 777
+    h, res, w = torch.randn(M, D, generator=g), torch.randn(M, D, generator=g), torch.randn(D, generator=g)
+    r = res.to(DEV).clone()
+    xn = ops.add_rmsnorm(h.to(DEV), r, True, w.to(DEV), 2)
+    assert rel_max(r.cpu(), h + res) < 1e-6
+    assert rel_max(_planes_value(xn), restate.rmsnorm_fwd(h + res, w)) < 5e-5
+    r = torch.full((M, D), float("nan"), device=DEV)
+    xn = ops.add_rmsnorm(h.to(DEV), r, False, w.to(DEV), 2)  # first block: residual := h
+    assert torch.equal(r.cpu(), h)
+    assert rel_max(_planes_value(xn), restate.rmsnorm_fwd(h, w)) < 5e-5
+
+
+@pytest.mark.parametrize("di,L,dtype", [(128, 77, torch.float32), (512, 1003, torch.float32), (1024, 130, torch.bfloat16)])
+def test_conv_silu_both_directions(di, L, dtype):
+    g = torch.Generator().manual_seed(di + L)
+    B = 2
+    xz = torch.randn(B * L, 2 * di, generator=g).to(dtype)
+    cw = torch.randn(2, di, 4, generator=g) * 0.5
+    cb = torch.randn(2, di, generator=g) * 0.5
+    u = ops.conv_silu(xz.to(DEV), cw.to(DEV), cb.to(DEV), B, L, di, 2)
+    xs = xz.float().view(B, L, 2 * di)[..., :di]
+    ref_f = restate.causal_conv_silu(xs, cw[0].unsqueeze(1), cb[0], reverse=False)
+    ref_b = restate.causal_conv_silu(xs, cw[1].unsqueeze(1), cb[1], reverse=True)
+    got = _planes_value(u).view(B, L, 2 * di)
+    assert rel_max(got[..., :di], ref_f) < 5e-5
+    assert rel_max(got[..., di:], ref_b) < 5e-5
+
+
+@pytest.mark.parametrize("N", [64, 256, 512])
+def test_decoder(N):
+    g = torch.Generator().manual_seed(N)
+    B, L = 2, 123
+    T = (L - 1) * 8 + 16
+    sep = torch.randn(B * L, 2 * N, generator=g)
+    w = torch.randn(N, 1, 16, generator=g) * 0.1
+    for T_out in (T, T + 24, T - 8):  # exact, zero-padded, trimmed (train_wsj0mix.py:104-109)
+        est = ops.decoder(sep.to(DEV), w.reshape(N, 16).to(DEV), B, T_out, L, N, 2).cpu()
+        ref = torch.stack([restate.decoder_fwd(sep.view(B, L, 2 * N)[..., s * N:(s + 1) * N], w) for s in range(2)], -1)
+        ref = torch.nn.functional.pad(ref, (0, 0, 0, max(0, T_out - T)))[:, :T_out]
+        assert rel_max(est, ref) < 1e-5
+
+
+# --------------------------------------------------------------------------- selective scan
+def _scan_case(di, R, L, B, seed, P=2, with_state=False, dir_mask=3):
+    g = torch.Generator().manual_seed(seed)
+    nd = ops.n_dbl_for(R)
+    M = B * L
+    u = torch.randn(2, M, di, generator=g)                      # per direction
+    dbl = torch.randn(M, 2 * nd, generator=g)
+    dbl[:, :R] *= 0.5
+    dbl[:, nd:nd + R] *= 0.5
+    z = torch.randn(M, di, generator=g)
+    w_dt = torch.randn(2, di, R, generator=g) * R ** -0.5
+    dt_bias = torch.randn(2, di, generator=g) * 0.5 - 3.0
+    A = -torch.exp(torch.randn(2, di, 16, generator=g) * 0.5 + 0.5)
+    Dk = torch.randn(2, di, generator=g)
+    h_in = torch.randn(2, B, di, 16, generator=g) if with_state else None
+    # device inputs: u as planes [P, M, 2di]; z pre-activated inside a wider [M, 2di] buffer at column di
+    u_cat = torch.cat([u[0], u[1]], dim=1)
+    up = ops.split_planes(u_cat.to(DEV), P)
+    zbuf = torch.zeros(M, 2 * di)
+    zbuf[:, di:] = torch.nn.functional.silu(z)
+    h_out = torch.zeros(2, B, di, 16, device=DEV) if with_state else None
+    y = ops.scan(up, dbl.to(DEV), zbuf.to(DEV), di, w_dt.to(DEV), dt_bias.to(DEV), (A * ops.LOG2E).to(DEV),
+                 Dk.to(DEV), B, L, di, R, h_in=h_in.to(DEV) if with_state else None, h_out=h_out, dir_mask=dir_mask)
+    torch.cuda.synchronize()
+    yv = _planes_value(y).view(B, L, 2 * di)
+    uv = _planes_value(up).view(B, L, 2 * di)                   # the values the kernel actually saw
+    res = []
+    for d in range(2):
+        if not (dir_mask >> d) & 1:
+            continue
+        ud = uv[..., d * di:(d + 1) * di].contiguous()
+        dd = dbl.view(B, L, 2 * nd)[..., d * nd:(d + 1) * nd]
+        delta_pre = dd[..., :R] @ w_dt[d].t()
+        ref, hl = restate.selective_scan(ud, delta_pre, A[d], dd[..., R:R + 16].contiguous(),
+                                         dd[..., R + 16:R + 32].contiguous(), Dk[d], z.view(B, L, di), dt_bias[d],
+                                         reverse=(d == 1), h_in=h_in[d] if with_state else None, impl="c")
+        res.append((rel_max(yv[..., d * di:(d + 1) * di], 0.5 * ref),
+                    rel_max(h_out[d].cpu(), hl) if with_state else 0.0))
+    return res
+
+
+@pytest.mark.parametrize("di,R,L,B", [(128, 4, 157, 2), (256, 8, 1003, 2), (512, 16, 3999, 1), (1024, 32, 333, 2)])
+def test_scan_matches_selective_scan_ref(di, R, L, B):
+    for err, _ in _scan_case(di, R, L, B, seed=di + L):
+        assert err < 1e-4, err  # fp32 state; u/y are split-bf16 (2^-17), exp/softplus via ex2/lg2.approx
+
+
+def test_scan_initial_and_final_state():
+    for err, herr in _scan_case(256, 8, 210, 3, seed=5, with_state=True):
+        assert err < 1e-4 and herr < 1e-4
+
+
+def test_scan_single_direction_launches():
+    (e0, _), = _scan_case(128, 4, 100, 2, seed=9, dir_mask=1)
+    (e1, _), = _scan_case(128, 4, 100, 2, seed=9, dir_mask=2)
+    assert e0 < 1e-4 and e1 < 1e-4
+
+
+def test_scan_bf16_mode():
+    for err, _ in _scan_case(256, 16, 500, 2, seed=11, P=1):
+        assert err < 1e-2  # single bf16 plane for u / y (2^-9 rounding of the output)
+
+
+# --------------------------------------------------------------------------- end to end
+def _gate(est, ref, src):
+    err = rel_max(est, ref)
+    d_sisnr = (pit_si_snr(est, src) - pit_si_snr(ref, src)).abs().max().item()
+    fidelity = si_snr(est, ref).min().item()
+    return err, d_sisnr, fidelity
+
+
+@pytest.mark.parametrize("tag", ["tiny_refinit", "tiny_trained"])
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_end_to_end_matches_reference_golden(golden_dir, tag, use_graph):
+    sds, g, taps = load_golden_forward(os.path.join(golden_dir, f"forward_{tag}.npz"))
+    hp = hp_from_sds(sds)
+    sep = modules.MambaTasNetSeparator.from_hparams(hp, mode="fp32", use_graph=use_graph)
+    sep.load_reference_state_dicts(sds, strict=True).to(DEV)
+    est = sep(g["mix"].to(DEV)).cpu()
+    est2 = sep(g["mix"].to(DEV)).cpu()
+    assert torch.equal(est, est2)  # deterministic; graph replay == first run
+    err, d_sisnr, fid = _gate(est, g["est"], g["src"])
+    assert err <= 1e-3 and d_sisnr <= 0.01, (err, d_sisnr, fid)
+    assert fid > 60.0
+
+
+def test_standalone_modules_follow_compute_forward(golden_dir):
+    """The reference's own call sequence (train_wsj0mix.py:86-111) on the three drop-in modules."""
+    sds, g, taps = load_golden_forward(os.path.join(golden_dir, "forward_tiny_trained.npz"))
+    hp = hp_from_sds(sds)
+    sep = modules.MambaTasNetSeparator.from_hparams(hp, mode="fp32")
+    sep.load_reference_state_dicts(sds).to(DEV)
+    Encoder, MaskNet, Decoder = sep.encoder, sep.masknet, sep.decoder
+    mix = g["mix"].to(DEV)
+    mix_w = Encoder(mix)
+    est_mask = MaskNet(mix_w)
+    assert rel_max(mix_w.cpu(), g["mix_w"]) < 1e-5
+    assert rel_max(est_mask.cpu(), g["est_mask"]) < 1e-3
+    mix_w = torch.stack([mix_w] * 2)
+    sep_h = mix_w * est_mask
+    est_source = torch.cat([Decoder(sep_h[i]).unsqueeze(-1) for i in range(2)], dim=-1)
+    T_origin, T_est = mix.size(1), est_source.size(1)
+    if T_origin > T_est:
+        est_source = torch.nn.functional.pad(est_source, (0, 0, 0, T_origin - T_est))
+    else:
+        est_source = est_source[:, :T_origin, :]
+    err, d_sisnr, _ = _gate(est_source.cpu(), g["est"], g["src"])
+    assert err <= 1e-3 and d_sisnr <= 0.01
+
+
+@pytest.mark.parametrize("name,B,T", [("XS", 2, 8000), ("S", 2, 32000), ("L", 1, 8000)])
+def test_end_to_end_vs_oracle_shipped_configs(name, B, T):
+    """Shipped hparams (S at BASELINE config-1/2 length: 4 s @ 8 kHz, L = 3999) against the CPU oracle."""
+    hp = CONFIGS[name]
+    sds = init_state_dicts(hp, 1234)
+    mix, src = synth_mixture(B, T, seed=1234)
+    with torch.no_grad():
+        ref = restate.separate(mix, sds, hp.n_mamba, scan_impl="c")
+    eng = SeparatorEngine(hp, sds, device=DEV, mode="fp32", use_graph=False)
+    est = eng(mix.to(DEV)).cpu()
+    err, d_sisnr, fid = _gate(est, ref, src)
+    print(f"{name}: max-abs/rms {err:.3e}  dSI-SNR {d_sisnr:.2e} dB  SI-SNR(est,ref) {fid:.1f} dB")
+    assert err <= 1e-3 and d_sisnr <= 0.01, (err, d_sisnr, fid)
+
+
+def test_bf16_mode_stated_tolerance():
+    """bf16 mode (config 3): bf16 GEMM operands and bf16 xz/u/y storage, fp32 scan state and residual stream.
+    Stated tolerance against the fp32 oracle: max-abs <= 0.15 * rms and SI-SNR(est, ref) >= 25 dB."""
+    hp = CONFIGS["S"]
+    sds = init_state_dicts(hp, 1234)
+    mix, src = synth_mixture(2, 8000, seed=7)
+    with torch.no_grad():
+        ref = restate.separate(mix, sds, hp.n_mamba, scan_impl="c")
+    eng = SeparatorEngine(hp, sds, device=DEV, mode="bf16", use_graph=False)
+    est = eng(mix.to(DEV)).cpu()
+    err, d_sisnr, fid = _gate(est, ref, src)
+    print(f"bf16 S: max-abs/rms {err:.3e}  dSI-SNR {d_sisnr:.2e} dB  SI-SNR(est,ref) {fid:.1f} dB")
+    assert err <= 0.15 and fid >= 25.0, (err, fid)
+
+
+def test_full_size_config2_properties():
+    """BASELINE config 2 (S, 32 x 4 s @ 8 kHz) at full size through size-independent properties:
+    (a) batch independence: utterance i of the batch of 32 == the same utterance run alone (bit-exact),
+    (b) silence in -> silence out, (c) two utterances of the batch against the oracle."""
+    hp = CONFIGS["S"]
+    sds = init_state_dicts(hp, 1234)
+    B, T = 32, 32000
+    mix, src = synth_mixture(B, T, seed=1234)
+    mix[5] = 0.0
+    eng = SeparatorEngine(hp, sds, device=DEV, mode="fp32", use_graph=True)
+    est = eng(mix.to(DEV)).cpu()
+    assert torch.isfinite(est).all()
+    assert est[5].abs().max() == 0.0
+    for i in (0, 17, 31):
+        alone = eng(mix[i:i + 1].to(DEV)).cpu()
+        assert torch.equal(alone[0], est[i]), i
+    with torch.no_grad():
+        ref = restate.separate(mix[[3, 30]], sds, hp.n_mamba, scan_impl="c")
+    err, d_sisnr, fid = _gate(est[[3, 30]], ref, src[[3, 30]])
+    assert err <= 1e-3 and d_sisnr <= 0.01, (err, d_sisnr, fid)

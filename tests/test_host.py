@@ -1,0 +1,107 @@
+"""CPU: host-side logic -- state_dict contract, hparams, synthetic data, C-ABI exports (no GPU compute)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from avse_challenge_b200 import CONFIGS, init_state_dicts, synth_mixture, pit_si_snr
+from avse_challenge_b200 import modules, _lib
+from tests.helpers import load_golden_forward, hp_from_sds
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("name,params", [("XS", 2210176), ("S", 7926528), ("M", 15647488), ("L", 58951168)])
+def test_param_counts_match_reference(name, params):
+    hp = CONFIGS[name]
+    sep = modules.MambaTasNetSeparator.from_hparams(hp)
+    n = sum(p.numel() for p in sep.masknet.parameters())
+    n += sum(p.numel() for p in sep.encoder.parameters()) + sum(p.numel() for p in sep.decoder.parameters())
+    assert n == params  # SURVEY.md section 0 (probe counts of the reference modules)
+
+
+@pytest.mark.parametrize("tag", ["tiny_refinit", "tiny_trained"])
+def test_reference_state_dict_loads_strict(golden_dir, tag):
+    sds, _, _ = load_golden_forward(os.path.join(golden_dir, f"forward_{tag}.npz"))
+    hp = hp_from_sds(sds)
+    sep = modules.MambaTasNetSeparator.from_hparams(hp)
+    sep.load_reference_state_dicts(sds, strict=True)
+    for grp, mod in (("encoder", sep.encoder), ("masknet", sep.masknet), ("decoder", sep.decoder)):
+        mine = mod.state_dict()
+        assert set(mine) == set(sds[grp])
+        for k, v in sds[grp].items():
+            assert mine[k].shape == v.shape, k
+            assert torch.equal(mine[k], v), k
+
+
+def test_init_state_dicts_has_reference_keys():
+    hp = CONFIGS["tiny"]
+    sds = init_state_dicts(hp, 3)
+    sep = modules.MambaTasNetSeparator.from_hparams(hp)
+    sep.load_reference_state_dicts(sds, strict=True)
+
+
+@pytest.mark.parametrize("kw", [dict(mask_nonlinear="softmax"), dict(bidirectional=False), dict(d_state=8),
+                                dict(d_conv=3), dict(rms_norm=False), dict(n_spk=3)])
+def test_unsupported_options_raise(kw):
+    with pytest.raises(NotImplementedError):
+        modules.MaskNet(64, 64, n_mamba=1, d_model=64, **kw)
+
+
+def test_no_cpu_fallback():
+    hp = CONFIGS["tiny"]
+    sep = modules.MambaTasNetSeparator.from_hparams(hp)
+    if torch.cuda.is_available():
+        pytest.skip("checks the no-GPU failure mode")
+    with pytest.raises(_lib.MtnError):
+        sep(torch.zeros(1, 160))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "avse_challenge_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f
+                assert "oracle/" not in src and "selscan_ref" not in src, f
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    header = open(os.path.join(ROOT, "include", "mtn_b200.h")).read()
+    declared = set(re.findall(r"\b(mtn_[a-z0-9_]+)\s*\(", header))
+    declared -= {"mtn_stream_t"}
+    assert declared == set(_lib.EXPORTS)
+    lib = ctypes.CDLL(built_lib)
+    for name in declared:
+        assert hasattr(lib, name), name
+    lib.mtn_abi_version.restype = ctypes.c_int
+    assert lib.mtn_abi_version() >= 1
+
+
+def test_struct_layouts_match_header(built_lib):
+    """ctypes Structures must mirror the C structs field for field."""
+    header = open(os.path.join(ROOT, "include", "mtn_b200.h")).read()
+    for cname, cls in (("mtn_gemm_args", _lib.GemmArgs), ("mtn_scan_args", _lib.ScanArgs)):
+        body = re.search(r"typedef struct \{([^}]*)\} " + cname + ";", header).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        names = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            decl = re.sub(r"^(const\s+)?(void|float|int)\s*\*?\s*", "", decl)
+            names += [n.strip().lstrip("*").strip() for n in decl.split(",")]
+        assert names == [f[0] for f in cls._fields_], cname
+
+
+def test_synth_is_deterministic_and_scaled():
+    mix, src = synth_mixture(2, 4000, seed=5)
+    mix2, _ = synth_mixture(2, 4000, seed=5)
+    assert torch.equal(mix, mix2)
+    assert torch.allclose(src.pow(2).mean(dim=1).sqrt(), torch.full((2, 2), 0.05), rtol=1e-3)
+    assert torch.allclose(mix, src.sum(-1))
+    s = pit_si_snr(src.flip(-1) * 1.7, src)
+    assert (s > 60).all()

@@ -1,0 +1,81 @@
+"""CPU: the oracle restatement is pinned against outputs of the REAL reference (tests/golden/*.npz, minted by
+oracle/make_golden.py from /root/reference under leaf shims -- the reference ships no tests of its own)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import restate
+from tests.helpers import load_golden_forward, rel_max, hp_from_sds
+
+
+def test_scan_restatement_matches_reference_selective_scan_ref(golden_dir):
+    z = np.load(os.path.join(golden_dir, "scan_ref.npz"))
+    t = lambda k: torch.from_numpy(z[k])
+    # reference layout [B, D, L] / [B, N, L]  ->  channel-last
+    u, delta, zz = (t(k).transpose(1, 2).contiguous() for k in ("u", "delta", "z"))
+    Bm, Cm = (t(k).transpose(1, 2).contiguous() for k in ("B", "C"))
+    for impl in ("torch", "c"):
+        out, last = restate.selective_scan(u, delta, t("A"), Bm, Cm, t("D"), zz, t("bias"), impl=impl)
+        assert rel_max(out.transpose(1, 2), t("out")) < 2e-6, impl
+        assert rel_max(last, t("last_state")) < 2e-6, impl
+        out_ng, _ = restate.selective_scan(u, delta, t("A"), Bm, Cm, t("D"), None, t("bias"), impl=impl, gate=False)
+        assert rel_max(out_ng.transpose(1, 2), t("out_nogate")) < 2e-6, impl
+        out_r, _ = restate.selective_scan(u, delta, t("A"), Bm, Cm, t("D"), zz, t("bias"), reverse=True, impl=impl)
+        assert rel_max(out_r.transpose(1, 2), t("out_reverse")) < 2e-6, impl
+
+
+def test_scan_chunk_carry_equals_one_shot(golden_dir):
+    z = np.load(os.path.join(golden_dir, "scan_ref.npz"))
+    t = lambda k: torch.from_numpy(z[k])
+    u, delta, zz = (t(k).transpose(1, 2).contiguous() for k in ("u", "delta", "z"))
+    Bm, Cm = (t(k).transpose(1, 2).contiguous() for k in ("B", "C"))
+    full, last = restate.selective_scan(u, delta, t("A"), Bm, Cm, t("D"), zz, t("bias"), impl="c")
+    cut = 61
+    a, ha = restate.selective_scan(u[:, :cut], delta[:, :cut], t("A"), Bm[:, :cut], Cm[:, :cut], t("D"), zz[:, :cut],
+                                   t("bias"), impl="c")
+    b, hb = restate.selective_scan(u[:, cut:], delta[:, cut:], t("A"), Bm[:, cut:], Cm[:, cut:], t("D"), zz[:, cut:],
+                                   t("bias"), impl="c", h_in=ha)
+    assert torch.equal(torch.cat([a, b], 1), full)
+    assert torch.equal(hb, last)
+
+
+@pytest.mark.parametrize("tag", ["tiny_refinit", "tiny_trained"])
+def test_forward_restatement_matches_reference(golden_dir, tag):
+    sds, g, taps = load_golden_forward(os.path.join(golden_dir, f"forward_{tag}.npz"))
+    hp = hp_from_sds(sds)
+    my_taps = []
+    with torch.no_grad():
+        est = restate.separate(g["mix"], sds, hp.n_mamba, scan_impl="c", taps=my_taps)
+    assert est.shape == g["est"].shape
+    assert rel_max(est, g["est"]) < 1e-5
+    mask, mix_w = my_taps[-1], my_taps[-2]
+    assert rel_max(mix_w.transpose(1, 2), g["mix_w"]) < 1e-5           # reference layout [B, N, L]
+    assert rel_max(mask.permute(0, 1, 3, 2), g["est_mask"]) < 1e-5     # reference layout [spk, B, N, L]
+    assert rel_max(my_taps[0], taps["mixer0_out"]) < 1e-5
+
+
+def test_torch_loop_scan_equals_c_scan(golden_dir):
+    sds, g, _ = load_golden_forward(os.path.join(golden_dir, "forward_tiny_trained.npz"))
+    hp = hp_from_sds(sds)
+    with torch.no_grad():
+        a = restate.separate(g["mix"][:1, :400], sds, hp.n_mamba, scan_impl="torch")
+        b = restate.separate(g["mix"][:1, :400], sds, hp.n_mamba, scan_impl="c")
+    assert rel_max(a, b) < 1e-5
+
+
+def test_gemm_rounding_models_are_ordered(golden_dir):
+    """bf16x3 (what the CUDA fp32 mode computes) must sit far inside the 1e-3 gate; plain tf32/bf16 do not."""
+    sds, g, _ = load_golden_forward(os.path.join(golden_dir, "forward_tiny_trained.npz"))
+    hp = hp_from_sds(sds)
+    errs = {}
+    try:
+        with torch.no_grad():
+            ref = restate.separate(g["mix"], sds, hp.n_mamba)
+            for mode in ("bf16x3", "tf32", "bf16"):
+                restate.set_gemm_mode(mode)
+                errs[mode] = rel_max(restate.separate(g["mix"], sds, hp.n_mamba), ref)
+    finally:
+        restate.set_gemm_mode("fp32")
+    assert errs["bf16x3"] < 1e-4 < errs["tf32"] < errs["bf16"]
