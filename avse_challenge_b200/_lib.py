@@ -58,7 +58,7 @@ def load():
     lib.mtn_last_error_string.restype = c_char_p
     lib.mtn_last_error_string.argtypes = []
     lib.mtn_abi_version.restype = c_int
-    lib.mtn_encoder_cln_fwd.argtypes = [c_void_p] * 6 + [c_int] * 5 + [c_float, c_void_p]
+    lib.mtn_encoder_cln_fwd.argtypes = [c_void_p, c_int] + [c_void_p] * 5 + [c_int] * 5 + [c_float, c_void_p]
     lib.mtn_gemm_fwd.argtypes = [POINTER(GemmArgs), c_void_p]
     lib.mtn_add_rmsnorm_fwd.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_float,
                                         c_void_p]

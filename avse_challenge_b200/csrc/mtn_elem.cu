@@ -61,7 +61,7 @@ template <int P, int NJ>  // NJ = N / 32 channels per lane
 __global__ void __launch_bounds__(256)
 encoder_cln_kernel(const float* __restrict__ mix, const float* __restrict__ w_enc, const float* __restrict__ gamma,
                    const float* __restrict__ beta, float* __restrict__ mix_w, __nv_bfloat16* __restrict__ yn, int batch,
-                   int T, int L, float eps) {
+                   int ld_mix, int L, float eps) {
     constexpr int N = NJ * 32;
     extern __shared__ float s_w[];  // [16][N] transposed filter bank
     for (int i = threadIdx.x; i < 16 * N; i += blockDim.x) {
@@ -82,7 +82,7 @@ encoder_cln_kernel(const float* __restrict__ mix, const float* __restrict__ w_en
     for (size_t tok = size_t(blockIdx.x) * warps_per_block + (threadIdx.x >> 5); tok < tokens;
          tok += size_t(gridDim.x) * warps_per_block) {
         const int b = int(tok / L), l = int(tok % L);
-        const float4* xp = reinterpret_cast<const float4*>(mix + size_t(b) * T + size_t(l) * 8);
+        const float4* xp = reinterpret_cast<const float4*>(mix + size_t(b) * ld_mix + size_t(l) * 8);
         float x[16];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -392,13 +392,13 @@ static int grid_for(size_t items, int per_block, int waves = 8) {
 
 using namespace mtn;
 
-extern "C" int mtn_encoder_cln_fwd(const float* mix, const float* w_enc, const float* gamma, const float* beta,
-                                   float* mix_w, void* yn_planes, int batch, int T, int L, int N, int planes, float eps,
-                                   mtn_stream_t stream) {
+extern "C" int mtn_encoder_cln_fwd(const float* mix, int ld_mix, const float* w_enc, const float* gamma,
+                                   const float* beta, float* mix_w, void* yn_planes, int batch, int T, int L, int N,
+                                   int planes, float eps, mtn_stream_t stream) {
     MTN_REQUIRE(mix && w_enc && gamma && beta && mix_w && yn_planes, "encoder: null pointer");
     MTN_REQUIRE(batch > 0 && T >= 16 && L == (T - 16) / 8 + 1, "encoder: bad shape batch=%d T=%d L=%d", batch, T, L);
-    MTN_REQUIRE(T % 4 == 0 && (reinterpret_cast<uintptr_t>(mix) & 15) == 0,
-                "encoder: T must be a multiple of 4 and mix 16-byte aligned (128-bit frame loads)");
+    MTN_REQUIRE(ld_mix >= T && ld_mix % 4 == 0 && (reinterpret_cast<uintptr_t>(mix) & 15) == 0,
+                "encoder: ld_mix must be >= T and a multiple of 4, mix 16-byte aligned (128-bit frame loads)");
     MTN_REQUIRE(planes == 1 || planes == 2, "encoder: planes=%d", planes);
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     const size_t tokens = size_t(batch) * L;
@@ -409,7 +409,7 @@ extern "C" int mtn_encoder_cln_fwd(const float* mix, const float* w_enc, const f
         auto k = encoder_cln_kernel<PP, NJ>;                                                                     \
         if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
         k<<<grid, 256, smem, s>>>(mix, w_enc, gamma, beta, mix_w, reinterpret_cast<__nv_bfloat16*>(yn_planes),  \
-                                  batch, T, L, eps);                                                             \
+                                  batch, ld_mix, L, eps);                                                           \
     } while (0)
 #define MTN_ENC_N(PP)                                                         \
     switch (N) {                                                              \

@@ -78,7 +78,7 @@ class Workspace:
         nd = n_dbl_for(hp.dt_rank)
         e = lambda shape, dt: torch.empty(shape, dtype=dt, device=device)
         self.batch, self.T, self.L, self.M = batch, T, L, M
-        self.mix = e((batch, T), torch.float32)
+        self.mix = torch.zeros((batch, (T + 7) // 8 * 8), dtype=torch.float32, device=device)  # pitched rows
         self.mix_w = e((M, N), torch.float32)
         self.yn = e((P, M, N), torch.bfloat16)
         self.h = e((M, D), torch.float32)
@@ -111,6 +111,7 @@ class SeparatorEngine:
             self.w = PackedWeights(hp, sds, self.device, mode)
         self._ws = {}
         self._graphs = {}
+        self._prof = None
         self.launches_per_forward = 2 + 1 + hp.n_mamba * 6 + 2 + 2  # enc, bottleneck, layers, norm_f+mask, decoder(2)
 
     # ------------------------------------------------------------------ building blocks
@@ -120,30 +121,64 @@ class SeparatorEngine:
             self._ws[key] = Workspace(self.hp, batch, T, self.device, self.mode)
         return self._ws[key]
 
+    def _op(self, name, fn, *a, **k):
+        """Launch one kernel; when a profiler is attached, bracket it with CUDA events on the launch stream."""
+        prof = self._prof
+        if prof is None:
+            return fn(*a, **k)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = fn(*a, **k)
+        e1.record()
+        prof.append((name, e0, e1))
+        return out
+
     def _layer(self, ws: Workspace, lw: dict, first: bool, taps=None):
         hp, P = self.hp, self.w.P
         D, di, R, nd, M = hp.d_model, hp.d_inner, hp.dt_rank, self.w.n_dbl, ws.M
-        ops.add_rmsnorm(ws.h, ws.res, not first, lw["norm"], P, xn=ws.xn)
-        ops.gemm(ws.xn, lw["w_in"], M, 2 * di, D, out=ws.xz, epilogue=_lib.EPI_INPROJ, epi_param=di,
-                 out_bf16=ws.xz.dtype == torch.bfloat16)
-        ops.conv_silu(ws.xz, lw["conv_w"], lw["conv_b"], ws.batch, ws.L, di, P, u=ws.u)
-        ops.gemm(ws.u, lw["w_x"], M, nd, di, out=ws.dbl, groups=2, out_group_stride=nd)
-        ops.scan(ws.u, ws.dbl, ws.xz, di, lw["w_dt"], lw["dt_bias"], lw["A2"], lw["D"], ws.batch, ws.L, di, R, y=ws.y)
-        ops.gemm(ws.y, lw["w_out"], M, D, 2 * di, out=ws.h)
+        op = self._op
+        op("add_rmsnorm", ops.add_rmsnorm, ws.h, ws.res, not first, lw["norm"], P, xn=ws.xn)
+        op("gemm_in_proj", ops.gemm, ws.xn, lw["w_in"], M, 2 * di, D, out=ws.xz, epilogue=_lib.EPI_INPROJ, epi_param=di,
+           out_bf16=ws.xz.dtype == torch.bfloat16)
+        op("conv_silu", ops.conv_silu, ws.xz, lw["conv_w"], lw["conv_b"], ws.batch, ws.L, di, P, u=ws.u)
+        op("gemm_x_proj", ops.gemm, ws.u, lw["w_x"], M, nd, di, out=ws.dbl, groups=2, out_group_stride=nd)
+        op("scan", ops.scan, ws.u, ws.dbl, ws.xz, di, lw["w_dt"], lw["dt_bias"], lw["A2"], lw["D"], ws.batch, ws.L, di, R,
+           y=ws.y)
+        op("gemm_out_proj", ops.gemm, ws.y, lw["w_out"], M, D, 2 * di, out=ws.h)
         if taps is not None:
             taps.append(ws.h.clone())
 
     def _run(self, ws: Workspace, taps=None):
         hp, w, P = self.hp, self.w, self.w.P
         N, D, M = hp.enc_dim, hp.d_model, ws.M
-        ops.encoder_cln(ws.mix, w.w_enc, w.gamma, w.beta, P, mix_w=ws.mix_w, yn=ws.yn)
-        ops.gemm(ws.yn, w.w_bot, M, D, N, out=ws.h)
+        op = self._op
+        op("encoder_cln", ops.encoder_cln, ws.mix, w.w_enc, w.gamma, w.beta, P, mix_w=ws.mix_w, yn=ws.yn, T=ws.T)
+        op("gemm_bottleneck", ops.gemm, ws.yn, w.w_bot, M, D, N, out=ws.h)
         for i, lw in enumerate(w.layers):
             self._layer(ws, lw, first=(i == 0), taps=taps)
-        ops.add_rmsnorm(ws.h, ws.res, True, w.norm_f, P, xn=ws.xn)
-        ops.gemm(ws.xn, w.w_mask, M, hp.n_spk * N, D, out=ws.sep, epilogue=_lib.EPI_MASK, epi_param=N, aux=ws.mix_w)
-        ops.decoder(ws.sep, w.w_dec, ws.batch, ws.T, ws.L, N, hp.n_spk, est=ws.est, frames=ws.frames)
+        op("add_rmsnorm", ops.add_rmsnorm, ws.h, ws.res, True, w.norm_f, P, xn=ws.xn)
+        op("gemm_mask", ops.gemm, ws.xn, w.w_mask, M, hp.n_spk * N, D, out=ws.sep, epilogue=_lib.EPI_MASK, epi_param=N,
+           aux=ws.mix_w)
+        op("decoder", ops.decoder, ws.sep, w.w_dec, ws.batch, ws.T, ws.L, N, hp.n_spk, est=ws.est, frames=ws.frames)
         return ws.est
+
+    def profile_ops(self, batch: int, T: int, steps: int = 1):
+        """Eager (no graph) run with CUDA events around every kernel launch, on the launch stream.
+        Returns {op name: {"launches": n per forward, "ms": mean ms per launch, "ms_per_forward": ...}}."""
+        ws = self.workspace(batch, T)
+        agg = {}
+        for _ in range(steps):
+            self._prof = []
+            try:
+                self._run(ws)
+                torch.cuda.current_stream().synchronize()
+                for name, e0, e1 in self._prof:
+                    a = agg.setdefault(name, [0, 0.0])
+                    a[0] += 1
+                    a[1] += e0.elapsed_time(e1)
+            finally:
+                self._prof = None
+        return {k: {"launches": n // steps, "ms": t / n, "ms_per_forward": t / steps} for k, (n, t) in agg.items()}
 
     # ------------------------------------------------------------------ public API
     @torch.no_grad()
@@ -152,10 +187,10 @@ class SeparatorEngine:
         if mix.dim() != 2 or mix.dtype != torch.float32 or not mix.is_cuda:
             raise _lib.MtnError("forward expects a CUDA fp32 tensor of shape [batch, T]")
         B, T = mix.shape
-        if T % 8 != 0 or T < 16:
-            raise _lib.MtnError(f"T={T}: need T >= 16 and T % 8 == 0 (stride-8 framing with 128-bit loads)")
+        if T < 16:
+            raise _lib.MtnError(f"T={T}: need at least one 16-sample frame")
         ws = self.workspace(B, T)
-        ws.mix.copy_(mix, non_blocking=True)
+        ws.mix[:, :T].copy_(mix, non_blocking=True)
         if taps is not None or not self.use_graph:
             return self._run(ws, taps).clone()
         key = (B, T)

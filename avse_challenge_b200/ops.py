@@ -47,17 +47,24 @@ def planes_to_float(p: torch.Tensor) -> torch.Tensor:
     return p.float().sum(dim=0)
 
 
-def encoder_cln(mix, w_enc, gamma, beta, planes, eps=1e-8, mix_w=None, yn=None):
+def encoder_cln(mix, w_enc, gamma, beta, planes, eps=1e-8, mix_w=None, yn=None, T=None):
+    """mix [B, ld] fp32 (row stride a multiple of 4 floats; ``T`` = valid samples per row, default ld)."""
     _req_cuda(mix, w_enc)
-    B, T = mix.shape
+    B = mix.shape[0]
+    if T is None:
+        T = mix.shape[1]
+    if mix.stride(0) % 4 != 0 or mix.stride(1) != 1 or mix.data_ptr() % 16 != 0:  # re-pitch for 128-bit frame loads
+        padded = torch.zeros((B, (T + 3) // 4 * 4), dtype=torch.float32, device=mix.device)
+        padded[:, :T] = mix[:, :T]
+        mix = padded
     N = w_enc.shape[0]
     L = (T - 16) // 8 + 1
     if mix_w is None:
         mix_w = torch.empty((B * L, N), dtype=torch.float32, device=mix.device)
     if yn is None:
         yn = torch.empty((planes, B * L, N), dtype=torch.bfloat16, device=mix.device)
-    check(_lib.load().mtn_encoder_cln_fwd(ptr(mix), ptr(w_enc), ptr(gamma), ptr(beta), ptr(mix_w), ptr(yn), B, T, L, N,
-                                          planes, eps, _stream()), "mtn_encoder_cln_fwd")
+    check(_lib.load().mtn_encoder_cln_fwd(ptr(mix), mix.stride(0), ptr(w_enc), ptr(gamma), ptr(beta), ptr(mix_w), ptr(yn),
+                                          B, T, L, N, planes, eps, _stream()), "mtn_encoder_cln_fwd")
     return mix_w, yn
 
 

@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""Benchmark of the Mamba-TasNet separator forward on B200 (BASELINE.json metric: audio-seconds separated per
+wall-second; selective-scan HBM GB/s against the measured roofline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--hparams S] [--batch 32] [--mode fp32]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+A "step" = one forward of the whole separator over one batch of synthetic mixtures.  Default workload =
+BASELINE config 2: S hparams, 32 x 4 s @ 8 kHz per GPU, fp32 mode.  N > 1: one process per GPU, each rank separates
+its own batch (utterances are independent: batch sharding, no collective on the data path; weak scaling).
+
+One JSON line on rank 0:
+  value      whole-job audio-s/s, inputs resident in HBM, CUDA-graph replay, device-timed, max over ranks
+  e2e        same metric through the public API with HOST buffers (pinned H2D of the mixtures + D2H of the estimates
+             inside the timed region)
+  roofline   selective-scan kernel: algorithmic bytes (SURVEY.md 8d / DESIGN.md) / mean launch time measured here
+             with CUDA events on the launch stream, vs MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the oracle port of the reference CPU path (torch loop selective_scan_ref), bounded sample, N=1 only
+--impl reference times that CPU path alone (the reference is Python and needs /root/reference + third-party
+packages that are absent on the GPU box; the oracle port is the same algorithm, see oracle/restate.py).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "audio_seconds_per_second"
+UNIT = "audio-s/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--hparams", default="S", choices=["XS", "S", "M", "L"])
+    ap.add_argument("--batch", type=int, default=32, help="utterances per GPU")
+    ap.add_argument("--seconds", type=float, default=4.0)
+    ap.add_argument("--sample-rate", type=int, default=8000)
+    ap.add_argument("--mode", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(a, n_gpus):
+    return {
+        "workload": (f"BASELINE config 2: Mamba-TasNet {a.hparams} hparams, {a.batch} x {a.seconds:g} s @ "
+                     f"{a.sample_rate // 1000} kHz 2-speaker mixtures per GPU, {a.mode} mode "
+                     + ("(split-bf16 x3 tcgen05 GEMMs, fp32 scan state)" if a.mode == "fp32"
+                        else "(bf16 tcgen05 GEMMs + bf16 activations, fp32 scan state)")),
+        "hparams": a.hparams, "batch_per_gpu": a.batch, "global_batch": a.batch * n_gpus, "seconds": a.seconds,
+        "sample_rate": a.sample_rate, "mode": a.mode,
+        "parallelism": f"batch-sharded x{n_gpus}, no collective on the data path",
+        "l2": "no flush needed: every step streams >3 GB of activations per layer group, far larger than the 126 MB L2",
+    }
+
+
+# ------------------------------------------------------------------------------------------ CPU reference arm
+def cpu_reference_throughput(hparams: str, sample_rate: int, steps: int, warmup: int, budget_s: float):
+    """Time the oracle port of the reference's CPU forward (selective_scan_ref = per-step torch loop,
+    Mamba-TasNet/modules/mamba/selective_scan_interface.py:91-157) on a bounded sample of the workload."""
+    import torch
+    from avse_challenge_b200 import CONFIGS, init_state_dicts, synth_mixture
+    from oracle import restate
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    hp = CONFIGS[hparams]
+    sds = init_state_dicts(hp, 1234)
+
+    def run(seconds):
+        T = int(round(seconds * sample_rate)) // 8 * 8
+        mix, _ = synth_mixture(1, T, sample_rate, seed=1234)
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            restate.separate(mix, sds, hp.n_mamba, scan_impl="torch")
+        return time.perf_counter() - t0, T / sample_rate
+
+    # calibrate on a very short clip, then pick the longest sample that keeps (steps + warmup) inside the budget
+    t_cal, s_cal = run(0.125)
+    per_audio_s = t_cal / s_cal
+    n = max(1, steps + warmup)
+    seconds = 4.0
+    while seconds > 0.125 and per_audio_s * seconds * n > budget_s:
+        seconds /= 2
+    for _ in range(warmup):
+        run(seconds)
+    times = []
+    for _ in range(max(1, steps)):
+        t, s = run(seconds)
+        times.append(t)
+    dt = sum(times) / len(times)
+    return {"value": s / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"1 utterance x {seconds:g} s @ {sample_rate} Hz, {hparams} hparams, fp32, torch {torch.get_num_threads()} threads, "
+                      f"{len(times)} timed run(s) of {dt:.2f} s"}, dt
+
+
+def run_reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    base, dt = cpu_reference_throughput(a.hparams, a.sample_rate, a.steps, a.warmup, budget_s=150.0)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": a.gpus,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(a, a.gpus),
+        "cpu_baseline": base,
+        "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,utilization.gpu,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.FIELDS}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for row in self.f.read().splitlines():
+            c = [x.strip() for x in row.split(",")]
+            if len(c) < 8:
+                continue
+            try:
+                clk, mx, util = float(c[0]), float(c[1]), float(c[3])
+            except ValueError:
+                continue
+            smax.append(mx)
+            if util >= 50:
+                sm.append(clk)
+                for n, v in zip(names, c[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+        os.unlink(self.f.name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples_under_load": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ B200 arm
+def scan_algorithmic_bytes(hp, batch, L, mode):
+    """Bytes one both-direction scan launch must move at the op boundary of the reference's
+    selective_scan_cuda.fwd: per direction B*L*[(u, delta, z read + out written)*di + (B, C)*Ns]*s_io
+    + parameters.  fp32 mode moves 4-byte elements (u / y as hi+lo bf16 planes = 4 B), bf16 mode 2-byte."""
+    s_io = 4 if mode == "fp32" else 2
+    di, Ns = hp.d_inner, hp.d_state
+    per_dir = batch * L * (4 * di + 2 * Ns) * s_io + (di * Ns + 2 * di) * 4
+    return 2 * per_dir
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)", d
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)", {}
+
+
+def run_b200_arm(a):
+    import torch
+    import torch.distributed as dist
+    from avse_challenge_b200 import CONFIGS, init_state_dicts, synth_mixture
+    from avse_challenge_b200.engine import SeparatorEngine
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback for the product path)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    hp = CONFIGS[a.hparams]
+    T = int(round(a.seconds * a.sample_rate)) // 8 * 8
+    L = hp.frames(T)
+    sds = init_state_dicts(hp, 1234)
+    mix_cpu, _ = synth_mixture(min(a.batch, 8), T, a.sample_rate, seed=1234 + rank)
+    reps = (a.batch + mix_cpu.shape[0] - 1) // mix_cpu.shape[0]
+    mix_cpu = mix_cpu.repeat(reps, 1)[: a.batch].contiguous()      # synthetic batch (8 distinct voices tiled)
+    eng = SeparatorEngine(hp, sds, device=dev, mode=a.mode, use_graph=not a.no_graph)
+    audio_s_per_step = a.batch * T / a.sample_rate
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        cpu_base, _ = cpu_reference_throughput(a.hparams, a.sample_rate, steps=1, warmup=0, budget_s=30.0)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+
+    # ---- device-resident timing (value): inputs already in HBM, graph replay
+    ws = eng.workspace(a.batch, T)
+    ws.mix[:, :T].copy_(mix_cpu.to(dev))
+    for _ in range(max(3, a.warmup)):
+        eng.forward_into_workspace(a.batch, T)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        eng.forward_into_workspace(a.batch, T)
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+
+    # ---- end-to-end through the public API with host buffers
+    pin_in = mix_cpu.pin_memory()
+    pin_out = torch.empty((a.batch, T, hp.n_spk), dtype=torch.float32).pin_memory()
+    dmix = torch.empty((a.batch, T), dtype=torch.float32, device=dev)
+
+    def e2e_step():
+        dmix.copy_(pin_in, non_blocking=True)
+        est = eng.forward(dmix)
+        pin_out.copy_(est, non_blocking=True)
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(a.steps):
+        e2e_step()
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+
+    # ---- per-kernel timing in situ (CUDA events around every launch, eager mode), for the roofline
+    prof = eng.profile_ops(a.batch, T, steps=max(2, min(a.steps, 5)))
+    clocks = sampler.stop() if sampler else None
+
+    t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, ms_e2e = t.tolist()
+
+    if rank == 0:
+        peak, peak_src, peaks = load_peaks()
+        scan_ms = prof["scan"]["ms"]
+        alg = scan_algorithmic_bytes(hp, a.batch, L, a.mode)
+        achieved = alg / (scan_ms * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "scan_traffic.json")
+        if os.path.exists(tp):
+            try:
+                tj = json.load(open(tp))
+                key = f"{a.hparams}_b{a.batch}_{a.mode}"
+                traffic = tj.get(key, {}).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        sm_mhz = (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
+        n_exp = 2 * a.batch * L * hp.d_inner * hp.d_state
+        mufu_ms = n_exp / (148 * 16 * sm_mhz * 1e6) * 1e3
+        step_ms = ms_total / a.steps
+        total_prof = sum(v["ms_per_forward"] for v in prof.values())
+        line = {
+            "metric": METRIC, "value": audio_s_per_step * world / (step_ms * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": a.steps, "warmup": max(3, a.warmup), "ms_per_step": step_ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32" if a.mode == "fp32" else "bf16",
+            "data": "synthetic", "config": workload_config(a, world),
+            "e2e": {"value": audio_s_per_step * world / (ms_e2e / a.steps * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": a.batch * T * 4, "d2h_bytes_per_step": a.batch * T * hp.n_spk * 4,
+                    "ms_per_step": ms_e2e / a.steps},
+            "gpu_launches": a.steps * sum(v["launches"] for v in prof.values()) + a.steps,  # +1: decoder = 2 kernels
+            "roofline": {"kernel": "mtn::scan_kernel (both directions per launch)", "bound": "hbm",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "peak_source": peak_src, "traffic": traffic, "algorithmic_bytes_per_launch": alg,
+                         "ms_per_launch": scan_ms, "launches_per_step": prof["scan"]["launches"],
+                         "share_of_step": prof["scan"]["ms_per_forward"] / total_prof,
+                         "mufu_bound_ms": mufu_ms, "mufu_frac": mufu_ms / scan_ms},
+            "kernels_ms_per_step": {k: round(v["ms_per_forward"], 4) for k, v in sorted(prof.items())},
+            "clocks": clocks,
+        }
+        if cpu_base is not None:
+            line["cpu_baseline"] = cpu_base
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference_arm(a)
+    else:
+        run_b200_arm(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -85,10 +85,11 @@ typedef struct {
     int dir_mask;         /* bit0 forward, bit1 backward (3 = both in one launch) */
 } mtn_scan_args;
 
-/* mix [batch][T] fp32 -> mix_w [batch*L][N] fp32 = relu(conv1d(k=16,s=8)); yn planes = cLN(mix_w) */
-int mtn_encoder_cln_fwd(const float* mix, const float* w_enc /*[N][16]*/, const float* gamma, const float* beta,
-                        float* mix_w, void* yn_planes, int batch, int T, int L, int N, int planes, float eps,
-                        mtn_stream_t stream);
+/* mix [batch][ld_mix >= T] fp32 -> mix_w [batch*L][N] fp32 = relu(conv1d(k=16,s=8)), L = (T-16)/8+1;
+ * yn planes = cLN(mix_w).  ld_mix % 4 == 0 (128-bit frame loads); T itself is arbitrary (>= 16). */
+int mtn_encoder_cln_fwd(const float* mix, int ld_mix, const float* w_enc /*[N][16]*/, const float* gamma,
+                        const float* beta, float* mix_w, void* yn_planes, int batch, int T, int L, int N, int planes,
+                        float eps, mtn_stream_t stream);
 
 int mtn_gemm_fwd(const mtn_gemm_args* args, mtn_stream_t stream);
 

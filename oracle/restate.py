@@ -147,12 +147,13 @@ def selective_scan(u, delta_pre, A, Bm, Cm, D, z, delta_bias, reverse=False, h_i
         return torch.from_numpy(out), torch.from_numpy(hl)
     delta = F.softplus(delta_pre + delta_bias)                           # :110-112
     h = torch.zeros(Bsz, di, Ns, dtype=u.dtype) if h_in is None else h_in.clone()
+    # like the reference, materialise the whole-sequence decay and input terms first (:126, :131) ...
+    deltaA = torch.exp(torch.einsum("bld,dn->bldn", delta, A))
+    deltaB_u = torch.einsum("bld,bln,bld->bldn", delta, Bm, u)
     ys = [None] * L
     order = range(L - 1, -1, -1) if reverse else range(L)
-    for t in order:                                                       # :138-151
-        dA = torch.exp(delta[:, t, :, None] * A)                          # :126
-        dBu = delta[:, t, :, None] * Bm[:, t, None, :] * u[:, t, :, None]  # :131
-        h = dA * h + dBu                                                  # :139
+    for t in order:                                                       # ... then the per-step loop (:138-151)
+        h = deltaA[:, t] * h + deltaB_u[:, t]                             # :139
         ys[t] = torch.einsum("bdn,bn->bd", h, Cm[:, t])                   # :144
     y = torch.stack(ys, dim=1) + u * D                                    # :152-153
     if gate and z is not None:

@@ -20,6 +20,13 @@ def rel_max(a, b):
     return ((a.double() - b.double()).abs().max() / b.double().pow(2).mean().sqrt().clamp(min=1e-30)).item()
 
 
+def rel_mixed(a, b):
+    """max |a-b| / (|b| + rms(b)): element-wise relative error with an rms floor.  Used for per-op checks on
+    heavy-tailed random data, where max-abs/rms is dominated by the rounding of a few very large elements."""
+    b = b.double()
+    return ((a.double() - b).abs() / (b.abs() + b.pow(2).mean().sqrt().clamp(min=1e-30))).max().item()
+
+
 def hp_from_sds(sds):
     from avse_challenge_b200.hparams import HParams
     m = sds["masknet"]

@@ -14,7 +14,7 @@ from avse_challenge_b200 import CONFIGS, init_state_dicts, synth_mixture, pit_si
 from avse_challenge_b200 import _lib, ops, modules
 from avse_challenge_b200.engine import SeparatorEngine
 from oracle import restate
-from tests.helpers import load_golden_forward, rel_max, hp_from_sds
+from tests.helpers import load_golden_forward, rel_max, rel_mixed, hp_from_sds
 
 pytestmark = pytest.mark.gpu
 
@@ -49,13 +49,13 @@ def test_gemm_store(M, N, K, P, groups):
     torch.cuda.synchronize()
     av, wv = _planes_value(ap).double(), _planes_value(wp).double()
     ref = torch.cat([av[:, gi * K:(gi + 1) * K] @ wv[gi * N:(gi + 1) * N].t() for gi in range(groups)], dim=1)
-    tol = 2e-5 if P == 2 else 1e-6  # P=2 drops the lo*lo term (2^-18); P=1 is exact up to fp32 accumulation
+    tol = 5e-5 if P == 2 else 5e-6  # P=2 drops the lo*lo term (2^-18 per product); P=1: fp32 accumulation only
     assert rel_max(out.cpu(), ref) < tol
     # and against the un-rounded fp32 operands: the split-bf16 scheme is fp32-class
     if P == 2:
         ref32 = torch.cat([a.double()[:, gi * K:(gi + 1) * K] @ w.double()[gi * N:(gi + 1) * N].t()
                            for gi in range(groups)], dim=1)
-        assert rel_max(out.cpu(), ref32) < 5e-5
+        assert rel_max(out.cpu(), ref32) < 1e-4
 
 
 def test_gemm_epilogues():
@@ -69,9 +69,9 @@ def test_gemm_epilogues():
     exp = ref.clone()
     exp[:, di:] = torch.nn.functional.silu(exp[:, di:])
     out = ops.gemm(ap, wp, M, 2 * di, K, epilogue=_lib.EPI_INPROJ, epi_param=di)
-    assert rel_max(out.cpu(), exp) < 2e-5
+    assert rel_max(out.cpu(), exp) < 5e-5
     outb = ops.gemm(ap, wp, M, 2 * di, K, epilogue=_lib.EPI_INPROJ, epi_param=di, out_bf16=True)
-    assert outb.dtype == torch.bfloat16 and rel_max(outb.float().cpu(), exp) < 2 ** -7
+    assert outb.dtype == torch.bfloat16 and rel_mixed(outb.float().cpu(), exp) < 2 ** -8
     # relu
     out = ops.gemm(ap, wp, M, 2 * di, K, epilogue=_lib.EPI_RELU)
     assert rel_max(out.cpu(), ref.clamp(min=0)) < 2e-5
@@ -79,7 +79,7 @@ def test_gemm_epilogues():
     mixw = torch.rand(M, enc, generator=g)
     out = ops.gemm(ap, wp, M, 2 * enc, K, epilogue=_lib.EPI_MASK, epi_param=enc, aux=mixw.to(DEV))
     exp = ref.clamp(min=0) * torch.cat([mixw, mixw], 1).double()
-    assert rel_max(out.cpu(), exp) < 2e-5
+    assert rel_max(out.cpu(), exp) < 5e-5
 
 
 def test_gemm_rejects_bad_shapes():
@@ -101,9 +101,9 @@ def test_encoder_cln(N):
     ref_w = restate.encoder_fwd(mix, w)
     ref_y = restate.cln_fwd(ref_w, gamma, beta)
     assert rel_max(mix_w.cpu().view_as(ref_w), ref_w) < 1e-5
-    assert rel_max(_planes_value(yn).view_as(ref_y), ref_y) < 5e-5
+    assert rel_mixed(_planes_value(yn).view_as(ref_y), ref_y) < 2e-5
     yn2 = ops.cln(mix_w, gamma.to(DEV), beta.to(DEV), 2)
-    assert rel_max(_planes_value(yn2).view_as(ref_y), ref_y) < 5e-5
+    assert rel_mixed(_planes_value(yn2).view_as(ref_y), ref_y) < 2e-5
 
 
 @pytest.mark.parametrize("D", [64, 128, 256, 512])
@@ -114,11 +114,11 @@ def test_add_rmsnorm(D):
     r = res.to(DEV).clone()
     xn = ops.add_rmsnorm(h.to(DEV), r, True, w.to(DEV), 2)
     assert rel_max(r.cpu(), h + res) < 1e-6
-    assert rel_max(_planes_value(xn), restate.rmsnorm_fwd(h + res, w)) < 5e-5
+    assert rel_mixed(_planes_value(xn), restate.rmsnorm_fwd(h + res, w)) < 2e-5
     r = torch.full((M, D), float("nan"), device=DEV)
     xn = ops.add_rmsnorm(h.to(DEV), r, False, w.to(DEV), 2)  # first block: residual := h
     assert torch.equal(r.cpu(), h)
-    assert rel_max(_planes_value(xn), restate.rmsnorm_fwd(h, w)) < 5e-5
+    assert rel_mixed(_planes_value(xn), restate.rmsnorm_fwd(h, w)) < 2e-5
 
 
 @pytest.mark.parametrize("di,L,dtype", [(128, 77, torch.float32), (512, 1003, torch.float32), (1024, 130, torch.bfloat16)])
@@ -133,8 +133,8 @@ def test_conv_silu_both_directions(di, L, dtype):
     ref_f = restate.causal_conv_silu(xs, cw[0].unsqueeze(1), cb[0], reverse=False)
     ref_b = restate.causal_conv_silu(xs, cw[1].unsqueeze(1), cb[1], reverse=True)
     got = _planes_value(u).view(B, L, 2 * di)
-    assert rel_max(got[..., :di], ref_f) < 5e-5
-    assert rel_max(got[..., di:], ref_b) < 5e-5
+    assert rel_mixed(got[..., :di], ref_f) < 2e-5
+    assert rel_mixed(got[..., di:], ref_b) < 2e-5
 
 
 @pytest.mark.parametrize("N", [64, 256, 512])
@@ -187,31 +187,31 @@ def _scan_case(di, R, L, B, seed, P=2, with_state=False, dir_mask=3):
         ref, hl = restate.selective_scan(ud, delta_pre, A[d], dd[..., R:R + 16].contiguous(),
                                          dd[..., R + 16:R + 32].contiguous(), Dk[d], z.view(B, L, di), dt_bias[d],
                                          reverse=(d == 1), h_in=h_in[d] if with_state else None, impl="c")
-        res.append((rel_max(yv[..., d * di:(d + 1) * di], 0.5 * ref),
-                    rel_max(h_out[d].cpu(), hl) if with_state else 0.0))
+        res.append((rel_mixed(yv[..., d * di:(d + 1) * di], 0.5 * ref),
+                    rel_mixed(h_out[d].cpu(), hl) if with_state else 0.0))
     return res
 
 
 @pytest.mark.parametrize("di,R,L,B", [(128, 4, 157, 2), (256, 8, 1003, 2), (512, 16, 3999, 1), (1024, 32, 333, 2)])
 def test_scan_matches_selective_scan_ref(di, R, L, B):
     for err, _ in _scan_case(di, R, L, B, seed=di + L):
-        assert err < 1e-4, err  # fp32 state; u/y are split-bf16 (2^-17), exp/softplus via ex2/lg2.approx
+        assert err < 5e-5, err  # fp32 state; y is split-bf16 (2^-18), exp/softplus via ex2/lg2.approx
 
 
 def test_scan_initial_and_final_state():
     for err, herr in _scan_case(256, 8, 210, 3, seed=5, with_state=True):
-        assert err < 1e-4 and herr < 1e-4
+        assert err < 5e-5 and herr < 5e-5
 
 
 def test_scan_single_direction_launches():
     (e0, _), = _scan_case(128, 4, 100, 2, seed=9, dir_mask=1)
     (e1, _), = _scan_case(128, 4, 100, 2, seed=9, dir_mask=2)
-    assert e0 < 1e-4 and e1 < 1e-4
+    assert e0 < 5e-5 and e1 < 5e-5
 
 
 def test_scan_bf16_mode():
     for err, _ in _scan_case(256, 16, 500, 2, seed=11, P=1):
-        assert err < 1e-2  # single bf16 plane for u / y (2^-9 rounding of the output)
+        assert err < 2 ** -8  # single bf16 plane for y (half-ulp 2^-9 .. 2^-8 relative)
 
 
 # --------------------------------------------------------------------------- end to end
