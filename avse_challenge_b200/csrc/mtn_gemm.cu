@@ -57,8 +57,9 @@ __global__ void __launch_bounds__(192, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                     const GemmParams p) {
     using Cfg = GemmCfg<P, BN>;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // 1024-B align inside the shared window without leaving the shared address space (keeps LDS/STS)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     float* staging = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::STAGING_BYTES);
     uint64_t* empty_bar = full_bar + Cfg::STAGES;

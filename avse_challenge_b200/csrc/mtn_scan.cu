@@ -41,21 +41,196 @@ struct ScanSmem {
     static constexpr int Z_BYTES = SC_TT * SC_CH * int(sizeof(ZT));
     static constexpr int D_BYTES = SC_TT * NDBL * 4;
     static constexpr int STAGE_BYTES = U_BYTES + Z_BYTES + D_BYTES;
-    static constexpr int TOTAL = 128 + SC_STAGES * STAGE_BYTES + 2 * SC_STAGES * 8;
+    static constexpr int Y_BYTES = (SC_CH / 32) * P * SC_TT * 32 * 2;  // per-warp output staging
+    static constexpr int TOTAL = 128 + SC_STAGES * STAGE_BYTES + 2 * SC_STAGES * 8 + Y_BYTES;
 };
 
 __device__ __forceinline__ float ldz(const float* p) { return *p; }
 __device__ __forceinline__ float ldz(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
+// softplus with ONE MUFU op: max(x,0) + log1p(exp(-|x|)); log1p(e) = e * Q(e) on [0,1], Q = degree-8 Chebyshev fit of
+// log1p(e)/e (max rel. err 9e-8, so tiny deltas keep full relative accuracy).  Equals torch's softplus incl. its
+// "linear above 20" branch to fp32 rounding (exp(-20) ~ 2e-9 vanishes against x).
+__device__ __forceinline__ float softplus_1mufu(float x) {
+    const float e = ex2_approx(-1.4426950408889634f * fabsf(x));
+    float q = 0.0051261021414032125f;
+    q = fmaf(q, e, -0.02907406467853027f);
+    q = fmaf(q, e, 0.07751608674076167f);
+    q = fmaf(q, e, -0.13602247622393474f);
+    q = fmaf(q, e, 0.19076880735651539f);
+    q = fmaf(q, e, -0.24835398988480129f);
+    q = fmaf(q, e, 0.3331812170752912f);
+    q = fmaf(q, e, -0.49999444976340335f);
+    q = fmaf(q, e, 0.9999999659255092f);
+    return fmaf(q, e, fmaxf(x, 0.f));
+}
+
+// One direction of one CTA's channels.  REV is a template parameter so that, with the 16-step tile fully unrolled,
+// every per-step register array index is a compile-time constant.
+template <int P, int R, int NDBL, typename ZT, bool REV>
+__device__ __forceinline__ void scan_consumer(uint8_t* smem, uint64_t* full_bar, uint64_t* empty_bar,
+                                              __nv_bfloat16* sy, const ScanParams& p, int ch0, int b, int dir) {
+    using SM = ScanSmem<P, NDBL, ZT>;
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int L = p.L;
+    const int ntiles = (L + SC_TT - 1) / SC_TT;
+    const int d = ch0 + tid;
+    const size_t pd = size_t(dir) * p.di + d;
+    float2 h2[SC_NS / 2], A2[SC_NS / 2];
+    float wdt[R];
+    {
+        const float4* ap = reinterpret_cast<const float4*>(p.A2 + pd * SC_NS);
+#pragma unroll
+        for (int q = 0; q < SC_NS / 4; ++q) {
+            const float4 a = ap[q];
+            A2[2 * q] = make_float2(a.x, a.y);
+            A2[2 * q + 1] = make_float2(a.z, a.w);
+        }
+        const float4* wp = reinterpret_cast<const float4*>(p.w_dt + pd * R);
+#pragma unroll
+        for (int q = 0; q < R / 4; ++q) {
+            const float4 w = wp[q];
+            wdt[4 * q] = w.x;
+            wdt[4 * q + 1] = w.y;
+            wdt[4 * q + 2] = w.z;
+            wdt[4 * q + 3] = w.w;
+        }
+        if (p.h_in) {
+            const float4* hp = reinterpret_cast<const float4*>(p.h_in + ((size_t(dir) * p.batch + b) * p.di + d) * SC_NS);
+#pragma unroll
+            for (int q = 0; q < SC_NS / 4; ++q) {
+                const float4 a = hp[q];
+                h2[2 * q] = make_float2(a.x, a.y);
+                h2[2 * q + 1] = make_float2(a.z, a.w);
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < SC_NS / 2; ++q) h2[q] = make_float2(0.f, 0.f);
+        }
+    }
+    const float bias = p.dt_bias[pd];
+    const float Dv = p.Dskip[pd];
+    const size_t M = size_t(p.batch) * L;
+    const size_t y_plane = M * 2 * p.di;
+    // this warp's 32-channel column block of y; rows are 2*di bf16 apart
+    __nv_bfloat16* ywarp = p.y + size_t(dir) * p.di + ch0 + warp * 32;
+    __nv_bfloat16* sy_w = sy + warp * (P * SC_TT * 32);  // warp-private staging [P][TT][32]
+
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int i = 0; i < ntiles; ++i) {
+        const int tile = REV ? (ntiles - 1 - i) : i;
+        const int t0 = tile * SC_TT;
+        const int nvalid = min(SC_TT, L - t0);
+        mbar_wait(&full_bar[stage], phase);
+        const uint8_t* st = smem + stage * SM::STAGE_BYTES;
+        const __nv_bfloat16* su = reinterpret_cast<const __nv_bfloat16*>(st);
+        const ZT* sz = reinterpret_cast<const ZT*>(st + SM::U_BYTES);
+        const float* sd = reinterpret_cast<const float*>(st + SM::U_BYTES + SM::Z_BYTES);
+
+        // ---- phase A: per-step scalars for the whole tile (16 independent chains -> ILP)
+        float delta[SC_TT], du[SC_TT];
+#pragma unroll
+        for (int j = 0; j < SC_TT; ++j) {
+            const float* drow = sd + j * NDBL;
+            float acc0 = bias, acc1 = 0.f;
+#pragma unroll
+            for (int q = 0; q < R / 4; ++q) {
+                const float4 x = *reinterpret_cast<const float4*>(drow + 4 * q);
+                acc0 = fmaf(x.x, wdt[4 * q], acc0);
+                acc1 = fmaf(x.y, wdt[4 * q + 1], acc1);
+                acc0 = fmaf(x.z, wdt[4 * q + 2], acc0);
+                acc1 = fmaf(x.w, wdt[4 * q + 3], acc1);
+            }
+            float dl = softplus_1mufu(acc0 + acc1);
+            dl = (j < nvalid) ? dl : 0.f;  // rows past the utterance end: exp2(0)=1, dBu=0 -> state unchanged
+            float uval = __bfloat162float(su[j * SC_CH + tid]);
+            if (P == 2) uval += __bfloat162float(su[SC_TT * SC_CH + j * SC_CH + tid]);
+            delta[j] = dl;
+            du[j] = dl * uval;
+        }
+        // ---- phase B: the recurrence, steps in processing order; exps of later steps are independent of h
+#pragma unroll
+        for (int jj = 0; jj < SC_TT; ++jj) {
+            const int j = REV ? (SC_TT - 1 - jj) : jj;
+            const float* drow = sd + j * NDBL;
+            const float2 delta2 = make_float2(delta[j], delta[j]);
+            const float2 du2 = make_float2(du[j], du[j]);
+            float2 ya = make_float2(0.f, 0.f), yb = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int q = 0; q < SC_NS / 4; ++q) {
+                const float4 Bq = *reinterpret_cast<const float4*>(drow + R + 4 * q);
+                const float4 Cq = *reinterpret_cast<const float4*>(drow + R + SC_NS + 4 * q);
+                {
+                    const float2 a = __fmul2_rn(delta2, A2[2 * q]);
+                    const float2 e = make_float2(ex2_approx(a.x), ex2_approx(a.y));
+                    const float2 bu = __fmul2_rn(du2, make_float2(Bq.x, Bq.y));
+                    h2[2 * q] = __ffma2_rn(e, h2[2 * q], bu);
+                    ya = __ffma2_rn(h2[2 * q], make_float2(Cq.x, Cq.y), ya);
+                }
+                {
+                    const float2 a = __fmul2_rn(delta2, A2[2 * q + 1]);
+                    const float2 e = make_float2(ex2_approx(a.x), ex2_approx(a.y));
+                    const float2 bu = __fmul2_rn(du2, make_float2(Bq.z, Bq.w));
+                    h2[2 * q + 1] = __ffma2_rn(e, h2[2 * q + 1], bu);
+                    yb = __ffma2_rn(h2[2 * q + 1], make_float2(Cq.z, Cq.w), yb);
+                }
+            }
+            float uval = __bfloat162float(su[j * SC_CH + tid]);
+            if (P == 2) uval += __bfloat162float(su[SC_TT * SC_CH + j * SC_CH + tid]);
+            const float zval = ldz(sz + j * SC_CH + tid);
+            const float y = ((ya.x + ya.y) + (yb.x + yb.y) + Dv * uval) * (0.5f * zval);
+            if (P == 2) {
+                __nv_bfloat16 hi, lo;
+                split_bf16(y, hi, lo);
+                sy_w[j * 32 + lane] = hi;
+                sy_w[SC_TT * 32 + j * 32 + lane] = lo;
+            } else {
+                sy_w[j * 32 + lane] = __float2bfloat16_rn(y);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[stage]);  // inputs of this stage are consumed
+        // ---- flush this warp's staged y rows: 4 lanes x 16 B cover one 64-byte row segment
+#pragma unroll
+        for (int pl = 0; pl < P; ++pl) {
+#pragma unroll
+            for (int it = 0; it < SC_TT / 8; ++it) {
+                const int row = it * 8 + (lane >> 2);
+                const int seg = lane & 3;
+                if (row < nvalid) {
+                    const uint4 v = *reinterpret_cast<const uint4*>(sy_w + pl * SC_TT * 32 + row * 32 + seg * 8);
+                    const size_t off = (size_t(b) * L + t0 + row) * (2 * size_t(p.di)) + seg * 8;
+                    *reinterpret_cast<uint4*>(ywarp + pl * y_plane + off) = v;
+                }
+            }
+        }
+        __syncwarp();
+        if (++stage == SC_STAGES) {
+            stage = 0;
+            phase ^= 1;
+        }
+    }
+    if (p.h_out) {
+        float4* hp = reinterpret_cast<float4*>(p.h_out + ((size_t(dir) * p.batch + b) * p.di + d) * SC_NS);
+#pragma unroll
+        for (int q = 0; q < SC_NS / 4; ++q)
+            hp[q] = make_float4(h2[2 * q].x, h2[2 * q].y, h2[2 * q + 1].x, h2[2 * q + 1].y);
+    }
+}
 
 template <int P, int R, int NDBL, typename ZT>
 __global__ void __launch_bounds__(SC_CH + 32)
 scan_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUtensorMap mapZ,
             const __grid_constant__ CUtensorMap mapD, const ScanParams p) {
     using SM = ScanSmem<P, NDBL, ZT>;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // align inside the shared window without leaving the shared address space (keeps LDS/STS, not generic LD/ST)
+    uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SC_STAGES * SM::STAGE_BYTES);
     uint64_t* empty_bar = full_bar + SC_STAGES;
+    __nv_bfloat16* sy = reinterpret_cast<__nv_bfloat16*>(smem + SC_STAGES * SM::STAGE_BYTES + 2 * SC_STAGES * 8);
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -100,124 +275,10 @@ scan_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CU
         }
         return;
     }
-
-    // ---------------------------------------------------------------- consumers: thread = channel
-    const int d = ch0 + tid;
-    const size_t pd = size_t(dir) * p.di + d;
-    float2 h2[SC_NS / 2], A2[SC_NS / 2];
-    float wdt[R];
-    {
-        const float4* ap = reinterpret_cast<const float4*>(p.A2 + pd * SC_NS);
-#pragma unroll
-        for (int q = 0; q < SC_NS / 4; ++q) {
-            const float4 a = ap[q];
-            A2[2 * q] = make_float2(a.x, a.y);
-            A2[2 * q + 1] = make_float2(a.z, a.w);
-        }
-        const float4* wp = reinterpret_cast<const float4*>(p.w_dt + pd * R);
-#pragma unroll
-        for (int q = 0; q < R / 4; ++q) {
-            const float4 w = wp[q];
-            wdt[4 * q] = w.x;
-            wdt[4 * q + 1] = w.y;
-            wdt[4 * q + 2] = w.z;
-            wdt[4 * q + 3] = w.w;
-        }
-        if (p.h_in) {
-            const float4* hp = reinterpret_cast<const float4*>(p.h_in + ((size_t(dir) * p.batch + b) * p.di + d) * SC_NS);
-#pragma unroll
-            for (int q = 0; q < SC_NS / 4; ++q) {
-                const float4 a = hp[q];
-                h2[2 * q] = make_float2(a.x, a.y);
-                h2[2 * q + 1] = make_float2(a.z, a.w);
-            }
-        } else {
-#pragma unroll
-            for (int q = 0; q < SC_NS / 2; ++q) h2[q] = make_float2(0.f, 0.f);
-        }
-    }
-    const float bias = p.dt_bias[pd];
-    const float Dv = p.Dskip[pd];
-    const size_t M = size_t(p.batch) * L;
-    const size_t y_plane = M * 2 * p.di;
-    __nv_bfloat16* ybase = p.y + size_t(dir) * p.di + d;
-
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int i = 0; i < ntiles; ++i) {
-        const int tile = rev ? (ntiles - 1 - i) : i;
-        const int t0 = tile * SC_TT;
-        const int nvalid = min(SC_TT, L - t0);
-        mbar_wait(&full_bar[stage], phase);
-        const uint8_t* st = smem + stage * SM::STAGE_BYTES;
-        const __nv_bfloat16* su = reinterpret_cast<const __nv_bfloat16*>(st);
-        const ZT* sz = reinterpret_cast<const ZT*>(st + SM::U_BYTES);
-        const float* sd = reinterpret_cast<const float*>(st + SM::U_BYTES + SM::Z_BYTES);
-#pragma unroll 2
-        for (int jj = 0; jj < nvalid; ++jj) {
-            const int j = rev ? (nvalid - 1 - jj) : jj;
-            const float* drow = sd + j * NDBL;
-            // dt_proj: R-term dot product against the broadcast low-rank row
-            float dt = bias;
-#pragma unroll
-            for (int q = 0; q < R / 4; ++q) {
-                const float4 x = *reinterpret_cast<const float4*>(drow + 4 * q);
-                dt = fmaf(x.x, wdt[4 * q], dt);
-                dt = fmaf(x.y, wdt[4 * q + 1], dt);
-                dt = fmaf(x.z, wdt[4 * q + 2], dt);
-                dt = fmaf(x.w, wdt[4 * q + 3], dt);
-            }
-            const float delta = softplus_f(dt);
-            float uval = __bfloat162float(su[j * SC_CH + tid]);
-            if (P == 2) uval += __bfloat162float(su[SC_TT * SC_CH + j * SC_CH + tid]);
-            const float zval = ldz(sz + j * SC_CH + tid);
-            const float du = delta * uval;
-            const float2 delta2 = make_float2(delta, delta);
-            const float2 du2 = make_float2(du, du);
-            float2 y2 = make_float2(0.f, 0.f);
-#pragma unroll
-            for (int q = 0; q < SC_NS / 4; ++q) {
-                const float4 Bq = *reinterpret_cast<const float4*>(drow + R + 4 * q);
-                const float4 Cq = *reinterpret_cast<const float4*>(drow + R + SC_NS + 4 * q);
-                {
-                    const float2 a = __fmul2_rn(delta2, A2[2 * q]);
-                    const float2 e = make_float2(ex2_approx(a.x), ex2_approx(a.y));
-                    const float2 bu = __fmul2_rn(du2, make_float2(Bq.x, Bq.y));
-                    h2[2 * q] = __ffma2_rn(e, h2[2 * q], bu);
-                    y2 = __ffma2_rn(h2[2 * q], make_float2(Cq.x, Cq.y), y2);
-                }
-                {
-                    const float2 a = __fmul2_rn(delta2, A2[2 * q + 1]);
-                    const float2 e = make_float2(ex2_approx(a.x), ex2_approx(a.y));
-                    const float2 bu = __fmul2_rn(du2, make_float2(Bq.z, Bq.w));
-                    h2[2 * q + 1] = __ffma2_rn(e, h2[2 * q + 1], bu);
-                    y2 = __ffma2_rn(h2[2 * q + 1], make_float2(Cq.z, Cq.w), y2);
-                }
-            }
-            const float y = (y2.x + y2.y + Dv * uval) * (0.5f * zval);
-            const size_t off = (size_t(b) * L + t0 + j) * (2 * size_t(p.di));
-            if (P == 2) {
-                __nv_bfloat16 hi, lo;
-                split_bf16(y, hi, lo);
-                ybase[off] = hi;
-                ybase[y_plane + off] = lo;
-            } else {
-                ybase[off] = __float2bfloat16_rn(y);
-            }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_bar[stage]);
-        if (++stage == SC_STAGES) {
-            stage = 0;
-            phase ^= 1;
-        }
-    }
-    if (p.h_out) {
-        float4* hp = reinterpret_cast<float4*>(p.h_out + ((size_t(dir) * p.batch + b) * p.di + d) * SC_NS);
-#pragma unroll
-        for (int q = 0; q < SC_NS / 4; ++q)
-            hp[q] = make_float4(h2[2 * q].x, h2[2 * q].y, h2[2 * q + 1].x, h2[2 * q + 1].y);
-    }
+    if (rev)
+        scan_consumer<P, R, NDBL, ZT, true>(smem, full_bar, empty_bar, sy, p, ch0, b, dir);
+    else
+        scan_consumer<P, R, NDBL, ZT, false>(smem, full_bar, empty_bar, sy, p, ch0, b, dir);
 }
 
 template <int P, int R, int NDBL, typename ZT>

@@ -1,0 +1,39 @@
+"""Micro-benchmark of mtn_scan_fwd alone at a BASELINE shape (used for ncu captures and kernel iteration).
+
+    python tools/scan_bench.py [--hparams S] [--batch 32] [--L 3999] [--mode fp32] [--iters 20]
+"""
+import argparse, json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from avse_challenge_b200 import CONFIGS, ops
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--hparams", default="S"); ap.add_argument("--batch", type=int, default=32)
+ap.add_argument("--L", type=int, default=3999); ap.add_argument("--mode", default="fp32")
+ap.add_argument("--iters", type=int, default=20)
+a = ap.parse_args()
+hp = CONFIGS[a.hparams]; di, R = hp.d_inner, hp.dt_rank; nd = ops.n_dbl_for(R)
+P = 2 if a.mode == "fp32" else 1
+M = a.batch * a.L
+dev = "cuda"
+g = torch.Generator(device=dev).manual_seed(0)
+u = (torch.randn(P, M, 2 * di, device=dev, generator=g) * (1.0 if P == 1 else 0.5)).to(torch.bfloat16)
+dbl = torch.randn(M, 2 * nd, device=dev, generator=g) * 0.5
+xz = torch.randn(M, 2 * di, device=dev, generator=g).to(torch.float32 if P == 2 else torch.bfloat16)
+w_dt = torch.randn(2, di, R, device=dev, generator=g) * R ** -0.5
+dt_bias = torch.randn(2, di, device=dev, generator=g) * 0.5 - 3.0
+A2 = -torch.exp(torch.randn(2, di, 16, device=dev, generator=g) * 0.5 + 0.5) * ops.LOG2E
+Dk = torch.randn(2, di, device=dev, generator=g)
+y = torch.empty_like(u)
+run = lambda: ops.scan(u, dbl, xz, di, w_dt, dt_bias, A2, Dk, a.batch, a.L, di, R, y=y)
+for _ in range(3): run()
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(a.iters): run()
+e1.record(); torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / a.iters
+s_io = 4 if P == 2 else 2
+alg = 2 * (M * (4 * di + 32) * s_io + (di * 16 + 2 * di) * 4)
+print(json.dumps({"scan_ms": ms, "alg_GBps": alg / ms / 1e6, "frac_of_6541": alg / ms / 1e6 / 6541.1,
+                  "mufu_bound_ms@1965": 2 * M * di * 16 / (148 * 16 * 1.965e9) * 1e3, "shape": [a.hparams, a.batch, a.L, a.mode]}))
