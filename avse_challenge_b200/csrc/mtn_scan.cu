@@ -8,19 +8,29 @@
 //     out    = 0.5 * y * silu(z)                                      (ssi.py:155; 0.5 = bimamba.py:253)
 // The backward direction walks t = L-1..0 on the same buffers (the reference flips xz instead, bimamba.py:237).
 //
-// Mapping: one thread owns one channel d of one utterance and keeps its 16 SSM states in registers (packed
-// f32x2 FMAs); a CTA = 128 channels + 1 producer warp.  The producer streams (u, silu(z), [dt|B|C]) time tiles
-// through a 4-stage TMA/mbarrier ring, so the consumers never touch global memory for inputs; B_t/C_t/dt_t are
-// warp-broadcast shared-memory reads.  delta is never materialised in HBM (dt_proj is R FMAs from registers).
-// The kernel is MUFU-bound before it is HBM-bound (16 ex2 per (t, d)); see DESIGN.md for both rooflines.
+// Mapping (default, "split"): TWO lanes (l, l+16 of one warp) own one channel d of one utterance, 8 of its 16 SSM
+// states each, in registers (packed f32x2 FMAs); a CTA = 128 channels = 8 consumer warps + 1 producer warp.  The
+// time recurrence offers only batch*d_inner*2 independent sequences (32 768 at BASELINE config 2, i.e. 2 warps per
+// SM sub-partition if one thread owned a whole channel); splitting the state vector doubles the resident warps so
+// the MUFU / FMA / LSU latencies overlap across warps, at the price of three shuffles per step (delta, delta*u and
+// the partial y).  Per-step scalar work (dt_proj, softplus, gating, stores) is shared between the two lanes by
+// time parity: lane half h prepares and finalises the rows t = 2k + h of each 16-row tile.
+// The producer streams (u, silu(z), [dt|B|C]) time tiles through a TMA/mbarrier ring, so consumers never touch
+// global memory for inputs; B_t/C_t/dt_t are warp-broadcast shared-memory reads.  delta is never materialised in
+// HBM (dt_proj is R FMAs from registers).  The kernel is MUFU-bound before it is HBM-bound (16 ex2 per (t, d));
+// KP > 0 moves KP of every 4 state pairs of a lane to an FMA-pipe polynomial exp2 (Cody-Waite + degree-5 minimax,
+// 2e-7 relative) to balance the MUFU and FMA pipes.  See DESIGN.md for both rooflines.
+// MTN_SCAN_VARIANT (debug knob, read per call): 0/unset = split mapping; 1 = one thread per channel (A/B baseline);
+// 10+k = split mapping with KP = k polynomial pairs.
 #include "mtn_ptx.cuh"
 #include "mtn_host.h"
+#include <stdlib.h>
 
 namespace mtn {
 
 constexpr int SC_CH = 128;
 constexpr int SC_TT = 16;
-constexpr int SC_STAGES = 4;
+constexpr int SC_STAGES = 5;
 constexpr int SC_NS = 16;
 
 struct ScanParams {
@@ -32,7 +42,9 @@ struct ScanParams {
     const float* h_in;
     float* h_out;
     int batch, L, di, n_dbl, z_col0;
-    int dir0;  // first direction handled by blockIdx.z == 0
+    int dir0;   // first direction of this launch
+    int ndirs;  // 1 or 2
+    int dirmap; // how blockIdx.x maps to (direction, channel block); see scan_kernel
 };
 
 template <int P, int NDBL, typename ZT>
@@ -41,12 +53,23 @@ struct ScanSmem {
     static constexpr int Z_BYTES = SC_TT * SC_CH * int(sizeof(ZT));
     static constexpr int D_BYTES = SC_TT * NDBL * 4;
     static constexpr int STAGE_BYTES = U_BYTES + Z_BYTES + D_BYTES;
-    static constexpr int Y_BYTES = (SC_CH / 32) * P * SC_TT * 32 * 2;  // per-warp output staging
+    static constexpr int Y_BYTES = P * SC_TT * SC_CH * 2;  // output staging, one column block per consumer warp
     static constexpr int TOTAL = 128 + SC_STAGES * STAGE_BYTES + 2 * SC_STAGES * 8 + Y_BYTES;
 };
 
 __device__ __forceinline__ float ldz(const float* p) { return *p; }
-__device__ __forceinline__ float ldz(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ float ldz(const __nv_bfloat16* p) {
+    return __uint_as_float(uint32_t(*reinterpret_cast<const uint16_t*>(p)) << 16);
+}
+__device__ __forceinline__ float bf16_bits_to_float(const __nv_bfloat16* p) {
+    return __uint_as_float(uint32_t(*reinterpret_cast<const uint16_t*>(p)) << 16);
+}
+// fp32 -> bf16 through the packed ALU-pipe convert (F2FP); the scalar F2F form runs on the XU pipe, which is the
+// bottleneck of this kernel.
+__device__ __forceinline__ uint16_t f2bf_bits(float x) {
+    const __nv_bfloat162 v = __floats2bfloat162_rn(x, 0.f);
+    return uint16_t(*reinterpret_cast<const uint32_t*>(&v) & 0xFFFFu);
+}
 
 // softplus with ONE MUFU op: max(x,0) + log1p(exp(-|x|)); log1p(e) = e * Q(e) on [0,1], Q = degree-8 Chebyshev fit of
 // log1p(e)/e (max rel. err 9e-8, so tiny deltas keep full relative accuracy).  Equals torch's softplus incl. its
@@ -65,11 +88,325 @@ __device__ __forceinline__ float softplus_1mufu(float x) {
     return fmaf(q, e, fmaxf(x, 0.f));
 }
 
-// One direction of one CTA's channels.  REV is a template parameter so that, with the 16-step tile fully unrolled,
-// every per-step register array index is a compile-time constant.
+// 2^(dl * a) for a pair of states on the FMA pipe: n = round(dl*a) via the 1.5*2^23 trick, f = dl*a - n in
+// [-0.5, 0.5] (single-rounded through the FMA), degree-5 polynomial with p(0) = 1 exactly (max rel. err 2e-7 in
+// fp32 Horner), exponent added with integer arithmetic.  dl*a must be >= -126 (caller clamps dl per channel).
+__device__ __forceinline__ float2 ex2_poly2(float2 dl2, float2 a2) {
+    const float2 t = __ffma2_rn(dl2, a2, make_float2(12582912.f, 12582912.f));
+    const float2 r = __fadd2_rn(t, make_float2(-12582912.f, -12582912.f));
+    const float2 f = __ffma2_rn(dl2, a2, make_float2(-r.x, -r.y));
+    float2 q = make_float2(MTN_EX2_C5, MTN_EX2_C5);
+    q = __ffma2_rn(q, f, make_float2(MTN_EX2_C4, MTN_EX2_C4));
+    q = __ffma2_rn(q, f, make_float2(MTN_EX2_C3, MTN_EX2_C3));
+    q = __ffma2_rn(q, f, make_float2(MTN_EX2_C2, MTN_EX2_C2));
+    q = __ffma2_rn(q, f, make_float2(MTN_EX2_C1, MTN_EX2_C1));
+    q = __ffma2_rn(q, f, make_float2(1.f, 1.f));
+    return make_float2(__uint_as_float(__float_as_uint(q.x) + (__float_as_uint(t.x) << 23)),
+                       __uint_as_float(__float_as_uint(q.y) + (__float_as_uint(t.y) << 23)));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Split mapping: 256 consumer threads per CTA, lane = (half, cl): channel = warp*16 + cl, states [8*half, 8*half+8).
+//
+// Instruction mix is kept uniform over time: the per-row scalar work ("prep": dt_proj, softplus, delta*u) for tile
+// i+1 is interleaved into the recurrence steps of tile i (one row every two steps, written over the register slot
+// whose row was just finalised), so every warp presents the same MUFU : FMA : LSU ratio at all times and the four
+// warps of an SM sub-partition never queue up on the XU pipe together.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void sts_b16(void* p, uint32_t v) {
+    // no "memory" clobber on purpose: it would pin every shared-memory load of the recurrence behind this store;
+    // the staging buffer is only read after the __syncwarp() that follows the tile.
+    asm volatile("{\n\t.reg .b16 t;\n\tcvt.u16.u32 t, %1;\n\tst.shared.b16 [%0], t;\n\t}" ::"r"(smem_u32(p)), "r"(v));
+}
+// bf16(x) in the low 16 bits (F2FP on the ALU pipe; the scalar F2F form would use the XU pipe)
+__device__ __forceinline__ uint32_t f2bf_lo(float x) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(0.f), "f"(x));
+    return r;
+}
+
+template <int P, int R, int NDBL, typename ZT, bool REV, int KP>
+__device__ __forceinline__ void scan_consumer_split(uint8_t* smem, uint64_t* full_bar, uint64_t* empty_bar,
+                                                    __nv_bfloat16* sy, const ScanParams& p, int ch0, int b, int dir,
+                                                    const CUtensorMap* mapU, const CUtensorMap* mapZ,
+                                                    const CUtensorMap* mapD) {
+    using SM = ScanSmem<P, NDBL, ZT>;
+    constexpr uint32_t FULL = 0xffffffffu;
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int half = lane >> 4, cl = lane & 15;
+    const int chl = warp * 16 + cl;
+    const int L = p.L;
+    const int ntiles = (L + SC_TT - 1) / SC_TT;
+    const int d = ch0 + chl;
+    const size_t pd = size_t(dir) * p.di + d;
+    float2 h2[4], A2[4];
+    float wdt[R];
+    {
+        const float4* ap = reinterpret_cast<const float4*>(p.A2 + pd * SC_NS + half * 8);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const float4 a = ap[q];
+            A2[2 * q] = make_float2(a.x, a.y);
+            A2[2 * q + 1] = make_float2(a.z, a.w);
+        }
+        const float4* wp = reinterpret_cast<const float4*>(p.w_dt + pd * R);
+#pragma unroll
+        for (int q = 0; q < R / 4; ++q) {
+            const float4 w = wp[q];
+            wdt[4 * q] = w.x;
+            wdt[4 * q + 1] = w.y;
+            wdt[4 * q + 2] = w.z;
+            wdt[4 * q + 3] = w.w;
+        }
+        if (p.h_in) {
+            const float4* hp =
+                reinterpret_cast<const float4*>(p.h_in + ((size_t(dir) * p.batch + b) * p.di + d) * SC_NS + half * 8);
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const float4 a = hp[q];
+                h2[2 * q] = make_float2(a.x, a.y);
+                h2[2 * q + 1] = make_float2(a.z, a.w);
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) h2[q] = make_float2(0.f, 0.f);
+        }
+    }
+    const float bias = p.dt_bias[pd];
+    const float Dv = p.Dskip[pd];
+    // polynomial exp2 needs dl * A2 >= -126 for its KP pairs: clamp delta for those pairs only
+    float dl_lim = 3.0e38f;
+    if (KP > 0) {
+        float amin = -1e-30f;
+#pragma unroll
+        for (int q = 0; q < KP; ++q) amin = fminf(amin, fminf(A2[q].x, A2[q].y));
+        dl_lim = -125.f / amin;
+    }
+    const size_t M = size_t(p.batch) * L;
+    const size_t y_plane = M * 2 * p.di;
+    // this warp's 16-channel column block of y; rows are 2*di bf16 apart
+    __nv_bfloat16* ywarp = p.y + size_t(dir) * p.di + ch0 + warp * 16;
+    uint16_t* sy_w = reinterpret_cast<uint16_t*>(sy) + warp * (P * SC_TT * 16);  // warp-private staging [P][TT][16]
+    const int src0 = cl, src1 = cl | 16;
+
+    // per-row scalars of the tile in flight: slot k <-> row 2k + half
+    float dmine[SC_TT / 2], dumine[SC_TT / 2], umine[SC_TT / 2];
+    auto prep_row = [&](int k, const uint8_t* st, int nvalid_t) {
+        const __nv_bfloat16* su_h = reinterpret_cast<const __nv_bfloat16*>(st) + half * SC_CH + chl;
+        const float* drow = reinterpret_cast<const float*>(st + SM::U_BYTES + SM::Z_BYTES) + (2 * k + half) * NDBL;
+        float acc0 = bias, acc1 = 0.f;
+#pragma unroll
+        for (int q = 0; q < R / 4; ++q) {
+            const float4 x = *reinterpret_cast<const float4*>(drow + 4 * q);
+            acc0 = fmaf(x.x, wdt[4 * q], acc0);
+            acc1 = fmaf(x.y, wdt[4 * q + 1], acc1);
+            acc0 = fmaf(x.z, wdt[4 * q + 2], acc0);
+            acc1 = fmaf(x.w, wdt[4 * q + 3], acc1);
+        }
+        float dl = softplus_1mufu(acc0 + acc1);
+        dl = (2 * k + half < nvalid_t) ? dl : 0.f;  // rows past the utterance end: exp2(0)=1, dBu=0 -> state unchanged
+        float uval = bf16_bits_to_float(su_h + k * 2 * SC_CH);
+        if (P == 2) uval += bf16_bits_to_float(su_h + SC_TT * SC_CH + k * 2 * SC_CH);
+        dmine[k] = dl;
+        dumine[k] = dl * uval;
+        umine[k] = uval;
+    };
+    auto make_exps = [&](float2(&ex)[4], float dl) {
+        const float2 dl2 = make_float2(dl, dl);
+        const float dlc = fminf(dl, dl_lim);
+        const float2 dlc2 = make_float2(dlc, dlc);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (q < KP) {
+                ex[q] = ex2_poly2(dlc2, A2[q]);
+            } else {
+                const float2 a = __fmul2_rn(dl2, A2[q]);
+                ex[q] = make_float2(ex2_approx(a.x), ex2_approx(a.y));
+            }
+        }
+    };
+
+    // No producer warp: lane 0 of warp 0 issues the TMA loads.  Tile i+3 (processing order) is requested at the start
+    // of tile i into the stage tile i-2 used (5-stage ring), whose "empty" barrier has normally completed long before (no stall);
+    // an even warp count per CTA also lifts the register cap from 96 to 128 at two CTAs per SM.
+    auto issue_tile = [&](int i2, int stg) {
+        const int tile2 = REV ? (ntiles - 1 - i2) : i2;
+        const int row0 = b * L + tile2 * SC_TT;
+        mbar_arrive_expect_tx(&full_bar[stg], SM::STAGE_BYTES);
+        uint8_t* dst = smem + stg * SM::STAGE_BYTES;
+        tma_load_3d(dst, mapU, &full_bar[stg], dir * p.di + ch0, row0, 0);
+        tma_load_2d(dst + SM::U_BYTES, mapZ, &full_bar[stg], p.z_col0 + ch0, row0);
+        tma_load_2d(dst + SM::U_BYTES + SM::Z_BYTES, mapD, &full_bar[stg], dir * p.n_dbl, row0);
+    };
+    if (tid == 0) {
+        issue_tile(0, 0);
+        if (ntiles > 1) issue_tile(1, 1);
+        if (ntiles > 2) issue_tile(2, 2);
+    }
+    int stage = 0;
+    uint32_t phase = 0;
+    // prologue: rows of the first tile
+    {
+        const int tile0 = REV ? (ntiles - 1) : 0;
+        mbar_wait(&full_bar[0], 0);
+        const int nv0 = min(SC_TT, L - tile0 * SC_TT);
+#pragma unroll
+        for (int k = 0; k < SC_TT / 2; ++k) prep_row(k, smem, nv0);
+    }
+    for (int i = 0; i < ntiles; ++i) {
+        const int tile = REV ? (ntiles - 1 - i) : i;
+        const int t0 = tile * SC_TT;
+        const int nvalid = min(SC_TT, L - t0);
+        const uint8_t* st = smem + stage * SM::STAGE_BYTES;
+        const ZT* sz = reinterpret_cast<const ZT*>(st + SM::U_BYTES);
+        const float* sd = reinterpret_cast<const float*>(st + SM::U_BYTES + SM::Z_BYTES);
+        // the next tile's inputs are prepared while this tile is scanned
+        const bool has_next = i + 1 < ntiles;
+        const int stage_n = (stage + 1 == SC_STAGES) ? 0 : stage + 1;
+        const uint8_t* st_n = smem + stage_n * SM::STAGE_BYTES;
+        int nvalid_n = SC_TT;
+        if (tid == 0 && i + 3 < ntiles) {
+            // stage (i+3) % 5 was last used by tile i-2, whose "empty" phase (parity ((i-2)/5)&1) is long complete
+            const int stg3 = (stage + 3) % SC_STAGES;
+            if (i >= 2) mbar_wait(&empty_bar[stg3], uint32_t((i - 2) / SC_STAGES) & 1u);
+            issue_tile(i + 3, stg3);
+        }
+        if (has_next) {
+            const int tile_n = REV ? (tile - 1) : (tile + 1);
+            nvalid_n = min(SC_TT, L - tile_n * SC_TT);
+            mbar_wait(&full_bar[stage_n], (stage + 1 == SC_STAGES) ? (phase ^ 1) : phase);
+        }
+
+        // Software pipeline over the 16 steps of the tile (processing order jj, row j):
+        //   step jj issues   - the B/C shared-memory loads of step jj+1,
+        //                    - the (delta, delta*u) shuffles of step jj+2,
+        //                    - the 8 exps of step jj+1,
+        //                    - the finalisation of the row pair completed at step jj-1 (its y shuffle is in flight),
+        //   then updates the state with values that were all requested one or two steps earlier.
+        const float* sdB = sd + R + half * 8;  // this lane's 8 B values; its C values are 16 floats further
+        auto jrow = [](int jj) { return REV ? (SC_TT - 1 - jj) : jj; };
+        auto shfl_row = [&](const float(&arr)[SC_TT / 2], int jj) {
+            const int j = jrow(jj);
+            return __shfl_sync(FULL, arr[j >> 1], (j & 1) ? src1 : src0);
+        };
+        float2 e[4];
+        float4 Bc[2], Cc[2];
+        float du_c, dl_n, du_n;
+        {
+            const float dl0 = shfl_row(dmine, 0);
+            du_c = shfl_row(dumine, 0);
+            dl_n = shfl_row(dmine, 1);
+            du_n = shfl_row(dumine, 1);
+            const float* brow = sdB + jrow(0) * NDBL;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                Bc[q] = *reinterpret_cast<const float4*>(brow + 4 * q);
+                Cc[q] = *reinterpret_cast<const float4*>(brow + SC_NS + 4 * q);
+            }
+            make_exps(e, dl0);
+        }
+        auto finalize = [&](int k, float mine, float recv) {
+            const int row = 2 * k + half;
+            const float zval = ldz(sz + row * SC_CH + chl);
+            const float y = fmaf(Dv, umine[k], mine + recv) * (0.5f * zval);
+            const uint32_t hi = f2bf_lo(y);
+            sts_b16(sy_w + row * 16 + cl, hi);
+            if (P == 2) sts_b16(sy_w + SC_TT * 16 + row * 16 + cl, f2bf_lo(y - __uint_as_float(hi << 16)));
+            // slot k is free now: fill it with the next tile's row.  Unconditional on purpose (keeps the 16 steps one
+            // basic block): after the last tile it reads a stale stage and the values are never used.
+            prep_row(k, st_n, nvalid_n);
+        };
+        float yprev = 0.f, mine_p = 0.f, recv_p = 0.f;
+#pragma unroll
+        for (int jj = 0; jj < SC_TT; ++jj) {
+            const int j = jrow(jj);
+            float4 Bn[2], Cn[2];
+            float2 en[4];
+            float dl_nn = 0.f, du_nn = 0.f;
+            if (jj + 1 < SC_TT) {
+                const float* brow = sdB + jrow(jj + 1) * NDBL;
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    Bn[q] = *reinterpret_cast<const float4*>(brow + 4 * q);
+                    Cn[q] = *reinterpret_cast<const float4*>(brow + SC_NS + 4 * q);
+                }
+            }
+            if (jj + 2 < SC_TT) {
+                dl_nn = shfl_row(dmine, jj + 2);
+                du_nn = shfl_row(dumine, jj + 2);
+            }
+            if (jj + 1 < SC_TT) make_exps(en, dl_n);
+            if (jj >= 2 && (jj & 1) == 0) finalize(jrow(jj - 1) >> 1, mine_p, recv_p);
+            const float2 du2 = make_float2(du_c, du_c);
+            float2 ya = make_float2(0.f, 0.f), yb = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const float2 bu0 = __fmul2_rn(du2, make_float2(Bc[q].x, Bc[q].y));
+                const float2 bu1 = __fmul2_rn(du2, make_float2(Bc[q].z, Bc[q].w));
+                h2[2 * q] = __ffma2_rn(e[2 * q], h2[2 * q], bu0);
+                h2[2 * q + 1] = __ffma2_rn(e[2 * q + 1], h2[2 * q + 1], bu1);
+                ya = __ffma2_rn(h2[2 * q], make_float2(Cc[q].x, Cc[q].y), ya);
+                yb = __ffma2_rn(h2[2 * q + 1], make_float2(Cc[q].z, Cc[q].w), yb);
+            }
+            const float2 yab = __fadd2_rn(ya, yb);
+            const float ypart = yab.x + yab.y;
+            if ((jj & 1) == 0) {
+                yprev = ypart;
+            } else {
+                // rows {2k, 2k+1} are complete in both lane halves: half h will finalise row 2k + h (the row it
+                // prepared); it needs the partner's partial sum for that row.
+                const float y_r0 = REV ? ypart : yprev;  // partial sums of rows 2k / 2k+1 over this lane's 8 states
+                const float y_r1 = REV ? yprev : ypart;
+                mine_p = half ? y_r1 : y_r0;
+                recv_p = __shfl_xor_sync(FULL, half ? y_r0 : y_r1, 16);
+            }
+            if (jj + 1 < SC_TT) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) e[q] = en[q];
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    Bc[q] = Bn[q];
+                    Cc[q] = Cn[q];
+                }
+                du_c = du_n;
+                dl_n = dl_nn;
+                du_n = du_nn;
+            }
+        }
+        finalize(jrow(SC_TT - 1) >> 1, mine_p, recv_p);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[stage]);  // inputs of this stage are consumed
+        // ---- flush this warp's staged y rows: 2 lanes x 16 B cover one 32-byte row segment
+#pragma unroll
+        for (int pl = 0; pl < P; ++pl) {
+            const int row = lane >> 1;
+            const int seg = lane & 1;
+            if (row < nvalid) {
+                const uint4 v = *reinterpret_cast<const uint4*>(sy_w + pl * SC_TT * 16 + row * 16 + seg * 8);
+                const size_t off = (size_t(b) * L + t0 + row) * (2 * size_t(p.di)) + seg * 8;
+                *reinterpret_cast<uint4*>(ywarp + pl * y_plane + off) = v;
+            }
+        }
+        __syncwarp();
+        if (++stage == SC_STAGES) {
+            stage = 0;
+            phase ^= 1;
+        }
+    }
+    if (p.h_out) {
+        float4* hp = reinterpret_cast<float4*>(p.h_out + ((size_t(dir) * p.batch + b) * p.di + d) * SC_NS + half * 8);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) hp[q] = make_float4(h2[2 * q].x, h2[2 * q].y, h2[2 * q + 1].x, h2[2 * q + 1].y);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// One-thread-per-channel mapping (variant 1): 128 consumer threads per CTA, 16 states per thread.
+// ---------------------------------------------------------------------------------------------------------------
 template <int P, int R, int NDBL, typename ZT, bool REV>
-__device__ __forceinline__ void scan_consumer(uint8_t* smem, uint64_t* full_bar, uint64_t* empty_bar,
-                                              __nv_bfloat16* sy, const ScanParams& p, int ch0, int b, int dir) {
+__device__ __forceinline__ void scan_consumer_full(uint8_t* smem, uint64_t* full_bar, uint64_t* empty_bar,
+                                                   __nv_bfloat16* sy, const ScanParams& p, int ch0, int b, int dir) {
     using SM = ScanSmem<P, NDBL, ZT>;
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -113,9 +450,8 @@ __device__ __forceinline__ void scan_consumer(uint8_t* smem, uint64_t* full_bar,
     const float Dv = p.Dskip[pd];
     const size_t M = size_t(p.batch) * L;
     const size_t y_plane = M * 2 * p.di;
-    // this warp's 32-channel column block of y; rows are 2*di bf16 apart
     __nv_bfloat16* ywarp = p.y + size_t(dir) * p.di + ch0 + warp * 32;
-    __nv_bfloat16* sy_w = sy + warp * (P * SC_TT * 32);  // warp-private staging [P][TT][32]
+    uint16_t* sy_w = reinterpret_cast<uint16_t*>(sy) + warp * (P * SC_TT * 32);  // warp-private staging [P][TT][32]
 
     int stage = 0;
     uint32_t phase = 0;
@@ -129,7 +465,6 @@ __device__ __forceinline__ void scan_consumer(uint8_t* smem, uint64_t* full_bar,
         const ZT* sz = reinterpret_cast<const ZT*>(st + SM::U_BYTES);
         const float* sd = reinterpret_cast<const float*>(st + SM::U_BYTES + SM::Z_BYTES);
 
-        // ---- phase A: per-step scalars for the whole tile (16 independent chains -> ILP)
         float delta[SC_TT], du[SC_TT];
 #pragma unroll
         for (int j = 0; j < SC_TT; ++j) {
@@ -144,13 +479,12 @@ __device__ __forceinline__ void scan_consumer(uint8_t* smem, uint64_t* full_bar,
                 acc1 = fmaf(x.w, wdt[4 * q + 3], acc1);
             }
             float dl = softplus_1mufu(acc0 + acc1);
-            dl = (j < nvalid) ? dl : 0.f;  // rows past the utterance end: exp2(0)=1, dBu=0 -> state unchanged
-            float uval = __bfloat162float(su[j * SC_CH + tid]);
-            if (P == 2) uval += __bfloat162float(su[SC_TT * SC_CH + j * SC_CH + tid]);
+            dl = (j < nvalid) ? dl : 0.f;
+            float uval = bf16_bits_to_float(su + j * SC_CH + tid);
+            if (P == 2) uval += bf16_bits_to_float(su + SC_TT * SC_CH + j * SC_CH + tid);
             delta[j] = dl;
             du[j] = dl * uval;
         }
-        // ---- phase B: the recurrence, steps in processing order; exps of later steps are independent of h
 #pragma unroll
         for (int jj = 0; jj < SC_TT; ++jj) {
             const int j = REV ? (SC_TT - 1 - jj) : jj;
@@ -177,22 +511,21 @@ __device__ __forceinline__ void scan_consumer(uint8_t* smem, uint64_t* full_bar,
                     yb = __ffma2_rn(h2[2 * q + 1], make_float2(Cq.z, Cq.w), yb);
                 }
             }
-            float uval = __bfloat162float(su[j * SC_CH + tid]);
-            if (P == 2) uval += __bfloat162float(su[SC_TT * SC_CH + j * SC_CH + tid]);
+            float uval = bf16_bits_to_float(su + j * SC_CH + tid);
+            if (P == 2) uval += bf16_bits_to_float(su + SC_TT * SC_CH + j * SC_CH + tid);
             const float zval = ldz(sz + j * SC_CH + tid);
             const float y = ((ya.x + ya.y) + (yb.x + yb.y) + Dv * uval) * (0.5f * zval);
             if (P == 2) {
-                __nv_bfloat16 hi, lo;
-                split_bf16(y, hi, lo);
+                const uint16_t hi = f2bf_bits(y);
+                const uint16_t lo = f2bf_bits(y - __uint_as_float(uint32_t(hi) << 16));
                 sy_w[j * 32 + lane] = hi;
                 sy_w[SC_TT * 32 + j * 32 + lane] = lo;
             } else {
-                sy_w[j * 32 + lane] = __float2bfloat16_rn(y);
+                sy_w[j * 32 + lane] = f2bf_bits(y);
             }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_bar[stage]);  // inputs of this stage are consumed
-        // ---- flush this warp's staged y rows: 4 lanes x 16 B cover one 64-byte row segment
+        if (lane == 0) mbar_arrive(&empty_bar[stage]);
 #pragma unroll
         for (int pl = 0; pl < P; ++pl) {
 #pragma unroll
@@ -220,8 +553,9 @@ __device__ __forceinline__ void scan_consumer(uint8_t* smem, uint64_t* full_bar,
     }
 }
 
-template <int P, int R, int NDBL, typename ZT>
-__global__ void __launch_bounds__(SC_CH + 32)
+// NCONS consumer threads (256: split mapping with KP polynomial pairs, 128: one thread per channel) + 1 producer warp.
+template <int P, int R, int NDBL, typename ZT, int NCONS, int KP>
+__global__ void __launch_bounds__(NCONS == 256 ? 256 : NCONS + 32, 2)
 scan_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUtensorMap mapZ,
             const __grid_constant__ CUtensorMap mapD, const ScanParams p) {
     using SM = ScanSmem<P, NDBL, ZT>;
@@ -234,9 +568,16 @@ scan_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CU
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    const int ch0 = blockIdx.x * SC_CH;
+    const int nchb = p.di / SC_CH;
+    int ch0, dir;
+    if (p.dirmap == 1) {  // direction = blockIdx.x & 1: the CTAs sharing an SM run the same direction
+        ch0 = (p.ndirs == 2 ? (blockIdx.x >> 1) : blockIdx.x) * SC_CH;
+        dir = p.dir0 + (p.ndirs == 2 ? int(blockIdx.x & 1) : 0);
+    } else {              // direction-major: blockIdx.x = dir * nchb + channel block
+        ch0 = (blockIdx.x % nchb) * SC_CH;
+        dir = p.dir0 + blockIdx.x / nchb;
+    }
     const int b = blockIdx.y;
-    const int dir = p.dir0 + blockIdx.z;
     const bool rev = dir == 1;
     const int L = p.L;
     const int ntiles = (L + SC_TT - 1) / SC_TT;
@@ -247,13 +588,13 @@ scan_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CU
         tma_prefetch_desc(&mapD);
         for (int s = 0; s < SC_STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], SC_CH / 32);
+            mbar_init(&empty_bar[s], NCONS / 32);
         }
         fence_barrier_init();
     }
     __syncthreads();
 
-    if (warp == SC_CH / 32) {
+    if (NCONS != 256 && warp == NCONS / 32) {
         // ------------------------------------------------------------ TMA producer
         if (lane == 0) {
             int stage = 0;
@@ -261,7 +602,7 @@ scan_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CU
             for (int i = 0; i < ntiles; ++i) {
                 const int tile = rev ? (ntiles - 1 - i) : i;
                 const int row0 = b * L + tile * SC_TT;
-                mbar_wait(&empty_bar[stage], phase ^ 1);
+                mbar_wait_sleep(&empty_bar[stage], phase ^ 1);  // back off: leave the issue slots to the consumers
                 mbar_arrive_expect_tx(&full_bar[stage], SM::STAGE_BYTES);
                 uint8_t* st = smem + stage * SM::STAGE_BYTES;
                 tma_load_3d(st, &mapU, &full_bar[stage], dir * p.di + ch0, row0, 0);
@@ -275,13 +616,20 @@ scan_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CU
         }
         return;
     }
-    if (rev)
-        scan_consumer<P, R, NDBL, ZT, true>(smem, full_bar, empty_bar, sy, p, ch0, b, dir);
-    else
-        scan_consumer<P, R, NDBL, ZT, false>(smem, full_bar, empty_bar, sy, p, ch0, b, dir);
+    if (NCONS == 256) {
+        if (rev)
+            scan_consumer_split<P, R, NDBL, ZT, true, KP>(smem, full_bar, empty_bar, sy, p, ch0, b, dir, &mapU, &mapZ, &mapD);
+        else
+            scan_consumer_split<P, R, NDBL, ZT, false, KP>(smem, full_bar, empty_bar, sy, p, ch0, b, dir, &mapU, &mapZ, &mapD);
+    } else {
+        if (rev)
+            scan_consumer_full<P, R, NDBL, ZT, true>(smem, full_bar, empty_bar, sy, p, ch0, b, dir);
+        else
+            scan_consumer_full<P, R, NDBL, ZT, false>(smem, full_bar, empty_bar, sy, p, ch0, b, dir);
+    }
 }
 
-template <int P, int R, int NDBL, typename ZT>
+template <int P, int R, int NDBL, typename ZT, int NCONS, int KP>
 static int launch_scan(const mtn_scan_args* a, cudaStream_t stream) {
     using SM = ScanSmem<P, NDBL, ZT>;
     const uint64_t M = uint64_t(a->batch) * a->L;
@@ -323,7 +671,10 @@ static int launch_scan(const mtn_scan_args* a, cudaStream_t stream) {
     p.z_col0 = a->z_col0;
     p.dir0 = (a->dir_mask & 1) ? 0 : 1;
     const int ndirs = (a->dir_mask == 3) ? 2 : 1;
-    auto kern = scan_kernel<P, R, NDBL, ZT>;
+    p.ndirs = ndirs;
+    p.dirmap = 0;
+    if (const char* v = getenv("MTN_SCAN_DIRMAP")) p.dirmap = atoi(v);
+    auto kern = scan_kernel<P, R, NDBL, ZT, NCONS, KP>;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL);
@@ -333,18 +684,31 @@ static int launch_scan(const mtn_scan_args* a, cudaStream_t stream) {
         }
         attr_set = true;
     }
-    dim3 grid(a->di / SC_CH, a->batch, ndirs);
-    kern<<<grid, SC_CH + 32, SM::TOTAL, stream>>>(mapU, mapZ, mapD, p);
+    dim3 grid(ndirs * (a->di / SC_CH), a->batch, 1);
+    kern<<<grid, NCONS == 256 ? 256 : NCONS + 32, SM::TOTAL, stream>>>(mapU, mapZ, mapD, p);
     MTN_CUDA_LAUNCH_CHECK("scan");
     return MTN_OK;
 }
 
+template <int P, int R, int NDBL, typename ZT>
+static int dispatch_scan_variant(const mtn_scan_args* a, cudaStream_t s) {
+    int variant = 0;
+    if (const char* v = getenv("MTN_SCAN_VARIANT")) variant = atoi(v);
+    switch (variant) {
+        case 0: return launch_scan<P, R, NDBL, ZT, 256, 0>(a, s);
+        case 1: return launch_scan<P, R, NDBL, ZT, 128, 0>(a, s);
+        case 11: return launch_scan<P, R, NDBL, ZT, 256, 1>(a, s);
+        case 12: return launch_scan<P, R, NDBL, ZT, 256, 2>(a, s);
+        default: set_error("scan: unknown MTN_SCAN_VARIANT=%d", variant); return MTN_EINVAL;
+    }
+}
+
 template <int P, typename ZT>
 static int dispatch_scan_r(const mtn_scan_args* a, cudaStream_t s) {
-    if (a->R == 4 && a->n_dbl == 48) return launch_scan<P, 4, 48, ZT>(a, s);
-    if (a->R == 8 && a->n_dbl == 48) return launch_scan<P, 8, 48, ZT>(a, s);
-    if (a->R == 16 && a->n_dbl == 48) return launch_scan<P, 16, 48, ZT>(a, s);
-    if (a->R == 32 && a->n_dbl == 64) return launch_scan<P, 32, 64, ZT>(a, s);
+    if (a->R == 4 && a->n_dbl == 48) return dispatch_scan_variant<P, 4, 48, ZT>(a, s);
+    if (a->R == 8 && a->n_dbl == 48) return dispatch_scan_variant<P, 8, 48, ZT>(a, s);
+    if (a->R == 16 && a->n_dbl == 48) return dispatch_scan_variant<P, 16, 48, ZT>(a, s);
+    if (a->R == 32 && a->n_dbl == 64) return dispatch_scan_variant<P, 32, 64, ZT>(a, s);
     set_error("scan: unsupported dt_rank R=%d / n_dbl=%d (supported: 4|8|16 with 48, 32 with 64)", a->R, a->n_dbl);
     return MTN_EINVAL;
 }

@@ -11,6 +11,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--hparams", default="S"); ap.add_argument("--batch", type=int, default=32)
 ap.add_argument("--L", type=int, default=3999); ap.add_argument("--mode", default="fp32")
 ap.add_argument("--iters", type=int, default=20)
+ap.add_argument("--variants", default="0", help="comma list of MTN_SCAN_VARIANT values to time (first = reference for the diff)")
 a = ap.parse_args()
 hp = CONFIGS[a.hparams]; di, R = hp.d_inner, hp.dt_rank; nd = ops.n_dbl_for(R)
 P = 2 if a.mode == "fp32" else 1
@@ -26,14 +27,24 @@ A2 = -torch.exp(torch.randn(2, di, 16, device=dev, generator=g) * 0.5 + 0.5) * o
 Dk = torch.randn(2, di, device=dev, generator=g)
 y = torch.empty_like(u)
 run = lambda: ops.scan(u, dbl, xz, di, w_dt, dt_bias, A2, Dk, a.batch, a.L, di, R, y=y)
-for _ in range(3): run()
-torch.cuda.synchronize()
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record()
-for _ in range(a.iters): run()
-e1.record(); torch.cuda.synchronize()
-ms = e0.elapsed_time(e1) / a.iters
 s_io = 4 if P == 2 else 2
 alg = 2 * (M * (4 * di + 32) * s_io + (di * 16 + 2 * di) * 4)
-print(json.dumps({"scan_ms": ms, "alg_GBps": alg / ms / 1e6, "frac_of_6541": alg / ms / 1e6 / 6541.1,
-                  "mufu_bound_ms@1965": 2 * M * di * 16 / (148 * 16 * 1.965e9) * 1e3, "shape": [a.hparams, a.batch, a.L, a.mode]}))
+y_ref = None
+for var in a.variants.split(","):
+    os.environ["MTN_SCAN_VARIANT"] = var
+    y.zero_()
+    for _ in range(3): run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.iters): run()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / a.iters
+    yv = y.float().sum(0)
+    if y_ref is None:
+        y_ref = yv.clone()
+    diff = ((yv - y_ref).abs().max() / y_ref.pow(2).mean().sqrt()).item()
+    print(json.dumps({"variant": var, "scan_ms": round(ms, 4), "alg_GBps": round(alg / ms / 1e6, 1),
+                      "frac_of_6541": round(alg / ms / 1e6 / 6541.1, 4), "max_abs_diff_vs_first/rms": diff,
+                      "mufu_bound_ms@1965": round(2 * M * di * 16 / (148 * 16 * 1.965e9) * 1e3, 4),
+                      "shape": [a.hparams, a.batch, a.L, a.mode]}), flush=True)
