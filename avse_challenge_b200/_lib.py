@@ -14,7 +14,8 @@ LIB_PATH = os.path.join(_HERE, "libmtn_b200.so")
 EPI_STORE, EPI_INPROJ, EPI_MASK, EPI_RELU = 0, 1, 2, 3
 
 EXPORTS = [
-    "mtn_encoder_cln_fwd", "mtn_gemm_fwd", "mtn_add_rmsnorm_fwd", "mtn_conv_silu_fwd", "mtn_scan_fwd",
+    "mtn_encoder_cln_fwd", "mtn_gemm_fwd", "mtn_add_rmsnorm_fwd", "mtn_conv_silu_fwd", "mtn_conv_silu_halo_fwd",
+    "mtn_scan_fwd", "mtn_fold_states_fwd",
     "mtn_decoder_fwd", "mtn_cln_fwd", "mtn_split_planes", "mtn_last_error_string", "mtn_abi_version",
 ]
 
@@ -35,6 +36,7 @@ class ScanArgs(Structure):
         ("A2", c_void_p), ("Dskip", c_void_p), ("y", c_void_p), ("h_in", c_void_p), ("h_out", c_void_p),
         ("batch", c_int), ("L", c_int), ("di", c_int), ("R", c_int), ("n_dbl", c_int), ("ld_dbl", c_int),
         ("ldz", c_int), ("z_col0", c_int), ("planes", c_int), ("z_bf16", c_int), ("dir_mask", c_int),
+        ("sum_delta", c_void_p), ("L_last", c_int),
     ]
 
 
@@ -64,7 +66,10 @@ def load():
                                         c_void_p]
     lib.mtn_conv_silu_fwd.argtypes = [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                       c_void_p]
+    lib.mtn_conv_silu_halo_fwd.argtypes = [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                                           c_void_p, c_int, c_int, c_int, c_int, c_void_p]
     lib.mtn_scan_fwd.argtypes = [POINTER(ScanArgs), c_void_p]
+    lib.mtn_fold_states_fwd.argtypes = [c_void_p] * 6 + [c_int] * 5 + [c_void_p]
     lib.mtn_decoder_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]
     lib.mtn_cln_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p]
     lib.mtn_split_planes.argtypes = [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p]

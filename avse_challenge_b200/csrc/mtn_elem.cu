@@ -245,14 +245,14 @@ constexpr int CONV_TT = 32;
 template <int P, typename XT>
 __global__ void __launch_bounds__(256)
 conv_silu_kernel(const XT* __restrict__ xz, int ldxz, const float* __restrict__ conv_w, const float* __restrict__ conv_b,
-                 __nv_bfloat16* __restrict__ u, int batch, int L, int di) {
+                 __nv_bfloat16* __restrict__ u, size_t u_rows, const float* __restrict__ halo_lo,
+                 const float* __restrict__ halo_hi, int batch, int L, int di) {
     const int c = (blockIdx.z * blockDim.x + threadIdx.x) * 4;
     if (c >= di) return;
     const int b = blockIdx.y;
     const int t0 = blockIdx.x * CONV_TT;
     const int t1 = min(t0 + CONV_TT, L);
-    const size_t M = size_t(batch) * L;
-    const size_t plane_stride = M * 2 * di;
+    const size_t plane_stride = u_rows * 2 * di;
     float4 wf[4], wb[4];  // wf[k] = tap k for channels c..c+3
     {
         float tf[4][4], tb[4][4];
@@ -273,7 +273,14 @@ conv_silu_kernel(const XT* __restrict__ xz, int ldxz, const float* __restrict__ 
     const float4 bb = *reinterpret_cast<const float4*>(conv_b + di + c);
     const XT* xbase = xz + size_t(b) * L * ldxz + c;
     const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-    auto ld = [&](int t) -> float4 { return (t >= 0 && t < L) ? load_x4<XT>(xbase + size_t(t) * ldxz) : zero; };
+    // rows outside [0, L): the neighbouring chunk's rows when a halo is given, else the zero padding of the conv
+    const float* hlo = halo_lo ? halo_lo + size_t(b) * 3 * di + c : nullptr;
+    const float* hhi = halo_hi ? halo_hi + size_t(b) * 3 * di + c : nullptr;
+    auto ld = [&](int t) -> float4 {
+        if (t >= 0 && t < L) return load_x4<XT>(xbase + size_t(t) * ldxz);
+        if (t < 0) return (hlo && t >= -3) ? *reinterpret_cast<const float4*>(hlo + size_t(t + 3) * di) : zero;
+        return (hhi && t < L + 3) ? *reinterpret_cast<const float4*>(hhi + size_t(t - L) * di) : zero;
+    };
     // window w[i] = x[t - 3 + i], i = 0..6
     float4 w0 = ld(t0 - 3), w1 = ld(t0 - 2), w2 = ld(t0 - 1), w3 = ld(t0), w4 = ld(t0 + 1), w5 = ld(t0 + 2), w6;
     for (int t = t0; t < t1; t += 4) {
@@ -475,10 +482,18 @@ extern "C" int mtn_add_rmsnorm_fwd(const float* h, float* res, int res_valid, co
 
 extern "C" int mtn_conv_silu_fwd(const void* xz, int ldxz, int xz_bf16, const float* conv_w, const float* conv_b,
                                  void* u_planes, int batch, int L, int di, int planes, mtn_stream_t stream) {
+    return mtn_conv_silu_halo_fwd(xz, ldxz, xz_bf16, conv_w, conv_b, u_planes, batch * L, nullptr, nullptr, batch, L, di,
+                                  planes, stream);
+}
+
+extern "C" int mtn_conv_silu_halo_fwd(const void* xz, int ldxz, int xz_bf16, const float* conv_w, const float* conv_b,
+                                      void* u_planes, int u_rows, const float* halo_lo, const float* halo_hi,
+                                      int batch, int L, int di, int planes, mtn_stream_t stream) {
     MTN_REQUIRE(xz && conv_w && conv_b && u_planes, "conv_silu: null pointer");
     MTN_REQUIRE(batch > 0 && L > 0 && di > 0 && di % 4 == 0 && ldxz % 4 == 0, "conv_silu: bad shape");
     MTN_REQUIRE(planes == 1 || planes == 2, "conv_silu: planes=%d", planes);
     MTN_REQUIRE(batch <= 65535, "conv_silu: batch too large for grid.y");
+    MTN_REQUIRE(u_rows >= batch * L, "conv_silu: u_rows=%d < batch*L=%d", u_rows, batch * L);
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     const int threads_needed = di / 4;
     const int block = threads_needed >= 256 ? 256 : ((threads_needed + 31) / 32) * 32;
@@ -486,12 +501,12 @@ extern "C" int mtn_conv_silu_fwd(const void* xz, int ldxz, int xz_bf16, const fl
     __nv_bfloat16* u = reinterpret_cast<__nv_bfloat16*>(u_planes);
     if (xz_bf16) {
         const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(xz);
-        if (planes == 2) conv_silu_kernel<2, __nv_bfloat16><<<grid, block, 0, s>>>(x, ldxz, conv_w, conv_b, u, batch, L, di);
-        else conv_silu_kernel<1, __nv_bfloat16><<<grid, block, 0, s>>>(x, ldxz, conv_w, conv_b, u, batch, L, di);
+        if (planes == 2) conv_silu_kernel<2, __nv_bfloat16><<<grid, block, 0, s>>>(x, ldxz, conv_w, conv_b, u, size_t(u_rows), halo_lo, halo_hi, batch, L, di);
+        else conv_silu_kernel<1, __nv_bfloat16><<<grid, block, 0, s>>>(x, ldxz, conv_w, conv_b, u, size_t(u_rows), halo_lo, halo_hi, batch, L, di);
     } else {
         const float* x = reinterpret_cast<const float*>(xz);
-        if (planes == 2) conv_silu_kernel<2, float><<<grid, block, 0, s>>>(x, ldxz, conv_w, conv_b, u, batch, L, di);
-        else conv_silu_kernel<1, float><<<grid, block, 0, s>>>(x, ldxz, conv_w, conv_b, u, batch, L, di);
+        if (planes == 2) conv_silu_kernel<2, float><<<grid, block, 0, s>>>(x, ldxz, conv_w, conv_b, u, size_t(u_rows), halo_lo, halo_hi, batch, L, di);
+        else conv_silu_kernel<1, float><<<grid, block, 0, s>>>(x, ldxz, conv_w, conv_b, u, size_t(u_rows), halo_lo, halo_hi, batch, L, di);
     }
     MTN_CUDA_LAUNCH_CHECK("conv_silu");
     return MTN_OK;

@@ -21,7 +21,7 @@
 // KP > 0 moves KP of every 4 state pairs of a lane to an FMA-pipe polynomial exp2 (Cody-Waite + degree-5 minimax,
 // 2e-7 relative) to balance the MUFU and FMA pipes.  See DESIGN.md for both rooflines.
 // MTN_SCAN_VARIANT (debug knob, read per call): 0/unset = split mapping; 1 = one thread per channel (A/B baseline);
-// 10+k = split mapping with KP = k polynomial pairs.
+// 11 = split mapping with KP = 1 polynomial pair per lane.
 #include "mtn_ptx.cuh"
 #include "mtn_host.h"
 #include <stdlib.h>
@@ -41,7 +41,9 @@ struct ScanParams {
     __nv_bfloat16* y;
     const float* h_in;
     float* h_out;
+    float* sum_delta;
     int batch, L, di, n_dbl, z_col0;
+    int L_last;  // valid length of the last sequence of the batch (== L when not ragged)
     int dir0;   // first direction of this launch
     int ndirs;  // 1 or 2
     int dirmap; // how blockIdx.x maps to (direction, channel block); see scan_kernel
@@ -125,7 +127,7 @@ __device__ __forceinline__ uint32_t f2bf_lo(float x) {
     return r;
 }
 
-template <int P, int R, int NDBL, typename ZT, bool REV, int KP>
+template <int P, int R, int NDBL, typename ZT, bool REV, int KP, bool WY>
 __device__ __forceinline__ void scan_consumer_split(uint8_t* smem, uint64_t* full_bar, uint64_t* empty_bar,
                                                     __nv_bfloat16* sy, const ScanParams& p, int ch0, int b, int dir,
                                                     const CUtensorMap* mapU, const CUtensorMap* mapZ,
@@ -136,10 +138,12 @@ __device__ __forceinline__ void scan_consumer_split(uint8_t* smem, uint64_t* ful
     const int warp = tid >> 5, lane = tid & 31;
     const int half = lane >> 4, cl = lane & 15;
     const int chl = warp * 16 + cl;
-    const int L = p.L;
-    const int ntiles = (L + SC_TT - 1) / SC_TT;
+    const int L = p.L;                                       // row stride between sequences
+    const int Lb = (b == p.batch - 1) ? p.L_last : p.L;      // valid steps of this sequence
+    const int ntiles = (Lb + SC_TT - 1) / SC_TT;
     const int d = ch0 + chl;
     const size_t pd = size_t(dir) * p.di + d;
+    float sdl = 0.f;  // sum of this lane's deltas (rows 2k + half)
     float2 h2[4], A2[4];
     float wdt[R];
     {
@@ -208,6 +212,7 @@ __device__ __forceinline__ void scan_consumer_split(uint8_t* smem, uint64_t* ful
         dl = (2 * k + half < nvalid_t) ? dl : 0.f;  // rows past the utterance end: exp2(0)=1, dBu=0 -> state unchanged
         float uval = bf16_bits_to_float(su_h + k * 2 * SC_CH);
         if (P == 2) uval += bf16_bits_to_float(su_h + SC_TT * SC_CH + k * 2 * SC_CH);
+        sdl += dl;
         dmine[k] = dl;
         dumine[k] = dl * uval;
         umine[k] = uval;
@@ -250,14 +255,14 @@ __device__ __forceinline__ void scan_consumer_split(uint8_t* smem, uint64_t* ful
     {
         const int tile0 = REV ? (ntiles - 1) : 0;
         mbar_wait(&full_bar[0], 0);
-        const int nv0 = min(SC_TT, L - tile0 * SC_TT);
+        const int nv0 = min(SC_TT, Lb - tile0 * SC_TT);
 #pragma unroll
         for (int k = 0; k < SC_TT / 2; ++k) prep_row(k, smem, nv0);
     }
     for (int i = 0; i < ntiles; ++i) {
         const int tile = REV ? (ntiles - 1 - i) : i;
         const int t0 = tile * SC_TT;
-        const int nvalid = min(SC_TT, L - t0);
+        const int nvalid = min(SC_TT, Lb - t0);
         const uint8_t* st = smem + stage * SM::STAGE_BYTES;
         const ZT* sz = reinterpret_cast<const ZT*>(st + SM::U_BYTES);
         const float* sd = reinterpret_cast<const float*>(st + SM::U_BYTES + SM::Z_BYTES);
@@ -265,7 +270,7 @@ __device__ __forceinline__ void scan_consumer_split(uint8_t* smem, uint64_t* ful
         const bool has_next = i + 1 < ntiles;
         const int stage_n = (stage + 1 == SC_STAGES) ? 0 : stage + 1;
         const uint8_t* st_n = smem + stage_n * SM::STAGE_BYTES;
-        int nvalid_n = SC_TT;
+        int nvalid_n = 0;  // no next tile: the (unconditional) row prep then yields delta = 0 everywhere
         if (tid == 0 && i + 3 < ntiles) {
             // stage (i+3) % 5 was last used by tile i-2, whose "empty" phase (parity ((i-2)/5)&1) is long complete
             const int stg3 = (stage + 3) % SC_STAGES;
@@ -274,7 +279,7 @@ __device__ __forceinline__ void scan_consumer_split(uint8_t* smem, uint64_t* ful
         }
         if (has_next) {
             const int tile_n = REV ? (tile - 1) : (tile + 1);
-            nvalid_n = min(SC_TT, L - tile_n * SC_TT);
+            nvalid_n = min(SC_TT, Lb - tile_n * SC_TT);
             mbar_wait(&full_bar[stage_n], (stage + 1 == SC_STAGES) ? (phase ^ 1) : phase);
         }
 
@@ -307,12 +312,14 @@ __device__ __forceinline__ void scan_consumer_split(uint8_t* smem, uint64_t* ful
             make_exps(e, dl0);
         }
         auto finalize = [&](int k, float mine, float recv) {
-            const int row = 2 * k + half;
-            const float zval = ldz(sz + row * SC_CH + chl);
-            const float y = fmaf(Dv, umine[k], mine + recv) * (0.5f * zval);
-            const uint32_t hi = f2bf_lo(y);
-            sts_b16(sy_w + row * 16 + cl, hi);
-            if (P == 2) sts_b16(sy_w + SC_TT * 16 + row * 16 + cl, f2bf_lo(y - __uint_as_float(hi << 16)));
+            if (WY) {
+                const int row = 2 * k + half;
+                const float zval = ldz(sz + row * SC_CH + chl);
+                const float y = fmaf(Dv, umine[k], mine + recv) * (0.5f * zval);
+                const uint32_t hi = f2bf_lo(y);
+                sts_b16(sy_w + row * 16 + cl, hi);
+                if (P == 2) sts_b16(sy_w + SC_TT * 16 + row * 16 + cl, f2bf_lo(y - __uint_as_float(hi << 16)));
+            }
             // slot k is free now: fill it with the next tile's row.  Unconditional on purpose (keeps the 16 steps one
             // basic block): after the last tile it reads a stale stage and the values are never used.
             prep_row(k, st_n, nvalid_n);
@@ -346,14 +353,16 @@ __device__ __forceinline__ void scan_consumer_split(uint8_t* smem, uint64_t* ful
                 const float2 bu1 = __fmul2_rn(du2, make_float2(Bc[q].z, Bc[q].w));
                 h2[2 * q] = __ffma2_rn(e[2 * q], h2[2 * q], bu0);
                 h2[2 * q + 1] = __ffma2_rn(e[2 * q + 1], h2[2 * q + 1], bu1);
-                ya = __ffma2_rn(h2[2 * q], make_float2(Cc[q].x, Cc[q].y), ya);
-                yb = __ffma2_rn(h2[2 * q + 1], make_float2(Cc[q].z, Cc[q].w), yb);
+                if (WY) {
+                    ya = __ffma2_rn(h2[2 * q], make_float2(Cc[q].x, Cc[q].y), ya);
+                    yb = __ffma2_rn(h2[2 * q + 1], make_float2(Cc[q].z, Cc[q].w), yb);
+                }
             }
             const float2 yab = __fadd2_rn(ya, yb);
             const float ypart = yab.x + yab.y;
             if ((jj & 1) == 0) {
                 yprev = ypart;
-            } else {
+            } else if (WY) {
                 // rows {2k, 2k+1} are complete in both lane halves: half h will finalise row 2k + h (the row it
                 // prepared); it needs the partner's partial sum for that row.
                 const float y_r0 = REV ? ypart : yprev;  // partial sums of rows 2k / 2k+1 over this lane's 8 states
@@ -382,7 +391,7 @@ __device__ __forceinline__ void scan_consumer_split(uint8_t* smem, uint64_t* ful
         for (int pl = 0; pl < P; ++pl) {
             const int row = lane >> 1;
             const int seg = lane & 1;
-            if (row < nvalid) {
+            if (WY && row < nvalid) {
                 const uint4 v = *reinterpret_cast<const uint4*>(sy_w + pl * SC_TT * 16 + row * 16 + seg * 8);
                 const size_t off = (size_t(b) * L + t0 + row) * (2 * size_t(p.di)) + seg * 8;
                 *reinterpret_cast<uint4*>(ywarp + pl * y_plane + off) = v;
@@ -398,6 +407,10 @@ __device__ __forceinline__ void scan_consumer_split(uint8_t* smem, uint64_t* ful
         float4* hp = reinterpret_cast<float4*>(p.h_out + ((size_t(dir) * p.batch + b) * p.di + d) * SC_NS + half * 8);
 #pragma unroll
         for (int q = 0; q < 2; ++q) hp[q] = make_float4(h2[2 * q].x, h2[2 * q].y, h2[2 * q + 1].x, h2[2 * q + 1].y);
+    }
+    if (p.sum_delta) {
+        const float tot = sdl + __shfl_xor_sync(FULL, sdl, 16);
+        if (half == 0) p.sum_delta[(size_t(dir) * p.batch + b) * p.di + d] = tot;
     }
 }
 
@@ -554,7 +567,7 @@ __device__ __forceinline__ void scan_consumer_full(uint8_t* smem, uint64_t* full
 }
 
 // NCONS consumer threads (256: split mapping with KP polynomial pairs, 128: one thread per channel) + 1 producer warp.
-template <int P, int R, int NDBL, typename ZT, int NCONS, int KP>
+template <int P, int R, int NDBL, typename ZT, int NCONS, int KP, bool WY>
 __global__ void __launch_bounds__(NCONS == 256 ? 256 : NCONS + 32, 2)
 scan_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUtensorMap mapZ,
             const __grid_constant__ CUtensorMap mapD, const ScanParams p) {
@@ -618,9 +631,9 @@ scan_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CU
     }
     if (NCONS == 256) {
         if (rev)
-            scan_consumer_split<P, R, NDBL, ZT, true, KP>(smem, full_bar, empty_bar, sy, p, ch0, b, dir, &mapU, &mapZ, &mapD);
+            scan_consumer_split<P, R, NDBL, ZT, true, KP, WY>(smem, full_bar, empty_bar, sy, p, ch0, b, dir, &mapU, &mapZ, &mapD);
         else
-            scan_consumer_split<P, R, NDBL, ZT, false, KP>(smem, full_bar, empty_bar, sy, p, ch0, b, dir, &mapU, &mapZ, &mapD);
+            scan_consumer_split<P, R, NDBL, ZT, false, KP, WY>(smem, full_bar, empty_bar, sy, p, ch0, b, dir, &mapU, &mapZ, &mapD);
     } else {
         if (rev)
             scan_consumer_full<P, R, NDBL, ZT, true>(smem, full_bar, empty_bar, sy, p, ch0, b, dir);
@@ -629,7 +642,7 @@ scan_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CU
     }
 }
 
-template <int P, int R, int NDBL, typename ZT, int NCONS, int KP>
+template <int P, int R, int NDBL, typename ZT, int NCONS, int KP, bool WY>
 static int launch_scan(const mtn_scan_args* a, cudaStream_t stream) {
     using SM = ScanSmem<P, NDBL, ZT>;
     const uint64_t M = uint64_t(a->batch) * a->L;
@@ -664,6 +677,8 @@ static int launch_scan(const mtn_scan_args* a, cudaStream_t stream) {
     p.y = reinterpret_cast<__nv_bfloat16*>(a->y);
     p.h_in = a->h_in;
     p.h_out = a->h_out;
+    p.sum_delta = a->sum_delta;
+    p.L_last = a->L_last > 0 ? a->L_last : a->L;
     p.batch = a->batch;
     p.L = a->L;
     p.di = a->di;
@@ -674,7 +689,7 @@ static int launch_scan(const mtn_scan_args* a, cudaStream_t stream) {
     p.ndirs = ndirs;
     p.dirmap = 0;
     if (const char* v = getenv("MTN_SCAN_DIRMAP")) p.dirmap = atoi(v);
-    auto kern = scan_kernel<P, R, NDBL, ZT, NCONS, KP>;
+    auto kern = scan_kernel<P, R, NDBL, ZT, NCONS, KP, WY>;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL);
@@ -694,11 +709,22 @@ template <int P, int R, int NDBL, typename ZT>
 static int dispatch_scan_variant(const mtn_scan_args* a, cudaStream_t s) {
     int variant = 0;
     if (const char* v = getenv("MTN_SCAN_VARIANT")) variant = atoi(v);
+    if (!a->y) {  // summary pass of the reduce-then-scan scheme: final states + sum(delta), no output
+        if (variant != 0) {
+            set_error("scan: y == NULL is only implemented by the default variant");
+            return MTN_EINVAL;
+        }
+        return launch_scan<P, R, NDBL, ZT, 256, 0, false>(a, s);
+    }
     switch (variant) {
-        case 0: return launch_scan<P, R, NDBL, ZT, 256, 0>(a, s);
-        case 1: return launch_scan<P, R, NDBL, ZT, 128, 0>(a, s);
-        case 11: return launch_scan<P, R, NDBL, ZT, 256, 1>(a, s);
-        case 12: return launch_scan<P, R, NDBL, ZT, 256, 2>(a, s);
+        case 0: return launch_scan<P, R, NDBL, ZT, 256, 0, true>(a, s);
+        case 1:
+            if (a->sum_delta || (a->L_last > 0 && a->L_last != a->L)) {
+                set_error("scan: sum_delta / L_last are not implemented by MTN_SCAN_VARIANT=1");
+                return MTN_EINVAL;
+            }
+            return launch_scan<P, R, NDBL, ZT, 128, 0, true>(a, s);
+        case 11: return launch_scan<P, R, NDBL, ZT, 256, 1, true>(a, s);
         default: set_error("scan: unknown MTN_SCAN_VARIANT=%d", variant); return MTN_EINVAL;
     }
 }
@@ -717,7 +743,9 @@ static int dispatch_scan_r(const mtn_scan_args* a, cudaStream_t s) {
 
 extern "C" int mtn_scan_fwd(const mtn_scan_args* a, mtn_stream_t stream) {
     using namespace mtn;
-    MTN_REQUIRE(a && a->u && a->dbl && a->z && a->w_dt && a->dt_bias && a->A2 && a->Dskip && a->y, "scan: null pointer");
+    MTN_REQUIRE(a && a->u && a->dbl && a->z && a->w_dt && a->dt_bias && a->A2 && a->Dskip, "scan: null pointer");
+    MTN_REQUIRE(a->y || a->h_out, "scan: y == NULL (summary pass) needs h_out");
+    MTN_REQUIRE(a->L_last >= 0 && a->L_last <= a->L, "scan: L_last=%d out of range (L=%d)", a->L_last, a->L);
     MTN_REQUIRE(a->batch > 0 && a->batch <= 65535 && a->L > 0, "scan: bad batch=%d L=%d", a->batch, a->L);
     MTN_REQUIRE(a->di > 0 && a->di % SC_CH == 0, "scan: di=%d must be a multiple of %d", a->di, SC_CH);
     MTN_REQUIRE(a->dir_mask >= 1 && a->dir_mask <= 3, "scan: dir_mask=%d", a->dir_mask);

@@ -105,30 +105,51 @@ def add_rmsnorm(h, res, res_valid, g, planes, eps=1e-5, xn=None):
     return xn
 
 
-def conv_silu(xz, conv_w, conv_b, batch, L, di, planes, u=None):
-    """xz [M, >= di] (fp32 or bf16; xs = first di columns) -> u planes [P, M, 2*di]."""
-    _req_cuda(xz, conv_w, conv_b)
+def conv_silu(xz, conv_w, conv_b, batch, L, di, planes, u=None, halo_lo=None, halo_hi=None):
+    """xz [M, >= di] (fp32 or bf16; xs = first di columns) -> u planes [P, M, 2*di].
+    ``halo_lo`` / ``halo_hi`` (fp32 [batch, 3, di]): xs rows just before / after this time chunk (None = zero pad)."""
+    _req_cuda(xz, conv_w, conv_b, halo_lo, halo_hi)
     M = batch * L
     if u is None:
         u = torch.empty((planes, M, 2 * di), dtype=torch.bfloat16, device=xz.device)
-    check(_lib.load().mtn_conv_silu_fwd(ptr(xz), xz.stride(0), int(xz.dtype == torch.bfloat16), ptr(conv_w),
-                                        ptr(conv_b), ptr(u), batch, L, di, planes, _stream()), "mtn_conv_silu_fwd")
+    for h in (halo_lo, halo_hi):
+        if h is not None:
+            assert h.dtype == torch.float32 and h.is_contiguous() and tuple(h.shape) == (batch, 3, di)
+    check(_lib.load().mtn_conv_silu_halo_fwd(ptr(xz), xz.stride(0), int(xz.dtype == torch.bfloat16), ptr(conv_w),
+                                             ptr(conv_b), ptr(u), u.shape[1], ptr(halo_lo), ptr(halo_hi), batch, L, di,
+                                             planes, _stream()), "mtn_conv_silu_halo_fwd")
     return u
 
 
-def scan(u, dbl, z, z_col0, w_dt, dt_bias, A2, Dskip, batch, L, di, R, *, y=None, h_in=None, h_out=None, dir_mask=3):
-    """Both-direction selective scan; see ``mtn_scan_args`` in include/mtn_b200.h."""
+def scan(u, dbl, z, z_col0, w_dt, dt_bias, A2, Dskip, batch, L, di, R, *, y=None, h_in=None, h_out=None, dir_mask=3,
+         sum_delta=None, L_last=0, summary_only=False):
+    """Both-direction selective scan; see ``mtn_scan_args`` in include/mtn_b200.h.
+    ``summary_only``: no output is written (chunk-summary pass: ``h_out`` and ``sum_delta`` only)."""
     _req_cuda(u, dbl, z)
     P = u.shape[0]
     nd = n_dbl_for(R)
-    if y is None:
+    if y is None and not summary_only:
         y = torch.empty_like(u)
     args = ScanArgs(u=ptr(u), dbl=ptr(dbl), z=ptr(z), w_dt=ptr(w_dt), dt_bias=ptr(dt_bias), A2=ptr(A2),
-                    Dskip=ptr(Dskip), y=ptr(y), h_in=ptr(h_in), h_out=ptr(h_out), batch=batch, L=L, di=di, R=R,
-                    n_dbl=nd, ld_dbl=dbl.stride(0), ldz=z.stride(0), z_col0=z_col0, planes=P,
-                    z_bf16=int(z.dtype == torch.bfloat16), dir_mask=dir_mask)
+                    Dskip=ptr(Dskip), y=None if summary_only else ptr(y), h_in=ptr(h_in), h_out=ptr(h_out),
+                    batch=batch, L=L, di=di, R=R, n_dbl=nd, ld_dbl=dbl.stride(0), ldz=z.stride(0), z_col0=z_col0,
+                    planes=P, z_bf16=int(z.dtype == torch.bfloat16), dir_mask=dir_mask, sum_delta=ptr(sum_delta),
+                    L_last=L_last)
     check(_lib.load().mtn_scan_fwd(args, _stream()), "mtn_scan_fwd")
     return y
+
+
+def fold_states(h_end, sum_delta, A2, g0, n_out, *, h0=None, want_final=False, dir_mask=3):
+    """Compose chunk operators (see ``mtn_fold_states_fwd``).  h_end [2, G, di, 16], sum_delta [2, G, di] ->
+    (h_in [2, n_out, di, 16], h_final [2, di, 16] or None)."""
+    _req_cuda(h_end, sum_delta, A2, h0)
+    _, G, di, ns = h_end.shape
+    assert ns == 16 and tuple(sum_delta.shape) == (2, G, di) and h_end.is_contiguous() and sum_delta.is_contiguous()
+    h_in = torch.zeros((2, n_out, di, 16), dtype=torch.float32, device=h_end.device)
+    h_final = torch.zeros((2, di, 16), dtype=torch.float32, device=h_end.device) if want_final else None
+    check(_lib.load().mtn_fold_states_fwd(ptr(h_end), ptr(sum_delta), ptr(A2), ptr(h0), ptr(h_in), ptr(h_final), G, di,
+                                          g0, n_out, dir_mask, _stream()), "mtn_fold_states_fwd")
+    return h_in, h_final
 
 
 def decoder(sep, w_dec, batch, T, L, N, n_spk=2, est=None, frames=None):

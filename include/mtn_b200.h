@@ -24,6 +24,9 @@
  *                        oracle selective_scan_ref ssi.py:91-157), both directions, incl. the 0.5
  *                        averaging of bimamba.py:253; optional initial/final state for the
  *                        sequence-parallel mode
+ *   mtn_conv_silu_halo_fwd / mtn_fold_states_fwd / mtn_scan_args.{sum_delta,L_last,h_in,h_out}
+ *                        the sequence-parallel long-form mode (BASELINE config 5); new functionality, the
+ *                        reference has no counterpart
  *   mtn_cln_fwd          ChannelwiseLayerNorm alone (mamba_masknet.py:118) for the stand-alone MaskNet module
  *   mtn_decoder_fwd      speechbrain dual_path.Decoder (== baseline/avse2/model.py:27-37), both
  *                        speakers, cat + pad/trim (train_wsj0mix.py:95-109)
@@ -83,6 +86,12 @@ typedef struct {
     int planes;           /* 1 or 2 */
     int z_bf16;
     int dir_mask;         /* bit0 forward, bit1 backward (3 = both in one launch) */
+    /* --- chunked / sequence-parallel scans (ABI >= 2); all optional ----------------------------------------- */
+    float* sum_delta;     /* nullable: fp32 [2][batch][di] = sum_t delta_t of each sequence.  With h_out it is the
+                             chunk summary of the reduce-then-scan scheme: h_end(h_in) = exp2(A2*sum_delta)*h_in +
+                             h_out(h_in = 0).  y may be NULL in that case (summary pass, no output written). */
+    int L_last;           /* 0, or the valid length (1..L) of the LAST sequence of the batch: rows beyond it are
+                             ignored (a long recording cut into `batch` equal chunks of L frames, ragged tail) */
 } mtn_scan_args;
 
 /* mix [batch][ld_mix >= T] fp32 -> mix_w [batch*L][N] fp32 = relu(conv1d(k=16,s=8)), L = (T-16)/8+1;
@@ -104,7 +113,24 @@ int mtn_add_rmsnorm_fwd(const float* h, float* res, int res_valid, const float* 
 int mtn_conv_silu_fwd(const void* xz, int ldxz, int xz_bf16, const float* conv_w, const float* conv_b, void* u_planes,
                       int batch, int L, int di, int planes, mtn_stream_t stream);
 
+/* Same, for a time chunk of a longer sequence (sequence-parallel mode): halo_lo / halo_hi (nullable, fp32
+ * [batch][3][di]) hold the xs rows t = -3..-1 and t = L..L+2 owned by the neighbouring chunks; NULL = zero padding
+ * (true utterance edge).  The reference has no such mode (its conv always sees the whole utterance,
+ * selective_scan_interface.py:182); the arithmetic per output element is unchanged. */
+int mtn_conv_silu_halo_fwd(const void* xz, int ldxz, int xz_bf16, const float* conv_w, const float* conv_b,
+                           void* u_planes, int u_rows /* rows allocated per plane, >= batch*L */, const float* halo_lo,
+                           const float* halo_hi, int batch, int L, int di, int planes, mtn_stream_t stream);
+
 int mtn_scan_fwd(const mtn_scan_args* args, mtn_stream_t stream);
+
+/* Chunked scan, step 2 of 3 (summary pass -> fold -> seeded pass): compose the per-chunk operators
+ * h -> exp2(A2 * sum_delta[g]) * h + h_end[g] in time order and write the state entering each chunk of
+ * [g0, g0 + n_out).  h_end fp32 [2][G][di][16], sum_delta fp32 [2][G][di] (chunk g of direction d at [d][g]),
+ * A2 [2][di][16], h0 nullable [2][di][16] = state entering the first chunk in time order (forward: before g = 0,
+ * backward: after g = G-1), h_in out [2][n_out][di][16], h_final nullable [2][di][16] = state after the last chunk.
+ * dir_mask as in mtn_scan_args.  No counterpart in the reference (it never chunks the scan across devices). */
+int mtn_fold_states_fwd(const float* h_end, const float* sum_delta, const float* A2, const float* h0, float* h_in,
+                        float* h_final, int G, int di, int g0, int n_out, int dir_mask, mtn_stream_t stream);
 
 /* sep fp32 [batch*L][n_spk*N] (speaker-major channels) -> est [batch][T][n_spk] fp32:
  * est[b, 8l+k, s] = sum over frames/taps of sum_n w_dec[n][k] * sep[b,l,s*N+n]; zero-padded / trimmed to T.

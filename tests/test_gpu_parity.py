@@ -311,3 +311,82 @@ def test_full_size_config2_properties():
         ref = restate.separate(mix[[3, 30]], sds, hp.n_mamba, scan_impl="c")
     err, d_sisnr, fid = _gate(est[[3, 30]], ref, src[[3, 30]])
     assert err <= 1e-3 and d_sisnr <= 0.01, (err, d_sisnr, fid)
+
+
+# --------------------------------------------------------------------------- chunked / sequence-parallel pieces
+def test_conv_silu_halo_equals_slice_of_full_sequence():
+    """A time chunk convolved with its neighbours' 3-frame halos == the same rows of the whole-utterance conv."""
+    g = torch.Generator().manual_seed(3)
+    di, L = 256, 211
+    xz = torch.randn(L, 2 * di, generator=g)
+    cw, cb = torch.randn(2, di, 4, generator=g) * 0.5, torch.randn(2, di, generator=g) * 0.5
+    full = _planes_value(ops.conv_silu(xz.to(DEV), cw.to(DEV), cb.to(DEV), 1, L, di, 2))
+    a, b = 70, 150
+    lo, hi = xz[a - 3:a, :di].contiguous().view(1, 3, di), xz[b:b + 3, :di].contiguous().view(1, 3, di)
+    part = _planes_value(ops.conv_silu(xz[a:b].contiguous().to(DEV), cw.to(DEV), cb.to(DEV), 1, b - a, di, 2,
+                                       halo_lo=lo.to(DEV), halo_hi=hi.to(DEV)))
+    assert torch.equal(part, full[a:b])
+    edge = _planes_value(ops.conv_silu(xz[:a].contiguous().to(DEV), cw.to(DEV), cb.to(DEV), 1, a, di, 2,
+                                       halo_hi=xz[a:a + 3, :di].contiguous().view(1, 3, di).to(DEV)))
+    assert torch.equal(edge, full[:a])          # no lower halo = true utterance start (zero padding)
+
+
+@pytest.mark.parametrize("L,C,slow", [(1000, 4, False), (1003, 7, True), (333, 1, False), (2000, 16, True)])
+def test_chunked_scan_summary_fold_seeded_equals_one_shot(L, C, slow):
+    """Reduce-then-scan on one GPU: summary pass (y = NULL) -> mtn_fold_states_fwd -> seeded pass over C chunks
+    (ragged last chunk through L_last) reproduces the one-shot scan of the whole sequence."""
+    g = torch.Generator().manual_seed(L + C)
+    di, R = 256, 8
+    nd = ops.n_dbl_for(R)
+    Ls = -(-L // C)
+    Cc = -(-L // Ls)
+    rows = Cc * Ls
+    u = torch.zeros(rows, 2 * di)
+    u[:L] = torch.randn(L, 2 * di, generator=g)
+    dbl = torch.zeros(rows, 2 * nd)
+    dbl[:L] = torch.randn(L, 2 * nd, generator=g) * 0.5
+    zbuf = torch.zeros(rows, 2 * di)
+    zbuf[:L, di:] = torch.nn.functional.silu(torch.randn(L, di, generator=g))
+    w_dt = (torch.randn(2, di, R, generator=g) * R ** -0.5).to(DEV)
+    # "slow": tiny deltas and small |A| so the state carried across chunk seams decays over thousands of steps and
+    # the composed operators exp2(A2 * sum_delta) really matter (with the default statistics they are ~1e-9)
+    dt_bias = (torch.randn(2, di, generator=g) * 0.5 - (6.5 if slow else 3.0)).to(DEV)
+    A2 = (-torch.exp(torch.randn(2, di, 16, generator=g) * 0.5 + (-1.0 if slow else 0.5)) * ops.LOG2E).to(DEV)
+    Dk = torch.randn(2, di, generator=g).to(DEV)
+    up = ops.split_planes(u.to(DEV), 2)
+    dbl_d, z_d = dbl.to(DEV), zbuf.to(DEV)
+    hfin = torch.zeros(2, 1, di, 16, device=DEV)
+    y_ref = ops.scan(up[:, :L].contiguous(), dbl_d[:L].contiguous(), z_d[:L].contiguous(), di, w_dt, dt_bias, A2, Dk, 1,
+                     L, di, R, h_out=hfin)
+    # chunked
+    h_end = torch.zeros(2, Cc, di, 16, device=DEV)
+    sdl = torch.zeros(2, Cc, di, device=DEV)
+    last = L - (Cc - 1) * Ls
+    ops.scan(up, dbl_d, z_d, di, w_dt, dt_bias, A2, Dk, Cc, Ls, di, R, h_out=h_end, sum_delta=sdl, L_last=last,
+             summary_only=True)
+    h_in, h_final = ops.fold_states(h_end, sdl, A2, 0, Cc, want_final=True)
+    y = ops.scan(up, dbl_d, z_d, di, w_dt, dt_bias, A2, Dk, Cc, Ls, di, R, h_in=h_in, L_last=last)
+    torch.cuda.synchronize()
+    got, ref = _planes_value(y)[:L], _planes_value(y_ref)
+    assert rel_mixed(got, ref) < 2e-5, rel_mixed(got, ref)
+    # the folded final state equals the one-shot final state: forward = after the last chunk, backward = after chunk 0
+    assert rel_mixed(h_final[0].cpu(), hfin[0, 0].cpu()) < 2e-5
+    assert rel_mixed(h_final[1].cpu(), hfin[1, 0].cpu()) < 2e-5
+
+
+@pytest.mark.parametrize("name,T,sub", [("tiny", 1608, 5), ("S", 16000, 16)])
+def test_sequence_parallel_driver_single_gpu(name, T, sub):
+    """SequenceParallelSeparator on one rank with several sub-chunks (the path that fills the GPU at batch 1)
+    against the unchunked engine and the CPU oracle."""
+    from avse_challenge_b200.parallel import SequenceParallelSeparator
+    hp = CONFIGS[name]
+    sds = init_state_dicts(hp, 1234)
+    mix, src = synth_mixture(1, T, seed=21)
+    est_sp = SequenceParallelSeparator(hp, sds, device=DEV, mode="fp32", sub_chunks=sub)(mix).cpu()
+    est_one = SeparatorEngine(hp, sds, device=DEV, mode="fp32", use_graph=False)(mix.to(DEV)).cpu()
+    assert est_sp.shape == est_one.shape
+    assert rel_max(est_sp, est_one) < 1e-4, rel_max(est_sp, est_one)
+    with torch.no_grad():
+        ref = restate.separate(mix, sds, hp.n_mamba, scan_impl="c")
+    err, d_sisnr, fid = _gate(est_sp, ref, src)
+    assert err <= 1e-3 and d_sisnr <= 0.01, (err, d_sisnr, fid)
