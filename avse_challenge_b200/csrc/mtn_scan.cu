@@ -134,6 +134,10 @@ __device__ __forceinline__ void scan_consumer_split(uint8_t* smem, uint64_t* ful
                                                     const CUtensorMap* mapD) {
     using SM = ScanSmem<P, NDBL, ZT>;
     constexpr uint32_t FULL = 0xffffffffu;
+    // KP >= 100: timing-only ablations (WRONG results; MTN_SCAN_VARIANT=101..107): bit0 drops the dt_proj FMAs, bit1
+    // the B/C shared-memory loads, bit2 the MUFU ex2.  They measure the marginal cost of each instruction group.
+    constexpr int ABL = KP >= 100 ? KP - 100 : 0;
+    constexpr int KPE = KP >= 100 ? 0 : KP;
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int half = lane >> 4, cl = lane & 15;
@@ -145,7 +149,7 @@ __device__ __forceinline__ void scan_consumer_split(uint8_t* smem, uint64_t* ful
     const size_t pd = size_t(dir) * p.di + d;
     float sdl = 0.f;  // sum of this lane's deltas (rows 2k + half)
     float2 h2[4], A2[4];
-    float wdt[R];
+    float2 wdt2[R / 2];
     {
         const float4* ap = reinterpret_cast<const float4*>(p.A2 + pd * SC_NS + half * 8);
 #pragma unroll
@@ -158,10 +162,8 @@ __device__ __forceinline__ void scan_consumer_split(uint8_t* smem, uint64_t* ful
 #pragma unroll
         for (int q = 0; q < R / 4; ++q) {
             const float4 w = wp[q];
-            wdt[4 * q] = w.x;
-            wdt[4 * q + 1] = w.y;
-            wdt[4 * q + 2] = w.z;
-            wdt[4 * q + 3] = w.w;
+            wdt2[2 * q] = make_float2(w.x, w.y);
+            wdt2[2 * q + 1] = make_float2(w.z, w.w);
         }
         if (p.h_in) {
             const float4* hp =
@@ -181,10 +183,10 @@ __device__ __forceinline__ void scan_consumer_split(uint8_t* smem, uint64_t* ful
     const float Dv = p.Dskip[pd];
     // polynomial exp2 needs dl * A2 >= -126 for its KP pairs: clamp delta for those pairs only
     float dl_lim = 3.0e38f;
-    if (KP > 0) {
+    if (KPE > 0) {
         float amin = -1e-30f;
 #pragma unroll
-        for (int q = 0; q < KP; ++q) amin = fminf(amin, fminf(A2[q].x, A2[q].y));
+        for (int q = 0; q < KPE; ++q) amin = fminf(amin, fminf(A2[q].x, A2[q].y));
         dl_lim = -125.f / amin;
     }
     const size_t M = size_t(p.batch) * L;
@@ -200,13 +202,20 @@ __device__ __forceinline__ void scan_consumer_split(uint8_t* smem, uint64_t* ful
         const __nv_bfloat16* su_h = reinterpret_cast<const __nv_bfloat16*>(st) + half * SC_CH + chl;
         const float* drow = reinterpret_cast<const float*>(st + SM::U_BYTES + SM::Z_BYTES) + (2 * k + half) * NDBL;
         float acc0 = bias, acc1 = 0.f;
+        if (ABL & 1) {
+            acc1 = drow[0] * wdt2[0].x;
+        } else {
+            // dt_proj: R MACs as R/2 packed FFMA2 on two independent accumulator pairs
+            float2 pa = make_float2(bias, 0.f), pb = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int q = 0; q < R / 4; ++q) {
-            const float4 x = *reinterpret_cast<const float4*>(drow + 4 * q);
-            acc0 = fmaf(x.x, wdt[4 * q], acc0);
-            acc1 = fmaf(x.y, wdt[4 * q + 1], acc1);
-            acc0 = fmaf(x.z, wdt[4 * q + 2], acc0);
-            acc1 = fmaf(x.w, wdt[4 * q + 3], acc1);
+            for (int q = 0; q < R / 4; ++q) {
+                const float4 x = *reinterpret_cast<const float4*>(drow + 4 * q);
+                pa = __ffma2_rn(make_float2(x.x, x.y), wdt2[2 * q], pa);
+                pb = __ffma2_rn(make_float2(x.z, x.w), wdt2[2 * q + 1], pb);
+            }
+            const float2 pab = __fadd2_rn(pa, pb);
+            acc0 = pab.x;
+            acc1 = pab.y;
         }
         float dl = softplus_1mufu(acc0 + acc1);
         dl = (2 * k + half < nvalid_t) ? dl : 0.f;  // rows past the utterance end: exp2(0)=1, dBu=0 -> state unchanged
@@ -223,11 +232,12 @@ __device__ __forceinline__ void scan_consumer_split(uint8_t* smem, uint64_t* ful
         const float2 dlc2 = make_float2(dlc, dlc);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            if (q < KP) {
+            if (q < KPE) {
                 ex[q] = ex2_poly2(dlc2, A2[q]);
             } else {
                 const float2 a = __fmul2_rn(dl2, A2[q]);
-                ex[q] = make_float2(ex2_approx(a.x), ex2_approx(a.y));
+                if (ABL & 4) ex[q] = __ffma2_rn(a, make_float2(0.5f, 0.5f), make_float2(1.f, 1.f));
+                else ex[q] = make_float2(ex2_approx(a.x), ex2_approx(a.y));
             }
         }
     };
@@ -271,11 +281,14 @@ __device__ __forceinline__ void scan_consumer_split(uint8_t* smem, uint64_t* ful
         const int stage_n = (stage + 1 == SC_STAGES) ? 0 : stage + 1;
         const uint8_t* st_n = smem + stage_n * SM::STAGE_BYTES;
         int nvalid_n = 0;  // no next tile: the (unconditional) row prep then yields delta = 0 everywhere
-        if (tid == 0 && i + 3 < ntiles) {
-            // stage (i+3) % 5 was last used by tile i-2, whose "empty" phase (parity ((i-2)/5)&1) is long complete
+        if (warp == 0 && i + 3 < ntiles) {
+            // stage (i+3) % 5 was last used by tile i-2, whose "empty" phase (parity ((i-2)/5)&1) is normally long
+            // complete.  The WHOLE warp waits (converged): a lone lane sleeping in try_wait on this barrier while its
+            // 31 siblings sleep on a different one (the "full" barrier below) produced millisecond stragglers.
             const int stg3 = (stage + 3) % SC_STAGES;
             if (i >= 2) mbar_wait(&empty_bar[stg3], uint32_t((i - 2) / SC_STAGES) & 1u);
-            issue_tile(i + 3, stg3);
+            if (lane == 0) issue_tile(i + 3, stg3);
+            __syncwarp();
         }
         if (has_next) {
             const int tile_n = REV ? (tile - 1) : (tile + 1);
@@ -306,8 +319,13 @@ __device__ __forceinline__ void scan_consumer_split(uint8_t* smem, uint64_t* ful
             const float* brow = sdB + jrow(0) * NDBL;
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
-                Bc[q] = *reinterpret_cast<const float4*>(brow + 4 * q);
-                Cc[q] = *reinterpret_cast<const float4*>(brow + SC_NS + 4 * q);
+                if (ABL & 2) {
+                    Bc[q] = make_float4(du_c, dl_n, du_n, 0.5f);
+                    Cc[q] = make_float4(dl_n, du_c, 0.25f, du_n);
+                } else {
+                    Bc[q] = *reinterpret_cast<const float4*>(brow + 4 * q);
+                    Cc[q] = *reinterpret_cast<const float4*>(brow + SC_NS + 4 * q);
+                }
             }
             make_exps(e, dl0);
         }
@@ -335,8 +353,13 @@ __device__ __forceinline__ void scan_consumer_split(uint8_t* smem, uint64_t* ful
                 const float* brow = sdB + jrow(jj + 1) * NDBL;
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
-                    Bn[q] = *reinterpret_cast<const float4*>(brow + 4 * q);
-                    Cn[q] = *reinterpret_cast<const float4*>(brow + SC_NS + 4 * q);
+                    if (ABL & 2) {
+                        Bn[q] = make_float4(du_c, dl_n, du_n, 0.5f);
+                        Cn[q] = make_float4(dl_n, du_c, 0.25f, du_n);
+                    } else {
+                        Bn[q] = *reinterpret_cast<const float4*>(brow + 4 * q);
+                        Cn[q] = *reinterpret_cast<const float4*>(brow + SC_NS + 4 * q);
+                    }
                 }
             }
             if (jj + 2 < SC_TT) {
@@ -567,6 +590,10 @@ __device__ __forceinline__ void scan_consumer_full(uint8_t* smem, uint64_t* full
 }
 
 // NCONS consumer threads (256: split mapping with KP polynomial pairs, 128: one thread per channel) + 1 producer warp.
+#ifdef MTN_SCAN_ABLATIONS
+__device__ unsigned long long g_scan_dbg[3 * 8192];  // per CTA: smid, start ns, end ns (timing experiments only)
+#endif
+
 template <int P, int R, int NDBL, typename ZT, int NCONS, int KP, bool WY>
 __global__ void __launch_bounds__(NCONS == 256 ? 256 : NCONS + 32, 2)
 scan_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUtensorMap mapZ,
@@ -630,10 +657,22 @@ scan_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CU
         return;
     }
     if (NCONS == 256) {
+#ifdef MTN_SCAN_ABLATIONS
+        const int cta = blockIdx.y * gridDim.x + blockIdx.x;
+        if (tid == 32 && cta < 8192) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            g_scan_dbg[3 * cta] = smid;
+            g_scan_dbg[3 * cta + 1] = global_timer_ns();
+        }
+#endif
         if (rev)
             scan_consumer_split<P, R, NDBL, ZT, true, KP, WY>(smem, full_bar, empty_bar, sy, p, ch0, b, dir, &mapU, &mapZ, &mapD);
         else
             scan_consumer_split<P, R, NDBL, ZT, false, KP, WY>(smem, full_bar, empty_bar, sy, p, ch0, b, dir, &mapU, &mapZ, &mapD);
+#ifdef MTN_SCAN_ABLATIONS
+        if (tid == 32 && cta < 8192) g_scan_dbg[3 * cta + 2] = global_timer_ns();
+#endif
     } else {
         if (rev)
             scan_consumer_full<P, R, NDBL, ZT, true>(smem, full_bar, empty_bar, sy, p, ch0, b, dir);
@@ -725,6 +764,13 @@ static int dispatch_scan_variant(const mtn_scan_args* a, cudaStream_t s) {
             }
             return launch_scan<P, R, NDBL, ZT, 128, 0, true>(a, s);
         case 11: return launch_scan<P, R, NDBL, ZT, 256, 1, true>(a, s);
+#ifdef MTN_SCAN_ABLATIONS
+        case 101: return launch_scan<P, R, NDBL, ZT, 256, 101, true>(a, s);
+        case 102: return launch_scan<P, R, NDBL, ZT, 256, 102, true>(a, s);
+        case 104: return launch_scan<P, R, NDBL, ZT, 256, 104, true>(a, s);
+        case 103: return launch_scan<P, R, NDBL, ZT, 256, 103, true>(a, s);
+        case 107: return launch_scan<P, R, NDBL, ZT, 256, 107, true>(a, s);
+#endif
         default: set_error("scan: unknown MTN_SCAN_VARIANT=%d", variant); return MTN_EINVAL;
     }
 }
@@ -740,6 +786,12 @@ static int dispatch_scan_r(const mtn_scan_args* a, cudaStream_t s) {
 }
 
 }  // namespace mtn
+
+#ifdef MTN_SCAN_ABLATIONS
+extern "C" int mtn_debug_scan_times(unsigned long long* host_dst, int n_ctas) {
+    return cudaMemcpyFromSymbol(host_dst, mtn::g_scan_dbg, sizeof(unsigned long long) * 3 * n_ctas) == cudaSuccess ? 0 : -2;
+}
+#endif
 
 extern "C" int mtn_scan_fwd(const mtn_scan_args* a, mtn_stream_t stream) {
     using namespace mtn;

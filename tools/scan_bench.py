@@ -26,12 +26,15 @@ dt_bias = torch.randn(2, di, device=dev, generator=g) * 0.5 - 3.0
 A2 = -torch.exp(torch.randn(2, di, 16, device=dev, generator=g) * 0.5 + 0.5) * ops.LOG2E
 Dk = torch.randn(2, di, device=dev, generator=g)
 y = torch.empty_like(u)
-run = lambda: ops.scan(u, dbl, xz, di, w_dt, dt_bias, A2, Dk, a.batch, a.L, di, R, y=y)
+hout = torch.zeros(2, a.batch, di, 16, device=dev)
+run_full = lambda: ops.scan(u, dbl, xz, di, w_dt, dt_bias, A2, Dk, a.batch, a.L, di, R, y=y)
+run_sum = lambda: ops.scan(u, dbl, xz, di, w_dt, dt_bias, A2, Dk, a.batch, a.L, di, R, h_out=hout, summary_only=True)
 s_io = 4 if P == 2 else 2
 alg = 2 * (M * (4 * di + 32) * s_io + (di * 16 + 2 * di) * 4)
 y_ref = None
 for var in a.variants.split(","):
-    os.environ["MTN_SCAN_VARIANT"] = var
+    run = run_sum if var == "S" else run_full          # "S" = summary pass (no y), default variant
+    os.environ["MTN_SCAN_VARIANT"] = "0" if var == "S" else var
     y.zero_()
     for _ in range(3): run()
     torch.cuda.synchronize()
