@@ -52,20 +52,53 @@ def parse():
     ap.add_argument("--mode", default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
-    return ap.parse_args()
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "longform", "custom"],
+                    help="cfg2 (default): S, 32 x 4 s @ 8 kHz per GPU, fp32 mode, weak scaling.  cfg3: L, global batch "
+                         "256 x 4 s sharded over the GPUs, bf16 mode, strong scaling.  longform: one 10-minute 16 kHz "
+                         "recording, sequence-parallel over the GPUs (S fp32 unless --hparams/--mode given), strong "
+                         "scaling.  custom: take --hparams/--batch/--seconds/--sample-rate/--mode as given.")
+    ap.add_argument("--sub-chunks", type=int, default=64, help="longform: time sub-chunks per GPU")
+    ap.add_argument("--exchange", default="allgather", choices=["allgather", "sendrecv"])
+    a = ap.parse_args()
+    explicit = {x.split("=")[0] for x in sys.argv[1:] if x.startswith("--")}
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if a.workload == "cfg3":
+        if "--hparams" not in explicit: a.hparams = "L"
+        if "--mode" not in explicit: a.mode = "bf16"
+        if "--batch" not in explicit: a.batch = max(1, 256 // world)
+    elif a.workload == "longform":
+        if "--seconds" not in explicit: a.seconds = 600.0
+        if "--sample-rate" not in explicit: a.sample_rate = 16000
+        a.batch = 1
+    return a
 
 
 def workload_config(a, n_gpus):
+    prec = ("(split-bf16 x3 tcgen05 GEMMs, fp32 scan state)" if a.mode == "fp32"
+            else "(bf16 tcgen05 GEMMs + bf16 activations, fp32 scan state)")
+    name = {"cfg2": "BASELINE config 2", "cfg3": "BASELINE config 3", "longform": "BASELINE config 5",
+            "custom": "custom"}[a.workload]
+    if a.workload == "longform":
+        return {
+            "workload": (f"{name}: Mamba-TasNet {a.hparams} hparams, one {a.seconds:g} s @ {a.sample_rate // 1000} kHz "
+                         f"recording, {a.mode} mode {prec}, time sharded over {n_gpus} GPU(s) x {a.sub_chunks} sub-chunks"),
+            "hparams": a.hparams, "batch_per_gpu": 1, "global_batch": 1, "seconds": a.seconds,
+            "sample_rate": a.sample_rate, "mode": a.mode,
+            "parallelism": f"sequence-parallel x{n_gpus}: conv halo + chunk-summary exchange ({a.exchange}) per layer",
+            "l2": "no flush needed: every layer streams far more than the 126 MB L2",
+        }
     return {
-        "workload": (f"BASELINE config 2: Mamba-TasNet {a.hparams} hparams, {a.batch} x {a.seconds:g} s @ "
-                     f"{a.sample_rate // 1000} kHz 2-speaker mixtures per GPU, {a.mode} mode "
-                     + ("(split-bf16 x3 tcgen05 GEMMs, fp32 scan state)" if a.mode == "fp32"
-                        else "(bf16 tcgen05 GEMMs + bf16 activations, fp32 scan state)")),
+        "workload": (f"{name}: Mamba-TasNet {a.hparams} hparams, {a.batch} x {a.seconds:g} s @ "
+                     f"{a.sample_rate // 1000} kHz 2-speaker mixtures per GPU, {a.mode} mode {prec}"),
         "hparams": a.hparams, "batch_per_gpu": a.batch, "global_batch": a.batch * n_gpus, "seconds": a.seconds,
         "sample_rate": a.sample_rate, "mode": a.mode,
         "parallelism": f"batch-sharded x{n_gpus}, no collective on the data path",
         "l2": "no flush needed: every step streams >3 GB of activations per layer group, far larger than the 126 MB L2",
     }
+
+
+def scaling_kind(a):
+    return "weak" if a.workload in ("cfg2", "custom") else "strong"
 
 
 # ------------------------------------------------------------------------------------------ CPU reference arm
@@ -115,7 +148,8 @@ def run_reference_arm(a):
     base, dt = cpu_reference_throughput(a.hparams, a.sample_rate, a.steps, a.warmup, budget_s=150.0)
     line = {
         "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": a.gpus,
-        "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": scaling_kind(a),
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(a, a.gpus),
         "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -296,7 +330,7 @@ def run_b200_arm(a):
         line = {
             "metric": METRIC, "value": audio_s_per_step * world / (step_ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": a.steps, "warmup": max(3, a.warmup), "ms_per_step": step_ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32" if a.mode == "fp32" else "bf16",
+            "scaling": scaling_kind(a), "vs_baseline": None, "dtype": "f32" if a.mode == "fp32" else "bf16",
             "data": "synthetic", "config": workload_config(a, world),
             "e2e": {"value": audio_s_per_step * world / (ms_e2e / a.steps * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": a.batch * T * 4, "d2h_bytes_per_step": a.batch * T * hp.n_spk * 4,
@@ -318,10 +352,108 @@ def run_b200_arm(a):
         dist.destroy_process_group()
 
 
+def run_longform_arm(a):
+    """BASELINE config 5: one long recording, sequence-parallel over the ranks (strong scaling)."""
+    import torch
+    import torch.distributed as dist
+    from avse_challenge_b200 import CONFIGS, init_state_dicts, synth_mixture
+    from avse_challenge_b200.parallel import SequenceParallelSeparator
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback for the product path)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    hp = CONFIGS[a.hparams]
+    T = int(round(a.seconds * a.sample_rate)) // 8 * 8
+    sds = init_state_dicts(hp, 1234)
+    mix_cpu, _ = synth_mixture(1, min(T, 30 * a.sample_rate), a.sample_rate, seed=1234)
+    reps = -(-T // mix_cpu.shape[1])
+    mix_cpu = mix_cpu.repeat(1, reps)[:, :T].contiguous()            # 30 s of synthetic speech tiled to length
+    sp = SequenceParallelSeparator(hp, sds, device=dev, mode=a.mode, sub_chunks=a.sub_chunks, exchange=a.exchange)
+    cpu_base = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        cpu_base, _ = cpu_reference_throughput(a.hparams, a.sample_rate, steps=1, warmup=0, budget_s=30.0)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    mix_d = mix_cpu.to(dev)
+    for _ in range(max(3, a.warmup)):
+        sp(mix_d)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        sp(mix_d)
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    pin_in = mix_cpu.pin_memory()
+    pin_out = torch.empty((1, T, hp.n_spk), dtype=torch.float32).pin_memory()
+    dmix = torch.empty((1, T), dtype=torch.float32, device=dev)
+
+    def e2e_step():
+        dmix.copy_(pin_in, non_blocking=True)
+        pin_out.copy_(sp(dmix), non_blocking=True)
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(a.steps):
+        e2e_step()
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, ms_e2e = t.tolist()
+    if rank == 0:
+        from avse_challenge_b200.parallel import make_seq_plan
+        peak, peak_src, _ = load_peaks()
+        audio_s = T / a.sample_rate
+        L = hp.frames(T)
+        plan = make_seq_plan(L, world, a.sub_chunks)
+        step_ms = ms_total / a.steps
+        per_fwd = 4 + hp.n_mamba * 8                 # enc, bottleneck, (norm, in_proj, conv, x_proj, scan A, fold, scan B, out_proj) x layers, norm_f+mask, decoder(2)
+        line = {
+            "metric": METRIC, "value": audio_s / (step_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": a.steps,
+            "warmup": max(3, a.warmup), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32" if a.mode == "fp32" else "bf16", "data": "synthetic",
+            "config": dict(workload_config(a, world), frames=L, frames_per_gpu=plan.ranges[0][1] - plan.ranges[0][0],
+                           sub_chunk_frames=plan.Ls),
+            "e2e": {"value": audio_s / (ms_e2e / a.steps * 1e-3), "unit": UNIT, "h2d_bytes_per_step": T * 4,
+                    "d2h_bytes_per_step": T * hp.n_spk * 4, "ms_per_step": ms_e2e / a.steps},
+            "gpu_launches": a.steps * (per_fwd + 1),
+            "roofline": {"kernel": "mtn::scan_kernel (summary pass + seeded pass per layer)", "bound": "hbm",
+                         "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "peak_source": peak_src,
+                         "traffic": None, "note": "per-kernel roofline is reported on the cfg2 workload"},
+            "clocks": clocks,
+        }
+        if cpu_base is not None:
+            line["cpu_baseline"] = cpu_base
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     a = parse()
     if a.impl == "reference":
         run_reference_arm(a)
+    elif a.workload == "longform":
+        run_longform_arm(a)
     else:
         run_b200_arm(a)
 
