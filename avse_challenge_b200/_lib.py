@@ -11,7 +11,7 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_void_p
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmtn_b200.so")
 
-EPI_STORE, EPI_INPROJ, EPI_MASK, EPI_RELU = 0, 1, 2, 3
+EPI_STORE, EPI_INPROJ, EPI_MASK, EPI_RELU, EPI_XPROJ = 0, 1, 2, 3, 4
 
 EXPORTS = [
     "mtn_encoder_cln_fwd", "mtn_gemm_fwd", "mtn_add_rmsnorm_fwd", "mtn_conv_silu_fwd", "mtn_conv_silu_halo_fwd",
@@ -36,7 +36,7 @@ class ScanArgs(Structure):
         ("A2", c_void_p), ("Dskip", c_void_p), ("y", c_void_p), ("h_in", c_void_p), ("h_out", c_void_p),
         ("batch", c_int), ("L", c_int), ("di", c_int), ("R", c_int), ("n_dbl", c_int), ("ld_dbl", c_int),
         ("ldz", c_int), ("z_col0", c_int), ("planes", c_int), ("z_bf16", c_int), ("dir_mask", c_int),
-        ("sum_delta", c_void_p), ("L_last", c_int),
+        ("sum_delta", c_void_p), ("L_last", c_int), ("dtp", c_void_p),
     ]
 
 

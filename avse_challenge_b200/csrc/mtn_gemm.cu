@@ -241,6 +241,27 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                                 f.z = fmaxf(f.z, 0.f) * a.z;
                                 f.w = fmaxf(f.w, 0.f) * a.w;
                             }
+                            if (EPI == MTN_EPI_XPROJ) {
+                                // dt columns also go out as hi | lo bf16 planes: the B operand of the scan's dt_proj MMA
+                                if (gcol < p.epi_param) {
+                                    __nv_bfloat16* drow = reinterpret_cast<__nv_bfloat16*>(const_cast<float*>(p.aux)) +
+                                                          (size_t(grow) * p.groups + g) * 2 * p.epi_param + gcol;
+                                    __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
+                                    split_bf16(f.x, h0, l0);
+                                    split_bf16(f.y, h1, l1);
+                                    split_bf16(f.z, h2, l2);
+                                    split_bf16(f.w, h3, l3);
+                                    __nv_bfloat162 a = __halves2bfloat162(h0, h1), b = __halves2bfloat162(h2, h3);
+                                    __nv_bfloat162 c = __halves2bfloat162(l0, l1), d = __halves2bfloat162(l2, l3);
+                                    uint2 ph, pl;
+                                    ph.x = *reinterpret_cast<uint32_t*>(&a);
+                                    ph.y = *reinterpret_cast<uint32_t*>(&b);
+                                    pl.x = *reinterpret_cast<uint32_t*>(&c);
+                                    pl.y = *reinterpret_cast<uint32_t*>(&d);
+                                    *reinterpret_cast<uint2*>(drow) = ph;
+                                    *reinterpret_cast<uint2*>(drow + p.epi_param) = pl;
+                                }
+                            }
                             const size_t off = size_t(grow) * p.ldo + size_t(g) * p.out_group_stride + gcol;
                             if (OUT_BF16) {
                                 __nv_bfloat162 lo2 = __floats2bfloat162_rn(f.x, f.y);
@@ -323,6 +344,9 @@ static int launch_gemm(const mtn_gemm_args* a, cudaStream_t stream) {
 template <int P, int BN>
 static int dispatch_epi(const mtn_gemm_args* a, cudaStream_t s) {
     if (a->epilogue == MTN_EPI_STORE && !a->out_bf16) return launch_gemm<P, BN, MTN_EPI_STORE, false>(a, s);
+    if (BN <= 64) {
+        if (a->epilogue == MTN_EPI_XPROJ && !a->out_bf16) return launch_gemm<P, BN, MTN_EPI_XPROJ, false>(a, s);
+    }
     if (BN >= 128) {
         if (a->epilogue == MTN_EPI_INPROJ && !a->out_bf16) return launch_gemm<P, BN, MTN_EPI_INPROJ, false>(a, s);
         if (a->epilogue == MTN_EPI_INPROJ && a->out_bf16) return launch_gemm<P, BN, MTN_EPI_INPROJ, true>(a, s);
@@ -362,6 +386,10 @@ extern "C" int mtn_gemm_fwd(const mtn_gemm_args* a, mtn_stream_t stream) {
         MTN_REQUIRE(a->aux && a->epi_param > 0 && a->epi_param % 4 == 0 && a->ld_aux % 4 == 0,
                     "gemm: mask epilogue needs aux / enc_dim");
     if (a->epilogue == MTN_EPI_INPROJ) MTN_REQUIRE(a->epi_param % 4 == 0, "gemm: inproj split must be a multiple of 4");
+    if (a->epilogue == MTN_EPI_XPROJ)
+        MTN_REQUIRE(a->aux && (a->epi_param == 16 || a->epi_param == 32) && a->epi_param <= a->N &&
+                        (reinterpret_cast<uintptr_t>(a->aux) & 15) == 0,
+                    "gemm: xproj epilogue needs a 16-byte aligned dtp buffer and RP = 16 or 32");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     if (a->planes == 2) return dispatch_bn<2>(a, s);
     if (a->planes == 1) return dispatch_bn<1>(a, s);

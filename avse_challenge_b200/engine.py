@@ -20,7 +20,7 @@ import torch
 
 from . import _lib, ops
 from .hparams import HParams
-from .ops import LOG2E, n_dbl_for
+from .ops import LOG2E, n_dbl_for, rp_for
 
 MODES = {"fp32": dict(planes=2, xz_bf16=False), "bf16": dict(planes=1, xz_bf16=True)}
 
@@ -87,6 +87,7 @@ class Workspace:
         self.xz = e((M, 2 * di), xz_dt)
         self.u = e((P, M, 2 * di), torch.bfloat16)
         self.dbl = e((M, 2 * nd), torch.float32)
+        self.dtp = e((M, 2, 2, rp_for(hp.dt_rank)), torch.bfloat16)   # dt columns as hi | lo planes (scan MMA operand)
         self.y = e((P, M, 2 * di), torch.bfloat16)
         self.sep = e((M, hp.n_spk * N), torch.float32)
         self.frames = e((M, hp.n_spk, 16), torch.float32)
@@ -113,6 +114,10 @@ class SeparatorEngine:
         self._graphs = {}
         self._prof = None
         self.launches_per_forward = 2 + 1 + hp.n_mamba * 6 + 2 + 2  # enc, bottleneck, layers, norm_f+mask, decoder(2)
+        # dt_proj inside the scan: tcgen05 MMA per 16-step tile, or R FMAs per (step, channel).  Measured on B200
+        # (tools/scan_bench.py): the MMA form wins only where R is large and the FMA pipe is the
+        # busier one (L hparams, fp32 mode: -6 %); elsewhere its shuffles / TMEM loads cost as much as the FMAs saved.
+        self.tc_dt = hp.dt_rank >= 32 and mode == "fp32"
 
     # ------------------------------------------------------------------ building blocks
     def workspace(self, batch, T) -> Workspace:
@@ -141,9 +146,13 @@ class SeparatorEngine:
         op("gemm_in_proj", ops.gemm, ws.xn, lw["w_in"], M, 2 * di, D, out=ws.xz, epilogue=_lib.EPI_INPROJ, epi_param=di,
            out_bf16=ws.xz.dtype == torch.bfloat16)
         op("conv_silu", ops.conv_silu, ws.xz, lw["conv_w"], lw["conv_b"], ws.batch, ws.L, di, P, u=ws.u)
-        op("gemm_x_proj", ops.gemm, ws.u, lw["w_x"], M, nd, di, out=ws.dbl, groups=2, out_group_stride=nd)
+        if self.tc_dt:
+            op("gemm_x_proj", ops.gemm, ws.u, lw["w_x"], M, nd, di, out=ws.dbl, groups=2, out_group_stride=nd,
+               epilogue=_lib.EPI_XPROJ, epi_param=rp_for(R), aux=ws.dtp)
+        else:
+            op("gemm_x_proj", ops.gemm, ws.u, lw["w_x"], M, nd, di, out=ws.dbl, groups=2, out_group_stride=nd)
         op("scan", ops.scan, ws.u, ws.dbl, ws.xz, di, lw["w_dt"], lw["dt_bias"], lw["A2"], lw["D"], ws.batch, ws.L, di, R,
-           y=ws.y)
+           y=ws.y, dtp=ws.dtp if self.tc_dt else None)
         op("gemm_out_proj", ops.gemm, ws.y, lw["w_out"], M, D, 2 * di, out=ws.h)
         if taps is not None:
             taps.append(ws.h.clone())

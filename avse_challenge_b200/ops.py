@@ -26,6 +26,11 @@ def _req_cuda(*ts):
             raise _lib.MtnError("mtn ops need CUDA tensors (there is no CPU path)")
 
 
+def rp_for(dt_rank: int) -> int:
+    """K extent of the tensor-core dt_proj operand: the dt columns padded to a multiple of 16."""
+    return 16 if dt_rank <= 16 else 32
+
+
 def n_dbl_for(dt_rank: int) -> int:
     """Padded width of one direction's [dt | B | C] row: 48 for R <= 16, 64 for R = 32."""
     w = dt_rank + 32
@@ -88,7 +93,7 @@ def gemm(a_planes, w_planes, M, N, K, *, out=None, groups=1, out_group_stride=0,
         out = torch.empty((M, width), dtype=torch.bfloat16 if out_bf16 else torch.float32, device=a_planes.device)
     args = GemmArgs(a=ptr(a_planes), w=ptr(w_planes), out=ptr(out), aux=ptr(aux), M=M, N=N, K=K, a_rows=a_rows,
                     lda=lda, ldo=ldo if ldo is not None else out.stride(0),
-                    ld_aux=aux.stride(0) if aux is not None else 0, planes=P, groups=groups,
+                    ld_aux=(aux.stride(0) if aux is not None and aux.dim() == 2 else 0), planes=P, groups=groups,
                     out_group_stride=out_group_stride, epilogue=epilogue, epi_param=epi_param,
                     out_bf16=int(out_bf16), max_ctas=max_ctas)
     check(_lib.load().mtn_gemm_fwd(args, _stream()), "mtn_gemm_fwd")
@@ -122,9 +127,10 @@ def conv_silu(xz, conv_w, conv_b, batch, L, di, planes, u=None, halo_lo=None, ha
 
 
 def scan(u, dbl, z, z_col0, w_dt, dt_bias, A2, Dskip, batch, L, di, R, *, y=None, h_in=None, h_out=None, dir_mask=3,
-         sum_delta=None, L_last=0, summary_only=False):
+         sum_delta=None, L_last=0, summary_only=False, dtp=None):
     """Both-direction selective scan; see ``mtn_scan_args`` in include/mtn_b200.h.
-    ``summary_only``: no output is written (chunk-summary pass: ``h_out`` and ``sum_delta`` only)."""
+    ``summary_only``: no output is written (chunk-summary pass: ``h_out`` and ``sum_delta`` only).
+    ``dtp`` (bf16 [M, 2, 2, RP], from ``gemm(..., epilogue=EPI_XPROJ)``): run dt_proj on the tensor cores."""
     _req_cuda(u, dbl, z)
     P = u.shape[0]
     nd = n_dbl_for(R)
@@ -134,7 +140,7 @@ def scan(u, dbl, z, z_col0, w_dt, dt_bias, A2, Dskip, batch, L, di, R, *, y=None
                     Dskip=ptr(Dskip), y=None if summary_only else ptr(y), h_in=ptr(h_in), h_out=ptr(h_out),
                     batch=batch, L=L, di=di, R=R, n_dbl=nd, ld_dbl=dbl.stride(0), ldz=z.stride(0), z_col0=z_col0,
                     planes=P, z_bf16=int(z.dtype == torch.bfloat16), dir_mask=dir_mask, sum_delta=ptr(sum_delta),
-                    L_last=L_last)
+                    L_last=L_last, dtp=ptr(dtp))
     check(_lib.load().mtn_scan_fwd(args, _stream()), "mtn_scan_fwd")
     return y
 

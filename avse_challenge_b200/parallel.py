@@ -149,6 +149,7 @@ class CudaSeqBackend:
             self.w = PackedWeights(hp, sds, self.device, mode)
         self.n_layers = hp.n_mamba
         self.di, self.enc_dim = hp.d_inner, hp.enc_dim
+        self.tc_dt = hp.dt_rank >= 32 and mode == "fp32"    # same rule as SeparatorEngine
 
     # ---- chunk set-up: encoder + cLN + bottleneck on this rank's samples
     def begin(self, mix_slice: torch.Tensor, Lr: int, Ls: int, chunks: int, last_len: int):
@@ -171,6 +172,7 @@ class CudaSeqBackend:
         self.xz = e((rows, 2 * di), self.xz_dt)
         self.u = e((P, rows, 2 * di), torch.bfloat16)
         self.dbl = e((rows, 2 * nd), torch.float32)
+        self.dtp = e((rows, 2, 2, self.ops.rp_for(hp.dt_rank)), torch.bfloat16)
         self.y = e((P, rows, 2 * di), torch.bfloat16)
         self.sep_full = e((Lr + 1, hp.n_spk * N), torch.float32)   # row 0 = last frame of the previous rank
         o, w = self.ops, self.w
@@ -195,12 +197,16 @@ class CudaSeqBackend:
         lo = halo_lo.reshape(1, 3, di).contiguous() if halo_lo is not None else None
         hi = halo_hi.reshape(1, 3, di).contiguous() if halo_hi is not None else None
         o.conv_silu(self.xz, lw["conv_w"], lw["conv_b"], 1, self.Lr, di, self.P, u=self.u, halo_lo=lo, halo_hi=hi)
-        o.gemm(self.u, lw["w_x"], self.Lr, nd, di, out=self.dbl, groups=2, out_group_stride=nd)
+        if self.tc_dt:
+            o.gemm(self.u, lw["w_x"], self.Lr, nd, di, out=self.dbl, groups=2, out_group_stride=nd,
+                   epilogue=self._lib.EPI_XPROJ, epi_param=o.rp_for(hp.dt_rank), aux=self.dtp)
+        else:
+            o.gemm(self.u, lw["w_x"], self.Lr, nd, di, out=self.dbl, groups=2, out_group_stride=nd)
 
     def _scan(self, i: int, **kw):
         lw, hp = self.w.layers[i], self.hp
         return self.ops.scan(self.u, self.dbl, self.xz, hp.d_inner, lw["w_dt"], lw["dt_bias"], lw["A2"], lw["D"], self.C,
-                             self.Ls, hp.d_inner, hp.dt_rank, L_last=self.last_len, **kw)
+                             self.Ls, hp.d_inner, hp.dt_rank, L_last=self.last_len, dtp=self.dtp if self.tc_dt else None, **kw)
 
     def scan_summary(self, i: int):
         """Summary pass: ``(h_end [2, C, di, 16], sum_delta [2, C, di])`` of this rank's sub-chunks, h_in = 0."""

@@ -52,13 +52,15 @@ extern "C" {
 
 typedef void* mtn_stream_t; /* cudaStream_t */
 
-enum { MTN_EPI_STORE = 0, MTN_EPI_INPROJ = 1, MTN_EPI_MASK = 2, MTN_EPI_RELU = 3 };
+enum { MTN_EPI_STORE = 0, MTN_EPI_INPROJ = 1, MTN_EPI_MASK = 2, MTN_EPI_RELU = 3, MTN_EPI_XPROJ = 4 };
 
 typedef struct {
     const void* a;       /* bf16 [planes][a_rows][lda]; group g reads columns [g*K, (g+1)*K) */
     const void* w;       /* bf16 [planes][groups*N][K]  (row-major, K contiguous) */
     void* out;           /* fp32 (or bf16 if out_bf16) [M][ldo]; group g writes columns g*out_group_stride + [0,N) */
-    const void* aux;     /* MTN_EPI_MASK: mix_w fp32 [M][ld_aux]; else NULL */
+    const void* aux;     /* MTN_EPI_MASK: mix_w fp32 [M][ld_aux].  MTN_EPI_XPROJ: OUTPUT dtp, bf16 [M][groups][2][RP]
+                            (hi plane | lo plane of the first RP = epi_param columns of each group: the dt columns of
+                            x_proj in the operand layout of the scan's tensor-core dt_proj).  Else NULL */
     int M, N, K;         /* per-group problem; N % 16 == 0, N <= 256 or N % 256 == 0 or N % 128 == 0; K % 64 == 0 */
     int a_rows;          /* rows allocated per A plane (>= M) */
     int lda, ldo, ld_aux;
@@ -66,7 +68,8 @@ typedef struct {
     int groups;          /* >= 1 */
     int out_group_stride;
     int epilogue;        /* MTN_EPI_* */
-    int epi_param;       /* INPROJ: first column that gets SiLU; MASK: enc_dim (aux column = col % enc_dim) */
+    int epi_param;       /* INPROJ: first column that gets SiLU; MASK: enc_dim (aux column = col % enc_dim);
+                            XPROJ: RP (16 or 32) */
     int out_bf16;        /* 0: fp32 output, 1: bf16 output */
     int max_ctas;        /* 0 = one persistent CTA per SM */
 } mtn_gemm_args;
@@ -92,6 +95,10 @@ typedef struct {
                              h_out(h_in = 0).  y may be NULL in that case (summary pass, no output written). */
     int L_last;           /* 0, or the valid length (1..L) of the LAST sequence of the batch: rows beyond it are
                              ignored (a long recording cut into `batch` equal chunks of L frames, ragged tail) */
+    /* --- dt_proj on the tensor cores (ABI >= 3); optional ---------------------------------------------------- */
+    const void* dtp;      /* nullable: bf16 [M][2][2][RP] written by mtn_gemm_fwd(MTN_EPI_XPROJ), RP = 16 (R <= 16) or
+                             32.  When given, delta_pre = dtp . w_dt is a tcgen05.mma per 16-step tile (W_dt rows as
+                             the M = 128 operand, accumulator in TMEM) instead of R FMAs per (step, channel). */
 } mtn_scan_args;
 
 /* mix [batch][ld_mix >= T] fp32 -> mix_w [batch*L][N] fp32 = relu(conv1d(k=16,s=8)), L = (T-16)/8+1;

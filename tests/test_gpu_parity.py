@@ -152,7 +152,17 @@ def test_decoder(N):
 
 
 # --------------------------------------------------------------------------- selective scan
-def _scan_case(di, R, L, B, seed, P=2, with_state=False, dir_mask=3):
+def _make_dtp(dbl, R):
+    """What the x_proj GEMM epilogue (MTN_EPI_XPROJ) emits: the first RP columns of each direction's dbl row as
+    hi | lo bf16 planes, [M, 2, 2, RP]."""
+    nd, RP = ops.n_dbl_for(R), ops.rp_for(R)
+    cols = torch.stack([dbl[:, :RP], dbl[:, nd:nd + RP]], dim=1)           # [M, 2, RP]
+    hi = cols.to(torch.bfloat16)
+    lo = (cols - hi.float()).to(torch.bfloat16)
+    return torch.stack([hi, lo], dim=2).contiguous()                       # [M, 2, 2, RP]
+
+
+def _scan_case(di, R, L, B, seed, P=2, with_state=False, dir_mask=3, tc=True):
     g = torch.Generator().manual_seed(seed)
     nd = ops.n_dbl_for(R)
     M = B * L
@@ -173,7 +183,8 @@ def _scan_case(di, R, L, B, seed, P=2, with_state=False, dir_mask=3):
     zbuf[:, di:] = torch.nn.functional.silu(z)
     h_out = torch.zeros(2, B, di, 16, device=DEV) if with_state else None
     y = ops.scan(up, dbl.to(DEV), zbuf.to(DEV), di, w_dt.to(DEV), dt_bias.to(DEV), (A * ops.LOG2E).to(DEV),
-                 Dk.to(DEV), B, L, di, R, h_in=h_in.to(DEV) if with_state else None, h_out=h_out, dir_mask=dir_mask)
+                 Dk.to(DEV), B, L, di, R, h_in=h_in.to(DEV) if with_state else None, h_out=h_out, dir_mask=dir_mask,
+                 dtp=_make_dtp(dbl, R).to(DEV) if tc else None)
     torch.cuda.synchronize()
     yv = _planes_value(y).view(B, L, 2 * di)
     uv = _planes_value(up).view(B, L, 2 * di)                   # the values the kernel actually saw
@@ -192,26 +203,47 @@ def _scan_case(di, R, L, B, seed, P=2, with_state=False, dir_mask=3):
     return res
 
 
+@pytest.mark.parametrize("tc", [True, False], ids=["tensor-core-dt", "fma-dt"])
 @pytest.mark.parametrize("di,R,L,B", [(128, 4, 157, 2), (256, 8, 1003, 2), (512, 16, 3999, 1), (1024, 32, 333, 2)])
-def test_scan_matches_selective_scan_ref(di, R, L, B):
-    for err, _ in _scan_case(di, R, L, B, seed=di + L):
-        assert err < 5e-5, err  # fp32 state; y is split-bf16 (2^-18), exp/softplus via ex2/lg2.approx
+def test_scan_matches_selective_scan_ref(di, R, L, B, tc):
+    for err, _ in _scan_case(di, R, L, B, seed=di + L, tc=tc):
+        # fp32 state; y is split-bf16 (2^-18), exp/softplus via ex2.approx.  The tensor-core dt_proj sums its
+        # 4 x RP bf16 products in the MMA's own order and truncating adder: a few 1e-5 more on 4000-step sequences.
+        assert err < (8e-5 if tc else 5e-5), err
 
 
-def test_scan_initial_and_final_state():
-    for err, herr in _scan_case(256, 8, 210, 3, seed=5, with_state=True):
+@pytest.mark.parametrize("tc", [True, False], ids=["tensor-core-dt", "fma-dt"])
+def test_scan_initial_and_final_state(tc):
+    for err, herr in _scan_case(256, 8, 210, 3, seed=5, with_state=True, tc=tc):
         assert err < 5e-5 and herr < 5e-5
 
 
-def test_scan_single_direction_launches():
-    (e0, _), = _scan_case(128, 4, 100, 2, seed=9, dir_mask=1)
-    (e1, _), = _scan_case(128, 4, 100, 2, seed=9, dir_mask=2)
+@pytest.mark.parametrize("tc", [True, False], ids=["tensor-core-dt", "fma-dt"])
+def test_scan_single_direction_launches(tc):
+    (e0, _), = _scan_case(128, 4, 100, 2, seed=9, dir_mask=1, tc=tc)
+    (e1, _), = _scan_case(128, 4, 100, 2, seed=9, dir_mask=2, tc=tc)
     assert e0 < 5e-5 and e1 < 5e-5
 
 
-def test_scan_bf16_mode():
-    for err, _ in _scan_case(256, 16, 500, 2, seed=11, P=1):
+@pytest.mark.parametrize("tc", [True, False], ids=["tensor-core-dt", "fma-dt"])
+def test_scan_bf16_mode(tc):
+    for err, _ in _scan_case(256, 16, 500, 2, seed=11, P=1, tc=tc):
         assert err < 2 ** -8  # single bf16 plane for y (half-ulp 2^-9 .. 2^-8 relative)
+
+
+def test_xproj_epilogue_emits_dt_planes():
+    """MTN_EPI_XPROJ: besides the fp32 dbl rows, the dt columns leave the GEMM as hi | lo bf16 planes."""
+    g = torch.Generator().manual_seed(2)
+    M, di, R = 300, 256, 8
+    nd, RP = ops.n_dbl_for(R), ops.rp_for(R)
+    a = torch.randn(M, 2 * di, generator=g)
+    w = torch.randn(2 * nd, di, generator=g) / di ** 0.5
+    ap, wp = ops.split_planes(a.to(DEV), 2), ops.split_planes(w.to(DEV), 2)
+    dtp = torch.zeros(M, 2, 2, RP, dtype=torch.bfloat16, device=DEV)
+    dbl = ops.gemm(ap, wp, M, nd, di, groups=2, out_group_stride=nd, epilogue=_lib.EPI_XPROJ, epi_param=RP, aux=dtp)
+    plain = ops.gemm(ap, wp, M, nd, di, groups=2, out_group_stride=nd)
+    assert torch.equal(dbl, plain)
+    assert torch.equal(dtp.cpu(), _make_dtp(dbl.cpu(), R))
 
 
 # --------------------------------------------------------------------------- end to end
@@ -356,16 +388,17 @@ def test_chunked_scan_summary_fold_seeded_equals_one_shot(L, C, slow):
     up = ops.split_planes(u.to(DEV), 2)
     dbl_d, z_d = dbl.to(DEV), zbuf.to(DEV)
     hfin = torch.zeros(2, 1, di, 16, device=DEV)
+    dtp = _make_dtp(dbl, R).to(DEV)
     y_ref = ops.scan(up[:, :L].contiguous(), dbl_d[:L].contiguous(), z_d[:L].contiguous(), di, w_dt, dt_bias, A2, Dk, 1,
-                     L, di, R, h_out=hfin)
+                     L, di, R, h_out=hfin, dtp=dtp[:L].contiguous())
     # chunked
     h_end = torch.zeros(2, Cc, di, 16, device=DEV)
     sdl = torch.zeros(2, Cc, di, device=DEV)
     last = L - (Cc - 1) * Ls
     ops.scan(up, dbl_d, z_d, di, w_dt, dt_bias, A2, Dk, Cc, Ls, di, R, h_out=h_end, sum_delta=sdl, L_last=last,
-             summary_only=True)
+             summary_only=True, dtp=dtp)
     h_in, h_final = ops.fold_states(h_end, sdl, A2, 0, Cc, want_final=True)
-    y = ops.scan(up, dbl_d, z_d, di, w_dt, dt_bias, A2, Dk, Cc, Ls, di, R, h_in=h_in, L_last=last)
+    y = ops.scan(up, dbl_d, z_d, di, w_dt, dt_bias, A2, Dk, Cc, Ls, di, R, h_in=h_in, L_last=last, dtp=dtp)
     torch.cuda.synchronize()
     got, ref = _planes_value(y)[:L], _planes_value(y_ref)
     assert rel_mixed(got, ref) < 2e-5, rel_mixed(got, ref)

@@ -27,8 +27,12 @@ A2 = -torch.exp(torch.randn(2, di, 16, device=dev, generator=g) * 0.5 + 0.5) * o
 Dk = torch.randn(2, di, device=dev, generator=g)
 y = torch.empty_like(u)
 hout = torch.zeros(2, a.batch, di, 16, device=dev)
-run_full = lambda: ops.scan(u, dbl, xz, di, w_dt, dt_bias, A2, Dk, a.batch, a.L, di, R, y=y)
-run_sum = lambda: ops.scan(u, dbl, xz, di, w_dt, dt_bias, A2, Dk, a.batch, a.L, di, R, h_out=hout, summary_only=True)
+RP = ops.rp_for(R)
+cols = torch.stack([dbl[:, :RP], dbl[:, nd:nd + RP]], dim=1)
+hi = cols.to(torch.bfloat16); lo = (cols - hi.float()).to(torch.bfloat16)
+dtp = torch.stack([hi, lo], dim=2).contiguous()            # [M, 2, 2, RP] as the x_proj epilogue writes it
+run_full = lambda: ops.scan(u, dbl, xz, di, w_dt, dt_bias, A2, Dk, a.batch, a.L, di, R, y=y, dtp=dtp)
+run_sum = lambda: ops.scan(u, dbl, xz, di, w_dt, dt_bias, A2, Dk, a.batch, a.L, di, R, h_out=hout, summary_only=True, dtp=dtp)
 s_io = 4 if P == 2 else 2
 alg = 2 * (M * (4 * di + 32) * s_io + (di * 16 + 2 * di) * 4)
 y_ref = None
