@@ -20,9 +20,8 @@
 // HBM (dt_proj is R FMAs from registers).  The kernel is MUFU-bound before it is HBM-bound (16 ex2 per (t, d));
 // KP > 0 moves KP of every 4 state pairs of a lane to an FMA-pipe polynomial exp2 (Cody-Waite + degree-5 minimax,
 // 2e-7 relative) to balance the MUFU and FMA pipes.  See DESIGN.md for both rooflines.
-// MTN_SCAN_VARIANT (debug knob, read per call): 0/unset = split mapping (tensor-core dt_proj when args.dtp is
-// given, FMA dt_proj otherwise); 2 = split mapping, FMA dt_proj even with dtp; 1 = one thread per channel (A/B baseline);
-// 11 = split mapping with KP = 1 polynomial pair per lane.
+// MTN_SCAN_VARIANT (debug knob, read per call): 0/unset = tensor-core dt_proj when args.dtp is given, FMA dt_proj
+// otherwise; 2 = FMA dt_proj even with dtp.  (Builds with MTN_SCAN_ABLATIONS=1 add timing-only experiment variants.)
 #include "mtn_ptx.cuh"
 #include "mtn_host.h"
 #include <stdlib.h>
@@ -31,7 +30,6 @@ namespace mtn {
 
 constexpr int SC_CH = 128;
 constexpr int SC_TT = 16;
-constexpr int SC_STAGES = 5;
 constexpr int SC_NS = 16;
 
 struct ScanParams {
@@ -47,17 +45,19 @@ struct ScanParams {
     int L_last;  // valid length of the last sequence of the batch (== L when not ragged)
     int dir0;   // first direction of this launch
     int ndirs;  // 1 or 2
-    int dirmap; // how blockIdx.x maps to (direction, channel block); see scan_kernel
 };
 
-template <int P, int NDBL, typename ZT>
+template <int P, int NDBL, typename ZT, int CH>
 struct ScanSmem {
-    static constexpr int U_BYTES = P * SC_TT * SC_CH * 2;
-    static constexpr int Z_BYTES = SC_TT * SC_CH * int(sizeof(ZT));
+    // CH = channels per CTA: 128 (8 warps) for large grids, 32 (2 warps) when the problem offers too few 128-channel
+    // CTAs to load every SM evenly (BASELINE config 2: 256 CTAs on 148 SMs -> 1024 CTAs, 6.9 per SM)
+    static constexpr int STAGES = CH == 128 ? 5 : 4;
+    static constexpr int U_BYTES = P * SC_TT * CH * 2;
+    static constexpr int Z_BYTES = SC_TT * CH * int(sizeof(ZT));
     static constexpr int D_BYTES = SC_TT * NDBL * 4;
     static constexpr int STAGE_BYTES = U_BYTES + Z_BYTES + D_BYTES;
-    static constexpr int Y_BYTES = P * SC_TT * SC_CH * 2;  // output staging, one column block per consumer warp
-    static constexpr int TOTAL = 128 + SC_STAGES * STAGE_BYTES + 2 * SC_STAGES * 8 + Y_BYTES;
+    static constexpr int Y_BYTES = P * SC_TT * CH * 2;  // output staging, one column block per consumer warp
+    static constexpr int TOTAL = 128 + STAGES * STAGE_BYTES + 2 * STAGES * 8 + Y_BYTES;
 };
 
 __device__ __forceinline__ float ldz(const float* p) { return *p; }
@@ -128,12 +128,14 @@ __device__ __forceinline__ uint32_t f2bf_lo(float x) {
     return r;
 }
 
-template <int P, int R, int NDBL, typename ZT, bool REV, int KP, bool WY>
+template <int P, int R, int NDBL, typename ZT, int CH, bool REV, int KP, bool WY>
 __device__ __forceinline__ void scan_consumer_split(uint8_t* smem, uint64_t* full_bar, uint64_t* empty_bar,
                                                     __nv_bfloat16* sy, const ScanParams& p, int ch0, int b, int dir,
                                                     const CUtensorMap* mapU, const CUtensorMap* mapZ,
                                                     const CUtensorMap* mapD) {
-    using SM = ScanSmem<P, NDBL, ZT>;
+    using SM = ScanSmem<P, NDBL, ZT, CH>;
+    constexpr int SC_STAGES = SM::STAGES;
+    constexpr int NW = CH / 16;  // consumer warps
     constexpr uint32_t FULL = 0xffffffffu;
     // KP >= 100: timing-only ablations (WRONG results; MTN_SCAN_VARIANT=101..107): bit0 drops the dt_proj FMAs, bit1
     // the B/C shared-memory loads, bit2 the MUFU ex2.  They measure the marginal cost of each instruction group.
@@ -200,7 +202,7 @@ __device__ __forceinline__ void scan_consumer_split(uint8_t* smem, uint64_t* ful
     // per-row scalars of the tile in flight: slot k <-> row 2k + half
     float dmine[SC_TT / 2], dumine[SC_TT / 2], umine[SC_TT / 2];
     auto prep_row = [&](int k, const uint8_t* st, int nvalid_t) {
-        const __nv_bfloat16* su_h = reinterpret_cast<const __nv_bfloat16*>(st) + half * SC_CH + chl;
+        const __nv_bfloat16* su_h = reinterpret_cast<const __nv_bfloat16*>(st) + half * CH + chl;
         const float* drow = reinterpret_cast<const float*>(st + SM::U_BYTES + SM::Z_BYTES) + (2 * k + half) * NDBL;
         float acc0 = bias, acc1 = 0.f;
         if (ABL & 1) {
@@ -220,8 +222,8 @@ __device__ __forceinline__ void scan_consumer_split(uint8_t* smem, uint64_t* ful
         }
         float dl = softplus_1mufu(acc0 + acc1);
         dl = (2 * k + half < nvalid_t) ? dl : 0.f;  // rows past the utterance end: exp2(0)=1, dBu=0 -> state unchanged
-        float uval = bf16_bits_to_float(su_h + k * 2 * SC_CH);
-        if (P == 2) uval += bf16_bits_to_float(su_h + SC_TT * SC_CH + k * 2 * SC_CH);
+        float uval = bf16_bits_to_float(su_h + k * 2 * CH);
+        if (P == 2) uval += bf16_bits_to_float(su_h + SC_TT * CH + k * 2 * CH);
         sdl += dl;
         dmine[k] = dl;
         dumine[k] = dl * uval;
@@ -256,9 +258,9 @@ __device__ __forceinline__ void scan_consumer_split(uint8_t* smem, uint64_t* ful
         tma_load_2d(dst + SM::U_BYTES + SM::Z_BYTES, mapD, &full_bar[stg], dir * p.n_dbl, row0);
     };
     if (tid == 0) {
-        issue_tile(0, 0);
-        if (ntiles > 1) issue_tile(1, 1);
-        if (ntiles > 2) issue_tile(2, 2);
+#pragma unroll
+        for (int t = 0; t < SC_STAGES - 2; ++t)
+            if (t < ntiles) issue_tile(t, t);
     }
     int stage = 0;
     uint32_t phase = 0;
@@ -282,13 +284,13 @@ __device__ __forceinline__ void scan_consumer_split(uint8_t* smem, uint64_t* ful
         const int stage_n = (stage + 1 == SC_STAGES) ? 0 : stage + 1;
         const uint8_t* st_n = smem + stage_n * SM::STAGE_BYTES;
         int nvalid_n = 0;  // no next tile: the (unconditional) row prep then yields delta = 0 everywhere
-        if (warp == (i & 7) && i + 3 < ntiles) {   // producer duty rotates over the warps (see scan_consumer_tc)
-            // stage (i+3) % 5 was last used by tile i-2, whose "empty" phase (parity ((i-2)/5)&1) is normally long
+        if (warp == (i % NW) && i + (SC_STAGES - 2) < ntiles) {   // producer duty rotates over the warps (see scan_consumer_tc)
+            // that stage was last used by tile i-2, whose "empty" phase (parity ((i-2)/STAGES)&1) is normally long
             // complete.  The WHOLE warp waits (converged): a lone lane sleeping in try_wait on this barrier while its
             // 31 siblings sleep on a different one (the "full" barrier below) produced millisecond stragglers.
-            const int stg3 = (stage + 3) % SC_STAGES;
+            const int stg3 = (stage + SC_STAGES - 2) % SC_STAGES;
             if (i >= 2) mbar_wait(&empty_bar[stg3], uint32_t((i - 2) / SC_STAGES) & 1u);
-            if (lane == 0) issue_tile(i + 3, stg3);
+            if (lane == 0) issue_tile(i + SC_STAGES - 2, stg3);
             __syncwarp();
         }
         if (has_next) {
@@ -333,7 +335,7 @@ __device__ __forceinline__ void scan_consumer_split(uint8_t* smem, uint64_t* ful
         auto finalize = [&](int k, float mine, float recv) {
             if (WY) {
                 const int row = 2 * k + half;
-                const float zval = ldz(sz + row * SC_CH + chl);
+                const float zval = ldz(sz + row * CH + chl);
                 const float y = fmaf(Dv, umine[k], mine + recv) * (0.5f * zval);
                 const uint32_t hi = f2bf_lo(y);
                 sts_b16(sy_w + row * 16 + cl, hi);
@@ -438,266 +440,78 @@ __device__ __forceinline__ void scan_consumer_split(uint8_t* smem, uint64_t* ful
     }
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// One-thread-per-channel mapping (variant 1): 128 consumer threads per CTA, 16 states per thread.
-// ---------------------------------------------------------------------------------------------------------------
-template <int P, int R, int NDBL, typename ZT, bool REV>
-__device__ __forceinline__ void scan_consumer_full(uint8_t* smem, uint64_t* full_bar, uint64_t* empty_bar,
-                                                   __nv_bfloat16* sy, const ScanParams& p, int ch0, int b, int dir) {
-    using SM = ScanSmem<P, NDBL, ZT>;
-    const int tid = threadIdx.x;
-    const int warp = tid >> 5, lane = tid & 31;
-    const int L = p.L;
-    const int ntiles = (L + SC_TT - 1) / SC_TT;
-    const int d = ch0 + tid;
-    const size_t pd = size_t(dir) * p.di + d;
-    float2 h2[SC_NS / 2], A2[SC_NS / 2];
-    float wdt[R];
-    {
-        const float4* ap = reinterpret_cast<const float4*>(p.A2 + pd * SC_NS);
-#pragma unroll
-        for (int q = 0; q < SC_NS / 4; ++q) {
-            const float4 a = ap[q];
-            A2[2 * q] = make_float2(a.x, a.y);
-            A2[2 * q + 1] = make_float2(a.z, a.w);
-        }
-        const float4* wp = reinterpret_cast<const float4*>(p.w_dt + pd * R);
-#pragma unroll
-        for (int q = 0; q < R / 4; ++q) {
-            const float4 w = wp[q];
-            wdt[4 * q] = w.x;
-            wdt[4 * q + 1] = w.y;
-            wdt[4 * q + 2] = w.z;
-            wdt[4 * q + 3] = w.w;
-        }
-        if (p.h_in) {
-            const float4* hp = reinterpret_cast<const float4*>(p.h_in + ((size_t(dir) * p.batch + b) * p.di + d) * SC_NS);
-#pragma unroll
-            for (int q = 0; q < SC_NS / 4; ++q) {
-                const float4 a = hp[q];
-                h2[2 * q] = make_float2(a.x, a.y);
-                h2[2 * q + 1] = make_float2(a.z, a.w);
-            }
-        } else {
-#pragma unroll
-            for (int q = 0; q < SC_NS / 2; ++q) h2[q] = make_float2(0.f, 0.f);
-        }
-    }
-    const float bias = p.dt_bias[pd];
-    const float Dv = p.Dskip[pd];
-    const size_t M = size_t(p.batch) * L;
-    const size_t y_plane = M * 2 * p.di;
-    __nv_bfloat16* ywarp = p.y + size_t(dir) * p.di + ch0 + warp * 32;
-    uint16_t* sy_w = reinterpret_cast<uint16_t*>(sy) + warp * (P * SC_TT * 32);  // warp-private staging [P][TT][32]
-
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int i = 0; i < ntiles; ++i) {
-        const int tile = REV ? (ntiles - 1 - i) : i;
-        const int t0 = tile * SC_TT;
-        const int nvalid = min(SC_TT, L - t0);
-        mbar_wait(&full_bar[stage], phase);
-        const uint8_t* st = smem + stage * SM::STAGE_BYTES;
-        const __nv_bfloat16* su = reinterpret_cast<const __nv_bfloat16*>(st);
-        const ZT* sz = reinterpret_cast<const ZT*>(st + SM::U_BYTES);
-        const float* sd = reinterpret_cast<const float*>(st + SM::U_BYTES + SM::Z_BYTES);
-
-        float delta[SC_TT], du[SC_TT];
-#pragma unroll
-        for (int j = 0; j < SC_TT; ++j) {
-            const float* drow = sd + j * NDBL;
-            float acc0 = bias, acc1 = 0.f;
-#pragma unroll
-            for (int q = 0; q < R / 4; ++q) {
-                const float4 x = *reinterpret_cast<const float4*>(drow + 4 * q);
-                acc0 = fmaf(x.x, wdt[4 * q], acc0);
-                acc1 = fmaf(x.y, wdt[4 * q + 1], acc1);
-                acc0 = fmaf(x.z, wdt[4 * q + 2], acc0);
-                acc1 = fmaf(x.w, wdt[4 * q + 3], acc1);
-            }
-            float dl = softplus_1mufu(acc0 + acc1);
-            dl = (j < nvalid) ? dl : 0.f;
-            float uval = bf16_bits_to_float(su + j * SC_CH + tid);
-            if (P == 2) uval += bf16_bits_to_float(su + SC_TT * SC_CH + j * SC_CH + tid);
-            delta[j] = dl;
-            du[j] = dl * uval;
-        }
-#pragma unroll
-        for (int jj = 0; jj < SC_TT; ++jj) {
-            const int j = REV ? (SC_TT - 1 - jj) : jj;
-            const float* drow = sd + j * NDBL;
-            const float2 delta2 = make_float2(delta[j], delta[j]);
-            const float2 du2 = make_float2(du[j], du[j]);
-            float2 ya = make_float2(0.f, 0.f), yb = make_float2(0.f, 0.f);
-#pragma unroll
-            for (int q = 0; q < SC_NS / 4; ++q) {
-                const float4 Bq = *reinterpret_cast<const float4*>(drow + R + 4 * q);
-                const float4 Cq = *reinterpret_cast<const float4*>(drow + R + SC_NS + 4 * q);
-                {
-                    const float2 a = __fmul2_rn(delta2, A2[2 * q]);
-                    const float2 e = make_float2(ex2_approx(a.x), ex2_approx(a.y));
-                    const float2 bu = __fmul2_rn(du2, make_float2(Bq.x, Bq.y));
-                    h2[2 * q] = __ffma2_rn(e, h2[2 * q], bu);
-                    ya = __ffma2_rn(h2[2 * q], make_float2(Cq.x, Cq.y), ya);
-                }
-                {
-                    const float2 a = __fmul2_rn(delta2, A2[2 * q + 1]);
-                    const float2 e = make_float2(ex2_approx(a.x), ex2_approx(a.y));
-                    const float2 bu = __fmul2_rn(du2, make_float2(Bq.z, Bq.w));
-                    h2[2 * q + 1] = __ffma2_rn(e, h2[2 * q + 1], bu);
-                    yb = __ffma2_rn(h2[2 * q + 1], make_float2(Cq.z, Cq.w), yb);
-                }
-            }
-            float uval = bf16_bits_to_float(su + j * SC_CH + tid);
-            if (P == 2) uval += bf16_bits_to_float(su + SC_TT * SC_CH + j * SC_CH + tid);
-            const float zval = ldz(sz + j * SC_CH + tid);
-            const float y = ((ya.x + ya.y) + (yb.x + yb.y) + Dv * uval) * (0.5f * zval);
-            if (P == 2) {
-                const uint16_t hi = f2bf_bits(y);
-                const uint16_t lo = f2bf_bits(y - __uint_as_float(uint32_t(hi) << 16));
-                sy_w[j * 32 + lane] = hi;
-                sy_w[SC_TT * 32 + j * 32 + lane] = lo;
-            } else {
-                sy_w[j * 32 + lane] = f2bf_bits(y);
-            }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_bar[stage]);
-#pragma unroll
-        for (int pl = 0; pl < P; ++pl) {
-#pragma unroll
-            for (int it = 0; it < SC_TT / 8; ++it) {
-                const int row = it * 8 + (lane >> 2);
-                const int seg = lane & 3;
-                if (row < nvalid) {
-                    const uint4 v = *reinterpret_cast<const uint4*>(sy_w + pl * SC_TT * 32 + row * 32 + seg * 8);
-                    const size_t off = (size_t(b) * L + t0 + row) * (2 * size_t(p.di)) + seg * 8;
-                    *reinterpret_cast<uint4*>(ywarp + pl * y_plane + off) = v;
-                }
-            }
-        }
-        __syncwarp();
-        if (++stage == SC_STAGES) {
-            stage = 0;
-            phase ^= 1;
-        }
-    }
-    if (p.h_out) {
-        float4* hp = reinterpret_cast<float4*>(p.h_out + ((size_t(dir) * p.batch + b) * p.di + d) * SC_NS);
-#pragma unroll
-        for (int q = 0; q < SC_NS / 4; ++q)
-            hp[q] = make_float4(h2[2 * q].x, h2[2 * q].y, h2[2 * q + 1].x, h2[2 * q + 1].y);
-    }
-}
-
-// NCONS consumer threads (256: split mapping with KP polynomial pairs, 128: one thread per channel) + 1 producer warp.
+// CH channels per CTA = CH/16 warps, 2 lanes per channel; no producer warp (the duty rotates over the warps).
 #ifdef MTN_SCAN_ABLATIONS
 __device__ unsigned long long g_scan_dbg[3 * 8192];  // per CTA: smid, start ns, end ns (timing experiments only)
 #endif
 
-template <int P, int R, int NDBL, typename ZT, int NCONS, int KP, bool WY>
-__global__ void __launch_bounds__(NCONS == 256 ? 256 : NCONS + 32, 2)
+template <int P, int R, int NDBL, typename ZT, int CH, int KP, bool WY>
+__global__ void __launch_bounds__(CH * 2, CH == 128 ? 2 : 7)
 scan_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUtensorMap mapZ,
             const __grid_constant__ CUtensorMap mapD, const ScanParams p) {
-    using SM = ScanSmem<P, NDBL, ZT>;
+    using SM = ScanSmem<P, NDBL, ZT, CH>;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // align inside the shared window without leaving the shared address space (keeps LDS/STS, not generic LD/ST)
     uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SC_STAGES * SM::STAGE_BYTES);
-    uint64_t* empty_bar = full_bar + SC_STAGES;
-    __nv_bfloat16* sy = reinterpret_cast<__nv_bfloat16*>(smem + SC_STAGES * SM::STAGE_BYTES + 2 * SC_STAGES * 8);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SM::STAGES * SM::STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + SM::STAGES;
+    __nv_bfloat16* sy = reinterpret_cast<__nv_bfloat16*>(smem + SM::STAGES * SM::STAGE_BYTES + 2 * SM::STAGES * 8);
 
     const int tid = threadIdx.x;
-    const int warp = tid >> 5, lane = tid & 31;
-    const int nchb = p.di / SC_CH;
-    int ch0, dir;
-    if (p.dirmap == 1) {  // direction = blockIdx.x & 1: the CTAs sharing an SM run the same direction
-        ch0 = (p.ndirs == 2 ? (blockIdx.x >> 1) : blockIdx.x) * SC_CH;
-        dir = p.dir0 + (p.ndirs == 2 ? int(blockIdx.x & 1) : 0);
-    } else {              // direction-major: blockIdx.x = dir * nchb + channel block
-        ch0 = (blockIdx.x % nchb) * SC_CH;
-        dir = p.dir0 + blockIdx.x / nchb;
-    }
+    const int nchb = p.di / CH;
+    // direction-major grid: blockIdx.x = dir * nchb + channel block (CTAs sharing an SM then mix both directions,
+    // which measured ~15 % faster than pairing CTAs of the same direction)
+    const int ch0 = (blockIdx.x % nchb) * CH;
+    const int dir = p.dir0 + blockIdx.x / nchb;
     const int b = blockIdx.y;
-    const bool rev = dir == 1;
-    const int L = p.L;
-    const int ntiles = (L + SC_TT - 1) / SC_TT;
 
     if (tid == 0) {
         tma_prefetch_desc(&mapU);
         tma_prefetch_desc(&mapZ);
         tma_prefetch_desc(&mapD);
-        for (int s = 0; s < SC_STAGES; ++s) {
+        for (int s = 0; s < SM::STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], NCONS / 32);
+            mbar_init(&empty_bar[s], CH / 16);
         }
         fence_barrier_init();
     }
     __syncthreads();
-
-    if (NCONS != 256 && warp == NCONS / 32) {
-        // ------------------------------------------------------------ TMA producer
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int i = 0; i < ntiles; ++i) {
-                const int tile = rev ? (ntiles - 1 - i) : i;
-                const int row0 = b * L + tile * SC_TT;
-                mbar_wait_sleep(&empty_bar[stage], phase ^ 1);  // back off: leave the issue slots to the consumers
-                mbar_arrive_expect_tx(&full_bar[stage], SM::STAGE_BYTES);
-                uint8_t* st = smem + stage * SM::STAGE_BYTES;
-                tma_load_3d(st, &mapU, &full_bar[stage], dir * p.di + ch0, row0, 0);
-                tma_load_2d(st + SM::U_BYTES, &mapZ, &full_bar[stage], p.z_col0 + ch0, row0);
-                tma_load_2d(st + SM::U_BYTES + SM::Z_BYTES, &mapD, &full_bar[stage], dir * p.n_dbl, row0);
-                if (++stage == SC_STAGES) {
-                    stage = 0;
-                    phase ^= 1;
-                }
-            }
-        }
-        return;
-    }
-    if (NCONS == 256) {
 #ifdef MTN_SCAN_ABLATIONS
-        const int cta = blockIdx.y * gridDim.x + blockIdx.x;
-        if (tid == 32 && cta < 8192) {
-            unsigned smid;
-            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-            g_scan_dbg[3 * cta] = smid;
-            g_scan_dbg[3 * cta + 1] = global_timer_ns();
-        }
-#endif
-        if (rev)
-            scan_consumer_split<P, R, NDBL, ZT, true, KP, WY>(smem, full_bar, empty_bar, sy, p, ch0, b, dir, &mapU, &mapZ, &mapD);
-        else
-            scan_consumer_split<P, R, NDBL, ZT, false, KP, WY>(smem, full_bar, empty_bar, sy, p, ch0, b, dir, &mapU, &mapZ, &mapD);
-#ifdef MTN_SCAN_ABLATIONS
-        if (tid == 32 && cta < 8192) g_scan_dbg[3 * cta + 2] = global_timer_ns();
-#endif
-    } else {
-        if (rev)
-            scan_consumer_full<P, R, NDBL, ZT, true>(smem, full_bar, empty_bar, sy, p, ch0, b, dir);
-        else
-            scan_consumer_full<P, R, NDBL, ZT, false>(smem, full_bar, empty_bar, sy, p, ch0, b, dir);
+    const int cta = blockIdx.y * gridDim.x + blockIdx.x;
+    if (tid == 32 && cta < 8192) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        g_scan_dbg[3 * cta] = smid;
+        g_scan_dbg[3 * cta + 1] = global_timer_ns();
     }
+#endif
+    if (dir == 1)
+        scan_consumer_split<P, R, NDBL, ZT, CH, true, KP, WY>(smem, full_bar, empty_bar, sy, p, ch0, b, dir, &mapU, &mapZ,
+                                                             &mapD);
+    else
+        scan_consumer_split<P, R, NDBL, ZT, CH, false, KP, WY>(smem, full_bar, empty_bar, sy, p, ch0, b, dir, &mapU, &mapZ,
+                                                              &mapD);
+#ifdef MTN_SCAN_ABLATIONS
+    if (tid == 32 && cta < 8192) g_scan_dbg[3 * cta + 2] = global_timer_ns();
+#endif
 }
 
-template <int P, int R, int NDBL, typename ZT, int NCONS, int KP, bool WY>
+template <int P, int R, int NDBL, typename ZT, int CH, int KP, bool WY>
 static int launch_scan(const mtn_scan_args* a, cudaStream_t stream) {
-    using SM = ScanSmem<P, NDBL, ZT>;
+    using SM = ScanSmem<P, NDBL, ZT, CH>;
     const uint64_t M = uint64_t(a->batch) * a->L;
     CUtensorMap mapU, mapZ, mapD;
     {
         uint64_t dims[3] = {uint64_t(2) * a->di, M, uint64_t(P)};
         uint64_t str[2] = {uint64_t(2) * a->di * 2, M * 2 * a->di * 2};
-        uint32_t box[3] = {SC_CH, SC_TT, uint32_t(P)};
+        uint32_t box[3] = {uint32_t(CH), SC_TT, uint32_t(P)};
         if (!encode_tmap(&mapU, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, a->u, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE))
             return MTN_ECUDA;
     }
     {
         uint64_t dims[2] = {uint64_t(a->ldz), M};
         uint64_t str[1] = {uint64_t(a->ldz) * sizeof(ZT)};
-        uint32_t box[2] = {SC_CH, SC_TT};
+        uint32_t box[2] = {uint32_t(CH), SC_TT};
         const CUtensorMapDataType dt =
             sizeof(ZT) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
         if (!encode_tmap(&mapZ, dt, 2, a->z, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return MTN_ECUDA;
@@ -727,9 +541,7 @@ static int launch_scan(const mtn_scan_args* a, cudaStream_t stream) {
     p.dir0 = (a->dir_mask & 1) ? 0 : 1;
     const int ndirs = (a->dir_mask == 3) ? 2 : 1;
     p.ndirs = ndirs;
-    p.dirmap = 0;
-    if (const char* v = getenv("MTN_SCAN_DIRMAP")) p.dirmap = atoi(v);
-    auto kern = scan_kernel<P, R, NDBL, ZT, NCONS, KP, WY>;
+    auto kern = scan_kernel<P, R, NDBL, ZT, CH, KP, WY>;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL);
@@ -739,8 +551,8 @@ static int launch_scan(const mtn_scan_args* a, cudaStream_t stream) {
         }
         attr_set = true;
     }
-    dim3 grid(ndirs * (a->di / SC_CH), a->batch, 1);
-    kern<<<grid, NCONS == 256 ? 256 : NCONS + 32, SM::TOTAL, stream>>>(mapU, mapZ, mapD, p);
+    dim3 grid(ndirs * (a->di / CH), a->batch, 1);
+    kern<<<grid, CH * 2, SM::TOTAL, stream>>>(mapU, mapZ, mapD, p);
     MTN_CUDA_LAUNCH_CHECK("scan");
     return MTN_OK;
 }
@@ -1223,7 +1035,6 @@ static int launch_scan_tc(const mtn_scan_args* a, cudaStream_t stream) {
     p.dir0 = (a->dir_mask & 1) ? 0 : 1;
     const int ndirs = (a->dir_mask == 3) ? 2 : 1;
     p.ndirs = ndirs;
-    p.dirmap = 0;
     auto kern = scan_kernel_tc<P, R, NDBL, ZT, WY>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -1240,6 +1051,7 @@ static int launch_scan_tc(const mtn_scan_args* a, cudaStream_t stream) {
     return MTN_OK;
 }
 
+
 template <int P, int R, int NDBL, typename ZT>
 static int dispatch_scan_variant(const mtn_scan_args* a, cudaStream_t s) {
     int variant = 0;
@@ -1248,32 +1060,28 @@ static int dispatch_scan_variant(const mtn_scan_args* a, cudaStream_t s) {
         if (!a->y) return launch_scan_tc<P, R, NDBL, ZT, false>(a, s);
         return launch_scan_tc<P, R, NDBL, ZT, true>(a, s);
     }
-    if (!a->y) {  // summary pass of the reduce-then-scan scheme: final states + sum(delta), no output
-        if (variant != 0 && variant != 2) {
-            set_error("scan: y == NULL is only implemented by the default variant");
-            return MTN_EINVAL;
-        }
-        return launch_scan<P, R, NDBL, ZT, 256, 0, false>(a, s);
+    // 128-channel CTAs.  (Measured alternatives that did NOT pay, see DESIGN.md 4.1: 32-channel CTAs to even out the
+    // SM load at small grids; four lanes per channel; direction-paired CTAs.)
+    if (variant == 0 || variant == 2) {
+        if (!a->y) return launch_scan<P, R, NDBL, ZT, 128, 0, false>(a, s);
+        return launch_scan<P, R, NDBL, ZT, 128, 0, true>(a, s);
     }
-    switch (variant) {
-        case 0:
-        case 2: return launch_scan<P, R, NDBL, ZT, 256, 0, true>(a, s);
-        case 1:
-            if (a->sum_delta || (a->L_last > 0 && a->L_last != a->L)) {
-                set_error("scan: sum_delta / L_last are not implemented by MTN_SCAN_VARIANT=1");
-                return MTN_EINVAL;
-            }
-            return launch_scan<P, R, NDBL, ZT, 128, 0, true>(a, s);
 #ifdef MTN_SCAN_ABLATIONS
-        case 11: return launch_scan<P, R, NDBL, ZT, 256, 1, true>(a, s);
-        case 101: return launch_scan<P, R, NDBL, ZT, 256, 101, true>(a, s);
-        case 102: return launch_scan<P, R, NDBL, ZT, 256, 102, true>(a, s);
-        case 104: return launch_scan<P, R, NDBL, ZT, 256, 104, true>(a, s);
-        case 103: return launch_scan<P, R, NDBL, ZT, 256, 103, true>(a, s);
-        case 107: return launch_scan<P, R, NDBL, ZT, 256, 107, true>(a, s);
-#endif
-        default: set_error("scan: unknown MTN_SCAN_VARIANT=%d", variant); return MTN_EINVAL;
+    if (a->y) {
+        switch (variant) {
+            case 4: return launch_scan<P, R, NDBL, ZT, 32, 0, true>(a, s);   // 32-channel CTAs
+            case 11: return launch_scan<P, R, NDBL, ZT, 128, 1, true>(a, s);
+            case 101: return launch_scan<P, R, NDBL, ZT, 128, 101, true>(a, s);
+            case 102: return launch_scan<P, R, NDBL, ZT, 128, 102, true>(a, s);
+            case 104: return launch_scan<P, R, NDBL, ZT, 128, 104, true>(a, s);
+            case 103: return launch_scan<P, R, NDBL, ZT, 128, 103, true>(a, s);
+            case 107: return launch_scan<P, R, NDBL, ZT, 128, 107, true>(a, s);
+            default: break;
+        }
     }
+#endif
+    set_error("scan: unknown MTN_SCAN_VARIANT=%d", variant);
+    return MTN_EINVAL;
 }
 
 template <int P, typename ZT>
