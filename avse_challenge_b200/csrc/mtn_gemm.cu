@@ -11,7 +11,7 @@
 //    three tcgen05.mma per K-step (hi*hi + lo*hi + hi*lo) into one fp32 TMEM accumulator -- ~2^-17 operand
 //    precision at the HBM traffic of plain fp32, with no in-kernel conversion pass.  P = 1 is bf16 mode.
 //  * Persistent, warp-specialised CTA (one per SM): warp 0 = TMA producer (128B-swizzled boxes straight into the
-//    UMMA canonical K-major layout), warp 1 = single-thread tcgen05.mma issuer, warps 2-5 = epilogue.  Two TMEM
+//    UMMA canonical K-major layout), warp 1 = single-thread tcgen05.mma issuer, warps 2-9 = epilogue.  Two TMEM
 //    accumulators so the epilogue of tile i overlaps the MMAs of tile i+1.
 //  * These GEMMs are HBM-bound (K <= 1024, output-write dominated), so the epilogue is the part that matters:
 //    TMEM -> registers -> per-warp padded smem transpose -> fully coalesced 128-bit global stores, with the
@@ -23,7 +23,8 @@ namespace mtn {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
-constexpr int STG_LD = 36;  // floats per staging row (32 + 4 pad: conflict-free 128-bit accesses)
+constexpr int STG_LD = 20;  // floats per staging row (16 + 4 pad: conflict-free 128-bit accesses)
+constexpr int EPI_WARPS = 8;  // two per TMEM lane quarter: they take alternate 16-column chunks of the accumulator
 
 struct GemmParams {
     void* out;
@@ -40,7 +41,7 @@ struct GemmCfg {
     static constexpr int A_BYTES = BM * BK * 2;
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = P * (A_BYTES + B_BYTES);
-    static constexpr int STAGING_BYTES = 4 * 32 * STG_LD * 4;
+    static constexpr int STAGING_BYTES = EPI_WARPS * 32 * STG_LD * 4;
     static constexpr int BAR_BYTES = 256;
     static constexpr int BUDGET = 227 * 1024 - 1024 - STAGING_BYTES - BAR_BYTES;
     static constexpr int STAGES_RAW = BUDGET / STAGE_BYTES;
@@ -53,7 +54,7 @@ struct GemmCfg {
 };
 
 template <int P, int BN, int EPI, bool OUT_BF16>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                     const GemmParams p) {
     using Cfg = GemmCfg<P, BN>;
@@ -79,7 +80,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull_bar[a], 1);
-            mbar_init(&tempty_bar[a], 4);  // one arrive per epilogue warp
+            mbar_init(&tempty_bar[a], EPI_WARPS);  // one arrive per epilogue warp
         }
         fence_barrier_init();
     }
@@ -163,9 +164,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         }
         __syncwarp();
     } else {
-        // ------------------------------------------------------------ epilogue warps (2..5)
-        const int q = warp & 3;  // TMEM lane quarter this warp may read
-        float* stg = staging + (warp - 2) * 32 * STG_LD;
+        // ------------------------------------------------------------ epilogue warps (2..9)
+        // One warp alone on an SM sub-partition is latency-bound (~5 cycles per instruction), and the epilogue, not the
+        // MMA, paced these output-heavy GEMMs: eight warps, two per TMEM lane quarter, split the accumulator columns.
+        const int e = warp - 2;
+        const int q = warp & 3;    // TMEM lane quarter this warp may read (warps 2..9 cover every quarter twice)
+        const int chalf = e >> 2;  // this warp takes the 16-column chunks c0 = 16*chalf, +32, ...
+        float* stg = staging + e * 32 * STG_LD;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -177,106 +182,105 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             tc_fence_after();
             const uint32_t t_base = tmem_base + acc * Cfg::ACC_COLS + (uint32_t(q * 32) << 16);
             const int row0 = mt * BM + q * 32;
+            bool released = false;
 #pragma unroll
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                constexpr int dummy = 0;
-                (void)dummy;
-                const int width = (BN - c0) >= 32 ? 32 : 16;
-                uint32_t v[32];
-                {
-                    uint32_t(&v0)[16] = *reinterpret_cast<uint32_t(*)[16]>(&v[0]);
-                    tmem_ld_x16(t_base + c0, v0);
-                    if (width == 32) {
-                        uint32_t(&v1)[16] = *reinterpret_cast<uint32_t(*)[16]>(&v[16]);
-                        tmem_ld_x16(t_base + c0 + 16, v1);
-                    }
-                }
+            for (int c0 = 0; c0 < BN; c0 += 16) {
+                if (((c0 >> 4) & 1) != chalf) continue;
+                uint32_t v[16];
+                tmem_ld_x16(t_base + c0, v);
                 tmem_ld_wait();
                 if (c0 + 32 >= BN) {
-                    // last TMEM read of this accumulator: hand it back to the MMA warp early
+                    // last TMEM read of this accumulator by this warp: hand it back to the MMA warp early
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                    released = true;
                 }
                 // registers (thread = row) -> padded smem
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    if (j * 4 < width) {
-                        float4 f = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                               __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-                        *reinterpret_cast<float4*>(&stg[lane * STG_LD + 4 * j]) = f;
+                for (int j = 0; j < 4; ++j)
+                    *reinterpret_cast<float4*>(&stg[lane * STG_LD + 4 * j]) =
+                        make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                    __uint_as_float(v[4 * j + 3]));
+                __syncwarp();
+                // smem -> global, row-contiguous: 4 lanes cover one 64-byte row segment, 8 rows per pass
+                const int rsub = lane >> 2;
+                const int c4 = lane & 3;
+                const int gcol = nt * BN + c0 + c4 * 4;  // column within the group's N
+                float4 aux[4];
+                if (EPI == MTN_EPI_MASK) {  // issue the four mix_w loads together (they were the epilogue's critical path)
+#pragma unroll
+                    for (int it = 0; it < 4; ++it) {
+                        const int grow = row0 + it * 8 + rsub;
+                        aux[it] = grow < p.M ? *reinterpret_cast<const float4*>(p.aux + size_t(grow) * p.ld_aux +
+                                                                               (gcol % p.epi_param))
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
                 }
-                __syncwarp();
-                // smem -> global, row-contiguous: (width/4) lanes cover one row segment
-                const int lanes_per_row = width / 4;           // 8 or 4
-                const int rows_per_it = 32 / lanes_per_row;    // 4 or 8
-                const int rsub = lane / lanes_per_row;
-                const int c4 = lane % lanes_per_row;
 #pragma unroll
-                for (int it = 0; it < 8; ++it) {
-                    if (it * rows_per_it < 32) {
-                        const int rr = it * rows_per_it + rsub;
-                        const int grow = row0 + rr;
-                        const int gcol = nt * BN + c0 + c4 * 4;  // column within the group's N
-                        float4 f = *reinterpret_cast<const float4*>(&stg[rr * STG_LD + c4 * 4]);
-                        if (grow < p.M) {
-                            if (EPI == MTN_EPI_INPROJ) {
-                                if (gcol >= p.epi_param) {
-                                    f.x = silu_f(f.x);
-                                    f.y = silu_f(f.y);
-                                    f.z = silu_f(f.z);
-                                    f.w = silu_f(f.w);
-                                }
-                            } else if (EPI == MTN_EPI_RELU) {
-                                f.x = fmaxf(f.x, 0.f);
-                                f.y = fmaxf(f.y, 0.f);
-                                f.z = fmaxf(f.z, 0.f);
-                                f.w = fmaxf(f.w, 0.f);
-                            } else if (EPI == MTN_EPI_MASK) {
-                                const float4 a = *reinterpret_cast<const float4*>(
-                                    p.aux + size_t(grow) * p.ld_aux + (gcol % p.epi_param));
-                                f.x = fmaxf(f.x, 0.f) * a.x;
-                                f.y = fmaxf(f.y, 0.f) * a.y;
-                                f.z = fmaxf(f.z, 0.f) * a.z;
-                                f.w = fmaxf(f.w, 0.f) * a.w;
+                for (int it = 0; it < 4; ++it) {
+                    const int rr = it * 8 + rsub;
+                    const int grow = row0 + rr;
+                    float4 f = *reinterpret_cast<const float4*>(&stg[rr * STG_LD + c4 * 4]);
+                    if (grow < p.M) {
+                        if (EPI == MTN_EPI_INPROJ) {
+                            if (gcol >= p.epi_param) {
+                                f.x = silu_f(f.x);
+                                f.y = silu_f(f.y);
+                                f.z = silu_f(f.z);
+                                f.w = silu_f(f.w);
                             }
-                            if (EPI == MTN_EPI_XPROJ) {
-                                // dt columns also go out as hi | lo bf16 planes: the B operand of the scan's dt_proj MMA
-                                if (gcol < p.epi_param) {
-                                    __nv_bfloat16* drow = reinterpret_cast<__nv_bfloat16*>(const_cast<float*>(p.aux)) +
-                                                          (size_t(grow) * p.groups + g) * 2 * p.epi_param + gcol;
-                                    __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
-                                    split_bf16(f.x, h0, l0);
-                                    split_bf16(f.y, h1, l1);
-                                    split_bf16(f.z, h2, l2);
-                                    split_bf16(f.w, h3, l3);
-                                    __nv_bfloat162 a = __halves2bfloat162(h0, h1), b = __halves2bfloat162(h2, h3);
-                                    __nv_bfloat162 c = __halves2bfloat162(l0, l1), d = __halves2bfloat162(l2, l3);
-                                    uint2 ph, pl;
-                                    ph.x = *reinterpret_cast<uint32_t*>(&a);
-                                    ph.y = *reinterpret_cast<uint32_t*>(&b);
-                                    pl.x = *reinterpret_cast<uint32_t*>(&c);
-                                    pl.y = *reinterpret_cast<uint32_t*>(&d);
-                                    *reinterpret_cast<uint2*>(drow) = ph;
-                                    *reinterpret_cast<uint2*>(drow + p.epi_param) = pl;
-                                }
+                        } else if (EPI == MTN_EPI_RELU) {
+                            f.x = fmaxf(f.x, 0.f);
+                            f.y = fmaxf(f.y, 0.f);
+                            f.z = fmaxf(f.z, 0.f);
+                            f.w = fmaxf(f.w, 0.f);
+                        } else if (EPI == MTN_EPI_MASK) {
+                            f.x = fmaxf(f.x, 0.f) * aux[it].x;
+                            f.y = fmaxf(f.y, 0.f) * aux[it].y;
+                            f.z = fmaxf(f.z, 0.f) * aux[it].z;
+                            f.w = fmaxf(f.w, 0.f) * aux[it].w;
+                        }
+                        if (EPI == MTN_EPI_XPROJ) {
+                            // dt columns also go out as hi | lo bf16 planes: the B operand of the scan's dt_proj MMA
+                            if (gcol < p.epi_param) {
+                                __nv_bfloat16* drow = reinterpret_cast<__nv_bfloat16*>(const_cast<float*>(p.aux)) +
+                                                      (size_t(grow) * p.groups + g) * 2 * p.epi_param + gcol;
+                                __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
+                                split_bf16(f.x, h0, l0);
+                                split_bf16(f.y, h1, l1);
+                                split_bf16(f.z, h2, l2);
+                                split_bf16(f.w, h3, l3);
+                                __nv_bfloat162 a2 = __halves2bfloat162(h0, h1), b2 = __halves2bfloat162(h2, h3);
+                                __nv_bfloat162 c2 = __halves2bfloat162(l0, l1), d2 = __halves2bfloat162(l2, l3);
+                                uint2 ph, pl;
+                                ph.x = *reinterpret_cast<uint32_t*>(&a2);
+                                ph.y = *reinterpret_cast<uint32_t*>(&b2);
+                                pl.x = *reinterpret_cast<uint32_t*>(&c2);
+                                pl.y = *reinterpret_cast<uint32_t*>(&d2);
+                                *reinterpret_cast<uint2*>(drow) = ph;
+                                *reinterpret_cast<uint2*>(drow + p.epi_param) = pl;
                             }
-                            const size_t off = size_t(grow) * p.ldo + size_t(g) * p.out_group_stride + gcol;
-                            if (OUT_BF16) {
-                                __nv_bfloat162 lo2 = __floats2bfloat162_rn(f.x, f.y);
-                                __nv_bfloat162 hi2 = __floats2bfloat162_rn(f.z, f.w);
-                                uint2 pk;
-                                pk.x = *reinterpret_cast<uint32_t*>(&lo2);
-                                pk.y = *reinterpret_cast<uint32_t*>(&hi2);
-                                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off) = pk;
-                            } else {
-                                *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off) = f;
-                            }
+                        }
+                        const size_t off = size_t(grow) * p.ldo + size_t(g) * p.out_group_stride + gcol;
+                        if (OUT_BF16) {
+                            __nv_bfloat162 lo2 = __floats2bfloat162_rn(f.x, f.y);
+                            __nv_bfloat162 hi2 = __floats2bfloat162_rn(f.z, f.w);
+                            uint2 pk;
+                            pk.x = *reinterpret_cast<uint32_t*>(&lo2);
+                            pk.y = *reinterpret_cast<uint32_t*>(&hi2);
+                            *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off) = pk;
+                        } else {
+                            *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off) = f;
                         }
                     }
                 }
                 __syncwarp();
+            }
+            if (!released) {  // a warp with no chunk of its own (cannot happen for BN >= 32) still has to release
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
             }
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
@@ -336,7 +340,7 @@ static int launch_gemm(const mtn_gemm_args* a, cudaStream_t stream) {
     int total = p.tiles_m * p.tiles_n * p.groups;
     int cap = a->max_ctas > 0 ? a->max_ctas : num_sms();
     int grid = total < cap ? total : cap;
-    kern<<<grid, 192, Cfg::SMEM_BYTES, stream>>>(mapA, mapB, p);
+    kern<<<grid, 64 + 32 * EPI_WARPS, Cfg::SMEM_BYTES, stream>>>(mapA, mapB, p);
     MTN_CUDA_LAUNCH_CHECK("gemm");
     return MTN_OK;
 }

@@ -58,9 +58,10 @@ def test_gemm_store(M, N, K, P, groups):
         assert rel_max(out.cpu(), ref32) < 1e-4
 
 
-def test_gemm_epilogues():
+@pytest.mark.parametrize("M", [391, 2000], ids=["streamed-weights", "weight-resident"])
+def test_gemm_epilogues(M):
     g = torch.Generator().manual_seed(7)
-    M, K, di, enc = 391, 128, 128, 128
+    K, di, enc = 128, 128, 128
     a = torch.randn(M, K, generator=g)
     w = torch.randn(2 * di, K, generator=g) / K ** 0.5
     ap, wp = ops.split_planes(a.to(DEV), 2), ops.split_planes(w.to(DEV), 2)
@@ -74,7 +75,7 @@ def test_gemm_epilogues():
     assert outb.dtype == torch.bfloat16 and rel_mixed(outb.float().cpu(), exp) < 2 ** -8
     # relu
     out = ops.gemm(ap, wp, M, 2 * di, K, epilogue=_lib.EPI_RELU)
-    assert rel_max(out.cpu(), ref.clamp(min=0)) < 2e-5
+    assert rel_max(out.cpu(), ref.clamp(min=0)) < 5e-5
     # relu(mask) * mix_w, speaker-major columns
     mixw = torch.rand(M, enc, generator=g)
     out = ops.gemm(ap, wp, M, 2 * enc, K, epilogue=_lib.EPI_MASK, epi_param=enc, aux=mixw.to(DEV))
