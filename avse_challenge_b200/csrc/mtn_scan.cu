@@ -45,7 +45,32 @@ struct ScanParams {
     int L_last;  // valid length of the last sequence of the batch (== L when not ragged)
     int dir0;   // first direction of this launch
     int ndirs;  // 1 or 2
+    const void* z;  // gate column block base (pair mapping reads it straight from global)
+    int ldz;
 };
+
+static ScanParams make_scan_params(const mtn_scan_args* a) {
+    ScanParams p;
+    p.w_dt = a->w_dt;
+    p.dt_bias = a->dt_bias;
+    p.A2 = a->A2;
+    p.Dskip = a->Dskip;
+    p.y = reinterpret_cast<__nv_bfloat16*>(a->y);
+    p.h_in = a->h_in;
+    p.h_out = a->h_out;
+    p.sum_delta = a->sum_delta;
+    p.L_last = a->L_last > 0 ? a->L_last : a->L;
+    p.batch = a->batch;
+    p.L = a->L;
+    p.di = a->di;
+    p.n_dbl = a->n_dbl;
+    p.z_col0 = a->z_col0;
+    p.dir0 = (a->dir_mask & 1) ? 0 : 1;
+    p.ndirs = (a->dir_mask == 3) ? 2 : 1;
+    p.z = a->z;
+    p.ldz = a->ldz;
+    return p;
+}
 
 template <int P, int NDBL, typename ZT, int CH>
 struct ScanSmem {
@@ -523,24 +548,8 @@ static int launch_scan(const mtn_scan_args* a, cudaStream_t stream) {
         if (!encode_tmap(&mapD, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, a->dbl, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE))
             return MTN_ECUDA;
     }
-    ScanParams p;
-    p.w_dt = a->w_dt;
-    p.dt_bias = a->dt_bias;
-    p.A2 = a->A2;
-    p.Dskip = a->Dskip;
-    p.y = reinterpret_cast<__nv_bfloat16*>(a->y);
-    p.h_in = a->h_in;
-    p.h_out = a->h_out;
-    p.sum_delta = a->sum_delta;
-    p.L_last = a->L_last > 0 ? a->L_last : a->L;
-    p.batch = a->batch;
-    p.L = a->L;
-    p.di = a->di;
-    p.n_dbl = a->n_dbl;
-    p.z_col0 = a->z_col0;
-    p.dir0 = (a->dir_mask & 1) ? 0 : 1;
-    const int ndirs = (a->dir_mask == 3) ? 2 : 1;
-    p.ndirs = ndirs;
+    ScanParams p = make_scan_params(a);
+    const int ndirs = p.ndirs;
     auto kern = scan_kernel<P, R, NDBL, ZT, CH, KP, WY>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -1017,24 +1026,8 @@ static int launch_scan_tc(const mtn_scan_args* a, cudaStream_t stream) {
         if (!encode_tmap(&mapT, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->dtp, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE))
             return MTN_ECUDA;
     }
-    ScanParams p;
-    p.w_dt = a->w_dt;
-    p.dt_bias = a->dt_bias;
-    p.A2 = a->A2;
-    p.Dskip = a->Dskip;
-    p.y = reinterpret_cast<__nv_bfloat16*>(a->y);
-    p.h_in = a->h_in;
-    p.h_out = a->h_out;
-    p.sum_delta = a->sum_delta;
-    p.L_last = a->L_last > 0 ? a->L_last : a->L;
-    p.batch = a->batch;
-    p.L = a->L;
-    p.di = a->di;
-    p.n_dbl = a->n_dbl;
-    p.z_col0 = a->z_col0;
-    p.dir0 = (a->dir_mask & 1) ? 0 : 1;
-    const int ndirs = (a->dir_mask == 3) ? 2 : 1;
-    p.ndirs = ndirs;
+    ScanParams p = make_scan_params(a);
+    const int ndirs = p.ndirs;
     auto kern = scan_kernel_tc<P, R, NDBL, ZT, WY>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -1052,17 +1045,40 @@ static int launch_scan_tc(const mtn_scan_args* a, cudaStream_t stream) {
 }
 
 
+}  // namespace mtn
+#include "mtn_scan_pair.cuh"
+namespace mtn {
+
+// every measured shape except the widest fp32 one (L hparams, R = 32, two planes: the split mapping with tensor-core dt_proj wins by 4 %)
+static bool pair_wins(const mtn_scan_args* a) { return !(a->R > 16 && a->planes == 2); }
+
 template <int P, int R, int NDBL, typename ZT>
 static int dispatch_scan_variant(const mtn_scan_args* a, cudaStream_t s) {
     int variant = 0;
     if (const char* v = getenv("MTN_SCAN_VARIANT")) variant = atoi(v);
-    if (a->dtp && variant == 0) {  // dt_proj on the tensor cores
+#ifdef MTN_SCAN_DEV   // experiment variants of the pair mapping (timing-only ablations give WRONG results)
+    if (variant == 15) return launch_scan_pair<P, R, NDBL, ZT, true, false, 1>(a, s);
+    if (variant == 25) return launch_scan_pair<P, R, NDBL, ZT, true, false, 2>(a, s);
+    if (variant == 35) return launch_scan_pair<P, R, NDBL, ZT, true, false, 3>(a, s);
+    if (variant == 75) return launch_scan_pair<P, R, NDBL, ZT, true, false, 7>(a, s);
+    if (variant == 85) return launch_scan_pair<P, R, NDBL, ZT, true, false, 8>(a, s);
+    if (variant == 7 && a->dtp && a->y) return launch_scan_pair<P, R, NDBL, ZT, true, true>(a, s);  // tensor-core dt_proj
+#endif
+    // Recurrence / helper warp pairs (mtn_scan_pair.cuh).  Measured on B200 (tools/scan_bench.py): faster
+    // than the split mapping for full passes; the summary pass (no y: nothing for the helper to take over) stays on the
+    // split mapping.  variant 5 forces it, variant 2/3 force the split mapping.
+    const bool pair_default = variant == 0 && a->y != nullptr && pair_wins(a);
+    if (variant == 5 || pair_default) {
+        if (!a->y) return launch_scan_pair<P, R, NDBL, ZT, false, false>(a, s);
+        return launch_scan_pair<P, R, NDBL, ZT, true, false>(a, s);
+    }
+    if (a->dtp && (variant == 0 || variant == 3)) {  // split mapping, dt_proj on the tensor cores
         if (!a->y) return launch_scan_tc<P, R, NDBL, ZT, false>(a, s);
         return launch_scan_tc<P, R, NDBL, ZT, true>(a, s);
     }
     // 128-channel CTAs.  (Measured alternatives that did NOT pay, see DESIGN.md 4.1: 32-channel CTAs to even out the
     // SM load at small grids; four lanes per channel; direction-paired CTAs.)
-    if (variant == 0 || variant == 2) {
+    if (variant == 0 || variant == 2 || variant == 3) {
         if (!a->y) return launch_scan<P, R, NDBL, ZT, 128, 0, false>(a, s);
         return launch_scan<P, R, NDBL, ZT, 128, 0, true>(a, s);
     }
@@ -1086,12 +1102,18 @@ static int dispatch_scan_variant(const mtn_scan_args* a, cudaStream_t s) {
 
 template <int P, typename ZT>
 static int dispatch_scan_r(const mtn_scan_args* a, cudaStream_t s) {
+#ifdef MTN_SCAN_DEV  // fast-iteration build: BASELINE config 2 instantiation only
+    if (a->R == 16 && a->n_dbl == 48) return dispatch_scan_variant<P, 16, 48, ZT>(a, s);
+    set_error("scan: MTN_SCAN_DEV build");
+    return MTN_EINVAL;
+#else
     if (a->R == 4 && a->n_dbl == 48) return dispatch_scan_variant<P, 4, 48, ZT>(a, s);
     if (a->R == 8 && a->n_dbl == 48) return dispatch_scan_variant<P, 8, 48, ZT>(a, s);
     if (a->R == 16 && a->n_dbl == 48) return dispatch_scan_variant<P, 16, 48, ZT>(a, s);
     if (a->R == 32 && a->n_dbl == 64) return dispatch_scan_variant<P, 32, 64, ZT>(a, s);
     set_error("scan: unsupported dt_rank R=%d / n_dbl=%d (supported: 4|8|16 with 48, 32 with 64)", a->R, a->n_dbl);
     return MTN_EINVAL;
+#endif
 }
 
 }  // namespace mtn
@@ -1117,8 +1139,10 @@ extern "C" int mtn_scan_fwd(const mtn_scan_args* a, mtn_stream_t stream) {
     MTN_REQUIRE(!a->dtp || (reinterpret_cast<uintptr_t>(a->dtp) & 15) == 0, "scan: dtp must be 16-byte aligned");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     if (a->planes == 2 && !a->z_bf16) return dispatch_scan_r<2, float>(a, s);
+#ifndef MTN_SCAN_DEV
     if (a->planes == 1 && a->z_bf16) return dispatch_scan_r<1, __nv_bfloat16>(a, s);
     if (a->planes == 1 && !a->z_bf16) return dispatch_scan_r<1, float>(a, s);
+#endif
     set_error("scan: unsupported planes=%d z_bf16=%d", a->planes, a->z_bf16);
     return MTN_EINVAL;
 }

@@ -37,8 +37,8 @@ s_io = 4 if P == 2 else 2
 alg = 2 * (M * (4 * di + 32) * s_io + (di * 16 + 2 * di) * 4)
 y_ref = None
 for var in a.variants.split(","):
-    run = run_sum if var == "S" else run_full          # "S" = summary pass (no y), default variant
-    os.environ["MTN_SCAN_VARIANT"] = "0" if var == "S" else var
+    run = run_sum if var.startswith("S") else run_full  # "S" / "S<v>" = summary pass (no y) of variant 0 / <v>
+    os.environ["MTN_SCAN_VARIANT"] = (var[1:] or "0") if var.startswith("S") else var
     y.zero_()
     for _ in range(3): run()
     torch.cuda.synchronize()
