@@ -336,7 +336,7 @@ def run_b200_arm(a):
                     "h2d_bytes_per_step": a.batch * T * 4, "d2h_bytes_per_step": a.batch * T * hp.n_spk * 4,
                     "ms_per_step": ms_e2e / a.steps},
             "gpu_launches": a.steps * sum(v["launches"] for v in prof.values()) + a.steps,  # +1: decoder = 2 kernels
-            "roofline": {"kernel": "mtn::scan_kernel (both directions per launch)", "bound": "hbm",
+            "roofline": {"kernel": "mtn::scan_kernel_pair / scan_kernel (selective scan, both directions per launch)", "bound": "hbm",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": peak_src, "traffic": traffic, "algorithmic_bytes_per_launch": alg,
                          "ms_per_launch": scan_ms, "launches_per_step": prof["scan"]["launches"],
