@@ -11,10 +11,10 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_void_p
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmtn_b200.so")
 
-EPI_STORE, EPI_INPROJ, EPI_MASK, EPI_RELU, EPI_XPROJ = 0, 1, 2, 3, 4
+EPI_STORE, EPI_INPROJ, EPI_MASK, EPI_RELU, EPI_XPROJ, EPI_RESADD = 0, 1, 2, 3, 4, 5
 
 EXPORTS = [
-    "mtn_encoder_cln_fwd", "mtn_gemm_fwd", "mtn_add_rmsnorm_fwd", "mtn_conv_silu_fwd", "mtn_conv_silu_halo_fwd",
+    "mtn_encoder_cln_fwd", "mtn_gemm_fwd", "mtn_gemm_rowsum_parts", "mtn_add_rmsnorm_fwd", "mtn_conv_silu_fwd", "mtn_conv_silu_halo_fwd",
     "mtn_scan_fwd", "mtn_fold_states_fwd",
     "mtn_decoder_fwd", "mtn_cln_fwd", "mtn_split_planes", "mtn_last_error_string", "mtn_abi_version",
 ]
@@ -27,6 +27,8 @@ class GemmArgs(Structure):
         ("lda", c_int), ("ldo", c_int), ("ld_aux", c_int),
         ("planes", c_int), ("groups", c_int), ("out_group_stride", c_int),
         ("epilogue", c_int), ("epi_param", c_int), ("out_bf16", c_int), ("max_ctas", c_int),
+        ("out2", c_void_p), ("rowsum", c_void_p), ("ldo2", c_int), ("a2_rows", c_int),
+        ("rowsq", c_void_p), ("rowsq_scale", c_float), ("rowsq_eps", c_float), ("rowsq_parts", c_int),
     ]
 
 
@@ -62,6 +64,7 @@ def load():
     lib.mtn_abi_version.restype = c_int
     lib.mtn_encoder_cln_fwd.argtypes = [c_void_p, c_int] + [c_void_p] * 5 + [c_int] * 5 + [c_float, c_void_p]
     lib.mtn_gemm_fwd.argtypes = [POINTER(GemmArgs), c_void_p]
+    lib.mtn_gemm_rowsum_parts.argtypes = [c_int]
     lib.mtn_add_rmsnorm_fwd.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_float,
                                         c_void_p]
     lib.mtn_conv_silu_fwd.argtypes = [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,

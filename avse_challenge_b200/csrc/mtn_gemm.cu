@@ -34,6 +34,13 @@ struct GemmParams {
     int groups, out_group_stride;
     int epi_param;
     int tiles_m, tiles_n;
+    __nv_bfloat16* out2;
+    float* rowsum;
+    const float* rowsq;
+    int ldo2;
+    size_t plane2;   // elements between the planes of out2
+    float rowsq_scale, rowsq_eps;
+    int rowsq_parts;
 };
 
 template <int P, int BN>
@@ -173,6 +180,31 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         float* stg = staging + e * 32 * STG_LD;
         int acc = 0;
         uint32_t acc_phase = 0;
+        float ss_next[4] = {0.f, 0.f, 0.f, 0.f};
+        auto load_ss = [&](int tile2) {  // sum of the partial-sum planes (fixed order) for this lane's 4 rows of tile2
+            if (tile2 >= total_tiles) return;
+            const int r2 = tile2 % tiles_per_group;
+            const int rowb = (r2 / p.tiles_n) * BM + q * 32 + (lane >> 2);
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                const int grow = rowb + it * 8;
+                float acc2 = 0.f;
+                if (grow < p.M)
+                    for (int k = 0; k < p.rowsq_parts; ++k) acc2 += p.rowsq[size_t(k) * p.M + grow];
+                ss_next[it] = acc2;
+            }
+        };
+        auto load_res = [&](float4(&dst)[4], int row0_, int gcol0) {  // old residual, 4 row groups x this lane's float4
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                const int grow = row0_ + it * 8 + (lane >> 2);
+                dst[it] = (p.epi_param && grow < p.M)
+                              ? *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.out) +
+                                                                 size_t(grow) * p.ldo + gcol0 + (lane & 3) * 4)
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        if (p.rowsq) load_ss(blockIdx.x);
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int g = tile / tiles_per_group;
             const int r = tile - g * tiles_per_group;
@@ -183,6 +215,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             const uint32_t t_base = tmem_base + acc * Cfg::ACC_COLS + (uint32_t(q * 32) << 16);
             const int row0 = mt * BM + q * 32;
             bool released = false;
+            float sqacc[4] = {0.f, 0.f, 0.f, 0.f};  // RESADD: sum of squares of this lane's 4 rows over the warp's chunks
+            // folded RMSNorm: one scale per row.  The partial sums of the NEXT tile's rows are requested now and turned
+            // into rstd when that tile starts, so their global latency never sits on the epilogue's critical path.
+            float rstd[4] = {1.f, 1.f, 1.f, 1.f};
+            if (p.rowsq) {
+#pragma unroll
+                for (int it = 0; it < 4; ++it) rstd[it] = rsqrtf(fmaf(ss_next[it], p.rowsq_scale, p.rowsq_eps));
+                load_ss(tile + gridDim.x);
+            }
+            float4 auxn[4];  // RESADD: residual rows of the warp's next chunk, requested one chunk ahead
+            if (EPI == MTN_EPI_RESADD) load_res(auxn, row0, nt * BN + 16 * chalf);
 #pragma unroll
             for (int c0 = 0; c0 < BN; c0 += 16) {
                 if (((c0 >> 4) & 1) != chalf) continue;
@@ -208,6 +251,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                 const int c4 = lane & 3;
                 const int gcol = nt * BN + c0 + c4 * 4;  // column within the group's N
                 float4 aux[4];
+                if (EPI == MTN_EPI_RESADD) {
+#pragma unroll
+                    for (int it = 0; it < 4; ++it) aux[it] = auxn[it];
+                    if (c0 + 32 < BN) load_res(auxn, row0, nt * BN + c0 + 32);
+                }
                 if (EPI == MTN_EPI_MASK) {  // issue the four mix_w loads together (they were the epilogue's critical path)
 #pragma unroll
                     for (int it = 0; it < 4; ++it) {
@@ -223,6 +271,45 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                     const int grow = row0 + rr;
                     float4 f = *reinterpret_cast<const float4*>(&stg[rr * STG_LD + c4 * 4]);
                     if (grow < p.M) {
+                        if (p.rowsq) {  // RMSNorm of the A operand's rows, applied after the contraction
+                            f.x *= rstd[it];
+                            f.y *= rstd[it];
+                            f.z *= rstd[it];
+                            f.w *= rstd[it];
+                        }
+                        if (EPI == MTN_EPI_RESADD) {
+                            f.x += aux[it].x;
+                            f.y += aux[it].y;
+                            f.z += aux[it].z;
+                            f.w += aux[it].w;
+                            // the planes of the updated residual: A operand of the next in_proj / mask GEMM
+                            __nv_bfloat16* pr = p.out2 + size_t(grow) * p.ldo2 + gcol;
+                            __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
+                            if (P == 2) {
+                                split_bf16(f.x, h0, l0);
+                                split_bf16(f.y, h1, l1);
+                                split_bf16(f.z, h2, l2);
+                                split_bf16(f.w, h3, l3);
+                            } else {
+                                h0 = __float2bfloat16_rn(f.x);
+                                h1 = __float2bfloat16_rn(f.y);
+                                h2 = __float2bfloat16_rn(f.z);
+                                h3 = __float2bfloat16_rn(f.w);
+                            }
+                            __nv_bfloat162 a2 = __halves2bfloat162(h0, h1), b2 = __halves2bfloat162(h2, h3);
+                            uint2 ph;
+                            ph.x = *reinterpret_cast<uint32_t*>(&a2);
+                            ph.y = *reinterpret_cast<uint32_t*>(&b2);
+                            *reinterpret_cast<uint2*>(pr) = ph;
+                            if (P == 2) {
+                                __nv_bfloat162 c2 = __halves2bfloat162(l0, l1), d2 = __halves2bfloat162(l2, l3);
+                                uint2 pl;
+                                pl.x = *reinterpret_cast<uint32_t*>(&c2);
+                                pl.y = *reinterpret_cast<uint32_t*>(&d2);
+                                *reinterpret_cast<uint2*>(pr + p.plane2) = pl;
+                            }
+                            sqacc[it] = fmaf(f.x, f.x, fmaf(f.y, f.y, fmaf(f.z, f.z, fmaf(f.w, f.w, sqacc[it]))));
+                        }
                         if (EPI == MTN_EPI_INPROJ) {
                             if (gcol >= p.epi_param) {
                                 f.x = silu_f(f.x);
@@ -277,6 +364,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                 }
                 __syncwarp();
             }
+            if (EPI == MTN_EPI_RESADD) {
+                // row sums of squares: 4 lanes share a row; every (N tile, warp half) owns one partial-sum plane, so the
+                // sums are plain stores (nothing to zero, bit-reproducible); the consumer adds the planes in order
+#pragma unroll
+                for (int it = 0; it < 4; ++it) {
+                    float sq = sqacc[it];
+                    sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+                    sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+                    const int grow = row0 + it * 8 + (lane >> 2);
+                    if ((lane & 3) == 0 && grow < p.M) p.rowsum[size_t(nt * 2 + chalf) * p.M + grow] = sq;
+                }
+            }
             if (!released) {  // a warp with no chunk of its own (cannot happen for BN >= 32) still has to release
                 tc_fence_before();
                 __syncwarp();
@@ -325,6 +424,14 @@ static int launch_gemm(const mtn_gemm_args* a, cudaStream_t stream) {
     p.groups = a->groups;
     p.out_group_stride = a->out_group_stride;
     p.epi_param = a->epi_param;
+    p.out2 = reinterpret_cast<__nv_bfloat16*>(a->out2);
+    p.rowsum = a->rowsum;
+    p.rowsq = a->rowsq;
+    p.ldo2 = a->ldo2;
+    p.plane2 = size_t(a->a2_rows) * a->ldo2;
+    p.rowsq_scale = a->rowsq_scale;
+    p.rowsq_eps = a->rowsq_eps;
+    p.rowsq_parts = a->rowsq_parts;
     p.tiles_m = (a->M + BM - 1) / BM;
     p.tiles_n = a->N / BN;
     auto kern = gemm_tcgen05_kernel<P, BN, EPI, OUT_BF16>;
@@ -351,7 +458,11 @@ static int dispatch_epi(const mtn_gemm_args* a, cudaStream_t s) {
     if (BN <= 64) {
         if (a->epilogue == MTN_EPI_XPROJ && !a->out_bf16) return launch_gemm<P, BN, MTN_EPI_XPROJ, false>(a, s);
     }
+    if (BN == 64) {
+        if (a->epilogue == MTN_EPI_RESADD && !a->out_bf16) return launch_gemm<P, BN, MTN_EPI_RESADD, false>(a, s);
+    }
     if (BN >= 128) {
+        if (a->epilogue == MTN_EPI_RESADD && !a->out_bf16) return launch_gemm<P, BN, MTN_EPI_RESADD, false>(a, s);
         if (a->epilogue == MTN_EPI_INPROJ && !a->out_bf16) return launch_gemm<P, BN, MTN_EPI_INPROJ, false>(a, s);
         if (a->epilogue == MTN_EPI_INPROJ && a->out_bf16) return launch_gemm<P, BN, MTN_EPI_INPROJ, true>(a, s);
         if (a->epilogue == MTN_EPI_MASK && !a->out_bf16) return launch_gemm<P, BN, MTN_EPI_MASK, false>(a, s);
@@ -360,6 +471,8 @@ static int dispatch_epi(const mtn_gemm_args* a, cudaStream_t s) {
     set_error("gemm: unsupported epilogue %d / out_bf16 %d for N tile %d", a->epilogue, a->out_bf16, BN);
     return MTN_EINVAL;
 }
+
+static int tile_n_for(int N) { return N % 256 == 0 ? 256 : N % 128 == 0 ? 128 : N; }
 
 template <int P>
 static int dispatch_bn(const mtn_gemm_args* a, cudaStream_t s) {
@@ -373,6 +486,8 @@ static int dispatch_bn(const mtn_gemm_args* a, cudaStream_t s) {
 }
 
 }  // namespace mtn
+
+extern "C" int mtn_gemm_rowsum_parts(int N) { return 2 * (N / mtn::tile_n_for(N)); }
 
 extern "C" int mtn_gemm_fwd(const mtn_gemm_args* a, mtn_stream_t stream) {
     using namespace mtn;
@@ -390,6 +505,11 @@ extern "C" int mtn_gemm_fwd(const mtn_gemm_args* a, mtn_stream_t stream) {
         MTN_REQUIRE(a->aux && a->epi_param > 0 && a->epi_param % 4 == 0 && a->ld_aux % 4 == 0,
                     "gemm: mask epilogue needs aux / enc_dim");
     if (a->epilogue == MTN_EPI_INPROJ) MTN_REQUIRE(a->epi_param % 4 == 0, "gemm: inproj split must be a multiple of 4");
+    if (a->rowsq) MTN_REQUIRE(a->rowsq_parts >= 1 && a->rowsq_parts <= 64, "gemm: rowsq_parts=%d", a->rowsq_parts);
+    if (a->epilogue == MTN_EPI_RESADD)
+        MTN_REQUIRE(a->out2 && a->rowsum && !a->out_bf16 && a->groups == 1 && a->ldo2 % 4 == 0 && a->a2_rows >= a->M &&
+                        (reinterpret_cast<uintptr_t>(a->out2) & 7) == 0,
+                    "gemm: resadd epilogue needs fp32 out, out2 planes (8-byte aligned, ldo2 %% 4 == 0, a2_rows >= M), rowsum");
     if (a->epilogue == MTN_EPI_XPROJ)
         MTN_REQUIRE(a->aux && (a->epi_param == 16 || a->epi_param == 32) && a->epi_param <= a->N &&
                         (reinterpret_cast<uintptr_t>(a->aux) & 15) == 0,

@@ -13,6 +13,12 @@ Per layer (reference call stack SURVEY.md 3.1):
     gemm(x_proj)  [dt|B|C]_f, [dt|B|C]_b (2 groups)             (ssi.py:186)
     scan          dt_proj + softplus + recurrence + D-skip + gate, x0.5, both directions (ssi.py:187,218-220)
     gemm(out_proj) h = [y_f | y_b] @ [W_out | W_out]^T          (bimamba.py:253)
+Optional plan without the add_rmsnorm kernel: RMSNorm(res) * g = rstd[row] * res * g[col], so g is folded
+into the consuming weight at load time, the residual add + sum of squares live in the producer GEMM's epilogue
+(MTN_EPI_RESADD) and rstd scales the consumer GEMM's accumulator rows (``fuse_norm=True``).  Measured on B200 at BASELINE
+config 2 this saves the 1.48 ms/forward of ``add_rmsnorm`` but costs the same again in the two epilogue-bound GEMMs
+(in_proj 3.2 -> 4.1 ms, out_proj 2.65 -> 3.2 ms per forward), 27.0-27.4 ms either way, so the default keeps the separate
+``add_rmsnorm`` kernel (``fuse_norm=False``; also what the sequence-parallel driver uses).
 """
 from __future__ import annotations
 
@@ -43,12 +49,14 @@ class PackedWeights:
         self.w_bot = ops.split_planes(f32(m["bottleneck_conv1x1.conv.weight"]).reshape(D, N), P)
         self.w_mask = ops.split_planes(f32(m["mask_conv1x1.conv.weight"]).reshape(hp.n_spk * N, D), P)
         self.norm_f = f32(m["mamba_net.norm_f.weight"])
+        self.w_mask_g = ops.split_planes(f32(m["mask_conv1x1.conv.weight"]).reshape(hp.n_spk * N, D) * self.norm_f[None, :], P)
         self.layers = []
         for i in range(hp.n_mamba):
             p = f"mamba_net.layers.{i}."
             lw = {}
             lw["norm"] = f32(m[p + "norm.weight"])
             lw["w_in"] = ops.split_planes(f32(m[p + "mixer.in_proj.weight"]), P)            # [P, 2di, D]
+            lw["w_in_g"] = ops.split_planes(f32(m[p + "mixer.in_proj.weight"]) * lw["norm"][None, :], P)  # RMSNorm gain folded in
             lw["conv_w"] = torch.stack([f32(m[p + "mixer.conv1d.weight"]).reshape(di, hp.d_conv),
                                         f32(m[p + "mixer.conv1d_b.weight"]).reshape(di, hp.d_conv)]).contiguous()
             lw["conv_b"] = torch.stack([f32(m[p + "mixer.conv1d.bias"]), f32(m[p + "mixer.conv1d_b.bias"])]).contiguous()
@@ -92,6 +100,8 @@ class Workspace:
         self.sep = e((M, hp.n_spk * N), torch.float32)
         self.frames = e((M, hp.n_spk, 16), torch.float32)
         self.est = e((batch, T, hp.n_spk), torch.float32)
+        # partial sums of res^2 per token entering the next norm; two buffers alternate (a GEMM reads one, the next writes one)
+        self.rowsum = e((2, ops.rowsum_parts(D), M), torch.float32)
 
     def nbytes(self):
         return sum(t.numel() * t.element_size() for t in vars(self).values() if isinstance(t, torch.Tensor))
@@ -100,7 +110,8 @@ class Workspace:
 class SeparatorEngine:
     """mix [B, T] fp32 (CUDA) -> est_source [B, T, n_spk] fp32, all in hand-written sm_100a kernels."""
 
-    def __init__(self, hp: HParams, sds: dict, device="cuda", mode: str = "fp32", use_graph: bool = True):
+    def __init__(self, hp: HParams, sds: dict, device="cuda", mode: str = "fp32", use_graph: bool = True,
+                 fuse_norm: bool = False):
         if mode not in MODES:
             raise ValueError(f"mode must be one of {list(MODES)}")
         if not torch.cuda.is_available():
@@ -108,12 +119,14 @@ class SeparatorEngine:
         _lib.load()
         self.hp, self.mode, self.device = hp, mode, torch.device(device)
         self.use_graph = use_graph
+        self.fuse_norm = fuse_norm
         with torch.cuda.device(self.device):
             self.w = PackedWeights(hp, sds, self.device, mode)
         self._ws = {}
         self._graphs = {}
         self._prof = None
-        self.launches_per_forward = 2 + 1 + hp.n_mamba * 6 + 2 + 2  # enc, bottleneck, layers, norm_f+mask, decoder(2)
+        # enc, bottleneck, layers, (norm_f +) mask, decoder(2); fused: no norm kernels
+        self.launches_per_forward = (1 + 1 + hp.n_mamba * 5 + 1 + 2) if fuse_norm else (1 + 1 + hp.n_mamba * 6 + 2 + 2)
         # dt_proj inside the scan: tcgen05 MMA per 16-step tile, or R FMAs per (step, channel).  Measured on B200
         # (tools/scan_bench.py): the MMA form wins only where R is large and the FMA pipe is the
         # busier one (L hparams, fp32 mode: -6 %); elsewhere its shuffles / TMEM loads cost as much as the FMAs saved.
@@ -138,13 +151,11 @@ class SeparatorEngine:
         prof.append((name, e0, e1))
         return out
 
-    def _layer(self, ws: Workspace, lw: dict, first: bool, taps=None):
+    def _mixer_core(self, ws: Workspace, lw: dict):
+        """conv -> x_proj -> scan on ws.xz; leaves the gated scan output in ws.y."""
         hp, P = self.hp, self.w.P
-        D, di, R, nd, M = hp.d_model, hp.d_inner, hp.dt_rank, self.w.n_dbl, ws.M
+        di, R, nd, M = hp.d_inner, hp.dt_rank, self.w.n_dbl, ws.M
         op = self._op
-        op("add_rmsnorm", ops.add_rmsnorm, ws.h, ws.res, not first, lw["norm"], P, xn=ws.xn)
-        op("gemm_in_proj", ops.gemm, ws.xn, lw["w_in"], M, 2 * di, D, out=ws.xz, epilogue=_lib.EPI_INPROJ, epi_param=di,
-           out_bf16=ws.xz.dtype == torch.bfloat16)
         op("conv_silu", ops.conv_silu, ws.xz, lw["conv_w"], lw["conv_b"], ws.batch, ws.L, di, P, u=ws.u)
         if self.tc_dt:
             op("gemm_x_proj", ops.gemm, ws.u, lw["w_x"], M, nd, di, out=ws.dbl, groups=2, out_group_stride=nd,
@@ -153,11 +164,20 @@ class SeparatorEngine:
             op("gemm_x_proj", ops.gemm, ws.u, lw["w_x"], M, nd, di, out=ws.dbl, groups=2, out_group_stride=nd)
         op("scan", ops.scan, ws.u, ws.dbl, ws.xz, di, lw["w_dt"], lw["dt_bias"], lw["A2"], lw["D"], ws.batch, ws.L, di, R,
            y=ws.y, dtp=ws.dtp if self.tc_dt else None)
+
+    def _layer(self, ws: Workspace, lw: dict, first: bool, taps=None):
+        hp, P = self.hp, self.w.P
+        D, di, M = hp.d_model, hp.d_inner, ws.M
+        op = self._op
+        op("add_rmsnorm", ops.add_rmsnorm, ws.h, ws.res, not first, lw["norm"], P, xn=ws.xn)
+        op("gemm_in_proj", ops.gemm, ws.xn, lw["w_in"], M, 2 * di, D, out=ws.xz, epilogue=_lib.EPI_INPROJ, epi_param=di,
+           out_bf16=ws.xz.dtype == torch.bfloat16)
+        self._mixer_core(ws, lw)
         op("gemm_out_proj", ops.gemm, ws.y, lw["w_out"], M, D, 2 * di, out=ws.h)
         if taps is not None:
             taps.append(ws.h.clone())
 
-    def _run(self, ws: Workspace, taps=None):
+    def _run_unfused(self, ws: Workspace, taps=None):
         hp, w, P = self.hp, self.w, self.w.P
         N, D, M = hp.enc_dim, hp.d_model, ws.M
         op = self._op
@@ -168,6 +188,30 @@ class SeparatorEngine:
         op("add_rmsnorm", ops.add_rmsnorm, ws.h, ws.res, True, w.norm_f, P, xn=ws.xn)
         op("gemm_mask", ops.gemm, ws.xn, w.w_mask, M, hp.n_spk * N, D, out=ws.sep, epilogue=_lib.EPI_MASK, epi_param=N,
            aux=ws.mix_w)
+        op("decoder", ops.decoder, ws.sep, w.w_dec, ws.batch, ws.T, ws.L, N, hp.n_spk, est=ws.est, frames=ws.frames)
+        return ws.est
+
+    def _run(self, ws: Workspace, taps=None):
+        if not self.fuse_norm or taps is not None:
+            return self._run_unfused(ws, taps)
+        hp, w, P = self.hp, self.w, self.w.P
+        N, D, di, M = hp.enc_dim, hp.d_model, hp.d_inner, ws.M
+        op = self._op
+        norm = dict(rowsq_scale=1.0 / D, rowsq_eps=1e-5)            # eps: mamba_blocks.py:120
+        op("encoder_cln", ops.encoder_cln, ws.mix, w.w_enc, w.gamma, w.beta, P, mix_w=ws.mix_w, yn=ws.yn, T=ws.T)
+        # first block: residual := bottleneck output (bimamba.py:446 with residual None)
+        op("gemm_bottleneck", ops.gemm, ws.yn, w.w_bot, M, D, N, out=ws.res, epilogue=_lib.EPI_RESADD, epi_param=0,
+           out2=ws.xn, rowsum=ws.rowsum[0])
+        cur = 0
+        for i, lw in enumerate(w.layers):
+            op("gemm_in_proj", ops.gemm, ws.xn, lw["w_in_g"], M, 2 * di, D, out=ws.xz, epilogue=_lib.EPI_INPROJ,
+               epi_param=di, out_bf16=ws.xz.dtype == torch.bfloat16, rowsq=ws.rowsum[cur], **norm)
+            self._mixer_core(ws, lw)
+            op("gemm_out_proj", ops.gemm, ws.y, lw["w_out"], M, D, 2 * di, out=ws.res, epilogue=_lib.EPI_RESADD,
+               epi_param=1, out2=ws.xn, rowsum=ws.rowsum[1 - cur])
+            cur = 1 - cur
+        op("gemm_mask", ops.gemm, ws.xn, w.w_mask_g, M, hp.n_spk * N, D, out=ws.sep, epilogue=_lib.EPI_MASK, epi_param=N,
+           aux=ws.mix_w, rowsq=ws.rowsum[cur], **norm)
         op("decoder", ops.decoder, ws.sep, w.w_dec, ws.batch, ws.T, ws.L, N, hp.n_spk, est=ws.est, frames=ws.frames)
         return ws.est
 

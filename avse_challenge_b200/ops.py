@@ -83,8 +83,13 @@ def cln(x, gamma, beta, planes, eps=1e-8, yn=None):
 
 
 def gemm(a_planes, w_planes, M, N, K, *, out=None, groups=1, out_group_stride=0, epilogue=_lib.EPI_STORE,
-         epi_param=0, aux=None, out_bf16=False, ldo=None, max_ctas=0):
-    """out[M, groups x N] = epilogue(A[M, K_g] @ W_g[N, K]^T); A planes [P, rows, lda], W planes [P, groups*N, K]."""
+         epi_param=0, aux=None, out_bf16=False, ldo=None, max_ctas=0, out2=None, rowsum=None, rowsq=None,
+         rowsq_scale=0.0, rowsq_eps=0.0):
+    """out[M, groups x N] = epilogue(A[M, K_g] @ W_g[N, K]^T); A planes [P, rows, lda], W planes [P, groups*N, K].
+    ``rowsq`` (fp32 [parts, M], written by an ``EPI_RESADD`` call): accumulator row r is scaled by
+    rsqrt(sum_k rowsq[k, r] * rowsq_scale + rowsq_eps) first (RMSNorm of the A rows folded in).  ``EPI_RESADD``: out (fp32,
+    in/out) += result when ``epi_param`` else := result; the updated rows also go to ``out2`` (bf16 planes [P, rows, N])
+    and their sums of squares to ``rowsum`` (fp32 [rowsum_parts(N), M], partial sums, plain stores)."""
     _req_cuda(a_planes, w_planes)
     P, a_rows, lda = a_planes.shape
     assert w_planes.shape == (P, groups * N, K), (tuple(w_planes.shape), (P, groups * N, K))
@@ -95,9 +100,17 @@ def gemm(a_planes, w_planes, M, N, K, *, out=None, groups=1, out_group_stride=0,
                     lda=lda, ldo=ldo if ldo is not None else out.stride(0),
                     ld_aux=(aux.stride(0) if aux is not None and aux.dim() == 2 else 0), planes=P, groups=groups,
                     out_group_stride=out_group_stride, epilogue=epilogue, epi_param=epi_param,
-                    out_bf16=int(out_bf16), max_ctas=max_ctas)
+                    out_bf16=int(out_bf16), max_ctas=max_ctas, out2=ptr(out2), rowsum=ptr(rowsum),
+                    ldo2=(out2.stride(1) if out2 is not None else 0), a2_rows=(out2.shape[1] if out2 is not None else 0),
+                    rowsq=ptr(rowsq), rowsq_scale=rowsq_scale, rowsq_eps=rowsq_eps,
+                    rowsq_parts=(rowsq.shape[0] if rowsq is not None else 0))
     check(_lib.load().mtn_gemm_fwd(args, _stream()), "mtn_gemm_fwd")
     return out
+
+
+def rowsum_parts(N: int) -> int:
+    """Partial-sum planes an ``EPI_RESADD`` GEMM with N output columns writes (see ``mtn_gemm_args.rowsum``)."""
+    return int(_lib.load().mtn_gemm_rowsum_parts(N))
 
 
 def add_rmsnorm(h, res, res_valid, g, planes, eps=1e-5, xn=None):

@@ -52,7 +52,8 @@ extern "C" {
 
 typedef void* mtn_stream_t; /* cudaStream_t */
 
-enum { MTN_EPI_STORE = 0, MTN_EPI_INPROJ = 1, MTN_EPI_MASK = 2, MTN_EPI_RELU = 3, MTN_EPI_XPROJ = 4 };
+enum { MTN_EPI_STORE = 0, MTN_EPI_INPROJ = 1, MTN_EPI_MASK = 2, MTN_EPI_RELU = 3, MTN_EPI_XPROJ = 4,
+       MTN_EPI_RESADD = 5 };
 
 typedef struct {
     const void* a;       /* bf16 [planes][a_rows][lda]; group g reads columns [g*K, (g+1)*K) */
@@ -69,9 +70,26 @@ typedef struct {
     int out_group_stride;
     int epilogue;        /* MTN_EPI_* */
     int epi_param;       /* INPROJ: first column that gets SiLU; MASK: enc_dim (aux column = col % enc_dim);
-                            XPROJ: RP (16 or 32) */
+                            XPROJ: RP (16 or 32); RESADD: 1 = out holds a valid residual to add to, 0 = first block
+                            (residual := result, bimamba.py:446 `residual = hidden_states`) */
     int out_bf16;        /* 0: fp32 output, 1: bf16 output */
     int max_ctas;        /* 0 = one persistent CTA per SM */
+    /* --- RMSNorm folded into the GEMMs (ABI >= 4); all optional ------------------------------------------------
+     * Block.forward is Add -> RMSNorm -> Mixer (bimamba.py:446-447).  RMSNorm(res) * g = rstd[row] * res * g[col]: g is
+     * folded into the consuming weight (W' = W * g, done once at load), rstd is a per-row scalar that commutes with
+     * the contraction.  So the producer GEMM (out_proj / bottleneck, MTN_EPI_RESADD) adds its result to the residual,
+     * stores it as fp32 AND as operand planes and accumulates sum(res^2) per row; the consumer GEMM (in_proj / mask)
+     * reads those planes and scales its accumulator rows by rsqrt(rowsq * rowsq_scale + rowsq_eps) before its own
+     * epilogue.  No separate add/norm kernel, no round trip of the mixer output through HBM. */
+    void* out2;          /* MTN_EPI_RESADD: bf16 planes [planes][a2_rows][ldo2] of the updated residual (next GEMM's A) */
+    float* rowsum;       /* MTN_EPI_RESADD: fp32 [parts][M], parts = mtn_gemm_rowsum_parts(N): plane k holds the sum of
+                            res^2 over the columns one epilogue warp group of one N tile owns (plain stores: nothing to
+                            zero, bit-reproducible) */
+    int ldo2, a2_rows;
+    const float* rowsq;  /* any epilogue: nullable fp32 [rowsq_parts][M] written by a RESADD call; accumulator row r is
+                            scaled by rsqrt(sum_k rowsq[k][r] * rowsq_scale + rowsq_eps) */
+    float rowsq_scale, rowsq_eps;
+    int rowsq_parts;
 } mtn_gemm_args;
 
 typedef struct {
@@ -108,6 +126,8 @@ int mtn_encoder_cln_fwd(const float* mix, int ld_mix, const float* w_enc /*[N][1
                         float eps, mtn_stream_t stream);
 
 int mtn_gemm_fwd(const mtn_gemm_args* args, mtn_stream_t stream);
+/* number of partial-sum planes a MTN_EPI_RESADD call with this N writes to `rowsum` */
+int mtn_gemm_rowsum_parts(int N);
 
 /* res = (h ? h : 0) + (res_valid ? res : 0); xn planes = res * rsqrt(mean(res^2)+eps) * g.
  * h fp32 [M][D] (nullable), res fp32 [M][D] in/out. */

@@ -83,6 +83,37 @@ def test_gemm_epilogues(M):
     assert rel_max(out.cpu(), exp) < 5e-5
 
 
+@pytest.mark.parametrize("M,N,K,P", [(1000, 256, 512, 2), (391, 512, 256, 2), (700, 128, 256, 1)])
+def test_gemm_resadd_and_folded_rmsnorm(M, N, K, P):
+    """MTN_EPI_RESADD (residual add + operand planes + row sums of squares in the producer GEMM) and the rowsq scaling
+    of the consumer GEMM together are Add -> RMSNorm -> Linear of bimamba.py:446-447 / mamba_blocks.py:195-197."""
+    g = torch.Generator().manual_seed(M + N)
+    a = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) / K ** 0.5
+    res0 = torch.randn(M, N, generator=g)
+    gain = torch.rand(N, generator=g) + 0.5
+    w2 = torch.randn(256, N, generator=g) / N ** 0.5
+    ap, wp = ops.split_planes(a.to(DEV), P), ops.split_planes(w.to(DEV), P)
+    prod = _planes_value(ap).double() @ _planes_value(wp).double().t()
+    tol = 5e-5 if P == 2 else 5e-6
+    for valid in (1, 0):
+        res = res0.clone().to(DEV)
+        planes = torch.empty((P, M, N), dtype=torch.bfloat16, device=DEV)
+        rowsum = torch.full((ops.rowsum_parts(N), M), float('nan'), device=DEV)   # plain stores: no zeroing needed
+        ops.gemm(ap, wp, M, N, K, out=res, epilogue=_lib.EPI_RESADD, epi_param=valid, out2=planes, rowsum=rowsum)
+        exp = prod + (res0.double() if valid else 0.0)
+        assert rel_max(res.cpu(), exp) < tol
+        assert rel_mixed(_planes_value(planes), res.cpu()) < (2 ** -15 if P == 2 else 2 ** -8)
+        assert rel_max(rowsum.sum(0).cpu(), res.cpu().double().pow(2).sum(1)) < 1e-5
+    # consumer: rows scaled by rsqrt(mean(res^2) + eps), gain folded into the weight
+    w2g = ops.split_planes((w2 * gain[None, :]).to(DEV), P)
+    out = ops.gemm(planes, w2g, M, 256, N, rowsq=rowsum, rowsq_scale=1.0 / N, rowsq_eps=1e-5)
+    r = _planes_value(planes).double()                       # the operand rows (bf16-rounded when P = 1) ...
+    xhat = r * torch.rsqrt(res.cpu().double().pow(2).mean(1, keepdim=True) + 1e-5)   # ... scaled by the fp32 residual's rstd
+    exp2 = xhat @ _planes_value(w2g).double().t()
+    assert rel_max(out.cpu(), exp2) < tol * 2
+
+
 def test_gemm_rejects_bad_shapes():
     ap = torch.zeros(2, 128, 64, dtype=torch.bfloat16, device=DEV)
     wp = torch.zeros(2, 40, 64, dtype=torch.bfloat16, device=DEV)
@@ -307,6 +338,17 @@ def test_end_to_end_vs_oracle_shipped_configs(name, B, T):
     err, d_sisnr, fid = _gate(est, ref, src)
     print(f"{name}: max-abs/rms {err:.3e}  dSI-SNR {d_sisnr:.2e} dB  SI-SNR(est,ref) {fid:.1f} dB")
     assert err <= 1e-3 and d_sisnr <= 0.01, (err, d_sisnr, fid)
+
+
+def test_fused_norm_equals_separate_add_rmsnorm_kernel():
+    """The default plan folds Add -> RMSNorm into the GEMM epilogues; the plan with the separate add_rmsnorm kernel
+    must give the same waveform to fp32 rounding."""
+    hp = CONFIGS["XS"]
+    sds = init_state_dicts(hp, 7)
+    mix, _ = synth_mixture(3, 8000, seed=5)
+    a = SeparatorEngine(hp, sds, device=DEV, mode="fp32", use_graph=False, fuse_norm=True)(mix.to(DEV)).cpu()
+    b = SeparatorEngine(hp, sds, device=DEV, mode="fp32", use_graph=False, fuse_norm=False)(mix.to(DEV)).cpu()
+    assert (a - b).abs().max() <= 2e-4 * b.pow(2).mean().sqrt()
 
 
 def test_bf16_mode_stated_tolerance():
