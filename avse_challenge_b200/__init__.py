@@ -5,6 +5,7 @@ Public surface:
     MambaTasNetSeparator                                              -- fused compute_forward equivalent
     SeparatorEngine                                                   -- the kernel plan itself
     CONFIGS / HParams / init_state_dicts                              -- the four shipped configurations
+    checkpoint (recipe yaml + CKPT dir loader), scoring (SI-SNR / PIT on device, test_results.csv)
 The compute path is ``libmtn_b200.so`` (C ABI in ``include/mtn_b200.h``); importing this package does not
 load it, calling any op without it raises.
 """

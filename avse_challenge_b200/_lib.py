@@ -6,7 +6,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmtn_b200.so")
@@ -16,7 +16,7 @@ EPI_STORE, EPI_INPROJ, EPI_MASK, EPI_RELU, EPI_XPROJ, EPI_RESADD = 0, 1, 2, 3, 4
 EXPORTS = [
     "mtn_encoder_cln_fwd", "mtn_gemm_fwd", "mtn_gemm_rowsum_parts", "mtn_add_rmsnorm_fwd", "mtn_conv_silu_fwd", "mtn_conv_silu_halo_fwd",
     "mtn_scan_fwd", "mtn_fold_states_fwd",
-    "mtn_decoder_fwd", "mtn_cln_fwd", "mtn_split_planes", "mtn_last_error_string", "mtn_abi_version",
+    "mtn_decoder_fwd", "mtn_cln_fwd", "mtn_split_planes", "mtn_si_snr_pit_fwd", "mtn_si_snr_workspace_bytes", "mtn_last_error_string", "mtn_abi_version",
 ]
 
 
@@ -76,10 +76,13 @@ def load():
     lib.mtn_decoder_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]
     lib.mtn_cln_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p]
     lib.mtn_split_planes.argtypes = [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p]
+    lib.mtn_si_snr_workspace_bytes.argtypes = [c_int, c_int]
+    lib.mtn_si_snr_pit_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p, c_void_p]
     for name in EXPORTS:
         fn = getattr(lib, name, None)
-        if fn is not None and name not in ("mtn_last_error_string", "mtn_abi_version"):
+        if fn is not None and name not in ("mtn_last_error_string", "mtn_abi_version", "mtn_si_snr_workspace_bytes"):
             fn.restype = c_int
+    lib.mtn_si_snr_workspace_bytes.restype = c_size_t
     _lib = lib
     return lib
 

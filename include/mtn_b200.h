@@ -172,6 +172,16 @@ int mtn_cln_fwd(const float* x, const float* gamma, const float* beta, void* yn_
 /* fp32 [rows][cols] (row stride ld) -> bf16 planes [planes][rows][cols] (weight packing helper) */
 int mtn_split_planes(const float* src, int ld, void* dst_planes, int rows, int cols, int planes, mtn_stream_t stream);
 
+/* Evaluation front end: SI-SNR with 2-speaker PIT and SI-SNR improvement over the mixture, as
+ * `save_results` computes them per utterance (Mamba-TasNet/train_wsj0mix.py:548-558; SI-SNR = cal_si_snr,
+ * baseline/avse2/utils/dnn.py:15-57).  est, src fp32 [batch][T][2], mix fp32 [batch][ld_mix >= T].
+ * out fp32 [batch][8] = { si_snr (best permutation, mean over speakers), si_snr_i, permutation (0 direct, 1 swapped),
+ * si_snr of the mixture, pair matrix est0/src0, est0/src1, est1/src0, est1/src1 }, all in dB (positive = better).
+ * workspace: mtn_si_snr_workspace_bytes(batch, T) bytes, 8-byte aligned. */
+size_t mtn_si_snr_workspace_bytes(int batch, int T);
+int mtn_si_snr_pit_fwd(const float* est, const float* src, const float* mix, int ld_mix, int batch, int T,
+                       void* workspace, size_t workspace_bytes, float* out, mtn_stream_t stream);
+
 const char* mtn_last_error_string(void);
 int mtn_abi_version(void);
 

@@ -89,12 +89,34 @@ def golden_forward(name, T, batch, seed, tag, own_init):
           os.path.getsize(os.path.join(OUT, f"forward_{tag}.npz")) // 1024, "KiB")
 
 
+def golden_si_snr():
+    """``cal_si_snr`` of the reference itself (``baseline/avse2/utils/dnn.py:15-57``; plain torch, imported from the
+    reference tree) on seeded (source, estimate) pairs: pins ``oracle.restate.cal_si_snr``."""
+    import importlib.util
+    path = os.path.join(ref_shims.REFERENCE_ROOT, "baseline", "avse2", "utils", "dnn.py")
+    spec = importlib.util.spec_from_file_location("_ref_dnn", path)
+    dnn = importlib.util.module_from_spec(spec)
+    sys.dont_write_bytecode = True
+    spec.loader.exec_module(dnn)
+    _, src = synth_mixture(3, 4001, seed=99)
+    g = torch.Generator().manual_seed(5)
+    est = src * 0.7 + torch.randn(src.shape, generator=g) * torch.tensor([0.002, 0.0002, 0.02]).view(3, 1, 1)
+    est[0] = est[0].flip(-1)   # speakers swapped: channel-paired SI-SNR is very low, PIT must undo it
+    est[0] += 0.3      # a DC offset must not matter (zero-mean)
+    # reference layout is [T, B, C]; it modifies its estimate argument in place -> pass a clone
+    neg = dnn.cal_si_snr(src.permute(1, 0, 2).contiguous(), est.permute(1, 0, 2).contiguous().clone())
+    np.savez_compressed(os.path.join(OUT, "si_snr_ref.npz"), src=src.numpy(), est=est.numpy(),
+                        si_snr=(-neg[0]).numpy())
+    print("si_snr_ref.npz", (-neg[0]).tolist())
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
     golden_scan()
     golden_forward("tiny", T=2000, batch=2, seed=1234, tag="tiny_refinit", own_init=False)
     golden_forward("tiny", T=1003, batch=3, seed=77, tag="tiny_trained", own_init=True)
+    golden_si_snr()
 
 
 if __name__ == "__main__":

@@ -235,3 +235,38 @@ def separate(mix, sds, n_mamba, n_spk=2, scan_impl="auto", taps=None):
         taps.append(mix_w)
         taps.append(mask)
     return est
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Evaluation metrics
+def cal_si_snr(source, estimate):
+    """SI-SNR in dB per (utterance, channel); ``source``, ``estimate`` [B, T, C].
+    Restates ``cal_si_snr`` of ``baseline/avse2/utils/dnn.py:15-57`` (the in-repo statement of the speechbrain loss
+    the Mamba-TasNet recipe trains and evaluates with, ``hparams/WSJ0Mix/mambatasnet_S.yaml:163``) for full-length
+    utterances, in float64, with the sign flipped back (the reference returns ``-si_snr``)."""
+    EPS = 1e-8
+    s = source.double() - source.double().mean(dim=1, keepdim=True)          # dnn.py:29-36 (zero-mean over time)
+    a = estimate.double() - estimate.double().mean(dim=1, keepdim=True)
+    dot = (a * s).sum(dim=1, keepdim=True)                                   # dnn.py:45
+    energy = (s ** 2).sum(dim=1, keepdim=True) + EPS                         # dnn.py:46-48
+    proj = dot * s / energy                                                  # dnn.py:49
+    noise = a - proj                                                         # dnn.py:51
+    ratio = (proj ** 2).sum(dim=1) / ((noise ** 2).sum(dim=1) + EPS)         # dnn.py:53-55
+    return 10 * torch.log10(ratio + EPS)                                     # dnn.py:56
+
+
+def pit_si_snr_improvement(est, src, mix):
+    """What ``save_results`` writes per utterance (``Mamba-TasNet/train_wsj0mix.py:548-558``): PIT SI-SNR of the
+    estimates, of the unprocessed mixture, and their difference.  The PIT wrapper [3P speechbrain
+    ``get_si_snr_with_pitwrapper``, published behaviour] takes the permutation with the smallest mean loss, i.e. the
+    largest mean SI-SNR over the speakers.  Returns (si_snr [B], si_snr_i [B], perm [B], pairs [B, 2, 2])."""
+    B = est.shape[0]
+    pairs = torch.stack([torch.stack([cal_si_snr(src[..., j:j + 1], est[..., i:i + 1])[:, 0] for j in range(2)], dim=-1)
+                         for i in range(2)], dim=1)                          # [B, est i, src j]
+    direct = 0.5 * (pairs[:, 0, 0] + pairs[:, 1, 1])
+    swapped = 0.5 * (pairs[:, 0, 1] + pairs[:, 1, 0])
+    perm = (swapped > direct).long()
+    best = torch.where(perm.bool(), swapped, direct)
+    mixture = torch.stack([mix] * 2, dim=-1)                                 # train_wsj0mix.py:551-553
+    base = cal_si_snr(src, mixture).mean(dim=-1)
+    return best, best - base, perm, pairs

@@ -79,3 +79,16 @@ def test_gemm_rounding_models_are_ordered(golden_dir):
     finally:
         restate.set_gemm_mode("fp32")
     assert errs["bf16x3"] < 1e-4 < errs["tf32"] < errs["bf16"]
+
+
+def test_si_snr_restatement_matches_reference_cal_si_snr(golden_dir):
+    """oracle.restate.cal_si_snr against outputs of the reference's own cal_si_snr (baseline/avse2/utils/dnn.py:15-57),
+    minted by oracle/make_golden.py::golden_si_snr."""
+    z = np.load(os.path.join(golden_dir, "si_snr_ref.npz"))
+    src, est, ref = torch.from_numpy(z["src"]), torch.from_numpy(z["est"]), torch.from_numpy(z["si_snr"]).double()
+    mine = restate.cal_si_snr(src, est)
+    assert (mine - ref).abs().max() < 1e-3          # the reference computes in fp32; dB
+    best, imp, perm, pairs = restate.pit_si_snr_improvement(est, src, src.sum(-1))
+    assert perm.tolist() == [1, 0, 0]               # utterance 0 was minted with its speakers swapped
+    assert torch.allclose(pairs[1:, [0, 1], [0, 1]], mine[1:], atol=1e-9)
+    assert (best > 4).all() and (imp > 4).all() and best[1] > 40
