@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libmtn_b200.so")
 EPI_STORE, EPI_INPROJ, EPI_MASK, EPI_RELU, EPI_XPROJ, EPI_RESADD = 0, 1, 2, 3, 4, 5
 
 EXPORTS = [
-    "mtn_encoder_cln_fwd", "mtn_gemm_fwd", "mtn_gemm_rowsum_parts", "mtn_add_rmsnorm_fwd", "mtn_conv_silu_fwd", "mtn_conv_silu_halo_fwd",
+    "mtn_encoder_cln_fwd", "mtn_gemm_fwd", "mtn_gemm_rowsum_parts", "mtn_add_rmsnorm_fwd", "mtn_add_rmsnorm_out_fwd", "mtn_conv_silu_fwd", "mtn_conv_silu_halo_fwd", "mtn_conv_silu_dir_fwd", "mtn_decoder_stream_fwd",
     "mtn_scan_fwd", "mtn_fold_states_fwd",
     "mtn_decoder_fwd", "mtn_cln_fwd", "mtn_split_planes", "mtn_si_snr_pit_fwd", "mtn_si_snr_workspace_bytes", "mtn_last_error_string", "mtn_abi_version",
 ]
@@ -67,10 +67,15 @@ def load():
     lib.mtn_gemm_rowsum_parts.argtypes = [c_int]
     lib.mtn_add_rmsnorm_fwd.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_float,
                                         c_void_p]
+    lib.mtn_add_rmsnorm_out_fwd.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                            c_float, c_void_p]
     lib.mtn_conv_silu_fwd.argtypes = [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                       c_void_p]
     lib.mtn_conv_silu_halo_fwd.argtypes = [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
                                            c_void_p, c_int, c_int, c_int, c_int, c_void_p]
+    lib.mtn_conv_silu_dir_fwd.argtypes = [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                                          c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]
+    lib.mtn_decoder_stream_fwd.argtypes = [c_void_p] * 5 + [c_int] * 5 + [c_void_p]
     lib.mtn_scan_fwd.argtypes = [POINTER(ScanArgs), c_void_p]
     lib.mtn_fold_states_fwd.argtypes = [c_void_p] * 6 + [c_int] * 5 + [c_void_p]
     lib.mtn_decoder_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]

@@ -119,8 +119,6 @@ def read_hparams_yaml(path: str, name: Optional[str] = None) -> HParams:
     missing = [k for k in need if k not in y]
     if missing:
         raise KeyError(f"{path}: missing {missing}")
-    if y.get("bidirectional", True) is not True:
-        raise NotImplementedError("bidirectional: False (mamba_ssm.Mamba path, mamba_blocks.py:128) is not built")
     if y.get("fused_add_norm", False) or not y.get("rms_norm", True):
         raise NotImplementedError("only fused_add_norm: False / rms_norm: True (all shipped recipes) is built")
     stride = y.get("kernel_stride", y["kernel_size"] // 2)
@@ -129,7 +127,8 @@ def read_hparams_yaml(path: str, name: Optional[str] = None) -> HParams:
     return HParams(name or os.path.splitext(os.path.basename(path))[0], int(y["N_encoder_out"]), int(y["out_channels"]),
                    int(y["n_mamba"]), kernel_size=int(y["kernel_size"]), d_state=int(y.get("ssm_dim", 16)),
                    expand=int(y.get("mamba_expand", 2)), d_conv=int(y.get("mamba_conv", 4)),
-                   n_spk=int(y.get("num_spks", 2)), sample_rate=int(y.get("sample_rate", 8000)))
+                   n_spk=int(y.get("num_spks", 2)), sample_rate=int(y.get("sample_rate", 8000)),
+                   bidirectional=bool(y.get("bidirectional", True)))
 
 
 def find_checkpoint_dir(save_folder: str) -> str:

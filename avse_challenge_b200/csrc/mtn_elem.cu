@@ -160,7 +160,7 @@ cln_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const f
 template <int P, int NV, bool VEC>  // VEC: NV float4 per lane (D = 128*NV); else NV floats per lane (D = 32*NV)
 __global__ void __launch_bounds__(256)
 add_rmsnorm_kernel(const float* __restrict__ h, float* __restrict__ res, int res_valid, const float* __restrict__ g,
-                   __nv_bfloat16* __restrict__ xn, int M, float eps) {
+                   __nv_bfloat16* __restrict__ xn, float* __restrict__ out_f32, int M, float eps) {
     constexpr int D = VEC ? 128 * NV : 32 * NV;
     const int lane = threadIdx.x & 31;
     const int warps_per_block = blockDim.x >> 5;
@@ -195,7 +195,8 @@ add_rmsnorm_kernel(const float* __restrict__ h, float* __restrict__ res, int res
                 o.y = r[j].y * rstd * gg.y;
                 o.z = r[j].z * rstd * gg.z;
                 o.w = r[j].w * rstd * gg.w;
-                store_planes4<P>(xn, plane_stride, off, o);
+                if (xn) store_planes4<P>(xn, plane_stride, off, o);
+                if (out_f32) *reinterpret_cast<float4*>(out_f32 + off) = o;
             }
         } else {
             float r[NV];
@@ -213,7 +214,9 @@ add_rmsnorm_kernel(const float* __restrict__ h, float* __restrict__ res, int res
             for (int j = 0; j < NV; ++j) {
                 const size_t off = base + 32 * j + lane;
                 if (h) res[off] = r[j];
-                store_planes1<P>(xn, plane_stride, off, r[j] * rstd * g[32 * j + lane]);
+                const float o = r[j] * rstd * g[32 * j + lane];
+                if (xn) store_planes1<P>(xn, plane_stride, off, o);
+                if (out_f32) out_f32[off] = o;
             }
         }
     }
@@ -246,20 +249,21 @@ template <int P, typename XT>
 __global__ void __launch_bounds__(256)
 conv_silu_kernel(const XT* __restrict__ xz, int ldxz, const float* __restrict__ conv_w, const float* __restrict__ conv_b,
                  __nv_bfloat16* __restrict__ u, size_t u_rows, const float* __restrict__ halo_lo,
-                 const float* __restrict__ halo_hi, int batch, int L, int di) {
+                 const float* __restrict__ halo_hi, int batch, int L, int di, int dir_mask) {
     const int c = (blockIdx.z * blockDim.x + threadIdx.x) * 4;
     if (c >= di) return;
     const int b = blockIdx.y;
     const int t0 = blockIdx.x * CONV_TT;
     const int t1 = min(t0 + CONV_TT, L);
     const size_t plane_stride = u_rows * 2 * di;
+    const bool do_f = dir_mask & 1, do_b = dir_mask & 2;  // unidirectional stacks run the forward half only
     float4 wf[4], wb[4];  // wf[k] = tap k for channels c..c+3
     {
         float tf[4][4], tb[4][4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const float4 a = *reinterpret_cast<const float4*>(conv_w + size_t(c + i) * 4);
-            const float4 bq = *reinterpret_cast<const float4*>(conv_w + size_t(di + c + i) * 4);
+            const float4 bq = do_b ? *reinterpret_cast<const float4*>(conv_w + size_t(di + c + i) * 4) : a;
             tf[i][0] = a.x; tf[i][1] = a.y; tf[i][2] = a.z; tf[i][3] = a.w;
             tb[i][0] = bq.x; tb[i][1] = bq.y; tb[i][2] = bq.z; tb[i][3] = bq.w;
         }
@@ -270,7 +274,7 @@ conv_silu_kernel(const XT* __restrict__ xz, int ldxz, const float* __restrict__ 
         }
     }
     const float4 bf = *reinterpret_cast<const float4*>(conv_b + c);
-    const float4 bb = *reinterpret_cast<const float4*>(conv_b + di + c);
+    const float4 bb = do_b ? *reinterpret_cast<const float4*>(conv_b + di + c) : bf;
     const XT* xbase = xz + size_t(b) * L * ldxz + c;
     const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
     // rows outside [0, L): the neighbouring chunk's rows when a halo is given, else the zero padding of the conv
@@ -304,8 +308,8 @@ conv_silu_kernel(const XT* __restrict__ xz, int ldxz, const float* __restrict__ 
                 f = make_float4(silu_f(f.x), silu_f(f.y), silu_f(f.z), silu_f(f.w));
                 r = make_float4(silu_f(r.x), silu_f(r.y), silu_f(r.z), silu_f(r.w));
                 const size_t off = (size_t(b) * L + (t + i)) * (2 * di) + c;
-                store_planes4<P>(u, plane_stride, off, f);
-                store_planes4<P>(u, plane_stride, off + di, r);
+                if (do_f) store_planes4<P>(u, plane_stride, off, f);
+                if (do_b) store_planes4<P>(u, plane_stride, off + di, r);
             }
             w0 = w1; w1 = w2; w2 = w3; w3 = w4; w4 = w5; w5 = w6;
         }
@@ -374,6 +378,32 @@ decoder_ola_kernel(const float* __restrict__ frames, float* __restrict__ est, in
         float v = 0.f;
         if (l1 < L) v += frames[((size_t(b) * L + l1) * S + s) * 16 + k];
         if (l1 >= 1 && l1 - 1 < L) v += frames[((size_t(b) * L + l1 - 1) * S + s) * 16 + 8 + k];
+        est[i] = v;
+    }
+}
+
+// Streaming overlap-add: this chunk's F frames finalise samples [0, 8F); the first 8 of them also receive the second
+// half of the previous chunk's last frame (tail, in), and the second half of frame F-1 becomes the new tail (out).
+// The thread that reads tail[b][s][k] is the one that overwrites it.
+__global__ void __launch_bounds__(256)
+decoder_ola_stream_kernel(const float* __restrict__ frames, float* __restrict__ est, float* __restrict__ tail, int batch,
+                          int F, int S) {
+    const int T = 8 * F;
+    const size_t total = size_t(batch) * T * S;
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+        const int s = int(i % S);
+        const size_t bt = i / S;
+        const int t = int(bt % T);
+        const int b = int(bt / T);
+        const int l1 = t >> 3, k = t & 7;
+        float v = frames[((size_t(b) * F + l1) * S + s) * 16 + k];
+        if (l1 >= 1) {
+            v += frames[((size_t(b) * F + l1 - 1) * S + s) * 16 + 8 + k];
+        } else {
+            float* tp = tail + (size_t(b) * S + s) * 8 + k;
+            v += *tp;
+            *tp = frames[((size_t(b) * F + F - 1) * S + s) * 16 + 8 + k];
+        }
         est[i] = v;
     }
 }
@@ -458,13 +488,19 @@ extern "C" int mtn_cln_fwd(const float* x, const float* gamma, const float* beta
 
 extern "C" int mtn_add_rmsnorm_fwd(const float* h, float* res, int res_valid, const float* g, void* xn_planes, int M,
                                    int D, int planes, float eps, mtn_stream_t stream) {
-    MTN_REQUIRE(res && g && xn_planes, "add_rmsnorm: null pointer");
+    MTN_REQUIRE(xn_planes, "add_rmsnorm: null pointer");
+    return mtn_add_rmsnorm_out_fwd(h, res, res_valid, g, xn_planes, nullptr, M, D, planes, eps, stream);
+}
+
+extern "C" int mtn_add_rmsnorm_out_fwd(const float* h, float* res, int res_valid, const float* g, void* xn_planes,
+                                       float* out_f32, int M, int D, int planes, float eps, mtn_stream_t stream) {
+    MTN_REQUIRE(res && g && (xn_planes || out_f32), "add_rmsnorm: null pointer");
     MTN_REQUIRE(h || res_valid, "add_rmsnorm: need h or a valid residual");
     MTN_REQUIRE(M > 0 && planes >= 1 && planes <= 2, "add_rmsnorm: bad M=%d planes=%d", M, planes);
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     const int grid = grid_for(size_t(M), 8, 8);
     __nv_bfloat16* xn = reinterpret_cast<__nv_bfloat16*>(xn_planes);
-#define MTN_RMS(PP, NV, VEC) add_rmsnorm_kernel<PP, NV, VEC><<<grid, 256, 0, s>>>(h, res, res_valid, g, xn, M, eps)
+#define MTN_RMS(PP, NV, VEC) add_rmsnorm_kernel<PP, NV, VEC><<<grid, 256, 0, s>>>(h, res, res_valid, g, xn, out_f32, M, eps)
 #define MTN_RMS_D(PP)                                                             \
     switch (D) {                                                                  \
         case 64: MTN_RMS(PP, 2, false); break;                                    \
@@ -489,7 +525,15 @@ extern "C" int mtn_conv_silu_fwd(const void* xz, int ldxz, int xz_bf16, const fl
 extern "C" int mtn_conv_silu_halo_fwd(const void* xz, int ldxz, int xz_bf16, const float* conv_w, const float* conv_b,
                                       void* u_planes, int u_rows, const float* halo_lo, const float* halo_hi,
                                       int batch, int L, int di, int planes, mtn_stream_t stream) {
+    return mtn_conv_silu_dir_fwd(xz, ldxz, xz_bf16, conv_w, conv_b, u_planes, u_rows, halo_lo, halo_hi, batch, L, di,
+                                 planes, 3, stream);
+}
+
+extern "C" int mtn_conv_silu_dir_fwd(const void* xz, int ldxz, int xz_bf16, const float* conv_w, const float* conv_b,
+                                     void* u_planes, int u_rows, const float* halo_lo, const float* halo_hi,
+                                     int batch, int L, int di, int planes, int dir_mask, mtn_stream_t stream) {
     MTN_REQUIRE(xz && conv_w && conv_b && u_planes, "conv_silu: null pointer");
+    MTN_REQUIRE(dir_mask >= 1 && dir_mask <= 3, "conv_silu: dir_mask=%d", dir_mask);
     MTN_REQUIRE(batch > 0 && L > 0 && di > 0 && di % 4 == 0 && ldxz % 4 == 0, "conv_silu: bad shape");
     MTN_REQUIRE(planes == 1 || planes == 2, "conv_silu: planes=%d", planes);
     MTN_REQUIRE(batch <= 65535, "conv_silu: batch too large for grid.y");
@@ -501,12 +545,12 @@ extern "C" int mtn_conv_silu_halo_fwd(const void* xz, int ldxz, int xz_bf16, con
     __nv_bfloat16* u = reinterpret_cast<__nv_bfloat16*>(u_planes);
     if (xz_bf16) {
         const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(xz);
-        if (planes == 2) conv_silu_kernel<2, __nv_bfloat16><<<grid, block, 0, s>>>(x, ldxz, conv_w, conv_b, u, size_t(u_rows), halo_lo, halo_hi, batch, L, di);
-        else conv_silu_kernel<1, __nv_bfloat16><<<grid, block, 0, s>>>(x, ldxz, conv_w, conv_b, u, size_t(u_rows), halo_lo, halo_hi, batch, L, di);
+        if (planes == 2) conv_silu_kernel<2, __nv_bfloat16><<<grid, block, 0, s>>>(x, ldxz, conv_w, conv_b, u, size_t(u_rows), halo_lo, halo_hi, batch, L, di, dir_mask);
+        else conv_silu_kernel<1, __nv_bfloat16><<<grid, block, 0, s>>>(x, ldxz, conv_w, conv_b, u, size_t(u_rows), halo_lo, halo_hi, batch, L, di, dir_mask);
     } else {
         const float* x = reinterpret_cast<const float*>(xz);
-        if (planes == 2) conv_silu_kernel<2, float><<<grid, block, 0, s>>>(x, ldxz, conv_w, conv_b, u, size_t(u_rows), halo_lo, halo_hi, batch, L, di);
-        else conv_silu_kernel<1, float><<<grid, block, 0, s>>>(x, ldxz, conv_w, conv_b, u, size_t(u_rows), halo_lo, halo_hi, batch, L, di);
+        if (planes == 2) conv_silu_kernel<2, float><<<grid, block, 0, s>>>(x, ldxz, conv_w, conv_b, u, size_t(u_rows), halo_lo, halo_hi, batch, L, di, dir_mask);
+        else conv_silu_kernel<1, float><<<grid, block, 0, s>>>(x, ldxz, conv_w, conv_b, u, size_t(u_rows), halo_lo, halo_hi, batch, L, di, dir_mask);
     }
     MTN_CUDA_LAUNCH_CHECK("conv_silu");
     return MTN_OK;
@@ -514,8 +558,14 @@ extern "C" int mtn_conv_silu_halo_fwd(const void* xz, int ldxz, int xz_bf16, con
 
 extern "C" int mtn_decoder_fwd(const float* sep, const float* w_dec, float* frames, float* est, int batch, int T, int L,
                                int N, int n_spk, mtn_stream_t stream) {
+    return mtn_decoder_stream_fwd(sep, w_dec, frames, est, nullptr, batch, T, L, N, n_spk, stream);
+}
+
+extern "C" int mtn_decoder_stream_fwd(const float* sep, const float* w_dec, float* frames, float* est, float* tail,
+                                      int batch, int T, int L, int N, int n_spk, mtn_stream_t stream) {
     MTN_REQUIRE(sep && w_dec && frames && est, "decoder: null pointer");
     MTN_REQUIRE(batch > 0 && T > 0 && L > 0 && n_spk >= 1, "decoder: bad shape");
+    MTN_REQUIRE(!tail || T == 8 * L, "decoder(stream): a chunk of L frames finalises exactly 8*L samples (T=%d, L=%d)", T, L);
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     const size_t tokens = size_t(batch) * L;
     const int grid = grid_for(tokens * n_spk, 8, 4);
@@ -535,7 +585,8 @@ extern "C" int mtn_decoder_fwd(const float* sep, const float* w_dec, float* fram
     }
 #undef MTN_DEC
     MTN_CUDA_LAUNCH_CHECK("decoder_frames");
-    decoder_ola_kernel<<<grid_for(size_t(batch) * T * n_spk, 256, 8), 256, 0, s>>>(frames, est, batch, T, L, n_spk);
+    if (tail) decoder_ola_stream_kernel<<<grid_for(size_t(batch) * T * n_spk, 256, 8), 256, 0, s>>>(frames, est, tail, batch, L, n_spk);
+    else decoder_ola_kernel<<<grid_for(size_t(batch) * T * n_spk, 256, 8), 256, 0, s>>>(frames, est, batch, T, L, n_spk);
     MTN_CUDA_LAUNCH_CHECK("decoder_ola");
     return MTN_OK;
 }

@@ -73,4 +73,4 @@ bool encode_tmap(CUtensorMap* map, CUtensorMapDataType dtype, int rank, const vo
 }  // namespace mtn
 
 extern "C" const char* mtn_last_error_string(void) { return mtn::g_err; }
-extern "C" int mtn_abi_version(void) { return 4; }
+extern "C" int mtn_abi_version(void) { return 5; }

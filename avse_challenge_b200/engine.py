@@ -50,45 +50,50 @@ class PackedWeights:
         self.w_mask = ops.split_planes(f32(m["mask_conv1x1.conv.weight"]).reshape(hp.n_spk * N, D), P)
         self.norm_f = f32(m["mamba_net.norm_f.weight"])
         self.w_mask_g = ops.split_planes(f32(m["mask_conv1x1.conv.weight"]).reshape(hp.n_spk * N, D) * self.norm_f[None, :], P)
-        self.layers = []
-        for i in range(hp.n_mamba):
-            p = f"mamba_net.layers.{i}."
-            lw = {}
-            lw["norm"] = f32(m[p + "norm.weight"])
-            lw["w_in"] = ops.split_planes(f32(m[p + "mixer.in_proj.weight"]), P)            # [P, 2di, D]
-            lw["w_in_g"] = ops.split_planes(f32(m[p + "mixer.in_proj.weight"]) * lw["norm"][None, :], P)  # RMSNorm gain folded in
-            lw["conv_w"] = torch.stack([f32(m[p + "mixer.conv1d.weight"]).reshape(di, hp.d_conv),
-                                        f32(m[p + "mixer.conv1d_b.weight"]).reshape(di, hp.d_conv)]).contiguous()
-            lw["conv_b"] = torch.stack([f32(m[p + "mixer.conv1d.bias"]), f32(m[p + "mixer.conv1d_b.bias"])]).contiguous()
-            wx = torch.zeros((2 * nd, di), dtype=torch.float32, device=device)              # rows padded R+32 -> nd
-            wx[: R + 32] = f32(m[p + "mixer.x_proj.weight"])
-            wx[nd: nd + R + 32] = f32(m[p + "mixer.x_proj_b.weight"])
-            lw["w_x"] = ops.split_planes(wx, P)                                             # [P, 2*nd, di]
-            lw["w_dt"] = torch.stack([f32(m[p + "mixer.dt_proj.weight"]), f32(m[p + "mixer.dt_proj_b.weight"])]).contiguous()
-            lw["dt_bias"] = torch.stack([f32(m[p + "mixer.dt_proj.bias"]), f32(m[p + "mixer.dt_proj_b.bias"])]).contiguous()
-            A = torch.stack([-torch.exp(f32(m[p + "mixer.A_log"])), -torch.exp(f32(m[p + "mixer.A_b_log"]))])
-            lw["A2"] = (A * LOG2E).contiguous()                                             # [2, di, 16]
-            lw["D"] = torch.stack([f32(m[p + "mixer.D"]), f32(m[p + "mixer.D_b"])]).contiguous()
-            w_out = f32(m[p + "mixer.out_proj.weight"])                                     # [D, di]
-            lw["w_out"] = ops.split_planes(torch.cat([w_out, w_out], dim=1).contiguous(), P)  # [P, D, 2di]
-            self.layers.append(lw)
+        self.layers = [pack_layer(m, f"mamba_net.layers.{i}.", hp, P, device) for i in range(hp.n_mamba)]
 
 
-class Workspace:
-    """Activation buffers for one (batch, T) shape; reused across layers and calls."""
+def pack_layer(m: dict, p: str, hp: HParams, P: int, device) -> dict:
+    """Kernel-ready tensors of one ``Block`` (``norm`` + ``mixer``; state_dict ``m``, key prefix ``p``)."""
+    f32 = lambda t: t.detach().to(device=device, dtype=torch.float32).contiguous()
+    di, R = hp.d_inner, hp.dt_rank
+    nd = n_dbl_for(R)
+    lw = {}
+    lw["norm"] = f32(m[p + "norm.weight"])
+    lw["w_in"] = ops.split_planes(f32(m[p + "mixer.in_proj.weight"]), P)            # [P, 2di, D]
+    lw["w_in_g"] = ops.split_planes(f32(m[p + "mixer.in_proj.weight"]) * lw["norm"][None, :], P)  # RMSNorm gain folded in
+    sfxs = ("", "_b") if hp.bidirectional else ("",)      # unidirectional: mamba_ssm.Mamba keys, forward set only
+    lw["conv_w"] = torch.stack([f32(m[p + f"mixer.conv1d{x}.weight"]).reshape(di, hp.d_conv) for x in sfxs]).contiguous()
+    lw["conv_b"] = torch.stack([f32(m[p + f"mixer.conv1d{x}.bias"]) for x in sfxs]).contiguous()
+    wx = torch.zeros((len(sfxs) * nd, di), dtype=torch.float32, device=device)      # rows padded R+32 -> nd
+    for k, x in enumerate(sfxs):
+        wx[k * nd: k * nd + R + 32] = f32(m[p + f"mixer.x_proj{x}.weight"])
+    lw["w_x"] = ops.split_planes(wx, P)                                             # [P, ndir*nd, di]
+    lw["w_dt"] = torch.stack([f32(m[p + f"mixer.dt_proj{x}.weight"]) for x in sfxs]).contiguous()
+    lw["dt_bias"] = torch.stack([f32(m[p + f"mixer.dt_proj{x}.bias"]) for x in sfxs]).contiguous()
+    A = torch.stack([-torch.exp(f32(m[p + f"mixer.{a}"])) for a in (("A_log", "A_b_log") if hp.bidirectional else ("A_log",))])
+    lw["A2"] = (A * LOG2E).contiguous()                                             # [ndir, di, 16]
+    lw["D"] = torch.stack([f32(m[p + f"mixer.{d}"]) for d in (("D", "D_b") if hp.bidirectional else ("D",))]).contiguous()
+    w_out = f32(m[p + "mixer.out_proj.weight"])                                     # [D, di]
+    if hp.bidirectional:   # K = 2*di sums the two directions (the scan already applied the 0.5 of bimamba.py:253)
+        lw["w_out"] = ops.split_planes(torch.cat([w_out, w_out], dim=1).contiguous(), P)  # [P, D, 2di]
+    else:                  # one direction, no averaging (bimamba.py:306): undo the scan's 0.5 exactly (power of two)
+        lw["w_out"] = ops.split_planes((2.0 * w_out).contiguous(), P)                     # [P, D, di]
+    return lw
 
-    def __init__(self, hp: HParams, batch: int, T: int, device, mode: str):
+
+class LayerWorkspace:
+    """Activation buffers of the Mamba stack for ``batch`` sequences of ``L`` frames (M = batch*L rows)."""
+
+    def __init__(self, hp: HParams, batch: int, L: int, device, mode: str):
         P = MODES[mode]["planes"]
         xz_dt = torch.bfloat16 if MODES[mode]["xz_bf16"] else torch.float32
-        L = hp.frames(T)
         M = batch * L
-        N, D, di = hp.enc_dim, hp.d_model, hp.d_inner
+        D, di = hp.d_model, hp.d_inner
         nd = n_dbl_for(hp.dt_rank)
         e = lambda shape, dt: torch.empty(shape, dtype=dt, device=device)
-        self.batch, self.T, self.L, self.M = batch, T, L, M
-        self.mix = torch.zeros((batch, (T + 7) // 8 * 8), dtype=torch.float32, device=device)  # pitched rows
-        self.mix_w = e((M, N), torch.float32)
-        self.yn = e((P, M, N), torch.bfloat16)
+        self._e = e
+        self.batch, self.L, self.M = batch, L, M
         self.h = e((M, D), torch.float32)
         self.res = e((M, D), torch.float32)
         self.xn = e((P, M, D), torch.bfloat16)
@@ -97,9 +102,6 @@ class Workspace:
         self.dbl = e((M, 2 * nd), torch.float32)
         self.dtp = e((M, 2, 2, rp_for(hp.dt_rank)), torch.bfloat16)   # dt columns as hi | lo planes (scan MMA operand)
         self.y = e((P, M, 2 * di), torch.bfloat16)
-        self.sep = e((M, hp.n_spk * N), torch.float32)
-        self.frames = e((M, hp.n_spk, 16), torch.float32)
-        self.est = e((batch, T, hp.n_spk), torch.float32)
         # partial sums of res^2 per token entering the next norm; two buffers alternate (a GEMM reads one, the next writes one)
         self.rowsum = e((2, ops.rowsum_parts(D), M), torch.float32)
 
@@ -107,37 +109,42 @@ class Workspace:
         return sum(t.numel() * t.element_size() for t in vars(self).values() if isinstance(t, torch.Tensor))
 
 
-class SeparatorEngine:
-    """mix [B, T] fp32 (CUDA) -> est_source [B, T, n_spk] fp32, all in hand-written sm_100a kernels."""
+class Workspace(LayerWorkspace):
+    """Activation buffers for one (batch, T) shape of the whole separator; reused across layers and calls."""
 
-    def __init__(self, hp: HParams, sds: dict, device="cuda", mode: str = "fp32", use_graph: bool = True,
-                 fuse_norm: bool = False):
+    def __init__(self, hp: HParams, batch: int, T: int, device, mode: str):
+        super().__init__(hp, batch, hp.frames(T), device, mode)
+        P = MODES[mode]["planes"]
+        N, M, e = hp.enc_dim, self.M, self._e
+        self.T = T
+        self.mix = torch.zeros((batch, (T + 7) // 8 * 8), dtype=torch.float32, device=device)  # pitched rows
+        self.mix_w = e((M, N), torch.float32)
+        self.yn = e((P, M, N), torch.bfloat16)
+        self.sep = e((M, hp.n_spk * N), torch.float32)
+        self.frames = e((M, hp.n_spk, 16), torch.float32)
+        self.est = e((batch, T, hp.n_spk), torch.float32)
+
+
+class LayerPlan:
+    """What every driver of the Mamba stack shares: mode / direction settings and the per-layer kernel sequence
+    (``_layer`` = Add -> RMSNorm -> in_proj -> conv -> x_proj -> scan -> out_proj, 6 launches)."""
+
+    def _init_plan(self, hp: HParams, mode: str, device):
         if mode not in MODES:
             raise ValueError(f"mode must be one of {list(MODES)}")
         if not torch.cuda.is_available():
-            raise _lib.MtnError("SeparatorEngine needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+            raise _lib.MtnError(f"{type(self).__name__} needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         _lib.load()
         self.hp, self.mode, self.device = hp, mode, torch.device(device)
-        self.use_graph = use_graph
-        self.fuse_norm = fuse_norm
-        with torch.cuda.device(self.device):
-            self.w = PackedWeights(hp, sds, self.device, mode)
-        self._ws = {}
-        self._graphs = {}
+        self.P = MODES[mode]["planes"]
+        self.n_dbl = n_dbl_for(hp.dt_rank)
         self._prof = None
-        # enc, bottleneck, layers, (norm_f +) mask, decoder(2); fused: no norm kernels
-        self.launches_per_forward = (1 + 1 + hp.n_mamba * 5 + 1 + 2) if fuse_norm else (1 + 1 + hp.n_mamba * 6 + 2 + 2)
         # dt_proj inside the scan: tcgen05 MMA per 16-step tile, or R FMAs per (step, channel).  Measured on B200
         # (tools/scan_bench.py, DESIGN.md 4.1): the MMA form wins only where R is large and the FMA pipe is the
         # busier one (L hparams, fp32 mode: -6 %); elsewhere its shuffles / TMEM loads cost as much as the FMAs saved.
-        self.tc_dt = hp.dt_rank >= 32 and mode == "fp32"
-
-    # ------------------------------------------------------------------ building blocks
-    def workspace(self, batch, T) -> Workspace:
-        key = (batch, T)
-        if key not in self._ws:
-            self._ws[key] = Workspace(self.hp, batch, T, self.device, self.mode)
-        return self._ws[key]
+        self.tc_dt = hp.dt_rank >= 32 and mode == "fp32" and hp.bidirectional
+        self.ndir = 2 if hp.bidirectional else 1
+        self.dir_mask = 3 if hp.bidirectional else 1
 
     def _op(self, name, fn, *a, **k):
         """Launch one kernel; when a profiler is attached, bracket it with CUDA events on the launch stream."""
@@ -151,45 +158,129 @@ class SeparatorEngine:
         prof.append((name, e0, e1))
         return out
 
-    def _mixer_core(self, ws: Workspace, lw: dict):
-        """conv -> x_proj -> scan on ws.xz; leaves the gated scan output in ws.y."""
-        hp, P = self.hp, self.w.P
-        di, R, nd, M = hp.d_inner, hp.dt_rank, self.w.n_dbl, ws.M
+    def _mixer_core(self, ws: Workspace, lw: dict, st=None):
+        """conv -> x_proj -> scan on ws.xz; leaves the gated scan output in ws.y.
+        ``st`` (unidirectional streaming only): ``{"halo": [B,3,di] fp32, "h": [2,B,di,16] fp32}`` = the reference's
+        conv_state / ssm_state caches (bimamba.py:374-380), read as the history before this chunk and updated."""
+        hp, P = self.hp, self.P
+        di, R, nd, M = hp.d_inner, hp.dt_rank, self.n_dbl, ws.M
         op = self._op
-        op("conv_silu", ops.conv_silu, ws.xz, lw["conv_w"], lw["conv_b"], ws.batch, ws.L, di, P, u=ws.u)
+        ndir = self.ndir
+        op("conv_silu", ops.conv_silu, ws.xz, lw["conv_w"], lw["conv_b"], ws.batch, ws.L, di, P, u=ws.u,
+           halo_lo=None if st is None else st["halo"], dir_mask=self.dir_mask)
+        if st is not None:   # new conv history = last 3 conv inputs (pure data movement; fp32 like the kernel's halo operand)
+            xs = ws.xz.view(ws.batch, ws.L, 2 * di)[:, :, :di]
+            if "conv4" in st:   # the reference's 4-wide conv_state (bimamba.py:274-277); its oldest entry is never read again
+                st["conv4"].copy_(torch.cat([st["conv4"], xs.float()], dim=1)[:, -4:])
+            if ws.L >= 3:
+                st["halo"].copy_(xs[:, ws.L - 3:])
+            else:
+                st["halo"].copy_(torch.cat([st["halo"], xs.float()], dim=1)[:, -3:])
         if self.tc_dt:
             op("gemm_x_proj", ops.gemm, ws.u, lw["w_x"], M, nd, di, out=ws.dbl, groups=2, out_group_stride=nd,
                epilogue=_lib.EPI_XPROJ, epi_param=rp_for(R), aux=ws.dtp)
         else:
-            op("gemm_x_proj", ops.gemm, ws.u, lw["w_x"], M, nd, di, out=ws.dbl, groups=2, out_group_stride=nd)
+            op("gemm_x_proj", ops.gemm, ws.u, lw["w_x"], M, nd, di, out=ws.dbl, groups=ndir, out_group_stride=nd)
+        h = None if st is None else st["h"]   # each thread reads its own state slice first and overwrites it last: in place
         op("scan", ops.scan, ws.u, ws.dbl, ws.xz, di, lw["w_dt"], lw["dt_bias"], lw["A2"], lw["D"], ws.batch, ws.L, di, R,
-           y=ws.y, dtp=ws.dtp if self.tc_dt else None)
+           y=ws.y, dtp=ws.dtp if self.tc_dt else None, dir_mask=self.dir_mask, h_in=h, h_out=h)
 
-    def _layer(self, ws: Workspace, lw: dict, first: bool, taps=None):
-        hp, P = self.hp, self.w.P
+    def _layer(self, ws: Workspace, lw: dict, first: bool, taps=None, st=None):
+        hp, P = self.hp, self.P
         D, di, M = hp.d_model, hp.d_inner, ws.M
         op = self._op
         op("add_rmsnorm", ops.add_rmsnorm, ws.h, ws.res, not first, lw["norm"], P, xn=ws.xn)
         op("gemm_in_proj", ops.gemm, ws.xn, lw["w_in"], M, 2 * di, D, out=ws.xz, epilogue=_lib.EPI_INPROJ, epi_param=di,
            out_bf16=ws.xz.dtype == torch.bfloat16)
-        self._mixer_core(ws, lw)
-        op("gemm_out_proj", ops.gemm, ws.y, lw["w_out"], M, D, 2 * di, out=ws.h)
+        self._mixer_core(ws, lw, st)
+        op("gemm_out_proj", ops.gemm, ws.y, lw["w_out"], M, D, self.ndir * di, out=ws.h)
         if taps is not None:
             taps.append(ws.h.clone())
 
-    def _run_unfused(self, ws: Workspace, taps=None):
+
+class MambaStack(LayerPlan):
+    """``MambaBlocksSequential.forward`` (``modules/mamba_blocks.py:186-197``) as a stand-alone sequence model:
+    ``x [Bseq, L, D] fp32 -> [Bseq, L, D] fp32`` (blocks, final add, ``norm_f``).  This is how DPMamba uses the stack
+    (intra / inter models over many short sequences, ``hparams/WSJ0Mix/dpmamba_L.yaml:139-161``) and what the reference's
+    ``inference_params`` streaming drives.  ``sd`` = the stack's own state_dict (keys ``layers.<i>...``, ``norm_f.weight``)."""
+
+    def __init__(self, hp: HParams, sd: dict, device="cuda", mode: str = "fp32", prefix: str = ""):
+        self._init_plan(hp, mode, device)
+        f32 = lambda t: t.detach().to(device=self.device, dtype=torch.float32).contiguous()
+        with torch.cuda.device(self.device):
+            self.layers = [pack_layer(sd, f"{prefix}layers.{i}.", hp, self.P, self.device) for i in range(hp.n_mamba)]
+            self.norm_f = f32(sd[prefix + "norm_f.weight"])
+        self._ws = {}
+
+    def workspace(self, batch, L) -> LayerWorkspace:
+        key = (batch, L)
+        if key not in self._ws:
+            self._ws[key] = LayerWorkspace(self.hp, batch, L, self.device, self.mode)
+        return self._ws[key]
+
+    def run(self, ws: LayerWorkspace, out: torch.Tensor, states=None):
+        """The stack on ``ws.h`` (fp32 [M, D], consumed) -> ``out`` (fp32 [M, D]).  ``states``: per-layer streaming caches
+        (``{"halo", "h"}``, unidirectional only)."""
+        for i, lw in enumerate(self.layers):
+            self._layer(ws, lw, first=(i == 0), st=None if states is None else states[i])
+        self._op("add_rmsnorm", ops.add_rmsnorm, ws.h, ws.res, True, self.norm_f, self.P, xn=False, out_f32=out)
+        return out
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor, states=None) -> torch.Tensor:
+        if x.dim() != 3 or x.shape[-1] != self.hp.d_model or not x.is_cuda:
+            raise _lib.MtnError(f"MambaStack.forward expects a CUDA tensor [Bseq, L, {self.hp.d_model}]")
+        B, L, D = x.shape
+        ws = self.workspace(B, L)
+        ws.h.copy_(x.reshape(B * L, D))
+        return self.run(ws, torch.empty((B * L, D), dtype=torch.float32, device=x.device), states).view(B, L, D)
+
+    __call__ = forward
+
+
+class SeparatorEngine(LayerPlan):
+    """mix [B, T] fp32 (CUDA) -> est_source [B, T, n_spk] fp32, all in hand-written sm_100a kernels."""
+
+    def __init__(self, hp: HParams, sds: dict, device="cuda", mode: str = "fp32", use_graph: bool = True,
+                 fuse_norm: bool = False):
+        self._init_plan(hp, mode, device)
+        self.use_graph = use_graph
+        self.fuse_norm = fuse_norm
+        with torch.cuda.device(self.device):
+            self.w = PackedWeights(hp, sds, self.device, mode)
+        self._ws = {}
+        self._graphs = {}
+        # enc, bottleneck, layers, (norm_f +) mask, decoder(2); fused: no norm kernels
+        self.launches_per_forward = (1 + 1 + hp.n_mamba * 5 + 1 + 2) if fuse_norm else (1 + 1 + hp.n_mamba * 6 + 2 + 2)
+
+    # ------------------------------------------------------------------ building blocks
+    def workspace(self, batch, T) -> Workspace:
+        key = (batch, T)
+        if key not in self._ws:
+            self._ws[key] = Workspace(self.hp, batch, T, self.device, self.mode)
+        return self._ws[key]
+
+    def _run_unfused(self, ws: Workspace, taps=None, stream_state=None):
+        """``stream_state`` (``StreamingSeparator``): per-layer conv / ssm caches + the decoder's overlap-add tail; the
+        workspace then holds one chunk ([8 carried samples | 8*F new ones] -> F frames -> 8*F finalised samples)."""
         hp, w, P = self.hp, self.w, self.w.P
         N, D, M = hp.enc_dim, hp.d_model, ws.M
         op = self._op
+        ss = stream_state
         op("encoder_cln", ops.encoder_cln, ws.mix, w.w_enc, w.gamma, w.beta, P, mix_w=ws.mix_w, yn=ws.yn, T=ws.T)
         op("gemm_bottleneck", ops.gemm, ws.yn, w.w_bot, M, D, N, out=ws.h)
         for i, lw in enumerate(w.layers):
-            self._layer(ws, lw, first=(i == 0), taps=taps)
+            self._layer(ws, lw, first=(i == 0), taps=taps, st=None if ss is None else ss["layers"][i])
         op("add_rmsnorm", ops.add_rmsnorm, ws.h, ws.res, True, w.norm_f, P, xn=ws.xn)
         op("gemm_mask", ops.gemm, ws.xn, w.w_mask, M, hp.n_spk * N, D, out=ws.sep, epilogue=_lib.EPI_MASK, epi_param=N,
            aux=ws.mix_w)
-        op("decoder", ops.decoder, ws.sep, w.w_dec, ws.batch, ws.T, ws.L, N, hp.n_spk, est=ws.est, frames=ws.frames)
-        return ws.est
+        if ss is None:
+            op("decoder", ops.decoder, ws.sep, w.w_dec, ws.batch, ws.T, ws.L, N, hp.n_spk, est=ws.est, frames=ws.frames)
+            return ws.est
+        est = ss["est"]   # [B, 8*L, n_spk], contiguous, owned by the streaming driver
+        op("decoder", ops.decoder, ws.sep, w.w_dec, ws.batch, 8 * ws.L, ws.L, N, hp.n_spk, est=est, frames=ws.frames,
+           tail=ss["ola_tail"])
+        return est
 
     def _run(self, ws: Workspace, taps=None):
         if not self.fuse_norm or taps is not None:
@@ -207,7 +298,7 @@ class SeparatorEngine:
             op("gemm_in_proj", ops.gemm, ws.xn, lw["w_in_g"], M, 2 * di, D, out=ws.xz, epilogue=_lib.EPI_INPROJ,
                epi_param=di, out_bf16=ws.xz.dtype == torch.bfloat16, rowsq=ws.rowsum[cur], **norm)
             self._mixer_core(ws, lw)
-            op("gemm_out_proj", ops.gemm, ws.y, lw["w_out"], M, D, 2 * di, out=ws.res, epilogue=_lib.EPI_RESADD,
+            op("gemm_out_proj", ops.gemm, ws.y, lw["w_out"], M, D, self.ndir * di, out=ws.res, epilogue=_lib.EPI_RESADD,
                epi_param=1, out2=ws.xn, rowsum=ws.rowsum[1 - cur])
             cur = 1 - cur
         op("gemm_mask", ops.gemm, ws.xn, w.w_mask_g, M, hp.n_spk * N, D, out=ws.sep, epilogue=_lib.EPI_MASK, epi_param=N,

@@ -8,7 +8,7 @@ needs HyperPyYAML to read those, this package hard-codes the resolved values
 from __future__ import annotations
 
 import math
-from dataclasses import dataclass, asdict
+from dataclasses import dataclass, asdict, replace
 
 import torch
 
@@ -25,6 +25,7 @@ class HParams:
     d_conv: int = 4
     n_spk: int = 2
     sample_rate: int = 8000
+    bidirectional: bool = True   # False: causal stack of unidirectional mixers (mamba_blocks.py:128, `mamba_ssm.Mamba`)
 
     @property
     def stride(self) -> int:
@@ -43,6 +44,10 @@ class HParams:
 
     def as_dict(self):
         return asdict(self)
+
+    def causal(self) -> "HParams":
+        """Same sizes with ``bidirectional=False`` (the streaming-capable variant)."""
+        return replace(self, name=self.name + "_causal", bidirectional=False)
 
 
 CONFIGS = {
@@ -88,10 +93,11 @@ def init_state_dicts(hp: HParams, seed: int = 1234, trained_like: bool = True):
         A_log = torch.log(torch.arange(1, Ns + 1, dtype=torch.float32)).repeat(di, 1)
         m[p + "mixer.A_log"] = A_log.clone()
         m[p + "mixer.D"] = torch.ones(di)
-        m[p + "mixer.A_b_log"] = A_log.clone()
-        m[p + "mixer.D_b"] = torch.ones(di)
+        if hp.bidirectional:
+            m[p + "mixer.A_b_log"] = A_log.clone()
+            m[p + "mixer.D_b"] = torch.ones(di)
         m[p + "mixer.in_proj.weight"] = linear_w(2 * di, D)
-        for sfx in ("", "_b"):
+        for sfx in (("", "_b") if hp.bidirectional else ("",)):
             m[p + f"mixer.conv1d{sfx}.weight"] = uni((di, 1, W), 1.0 / math.sqrt(W))
             m[p + f"mixer.conv1d{sfx}.bias"] = uni((di,), 1.0 / math.sqrt(W))
             m[p + f"mixer.x_proj{sfx}.weight"] = linear_w(R + 2 * Ns, di)

@@ -57,13 +57,17 @@ class _SBConv1d(nn.Module):
 
 
 class Mamba(nn.Module):
-    """Bidirectional ("v2") Mamba mixer parameters (``modules/mamba/bimamba.py:40-174``)."""
+    """Mamba mixer parameters.  ``bimamba_type="v2"``: the bidirectional mixer of ``modules/mamba/bimamba.py:40-174``.
+    ``bimamba_type="none"``: the unidirectional ``mamba_ssm.Mamba`` [3P] that ``modules/mamba_blocks.py:128`` selects for
+    ``bidirectional=False`` -- same parameters without the ``*_b`` set; it also offers the reference's single-token
+    decode interface (``step`` / ``allocate_inference_cache``, vendored copy at ``bimamba.py:320-380``)."""
 
     def __init__(self, d_model, d_state=16, d_conv=4, expand=2, dt_rank="auto", conv_bias=True, bias=False,
                  layer_idx=None, bimamba_type="v2", if_devide_out=True, init_layer_scale=None, **_ignored):
         super().__init__()
-        if bimamba_type != "v2":
+        if bimamba_type not in ("v2", "none"):
             _unsupported(f"bimamba_type={bimamba_type!r}")
+        self.bimamba_type = bimamba_type
         if d_state != 16 or d_conv != 4:
             _unsupported(f"d_state={d_state}, d_conv={d_conv} (kernels are specialised for 16 / 4)")
         if bias or not conv_bias or not if_devide_out or init_layer_scale is not None:
@@ -80,12 +84,66 @@ class Mamba(nn.Module):
         A_log = torch.log(torch.arange(1, d_state + 1, dtype=torch.float32)).repeat(di, 1)
         self.A_log = nn.Parameter(A_log.clone())
         self.D = nn.Parameter(torch.ones(di))
-        self.A_b_log = nn.Parameter(A_log.clone())
-        self.conv1d_b = nn.Conv1d(di, di, d_conv, groups=di, padding=d_conv - 1, bias=True)
-        self.x_proj_b = nn.Linear(di, R + 2 * d_state, bias=False)
-        self.dt_proj_b = nn.Linear(R, di, bias=True)
-        self.D_b = nn.Parameter(torch.ones(di))
+        if bimamba_type == "v2":
+            self.A_b_log = nn.Parameter(A_log.clone())
+            self.conv1d_b = nn.Conv1d(di, di, d_conv, groups=di, padding=d_conv - 1, bias=True)
+            self.x_proj_b = nn.Linear(di, R + 2 * d_state, bias=False)
+            self.dt_proj_b = nn.Linear(R, di, bias=True)
+            self.D_b = nn.Parameter(torch.ones(di))
         self.out_proj = nn.Linear(di, d_model, bias=False)
+        self.__dict__["_packed"] = None
+
+    # ------------------------------------------------------------------ single-token decode (unidirectional only)
+    def allocate_inference_cache(self, batch_size, max_seqlen=None, dtype=None, **kwargs):
+        """``(conv_state [B, di, d_conv], ssm_state [B, di, d_state])`` zeros, as ``bimamba.py:368-380``."""
+        dev = self.out_proj.weight.device
+        return (torch.zeros(batch_size, self.d_inner, self.d_conv, device=dev, dtype=dtype or torch.float32),
+                torch.zeros(batch_size, self.d_inner, self.d_state, device=dev, dtype=dtype or torch.float32))
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        super()._load_from_state_dict(*args, **kwargs)
+        self.__dict__["_packed"] = None
+
+    def _apply(self, fn, *a, **k):
+        out = super()._apply(fn, *a, **k)
+        self.__dict__["_packed"] = None
+        return out
+
+    @torch.no_grad()
+    def step(self, hidden_states, conv_state, ssm_state):
+        """``Mamba.step`` (``bimamba.py:320-372``): one token ``[B, 1, D]``; ``conv_state`` / ``ssm_state`` (fp32) are
+        updated in place; returns ``(out [B, 1, D], conv_state, ssm_state)``.  Runs the same kernels as the sequence
+        forward on a 1-frame chunk (in_proj, conv with the cached history, x_proj, scan seeded with the state, out_proj)."""
+        if self.bimamba_type != "none":
+            _unsupported("step() on the bidirectional mixer (the backward direction needs the future)")
+        if hidden_states.dim() != 3 or hidden_states.shape[1] != 1:
+            raise AssertionError("Only support decoding with 1 token at a time for now")   # bimamba.py:322
+        if conv_state.dtype != torch.float32 or ssm_state.dtype != torch.float32:
+            _unsupported("inference caches other than fp32")
+        from .engine import pack_layer
+        B, di, R, D = hidden_states.shape[0], self.d_inner, self.dt_rank, self.d_model
+        dev = hidden_states.device
+        hp = HParams("step", D, D, 1, d_state=self.d_state, expand=self.expand, d_conv=self.d_conv, bidirectional=False)
+        lw = self.__dict__.get("_packed")
+        if lw is None:
+            sd = {"l.mixer." + k: v for k, v in self.state_dict().items()}
+            sd["l.norm.weight"] = torch.ones(D, device=dev)
+            lw = pack_layer(sd, "l.", hp, 2, dev)
+            self.__dict__["_packed"] = lw
+        nd = ops.n_dbl_for(R)
+        xn = ops.split_planes(hidden_states.reshape(B, D).float().contiguous(), 2)
+        xz = ops.gemm(xn, lw["w_in"], B, 2 * di, D, epilogue=_lib.EPI_INPROJ, epi_param=di)
+        halo = conv_state[:, :, 1:].transpose(1, 2).contiguous()                    # the 3 inputs before this token
+        u = ops.conv_silu(xz, lw["conv_w"], lw["conv_b"], B, 1, di, 2, halo_lo=halo, dir_mask=1)
+        conv_state.copy_(torch.cat([conv_state[:, :, 1:], xz[:, :di].unsqueeze(-1)], dim=-1))   # bimamba.py:328-329
+        dbl = torch.empty((B, 2 * nd), dtype=torch.float32, device=dev)
+        ops.gemm(u, lw["w_x"], B, nd, di, out=dbl, groups=1, out_group_stride=nd)
+        h = torch.zeros((2, B, di, 16), dtype=torch.float32, device=dev)
+        h[0].copy_(ssm_state)
+        y = ops.scan(u, dbl, xz, di, lw["w_dt"], lw["dt_bias"], lw["A2"], lw["D"], B, 1, di, R, dir_mask=1, h_in=h, h_out=h)
+        ssm_state.copy_(h[0])
+        out = ops.gemm(y, lw["w_out"], B, D, di)
+        return out.view(B, 1, D).to(hidden_states.dtype), conv_state, ssm_state
 
 
 class Block(nn.Module):
@@ -97,6 +155,45 @@ class Block(nn.Module):
         self.norm = norm_cls(dim)
 
 
+def _stack_forward(self, x, keep_to=None, inference_params=None):
+    """``MambaBlocksSequential.forward`` (``modules/mamba_blocks.py:186-212``): ``[B, L, D] -> [B, L, D]``.
+    ``inference_params`` (unidirectional stacks): an object with ``seqlen_offset`` and ``key_value_memory_dict`` as the
+    reference's mixers use it (``bimamba.py:186-190,382-404``): layer i's ``(conv_state [B, di, 4], ssm_state [B, di, 16])``
+    are created on first use, read as the history of this call and updated in place -- prefill and ``step`` are the same
+    chunk kernels here, so any number of tokens per call is accepted."""
+    from .engine import MambaStack
+    cache = self.__dict__.setdefault("_stack_cache", {})
+    dev = self.norm_f.weight.device
+    if "s" not in cache:
+        D = self.norm_f.weight.shape[0]
+        hp = HParams("stack", D, D, self.n_mamba, bidirectional=self.bidirectional)
+        cache["s"] = MambaStack(hp, self.state_dict(), device=dev, mode="fp32")
+    stack = cache["s"]
+    B, L, D = x.shape
+    states = None
+    if inference_params is not None:
+        if self.bidirectional:
+            _unsupported("inference_params with bidirectional=True (the backward direction needs the future)")
+        kv = inference_params.key_value_memory_dict
+        di = stack.hp.d_inner
+        states = []
+        for i in range(self.n_mamba):
+            if i not in kv:
+                kv[i] = (torch.zeros(B, di, 4, device=dev), torch.zeros(B, di, 16, device=dev))
+            cs, ss = kv[i]
+            conv4 = cs.transpose(1, 2).contiguous().float()
+            h = torch.zeros(2, B, di, 16, device=dev)
+            h[0].copy_(ss)
+            states.append({"conv4": conv4, "halo": conv4[:, 1:].contiguous(), "h": h})
+    out = stack.forward(x.float().contiguous(), states)
+    if states is not None:
+        for i, st in enumerate(states):
+            cs, ss = inference_params.key_value_memory_dict[i]
+            cs.copy_(st["conv4"].transpose(1, 2))
+            ss.copy_(st["h"][0])
+    return out.to(x.dtype)
+
+
 class MambaBlocksSequential(nn.Module):
     """``modules/mamba_blocks.py:87-212`` (parameters + init); forward runs inside the fused engine."""
 
@@ -104,28 +201,38 @@ class MambaBlocksSequential(nn.Module):
                  conv_bias=True, bias=False, fused_add_norm=True, rms_norm=False, norm_epsilon=1e-5,
                  initializer_cfg=None, residual_in_fp32=False):
         super().__init__()
-        if not bidirectional:
-            _unsupported("bidirectional=False (external mamba_ssm.Mamba)")
         if not rms_norm:
             _unsupported("rms_norm=False (nn.LayerNorm blocks)")
         if norm_epsilon != 1e-5:
             _unsupported("norm_epsilon != 1e-5")
         # fused_add_norm only selects between two mathematically identical reference code paths
         # (mamba_blocks.py:195-210); residual_in_fp32: the residual stream here is always fp32.
-        self.n_mamba = n_mamba
+        self.n_mamba, self.bidirectional = n_mamba, bidirectional
+        btype = "v2" if bidirectional else "none"      # mamba_blocks.py:128: BiMamba if bidirectional else mamba_ssm.Mamba
         mk = lambda i: Block(d_model, lambda d: Mamba(d, d_state=d_state, d_conv=d_conv, expand=expand, dt_rank=dt_rank,
-                                                      conv_bias=conv_bias, bias=bias, layer_idx=i, bimamba_type="v2"))
+                                                      conv_bias=conv_bias, bias=bias, layer_idx=i, bimamba_type=btype))
         self.layers = nn.Sequential(*[mk(i) for i in range(n_mamba)])
         self.norm_f = RMSNorm(d_model, eps=norm_epsilon)
         with torch.no_grad():  # out_proj rescale, mamba_blocks.py:76-84
             for blk in self.layers:
                 nn.init.kaiming_uniform_(blk.mixer.out_proj.weight, a=math.sqrt(5))
                 blk.mixer.out_proj.weight /= math.sqrt(n_mamba)
-                for dtp in (blk.mixer.dt_proj, blk.mixer.dt_proj_b):  # bimamba.py:101-118
+                for dtp in ((blk.mixer.dt_proj, blk.mixer.dt_proj_b) if bidirectional else (blk.mixer.dt_proj,)):  # bimamba.py:101-118
                     R = dtp.weight.shape[1]
                     nn.init.uniform_(dtp.weight, -R ** -0.5, R ** -0.5)
                     dt = torch.exp(torch.rand(dtp.bias.shape[0]) * (math.log(0.1) - math.log(1e-3)) + math.log(1e-3)).clamp(min=1e-4)
                     dtp.bias.copy_(dt + torch.log(-torch.expm1(-dt)))
+
+    forward = torch.no_grad()(_stack_forward)
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        super()._load_from_state_dict(*args, **kwargs)
+        self.__dict__["_stack_cache"] = {}
+
+    def _apply(self, fn, *a, **k):
+        out = super()._apply(fn, *a, **k)
+        self.__dict__["_stack_cache"] = {}
+        return out
 
 
 class _EngineOwner(nn.Module):
@@ -207,7 +314,8 @@ class MaskNet(_EngineOwner):
                                                fused_add_norm=fused_add_norm, rms_norm=rms_norm,
                                                residual_in_fp32=residual_in_fp32, conv_bias=True, bias=False)
         self.mask_conv1x1 = _SBConv1d(bot_dim, n_spk * enc_dim)
-        self.hp = HParams("custom", enc_dim, d_model, n_mamba, d_state=d_state, expand=expand, d_conv=d_conv, n_spk=n_spk)
+        self.hp = HParams("custom", enc_dim, d_model, n_mamba, d_state=d_state, expand=expand, d_conv=d_conv, n_spk=n_spk,
+                          bidirectional=bidirectional)
         self._invalidate()
 
     def engine(self, encoder_sd=None, decoder_sd=None, mode=None, use_graph=True) -> SeparatorEngine:
@@ -253,7 +361,7 @@ class MambaTasNetSeparator(_EngineOwner):
     def from_hparams(cls, hp: HParams, mode="fp32", use_graph=True):
         enc = Encoder(hp.kernel_size, hp.enc_dim)
         mask = MaskNet(hp.enc_dim, hp.d_model, n_spk=hp.n_spk, n_mamba=hp.n_mamba, d_model=hp.d_model,
-                       d_state=hp.d_state, expand=hp.expand, d_conv=hp.d_conv, mode=mode)
+                       d_state=hp.d_state, expand=hp.expand, d_conv=hp.d_conv, mode=mode, bidirectional=hp.bidirectional)
         dec = Decoder(hp.enc_dim, 1, hp.kernel_size, hp.stride, bias=False)
         return cls(enc, mask, dec, mode=mode, use_graph=use_graph)
 

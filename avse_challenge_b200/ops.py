@@ -113,19 +113,24 @@ def rowsum_parts(N: int) -> int:
     return int(_lib.load().mtn_gemm_rowsum_parts(N))
 
 
-def add_rmsnorm(h, res, res_valid, g, planes, eps=1e-5, xn=None):
+def add_rmsnorm(h, res, res_valid, g, planes, eps=1e-5, xn=None, out_f32=None):
+    """``out_f32`` (fp32 [M, D]): also (or, with ``xn=False``, only) write the normalised rows in fp32."""
     _req_cuda(res, g)
     M, D = res.shape
     if xn is None:
         xn = torch.empty((planes, M, D), dtype=torch.bfloat16, device=res.device)
-    check(_lib.load().mtn_add_rmsnorm_fwd(ptr(h), ptr(res), int(res_valid), ptr(g), ptr(xn), M, D, planes, eps,
-                                          _stream()), "mtn_add_rmsnorm_fwd")
-    return xn
+    elif xn is False:
+        assert out_f32 is not None
+        xn = None
+    check(_lib.load().mtn_add_rmsnorm_out_fwd(ptr(h), ptr(res), int(res_valid), ptr(g), ptr(xn), ptr(out_f32), M, D, planes,
+                                              eps, _stream()), "mtn_add_rmsnorm_out_fwd")
+    return xn if xn is not None else out_f32
 
 
-def conv_silu(xz, conv_w, conv_b, batch, L, di, planes, u=None, halo_lo=None, halo_hi=None):
+def conv_silu(xz, conv_w, conv_b, batch, L, di, planes, u=None, halo_lo=None, halo_hi=None, dir_mask=3):
     """xz [M, >= di] (fp32 or bf16; xs = first di columns) -> u planes [P, M, 2*di].
-    ``halo_lo`` / ``halo_hi`` (fp32 [batch, 3, di]): xs rows just before / after this time chunk (None = zero pad)."""
+    ``halo_lo`` / ``halo_hi`` (fp32 [batch, 3, di]): xs rows just before / after this time chunk (None = zero pad).
+    ``dir_mask``: 1 = forward half only (unidirectional stacks; the backward columns of ``u`` are left untouched)."""
     _req_cuda(xz, conv_w, conv_b, halo_lo, halo_hi)
     M = batch * L
     if u is None:
@@ -133,9 +138,9 @@ def conv_silu(xz, conv_w, conv_b, batch, L, di, planes, u=None, halo_lo=None, ha
     for h in (halo_lo, halo_hi):
         if h is not None:
             assert h.dtype == torch.float32 and h.is_contiguous() and tuple(h.shape) == (batch, 3, di)
-    check(_lib.load().mtn_conv_silu_halo_fwd(ptr(xz), xz.stride(0), int(xz.dtype == torch.bfloat16), ptr(conv_w),
-                                             ptr(conv_b), ptr(u), u.shape[1], ptr(halo_lo), ptr(halo_hi), batch, L, di,
-                                             planes, _stream()), "mtn_conv_silu_halo_fwd")
+    check(_lib.load().mtn_conv_silu_dir_fwd(ptr(xz), xz.stride(0), int(xz.dtype == torch.bfloat16), ptr(conv_w),
+                                            ptr(conv_b), ptr(u), u.shape[1], ptr(halo_lo), ptr(halo_hi), batch, L, di,
+                                            planes, dir_mask, _stream()), "mtn_conv_silu_dir_fwd")
     return u
 
 
@@ -171,12 +176,15 @@ def fold_states(h_end, sum_delta, A2, g0, n_out, *, h0=None, want_final=False, d
     return h_in, h_final
 
 
-def decoder(sep, w_dec, batch, T, L, N, n_spk=2, est=None, frames=None):
-    _req_cuda(sep, w_dec)
+def decoder(sep, w_dec, batch, T, L, N, n_spk=2, est=None, frames=None, tail=None):
+    """``tail`` (fp32 [batch, n_spk, 8], in/out): streaming overlap-add carry (then ``T`` must be ``8 * L``)."""
+    _req_cuda(sep, w_dec, tail)
     if frames is None:
         frames = torch.empty((batch * L, n_spk, 16), dtype=torch.float32, device=sep.device)
     if est is None:
         est = torch.empty((batch, T, n_spk), dtype=torch.float32, device=sep.device)
-    check(_lib.load().mtn_decoder_fwd(ptr(sep), ptr(w_dec), ptr(frames), ptr(est), batch, T, L, N, n_spk, _stream()),
-          "mtn_decoder_fwd")
+    if tail is not None:
+        assert tail.dtype == torch.float32 and tail.is_contiguous() and tuple(tail.shape) == (batch, n_spk, 8)
+    check(_lib.load().mtn_decoder_stream_fwd(ptr(sep), ptr(w_dec), ptr(frames), ptr(est), ptr(tail), batch, T, L, N, n_spk,
+                                             _stream()), "mtn_decoder_stream_fwd")
     return est

@@ -134,6 +134,12 @@ int mtn_gemm_rowsum_parts(int N);
 int mtn_add_rmsnorm_fwd(const float* h, float* res, int res_valid, const float* g, void* xn_planes, int M, int D,
                         int planes, float eps, mtn_stream_t stream);
 
+/* Same; additionally (or instead: xn_planes may be NULL) writes the normalised rows as fp32 [M][D].  This is the output
+ * of a whole MambaBlocksSequential.forward (modules/mamba_blocks.py:196-197) when the stack is used as a stand-alone
+ * sequence model, e.g. as the intra / inter model of DPMamba (hparams/WSJ0Mix/dpmamba_L.yaml:139-161). */
+int mtn_add_rmsnorm_out_fwd(const float* h, float* res, int res_valid, const float* g, void* xn_planes, float* out_f32,
+                            int M, int D, int planes, float eps, mtn_stream_t stream);
+
 /* xs = xz[:, 0:di] (fp32 or bf16, row stride ldxz) -> u planes [P][M][2*di]:
  * u_fwd[t] = silu(b + sum_k w[k]*xs[t-3+k]),  u_bwd[t] = silu(b' + sum_k w'[k]*xs[t+3-k]), zero padded per
  * utterance.  conv_w [2][di][4], conv_b [2][di]. */
@@ -147,6 +153,14 @@ int mtn_conv_silu_fwd(const void* xz, int ldxz, int xz_bf16, const float* conv_w
 int mtn_conv_silu_halo_fwd(const void* xz, int ldxz, int xz_bf16, const float* conv_w, const float* conv_b,
                            void* u_planes, int u_rows /* rows allocated per plane, >= batch*L */, const float* halo_lo,
                            const float* halo_hi, int batch, int L, int di, int planes, mtn_stream_t stream);
+
+/* Same with a direction mask (bit0 forward, bit1 backward): a unidirectional stack (`bidirectional=False`,
+ * modules/mamba_blocks.py:128 -> mamba_ssm.Mamba; the vendored non-fused branch modules/mamba/bimamba.py:271-285) runs
+ * dir_mask = 1, conv_w/conv_b then only need their first [di] rows.  With halo_lo = the last 3 conv inputs of the previous
+ * chunk this is also the streaming form of the reference's conv_state cache (bimamba.py:274-277, step :327-333). */
+int mtn_conv_silu_dir_fwd(const void* xz, int ldxz, int xz_bf16, const float* conv_w, const float* conv_b,
+                          void* u_planes, int u_rows, const float* halo_lo, const float* halo_hi, int batch, int L,
+                          int di, int planes, int dir_mask, mtn_stream_t stream);
 
 int mtn_scan_fwd(const mtn_scan_args* args, mtn_stream_t stream);
 
@@ -164,6 +178,13 @@ int mtn_fold_states_fwd(const float* h_end, const float* sum_delta, const float*
  * frames: scratch fp32 [batch*L][n_spk][16]. */
 int mtn_decoder_fwd(const float* sep, const float* w_dec /*[N][16]*/, float* frames, float* est, int batch, int T, int L,
                     int N, int n_spk, mtn_stream_t stream);
+
+/* Streaming decoder: the chunk's L frames finalise est [batch][T = 8*L][n_spk]; `tail` fp32 [batch][n_spk][8] holds the
+ * second half of the previous chunk's last frame on entry (zeros before the first chunk) and of this chunk's last frame on
+ * return.  tail == NULL is mtn_decoder_fwd.  Concatenating the chunks' outputs (plus the final tail) reproduces the
+ * one-shot ConvTranspose1d overlap-add bit for bit. */
+int mtn_decoder_stream_fwd(const float* sep, const float* w_dec, float* frames, float* est, float* tail, int batch, int T,
+                           int L, int N, int n_spk, mtn_stream_t stream);
 
 /* ChannelwiseLayerNorm alone (MaskNet called on an externally produced mix_w): x fp32 [M][N] -> yn planes */
 int mtn_cln_fwd(const float* x, const float* gamma, const float* beta, void* yn_planes, int M, int N, int planes,

@@ -54,10 +54,10 @@ def golden_scan():
                         out_reverse=out_b.numpy())
 
 
-def golden_forward(name, T, batch, seed, tag, own_init):
-    hp = CONFIGS[name]
+def golden_forward(name, T, batch, seed, tag, own_init, bidirectional=True):
+    hp = CONFIGS[name] if bidirectional else CONFIGS[name].causal()
     ref = ref_shims.load_reference()
-    enc, mask, dec = ref_shims.build_reference_model(hp.as_dict(), seed=seed)
+    enc, mask, dec = ref_shims.build_reference_model(hp.as_dict(), seed=seed, bidirectional=bidirectional)
     if own_init:  # perturbed ("trained-like") weights, loaded strict into the reference modules
         sds = init_state_dicts(hp, seed)
         enc.load_state_dict(sds["encoder"], strict=True)
@@ -87,6 +87,35 @@ def golden_forward(name, T, batch, seed, tag, own_init):
     np.savez_compressed(os.path.join(OUT, f"forward_{tag}.npz"), **arrs)
     print(tag, "est rms", float(est.pow(2).mean().sqrt()), "file",
           os.path.getsize(os.path.join(OUT, f"forward_{tag}.npz")) // 1024, "KiB")
+    return enc, mask, dec
+
+
+def golden_stream(mask, tag):
+    """Streaming through the reference's own inference caches: ``MambaBlocksSequential.forward(x, inference_params)``
+    (``modules/mamba_blocks.py:186-193``) -> prefill branch ``bimamba.py:271-304`` on the first ``L0`` tokens, then
+    ``Mamba.step`` (``:320-372``) one token at a time.  Stored: input, the one-shot output, the streamed output and the
+    final conv / ssm caches of every layer.  Weights are the ``masknet/mamba_net.*`` entries of forward_<tag>.npz."""
+    ref = ref_shims.load_reference()
+    net = mask.mamba_net
+    g = torch.Generator().manual_seed(4321)
+    B, L, L0 = 2, 41, 9
+    h = torch.randn(B, L, net.norm_f.weight.shape[0], generator=g)
+    with torch.no_grad():
+        full = net(h)
+        ip = ref.InferenceParams()
+        outs = [net(h[:, :L0], inference_params=ip)]
+        ip.seqlen_offset = L0
+        for t in range(L0, L):
+            outs.append(net(h[:, t:t + 1], inference_params=ip))
+            ip.seqlen_offset += 1
+        streamed = torch.cat(outs, dim=1)
+    assert (streamed - full).abs().max() < 1e-5
+    arrs = {"h": h.numpy(), "full": full.numpy(), "streamed": streamed.numpy(), "L0": np.int64(L0)}
+    for i, (cs, ss) in ip.key_value_memory_dict.items():
+        arrs[f"conv_state/{i}"] = cs.numpy()
+        arrs[f"ssm_state/{i}"] = ss.numpy()
+    np.savez_compressed(os.path.join(OUT, f"stream_{tag}.npz"), **arrs)
+    print(f"stream_{tag}.npz", "max |streamed - one-shot|", float((streamed - full).abs().max()))
 
 
 def golden_si_snr():
@@ -117,6 +146,8 @@ def main():
     golden_forward("tiny", T=2000, batch=2, seed=1234, tag="tiny_refinit", own_init=False)
     golden_forward("tiny", T=1003, batch=3, seed=77, tag="tiny_trained", own_init=True)
     golden_si_snr()
+    _, mask, _ = golden_forward("tiny", T=1203, batch=2, seed=55, tag="tiny_causal", own_init=True, bidirectional=False)
+    golden_stream(mask, "tiny_causal")
 
 
 if __name__ == "__main__":

@@ -130,13 +130,44 @@ def load_reference():
     from modules.mamba import selective_scan_interface as ssi  # noqa: E402
 
     def _fwd(u, delta, A, B, C, D, z, delta_bias, delta_softplus):
-        out_z = ssi.selective_scan_ref(u, delta, A, B, C, D, z, delta_bias, delta_softplus)
-        return out_z, torch.empty(0), out_z
+        out_z, last = ssi.selective_scan_ref(u, delta, A, B, C, D, z, delta_bias, delta_softplus, True)
+        # `x` = the kernel's per-chunk running states [B, D, n_chunks, 2*Ns]; SelectiveScanFn.forward reads the final
+        # state from x[:, :, -1, 1::2] (selective_scan_interface.py:46)
+        x = torch.zeros(last.shape[0], last.shape[1], 1, 2 * last.shape[2], dtype=last.dtype)
+        x[:, :, 0, 1::2] = last
+        return out_z, x, out_z
 
     ssc.fwd = _fwd
+    from modules.mamba.bimamba import Mamba as BiMamba, Block  # noqa: E402
+
+    class UniMamba(BiMamba):
+        """Stand-in for ``mamba_ssm.Mamba`` (mamba-ssm 1.1.3.post1 ``modules/mamba_simple.py``, not vendored; used by
+        ``modules/mamba_blocks.py:128`` when ``bidirectional=False``).  The vendored ``bimamba.Mamba`` is a modified
+        copy of that class: its non-fused branch (``bimamba.py:271-310``) and ``step`` (``:320-372``) are the
+        unidirectional mixer verbatim, using only the forward-direction parameters.  So: construct the vendored class,
+        drop the ``*_b`` parameters (state_dict keys then equal ``mamba_ssm.Mamba``'s), and force the non-fused branch."""
+
+        def __init__(self, d_model, d_state=16, d_conv=4, expand=2, dt_rank="auto", conv_bias=True, bias=False,
+                     use_fast_path=True, layer_idx=None, device=None, dtype=None, **kw):
+            super().__init__(d_model, d_state=d_state, d_conv=d_conv, expand=expand, dt_rank=dt_rank,
+                             conv_bias=conv_bias, bias=bias, layer_idx=layer_idx, device=device, dtype=dtype,
+                             bimamba_type="v2")
+            for name in ("A_b_log", "conv1d_b", "x_proj_b", "dt_proj_b", "D_b"):
+                delattr(self, name)
+            self.use_fast_path = False   # bimamba.py:203 -> falls through to the unidirectional branch at :271
+
+    sys.modules["mamba_ssm"].Mamba = UniMamba
     from modules.mamba_masknet import MaskNet  # noqa: E402
     from modules.mamba_blocks import MambaBlocksSequential  # noqa: E402
-    from modules.mamba.bimamba import Mamba as BiMamba, Block  # noqa: E402
+
+    class InferenceParams:
+        """mamba_ssm.utils.generation.InferenceParams restricted to the two fields the vendored code reads
+        (``bimamba.py:186-190,375-404``)."""
+
+        def __init__(self, max_seqlen=0, max_batch_size=0):
+            self.max_seqlen, self.max_batch_size = max_seqlen, max_batch_size
+            self.seqlen_offset = 0
+            self.key_value_memory_dict = {}
 
     class RefEncoder(nn.Module):
         """speechbrain dual_path.Encoder == baseline/avse2/model.py:14-24 (in-repo twin)."""
@@ -176,12 +207,12 @@ def load_reference():
     _loaded = types.SimpleNamespace(
         MaskNet=MaskNet, MambaBlocksSequential=MambaBlocksSequential, BiMamba=BiMamba, Block=Block,
         selective_scan_ref=ssi.selective_scan_ref, Encoder=RefEncoder, Decoder=RefDecoder,
-        compute_forward=compute_forward, ssi=ssi,
+        compute_forward=compute_forward, ssi=ssi, UniMamba=UniMamba, InferenceParams=InferenceParams,
     )
     return _loaded
 
 
-def build_reference_model(hp, seed=1234):
+def build_reference_model(hp, seed=1234, bidirectional=True):
     """Construct reference Encoder/MaskNet/Decoder with the reference's own init under a seed.
 
     ``hp`` needs: enc_dim, d_model, n_mamba, kernel_size."""
@@ -189,7 +220,7 @@ def build_reference_model(hp, seed=1234):
     torch.manual_seed(seed)
     enc = ref.Encoder(kernel_size=hp["kernel_size"], out_channels=hp["enc_dim"])
     mask = ref.MaskNet(enc_dim=hp["enc_dim"], bot_dim=hp["d_model"], n_spk=2, n_mamba=hp["n_mamba"],
-                       bidirectional=True, d_model=hp["d_model"], d_state=16, expand=2, d_conv=4,
+                       bidirectional=bidirectional, d_model=hp["d_model"], d_state=16, expand=2, d_conv=4,
                        fused_add_norm=False, rms_norm=True, residual_in_fp32=False)
     dec = ref.Decoder(in_channels=hp["enc_dim"], out_channels=1, kernel_size=hp["kernel_size"],
                       stride=hp["kernel_size"] // 2, bias=False)

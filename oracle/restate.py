@@ -161,41 +161,100 @@ def selective_scan(u, delta_pre, A, Bm, Cm, D, z, delta_bias, reverse=False, h_i
     return y, h
 
 
-def mixer_fwd(x, sd, prefix, scan_impl="auto"):
-    """Bidirectional ("v2") Mamba mixer (``modules/mamba/bimamba.py:176-253`` +
-    ``MambaInnerFnNoOutProj.forward`` ``selective_scan_interface.py:164-229``), ``[B,L,D]->[B,L,D]``."""
+def mixer_fwd(x, sd, prefix, scan_impl="auto", state=None):
+    """Mamba mixer, ``[B,L,D]->[B,L,D]``.  Bidirectional ("v2", when the ``*_b`` parameters exist):
+    ``modules/mamba/bimamba.py:176-253`` + ``MambaInnerFnNoOutProj.forward`` ``selective_scan_interface.py:164-229``.
+    Unidirectional (no ``*_b`` parameters; ``mamba_ssm.Mamba`` via ``modules/mamba_blocks.py:128``): the vendored
+    non-fused branch ``bimamba.py:271-310`` -- same conv / x_proj / dt_proj / scan, no 0.5 averaging.
+
+    ``state`` (unidirectional only): dict with ``conv`` [B, di, 4] (last 4 inputs of the conv, oldest first -- the
+    reference's ``conv_state`` layout, ``bimamba.py:274-277,374-380``) and ``ssm`` [B, di, Ns]; read as the history
+    before this call and updated in place, which is what prefill (``:274-277,302-304``) followed by ``step``
+    (``:320-372``) does one token at a time."""
     p = prefix
     W_in = sd[p + "in_proj.weight"]
     di = W_in.shape[0] // 2
     xz = _mm(x, W_in)                                                       # bimamba.py:192-196
     xs, z = xz[..., :di], xz[..., di:]                                     # ssi.py:180 (x first, z last)
+    bidir = (p + "A_b_log") in sd
+    if state is not None and bidir:
+        raise ValueError("streaming state exists only for the unidirectional mixer")
     outs = []
-    for sfx, rev in (("", False), ("_b", True)):
+    for sfx, rev in ((("", False), ("_b", True)) if bidir else (("", False),)):
         conv_w, conv_b = sd[p + f"conv1d{sfx}.weight"], sd[p + f"conv1d{sfx}.bias"]
         W_x, W_dt, b_dt = sd[p + f"x_proj{sfx}.weight"], sd[p + f"dt_proj{sfx}.weight"], sd[p + f"dt_proj{sfx}.bias"]
         A = -torch.exp(sd[p + ("A_log" if not rev else "A_b_log")].float())   # bimamba.py:200,222
         D = sd[p + ("D" if not rev else "D_b")].float()
         R = W_dt.shape[1]
         Ns = A.shape[1]
-        u = causal_conv_silu(xs, conv_w, conv_b, reverse=rev)             # ssi.py:182
+        h_in = None
+        if state is not None:
+            # history = the last 3 conv inputs (conv_state[..., 1:]); new conv_state = last 4 inputs (:274-277, :327-328)
+            hist = state["conv"][:, :, 1:].transpose(1, 2).to(xs.dtype)    # [B, 3, di]
+            cat = torch.cat([hist, xs], dim=1)
+            u = causal_conv_silu(cat, conv_w, conv_b)[:, 3:]
+            state["conv"].copy_(torch.cat([state["conv"].transpose(1, 2).to(xs.dtype), xs], dim=1)[:, -4:].transpose(1, 2))
+            h_in = state["ssm"].to(xs.dtype)
+        else:
+            u = causal_conv_silu(xs, conv_w, conv_b, reverse=rev)         # ssi.py:182
         dbl = _mm(u, W_x)                                                  # ssi.py:186
         delta_pre = dbl[..., :R] @ W_dt.t()                                # ssi.py:187 (bias NOT added here)
         Bm, Cm = dbl[..., R:R + Ns], dbl[..., R + Ns:]                     # ssi.py:193,205
-        y, _ = selective_scan(u, delta_pre, A.to(u.dtype), Bm, Cm, D.to(u.dtype), z,
-                              b_dt.to(u.dtype), reverse=rev, impl=scan_impl)  # ssi.py:218-220
+        y, h_last = selective_scan(u, delta_pre, A.to(u.dtype), Bm, Cm, D.to(u.dtype), z,
+                                   b_dt.to(u.dtype), reverse=rev, impl=scan_impl, h_in=h_in)  # ssi.py:218-220
+        if state is not None:
+            state["ssm"].copy_(h_last)                                     # bimamba.py:302-304, :357
         outs.append(y)
+    if not bidir:
+        return _mm(outs[0], sd[p + "out_proj.weight"])                    # bimamba.py:306
     return _mm(0.5 * outs[0] + 0.5 * outs[1], sd[p + "out_proj.weight"])  # bimamba.py:253
 
 
-def mamba_stack_fwd(h, sd, n_mamba, prefix="mamba_net.", scan_impl="auto", taps=None):
+def mixer_step(x_t, sd, prefix, conv_state, ssm_state):
+    """``Mamba.step`` (``modules/mamba/bimamba.py:320-372``) restated literally: one token ``x_t [B, D]``,
+    ``conv_state [B, di, 4]`` and ``ssm_state [B, di, Ns]`` updated in place; returns ``[B, D]``."""
+    p = prefix
+    xz = x_t @ sd[p + "in_proj.weight"].t()                                # :323
+    di = xz.shape[-1] // 2
+    x, z = xz[:, :di], xz[:, di:]                                          # :324
+    conv_state.copy_(torch.roll(conv_state, shifts=-1, dims=-1))           # :328
+    conv_state[:, :, -1] = x                                               # :329
+    x = torch.sum(conv_state * sd[p + "conv1d.weight"][:, 0, :], dim=-1) + sd[p + "conv1d.bias"]   # :330-332
+    x = F.silu(x)                                                          # :333
+    x_db = x @ sd[p + "x_proj.weight"].t()                                 # :343
+    R = sd[p + "dt_proj.weight"].shape[1]
+    Ns = ssm_state.shape[-1]
+    dt, Bm, Cm = x_db[:, :R], x_db[:, R:R + Ns], x_db[:, R + Ns:]          # :344
+    dt = dt @ sd[p + "dt_proj.weight"].t()                                 # :346
+    A = -torch.exp(sd[p + "A_log"].float())                                # :347
+    dt = F.softplus(dt + sd[p + "dt_proj.bias"])                           # :352
+    dA = torch.exp(torch.einsum("bd,dn->bdn", dt, A))                      # :353
+    dB = torch.einsum("bd,bn->bdn", dt, Bm)                                # :354
+    ssm_state.copy_(ssm_state * dA + x.unsqueeze(-1) * dB)                 # :355
+    y = torch.einsum("bdn,bn->bd", ssm_state, Cm) + sd[p + "D"] * x        # :356-357
+    y = y * F.silu(z)                                                      # :358
+    return y @ sd[p + "out_proj.weight"].t()                               # :365
+
+
+def new_stream_state(sd, n_mamba, batch, prefix="mamba_net."):
+    """Zero conv / ssm caches per layer (``allocate_inference_cache``, ``bimamba.py:368-380``)."""
+    out = []
+    for i in range(n_mamba):
+        A = sd[f"{prefix}layers.{i}.mixer.A_log"]
+        out.append({"conv": torch.zeros(batch, A.shape[0], 4), "ssm": torch.zeros(batch, A.shape[0], A.shape[1])})
+    return out
+
+
+def mamba_stack_fwd(h, sd, n_mamba, prefix="mamba_net.", scan_impl="auto", taps=None, states=None):
     """``MambaBlocksSequential.forward`` non-fused branch (``modules/mamba_blocks.py:186-197``)
-    over ``Block.forward`` (``modules/mamba/bimamba.py:445-462``): Add -> RMSNorm -> Mixer."""
+    over ``Block.forward`` (``modules/mamba/bimamba.py:445-462``): Add -> RMSNorm -> Mixer.
+    ``states`` (list from ``new_stream_state``): the ``inference_params`` caches of the reference, for streaming."""
     residual = None
     for i in range(n_mamba):
         p = f"{prefix}layers.{i}."
         residual = h if residual is None else h + residual                # bimamba.py:446
         hn = rmsnorm_fwd(residual, sd[p + "norm.weight"])                  # bimamba.py:447
-        h = mixer_fwd(hn, sd, p + "mixer.", scan_impl)                     # bimamba.py:461
+        h = mixer_fwd(hn, sd, p + "mixer.", scan_impl, state=None if states is None else states[i])  # bimamba.py:461
         if taps is not None:
             taps.append(h)
     residual = h + residual if residual is not None else h                 # mamba_blocks.py:196

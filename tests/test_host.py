@@ -43,7 +43,20 @@ def test_init_state_dicts_has_reference_keys():
     sep.load_reference_state_dicts(sds, strict=True)
 
 
-@pytest.mark.parametrize("kw", [dict(mask_nonlinear="softmax"), dict(bidirectional=False), dict(d_state=8),
+def test_causal_modules_have_mamba_ssm_state_dict_keys():
+    """bidirectional=False -> mamba_ssm.Mamba parameter set (no *_b keys), strict load of a causal state_dict."""
+    hp = CONFIGS["tiny"].causal()
+    sds = init_state_dicts(hp, 3)
+    assert not any("_b" in k.split(".")[-2] + k.split(".")[-1] for k in sds["masknet"] if "mixer" in k)
+    sep = modules.MambaTasNetSeparator.from_hparams(hp)
+    sep.load_reference_state_dicts(sds, strict=True)
+    with pytest.raises(RuntimeError):      # a bidirectional checkpoint does not fit a causal model
+        sep.load_reference_state_dicts(init_state_dicts(CONFIGS["tiny"], 3), strict=True)
+    with pytest.raises(NotImplementedError):   # step() is the unidirectional mixer's interface
+        modules.Mamba(64).step(torch.zeros(1, 1, 64), torch.zeros(1, 128, 4), torch.zeros(1, 128, 16))
+
+
+@pytest.mark.parametrize("kw", [dict(mask_nonlinear="softmax"), dict(d_state=8),
                                 dict(d_conv=3), dict(rms_norm=False), dict(n_spk=3)])
 def test_unsupported_options_raise(kw):
     with pytest.raises(NotImplementedError):

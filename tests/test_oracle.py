@@ -92,3 +92,47 @@ def test_si_snr_restatement_matches_reference_cal_si_snr(golden_dir):
     assert perm.tolist() == [1, 0, 0]               # utterance 0 was minted with its speakers swapped
     assert torch.allclose(pairs[1:, [0, 1], [0, 1]], mine[1:], atol=1e-9)
     assert (best > 4).all() and (imp > 4).all() and best[1] > 40
+
+
+# ------------------------------------------------------------------------------------------------ causal / streaming
+def test_causal_restatement_matches_reference_golden(golden_dir):
+    """bidirectional=False: the reference's own run (vendored unidirectional branch, oracle/ref_shims.UniMamba)."""
+    sds, out, taps = load_golden_forward(os.path.join(golden_dir, "forward_tiny_causal.npz"))
+    assert not any(k.endswith("A_b_log") for k in sds["masknet"])
+    n = 1 + max(int(k.split(".")[2]) for k in sds["masknet"] if k.startswith("mamba_net.layers."))
+    for impl in ("torch", "c"):
+        est = restate.separate(out["mix"], sds, n, scan_impl=impl)
+        assert (est - out["est"]).abs().max().item() <= 2e-6, impl
+
+
+def test_streaming_restatement_matches_reference_inference_cache(golden_dir):
+    """Prefill + Mamba.step through the reference's inference_params caches (golden) vs the oracle's chunk-carry
+    restatement, for two different chunkings, including the literal per-token `mixer_step`."""
+    sds, _, _ = load_golden_forward(os.path.join(golden_dir, "forward_tiny_causal.npz"))
+    z = np.load(os.path.join(golden_dir, "stream_tiny_causal.npz"))
+    h = torch.from_numpy(z["h"])
+    m = sds["masknet"]
+    n = 1 + max(int(k.split(".")[2]) for k in m if k.startswith("mamba_net.layers."))
+    L0 = int(z["L0"])
+    for cuts in ([L0] + [1] * (h.shape[1] - L0), [5, 2, 1, 13, 20]):
+        st = restate.new_stream_state(m, n, h.shape[0])
+        outs, pos = [], 0
+        for c in cuts:
+            outs.append(restate.mamba_stack_fwd(h[:, pos:pos + c], m, n, states=st))
+            pos += c
+        assert pos == h.shape[1]
+        got = torch.cat(outs, dim=1)
+        assert (got - torch.from_numpy(z["streamed"])).abs().max().item() <= 2e-6
+        assert (got - torch.from_numpy(z["full"])).abs().max().item() <= 2e-6
+        for i in range(n):
+            assert (st[i]["conv"] - torch.from_numpy(z[f"conv_state/{i}"])).abs().max().item() <= 1e-6
+            assert (st[i]["ssm"] - torch.from_numpy(z[f"ssm_state/{i}"])).abs().max().item() <= 1e-6
+    # literal step: layer 0 mixer, one token from zero caches == first output row of the chunk form
+    p = "mamba_net.layers.0.mixer."
+    cs, ss = torch.zeros(h.shape[0], m[p + "A_log"].shape[0], 4), torch.zeros(h.shape[0], m[p + "A_log"].shape[0], 16)
+    st0 = {"conv": cs.clone(), "ssm": ss.clone()}
+    x = h[:, :3]
+    chunk = restate.mixer_fwd(x, m, p, state=st0)
+    rows = [restate.mixer_step(x[:, t], m, p, cs, ss) for t in range(3)]
+    assert (torch.stack(rows, dim=1) - chunk).abs().max().item() <= 2e-6
+    assert (cs - st0["conv"]).abs().max().item() <= 1e-6 and (ss - st0["ssm"]).abs().max().item() <= 1e-6
