@@ -52,7 +52,10 @@ def parse():
     ap.add_argument("--mode", default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "longform", "custom"],
+    ap.add_argument("--causal", action="store_true",
+                    help="unidirectional stack (bidirectional=False, mamba_blocks.py:128): one scan direction per layer")
+    ap.add_argument("--chunk-ms", type=float, default=20.0, help="stream: audio per push() call")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "longform", "stream", "custom"],
                     help="cfg2 (default): S, 32 x 4 s @ 8 kHz per GPU, fp32 mode, weak scaling.  cfg3: L, global batch "
                          "256 x 4 s sharded over the GPUs, bf16 mode, strong scaling.  longform: one 10-minute 16 kHz "
                          "recording, sequence-parallel over the GPUs (S fp32 unless --hparams/--mode given), strong "
@@ -70,6 +73,9 @@ def parse():
         if "--seconds" not in explicit: a.seconds = 600.0
         if "--sample-rate" not in explicit: a.sample_rate = 16000
         a.batch = 1
+    elif a.workload == "stream":
+        a.causal = True
+        if "--batch" not in explicit: a.batch = 1
     return a
 
 
@@ -77,7 +83,9 @@ def workload_config(a, n_gpus):
     prec = ("(split-bf16 x3 tcgen05 GEMMs, fp32 scan state)" if a.mode == "fp32"
             else "(bf16 tcgen05 GEMMs + bf16 activations, fp32 scan state)")
     name = {"cfg2": "BASELINE config 2", "cfg3": "BASELINE config 3", "longform": "BASELINE config 5",
-            "custom": "custom"}[a.workload]
+            "custom": "custom", "stream": "streaming (SURVEY 8f rank 2)"}[a.workload]
+    if a.causal:
+        name += " [causal: bidirectional=False]"
     if a.workload == "longform":
         return {
             "workload": (f"{name}: Mamba-TasNet {a.hparams} hparams, one {a.seconds:g} s @ {a.sample_rate // 1000} kHz "
@@ -102,7 +110,7 @@ def scaling_kind(a):
 
 
 # ------------------------------------------------------------------------------------------ CPU reference arm
-def cpu_reference_throughput(hparams: str, sample_rate: int, steps: int, warmup: int, budget_s: float):
+def cpu_reference_throughput(hparams: str, sample_rate: int, steps: int, warmup: int, budget_s: float, causal: bool = False):
     """Time the oracle port of the reference's CPU forward (selective_scan_ref = per-step torch loop,
     Mamba-TasNet/modules/mamba/selective_scan_interface.py:91-157) on a bounded sample of the workload."""
     import torch
@@ -111,7 +119,7 @@ def cpu_reference_throughput(hparams: str, sample_rate: int, steps: int, warmup:
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    hp = CONFIGS[hparams]
+    hp = CONFIGS[hparams].causal() if causal else CONFIGS[hparams]
     sds = init_state_dicts(hp, 1234)
 
     def run(seconds):
@@ -145,7 +153,7 @@ def run_reference_arm(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    base, dt = cpu_reference_throughput(a.hparams, a.sample_rate, a.steps, a.warmup, budget_s=150.0)
+    base, dt = cpu_reference_throughput(a.hparams, a.sample_rate, a.steps, a.warmup, budget_s=150.0, causal=a.causal)
     line = {
         "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": a.gpus,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
@@ -205,14 +213,14 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------ B200 arm
-def scan_algorithmic_bytes(hp, batch, L, mode):
+def scan_algorithmic_bytes(hp, batch, L, mode, ndir=2):
     """Bytes one both-direction scan launch must move at the op boundary of the reference's
     selective_scan_cuda.fwd: per direction B*L*[(u, delta, z read + out written)*di + (B, C)*Ns]*s_io
     + parameters.  fp32 mode moves 4-byte elements (u / y as hi+lo bf16 planes = 4 B), bf16 mode 2-byte."""
     s_io = 4 if mode == "fp32" else 2
     di, Ns = hp.d_inner, hp.d_state
     per_dir = batch * L * (4 * di + 2 * Ns) * s_io + (di * Ns + 2 * di) * 4
-    return 2 * per_dir
+    return ndir * per_dir
 
 
 def load_peaks():
@@ -243,7 +251,7 @@ def run_b200_arm(a):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    hp = CONFIGS[a.hparams]
+    hp = CONFIGS[a.hparams].causal() if a.causal else CONFIGS[a.hparams]
     T = int(round(a.seconds * a.sample_rate)) // 8 * 8
     L = hp.frames(T)
     sds = init_state_dicts(hp, 1234)
@@ -255,7 +263,7 @@ def run_b200_arm(a):
 
     cpu_base = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        cpu_base, _ = cpu_reference_throughput(a.hparams, a.sample_rate, steps=1, warmup=0, budget_s=30.0)
+        cpu_base, _ = cpu_reference_throughput(a.hparams, a.sample_rate, steps=1, warmup=0, budget_s=30.0, causal=a.causal)
 
     def barrier():
         if world > 1:
@@ -311,19 +319,19 @@ def run_b200_arm(a):
     if rank == 0:
         peak, peak_src, peaks = load_peaks()
         scan_ms = prof["scan"]["ms"]
-        alg = scan_algorithmic_bytes(hp, a.batch, L, a.mode)
+        alg = scan_algorithmic_bytes(hp, a.batch, L, a.mode, 2 if hp.bidirectional else 1)
         achieved = alg / (scan_ms * 1e-3) / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "scan_traffic.json")
         if os.path.exists(tp):
             try:
                 tj = json.load(open(tp))
-                key = f"{a.hparams}_b{a.batch}_{a.mode}"
+                key = f"{a.hparams}_b{a.batch}_{a.mode}" + ("" if hp.bidirectional else "_causal")
                 traffic = tj.get(key, {}).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
         sm_mhz = (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
-        n_exp = 2 * a.batch * L * hp.d_inner * hp.d_state
+        n_exp = (2 if hp.bidirectional else 1) * a.batch * L * hp.d_inner * hp.d_state
         mufu_ms = n_exp / (148 * 16 * sm_mhz * 1e6) * 1e3
         step_ms = ms_total / a.steps
         total_prof = sum(v["ms_per_forward"] for v in prof.values())
@@ -377,7 +385,7 @@ def run_longform_arm(a):
     sp = SequenceParallelSeparator(hp, sds, device=dev, mode=a.mode, sub_chunks=a.sub_chunks, exchange=a.exchange)
     cpu_base = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        cpu_base, _ = cpu_reference_throughput(a.hparams, a.sample_rate, steps=1, warmup=0, budget_s=30.0)
+        cpu_base, _ = cpu_reference_throughput(a.hparams, a.sample_rate, steps=1, warmup=0, budget_s=30.0, causal=a.causal)
 
     def barrier():
         if world > 1:
@@ -448,10 +456,116 @@ def run_longform_arm(a):
         dist.destroy_process_group()
 
 
+def run_stream_arm(a):
+    """Streaming causal separation: `batch` concurrent streams per GPU, one push() per `chunk_ms` of
+    audio.  value = audio-s/s with the chunks already in HBM; e2e = every chunk copied from pinned host memory and its
+    estimate copied back (what a live pipeline does); latency = device time of one push."""
+    import torch
+    import torch.distributed as dist
+    from avse_challenge_b200 import CONFIGS, init_state_dicts, synth_mixture
+    from avse_challenge_b200.engine import SeparatorEngine
+    from avse_challenge_b200.streaming import StreamingSeparator
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback for the product path)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    hp = CONFIGS[a.hparams].causal()
+    n = max(16, int(round(a.chunk_ms * 1e-3 * a.sample_rate)) // 8 * 8)     # samples per push
+    sds = init_state_dicts(hp, 1234)
+    eng = SeparatorEngine(hp, sds, device=dev, mode=a.mode, use_graph=False)
+    st = StreamingSeparator(eng, a.batch, use_graph=not a.no_graph)
+    n_chunks = 64
+    mix_cpu, _ = synth_mixture(min(a.batch, 8), n * n_chunks, a.sample_rate, seed=1234 + rank)
+    mix_cpu = mix_cpu.repeat(-(-a.batch // mix_cpu.shape[0]), 1)[: a.batch].contiguous()
+    chunks_d = [mix_cpu[:, i * n:(i + 1) * n].contiguous().to(dev) for i in range(n_chunks)]
+    chunks_h = [mix_cpu[:, i * n:(i + 1) * n].contiguous().pin_memory() for i in range(n_chunks)]
+    out_h = torch.empty((a.batch, n, hp.n_spk), dtype=torch.float32).pin_memory()
+    stage = torch.empty((a.batch, n), dtype=torch.float32, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    st.push(chunks_d[0])                                            # first chunk has its own shape (no carried samples)
+    for i in range(max(3, a.warmup)):
+        st.push(chunks_d[1 + i % (n_chunks - 1)])
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(a.steps):
+        st.push(chunks_d[1 + i % (n_chunks - 1)])
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+
+    def e2e_step(i):
+        stage.copy_(chunks_h[1 + i % (n_chunks - 1)], non_blocking=True)
+        out_h.copy_(st.push(stage), non_blocking=True)
+
+    for i in range(3):
+        e2e_step(i)
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for i in range(a.steps):
+        e2e_step(i)
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+    # host-observed latency of one live chunk (copy in, push, copy out, wait)
+    lat = []
+    for i in range(min(a.steps, 50)):
+        t0 = time.perf_counter()
+        e2e_step(i)
+        torch.cuda.synchronize()
+        lat.append((time.perf_counter() - t0) * 1e3)
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, ms_e2e = t.tolist()
+    if rank == 0:
+        peak, peak_src, _ = load_peaks()
+        audio_s = a.batch * n / a.sample_rate
+        step_ms = ms_total / a.steps
+        cfg = workload_config(a, world)
+        cfg["workload"] = (f"streaming causal Mamba-TasNet {a.hparams} hparams (bidirectional=False), {a.batch} concurrent stream(s) "
+                           f"per GPU, {n / a.sample_rate * 1e3:g} ms ({n // 8} frames) per push, {a.mode} mode, CUDA graph per chunk shape")
+        cfg["chunk_samples"] = n
+        line = {
+            "metric": METRIC, "value": audio_s * world / (step_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": a.steps,
+            "warmup": max(3, a.warmup), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32" if a.mode == "fp32" else "bf16", "data": "synthetic", "config": cfg,
+            "e2e": {"value": audio_s * world / (ms_e2e / a.steps * 1e-3), "unit": UNIT, "h2d_bytes_per_step": a.batch * n * 4,
+                    "d2h_bytes_per_step": a.batch * n * hp.n_spk * 4, "ms_per_step": ms_e2e / a.steps},
+            "latency_ms": {"chunk_audio_ms": n / a.sample_rate * 1e3, "device_ms_per_push": step_ms,
+                           "host_observed_median_ms": statistics.median(lat), "host_observed_max_ms": max(lat),
+                           "algorithmic_latency_ms": 16 / a.sample_rate * 1e3},
+            "gpu_launches": a.steps * (2 + hp.n_mamba * 6 + 2 + 2),
+            "roofline": {"kernel": "launch-latency bound (about 100 launches of a few-frame chunk per push)", "bound": "hbm",
+                         "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "peak_source": peak_src, "traffic": None,
+                         "note": "per-kernel roofline is reported on the cfg2 workload"},
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     a = parse()
     if a.impl == "reference":
         run_reference_arm(a)
+    elif a.workload == "stream":
+        run_stream_arm(a)
     elif a.workload == "longform":
         run_longform_arm(a)
     else:
