@@ -9,13 +9,14 @@ Public surface:
 The compute path is ``libmtn_b200.so`` (C ABI in ``include/mtn_b200.h``); importing this package does not
 load it, calling any op without it raises.
 """
-from .hparams import CONFIGS, HParams, init_state_dicts  # noqa: F401
+from .hparams import CONFIGS, DP_CONFIGS, DPHParams, HParams, init_dp_state_dicts, init_state_dicts  # noqa: F401
 from .synth import synth_mixture, si_snr, pit_si_snr  # noqa: F401
 
 
 def __getattr__(name):
     if name in ("Encoder", "MaskNet", "Decoder", "MambaBlocksSequential", "Block", "Mamba", "MambaTasNetSeparator",
-                "RMSNorm", "ChannelwiseLayerNorm"):
+                "RMSNorm", "ChannelwiseLayerNorm", "Dual_Path_Model", "Dual_Path_Model_Skip", "Dual_Computation_Block",
+                "DPMambaSeparator"):
         from . import modules
         return getattr(modules, name)
     if name == "SeparatorEngine":

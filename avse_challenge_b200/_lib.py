@@ -16,6 +16,8 @@ EPI_STORE, EPI_INPROJ, EPI_MASK, EPI_RELU, EPI_XPROJ, EPI_RESADD = 0, 1, 2, 3, 4
 EXPORTS = [
     "mtn_encoder_cln_fwd", "mtn_gemm_fwd", "mtn_gemm_rowsum_parts", "mtn_add_rmsnorm_fwd", "mtn_add_rmsnorm_out_fwd", "mtn_conv_silu_fwd", "mtn_conv_silu_halo_fwd", "mtn_conv_silu_dir_fwd", "mtn_decoder_stream_fwd",
     "mtn_scan_fwd", "mtn_fold_states_fwd",
+    "mtn_gn_partials_bytes", "mtn_gn_stats_fwd", "mtn_gn_apply_fwd", "mtn_dp_num_chunks", "mtn_dp_segment_fwd",
+    "mtn_dp_overadd_prelu_fwd", "mtn_bias_planes_fwd", "mtn_gate_planes_fwd",
     "mtn_decoder_fwd", "mtn_cln_fwd", "mtn_split_planes", "mtn_si_snr_pit_fwd", "mtn_si_snr_workspace_bytes", "mtn_last_error_string", "mtn_abi_version",
 ]
 
@@ -39,6 +41,15 @@ class ScanArgs(Structure):
         ("batch", c_int), ("L", c_int), ("di", c_int), ("R", c_int), ("n_dbl", c_int), ("ld_dbl", c_int),
         ("ldz", c_int), ("z_col0", c_int), ("planes", c_int), ("z_bf16", c_int), ("dir_mask", c_int),
         ("sum_delta", c_void_p), ("L_last", c_int), ("dtp", c_void_p),
+    ]
+
+
+class GnApplyArgs(Structure):
+    _fields_ = [
+        ("x", c_void_p), ("partials", c_void_p), ("w", c_void_p), ("bias", c_void_p), ("skip", c_void_p),
+        ("out_a", c_void_p), ("out_a2", c_void_p), ("out_t", c_void_p), ("planes", c_void_p),
+        ("batch", c_int), ("S", c_int), ("K", c_int), ("C", c_int), ("x_transposed", c_int),
+        ("n_planes", c_int), ("plane_rows", c_int), ("eps", c_float),
     ]
 
 
@@ -83,11 +94,22 @@ def load():
     lib.mtn_split_planes.argtypes = [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p]
     lib.mtn_si_snr_workspace_bytes.argtypes = [c_int, c_int]
     lib.mtn_si_snr_pit_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p, c_void_p]
+    lib.mtn_gn_partials_bytes.argtypes = [c_int, c_int, c_int]
+    lib.mtn_gn_stats_fwd.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]
+    lib.mtn_gn_apply_fwd.argtypes = [POINTER(GnApplyArgs), c_void_p]
+    lib.mtn_dp_num_chunks.argtypes = [c_int, c_int]
+    lib.mtn_dp_segment_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]
+    lib.mtn_dp_overadd_prelu_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                             c_void_p]
+    lib.mtn_bias_planes_fwd.argtypes = [c_void_p, c_int, c_void_p, c_float, c_void_p, c_int, c_int, c_int, c_int, c_void_p]
+    lib.mtn_gate_planes_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]
     for name in EXPORTS:
         fn = getattr(lib, name, None)
-        if fn is not None and name not in ("mtn_last_error_string", "mtn_abi_version", "mtn_si_snr_workspace_bytes"):
+        if fn is not None and name not in ("mtn_last_error_string", "mtn_abi_version", "mtn_si_snr_workspace_bytes",
+                                           "mtn_gn_partials_bytes"):
             fn.restype = c_int
     lib.mtn_si_snr_workspace_bytes.restype = c_size_t
+    lib.mtn_gn_partials_bytes.restype = c_size_t
     _lib = lib
     return lib
 

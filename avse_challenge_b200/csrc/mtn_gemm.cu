@@ -460,6 +460,9 @@ static int dispatch_epi(const mtn_gemm_args* a, cudaStream_t s) {
     }
     if (BN == 64) {
         if (a->epilogue == MTN_EPI_RESADD && !a->out_bf16) return launch_gemm<P, BN, MTN_EPI_RESADD, false>(a, s);
+        // per-speaker grouped end_conv1x1 of DPMamba at enc_dim = 64 (unit-test sizes)
+        if (a->epilogue == MTN_EPI_MASK && !a->out_bf16) return launch_gemm<P, BN, MTN_EPI_MASK, false>(a, s);
+        if (a->epilogue == MTN_EPI_RELU && !a->out_bf16) return launch_gemm<P, BN, MTN_EPI_RELU, false>(a, s);
     }
     if (BN >= 128) {
         if (a->epilogue == MTN_EPI_RESADD && !a->out_bf16) return launch_gemm<P, BN, MTN_EPI_RESADD, false>(a, s);

@@ -191,4 +191,50 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bflo
     lo = __float2bfloat16_rn(x - __bfloat162float(hi));
 }
 
+// ---- shared by the streaming kernels (mtn_elem.cu, mtn_dp.cu): warp reduction, operand-plane stores
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <int P>
+__device__ __forceinline__ void store_planes1(__nv_bfloat16* base, size_t plane_stride, size_t off, float v) {
+    if (P == 2) {
+        __nv_bfloat16 hi, lo;
+        split_bf16(v, hi, lo);
+        base[off] = hi;
+        base[plane_stride + off] = lo;
+    } else {
+        base[off] = __float2bfloat16_rn(v);
+    }
+}
+
+template <int P>
+__device__ __forceinline__ void store_planes4(__nv_bfloat16* base, size_t plane_stride, size_t off, float4 v) {
+    __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
+    if (P == 2) {
+        split_bf16(v.x, h0, l0);
+        split_bf16(v.y, h1, l1);
+        split_bf16(v.z, h2, l2);
+        split_bf16(v.w, h3, l3);
+    } else {
+        h0 = __float2bfloat16_rn(v.x);
+        h1 = __float2bfloat16_rn(v.y);
+        h2 = __float2bfloat16_rn(v.z);
+        h3 = __float2bfloat16_rn(v.w);
+    }
+    __nv_bfloat162 a = __halves2bfloat162(h0, h1), b = __halves2bfloat162(h2, h3);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&a);
+    pk.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(base + off) = pk;
+    if (P == 2) {
+        __nv_bfloat162 c = __halves2bfloat162(l0, l1), d = __halves2bfloat162(l2, l3);
+        pk.x = *reinterpret_cast<uint32_t*>(&c);
+        pk.y = *reinterpret_cast<uint32_t*>(&d);
+        *reinterpret_cast<uint2*>(base + plane_stride + off) = pk;
+    }
+}
+
 }  // namespace mtn

@@ -120,3 +120,85 @@ def init_state_dicts(hp: HParams, seed: int = 1234, trained_like: bool = True):
             elif k.endswith("beta"):
                 m[k] = m[k] + 0.05 * torch.randn(m[k].shape, generator=g)
     return {"encoder": enc, "masknet": m, "decoder": dec}
+
+
+# ------------------------------------------------------------------------------------------------------- DPMamba
+@dataclass(frozen=True)
+class DPHParams:
+    """DPMamba recipes (``Mamba-TasNet/hparams/WSJ0Mix/dpmamba_{XS,S,M,L}.yaml:108-123,164-174``): speechbrain
+    ``Dual_Path_Model`` with ``MambaBlocksSequential(n_mamba_dp // 2)`` as intra and as inter model."""
+    name: str
+    enc_dim: int                 # N_encoder_out
+    d_model: int                 # out_channels
+    n_dp: int                    # dual-path blocks
+    skip_around_intra: bool
+    chunk_size: int = 250        # K
+    n_mamba_dp: int = 2
+    kernel_size: int = 16
+    d_state: int = 16
+    expand: int = 2
+    d_conv: int = 4
+    n_spk: int = 2
+    sample_rate: int = 8000
+
+    @property
+    def stride(self) -> int:
+        return self.kernel_size // 2
+
+    def frames(self, T: int) -> int:
+        return (T - self.kernel_size) // self.stride + 1
+
+    @property
+    def stack(self) -> HParams:
+        """Hyper-parameters of one intra / inter stack."""
+        return HParams(self.name + "_stack", self.d_model, self.d_model, self.n_mamba_dp // 2, kernel_size=self.kernel_size,
+                       d_state=self.d_state, expand=self.expand, d_conv=self.d_conv, n_spk=self.n_spk,
+                       sample_rate=self.sample_rate)
+
+    def as_dict(self):
+        return asdict(self)
+
+
+DP_CONFIGS = {
+    "XS": DPHParams("dp_XS", 128, 128, 8, False),
+    "S": DPHParams("dp_S", 256, 256, 8, False),
+    "M": DPHParams("dp_M", 256, 256, 16, True),
+    "L": DPHParams("dp_L", 512, 512, 16, True),
+    # not shipped: small shapes for unit tests / golden fixtures (K = 10 -> many ragged chunks at short lengths)
+    "tiny": DPHParams("dp_tiny", 64, 64, 2, True, chunk_size=10),
+}
+
+
+def init_dp_state_dicts(hp: DPHParams, seed: int = 1234, trained_like: bool = True):
+    """``{encoder, masknet, decoder}`` state_dicts of a DPMamba model with speechbrain ``Dual_Path_Model`` key names
+    (``norm``, ``conv1d``, ``dual_mdl.<i>.{intra_mdl,inter_mdl,intra_norm,inter_norm}``, ``conv2d``, ``end_conv1x1``,
+    ``prelu``, ``output.0``, ``output_gate.0``); the stacks are initialised like ``init_state_dicts``."""
+    g = torch.Generator().manual_seed(seed)
+    N, D = hp.enc_dim, hp.d_model
+
+    def uni(shape, bound):
+        return (torch.rand(shape, generator=g) * 2 - 1) * bound
+
+    enc = {"conv1d.weight": uni((N, 1, hp.kernel_size), 1.0 / math.sqrt(hp.kernel_size))}
+    dec = {"weight": uni((N, 1, hp.kernel_size), 1.0 / math.sqrt(hp.kernel_size))}
+    m = {}
+    pert = (lambda t, s: t + s * torch.randn(t.shape, generator=g)) if trained_like else (lambda t, s: t)
+    m["norm.weight"], m["norm.bias"] = pert(torch.ones(N), 0.1), pert(torch.zeros(N), 0.05)
+    m["conv1d.weight"] = uni((D, N, 1), 1.0 / math.sqrt(N))
+    for i in range(hp.n_dp):
+        for which in ("intra", "inter"):
+            sub = init_state_dicts(hp.stack, seed=seed + 17 * i + (0 if which == "intra" else 7),
+                                   trained_like=trained_like)["masknet"]
+            for k, v in sub.items():
+                if k.startswith("mamba_net."):
+                    m[f"dual_mdl.{i}.{which}_mdl.{k[len('mamba_net.'):]}"] = v
+            m[f"dual_mdl.{i}.{which}_norm.weight"] = pert(torch.ones(D), 0.1)
+            m[f"dual_mdl.{i}.{which}_norm.bias"] = pert(torch.zeros(D), 0.05)
+    m["conv2d.weight"] = uni((D * hp.n_spk, D, 1, 1), 1.0 / math.sqrt(D))
+    m["conv2d.bias"] = uni((D * hp.n_spk,), 1.0 / math.sqrt(D))
+    m["end_conv1x1.weight"] = uni((N, D, 1), 1.0 / math.sqrt(D))
+    m["prelu.weight"] = torch.full((1,), 0.25)
+    for name in ("output", "output_gate"):
+        m[f"{name}.0.weight"] = uni((D, D, 1), 1.0 / math.sqrt(D))
+        m[f"{name}.0.bias"] = uni((D,), 1.0 / math.sqrt(D))
+    return {"encoder": enc, "masknet": m, "decoder": dec}

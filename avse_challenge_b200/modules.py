@@ -386,3 +386,133 @@ class MambaTasNetSeparator(_EngineOwner):
     @torch.no_grad()
     def forward(self, mix):
         return self.engine().forward(mix)
+
+
+# ---------------------------------------------------------------------------------------------------- DPMamba
+class Dual_Computation_Block(nn.Module):
+    """Parameter container of speechbrain's ``Dual_Computation_Block`` (``norm="ln"``, no linear layers)."""
+
+    def __init__(self, intra_mdl, inter_mdl, out_channels, norm="ln", skip_around_intra=True,
+                 linear_layer_after_inter_intra=True):
+        super().__init__()
+        if norm != "ln" or linear_layer_after_inter_intra:
+            _unsupported("Dual_Computation_Block with norm != 'ln' or linear_layer_after_inter_intra=True")
+        self.intra_mdl, self.inter_mdl = intra_mdl, inter_mdl
+        self.skip_around_intra = skip_around_intra
+        self.intra_norm = nn.GroupNorm(1, out_channels, eps=1e-8)
+        self.inter_norm = nn.GroupNorm(1, out_channels, eps=1e-8)
+
+
+class Dual_Path_Model(_EngineOwner):
+    """speechbrain ``lobes.models.dual_path.Dual_Path_Model`` as the dpmamba recipes instantiate it
+    (``hparams/WSJ0Mix/dpmamba_L.yaml:164-174``): same constructor, same state_dict keys; ``forward`` is
+    [B, N, L] -> [n_spk, B, N, L] (``modules/dual_path.py:56-150``).  ``intra_model`` / ``inter_model`` must be this
+    package's one-layer-per-stack bidirectional ``MambaBlocksSequential``."""
+
+    def __init__(self, in_channels, out_channels, intra_model, inter_model, num_layers=1, norm="ln", K=200, num_spks=2,
+                 skip_around_intra=True, linear_layer_after_inter_intra=True, use_global_pos_enc=False,
+                 max_length=20000, mode="fp32"):
+        super().__init__()
+        import copy
+        if use_global_pos_enc:
+            _unsupported("use_global_pos_enc=True")
+        for mdl in (intra_model, inter_model):
+            if not isinstance(mdl, MambaBlocksSequential) or not mdl.bidirectional:
+                _unsupported("intra / inter models other than a bidirectional MambaBlocksSequential")
+        if intra_model.n_mamba != inter_model.n_mamba:
+            _unsupported("intra / inter stacks of different depth")
+        if num_spks != 2 or K % 2:
+            _unsupported("num_spks != 2 or odd K")
+        self.K, self.num_spks, self.num_layers, self.mode = K, num_spks, num_layers, mode
+        self.norm = nn.GroupNorm(1, in_channels, eps=1e-8)
+        self.conv1d = nn.Conv1d(in_channels, out_channels, 1, bias=False)
+        self.dual_mdl = nn.ModuleList([
+            copy.deepcopy(Dual_Computation_Block(intra_model, inter_model, out_channels, norm,
+                                                 skip_around_intra=skip_around_intra,
+                                                 linear_layer_after_inter_intra=linear_layer_after_inter_intra))
+            for _ in range(num_layers)])
+        self.conv2d = nn.Conv2d(out_channels, out_channels * num_spks, kernel_size=1)
+        self.end_conv1x1 = nn.Conv1d(out_channels, in_channels, 1, bias=False)
+        self.prelu = nn.PReLU()
+        self.output = nn.Sequential(nn.Conv1d(out_channels, out_channels, 1), nn.Tanh())
+        self.output_gate = nn.Sequential(nn.Conv1d(out_channels, out_channels, 1), nn.Sigmoid())
+        from .hparams import DPHParams
+        self.hp = DPHParams("custom_dp", in_channels, out_channels, num_layers, skip_around_intra, chunk_size=K,
+                            n_mamba_dp=2 * intra_model.n_mamba, n_spk=num_spks)
+        self._invalidate()
+
+    def engine(self, encoder_sd=None, decoder_sd=None, mode=None, use_graph=True):
+        from .dpmamba import DPSeparatorEngine
+        mode = mode or self.mode
+        key = (mode, use_graph, id(encoder_sd), id(decoder_sd))
+        cache = self.__dict__.setdefault("_engine_cache", {})
+        if key not in cache:
+            N = self.hp.enc_dim
+            enc = encoder_sd or {"conv1d.weight": torch.zeros(N, 1, 16)}
+            dec = decoder_sd or {"weight": torch.zeros(N, 1, 16)}
+            cache[key] = DPSeparatorEngine(self.hp, {"encoder": enc, "masknet": self.state_dict(), "decoder": dec},
+                                           device=self.conv1d.weight.device, mode=mode, use_graph=use_graph)
+        return cache[key]
+
+    @torch.no_grad()
+    def forward(self, x):
+        B, N, L = x.shape
+        eng = self.engine(use_graph=False)
+        ws = eng.workspace(B, (L - 1) * 8 + 16)
+        ws.mix_w.copy_(x.transpose(1, 2).reshape(B * L, N))
+        mask = eng._run(ws, mask_only=True)
+        return mask.view(B, L, self.num_spks, N).permute(2, 0, 3, 1).clone()
+
+
+class Dual_Path_Model_Skip(Dual_Path_Model):
+    """``modules/dual_path.py:17-150`` (vendored subclass).  ``skip_n_block = 0`` -- what every shipped recipe sets
+    (``dpmamba_L.yaml:116``) -- makes it identical to ``Dual_Path_Model``; other values are not built."""
+
+    def __init__(self, *args, skip_n_block=0, **kw):
+        if skip_n_block != 0:
+            _unsupported("skip_n_block != 0")
+        super().__init__(*args, **kw)
+        self.skip_n_block = skip_n_block
+
+
+class DPMambaSeparator(_EngineOwner):
+    """Fused ``Encoder -> Dual_Path_Model -> mask * mix_w -> Decoder`` (``train_wsj0mix.py:86-111`` with the dpmamba
+    recipes): ``forward(mix [B, T]) -> est_source [B, T, n_spk]``."""
+
+    def __init__(self, encoder: Encoder, masknet: Dual_Path_Model, decoder: Decoder, mode="fp32", use_graph=True):
+        super().__init__()
+        self.encoder, self.masknet, self.decoder = encoder, masknet, decoder
+        self.mode, self.use_graph = mode, use_graph
+        self._invalidate()
+
+    @classmethod
+    def from_hparams(cls, hp, mode="fp32", use_graph=True):
+        mk = lambda: MambaBlocksSequential(hp.n_mamba_dp // 2, bidirectional=True, d_model=hp.d_model, d_state=hp.d_state,
+                                           expand=hp.expand, d_conv=hp.d_conv, fused_add_norm=False, rms_norm=True)
+        mask = Dual_Path_Model(hp.enc_dim, hp.d_model, mk(), mk(), num_layers=hp.n_dp, norm="ln", K=hp.chunk_size,
+                               num_spks=hp.n_spk, skip_around_intra=hp.skip_around_intra,
+                               linear_layer_after_inter_intra=False, mode=mode)
+        return cls(Encoder(hp.kernel_size, hp.enc_dim), mask, Decoder(hp.enc_dim, 1, hp.kernel_size, hp.stride, bias=False),
+                   mode=mode, use_graph=use_graph)
+
+    def load_reference_state_dicts(self, sds: dict, strict=True):
+        self.encoder.load_state_dict(sds["encoder"], strict=strict)
+        self.masknet.load_state_dict(sds["masknet"], strict=strict)
+        self.decoder.load_state_dict(sds["decoder"], strict=strict)
+        self._invalidate()
+        self.masknet._invalidate()
+        return self
+
+    def engine(self):
+        from .dpmamba import DPSeparatorEngine
+        cache = self.__dict__.setdefault("_engine_cache", {})
+        if "e" not in cache:
+            sds = {"encoder": self.encoder.state_dict(), "masknet": self.masknet.state_dict(),
+                   "decoder": self.decoder.state_dict()}
+            cache["e"] = DPSeparatorEngine(self.masknet.hp, sds, device=self.masknet.conv1d.weight.device, mode=self.mode,
+                                           use_graph=self.use_graph)
+        return cache["e"]
+
+    @torch.no_grad()
+    def forward(self, mix):
+        return self.engine().forward(mix)

@@ -11,7 +11,7 @@ import math
 import torch
 
 from . import _lib
-from ._lib import GemmArgs, ScanArgs, check, ptr
+from ._lib import GemmArgs, GnApplyArgs, ScanArgs, check, ptr
 
 LOG2E = 1.4426950408889634
 
@@ -188,3 +188,64 @@ def decoder(sep, w_dec, batch, T, L, N, n_spk=2, est=None, frames=None, tail=Non
     check(_lib.load().mtn_decoder_stream_fwd(ptr(sep), ptr(w_dec), ptr(frames), ptr(est), ptr(tail), batch, T, L, N, n_spk,
                                              _stream()), "mtn_decoder_stream_fwd")
     return est
+
+
+# ---------------------------------------------------------------------------------------------------- DPMamba glue
+def dp_num_chunks(L: int, K: int) -> int:
+    """Chunks S of ``Dual_Path_Model._Segmentation`` for L frames, chunk size K (needs no GPU)."""
+    S = int(_lib.load().mtn_dp_num_chunks(L, K))
+    if S < 0:
+        raise _lib.MtnError(f"dp_num_chunks: bad L={L} K={K}")
+    return S
+
+
+def gn_partials(batch, rows, C, device):
+    n = int(_lib.load().mtn_gn_partials_bytes(batch, rows, C))
+    return torch.empty(n // 8, dtype=torch.float64, device=device)
+
+
+def gn_stats(x, batch, rows, C, partials=None):
+    """Pass 1 of GroupNorm(1, C): x fp32 [batch, rows, C] (any row order) -> per-utterance partial sums."""
+    _req_cuda(x)
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.numel() == batch * rows * C
+    if partials is None:
+        partials = gn_partials(batch, rows, C, x.device)
+    check(_lib.load().mtn_gn_stats_fwd(ptr(x), ptr(partials), batch, rows, C, _stream()), "mtn_gn_stats_fwd")
+    return partials
+
+
+def gn_apply(x, partials, w, bias, batch, S, K, C, *, eps=1e-8, skip=None, out_a=None, out_a2=None, out_t=None, planes=None,
+             x_transposed=False):
+    _req_cuda(x, partials, w, bias, skip, out_a, out_a2, out_t, planes)
+    args = GnApplyArgs(x=ptr(x), partials=ptr(partials), w=ptr(w), bias=ptr(bias), skip=ptr(skip), out_a=ptr(out_a),
+                       out_a2=ptr(out_a2), out_t=ptr(out_t), planes=ptr(planes), batch=batch, S=S, K=K, C=C,
+                       x_transposed=int(x_transposed), n_planes=(planes.shape[0] if planes is not None else 0),
+                       plane_rows=(planes.shape[1] if planes is not None else 0), eps=eps)
+    check(_lib.load().mtn_gn_apply_fwd(args, _stream()), "mtn_gn_apply_fwd")
+
+
+def dp_segment(x, batch, L, C, K, S, out_a, out_a2=None):
+    _req_cuda(x, out_a, out_a2)
+    check(_lib.load().mtn_dp_segment_fwd(ptr(x), ptr(out_a), ptr(out_a2), batch, L, C, K, S, _stream()), "mtn_dp_segment_fwd")
+    return out_a
+
+
+def dp_overadd_prelu(X, prelu_w, planes, batch, L, C, K, S):
+    _req_cuda(X, prelu_w, planes)
+    check(_lib.load().mtn_dp_overadd_prelu_fwd(ptr(X), ptr(prelu_w), ptr(planes), planes.shape[1], batch, L, C, K, S,
+                                               planes.shape[0], _stream()), "mtn_dp_overadd_prelu_fwd")
+    return planes
+
+
+def bias_planes(x, bias, bias_scale, planes, rows, C):
+    _req_cuda(x, bias, planes)
+    check(_lib.load().mtn_bias_planes_fwd(ptr(x), x.stride(0), ptr(bias), bias_scale, ptr(planes), planes.shape[1], rows, C,
+                                          planes.shape[0], _stream()), "mtn_bias_planes_fwd")
+    return planes
+
+
+def gate_planes(og, bo, bg, planes, rows, groups, D):
+    _req_cuda(og, bo, bg, planes)
+    check(_lib.load().mtn_gate_planes_fwd(ptr(og), ptr(bo), ptr(bg), ptr(planes), planes.shape[1], rows, groups, D,
+                                          planes.shape[0], _stream()), "mtn_gate_planes_fwd")
+    return planes

@@ -203,6 +203,55 @@ size_t mtn_si_snr_workspace_bytes(int batch, int T);
 int mtn_si_snr_pit_fwd(const float* est, const float* src, const float* mix, int ld_mix, int batch, int T,
                        void* workspace, size_t workspace_bytes, float* out, mtn_stream_t stream);
 
+/* ---- DPMamba (dual-path) glue, SURVEY 8f rank 1 ------------------------------------------------------------------
+ * The mask network of the dpmamba_* recipes is speechbrain 1.0.0 `Dual_Path_Model` [third party, not vendored]
+ * (Mamba-TasNet/hparams/WSJ0Mix/dpmamba_L.yaml:164-174) with MambaBlocksSequential as intra and inter model; its forward
+ * is restated in the vendored subclass Mamba-TasNet/modules/dual_path.py:56-150.  The reference's 4-D tensor [B, N, K, S]
+ * is held as fp32 rows (b, s, k) x C ("layout A", consumed by the intra model) or (b, k, s) x C ("layout T", inter). */
+
+/* GroupNorm(1, C, eps) = `select_norm("ln", ...)` of speechbrain: one mean / biased variance per utterance over all
+ * rows x C elements.  Pass 1: deterministic partial sums, `partials` = mtn_gn_partials_bytes(batch, rows, C) bytes,
+ * 16-byte aligned.  Replaces `self.norm` (dual_path.py:83) and intra_norm / inter_norm of every Dual_Computation_Block. */
+size_t mtn_gn_partials_bytes(int batch, int rows, int C);
+int mtn_gn_stats_fwd(const float* x /* [batch][rows][C] */, void* partials, int batch, int rows, int C, mtn_stream_t stream);
+
+typedef struct {
+    const float* x;        /* fp32 [batch][S*K][C]; rows ordered (s, k), or (k, s) when x_transposed */
+    const void* partials;  /* from mtn_gn_stats_fwd on x */
+    const float* w;        /* [C] GroupNorm weight */
+    const float* bias;     /* [C] GroupNorm bias */
+    const float* skip;     /* nullable fp32 [batch][S][K][C]: added after the affine (the block's residual connections) */
+    float* out_a;          /* nullable fp32 [batch][S][K][C] */
+    float* out_a2;         /* nullable second copy in the same layout (the next stack's input buffer, which it consumes) */
+    float* out_t;          /* nullable fp32 [batch][K][S][C]: the same values with rows transposed (inter-model input) */
+    void* planes;          /* nullable bf16 operand planes [n_planes][plane_rows][C], rows as out_a */
+    int batch, S, K, C;
+    int x_transposed;
+    int n_planes, plane_rows;
+    float eps;
+} mtn_gn_apply_args;
+/* Pass 2: y = (x - mean) * rstd * w + bias (+ skip), written to every non-NULL output. */
+int mtn_gn_apply_fwd(const mtn_gn_apply_args* args, mtn_stream_t stream);
+
+/* Number of chunks S that Dual_Path_Model._Segmentation makes of L frames with chunk size K (50 % overlap, zero padded). */
+int mtn_dp_num_chunks(int L, int K);
+/* _padding + _Segmentation: x fp32 [batch][L][C] -> out_a (and out_a2, nullable) fp32 [batch][S][K][C]. */
+int mtn_dp_segment_fwd(const float* x, float* out_a, float* out_a2, int batch, int L, int C, int K, int S,
+                       mtn_stream_t stream);
+/* PReLU (one slope, dual_path.py:112) + _over_add (dual_path.py:126): X fp32 [batch][S][K][C] -> operand planes
+ * [n_planes][plane_rows >= batch*L][C] of the frame-domain sum, ready for the conv2d 1x1 (dual_path.py:117; applied after
+ * the overlap-add here, which is the same linear map on half the rows -- its bias then counts twice). */
+int mtn_dp_overadd_prelu_fwd(const float* X, const float* prelu_w, void* planes, int plane_rows, int batch, int L, int C,
+                             int K, int S, int n_planes, mtn_stream_t stream);
+/* planes = x + bias_scale * bias; x fp32 [rows][ldx], first C columns. */
+int mtn_bias_planes_fwd(const float* x, int ldx, const float* bias, float bias_scale, void* planes, int plane_rows, int rows,
+                        int C, int n_planes, mtn_stream_t stream);
+/* Gated output layer `output(x) * output_gate(x)` (dual_path.py:127): og fp32 [rows][groups][2*D] = pre-activations
+ * (tanh branch | sigmoid branch) per speaker group -> planes [n_planes][plane_rows][groups*D] =
+ * tanh(o + bo) * sigmoid(g + bg). */
+int mtn_gate_planes_fwd(const float* og, const float* bo, const float* bg, void* planes, int plane_rows, int rows, int groups,
+                        int D, int n_planes, mtn_stream_t stream);
+
 const char* mtn_last_error_string(void);
 int mtn_abi_version(void);
 

@@ -19,7 +19,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 from oracle import ref_shims  # noqa: E402
-from avse_challenge_b200.hparams import CONFIGS, init_state_dicts  # noqa: E402
+from avse_challenge_b200.hparams import CONFIGS, DP_CONFIGS, init_state_dicts, init_dp_state_dicts  # noqa: E402
 from avse_challenge_b200.synth import synth_mixture  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
@@ -118,6 +118,34 @@ def golden_stream(mask, tag):
     print(f"stream_{tag}.npz", "max |streamed - one-shot|", float((streamed - full).abs().max()))
 
 
+def golden_dp(tag, T, batch, seed, skip_around_intra):
+    """DPMamba: the reference's ``Dual_Path_Model_Skip`` (vendored forward, ``modules/dual_path.py``) over the published
+    speechbrain ``Dual_Path_Model`` members, with the real ``MambaBlocksSequential`` as intra / inter model."""
+    from dataclasses import replace
+    hp = replace(DP_CONFIGS["tiny"], skip_around_intra=skip_around_intra)
+    ref = ref_shims.load_reference()
+    enc, mask, dec = ref_shims.build_reference_dp_model(hp.as_dict(), seed=seed)
+    sds = init_dp_state_dicts(hp, seed)
+    enc.load_state_dict(sds["encoder"], strict=True)
+    mask.load_state_dict(sds["masknet"], strict=True)
+    dec.load_state_dict(sds["decoder"], strict=True)
+    mix, src = synth_mixture(batch, T, hp.sample_rate, seed=seed)
+    with torch.no_grad():
+        mix_w = enc(mix)
+        est_mask = mask(mix_w)
+        est = ref.compute_forward(enc, mask, dec, mix)
+    arrs = {"mix": mix.numpy(), "src": src.numpy(), "est": est.numpy(), "mix_w": mix_w.numpy(),
+            "est_mask": est_mask.numpy(), "T": np.int64(T), "batch": np.int64(batch),
+            "skip_around_intra": np.int64(skip_around_intra), "chunk_size": np.int64(hp.chunk_size),
+            "n_dp": np.int64(hp.n_dp)}
+    arrs.update(_np(enc.state_dict(), "encoder"))
+    arrs.update(_np(mask.state_dict(), "masknet"))
+    arrs.update(_np(dec.state_dict(), "decoder"))
+    np.savez_compressed(os.path.join(OUT, f"forward_{tag}.npz"), **arrs)
+    print(tag, "est rms", float(est.pow(2).mean().sqrt()), "file",
+          os.path.getsize(os.path.join(OUT, f"forward_{tag}.npz")) // 1024, "KiB")
+
+
 def golden_si_snr():
     """``cal_si_snr`` of the reference itself (``baseline/avse2/utils/dnn.py:15-57``; plain torch, imported from the
     reference tree) on seeded (source, estimate) pairs: pins ``oracle.restate.cal_si_snr``."""
@@ -148,6 +176,8 @@ def main():
     golden_si_snr()
     _, mask, _ = golden_forward("tiny", T=1203, batch=2, seed=55, tag="tiny_causal", own_init=True, bidirectional=False)
     golden_stream(mask, "tiny_causal")
+    golden_dp("dp_tiny_skip", T=1203, batch=2, seed=91, skip_around_intra=True)
+    golden_dp("dp_tiny_noskip", T=811, batch=1, seed=92, skip_around_intra=False)
 
 
 if __name__ == "__main__":

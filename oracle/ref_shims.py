@@ -92,6 +92,109 @@ class _SBConv1d(nn.Module):
         return self.conv(x.transpose(1, -1)).transpose(1, -1)
 
 
+class _DualComputationBlock(nn.Module):
+    """speechbrain 1.0.0 ``lobes.models.dual_path.Dual_Computation_Block`` [3P, restated from the published source]
+    restricted to ``linear_layer_after_inter_intra=False`` (all dpmamba recipes, ``dpmamba_L.yaml:173``)."""
+
+    def __init__(self, intra_mdl, inter_mdl, out_channels, norm="ln", skip_around_intra=True,
+                 linear_layer_after_inter_intra=True):
+        super().__init__()
+        assert not linear_layer_after_inter_intra and norm == "ln"
+        self.intra_mdl, self.inter_mdl = intra_mdl, inter_mdl
+        self.skip_around_intra = skip_around_intra
+        self.intra_norm = nn.GroupNorm(1, out_channels, eps=1e-8)      # select_norm("ln", out_channels, 4)
+        self.inter_norm = nn.GroupNorm(1, out_channels, eps=1e-8)
+
+    def forward(self, x):
+        B, N, K, S = x.shape
+        intra = x.permute(0, 3, 2, 1).contiguous().view(B * S, K, N)
+        intra = self.intra_mdl(intra)
+        intra = intra.view(B, S, K, N).permute(0, 3, 2, 1).contiguous()
+        intra = self.intra_norm(intra)
+        if self.skip_around_intra:
+            intra = intra + x
+        inter = intra.permute(0, 2, 3, 1).contiguous().view(B * K, S, N)
+        inter = self.inter_mdl(inter)
+        inter = inter.view(B, K, S, N).permute(0, 3, 1, 2).contiguous()
+        inter = self.inter_norm(inter)
+        return inter + intra
+
+
+class _DualPathModel(nn.Module):
+    """speechbrain 1.0.0 ``lobes.models.dual_path.Dual_Path_Model`` [3P, restated from the published source]: members,
+    ``_padding`` / ``_Segmentation`` / ``_over_add`` and ``forward``.  The forward is additionally pinned by the vendored
+    subclass ``Mamba-TasNet/modules/dual_path.py:56-150`` (same statements), which the golden generator runs on top of
+    this class."""
+
+    def __init__(self, in_channels, out_channels, intra_model, inter_model, num_layers=1, norm="ln", K=200, num_spks=2,
+                 skip_around_intra=True, linear_layer_after_inter_intra=True, use_global_pos_enc=False, max_length=20000):
+        super().__init__()
+        import copy
+        assert not use_global_pos_enc
+        self.K, self.num_spks, self.num_layers = K, num_spks, num_layers
+        self.use_global_pos_enc = use_global_pos_enc
+        self.norm = nn.GroupNorm(1, in_channels, eps=1e-8)             # select_norm(norm, in_channels, 3)
+        self.conv1d = nn.Conv1d(in_channels, out_channels, 1, bias=False)
+        self.dual_mdl = nn.ModuleList([
+            copy.deepcopy(_DualComputationBlock(intra_model, inter_model, out_channels, norm,
+                                                skip_around_intra=skip_around_intra,
+                                                linear_layer_after_inter_intra=linear_layer_after_inter_intra))
+            for _ in range(num_layers)])
+        self.conv2d = nn.Conv2d(out_channels, out_channels * num_spks, kernel_size=1)
+        self.end_conv1x1 = nn.Conv1d(out_channels, in_channels, 1, bias=False)
+        self.prelu = nn.PReLU()
+        self.activation = nn.ReLU()
+        self.output = nn.Sequential(nn.Conv1d(out_channels, out_channels, 1), nn.Tanh())
+        self.output_gate = nn.Sequential(nn.Conv1d(out_channels, out_channels, 1), nn.Sigmoid())
+
+    def forward(self, x):
+        x = self.norm(x)
+        x = self.conv1d(x)
+        x, gap = self._Segmentation(x, self.K)
+        for i in range(self.num_layers):
+            x = self.dual_mdl[i](x)
+        x = self.prelu(x)
+        x = self.conv2d(x)
+        B, _, K, S = x.shape
+        x = x.view(B * self.num_spks, -1, K, S)
+        x = self._over_add(x, gap)
+        x = self.output(x) * self.output_gate(x)
+        x = self.end_conv1x1(x)
+        _, N, L = x.shape
+        x = x.view(B, self.num_spks, N, L)
+        x = self.activation(x)
+        return x.transpose(0, 1)
+
+    def _padding(self, input, K):
+        B, N, L = input.shape
+        P = K // 2
+        gap = K - (P + L % K) % K
+        if gap > 0:
+            input = torch.cat([input, torch.zeros(B, N, gap).type(input.type())], dim=2)
+        _pad = torch.zeros(B, N, P).type(input.type())
+        return torch.cat([_pad, input, _pad], dim=2), gap
+
+    def _Segmentation(self, input, K):
+        B, N, L = input.shape
+        P = K // 2
+        input, gap = self._padding(input, K)
+        input1 = input[:, :, :-P].contiguous().view(B, N, -1, K)
+        input2 = input[:, :, P:].contiguous().view(B, N, -1, K)
+        input = torch.cat([input1, input2], dim=3).view(B, N, -1, K).transpose(2, 3)
+        return input.contiguous(), gap
+
+    def _over_add(self, input, gap):
+        B, N, K, S = input.shape
+        P = K // 2
+        input = input.transpose(2, 3).contiguous().view(B, N, -1, K * 2)
+        input1 = input[:, :, :, :K].contiguous().view(B, N, -1)[:, :, P:]
+        input2 = input[:, :, :, K:].contiguous().view(B, N, -1)[:, :, :-P]
+        input = input1 + input2
+        if gap > 0:
+            input = input[:, :, :-gap]
+        return input
+
+
 _loaded = None
 
 
@@ -123,6 +226,7 @@ def load_reference():
     mod("speechbrain.lobes")
     mod("speechbrain.lobes.models")
     mod("speechbrain.lobes.models.conv_tasnet", ChannelwiseLayerNorm=_ChannelwiseLayerNorm)
+    mod("speechbrain.lobes.models.dual_path", Dual_Path_Model=_DualPathModel)
 
     sys.dont_write_bytecode = True  # reference tree is read-only
     if _MT_ROOT not in sys.path:
@@ -159,6 +263,10 @@ def load_reference():
     sys.modules["mamba_ssm"].Mamba = UniMamba
     from modules.mamba_masknet import MaskNet  # noqa: E402
     from modules.mamba_blocks import MambaBlocksSequential  # noqa: E402
+
+    import contextlib
+    import io
+    from modules.dual_path import Dual_Path_Model_Skip  # noqa: E402  (vendored subclass: its forward is the pinned one)
 
     class InferenceParams:
         """mamba_ssm.utils.generation.InferenceParams restricted to the two fields the vendored code reads
@@ -208,6 +316,7 @@ def load_reference():
         MaskNet=MaskNet, MambaBlocksSequential=MambaBlocksSequential, BiMamba=BiMamba, Block=Block,
         selective_scan_ref=ssi.selective_scan_ref, Encoder=RefEncoder, Decoder=RefDecoder,
         compute_forward=compute_forward, ssi=ssi, UniMamba=UniMamba, InferenceParams=InferenceParams,
+        Dual_Path_Model=_DualPathModel, Dual_Path_Model_Skip=Dual_Path_Model_Skip,
     )
     return _loaded
 
@@ -222,6 +331,29 @@ def build_reference_model(hp, seed=1234, bidirectional=True):
     mask = ref.MaskNet(enc_dim=hp["enc_dim"], bot_dim=hp["d_model"], n_spk=2, n_mamba=hp["n_mamba"],
                        bidirectional=bidirectional, d_model=hp["d_model"], d_state=16, expand=2, d_conv=4,
                        fused_add_norm=False, rms_norm=True, residual_in_fp32=False)
+    dec = ref.Decoder(in_channels=hp["enc_dim"], out_channels=1, kernel_size=hp["kernel_size"],
+                      stride=hp["kernel_size"] // 2, bias=False)
+    return enc.eval(), mask.eval(), dec.eval()
+
+
+def build_reference_dp_model(hp, seed=1234):
+    """DPMamba as ``hparams/WSJ0Mix/dpmamba_*.yaml:135-181`` builds it: Encoder, ``Dual_Path_Model`` with one
+    ``MambaBlocksSequential(n_mamba_dp // 2)`` each as intra and inter model, Decoder.  The mask network is instantiated
+    through the vendored ``Dual_Path_Model_Skip`` (``modules/dual_path.py``, ``skip_n_block=0``) so that the forward that
+    runs is the one in the reference tree.  ``hp``: dict of a ``DPHParams``."""
+    import contextlib
+    import io
+    ref = load_reference()
+    torch.manual_seed(seed)
+    enc = ref.Encoder(kernel_size=hp["kernel_size"], out_channels=hp["enc_dim"])
+    mk = lambda: ref.MambaBlocksSequential(n_mamba=hp["n_mamba_dp"] // 2, bidirectional=True, d_model=hp["d_model"],
+                                           d_state=16, expand=2, d_conv=4, fused_add_norm=False, rms_norm=True,
+                                           residual_in_fp32=False)
+    with contextlib.redirect_stdout(io.StringIO()):       # the vendored ctor prints skip_n_block
+        mask = ref.Dual_Path_Model_Skip(in_channels=hp["enc_dim"], out_channels=hp["d_model"], intra_model=mk(),
+                                        inter_model=mk(), num_layers=hp["n_dp"], norm="ln", K=hp["chunk_size"], num_spks=2,
+                                        skip_around_intra=hp["skip_around_intra"], skip_n_block=0,
+                                        linear_layer_after_inter_intra=False)
     dec = ref.Decoder(in_channels=hp["enc_dim"], out_channels=1, kernel_size=hp["kernel_size"],
                       stride=hp["kernel_size"] // 2, bias=False)
     return enc.eval(), mask.eval(), dec.eval()

@@ -297,6 +297,86 @@ def separate(mix, sds, n_mamba, n_spk=2, scan_impl="auto", taps=None):
 
 
 # ---------------------------------------------------------------------------------------------------------------
+# DPMamba: speechbrain 1.0.0 ``Dual_Path_Model`` [3P, not vendored; published algorithm] whose forward
+# is restated in the vendored subclass ``Mamba-TasNet/modules/dual_path.py:56-150`` (cited below as dp.py).
+def group_norm1(x, w, b, eps=1e-8):
+    """``nn.GroupNorm(1, C, eps=1e-8)`` (= speechbrain ``select_norm("ln", ...)``) on channel-last ``[B, ..., C]``: one
+    mean / biased variance per utterance over everything but the batch axis, per-channel affine."""
+    dims = tuple(range(1, x.dim()))
+    mean = x.mean(dim=dims, keepdim=True)
+    var = x.var(dim=dims, keepdim=True, unbiased=False)
+    return (x - mean) / torch.sqrt(var + eps) * w + b
+
+
+def dp_num_chunks(L, K):
+    P = K // 2
+    gap = K - (P + L % K) % K                                              # Dual_Path_Model._padding
+    return 2 * ((L + gap + P) // K), gap
+
+
+def dp_segment(x, K):
+    """``_padding`` + ``_Segmentation`` on channel-last ``[B, L, C]`` -> ``[B, S, K, C]`` (chunk s starts at padded
+    position s*K/2: the even chunks tile ``padded[:-P]``, the odd ones ``padded[P:]``)."""
+    B, L, C = x.shape
+    P = K // 2
+    S, gap = dp_num_chunks(L, K)
+    padded = F.pad(x, (0, 0, P, gap + P))
+    return torch.stack([padded[:, s * P: s * P + K] for s in range(S)], dim=1), gap
+
+
+def dp_over_add(x, gap):
+    """``_over_add`` on ``[B, S, K, C]`` -> ``[B, L, C]``: even chunks laid end to end minus the first P frames, plus odd
+    chunks laid end to end minus the last P, minus the trailing gap."""
+    B, S, K, C = x.shape
+    P = K // 2
+    even = x[:, 0::2].reshape(B, -1, C)[:, P:]
+    odd = x[:, 1::2].reshape(B, -1, C)[:, :-P]
+    out = even + odd
+    return out[:, :-gap] if gap > 0 else out
+
+
+def dp_masknet_fwd(mix_w, sd, n_dp, K, skip_around_intra, n_mamba_stack=1, n_spk=2, scan_impl="auto"):
+    """``Dual_Path_Model.forward`` (dp.py:56-150 with ``skip_n_block = 0``) + ``Dual_Computation_Block.forward`` on
+    channel-last ``mix_w [B, L, N]``; returns the mask ``[n_spk, B, L, N]``."""
+    B, L, N = mix_w.shape
+    x = group_norm1(mix_w, sd["norm.weight"], sd["norm.bias"])             # dp.py:83
+    x = _mm(x, sd["conv1d.weight"][:, :, 0])                               # dp.py:88
+    x, gap = dp_segment(x, K)                                              # dp.py:97  [B, S, K, D]
+    S, D = x.shape[1], x.shape[3]
+    for i in range(n_dp):                                                  # dp.py:113-119
+        p = f"dual_mdl.{i}."
+        intra = mamba_stack_fwd(x.reshape(B * S, K, D), sd, n_mamba_stack, prefix=p + "intra_mdl.",
+                                scan_impl=scan_impl).reshape(B, S, K, D)
+        intra = group_norm1(intra, sd[p + "intra_norm.weight"], sd[p + "intra_norm.bias"])
+        if skip_around_intra:
+            intra = intra + x
+        inter = mamba_stack_fwd(intra.transpose(1, 2).reshape(B * K, S, D), sd, n_mamba_stack, prefix=p + "inter_mdl.",
+                                scan_impl=scan_impl).reshape(B, K, S, D).transpose(1, 2)
+        inter = group_norm1(inter, sd[p + "inter_norm.weight"], sd[p + "inter_norm.bias"])
+        x = inter + intra
+    x = torch.where(x >= 0, x, sd["prelu.weight"] * x)                     # dp.py:126
+    w2 = sd["conv2d.weight"][:, :, 0, 0]
+    x = _mm(x, w2) + sd["conv2d.bias"]                                     # dp.py:131  [B, S, K, spk*D]
+    x = x.reshape(B, S, K, n_spk, D).permute(0, 3, 1, 2, 4).reshape(B * n_spk, S, K, D)   # dp.py:137 (view B*spks)
+    x = dp_over_add(x, gap)                                                # dp.py:140  [B*spk, L, D]
+    o = torch.tanh(_mm(x, sd["output.0.weight"][:, :, 0]) + sd["output.0.bias"])
+    g = torch.sigmoid(_mm(x, sd["output_gate.0.weight"][:, :, 0]) + sd["output_gate.0.bias"])
+    x = _mm(o * g, sd["end_conv1x1.weight"][:, :, 0])                      # dp.py:141-146
+    x = F.relu(x.reshape(B, n_spk, L, N))                                  # dp.py:152-154
+    return x.transpose(0, 1)                                               # dp.py:157  [spk, B, L, N]
+
+
+def separate_dp(mix, sds, hp, scan_impl="auto"):
+    """``Separation.compute_forward`` (``train_wsj0mix.py:86-111``) with the DPMamba mask network; ``hp``: DPHParams."""
+    mix_w = encoder_fwd(mix, sds["encoder"]["conv1d.weight"])
+    mask = dp_masknet_fwd(mix_w, sds["masknet"], hp.n_dp, hp.chunk_size, hp.skip_around_intra, hp.n_mamba_dp // 2,
+                          hp.n_spk, scan_impl)
+    est = torch.stack([decoder_fwd(mix_w * mask[s], sds["decoder"]["weight"]) for s in range(hp.n_spk)], dim=-1)
+    T, T_est = mix.shape[1], est.shape[1]
+    return F.pad(est, (0, 0, 0, T - T_est)) if T > T_est else est[:, :T, :]
+
+
+# ---------------------------------------------------------------------------------------------------------------
 # Evaluation metrics (SURVEY 8f rank 3)
 def cal_si_snr(source, estimate):
     """SI-SNR in dB per (utterance, channel); ``source``, ``estimate`` [B, T, C].

@@ -136,3 +136,32 @@ def test_streaming_restatement_matches_reference_inference_cache(golden_dir):
     rows = [restate.mixer_step(x[:, t], m, p, cs, ss) for t in range(3)]
     assert (torch.stack(rows, dim=1) - chunk).abs().max().item() <= 2e-6
     assert (cs - st0["conv"]).abs().max().item() <= 1e-6 and (ss - st0["ssm"]).abs().max().item() <= 1e-6
+
+
+# ------------------------------------------------------------------------------------------------ DPMamba
+@pytest.mark.parametrize("tag", ["dp_tiny_skip", "dp_tiny_noskip"])
+def test_dpmamba_restatement_matches_reference_golden(golden_dir, tag):
+    """Golden = the reference's vendored Dual_Path_Model_Skip.forward over the real MambaBlocksSequential stacks."""
+    from dataclasses import replace
+    from avse_challenge_b200.hparams import DP_CONFIGS
+    path = os.path.join(golden_dir, f"forward_{tag}.npz")
+    sds, out, _ = load_golden_forward(path)
+    z = np.load(path)
+    hp = replace(DP_CONFIGS["tiny"], skip_around_intra=bool(z["skip_around_intra"]), chunk_size=int(z["chunk_size"]),
+                 n_dp=int(z["n_dp"]))
+    with torch.no_grad():
+        mix_w = restate.encoder_fwd(out["mix"], sds["encoder"]["conv1d.weight"])
+        mask = restate.dp_masknet_fwd(mix_w, sds["masknet"], hp.n_dp, hp.chunk_size, hp.skip_around_intra, scan_impl="c")
+        est = restate.separate_dp(out["mix"], sds, hp, scan_impl="c")
+    assert (mask.permute(0, 1, 3, 2) - out["est_mask"]).abs().max().item() <= 2e-6
+    assert (est - out["est"]).abs().max().item() <= 2e-6
+
+
+@pytest.mark.parametrize("L,K", [(3999, 250), (7, 10), (10, 10), (249, 250), (250, 250), (375, 250), (11999, 250)])
+def test_dp_segmentation_round_trip(L, K):
+    """over_add(segment(x)) == 2 x (every frame is covered by exactly two chunks), chunk count as the reference's."""
+    x = torch.randn(2, L, 3)
+    seg, gap = restate.dp_segment(x, K)
+    S, gap2 = restate.dp_num_chunks(L, K)
+    assert seg.shape == (2, S, K, 3) and gap == gap2 and S % 2 == 0
+    assert torch.allclose(restate.dp_over_add(seg, gap), 2 * x)
