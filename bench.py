@@ -52,6 +52,8 @@ def parse():
     ap.add_argument("--mode", default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--model", default="mambatasnet", choices=["mambatasnet", "dpmamba"],
+                    help="dpmamba: the dual-path recipes (hparams/WSJ0Mix/dpmamba_*.yaml), SURVEY 8f rank 1")
     ap.add_argument("--causal", action="store_true",
                     help="unidirectional stack (bidirectional=False, mamba_blocks.py:128): one scan direction per layer")
     ap.add_argument("--chunk-ms", type=float, default=20.0, help="stream: audio per push() call")
@@ -86,6 +88,8 @@ def workload_config(a, n_gpus):
             "custom": "custom", "stream": "streaming (SURVEY 8f rank 2)"}[a.workload]
     if a.causal:
         name += " [causal: bidirectional=False]"
+    if a.model == "dpmamba":
+        name += " [DPMamba mask network: Dual_Path_Model, K=250]"
     if a.workload == "longform":
         return {
             "workload": (f"{name}: Mamba-TasNet {a.hparams} hparams, one {a.seconds:g} s @ {a.sample_rate // 1000} kHz "
@@ -110,7 +114,8 @@ def scaling_kind(a):
 
 
 # ------------------------------------------------------------------------------------------ CPU reference arm
-def cpu_reference_throughput(hparams: str, sample_rate: int, steps: int, warmup: int, budget_s: float, causal: bool = False):
+def cpu_reference_throughput(hparams: str, sample_rate: int, steps: int, warmup: int, budget_s: float, causal: bool = False,
+                             model: str = "mambatasnet"):
     """Time the oracle port of the reference's CPU forward (selective_scan_ref = per-step torch loop,
     Mamba-TasNet/modules/mamba/selective_scan_interface.py:91-157) on a bounded sample of the workload."""
     import torch
@@ -119,15 +124,23 @@ def cpu_reference_throughput(hparams: str, sample_rate: int, steps: int, warmup:
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    hp = CONFIGS[hparams].causal() if causal else CONFIGS[hparams]
-    sds = init_state_dicts(hp, 1234)
+    if model == "dpmamba":
+        from avse_challenge_b200 import DP_CONFIGS, init_dp_state_dicts
+        hp = DP_CONFIGS[hparams]
+        sds = init_dp_state_dicts(hp, 1234)
+    else:
+        hp = CONFIGS[hparams].causal() if causal else CONFIGS[hparams]
+        sds = init_state_dicts(hp, 1234)
 
     def run(seconds):
         T = int(round(seconds * sample_rate)) // 8 * 8
         mix, _ = synth_mixture(1, T, sample_rate, seed=1234)
         t0 = time.perf_counter()
         with torch.no_grad():
-            restate.separate(mix, sds, hp.n_mamba, scan_impl="torch")
+            if model == "dpmamba":
+                restate.separate_dp(mix, sds, hp, scan_impl="torch")
+            else:
+                restate.separate(mix, sds, hp.n_mamba, scan_impl="torch")
         return time.perf_counter() - t0, T / sample_rate
 
     # calibrate on a very short clip, then pick the longest sample that keeps (steps + warmup) inside the budget
@@ -153,7 +166,7 @@ def run_reference_arm(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    base, dt = cpu_reference_throughput(a.hparams, a.sample_rate, a.steps, a.warmup, budget_s=150.0, causal=a.causal)
+    base, dt = cpu_reference_throughput(a.hparams, a.sample_rate, a.steps, a.warmup, budget_s=150.0, causal=a.causal, model=a.model)
     line = {
         "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": a.gpus,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
@@ -251,19 +264,33 @@ def run_b200_arm(a):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    hp = CONFIGS[a.hparams].causal() if a.causal else CONFIGS[a.hparams]
     T = int(round(a.seconds * a.sample_rate)) // 8 * 8
-    L = hp.frames(T)
-    sds = init_state_dicts(hp, 1234)
+    if a.model == "dpmamba":
+        from avse_challenge_b200 import DP_CONFIGS, init_dp_state_dicts
+        from avse_challenge_b200.dpmamba import DPSeparatorEngine
+        from avse_challenge_b200 import ops as _ops
+        dhp = DP_CONFIGS[a.hparams]
+        hp = dhp.stack                        # what one scan launch sees: the intra / inter stack
+        sds = init_dp_state_dicts(dhp, 1234)
+        L = dhp.frames(T)
+        scan_tokens = a.batch * _ops.dp_num_chunks(L, dhp.chunk_size) * dhp.chunk_size
+    else:
+        hp = CONFIGS[a.hparams].causal() if a.causal else CONFIGS[a.hparams]
+        L = hp.frames(T)
+        sds = init_state_dicts(hp, 1234)
+        scan_tokens = a.batch * L
     mix_cpu, _ = synth_mixture(min(a.batch, 8), T, a.sample_rate, seed=1234 + rank)
     reps = (a.batch + mix_cpu.shape[0] - 1) // mix_cpu.shape[0]
     mix_cpu = mix_cpu.repeat(reps, 1)[: a.batch].contiguous()      # synthetic batch (8 distinct voices tiled)
-    eng = SeparatorEngine(hp, sds, device=dev, mode=a.mode, use_graph=not a.no_graph)
+    if a.model == "dpmamba":
+        eng = DPSeparatorEngine(dhp, sds, device=dev, mode=a.mode, use_graph=not a.no_graph)
+    else:
+        eng = SeparatorEngine(hp, sds, device=dev, mode=a.mode, use_graph=not a.no_graph)
     audio_s_per_step = a.batch * T / a.sample_rate
 
     cpu_base = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        cpu_base, _ = cpu_reference_throughput(a.hparams, a.sample_rate, steps=1, warmup=0, budget_s=30.0, causal=a.causal)
+        cpu_base, _ = cpu_reference_throughput(a.hparams, a.sample_rate, steps=1, warmup=0, budget_s=30.0, causal=a.causal, model=a.model)
 
     def barrier():
         if world > 1:
@@ -319,19 +346,19 @@ def run_b200_arm(a):
     if rank == 0:
         peak, peak_src, peaks = load_peaks()
         scan_ms = prof["scan"]["ms"]
-        alg = scan_algorithmic_bytes(hp, a.batch, L, a.mode, 2 if hp.bidirectional else 1)
+        alg = scan_algorithmic_bytes(hp, 1, scan_tokens, a.mode, 2 if hp.bidirectional else 1)
         achieved = alg / (scan_ms * 1e-3) / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "scan_traffic.json")
         if os.path.exists(tp):
             try:
                 tj = json.load(open(tp))
-                key = f"{a.hparams}_b{a.batch}_{a.mode}" + ("" if hp.bidirectional else "_causal")
+                key = f"{a.hparams}_b{a.batch}_{a.mode}" + ("" if hp.bidirectional else "_causal") + ("_dp" if a.model == "dpmamba" else "")
                 traffic = tj.get(key, {}).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
         sm_mhz = (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
-        n_exp = (2 if hp.bidirectional else 1) * a.batch * L * hp.d_inner * hp.d_state
+        n_exp = (2 if hp.bidirectional else 1) * scan_tokens * hp.d_inner * hp.d_state
         mufu_ms = n_exp / (148 * 16 * sm_mhz * 1e6) * 1e3
         step_ms = ms_total / a.steps
         total_prof = sum(v["ms_per_forward"] for v in prof.values())
@@ -344,6 +371,7 @@ def run_b200_arm(a):
                     "h2d_bytes_per_step": a.batch * T * 4, "d2h_bytes_per_step": a.batch * T * hp.n_spk * 4,
                     "ms_per_step": ms_e2e / a.steps},
             "gpu_launches": a.steps * sum(v["launches"] for v in prof.values()) + a.steps,  # +1: decoder = 2 kernels
+            "launches_per_step": sum(v["launches"] for v in prof.values()) + 1,
             "roofline": {"kernel": "mtn::scan_kernel_pair / scan_kernel (selective scan, both directions per launch)", "bound": "hbm",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": peak_src, "traffic": traffic, "algorithmic_bytes_per_launch": alg,
@@ -385,7 +413,7 @@ def run_longform_arm(a):
     sp = SequenceParallelSeparator(hp, sds, device=dev, mode=a.mode, sub_chunks=a.sub_chunks, exchange=a.exchange)
     cpu_base = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        cpu_base, _ = cpu_reference_throughput(a.hparams, a.sample_rate, steps=1, warmup=0, budget_s=30.0, causal=a.causal)
+        cpu_base, _ = cpu_reference_throughput(a.hparams, a.sample_rate, steps=1, warmup=0, budget_s=30.0, causal=a.causal, model=a.model)
 
     def barrier():
         if world > 1:
