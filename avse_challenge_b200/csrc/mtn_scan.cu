@@ -1047,6 +1047,9 @@ static int launch_scan_tc(const mtn_scan_args* a, cudaStream_t stream) {
 
 }  // namespace mtn
 #include "mtn_scan_pair.cuh"
+#ifdef MTN_SCAN_DEV
+#include "mtn_scan_trio.cuh"   // measured and rejected: kept as a dev-build variant only
+#endif
 namespace mtn {
 
 // every measured shape except the widest fp32 one (L hparams, R = 32, two planes: the split mapping with tensor-core dt_proj wins by 4 %)
@@ -1063,6 +1066,7 @@ static int dispatch_scan_variant(const mtn_scan_args* a, cudaStream_t s) {
     if (variant == 75) return launch_scan_pair<P, R, NDBL, ZT, true, false, 7>(a, s);
     if (variant == 85) return launch_scan_pair<P, R, NDBL, ZT, true, false, 8>(a, s);
     if (variant == 7 && a->dtp && a->y) return launch_scan_pair<P, R, NDBL, ZT, true, true>(a, s);  // tensor-core dt_proj
+    if (variant == 9 && a->y) return launch_scan_trio<P, R, NDBL, ZT>(a, s);   // recurrence / prep / post warp trios
 #endif
     // Recurrence / helper warp pairs (mtn_scan_pair.cuh).  Measured on B200 (tools/scan_bench.py): faster
     // than the split mapping for full passes; the summary pass (no y: nothing for the helper to take over) stays on the
