@@ -200,18 +200,18 @@ __device__ __forceinline__ float4 load_x4<__nv_bfloat16>(const __nv_bfloat16* p)
 
 constexpr int CONV_TT = 32;
 
-template <int P, typename XT>
+template <int P, typename XT, int DIRS>   // DIRS: 3 = both directions, 1 = forward only (compile time: keeps the hot both-direction code branch-free)
 __global__ void __launch_bounds__(256)
 conv_silu_kernel(const XT* __restrict__ xz, int ldxz, const float* __restrict__ conv_w, const float* __restrict__ conv_b,
                  __nv_bfloat16* __restrict__ u, size_t u_rows, const float* __restrict__ halo_lo,
-                 const float* __restrict__ halo_hi, int batch, int L, int di, int dir_mask) {
+                 const float* __restrict__ halo_hi, int batch, int L, int di) {
     const int c = (blockIdx.z * blockDim.x + threadIdx.x) * 4;
     if (c >= di) return;
     const int b = blockIdx.y;
     const int t0 = blockIdx.x * CONV_TT;
     const int t1 = min(t0 + CONV_TT, L);
     const size_t plane_stride = u_rows * 2 * di;
-    const bool do_f = dir_mask & 1, do_b = dir_mask & 2;  // unidirectional stacks run the forward half only
+    constexpr bool do_f = DIRS & 1, do_b = DIRS & 2;  // unidirectional stacks run the forward half only
     float4 wf[4], wb[4];  // wf[k] = tap k for channels c..c+3
     {
         float tf[4][4], tb[4][4];
@@ -260,8 +260,9 @@ conv_silu_kernel(const XT* __restrict__ xz, int ldxz, const float* __restrict__ 
                 r.y = fmaf(wb[0].y, w6.y, fmaf(wb[1].y, w5.y, fmaf(wb[2].y, w4.y, fmaf(wb[3].y, w3.y, bb.y))));
                 r.z = fmaf(wb[0].z, w6.z, fmaf(wb[1].z, w5.z, fmaf(wb[2].z, w4.z, fmaf(wb[3].z, w3.z, bb.z))));
                 r.w = fmaf(wb[0].w, w6.w, fmaf(wb[1].w, w5.w, fmaf(wb[2].w, w4.w, fmaf(wb[3].w, w3.w, bb.w))));
-                f = make_float4(silu_f(f.x), silu_f(f.y), silu_f(f.z), silu_f(f.w));
-                r = make_float4(silu_f(r.x), silu_f(r.y), silu_f(r.z), silu_f(r.w));
+                constexpr bool FS = (P == 1);   // one bf16 plane: the result is rounded to 8 mantissa bits anyway
+                if (do_f) f = make_float4(silu_sel<FS>(f.x), silu_sel<FS>(f.y), silu_sel<FS>(f.z), silu_sel<FS>(f.w));
+                if (do_b) r = make_float4(silu_sel<FS>(r.x), silu_sel<FS>(r.y), silu_sel<FS>(r.z), silu_sel<FS>(r.w));
                 const size_t off = (size_t(b) * L + (t + i)) * (2 * di) + c;
                 if (do_f) store_planes4<P>(u, plane_stride, off, f);
                 if (do_b) store_planes4<P>(u, plane_stride, off + di, r);
@@ -498,15 +499,17 @@ extern "C" int mtn_conv_silu_dir_fwd(const void* xz, int ldxz, int xz_bf16, cons
     const int block = threads_needed >= 256 ? 256 : ((threads_needed + 31) / 32) * 32;
     dim3 grid((L + CONV_TT - 1) / CONV_TT, batch, (threads_needed + block - 1) / block);
     __nv_bfloat16* u = reinterpret_cast<__nv_bfloat16*>(u_planes);
+    MTN_REQUIRE(dir_mask == 3 || dir_mask == 1, "conv_silu: dir_mask=%d (3 = both, 1 = forward only)", dir_mask);
+#define MTN_CONV(PP, XT_, DD) \
+    conv_silu_kernel<PP, XT_, DD><<<grid, block, 0, s>>>(reinterpret_cast<const XT_*>(xz), ldxz, conv_w, conv_b, u, size_t(u_rows), halo_lo, halo_hi, batch, L, di)
+#define MTN_CONV_D(PP, XT_) do { if (dir_mask == 3) MTN_CONV(PP, XT_, 3); else MTN_CONV(PP, XT_, 1); } while (0)
     if (xz_bf16) {
-        const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(xz);
-        if (planes == 2) conv_silu_kernel<2, __nv_bfloat16><<<grid, block, 0, s>>>(x, ldxz, conv_w, conv_b, u, size_t(u_rows), halo_lo, halo_hi, batch, L, di, dir_mask);
-        else conv_silu_kernel<1, __nv_bfloat16><<<grid, block, 0, s>>>(x, ldxz, conv_w, conv_b, u, size_t(u_rows), halo_lo, halo_hi, batch, L, di, dir_mask);
+        if (planes == 2) MTN_CONV_D(2, __nv_bfloat16); else MTN_CONV_D(1, __nv_bfloat16);
     } else {
-        const float* x = reinterpret_cast<const float*>(xz);
-        if (planes == 2) conv_silu_kernel<2, float><<<grid, block, 0, s>>>(x, ldxz, conv_w, conv_b, u, size_t(u_rows), halo_lo, halo_hi, batch, L, di, dir_mask);
-        else conv_silu_kernel<1, float><<<grid, block, 0, s>>>(x, ldxz, conv_w, conv_b, u, size_t(u_rows), halo_lo, halo_hi, batch, L, di, dir_mask);
+        if (planes == 2) MTN_CONV_D(2, float); else MTN_CONV_D(1, float);
     }
+#undef MTN_CONV_D
+#undef MTN_CONV
     MTN_CUDA_LAUNCH_CHECK("conv_silu");
     return MTN_OK;
 }

@@ -312,10 +312,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                         }
                         if (EPI == MTN_EPI_INPROJ) {
                             if (gcol >= p.epi_param) {
-                                f.x = silu_f(f.x);
-                                f.y = silu_f(f.y);
-                                f.z = silu_f(f.z);
-                                f.w = silu_f(f.w);
+                                f.x = silu_sel<OUT_BF16>(f.x);   // bf16 output: 1-MUFU form (rounded to bf16 right below)
+                                f.y = silu_sel<OUT_BF16>(f.y);
+                                f.z = silu_sel<OUT_BF16>(f.z);
+                                f.w = silu_sel<OUT_BF16>(f.w);
                             }
                         } else if (EPI == MTN_EPI_RELU) {
                             f.x = fmaxf(f.x, 0.f);

@@ -177,6 +177,16 @@ __device__ __forceinline__ float silu_f(float x) {
     // x * sigmoid(x); exp via ex2 (rel. err ~2^-22), division via rcp.approx (1 ulp)
     return x * rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x));
 }
+// SiLU for values that are rounded to bf16 right away (bf16 mode): x * sigmoid(x) = 0.5 x (1 + tanh(0.5 x)) with ONE MUFU
+// (tanh.approx.f32, max relative error 2^-11 -- below half a bf16 ulp, 2^-9) instead of ex2 + rcp.
+__device__ __forceinline__ float silu_bf16_f(float x) {
+    float t;
+    const float hx = 0.5f * x;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(hx));
+    return fmaf(hx, t, hx);
+}
+template <bool FAST>
+__device__ __forceinline__ float silu_sel(float x) { return FAST ? silu_bf16_f(x) : silu_f(x); }
 // torch.nn.functional.softplus (beta 1, threshold 20): log1p(exp(x)), linear above 20.
 __device__ __forceinline__ float softplus_f(float x) {
     float e = ex2_approx(1.4426950408889634f * x);

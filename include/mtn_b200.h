@@ -154,7 +154,7 @@ int mtn_conv_silu_halo_fwd(const void* xz, int ldxz, int xz_bf16, const float* c
                            void* u_planes, int u_rows /* rows allocated per plane, >= batch*L */, const float* halo_lo,
                            const float* halo_hi, int batch, int L, int di, int planes, mtn_stream_t stream);
 
-/* Same with a direction mask (bit0 forward, bit1 backward): a unidirectional stack (`bidirectional=False`,
+/* Same with a direction mask (3 = both directions, 1 = forward only; backward-only is not built): a unidirectional stack (`bidirectional=False`,
  * modules/mamba_blocks.py:128 -> mamba_ssm.Mamba; the vendored non-fused branch modules/mamba/bimamba.py:271-285) runs
  * dir_mask = 1, conv_w/conv_b then only need their first [di] rows.  With halo_lo = the last 3 conv inputs of the previous
  * chunk this is also the streaming form of the reference's conv_state cache (bimamba.py:274-277, step :327-333). */

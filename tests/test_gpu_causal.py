@@ -43,7 +43,7 @@ def test_conv_dir_mask_forward_only():
     assert torch.equal(u[:, :, :di], both[:, :, :di])
     assert (u[:, :, di:] == 7.0).all()          # backward half untouched
     with pytest.raises(_lib.MtnError):
-        ops.conv_silu(xz, w, b, B, L, di, 2, dir_mask=0)
+        ops.conv_silu(xz, w, b, B, L, di, 2, dir_mask=2)
 
 
 @pytest.mark.parametrize("cuts", [[40], [1, 1, 38], [7, 20, 13]])

@@ -135,6 +135,21 @@ def test_dpmamba_shipped_sizes_vs_oracle(name, B, T):
     assert err <= 1e-3 and d <= 0.01, (err, d)
 
 
+def test_dpmamba_bf16_mode_stated_tolerance():
+    """bf16 mode (bf16 GEMM operands and xz / u / y storage; fp32 scan state, residual stream and GroupNorm statistics).
+    Stated tolerance against the fp32 oracle, as for Mamba-TasNet: max-abs <= 0.15 * rms, SI-SNR(est, ref) >= 25 dB."""
+    from avse_challenge_b200 import si_snr
+    hp = replace(DP_CONFIGS["S"], n_dp=2)
+    sds = init_dp_state_dicts(hp, 1234)
+    mix, src = synth_mixture(1, 8000, seed=3)
+    with torch.no_grad():
+        ref = restate.separate_dp(mix, sds, hp, scan_impl="c")
+    est = DPSeparatorEngine(hp, sds, device=DEV, mode="bf16", use_graph=False)(mix.to(DEV)).cpu()
+    err, fid = rel_max(est, ref), si_snr(est, ref).min().item()
+    print(f"dp_S bf16: max-abs/rms {err:.3e} SI-SNR(est,ref) {fid:.1f} dB")
+    assert err <= 0.15 and fid >= 25.0, (err, fid)
+
+
 def test_dpmamba_unsupported_options_raise():
     mk = lambda **kw: modules.MambaBlocksSequential(1, bidirectional=True, d_model=64, fused_add_norm=False, rms_norm=True, **kw)
     with pytest.raises(NotImplementedError):

@@ -169,6 +169,22 @@ def test_conv_silu_both_directions(di, L, dtype):
     assert rel_mixed(got[..., di:], ref_b) < 2e-5
 
 
+def test_conv_silu_single_plane_uses_bf16_accuracy():
+    """bf16 mode (one plane): the 1-MUFU SiLU (tanh.approx, rel. error 2^-11) must stay below bf16 rounding (2^-9)."""
+    g = torch.Generator().manual_seed(5)
+    B, L, di = 2, 333, 256
+    xz = (torch.randn(B * L, 2 * di, generator=g) * 2).to(torch.bfloat16)
+    cw = torch.randn(2, di, 4, generator=g) * 0.5
+    cb = torch.randn(2, di, generator=g) * 0.5
+    u = ops.conv_silu(xz.to(DEV), cw.to(DEV), cb.to(DEV), B, L, di, 1)
+    xs = xz.float().view(B, L, 2 * di)[..., :di]
+    ref_f = restate.causal_conv_silu(xs, cw[0].unsqueeze(1), cb[0], reverse=False)
+    ref_b = restate.causal_conv_silu(xs, cw[1].unsqueeze(1), cb[1], reverse=True)
+    got = _planes_value(u).view(B, L, 2 * di)
+    assert rel_mixed(got[..., :di], ref_f) < 4e-3      # one bf16 rounding: <= 2^-9 relative (+ rms floor)
+    assert rel_mixed(got[..., di:], ref_b) < 4e-3
+
+
 @pytest.mark.parametrize("N", [64, 256, 512])
 def test_decoder(N):
     g = torch.Generator().manual_seed(N)
