@@ -272,6 +272,122 @@ conv_silu_kernel(const XT* __restrict__ xz, int ldxz, const float* __restrict__ 
     }
 }
 
+// bf16 mode (bf16 xz, one output plane): 8 channels per thread so that every global access is 16 bytes (the 4-channel
+// kernel above moves 8 bytes per access there and reached only 2.1 TB/s at BASELINE config 3).  One direction per CTA
+// (blockIdx.z: low bit = direction when both are requested) keeps the register footprint at 32 weights + a 4-row fp32
+// window; the second read of xs hits L1/L2.  Same fmaf nesting as conv_silu_kernel -> identical results.
+constexpr int CONV8_TT = 32;
+
+__device__ __forceinline__ void unpack_bf16x8(const uint4 raw, float (&v)[8]) {
+    const uint32_t r[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        v[2 * i] = __uint_as_float(r[i] << 16);
+        v[2 * i + 1] = __uint_as_float(r[i] & 0xffff0000u);
+    }
+}
+
+// `dir` is a template parameter: indexing the register window with a run-time direction sent it to local memory (stack
+// frame, 19 % of HBM peak); the kernel below branches once per CTA into the two instantiations.
+template <int dir, bool BOTH_>
+__device__ __forceinline__ void conv_silu_bf16x8_body(const __nv_bfloat16* __restrict__ xz, int ldxz,
+                                                      const float* __restrict__ conv_w, const float* __restrict__ conv_b,
+                                                      __nv_bfloat16* __restrict__ u, const float* __restrict__ halo_lo,
+                                                      const float* __restrict__ halo_hi, int L, int di, int cblk) {
+    const int c = (cblk * blockDim.x + threadIdx.x) * 8;
+    if (c >= di) return;
+    const int b = blockIdx.y;
+    const int t0 = int(blockIdx.x >> (BOTH_ ? 1 : 0)) * CONV8_TT;
+    const int t1 = min(t0 + CONV8_TT, L);
+    float w[4][8], bias[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float4 a = *reinterpret_cast<const float4*>(conv_w + (size_t(dir) * di + c + i) * 4);
+        w[0][i] = a.x; w[1][i] = a.y; w[2][i] = a.z; w[3][i] = a.w;
+        bias[i] = conv_b[size_t(dir) * di + c + i];
+    }
+    const __nv_bfloat16* xbase = xz + size_t(b) * L * ldxz + c;
+    const float* hlo = halo_lo ? halo_lo + size_t(b) * 3 * di + c : nullptr;
+    const float* hhi = halo_hi ? halo_hi + size_t(b) * 3 * di + c : nullptr;
+    auto ld_halo = [&](int t, float (&v)[8]) {      // rows outside [0, L): neighbouring chunk's rows or zero padding
+        const float* h = (t < 0) ? ((hlo && t >= -3) ? hlo + size_t(t + 3) * di : nullptr)
+                                 : ((hhi && t < L + 3) ? hhi + size_t(t - L) * di : nullptr);
+        if (h) {
+            const float4 a = *reinterpret_cast<const float4*>(h), q = *reinterpret_cast<const float4*>(h + 4);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = q.x; v[5] = q.y; v[6] = q.z; v[7] = q.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = 0.f;
+        }
+    };
+    auto ld = [&](int t, float (&v)[8]) {
+        if (t >= 0 && t < L) unpack_bf16x8(*reinterpret_cast<const uint4*>(xbase + size_t(t) * ldxz), v);
+        else ld_halo(t, v);
+    };
+    // forward: out[t] = sum_k w[k] x[t-3+k] -> window rows r[k] = x[t-3+k]; backward: out[t] = sum_k w[k] x[t+3-k] ->
+    // r[k] = x[t+3-k].  Either way the window slides by one row per step in the direction of increasing t: forward drops
+    // r[0] and appends x[t] as r[3]; backward drops r[3] and prepends x[t+3] as r[0].
+    float r[4][8];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) ld(dir ? (t0 + 2 - k) : (t0 - 3 + k), r[dir ? k + 1 : k]);
+    __nv_bfloat16* ubase = u + (size_t(b) * L) * (2 * size_t(di)) + size_t(dir) * di + c;
+    // PF rows are requested together (PF x 16 B in flight per thread: with 16 resident warps per SM a single outstanding
+    // load per thread left the kernel latency-bound at 2.2 TB/s), then consumed one step at a time.
+    constexpr int PF = 8;
+    constexpr int shift = dir ? 3 : 0;                 // the new row of step t is x[t + shift]
+#pragma unroll 1
+    for (int tb = t0; tb < t1; tb += PF) {
+        uint4 raw[PF];
+#pragma unroll
+        for (int j = 0; j < PF; ++j) {
+            const int tr = tb + j + shift;
+            raw[j] = (tb + j < t1 && tr < L) ? *reinterpret_cast<const uint4*>(xbase + size_t(tr) * ldxz)
+                                             : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int j = 0; j < PF; ++j) {
+            const int t = tb + j;
+            if (t < t1) {
+                const int tr = t + shift;
+                if (tr < L) unpack_bf16x8(raw[j], r[dir ? 0 : 3]);
+                else ld_halo(tr, r[dir ? 0 : 3]);
+                uint32_t pk[4];
+#pragma unroll
+                for (int i = 0; i < 8; i += 2) {
+                    float f0 = fmaf(w[0][i], r[0][i], fmaf(w[1][i], r[1][i], fmaf(w[2][i], r[2][i], fmaf(w[3][i], r[3][i], bias[i]))));
+                    float f1 = fmaf(w[0][i + 1], r[0][i + 1],
+                                    fmaf(w[1][i + 1], r[1][i + 1], fmaf(w[2][i + 1], r[2][i + 1], fmaf(w[3][i + 1], r[3][i + 1], bias[i + 1]))));
+                    f0 = silu_bf16_f(f0);
+                    f1 = silu_bf16_f(f1);
+                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(f0, f1);
+                    pk[i / 2] = *reinterpret_cast<const uint32_t*>(&h2);
+                }
+                *reinterpret_cast<uint4*>(ubase + size_t(t) * (2 * size_t(di))) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                if (dir) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { r[3][i] = r[2][i]; r[2][i] = r[1][i]; r[1][i] = r[0][i]; }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { r[0][i] = r[1][i]; r[1][i] = r[2][i]; r[2][i] = r[3][i]; }
+                }
+            }
+        }
+    }
+}
+
+template <bool BOTH>
+__global__ void __launch_bounds__(128)
+conv_silu_bf16x8_kernel(const __nv_bfloat16* __restrict__ xz, int ldxz, const float* __restrict__ conv_w,
+                        const float* __restrict__ conv_b, __nv_bfloat16* __restrict__ u, const float* __restrict__ halo_lo,
+                        const float* __restrict__ halo_hi, int L, int di) {
+    // both directions of a time tile are neighbours in launch order (blockIdx.x = 2 * tile + dir), so the second read
+    // of the tile's xs rows hits L2 instead of DRAM (direction-major order read xs twice from DRAM: ncu 1.06 vs 0.52 GB)
+    if (BOTH && (blockIdx.x & 1))
+        conv_silu_bf16x8_body<1, BOTH>(xz, ldxz, conv_w, conv_b, u, halo_lo, halo_hi, L, di, blockIdx.z);
+    else
+        conv_silu_bf16x8_body<0, BOTH>(xz, ldxz, conv_w, conv_b, u, halo_lo, halo_hi, L, di, blockIdx.z);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Decoder: ConvTranspose1d(N -> 1, k=16, s=8, no bias) per speaker = frame GEMV + overlap-add.
 // Reference: speechbrain dual_path.Decoder == baseline/avse2/model.py:27-37; speaker loop, cat and
@@ -500,6 +616,18 @@ extern "C" int mtn_conv_silu_dir_fwd(const void* xz, int ldxz, int xz_bf16, cons
     dim3 grid((L + CONV_TT - 1) / CONV_TT, batch, (threads_needed + block - 1) / block);
     __nv_bfloat16* u = reinterpret_cast<__nv_bfloat16*>(u_planes);
     MTN_REQUIRE(dir_mask == 3 || dir_mask == 1, "conv_silu: dir_mask=%d (3 = both, 1 = forward only)", dir_mask);
+    if (xz_bf16 && planes == 1 && di % 8 == 0 && ldxz % 8 == 0 && u_rows == batch * L &&
+        (reinterpret_cast<uintptr_t>(xz) & 15) == 0 && (reinterpret_cast<uintptr_t>(u_planes) & 15) == 0) {
+        const int tn = di / 8;
+        const int blk = tn >= 128 ? 128 : ((tn + 31) / 32) * 32;
+        const int cblks = (tn + blk - 1) / blk;
+        dim3 g8(((L + CONV8_TT - 1) / CONV8_TT) * (dir_mask == 3 ? 2 : 1), batch, cblks);
+        const __nv_bfloat16* x8 = reinterpret_cast<const __nv_bfloat16*>(xz);
+        if (dir_mask == 3) conv_silu_bf16x8_kernel<true><<<g8, blk, 0, s>>>(x8, ldxz, conv_w, conv_b, u, halo_lo, halo_hi, L, di);
+        else conv_silu_bf16x8_kernel<false><<<g8, blk, 0, s>>>(x8, ldxz, conv_w, conv_b, u, halo_lo, halo_hi, L, di);
+        MTN_CUDA_LAUNCH_CHECK("conv_silu(bf16x8)");
+        return MTN_OK;
+    }
 #define MTN_CONV(PP, XT_, DD) \
     conv_silu_kernel<PP, XT_, DD><<<grid, block, 0, s>>>(reinterpret_cast<const XT_*>(xz), ldxz, conv_w, conv_b, u, size_t(u_rows), halo_lo, halo_hi, batch, L, di)
 #define MTN_CONV_D(PP, XT_) do { if (dir_mask == 3) MTN_CONV(PP, XT_, 3); else MTN_CONV(PP, XT_, 1); } while (0)

@@ -57,7 +57,7 @@ def parse():
     ap.add_argument("--causal", action="store_true",
                     help="unidirectional stack (bidirectional=False, mamba_blocks.py:128): one scan direction per layer")
     ap.add_argument("--chunk-ms", type=float, default=20.0, help="stream: audio per push() call")
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "longform", "stream", "custom"],
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "longform", "stream", "custom"],
                     help="cfg2 (default): S, 32 x 4 s @ 8 kHz per GPU, fp32 mode, weak scaling.  cfg3: L, global batch "
                          "256 x 4 s sharded over the GPUs, bf16 mode, strong scaling.  longform: one 10-minute 16 kHz "
                          "recording, sequence-parallel over the GPUs (S fp32 unless --hparams/--mode given), strong "
@@ -71,6 +71,11 @@ def parse():
         if "--hparams" not in explicit: a.hparams = "L"
         if "--mode" not in explicit: a.mode = "bf16"
         if "--batch" not in explicit: a.batch = max(1, 256 // world)
+    elif a.workload == "cfg4":   # AVSEC-4-shaped: 16 kHz mono 6 s noisy mixtures, 4096 utterances over the GPUs in micro-batches
+        if "--seconds" not in explicit: a.seconds = 6.0
+        if "--sample-rate" not in explicit: a.sample_rate = 16000
+        if "--mode" not in explicit: a.mode = "bf16"
+        if "--batch" not in explicit: a.batch = 64
     elif a.workload == "longform":
         if "--seconds" not in explicit: a.seconds = 600.0
         if "--sample-rate" not in explicit: a.sample_rate = 16000
@@ -85,6 +90,7 @@ def workload_config(a, n_gpus):
     prec = ("(split-bf16 x3 tcgen05 GEMMs, fp32 scan state)" if a.mode == "fp32"
             else "(bf16 tcgen05 GEMMs + bf16 activations, fp32 scan state)")
     name = {"cfg2": "BASELINE config 2", "cfg3": "BASELINE config 3", "longform": "BASELINE config 5",
+            "cfg4": "BASELINE config 4 (one micro-batch per step; 4096 utterances = 4096 / (batch x GPUs) steps)",
             "custom": "custom", "stream": "streaming (SURVEY 8f rank 2)"}[a.workload]
     if a.causal:
         name += " [causal: bidirectional=False]"
@@ -110,7 +116,7 @@ def workload_config(a, n_gpus):
 
 
 def scaling_kind(a):
-    return "weak" if a.workload in ("cfg2", "custom") else "strong"
+    return "weak" if a.workload in ("cfg2", "cfg4", "custom", "stream") else "strong"
 
 
 # ------------------------------------------------------------------------------------------ CPU reference arm
@@ -279,7 +285,8 @@ def run_b200_arm(a):
         L = hp.frames(T)
         sds = init_state_dicts(hp, 1234)
         scan_tokens = a.batch * L
-    mix_cpu, _ = synth_mixture(min(a.batch, 8), T, a.sample_rate, seed=1234 + rank)
+    mix_cpu, _ = synth_mixture(min(a.batch, 8), T, a.sample_rate, seed=1234 + rank,
+                               noise_second_source=(a.workload == "cfg4"))    # cfg4: speech + noise at 0 dB
     reps = (a.batch + mix_cpu.shape[0] - 1) // mix_cpu.shape[0]
     mix_cpu = mix_cpu.repeat(reps, 1)[: a.batch].contiguous()      # synthetic batch (8 distinct voices tiled)
     if a.model == "dpmamba":

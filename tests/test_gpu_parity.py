@@ -183,6 +183,18 @@ def test_conv_silu_single_plane_uses_bf16_accuracy():
     got = _planes_value(u).view(B, L, 2 * di)
     assert rel_mixed(got[..., :di], ref_f) < 4e-3      # one bf16 rounding: <= 2^-9 relative (+ rms floor)
     assert rel_mixed(got[..., di:], ref_b) < 4e-3
+    # forward-only launch writes the same forward half and leaves the rest alone
+    u1 = torch.full_like(u, 3.0)
+    ops.conv_silu(xz.to(DEV), cw[:1].contiguous().to(DEV), cb[:1].contiguous().to(DEV), B, L, di, 1, u=u1, dir_mask=1)
+    assert torch.equal(u1[..., :di], u[..., :di]) and (u1[..., di:] == 3.0).all()
+    # a time chunk with halos equals the same rows of the full-sequence result (sequence-parallel / streaming use)
+    a, b_ = 100, 217
+    xs3 = xz.view(B, L, 2 * di)
+    chunk = xs3[:, a:b_].contiguous().view(B * (b_ - a), 2 * di)
+    lo = xs3[:, a - 3:a, :di].float().contiguous()
+    hi = xs3[:, b_:b_ + 3, :di].float().contiguous()
+    uc = ops.conv_silu(chunk.to(DEV), cw.to(DEV), cb.to(DEV), B, b_ - a, di, 1, halo_lo=lo.to(DEV), halo_hi=hi.to(DEV))
+    assert torch.equal(uc.view(1, B, b_ - a, 2 * di), u.view(1, B, L, 2 * di)[:, :, a:b_])
 
 
 @pytest.mark.parametrize("N", [64, 256, 512])
