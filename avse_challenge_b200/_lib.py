@@ -49,7 +49,7 @@ class GnApplyArgs(Structure):
         ("x", c_void_p), ("partials", c_void_p), ("w", c_void_p), ("bias", c_void_p), ("skip", c_void_p),
         ("out_a", c_void_p), ("out_a2", c_void_p), ("out_t", c_void_p), ("planes", c_void_p),
         ("batch", c_int), ("S", c_int), ("K", c_int), ("C", c_int), ("x_transposed", c_int),
-        ("n_planes", c_int), ("plane_rows", c_int), ("eps", c_float),
+        ("n_planes", c_int), ("plane_rows", c_int), ("eps", c_float), ("blend", c_void_p),
     ]
 
 

@@ -64,6 +64,7 @@ struct GnApplyParams {
     const float* w;
     const float* bias;
     const float* skip;
+    const float* blend;      // nullable: result = 0.5 * result + 0.5 * blend (Dual_Path_Model_Skip, dual_path.py:114-116)
     float* out_a;
     float* out_a2;
     float* out_t;
@@ -124,6 +125,11 @@ gn_apply_kernel(GnApplyParams p) {
         if (p.skip) {
             const float4 k4 = *reinterpret_cast<const float4*>(p.skip + row_a * p.C + c);
             o.x += k4.x; o.y += k4.y; o.z += k4.z; o.w += k4.w;
+        }
+        if (p.blend) {
+            const float4 r4 = *reinterpret_cast<const float4*>(p.blend + row_a * p.C + c);
+            o.x = 0.5f * o.x + 0.5f * r4.x; o.y = 0.5f * o.y + 0.5f * r4.y;
+            o.z = 0.5f * o.z + 0.5f * r4.z; o.w = 0.5f * o.w + 0.5f * r4.w;
         }
         if (p.out_a) *reinterpret_cast<float4*>(p.out_a + row_a * p.C + c) = o;
         if (p.out_a2) *reinterpret_cast<float4*>(p.out_a2 + row_a * p.C + c) = o;
@@ -272,6 +278,7 @@ extern "C" int mtn_gn_apply_fwd(const mtn_gn_apply_args* a, mtn_stream_t stream)
     MTN_REQUIRE(!a->planes || a->n_planes == 1 || a->n_planes == 2, "gn_apply: n_planes=%d", a->n_planes);
     GnApplyParams p;
     p.x = a->x; p.partials = reinterpret_cast<const double2*>(a->partials); p.w = a->w; p.bias = a->bias; p.skip = a->skip;
+    p.blend = a->blend;
     p.out_a = a->out_a; p.out_a2 = a->out_a2; p.out_t = a->out_t;
     p.planes = reinterpret_cast<__nv_bfloat16*>(a->planes);
     const size_t rows = size_t(a->S) * a->K;

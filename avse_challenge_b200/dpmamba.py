@@ -45,6 +45,7 @@ class DPWorkspace:
         self.X = e((M2, D))                             # dual-path tensor, rows (b, s, k)
         self.I = e((M2, D))                             # intra branch output (kept for the block's residual)
         self.O = e((M2, D))                             # stack output before its GroupNorm
+        self.R = e((M2, D)) if hp.skip_n_block > 0 else None   # segmented input kept for Dual_Path_Model_Skip's blend
         self.partials = ops.gn_partials(batch, max(S * K, L), max(N, D), device)
         self.intra = LayerWorkspace(hp.stack, batch * S, K, device, mode)
         self.inter = copy.copy(self.intra)              # same buffers, viewed as B*K sequences of S frames
@@ -134,8 +135,14 @@ class DPSeparatorEngine:
         op("gn_apply", ops.gn_apply, ws.mix_w, ws.partials, self.norm_w, self.norm_b, B, 1, L, N, planes=ws.yn)
         op("gemm_conv1d", ops.gemm, ws.yn, self.w_conv1d, M, D, N, out=ws.xc)               # dual_path.py:88
         op("dp_segment", ops.dp_segment, ws.xc, B, L, D, K, S, ws.X, ws.intra.h)            # dual_path.py:97
+        n_skip = hp.skip_n_block
+        if n_skip > 0:
+            ws.R.copy_(ws.X)                                                               # residual = x, dual_path.py:100
         for i, blk in enumerate(self.blocks):
             last = i == len(self.blocks) - 1
+            # `x = 0.5 * x + 0.5 * residual` in front of block i + 1 (dual_path.py:114-116) is applied by the norm that ends
+            # block i
+            blend = ws.R if (n_skip > 0 and not last and (i + 1) % n_skip == 0) else None
             blk["intra"].run(ws.intra, ws.O)                                               # rows (b, s, k)
             op("gn_stats", ops.gn_stats, ws.O, B, S * K, D, ws.partials)
             op("gn_apply", ops.gn_apply, ws.O, ws.partials, blk["intra_w"], blk["intra_b"], B, S, K, D,
@@ -143,7 +150,7 @@ class DPSeparatorEngine:
             blk["inter"].run(ws.inter, ws.O)                                               # rows (b, k, s)
             op("gn_stats", ops.gn_stats, ws.O, B, S * K, D, ws.partials)
             op("gn_apply", ops.gn_apply, ws.O, ws.partials, blk["inter_w"], blk["inter_b"], B, S, K, D, skip=ws.I,
-               out_a=ws.X, out_a2=None if last else ws.intra.h, x_transposed=True)
+               out_a=ws.X, out_a2=None if last else ws.intra.h, x_transposed=True, blend=blend)
         op("dp_overadd_prelu", ops.dp_overadd_prelu, ws.X, self.prelu_w, ws.Yp, B, L, D, K, S)   # dual_path.py:126,140
         op("gemm_conv2d", ops.gemm, ws.Yp, self.w_conv2d, M, spk * D, D, out=ws.c2)         # dual_path.py:131
         op("bias_planes", ops.bias_planes, ws.c2, self.b_conv2d, 2.0, ws.c2p, M, spk * D)

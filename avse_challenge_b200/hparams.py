@@ -140,6 +140,7 @@ class DPHParams:
     d_conv: int = 4
     n_spk: int = 2
     sample_rate: int = 8000
+    skip_n_block: int = 0        # Dual_Path_Model_Skip (modules/dual_path.py:114-116); 0 in every shipped recipe
 
     @property
     def stride(self) -> int:

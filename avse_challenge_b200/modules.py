@@ -465,14 +465,17 @@ class Dual_Path_Model(_EngineOwner):
 
 
 class Dual_Path_Model_Skip(Dual_Path_Model):
-    """``modules/dual_path.py:17-150`` (vendored subclass).  ``skip_n_block = 0`` -- what every shipped recipe sets
-    (``dpmamba_L.yaml:116``) -- makes it identical to ``Dual_Path_Model``; other values are not built."""
+    """``modules/dual_path.py:17-150`` (vendored subclass): every ``skip_n_block`` dual blocks the running tensor is
+    averaged with the segmented input (``:114-116``).  ``skip_n_block = 0`` -- what every shipped recipe sets
+    (``dpmamba_L.yaml:116``) -- makes it identical to ``Dual_Path_Model``."""
 
     def __init__(self, *args, skip_n_block=0, **kw):
-        if skip_n_block != 0:
-            _unsupported("skip_n_block != 0")
+        if skip_n_block < 0:
+            raise ValueError("skip_n_block must be >= 0")
         super().__init__(*args, **kw)
         self.skip_n_block = skip_n_block
+        from dataclasses import replace
+        self.hp = replace(self.hp, skip_n_block=skip_n_block)
 
 
 class DPMambaSeparator(_EngineOwner):

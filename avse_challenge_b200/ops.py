@@ -215,12 +215,12 @@ def gn_stats(x, batch, rows, C, partials=None):
 
 
 def gn_apply(x, partials, w, bias, batch, S, K, C, *, eps=1e-8, skip=None, out_a=None, out_a2=None, out_t=None, planes=None,
-             x_transposed=False):
-    _req_cuda(x, partials, w, bias, skip, out_a, out_a2, out_t, planes)
+             x_transposed=False, blend=None):
+    _req_cuda(x, partials, w, bias, skip, out_a, out_a2, out_t, planes, blend)
     args = GnApplyArgs(x=ptr(x), partials=ptr(partials), w=ptr(w), bias=ptr(bias), skip=ptr(skip), out_a=ptr(out_a),
                        out_a2=ptr(out_a2), out_t=ptr(out_t), planes=ptr(planes), batch=batch, S=S, K=K, C=C,
                        x_transposed=int(x_transposed), n_planes=(planes.shape[0] if planes is not None else 0),
-                       plane_rows=(planes.shape[1] if planes is not None else 0), eps=eps)
+                       plane_rows=(planes.shape[1] if planes is not None else 0), eps=eps, blend=ptr(blend))
     check(_lib.load().mtn_gn_apply_fwd(args, _stream()), "mtn_gn_apply_fwd")
 
 

@@ -229,6 +229,9 @@ typedef struct {
     int x_transposed;
     int n_planes, plane_rows;
     float eps;
+    const float* blend;    /* nullable fp32 [batch][S][K][C]: result = 0.5 * result + 0.5 * blend afterwards -- the periodic
+                              skip to the segmented input of Dual_Path_Model_Skip (modules/dual_path.py:114-116), folded
+                              into the norm that ends the preceding block */
 } mtn_gn_apply_args;
 /* Pass 2: y = (x - mean) * rstd * w + bias (+ skip), written to every non-NULL output. */
 int mtn_gn_apply_fwd(const mtn_gn_apply_args* args, mtn_stream_t stream);

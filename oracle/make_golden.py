@@ -118,11 +118,11 @@ def golden_stream(mask, tag):
     print(f"stream_{tag}.npz", "max |streamed - one-shot|", float((streamed - full).abs().max()))
 
 
-def golden_dp(tag, T, batch, seed, skip_around_intra):
+def golden_dp(tag, T, batch, seed, skip_around_intra, skip_n_block=0, n_dp=2):
     """DPMamba: the reference's ``Dual_Path_Model_Skip`` (vendored forward, ``modules/dual_path.py``) over the published
     speechbrain ``Dual_Path_Model`` members, with the real ``MambaBlocksSequential`` as intra / inter model."""
     from dataclasses import replace
-    hp = replace(DP_CONFIGS["tiny"], skip_around_intra=skip_around_intra)
+    hp = replace(DP_CONFIGS["tiny"], skip_around_intra=skip_around_intra, skip_n_block=skip_n_block, n_dp=n_dp)
     ref = ref_shims.load_reference()
     enc, mask, dec = ref_shims.build_reference_dp_model(hp.as_dict(), seed=seed)
     sds = init_dp_state_dicts(hp, seed)
@@ -137,7 +137,7 @@ def golden_dp(tag, T, batch, seed, skip_around_intra):
     arrs = {"mix": mix.numpy(), "src": src.numpy(), "est": est.numpy(), "mix_w": mix_w.numpy(),
             "est_mask": est_mask.numpy(), "T": np.int64(T), "batch": np.int64(batch),
             "skip_around_intra": np.int64(skip_around_intra), "chunk_size": np.int64(hp.chunk_size),
-            "n_dp": np.int64(hp.n_dp)}
+            "n_dp": np.int64(hp.n_dp), "skip_n_block": np.int64(hp.skip_n_block)}
     arrs.update(_np(enc.state_dict(), "encoder"))
     arrs.update(_np(mask.state_dict(), "masknet"))
     arrs.update(_np(dec.state_dict(), "decoder"))
@@ -178,6 +178,7 @@ def main():
     golden_stream(mask, "tiny_causal")
     golden_dp("dp_tiny_skip", T=1203, batch=2, seed=91, skip_around_intra=True)
     golden_dp("dp_tiny_noskip", T=811, batch=1, seed=92, skip_around_intra=False)
+    golden_dp("dp_tiny_blockskip", T=643, batch=1, seed=93, skip_around_intra=True, skip_n_block=1, n_dp=3)
 
 
 if __name__ == "__main__":

@@ -352,7 +352,7 @@ def build_reference_dp_model(hp, seed=1234):
     with contextlib.redirect_stdout(io.StringIO()):       # the vendored ctor prints skip_n_block
         mask = ref.Dual_Path_Model_Skip(in_channels=hp["enc_dim"], out_channels=hp["d_model"], intra_model=mk(),
                                         inter_model=mk(), num_layers=hp["n_dp"], norm="ln", K=hp["chunk_size"], num_spks=2,
-                                        skip_around_intra=hp["skip_around_intra"], skip_n_block=0,
+                                        skip_around_intra=hp["skip_around_intra"], skip_n_block=hp.get("skip_n_block", 0),
                                         linear_layer_after_inter_intra=False)
     dec = ref.Decoder(in_channels=hp["enc_dim"], out_channels=1, kernel_size=hp["kernel_size"],
                       stride=hp["kernel_size"] // 2, bias=False)

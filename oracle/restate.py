@@ -335,7 +335,7 @@ def dp_over_add(x, gap):
     return out[:, :-gap] if gap > 0 else out
 
 
-def dp_masknet_fwd(mix_w, sd, n_dp, K, skip_around_intra, n_mamba_stack=1, n_spk=2, scan_impl="auto"):
+def dp_masknet_fwd(mix_w, sd, n_dp, K, skip_around_intra, n_mamba_stack=1, n_spk=2, scan_impl="auto", skip_n_block=0):
     """``Dual_Path_Model.forward`` (dp.py:56-150 with ``skip_n_block = 0``) + ``Dual_Computation_Block.forward`` on
     channel-last ``mix_w [B, L, N]``; returns the mask ``[n_spk, B, L, N]``."""
     B, L, N = mix_w.shape
@@ -343,7 +343,10 @@ def dp_masknet_fwd(mix_w, sd, n_dp, K, skip_around_intra, n_mamba_stack=1, n_spk
     x = _mm(x, sd["conv1d.weight"][:, :, 0])                               # dp.py:88
     x, gap = dp_segment(x, K)                                              # dp.py:97  [B, S, K, D]
     S, D = x.shape[1], x.shape[3]
+    residual = x                                                           # dp.py:100
     for i in range(n_dp):                                                  # dp.py:113-119
+        if skip_n_block > 0 and i % skip_n_block == 0 and i != 0:          # dp.py:114-116
+            x = 0.5 * x + 0.5 * residual
         p = f"dual_mdl.{i}."
         intra = mamba_stack_fwd(x.reshape(B * S, K, D), sd, n_mamba_stack, prefix=p + "intra_mdl.",
                                 scan_impl=scan_impl).reshape(B, S, K, D)
@@ -370,7 +373,7 @@ def separate_dp(mix, sds, hp, scan_impl="auto"):
     """``Separation.compute_forward`` (``train_wsj0mix.py:86-111``) with the DPMamba mask network; ``hp``: DPHParams."""
     mix_w = encoder_fwd(mix, sds["encoder"]["conv1d.weight"])
     mask = dp_masknet_fwd(mix_w, sds["masknet"], hp.n_dp, hp.chunk_size, hp.skip_around_intra, hp.n_mamba_dp // 2,
-                          hp.n_spk, scan_impl)
+                          hp.n_spk, scan_impl, skip_n_block=getattr(hp, "skip_n_block", 0))
     est = torch.stack([decoder_fwd(mix_w * mask[s], sds["decoder"]["weight"]) for s in range(hp.n_spk)], dim=-1)
     T, T_est = mix.shape[1], est.shape[1]
     return F.pad(est, (0, 0, 0, T - T_est)) if T > T_est else est[:, :T, :]

@@ -97,7 +97,8 @@ def test_library_exports_every_declared_symbol(built_lib):
 def test_struct_layouts_match_header(built_lib):
     """ctypes Structures must mirror the C structs field for field."""
     header = open(os.path.join(ROOT, "include", "mtn_b200.h")).read()
-    for cname, cls in (("mtn_gemm_args", _lib.GemmArgs), ("mtn_scan_args", _lib.ScanArgs)):
+    for cname, cls in (("mtn_gemm_args", _lib.GemmArgs), ("mtn_scan_args", _lib.ScanArgs),
+                       ("mtn_gn_apply_args", _lib.GnApplyArgs)):
         body = re.search(r"typedef struct \{([^}]*)\} " + cname + ";", header).group(1)
         body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
         names = []

@@ -139,7 +139,7 @@ def test_streaming_restatement_matches_reference_inference_cache(golden_dir):
 
 
 # ------------------------------------------------------------------------------------------------ DPMamba
-@pytest.mark.parametrize("tag", ["dp_tiny_skip", "dp_tiny_noskip"])
+@pytest.mark.parametrize("tag", ["dp_tiny_skip", "dp_tiny_noskip", "dp_tiny_blockskip"])
 def test_dpmamba_restatement_matches_reference_golden(golden_dir, tag):
     """Golden = the reference's vendored Dual_Path_Model_Skip.forward over the real MambaBlocksSequential stacks."""
     from dataclasses import replace
@@ -148,10 +148,11 @@ def test_dpmamba_restatement_matches_reference_golden(golden_dir, tag):
     sds, out, _ = load_golden_forward(path)
     z = np.load(path)
     hp = replace(DP_CONFIGS["tiny"], skip_around_intra=bool(z["skip_around_intra"]), chunk_size=int(z["chunk_size"]),
-                 n_dp=int(z["n_dp"]))
+                 n_dp=int(z["n_dp"]), skip_n_block=int(z["skip_n_block"]) if "skip_n_block" in z.files else 0)
     with torch.no_grad():
         mix_w = restate.encoder_fwd(out["mix"], sds["encoder"]["conv1d.weight"])
-        mask = restate.dp_masknet_fwd(mix_w, sds["masknet"], hp.n_dp, hp.chunk_size, hp.skip_around_intra, scan_impl="c")
+        mask = restate.dp_masknet_fwd(mix_w, sds["masknet"], hp.n_dp, hp.chunk_size, hp.skip_around_intra, scan_impl="c",
+                                      skip_n_block=hp.skip_n_block)
         est = restate.separate_dp(out["mix"], sds, hp, scan_impl="c")
     assert (mask.permute(0, 1, 3, 2) - out["est_mask"]).abs().max().item() <= 2e-6
     assert (est - out["est"]).abs().max().item() <= 2e-6
