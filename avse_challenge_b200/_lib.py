@@ -16,7 +16,7 @@ EPI_STORE, EPI_INPROJ, EPI_MASK, EPI_RELU, EPI_XPROJ, EPI_RESADD = 0, 1, 2, 3, 4
 EXPORTS = [
     "mtn_encoder_cln_fwd", "mtn_gemm_fwd", "mtn_gemm_rowsum_parts", "mtn_add_rmsnorm_fwd", "mtn_add_rmsnorm_out_fwd", "mtn_conv_silu_fwd", "mtn_conv_silu_halo_fwd", "mtn_conv_silu_dir_fwd", "mtn_decoder_stream_fwd",
     "mtn_scan_fwd", "mtn_fold_states_fwd",
-    "mtn_gn_partials_bytes", "mtn_gn_stats_fwd", "mtn_gn_apply_fwd", "mtn_dp_num_chunks", "mtn_dp_segment_fwd",
+    "mtn_gn_partials_bytes", "mtn_gn_stats_fwd", "mtn_gn_apply_fwd", "mtn_gn_apply_norm_fwd", "mtn_dp_num_chunks", "mtn_dp_segment_fwd",
     "mtn_dp_overadd_prelu_fwd", "mtn_bias_planes_fwd", "mtn_gate_planes_fwd",
     "mtn_decoder_fwd", "mtn_cln_fwd", "mtn_split_planes", "mtn_si_snr_pit_fwd", "mtn_si_snr_workspace_bytes", "mtn_last_error_string", "mtn_abi_version",
 ]
@@ -97,6 +97,7 @@ def load():
     lib.mtn_gn_partials_bytes.argtypes = [c_int, c_int, c_int]
     lib.mtn_gn_stats_fwd.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]
     lib.mtn_gn_apply_fwd.argtypes = [POINTER(GnApplyArgs), c_void_p]
+    lib.mtn_gn_apply_norm_fwd.argtypes = [POINTER(GnApplyArgs), c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p]
     lib.mtn_dp_num_chunks.argtypes = [c_int, c_int]
     lib.mtn_dp_segment_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]
     lib.mtn_dp_overadd_prelu_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,

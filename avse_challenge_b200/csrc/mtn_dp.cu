@@ -138,6 +138,93 @@ gn_apply_kernel(GnApplyParams p) {
     }
 }
 
+// Same values as gn_apply_kernel, one warp per row, fused with the Add -> RMSNorm that opens the next stack
+// (Block.forward with residual None, bimamba.py:446-447): the row is written to out_a (the block's residual copy), to the
+// next stack's residual stream `res_next` and, RMS-normalised with that stack's first norm weight, to its operand planes --
+// both at the row position the next stack uses (transposed for the inter model).  Replaces gn_apply's second output and the
+// next stack's first add_rmsnorm launch (5 row transfers -> 3).
+template <int P, int NV>   // C = 128 * NV
+__global__ void __launch_bounds__(256)
+gn_apply_norm_kernel(GnApplyParams p, float* __restrict__ res_next, __nv_bfloat16* __restrict__ xn_next,
+                     const float* __restrict__ g_next, int next_transposed, float rms_eps) {
+    constexpr int C = 128 * NV;
+    const int b = blockIdx.y;
+    __shared__ float s_mean, s_rstd;
+    if (threadIdx.x < 32) {
+        double s = 0.0, q = 0.0;
+        for (int i = threadIdx.x; i < p.nblk; i += 32) {
+            const double2 v = p.partials[size_t(b) * p.nblk + i];
+            s += v.x;
+            q += v.y;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, o);
+            q += __shfl_xor_sync(0xffffffffu, q, o);
+        }
+        if (threadIdx.x == 0) {
+            const double n = double(p.S) * p.K * C;
+            const double mean = s / n;
+            double var = q / n - mean * mean;
+            if (var < 0.0) var = 0.0;
+            s_mean = float(mean);
+            s_rstd = float(1.0 / sqrt(var + double(p.eps)));
+        }
+    }
+    __syncthreads();
+    const float mean = s_mean, rstd = s_rstd;
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    const size_t rows = size_t(p.S) * p.K;
+    const size_t base_b = size_t(b) * rows;
+    for (size_t r = size_t(blockIdx.x) * wpb + (threadIdx.x >> 5); r < rows; r += size_t(gridDim.x) * wpb) {
+        const int s = int(r / p.K), k = int(r - size_t(s) * p.K);
+        const size_t row_a = base_b + r;
+        const size_t row_t = base_b + size_t(k) * p.S + s;
+        const size_t row_x = p.x_transposed ? row_t : row_a;
+        const size_t row_n = next_transposed ? row_t : row_a;
+        float4 o[NV];
+        float sq = 0.f;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const int c = 128 * j + 4 * lane;
+            const float4 v = *reinterpret_cast<const float4*>(p.x + row_x * C + c);
+            const float4 g = *reinterpret_cast<const float4*>(p.w + c);
+            const float4 bb = *reinterpret_cast<const float4*>(p.bias + c);
+            float4 t;
+            t.x = fmaf((v.x - mean) * rstd, g.x, bb.x);
+            t.y = fmaf((v.y - mean) * rstd, g.y, bb.y);
+            t.z = fmaf((v.z - mean) * rstd, g.z, bb.z);
+            t.w = fmaf((v.w - mean) * rstd, g.w, bb.w);
+            if (p.skip) {
+                const float4 k4 = *reinterpret_cast<const float4*>(p.skip + row_a * C + c);
+                t.x += k4.x; t.y += k4.y; t.z += k4.z; t.w += k4.w;
+            }
+            if (p.blend) {
+                const float4 r4 = *reinterpret_cast<const float4*>(p.blend + row_a * C + c);
+                t.x = 0.5f * t.x + 0.5f * r4.x; t.y = 0.5f * t.y + 0.5f * r4.y;
+                t.z = 0.5f * t.z + 0.5f * r4.z; t.w = 0.5f * t.w + 0.5f * r4.w;
+            }
+            o[j] = t;
+            sq += t.x * t.x + t.y * t.y + t.z * t.z + t.w * t.w;     // same order as add_rmsnorm_kernel
+        }
+        const float rr = rsqrtf(warp_sum(sq) * (1.0f / C) + rms_eps);
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const int c = 128 * j + 4 * lane;
+            if (p.out_a) *reinterpret_cast<float4*>(p.out_a + row_a * C + c) = o[j];
+            *reinterpret_cast<float4*>(res_next + row_n * C + c) = o[j];
+            const float4 gg = *reinterpret_cast<const float4*>(g_next + c);
+            float4 n4;
+            n4.x = o[j].x * rr * gg.x;
+            n4.y = o[j].y * rr * gg.y;
+            n4.z = o[j].z * rr * gg.z;
+            n4.w = o[j].w * rr * gg.w;
+            store_planes4<P>(xn_next, p.plane_stride, row_n * C + c, n4);
+        }
+    }
+}
+
 // speechbrain Dual_Path_Model._padding + _Segmentation: chunk s, offset k <- frame l = s*(K/2) + k - K/2 (zero outside [0, L))
 __global__ void __launch_bounds__(256)
 dp_segment_kernel(const float* __restrict__ x, float* __restrict__ out_a, float* __restrict__ out_a2, int L, int C, int K,
@@ -293,6 +380,38 @@ extern "C" int mtn_gn_apply_fwd(const mtn_gn_apply_args* a, mtn_stream_t stream)
     if (a->planes && a->n_planes == 2) gn_apply_kernel<2><<<grid, 256, 0, s>>>(p);
     else gn_apply_kernel<1><<<grid, 256, 0, s>>>(p);
     MTN_CUDA_LAUNCH_CHECK("gn_apply");
+    return MTN_OK;
+}
+
+extern "C" int mtn_gn_apply_norm_fwd(const mtn_gn_apply_args* a, float* res_next, void* xn_next_planes, const float* g_next,
+                                     int next_transposed, float rms_eps, mtn_stream_t stream) {
+    MTN_REQUIRE(a && a->x && a->partials && a->w && a->bias && res_next && xn_next_planes && g_next,
+                "gn_apply_norm: null pointer");
+    MTN_REQUIRE(a->batch > 0 && a->batch <= 65535 && a->S > 0 && a->K > 0, "gn_apply_norm: bad shape");
+    MTN_REQUIRE(a->C == 128 || a->C == 256 || a->C == 512, "gn_apply_norm: C=%d (supported: 128, 256, 512)", a->C);
+    MTN_REQUIRE(a->n_planes == 1 || a->n_planes == 2, "gn_apply_norm: n_planes=%d", a->n_planes);
+    MTN_REQUIRE(!a->out_a2 && !a->out_t && !a->planes, "gn_apply_norm: only out_a is supported beside the fused outputs");
+    GnApplyParams p;
+    p.x = a->x; p.partials = reinterpret_cast<const double2*>(a->partials); p.w = a->w; p.bias = a->bias; p.skip = a->skip;
+    p.blend = a->blend;
+    p.out_a = a->out_a; p.out_a2 = nullptr; p.out_t = nullptr; p.planes = nullptr;
+    const size_t rows = size_t(a->S) * a->K;
+    p.plane_stride = (a->plane_rows > 0 ? size_t(a->plane_rows) : size_t(a->batch) * rows) * a->C;
+    p.S = a->S; p.K = a->K; p.C = a->C; p.nblk = gn_nblk(rows * a->C); p.x_transposed = a->x_transposed; p.eps = a->eps;
+    size_t gx = (rows + 7) / 8;
+    const size_t cap = size_t(num_sms()) * 8 / a->batch + 1;
+    if (gx > cap) gx = cap;
+    dim3 grid((unsigned)gx, a->batch);
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    __nv_bfloat16* xn = reinterpret_cast<__nv_bfloat16*>(xn_next_planes);
+#define MTN_GNN(PP, NV) gn_apply_norm_kernel<PP, NV><<<grid, 256, 0, s>>>(p, res_next, xn, g_next, next_transposed, rms_eps)
+    if (a->n_planes == 2) {
+        if (a->C == 128) MTN_GNN(2, 1); else if (a->C == 256) MTN_GNN(2, 2); else MTN_GNN(2, 4);
+    } else {
+        if (a->C == 128) MTN_GNN(1, 1); else if (a->C == 256) MTN_GNN(1, 2); else MTN_GNN(1, 4);
+    }
+#undef MTN_GNN
+    MTN_CUDA_LAUNCH_CHECK("gn_apply_norm");
     return MTN_OK;
 }
 

@@ -138,19 +138,31 @@ class DPSeparatorEngine:
         n_skip = hp.skip_n_block
         if n_skip > 0:
             ws.R.copy_(ws.X)                                                               # residual = x, dual_path.py:100
+        fused = D in (128, 256, 512)   # GroupNorm apply + the next stack's opening RMSNorm in one kernel (gn_apply_norm)
         for i, blk in enumerate(self.blocks):
             last = i == len(self.blocks) - 1
             # `x = 0.5 * x + 0.5 * residual` in front of block i + 1 (dual_path.py:114-116) is applied by the norm that ends
             # block i
             blend = ws.R if (n_skip > 0 and not last and (i + 1) % n_skip == 0) else None
-            blk["intra"].run(ws.intra, ws.O)                                               # rows (b, s, k)
+            blk["intra"].run(ws.intra, ws.O, prenormed=fused and i > 0)                     # rows (b, s, k)
             op("gn_stats", ops.gn_stats, ws.O, B, S * K, D, ws.partials)
-            op("gn_apply", ops.gn_apply, ws.O, ws.partials, blk["intra_w"], blk["intra_b"], B, S, K, D,
-               skip=ws.X if hp.skip_around_intra else None, out_a=ws.I, out_t=ws.inter.h)
-            blk["inter"].run(ws.inter, ws.O)                                               # rows (b, k, s)
+            skip = ws.X if hp.skip_around_intra else None
+            if fused:
+                op("gn_apply_norm", ops.gn_apply_norm, ws.O, ws.partials, blk["intra_w"], blk["intra_b"], B, S, K, D,
+                   skip=skip, out_a=ws.I, res_next=ws.inter.res, xn_next=ws.inter.xn,
+                   g_next=blk["inter"].layers[0]["norm"], next_transposed=True)
+            else:
+                op("gn_apply", ops.gn_apply, ws.O, ws.partials, blk["intra_w"], blk["intra_b"], B, S, K, D, skip=skip,
+                   out_a=ws.I, out_t=ws.inter.h)
+            blk["inter"].run(ws.inter, ws.O, prenormed=fused)                               # rows (b, k, s)
             op("gn_stats", ops.gn_stats, ws.O, B, S * K, D, ws.partials)
-            op("gn_apply", ops.gn_apply, ws.O, ws.partials, blk["inter_w"], blk["inter_b"], B, S, K, D, skip=ws.I,
-               out_a=ws.X, out_a2=None if last else ws.intra.h, x_transposed=True, blend=blend)
+            if fused and not last:
+                op("gn_apply_norm", ops.gn_apply_norm, ws.O, ws.partials, blk["inter_w"], blk["inter_b"], B, S, K, D,
+                   skip=ws.I, out_a=ws.X, x_transposed=True, blend=blend, res_next=ws.intra.res, xn_next=ws.intra.xn,
+                   g_next=self.blocks[i + 1]["intra"].layers[0]["norm"], next_transposed=False)
+            else:
+                op("gn_apply", ops.gn_apply, ws.O, ws.partials, blk["inter_w"], blk["inter_b"], B, S, K, D, skip=ws.I,
+                   out_a=ws.X, out_a2=None if last else ws.intra.h, x_transposed=True, blend=blend)
         op("dp_overadd_prelu", ops.dp_overadd_prelu, ws.X, self.prelu_w, ws.Yp, B, L, D, K, S)   # dual_path.py:126,140
         op("gemm_conv2d", ops.gemm, ws.Yp, self.w_conv2d, M, spk * D, D, out=ws.c2)         # dual_path.py:131
         op("bias_planes", ops.bias_planes, ws.c2, self.b_conv2d, 2.0, ws.c2p, M, spk * D)

@@ -185,11 +185,12 @@ class LayerPlan:
         op("scan", ops.scan, ws.u, ws.dbl, ws.xz, di, lw["w_dt"], lw["dt_bias"], lw["A2"], lw["D"], ws.batch, ws.L, di, R,
            y=ws.y, dtp=ws.dtp if self.tc_dt else None, dir_mask=self.dir_mask, h_in=h, h_out=h)
 
-    def _layer(self, ws: Workspace, lw: dict, first: bool, taps=None, st=None):
+    def _layer(self, ws: Workspace, lw: dict, first: bool, taps=None, st=None, prenormed: bool = False):
         hp, P = self.hp, self.P
         D, di, M = hp.d_model, hp.d_inner, ws.M
         op = self._op
-        op("add_rmsnorm", ops.add_rmsnorm, ws.h, ws.res, not first, lw["norm"], P, xn=ws.xn)
+        if not prenormed:   # prenormed: the producer already wrote ws.res and ws.xn = RMSNorm(res) * lw["norm"]
+            op("add_rmsnorm", ops.add_rmsnorm, ws.h, ws.res, not first, lw["norm"], P, xn=ws.xn)
         op("gemm_in_proj", ops.gemm, ws.xn, lw["w_in"], M, 2 * di, D, out=ws.xz, epilogue=_lib.EPI_INPROJ, epi_param=di,
            out_bf16=ws.xz.dtype == torch.bfloat16)
         self._mixer_core(ws, lw, st)
@@ -218,11 +219,12 @@ class MambaStack(LayerPlan):
             self._ws[key] = LayerWorkspace(self.hp, batch, L, self.device, self.mode)
         return self._ws[key]
 
-    def run(self, ws: LayerWorkspace, out: torch.Tensor, states=None):
+    def run(self, ws: LayerWorkspace, out: torch.Tensor, states=None, prenormed: bool = False):
         """The stack on ``ws.h`` (fp32 [M, D], consumed) -> ``out`` (fp32 [M, D]).  ``states``: per-layer streaming caches
-        (``{"halo", "h"}``, unidirectional only)."""
+        (``{"halo", "h"}``, unidirectional only).  ``prenormed``: the caller has already filled ``ws.res`` with the input
+        and ``ws.xn`` with its RMSNorm under ``self.layers[0]["norm"]`` (fused producer), so the first launch is skipped."""
         for i, lw in enumerate(self.layers):
-            self._layer(ws, lw, first=(i == 0), st=None if states is None else states[i])
+            self._layer(ws, lw, first=(i == 0), st=None if states is None else states[i], prenormed=(prenormed and i == 0))
         self._op("add_rmsnorm", ops.add_rmsnorm, ws.h, ws.res, True, self.norm_f, self.P, xn=False, out_f32=out)
         return out
 

@@ -224,6 +224,17 @@ def gn_apply(x, partials, w, bias, batch, S, K, C, *, eps=1e-8, skip=None, out_a
     check(_lib.load().mtn_gn_apply_fwd(args, _stream()), "mtn_gn_apply_fwd")
 
 
+def gn_apply_norm(x, partials, w, bias, batch, S, K, C, *, res_next, xn_next, g_next, next_transposed, eps=1e-8, rms_eps=1e-5,
+                  skip=None, out_a=None, x_transposed=False, blend=None):
+    """``gn_apply`` fused with the next stack's opening Add -> RMSNorm (see ``mtn_gn_apply_norm_fwd``)."""
+    _req_cuda(x, partials, w, bias, skip, out_a, blend, res_next, xn_next, g_next)
+    args = GnApplyArgs(x=ptr(x), partials=ptr(partials), w=ptr(w), bias=ptr(bias), skip=ptr(skip), out_a=ptr(out_a),
+                       out_a2=None, out_t=None, planes=None, batch=batch, S=S, K=K, C=C, x_transposed=int(x_transposed),
+                       n_planes=xn_next.shape[0], plane_rows=xn_next.shape[1], eps=eps, blend=ptr(blend))
+    check(_lib.load().mtn_gn_apply_norm_fwd(args, ptr(res_next), ptr(xn_next), ptr(g_next), int(next_transposed), rms_eps,
+                                            _stream()), "mtn_gn_apply_norm_fwd")
+
+
 def dp_segment(x, batch, L, C, K, S, out_a, out_a2=None):
     _req_cuda(x, out_a, out_a2)
     check(_lib.load().mtn_dp_segment_fwd(ptr(x), ptr(out_a), ptr(out_a2), batch, L, C, K, S, _stream()), "mtn_dp_segment_fwd")

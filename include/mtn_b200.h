@@ -236,6 +236,14 @@ typedef struct {
 /* Pass 2: y = (x - mean) * rstd * w + bias (+ skip), written to every non-NULL output. */
 int mtn_gn_apply_fwd(const mtn_gn_apply_args* args, mtn_stream_t stream);
 
+/* Pass 2 fused with the Add -> RMSNorm that opens the NEXT Mamba stack (Block.forward with residual None,
+ * modules/mamba/bimamba.py:446-447): besides args->out_a (optional) the row goes to that stack's residual stream res_next
+ * (fp32 [batch][S*K][C]) and, times rsqrt(mean_C(row^2) + rms_eps) * g_next, to its operand planes xn_next
+ * ([n_planes][plane_rows][C]); both at row (b,k,s) when next_transposed (inter model), else (b,s,k).  C in {128, 256, 512};
+ * args->out_a2 / out_t / planes must be NULL. */
+int mtn_gn_apply_norm_fwd(const mtn_gn_apply_args* args, float* res_next, void* xn_next_planes, const float* g_next,
+                          int next_transposed, float rms_eps, mtn_stream_t stream);
+
 /* Number of chunks S that Dual_Path_Model._Segmentation makes of L frames with chunk size K (50 % overlap, zero padded). */
 int mtn_dp_num_chunks(int L, int K);
 /* _padding + _Segmentation: x fp32 [batch][L][C] -> out_a (and out_a2, nullable) fp32 [batch][S][K][C]. */

@@ -142,7 +142,7 @@ def test_dual_path_model_standalone_forward(golden_dir):
     assert rel_max(mask.cpu(), g["est_mask"]) <= 1e-3
 
 
-@pytest.mark.parametrize("name,B,T", [("S", 1, 8000), ("L", 1, 4000)])
+@pytest.mark.parametrize("name,B,T", [("XS", 2, 6000), ("S", 1, 8000), ("L", 1, 4000)])
 def test_dpmamba_shipped_sizes_vs_oracle(name, B, T):
     """Shipped DPMamba hparams with K = 250 (intra sequences of 250 frames, inter sequences of S chunks) vs the oracle."""
     hp = replace(DP_CONFIGS[name], n_dp=2)          # 2 of the 8 / 16 identical-shape blocks keep the CPU oracle in seconds
