@@ -281,7 +281,7 @@ scan_kernel_trio(const __grid_constant__ CUtensorMap mapU, const __grid_constant
     if (warp < 4) {
         reg_inc<128>();
         scan_pair_recur<SM::STAGES, SM::NB, R, true, ABL>(ring, slots, SM::STAGE_BYTES, SM::U_BYTES, full_bar, empty_bar,
-                                                         prepped, ydone, p, w, lane, d, b, dir, ntiles);
+                                                         prepped, ydone, p, w, lane, d, b, dir, ntiles, Lb);
     } else if (warp < 8) {
         reg_dec<64>();
         scan_trio_prep<P, R, NDBL, ABL>(ring, slots, full_bar, empty_bar, prepped, slotfree, p, w, lane, ch0, d, b, dir,
