@@ -18,7 +18,7 @@ EXPORTS = [
     "mtn_scan_fwd", "mtn_fold_states_fwd",
     "mtn_gn_partials_bytes", "mtn_gn_stats_fwd", "mtn_gn_apply_fwd", "mtn_gn_apply_norm_fwd", "mtn_dp_num_chunks", "mtn_dp_segment_fwd",
     "mtn_dp_overadd_prelu_fwd", "mtn_bias_planes_fwd", "mtn_gate_planes_fwd",
-    "mtn_decoder_fwd", "mtn_cln_fwd", "mtn_split_planes", "mtn_si_snr_pit_fwd", "mtn_si_snr_workspace_bytes", "mtn_last_error_string", "mtn_abi_version",
+    "mtn_decoder_fwd", "mtn_cln_fwd", "mtn_softmax_mask_fwd", "mtn_split_planes", "mtn_si_snr_pit_fwd", "mtn_si_snr_workspace_bytes", "mtn_last_error_string", "mtn_abi_version",
 ]
 
 
@@ -91,6 +91,7 @@ def load():
     lib.mtn_fold_states_fwd.argtypes = [c_void_p] * 6 + [c_int] * 5 + [c_void_p]
     lib.mtn_decoder_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]
     lib.mtn_cln_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p]
+    lib.mtn_softmax_mask_fwd.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]
     lib.mtn_split_planes.argtypes = [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p]
     lib.mtn_si_snr_workspace_bytes.argtypes = [c_int, c_int]
     lib.mtn_si_snr_pit_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p, c_void_p]

@@ -480,6 +480,39 @@ decoder_ola_stream_kernel(const float* __restrict__ frames, float* __restrict__ 
     }
 }
 
+// mask_nonlinear = "softmax" (modules/mamba_masknet.py:133-134): `F.softmax(score, dim=2)` on score [n_spk, B, N, L], i.e.
+// over the N encoder channels of one (speaker, utterance, frame).  One warp per (frame, speaker); in place; optionally
+// times mix_w (the mask application of train_wsj0mix.py:91-92).
+template <int NJ>
+__global__ void __launch_bounds__(256)
+softmax_mask_kernel(float* __restrict__ score, const float* __restrict__ mix_w, size_t items, int S) {
+    constexpr int N = 32 * NJ;
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    for (size_t item = size_t(blockIdx.x) * wpb + (threadIdx.x >> 5); item < items; item += size_t(gridDim.x) * wpb) {
+        float* row = score + item * N;
+        float v[NJ];
+        float m = -3.0e38f;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            v[j] = row[lane + 32 * j];
+            m = fmaxf(m, v[j]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            v[j] = ex2_approx(1.4426950408889634f * (v[j] - m));
+            sum += v[j];
+        }
+        const float inv = 1.0f / warp_sum(sum);
+        const float* mw = mix_w ? mix_w + (item / S) * N : nullptr;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) row[lane + 32 * j] = v[j] * inv * (mw ? mw[lane + 32 * j] : 1.0f);
+    }
+}
+
 template <int P>
 __global__ void __launch_bounds__(256)
 split_planes_kernel(const float* __restrict__ src, int ld, __nv_bfloat16* __restrict__ dst, int rows, int cols) {
@@ -674,6 +707,22 @@ extern "C" int mtn_decoder_stream_fwd(const float* sep, const float* w_dec, floa
     if (tail) decoder_ola_stream_kernel<<<grid_for(size_t(batch) * T * n_spk, 256, 8), 256, 0, s>>>(frames, est, tail, batch, L, n_spk);
     else decoder_ola_kernel<<<grid_for(size_t(batch) * T * n_spk, 256, 8), 256, 0, s>>>(frames, est, batch, T, L, n_spk);
     MTN_CUDA_LAUNCH_CHECK("decoder_ola");
+    return MTN_OK;
+}
+
+extern "C" int mtn_softmax_mask_fwd(float* score, const float* mix_w, int rows, int N, int n_spk, mtn_stream_t stream) {
+    MTN_REQUIRE(score && rows > 0 && n_spk >= 1, "softmax_mask: bad arguments");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const size_t items = size_t(rows) * n_spk;
+    const int grid = grid_for(items, 8, 8);
+    switch (N) {
+        case 64: softmax_mask_kernel<2><<<grid, 256, 0, s>>>(score, mix_w, items, n_spk); break;
+        case 128: softmax_mask_kernel<4><<<grid, 256, 0, s>>>(score, mix_w, items, n_spk); break;
+        case 256: softmax_mask_kernel<8><<<grid, 256, 0, s>>>(score, mix_w, items, n_spk); break;
+        case 512: softmax_mask_kernel<16><<<grid, 256, 0, s>>>(score, mix_w, items, n_spk); break;
+        default: set_error("softmax_mask: unsupported N=%d", N); return MTN_EINVAL;
+    }
+    MTN_CUDA_LAUNCH_CHECK("softmax_mask");
     return MTN_OK;
 }
 

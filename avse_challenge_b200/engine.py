@@ -246,6 +246,8 @@ class SeparatorEngine(LayerPlan):
     def __init__(self, hp: HParams, sds: dict, device="cuda", mode: str = "fp32", use_graph: bool = True,
                  fuse_norm: bool = False):
         self._init_plan(hp, mode, device)
+        if hp.mask_nonlinear not in ("relu", "softmax"):
+            raise ValueError("Unsupported mask non-linear function")      # mamba_masknet.py:138
         self.use_graph = use_graph
         self.fuse_norm = fuse_norm
         with torch.cuda.device(self.device):
@@ -274,8 +276,12 @@ class SeparatorEngine(LayerPlan):
         for i, lw in enumerate(w.layers):
             self._layer(ws, lw, first=(i == 0), taps=taps, st=None if ss is None else ss["layers"][i])
         op("add_rmsnorm", ops.add_rmsnorm, ws.h, ws.res, True, w.norm_f, P, xn=ws.xn)
-        op("gemm_mask", ops.gemm, ws.xn, w.w_mask, M, hp.n_spk * N, D, out=ws.sep, epilogue=_lib.EPI_MASK, epi_param=N,
-           aux=ws.mix_w)
+        if hp.mask_nonlinear == "softmax":   # mamba_masknet.py:133-134 + train_wsj0mix.py:91-92
+            op("gemm_mask", ops.gemm, ws.xn, w.w_mask, M, hp.n_spk * N, D, out=ws.sep)
+            op("softmax_mask", ops.softmax_mask, ws.sep, ws.mix_w, M, N, hp.n_spk)
+        else:
+            op("gemm_mask", ops.gemm, ws.xn, w.w_mask, M, hp.n_spk * N, D, out=ws.sep, epilogue=_lib.EPI_MASK, epi_param=N,
+               aux=ws.mix_w)
         if ss is None:
             op("decoder", ops.decoder, ws.sep, w.w_dec, ws.batch, ws.T, ws.L, N, hp.n_spk, est=ws.est, frames=ws.frames)
             return ws.est
@@ -285,7 +291,7 @@ class SeparatorEngine(LayerPlan):
         return est
 
     def _run(self, ws: Workspace, taps=None):
-        if not self.fuse_norm or taps is not None:
+        if not self.fuse_norm or taps is not None or self.hp.mask_nonlinear != "relu":
             return self._run_unfused(ws, taps)
         hp, w, P = self.hp, self.w, self.w.P
         N, D, di, M = hp.enc_dim, hp.d_model, hp.d_inner, ws.M

@@ -25,6 +25,7 @@ class HParams:
     d_conv: int = 4
     n_spk: int = 2
     sample_rate: int = 8000
+    mask_nonlinear: str = "relu"  # or "softmax" (modules/mamba_masknet.py:133-138)
     bidirectional: bool = True   # False: causal stack of unidirectional mixers (mamba_blocks.py:128, `mamba_ssm.Mamba`)
 
     @property

@@ -300,8 +300,8 @@ class MaskNet(_EngineOwner):
                  bidirectional=True, d_model=256, d_state=16, expand=2, d_conv=4, fused_add_norm=False, rms_norm=True,
                  residual_in_fp32=False, mode="fp32"):
         super().__init__()
-        if mask_nonlinear != "relu":
-            _unsupported(f"mask_nonlinear={mask_nonlinear!r}")
+        if mask_nonlinear not in ("relu", "softmax"):
+            raise ValueError("Unsupported mask non-linear function")      # modules/mamba_masknet.py:138
         if n_spk != 2:
             _unsupported(f"n_spk={n_spk}")
         if bot_dim != d_model:
@@ -315,7 +315,7 @@ class MaskNet(_EngineOwner):
                                                residual_in_fp32=residual_in_fp32, conv_bias=True, bias=False)
         self.mask_conv1x1 = _SBConv1d(bot_dim, n_spk * enc_dim)
         self.hp = HParams("custom", enc_dim, d_model, n_mamba, d_state=d_state, expand=expand, d_conv=d_conv, n_spk=n_spk,
-                          bidirectional=bidirectional)
+                          bidirectional=bidirectional, mask_nonlinear=mask_nonlinear)
         self._invalidate()
 
     def engine(self, encoder_sd=None, decoder_sd=None, mode=None, use_graph=True) -> SeparatorEngine:
@@ -343,7 +343,10 @@ class MaskNet(_EngineOwner):
         for i, lw in enumerate(w.layers):
             eng._layer(ws, lw, first=(i == 0))
         ops.add_rmsnorm(ws.h, ws.res, True, w.norm_f, P, xn=ws.xn)
-        score = ops.gemm(ws.xn, w.w_mask, ws.M, hp.n_spk * N, hp.d_model, epilogue=_lib.EPI_RELU)
+        if self.mask_nonlinear == "softmax":                      # mamba_masknet.py:133-134 (dim 2 = the N channels)
+            score = ops.softmax_mask(ops.gemm(ws.xn, w.w_mask, ws.M, hp.n_spk * N, hp.d_model), None, ws.M, N, hp.n_spk)
+        else:
+            score = ops.gemm(ws.xn, w.w_mask, ws.M, hp.n_spk * N, hp.d_model, epilogue=_lib.EPI_RELU)
         return score.view(B, L, hp.n_spk, N).permute(2, 0, 3, 1)  # mamba_masknet.py:126-131
 
 
@@ -361,7 +364,8 @@ class MambaTasNetSeparator(_EngineOwner):
     def from_hparams(cls, hp: HParams, mode="fp32", use_graph=True):
         enc = Encoder(hp.kernel_size, hp.enc_dim)
         mask = MaskNet(hp.enc_dim, hp.d_model, n_spk=hp.n_spk, n_mamba=hp.n_mamba, d_model=hp.d_model,
-                       d_state=hp.d_state, expand=hp.expand, d_conv=hp.d_conv, mode=mode, bidirectional=hp.bidirectional)
+                       d_state=hp.d_state, expand=hp.expand, d_conv=hp.d_conv, mode=mode, bidirectional=hp.bidirectional,
+                       mask_nonlinear=hp.mask_nonlinear)
         dec = Decoder(hp.enc_dim, 1, hp.kernel_size, hp.stride, bias=False)
         return cls(enc, mask, dec, mode=mode, use_graph=use_graph)
 

@@ -163,6 +163,14 @@ def scan(u, dbl, z, z_col0, w_dt, dt_bias, A2, Dskip, batch, L, di, R, *, y=None
     return y
 
 
+def softmax_mask(score, mix_w, rows, N, n_spk):
+    """In place: softmax over each speaker's N channels of score [rows, n_spk*N] (x mix_w [rows, N] when given)."""
+    _req_cuda(score, mix_w)
+    assert score.dtype == torch.float32 and score.is_contiguous()
+    check(_lib.load().mtn_softmax_mask_fwd(ptr(score), ptr(mix_w), rows, N, n_spk, _stream()), "mtn_softmax_mask_fwd")
+    return score
+
+
 def fold_states(h_end, sum_delta, A2, g0, n_out, *, h0=None, want_final=False, dir_mask=3):
     """Compose chunk operators (see ``mtn_fold_states_fwd``).  h_end [2, G, di, 16], sum_delta [2, G, di] ->
     (h_in [2, n_out, di, 16], h_final [2, di, 16] or None)."""

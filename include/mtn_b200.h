@@ -190,6 +190,11 @@ int mtn_decoder_stream_fwd(const float* sep, const float* w_dec, float* frames, 
 int mtn_cln_fwd(const float* x, const float* gamma, const float* beta, void* yn_planes, int M, int N, int planes,
                 float eps, mtn_stream_t stream);
 
+/* mask_nonlinear = "softmax" of MaskNet (modules/mamba_masknet.py:133-134: F.softmax(score, dim=2) on [n_spk, B, N, L],
+ * i.e. over the N encoder channels): score fp32 [rows][n_spk*N] in place; mix_w nullable fp32 [rows][N]: the result is
+ * also multiplied by it (mask application, train_wsj0mix.py:91-92). */
+int mtn_softmax_mask_fwd(float* score, const float* mix_w, int rows, int N, int n_spk, mtn_stream_t stream);
+
 /* fp32 [rows][cols] (row stride ld) -> bf16 planes [planes][rows][cols] (weight packing helper) */
 int mtn_split_planes(const float* src, int ld, void* dst_planes, int rows, int cols, int planes, mtn_stream_t stream);
 

@@ -261,7 +261,7 @@ def mamba_stack_fwd(h, sd, n_mamba, prefix="mamba_net.", scan_impl="auto", taps=
     return rmsnorm_fwd(residual, sd[prefix + "norm_f.weight"])             # mamba_blocks.py:197
 
 
-def masknet_fwd(mix_w, sd, n_mamba, n_spk=2, scan_impl="auto", taps=None):
+def masknet_fwd(mix_w, sd, n_mamba, n_spk=2, scan_impl="auto", taps=None, mask_nonlinear="relu"):
     """``MaskNet.forward`` (``modules/mamba_masknet.py:101-139``) on channel-last ``mix_w [B,L,N]``;
     returns the mask ``[n_spk, B, L, N]`` (channel index ``s*N + n``, :126-131; ReLU :136)."""
     B, L, N = mix_w.shape
@@ -269,7 +269,10 @@ def masknet_fwd(mix_w, sd, n_mamba, n_spk=2, scan_impl="auto", taps=None):
     y = _mm(y, sd["bottleneck_conv1x1.conv.weight"][:, :, 0])             # :121
     y = mamba_stack_fwd(y, sd, n_mamba, scan_impl=scan_impl, taps=taps)    # :122
     score = _mm(y, sd["mask_conv1x1.conv.weight"][:, :, 0])               # :123
-    return F.relu(score.reshape(B, L, n_spk, N).permute(2, 0, 1, 3))       # :126-136
+    score = score.reshape(B, L, n_spk, N).permute(2, 0, 1, 3)              # :126-131 ([spk, B, L, N] here)
+    if mask_nonlinear == "softmax":
+        return F.softmax(score, dim=-1)    # :133-134: dim=2 of the reference's [spk, B, N, L] = the N channels
+    return F.relu(score)                                                   # :136
 
 
 def decoder_fwd(sep_h, w_dec):
@@ -279,10 +282,10 @@ def decoder_fwd(sep_h, w_dec):
     return F.conv_transpose1d(sep_h.transpose(1, 2), w_dec, stride=k // 2)[:, 0, :]
 
 
-def separate(mix, sds, n_mamba, n_spk=2, scan_impl="auto", taps=None):
+def separate(mix, sds, n_mamba, n_spk=2, scan_impl="auto", taps=None, mask_nonlinear="relu"):
     """``Separation.compute_forward`` (``Mamba-TasNet/train_wsj0mix.py:86-111``): ``[B,T] -> [B,T,n_spk]``."""
     mix_w = encoder_fwd(mix, sds["encoder"]["conv1d.weight"])              # :89
-    mask = masknet_fwd(mix_w, sds["masknet"], n_mamba, n_spk, scan_impl, taps)  # :90
+    mask = masknet_fwd(mix_w, sds["masknet"], n_mamba, n_spk, scan_impl, taps, mask_nonlinear)  # :90
     est = torch.stack([decoder_fwd(mix_w * mask[s], sds["decoder"]["weight"]) for s in range(n_spk)],
                       dim=-1)                                              # :91-101
     T, T_est = mix.shape[1], est.shape[1]

@@ -329,6 +329,21 @@ def test_end_to_end_matches_reference_golden(golden_dir, tag, use_graph):
     assert fid > 60.0
 
 
+def test_softmax_mask_nonlinear_matches_reference_golden(golden_dir):
+    """mask_nonlinear="softmax": fused engine and the stand-alone MaskNet against the reference's own run."""
+    from dataclasses import replace
+    sds, g, _ = load_golden_forward(os.path.join(golden_dir, "forward_tiny_softmax.npz"))
+    hp = replace(hp_from_sds(sds), mask_nonlinear="softmax")
+    sep = modules.MambaTasNetSeparator.from_hparams(hp, mode="fp32", use_graph=True)
+    sep.load_reference_state_dicts(sds, strict=True).to(DEV)
+    est = sep(g["mix"].to(DEV)).cpu()
+    err, d_sisnr, fid = _gate(est, g["est"], g["src"])
+    assert err <= 1e-3 and d_sisnr <= 0.01, (err, d_sisnr, fid)
+    mask = sep.masknet(torch.as_tensor(g["mix_w"]).to(DEV)).cpu()
+    assert rel_max(mask, g["est_mask"]) <= 1e-3
+    assert torch.allclose(mask.sum(dim=2), torch.ones_like(mask.sum(dim=2)), atol=1e-4)
+
+
 def test_standalone_modules_follow_compute_forward(golden_dir):
     """The reference's own call sequence (train_wsj0mix.py:86-111) on the three drop-in modules."""
     sds, g, taps = load_golden_forward(os.path.join(golden_dir, "forward_tiny_trained.npz"))

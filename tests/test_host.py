@@ -56,7 +56,13 @@ def test_causal_modules_have_mamba_ssm_state_dict_keys():
         modules.Mamba(64).step(torch.zeros(1, 1, 64), torch.zeros(1, 128, 4), torch.zeros(1, 128, 16))
 
 
-@pytest.mark.parametrize("kw", [dict(mask_nonlinear="softmax"), dict(d_state=8),
+def test_unknown_mask_nonlinear_raises_like_the_reference():
+    with pytest.raises(ValueError):                       # modules/mamba_masknet.py:138
+        modules.MaskNet(64, 64, n_mamba=1, d_model=64, mask_nonlinear="tanh")
+    modules.MaskNet(64, 64, n_mamba=1, d_model=64, mask_nonlinear="softmax")
+
+
+@pytest.mark.parametrize("kw", [dict(d_state=8),
                                 dict(d_conv=3), dict(rms_norm=False), dict(n_spk=3)])
 def test_unsupported_options_raise(kw):
     with pytest.raises(NotImplementedError):

@@ -166,3 +166,15 @@ def test_dp_segmentation_round_trip(L, K):
     S, gap2 = restate.dp_num_chunks(L, K)
     assert seg.shape == (2, S, K, 3) and gap == gap2 and S % 2 == 0
     assert torch.allclose(restate.dp_over_add(seg, gap), 2 * x)
+
+
+def test_softmax_mask_restatement_matches_reference_golden(golden_dir):
+    """mask_nonlinear="softmax" (mamba_masknet.py:133-134: softmax over dim 2 of [spk, B, N, L] = the N channels)."""
+    sds, out, _ = load_golden_forward(os.path.join(golden_dir, "forward_tiny_softmax.npz"))
+    with torch.no_grad():
+        mix_w = restate.encoder_fwd(out["mix"], sds["encoder"]["conv1d.weight"])
+        mask = restate.masknet_fwd(mix_w, sds["masknet"], 2, scan_impl="c", mask_nonlinear="softmax")
+        est = restate.separate(out["mix"], sds, 2, scan_impl="c", mask_nonlinear="softmax")
+    assert (mask.permute(0, 1, 3, 2) - out["est_mask"]).abs().max().item() <= 2e-6
+    assert torch.allclose(out["est_mask"].sum(dim=2), torch.ones(2, 1, out["est_mask"].shape[3]), atol=1e-5)
+    assert (est - out["est"]).abs().max().item() <= 2e-6
