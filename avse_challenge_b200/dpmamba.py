@@ -72,8 +72,8 @@ class DPSeparatorEngine:
             raise ValueError(f"mode must be one of {list(MODES)}")
         if not torch.cuda.is_available():
             raise _lib.MtnError("DPSeparatorEngine needs a CUDA device (B200, sm_100a); there is no CPU fallback")
-        if hp.n_spk != 2 or hp.chunk_size % 2 or hp.n_mamba_dp < 2:
-            raise NotImplementedError("DPMamba: n_spk must be 2, chunk_size even, n_mamba_dp >= 2")
+        if hp.n_spk < 1 or hp.chunk_size % 2 or hp.n_mamba_dp < 2:
+            raise NotImplementedError("DPMamba: n_spk >= 1, chunk_size even, n_mamba_dp >= 2")
         _lib.load()
         self.hp, self.mode, self.device, self.use_graph = hp, mode, torch.device(device), use_graph
         P = self.P = MODES[mode]["planes"]

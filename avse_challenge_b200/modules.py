@@ -302,8 +302,8 @@ class MaskNet(_EngineOwner):
         super().__init__()
         if mask_nonlinear not in ("relu", "softmax"):
             raise ValueError("Unsupported mask non-linear function")      # modules/mamba_masknet.py:138
-        if n_spk != 2:
-            _unsupported(f"n_spk={n_spk}")
+        if n_spk < 1:
+            raise ValueError("n_spk must be >= 1")
         if bot_dim != d_model:
             _unsupported("bot_dim != d_model")
         self.n_spk, self.mask_nonlinear, self.mode = n_spk, mask_nonlinear, mode
@@ -425,8 +425,8 @@ class Dual_Path_Model(_EngineOwner):
                 _unsupported("intra / inter models other than a bidirectional MambaBlocksSequential")
         if intra_model.n_mamba != inter_model.n_mamba:
             _unsupported("intra / inter stacks of different depth")
-        if num_spks != 2 or K % 2:
-            _unsupported("num_spks != 2 or odd K")
+        if num_spks < 1 or K % 2:
+            _unsupported("num_spks < 1 or odd K")
         self.K, self.num_spks, self.num_layers, self.mode = K, num_spks, num_layers, mode
         self.norm = nn.GroupNorm(1, in_channels, eps=1e-8)
         self.conv1d = nn.Conv1d(in_channels, out_channels, 1, bias=False)

@@ -156,6 +156,17 @@ def test_dpmamba_shipped_sizes_vs_oracle(name, B, T):
     assert err <= 1e-3 and d <= 0.01, (err, d)
 
 
+def test_dpmamba_three_speakers_vs_oracle():
+    hp = replace(DP_CONFIGS["XS"], n_dp=1, n_spk=3)
+    sds = init_dp_state_dicts(hp, 5)
+    mix, _ = synth_mixture(1, 4000, seed=2)
+    with torch.no_grad():
+        ref = restate.separate_dp(mix, sds, hp, scan_impl="c")
+    est = DPSeparatorEngine(hp, sds, device=DEV, mode="fp32", use_graph=False)(mix.to(DEV)).cpu()
+    assert est.shape == (1, 4000, 3)
+    assert rel_max(est, ref) <= 1e-3
+
+
 def test_dpmamba_bf16_mode_stated_tolerance():
     """bf16 mode (bf16 GEMM operands and xz / u / y storage; fp32 scan state, residual stream and GroupNorm statistics).
     Stated tolerance against the fp32 oracle, as for Mamba-TasNet: max-abs <= 0.15 * rms, SI-SNR(est, ref) >= 25 dB."""
