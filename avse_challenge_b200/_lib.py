@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libmtn_b200.so")
 EPI_STORE, EPI_INPROJ, EPI_MASK, EPI_RELU, EPI_XPROJ, EPI_RESADD = 0, 1, 2, 3, 4, 5
 
 EXPORTS = [
-    "mtn_encoder_cln_fwd", "mtn_gemm_fwd", "mtn_gemm_rowsum_parts", "mtn_add_rmsnorm_fwd", "mtn_add_rmsnorm_out_fwd", "mtn_conv_silu_fwd", "mtn_conv_silu_halo_fwd", "mtn_conv_silu_dir_fwd", "mtn_decoder_stream_fwd",
+    "mtn_encoder_cln_fwd", "mtn_gemm_fwd", "mtn_gemm_rowsum_parts", "mtn_add_rmsnorm_fwd", "mtn_add_rmsnorm_out_fwd", "mtn_add_norm_fwd", "mtn_conv_silu_fwd", "mtn_conv_silu_halo_fwd", "mtn_conv_silu_dir_fwd", "mtn_decoder_stream_fwd",
     "mtn_scan_fwd", "mtn_fold_states_fwd",
     "mtn_gn_partials_bytes", "mtn_gn_stats_fwd", "mtn_gn_apply_fwd", "mtn_gn_apply_norm_fwd", "mtn_dp_num_chunks", "mtn_dp_segment_fwd",
     "mtn_dp_overadd_prelu_fwd", "mtn_bias_planes_fwd", "mtn_gate_planes_fwd",
@@ -80,6 +80,8 @@ def load():
                                         c_void_p]
     lib.mtn_add_rmsnorm_out_fwd.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                             c_float, c_void_p]
+    lib.mtn_add_norm_fwd.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                     c_float, c_void_p]
     lib.mtn_conv_silu_fwd.argtypes = [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                       c_void_p]
     lib.mtn_conv_silu_halo_fwd.argtypes = [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p,

@@ -112,10 +112,13 @@ cln_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const f
 // Reference: Block.forward Mamba-TasNet/modules/mamba/bimamba.py:446-447; final add + norm_f
 // modules/mamba_blocks.py:196-197; RMSNorm math = mamba-ssm rms_norm_ref (fp32, eps 1e-5).
 // ------------------------------------------------------------------------------------------------
-template <int P, int NV, bool VEC>  // VEC: NV float4 per lane (D = 128*NV); else NV floats per lane (D = 32*NV)
+// LN: nn.LayerNorm instead of RMSNorm (`rms_norm=False`, modules/mamba_blocks.py:36-41: mean removed, biased variance,
+// weight and bias) -- the row is already in registers, so the centred second moment costs one more warp reduction.
+template <int P, int NV, bool VEC, bool LN>  // VEC: NV float4 per lane (D = 128*NV); else NV floats per lane (D = 32*NV)
 __global__ void __launch_bounds__(256)
 add_rmsnorm_kernel(const float* __restrict__ h, float* __restrict__ res, int res_valid, const float* __restrict__ g,
-                   __nv_bfloat16* __restrict__ xn, float* __restrict__ out_f32, int M, float eps) {
+                   const float* __restrict__ beta, __nv_bfloat16* __restrict__ xn, float* __restrict__ out_f32, int M,
+                   float eps) {
     constexpr int D = VEC ? 128 * NV : 32 * NV;
     const int lane = threadIdx.x & 31;
     const int warps_per_block = blockDim.x >> 5;
@@ -139,6 +142,19 @@ add_rmsnorm_kernel(const float* __restrict__ h, float* __restrict__ res, int res
                 r[j] = a;
                 sq += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
             }
+            float mean = 0.f;
+            if (LN) {
+                float sm = 0.f;
+#pragma unroll
+                for (int j = 0; j < NV; ++j) sm += (r[j].x + r[j].y) + (r[j].z + r[j].w);
+                mean = warp_sum(sm) * (1.0f / D);
+                sq = 0.f;
+#pragma unroll
+                for (int j = 0; j < NV; ++j) {
+                    const float a0 = r[j].x - mean, a1 = r[j].y - mean, a2 = r[j].z - mean, a3 = r[j].w - mean;
+                    sq += a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3;
+                }
+            }
             const float rstd = rsqrtf(warp_sum(sq) * (1.0f / D) + eps);
 #pragma unroll
             for (int j = 0; j < NV; ++j) {
@@ -146,10 +162,18 @@ add_rmsnorm_kernel(const float* __restrict__ h, float* __restrict__ res, int res
                 if (h) *reinterpret_cast<float4*>(res + off) = r[j];
                 const float4 gg = *reinterpret_cast<const float4*>(g + 128 * j + 4 * lane);
                 float4 o;
+                if (LN) {
+                    const float4 bb = *reinterpret_cast<const float4*>(beta + 128 * j + 4 * lane);
+                    o.x = fmaf((r[j].x - mean) * rstd, gg.x, bb.x);
+                    o.y = fmaf((r[j].y - mean) * rstd, gg.y, bb.y);
+                    o.z = fmaf((r[j].z - mean) * rstd, gg.z, bb.z);
+                    o.w = fmaf((r[j].w - mean) * rstd, gg.w, bb.w);
+                } else {
                 o.x = r[j].x * rstd * gg.x;
                 o.y = r[j].y * rstd * gg.y;
                 o.z = r[j].z * rstd * gg.z;
                 o.w = r[j].w * rstd * gg.w;
+                }
                 if (xn) store_planes4<P>(xn, plane_stride, off, o);
                 if (out_f32) *reinterpret_cast<float4*>(out_f32 + off) = o;
             }
@@ -164,12 +188,23 @@ add_rmsnorm_kernel(const float* __restrict__ h, float* __restrict__ res, int res
                 r[j] = a;
                 sq = fmaf(a, a, sq);
             }
+            float mean = 0.f;
+            if (LN) {
+                float sm = 0.f;
+#pragma unroll
+                for (int j = 0; j < NV; ++j) sm += r[j];
+                mean = warp_sum(sm) * (1.0f / D);
+                sq = 0.f;
+#pragma unroll
+                for (int j = 0; j < NV; ++j) sq = fmaf(r[j] - mean, r[j] - mean, sq);
+            }
             const float rstd = rsqrtf(warp_sum(sq) * (1.0f / D) + eps);
 #pragma unroll
             for (int j = 0; j < NV; ++j) {
                 const size_t off = base + 32 * j + lane;
                 if (h) res[off] = r[j];
-                const float o = r[j] * rstd * g[32 * j + lane];
+                const float o = LN ? fmaf((r[j] - mean) * rstd, g[32 * j + lane], beta[32 * j + lane])
+                                   : r[j] * rstd * g[32 * j + lane];
                 if (xn) store_planes1<P>(xn, plane_stride, off, o);
                 if (out_f32) out_f32[off] = o;
             }
@@ -599,13 +634,22 @@ extern "C" int mtn_add_rmsnorm_fwd(const float* h, float* res, int res_valid, co
 
 extern "C" int mtn_add_rmsnorm_out_fwd(const float* h, float* res, int res_valid, const float* g, void* xn_planes,
                                        float* out_f32, int M, int D, int planes, float eps, mtn_stream_t stream) {
+    return mtn_add_norm_fwd(h, res, res_valid, g, nullptr, xn_planes, out_f32, M, D, planes, eps, stream);
+}
+
+extern "C" int mtn_add_norm_fwd(const float* h, float* res, int res_valid, const float* g, const float* beta, void* xn_planes,
+                                float* out_f32, int M, int D, int planes, float eps, mtn_stream_t stream) {
     MTN_REQUIRE(res && g && (xn_planes || out_f32), "add_rmsnorm: null pointer");
     MTN_REQUIRE(h || res_valid, "add_rmsnorm: need h or a valid residual");
     MTN_REQUIRE(M > 0 && planes >= 1 && planes <= 2, "add_rmsnorm: bad M=%d planes=%d", M, planes);
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     const int grid = grid_for(size_t(M), 8, 8);
     __nv_bfloat16* xn = reinterpret_cast<__nv_bfloat16*>(xn_planes);
-#define MTN_RMS(PP, NV, VEC) add_rmsnorm_kernel<PP, NV, VEC><<<grid, 256, 0, s>>>(h, res, res_valid, g, xn, out_f32, M, eps)
+#define MTN_RMS(PP, NV, VEC)                                                                                          \
+    do {                                                                                                             \
+        if (beta) add_rmsnorm_kernel<PP, NV, VEC, true><<<grid, 256, 0, s>>>(h, res, res_valid, g, beta, xn, out_f32, M, eps);  \
+        else add_rmsnorm_kernel<PP, NV, VEC, false><<<grid, 256, 0, s>>>(h, res, res_valid, g, beta, xn, out_f32, M, eps);      \
+    } while (0)
 #define MTN_RMS_D(PP)                                                             \
     switch (D) {                                                                  \
         case 64: MTN_RMS(PP, 2, false); break;                                    \

@@ -138,7 +138,7 @@ class DPSeparatorEngine:
         n_skip = hp.skip_n_block
         if n_skip > 0:
             ws.R.copy_(ws.X)                                                               # residual = x, dual_path.py:100
-        fused = D in (128, 256, 512)   # GroupNorm apply + the next stack's opening RMSNorm in one kernel (gn_apply_norm)
+        fused = D in (128, 256, 512) and hp.stack.rms_norm   # GroupNorm apply + the next stack's opening RMSNorm in one kernel (gn_apply_norm)
         for i, blk in enumerate(self.blocks):
             last = i == len(self.blocks) - 1
             # `x = 0.5 * x + 0.5 * residual` in front of block i + 1 (dual_path.py:114-116) is applied by the norm that ends

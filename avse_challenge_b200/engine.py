@@ -49,6 +49,7 @@ class PackedWeights:
         self.w_bot = ops.split_planes(f32(m["bottleneck_conv1x1.conv.weight"]).reshape(D, N), P)
         self.w_mask = ops.split_planes(f32(m["mask_conv1x1.conv.weight"]).reshape(hp.n_spk * N, D), P)
         self.norm_f = f32(m["mamba_net.norm_f.weight"])
+        self.norm_f_b = f32(m["mamba_net.norm_f.bias"]) if not hp.rms_norm else None     # nn.LayerNorm (rms_norm=False)
         self.w_mask_g = ops.split_planes(f32(m["mask_conv1x1.conv.weight"]).reshape(hp.n_spk * N, D) * self.norm_f[None, :], P)
         self.layers = [pack_layer(m, f"mamba_net.layers.{i}.", hp, P, device) for i in range(hp.n_mamba)]
 
@@ -60,6 +61,7 @@ def pack_layer(m: dict, p: str, hp: HParams, P: int, device) -> dict:
     nd = n_dbl_for(R)
     lw = {}
     lw["norm"] = f32(m[p + "norm.weight"])
+    lw["norm_b"] = f32(m[p + "norm.bias"]) if not hp.rms_norm else None                 # nn.LayerNorm (rms_norm=False)
     lw["w_in"] = ops.split_planes(f32(m[p + "mixer.in_proj.weight"]), P)            # [P, 2di, D]
     lw["w_in_g"] = ops.split_planes(f32(m[p + "mixer.in_proj.weight"]) * lw["norm"][None, :], P)  # RMSNorm gain folded in
     sfxs = ("", "_b") if hp.bidirectional else ("",)      # unidirectional: mamba_ssm.Mamba keys, forward set only
@@ -190,7 +192,7 @@ class LayerPlan:
         D, di, M = hp.d_model, hp.d_inner, ws.M
         op = self._op
         if not prenormed:   # prenormed: the producer already wrote ws.res and ws.xn = RMSNorm(res) * lw["norm"]
-            op("add_rmsnorm", ops.add_rmsnorm, ws.h, ws.res, not first, lw["norm"], P, xn=ws.xn)
+            op("add_rmsnorm", ops.add_rmsnorm, ws.h, ws.res, not first, lw["norm"], P, xn=ws.xn, beta=lw["norm_b"])
         op("gemm_in_proj", ops.gemm, ws.xn, lw["w_in"], M, 2 * di, D, out=ws.xz, epilogue=_lib.EPI_INPROJ, epi_param=di,
            out_bf16=ws.xz.dtype == torch.bfloat16)
         self._mixer_core(ws, lw, st)
@@ -211,6 +213,7 @@ class MambaStack(LayerPlan):
         with torch.cuda.device(self.device):
             self.layers = [pack_layer(sd, f"{prefix}layers.{i}.", hp, self.P, self.device) for i in range(hp.n_mamba)]
             self.norm_f = f32(sd[prefix + "norm_f.weight"])
+            self.norm_f_b = f32(sd[prefix + "norm_f.bias"]) if not hp.rms_norm else None
         self._ws = {}
 
     def workspace(self, batch, L) -> LayerWorkspace:
@@ -225,7 +228,8 @@ class MambaStack(LayerPlan):
         and ``ws.xn`` with its RMSNorm under ``self.layers[0]["norm"]`` (fused producer), so the first launch is skipped."""
         for i, lw in enumerate(self.layers):
             self._layer(ws, lw, first=(i == 0), st=None if states is None else states[i], prenormed=(prenormed and i == 0))
-        self._op("add_rmsnorm", ops.add_rmsnorm, ws.h, ws.res, True, self.norm_f, self.P, xn=False, out_f32=out)
+        self._op("add_rmsnorm", ops.add_rmsnorm, ws.h, ws.res, True, self.norm_f, self.P, xn=False, out_f32=out,
+                 beta=self.norm_f_b)
         return out
 
     @torch.no_grad()
@@ -275,7 +279,7 @@ class SeparatorEngine(LayerPlan):
         op("gemm_bottleneck", ops.gemm, ws.yn, w.w_bot, M, D, N, out=ws.h)
         for i, lw in enumerate(w.layers):
             self._layer(ws, lw, first=(i == 0), taps=taps, st=None if ss is None else ss["layers"][i])
-        op("add_rmsnorm", ops.add_rmsnorm, ws.h, ws.res, True, w.norm_f, P, xn=ws.xn)
+        op("add_rmsnorm", ops.add_rmsnorm, ws.h, ws.res, True, w.norm_f, P, xn=ws.xn, beta=w.norm_f_b)
         if hp.mask_nonlinear == "softmax":   # mamba_masknet.py:133-134 + train_wsj0mix.py:91-92
             op("gemm_mask", ops.gemm, ws.xn, w.w_mask, M, hp.n_spk * N, D, out=ws.sep)
             op("softmax_mask", ops.softmax_mask, ws.sep, ws.mix_w, M, N, hp.n_spk)
@@ -291,7 +295,7 @@ class SeparatorEngine(LayerPlan):
         return est
 
     def _run(self, ws: Workspace, taps=None):
-        if not self.fuse_norm or taps is not None or self.hp.mask_nonlinear != "relu":
+        if not self.fuse_norm or taps is not None or self.hp.mask_nonlinear != "relu" or not self.hp.rms_norm:
             return self._run_unfused(ws, taps)
         hp, w, P = self.hp, self.w, self.w.P
         N, D, di, M = hp.enc_dim, hp.d_model, hp.d_inner, ws.M

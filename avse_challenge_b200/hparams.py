@@ -26,6 +26,7 @@ class HParams:
     n_spk: int = 2
     sample_rate: int = 8000
     mask_nonlinear: str = "relu"  # or "softmax" (modules/mamba_masknet.py:133-138)
+    rms_norm: bool = True         # False: nn.LayerNorm blocks and norm_f (modules/mamba_blocks.py:36-41,167-169)
     bidirectional: bool = True   # False: causal stack of unidirectional mixers (mamba_blocks.py:128, `mamba_ssm.Mamba`)
 
     @property
@@ -108,7 +109,11 @@ def init_state_dicts(hp: HParams, seed: int = 1234, trained_like: bool = True):
             m[p + f"mixer.dt_proj{sfx}.bias"] = dt + torch.log(-torch.expm1(-dt))
         m[p + "mixer.out_proj.weight"] = linear_w(D, di) / math.sqrt(hp.n_mamba)
         m[p + "norm.weight"] = torch.ones(D)
+        if not hp.rms_norm:
+            m[p + "norm.bias"] = torch.zeros(D)
     m["mamba_net.norm_f.weight"] = torch.ones(D)
+    if not hp.rms_norm:
+        m["mamba_net.norm_f.bias"] = torch.zeros(D)
     m["mask_conv1x1.conv.weight"] = linear_w(hp.n_spk * N, D).unsqueeze(-1)
     if trained_like:
         for k in list(m.keys()):
@@ -118,7 +123,7 @@ def init_state_dicts(hp: HParams, seed: int = 1234, trained_like: bool = True):
                 m[k] = m[k] + 0.2 * torch.randn(m[k].shape, generator=g)
             elif k.endswith("norm.weight") or k.endswith("norm_f.weight") or k.endswith("gamma"):
                 m[k] = m[k] + 0.1 * torch.randn(m[k].shape, generator=g)
-            elif k.endswith("beta"):
+            elif k.endswith("beta") or k.endswith("norm.bias") or k.endswith("norm_f.bias"):
                 m[k] = m[k] + 0.05 * torch.randn(m[k].shape, generator=g)
     return {"encoder": enc, "masknet": m, "decoder": dec}
 

@@ -146,6 +146,10 @@ class Mamba(nn.Module):
         return out.view(B, 1, D).to(hidden_states.dtype), conv_state, ssm_state
 
 
+class LayerNormParams(nn.LayerNorm):
+    """``nn.LayerNorm`` parameter container (``rms_norm=False``: ``modules/mamba_blocks.py:36-41``)."""
+
+
 class Block(nn.Module):
     """Add -> RMSNorm -> Mixer (``modules/mamba/bimamba.py:409-462``); parameters only."""
 
@@ -166,7 +170,7 @@ def _stack_forward(self, x, keep_to=None, inference_params=None):
     dev = self.norm_f.weight.device
     if "s" not in cache:
         D = self.norm_f.weight.shape[0]
-        hp = HParams("stack", D, D, self.n_mamba, bidirectional=self.bidirectional)
+        hp = HParams("stack", D, D, self.n_mamba, bidirectional=self.bidirectional, rms_norm=self.rms_norm)
         cache["s"] = MambaStack(hp, self.state_dict(), device=dev, mode="fp32")
     stack = cache["s"]
     B, L, D = x.shape
@@ -201,18 +205,18 @@ class MambaBlocksSequential(nn.Module):
                  conv_bias=True, bias=False, fused_add_norm=True, rms_norm=False, norm_epsilon=1e-5,
                  initializer_cfg=None, residual_in_fp32=False):
         super().__init__()
-        if not rms_norm:
-            _unsupported("rms_norm=False (nn.LayerNorm blocks)")
         if norm_epsilon != 1e-5:
             _unsupported("norm_epsilon != 1e-5")
         # fused_add_norm only selects between two mathematically identical reference code paths
         # (mamba_blocks.py:195-210); residual_in_fp32: the residual stream here is always fp32.
-        self.n_mamba, self.bidirectional = n_mamba, bidirectional
+        self.n_mamba, self.bidirectional, self.rms_norm = n_mamba, bidirectional, rms_norm
         btype = "v2" if bidirectional else "none"      # mamba_blocks.py:128: BiMamba if bidirectional else mamba_ssm.Mamba
+        norm_cls = RMSNorm if rms_norm else (lambda d: LayerNormParams(d, eps=norm_epsilon))   # mamba_blocks.py:36-41
         mk = lambda i: Block(d_model, lambda d: Mamba(d, d_state=d_state, d_conv=d_conv, expand=expand, dt_rank=dt_rank,
-                                                      conv_bias=conv_bias, bias=bias, layer_idx=i, bimamba_type=btype))
+                                                      conv_bias=conv_bias, bias=bias, layer_idx=i, bimamba_type=btype),
+                             norm_cls=norm_cls)
         self.layers = nn.Sequential(*[mk(i) for i in range(n_mamba)])
-        self.norm_f = RMSNorm(d_model, eps=norm_epsilon)
+        self.norm_f = RMSNorm(d_model, eps=norm_epsilon) if rms_norm else LayerNormParams(d_model, eps=norm_epsilon)
         with torch.no_grad():  # out_proj rescale, mamba_blocks.py:76-84
             for blk in self.layers:
                 nn.init.kaiming_uniform_(blk.mixer.out_proj.weight, a=math.sqrt(5))
@@ -315,7 +319,7 @@ class MaskNet(_EngineOwner):
                                                residual_in_fp32=residual_in_fp32, conv_bias=True, bias=False)
         self.mask_conv1x1 = _SBConv1d(bot_dim, n_spk * enc_dim)
         self.hp = HParams("custom", enc_dim, d_model, n_mamba, d_state=d_state, expand=expand, d_conv=d_conv, n_spk=n_spk,
-                          bidirectional=bidirectional, mask_nonlinear=mask_nonlinear)
+                          bidirectional=bidirectional, mask_nonlinear=mask_nonlinear, rms_norm=rms_norm)
         self._invalidate()
 
     def engine(self, encoder_sd=None, decoder_sd=None, mode=None, use_graph=True) -> SeparatorEngine:
@@ -342,7 +346,7 @@ class MaskNet(_EngineOwner):
         ops.gemm(ws.yn, w.w_bot, ws.M, hp.d_model, N, out=ws.h)
         for i, lw in enumerate(w.layers):
             eng._layer(ws, lw, first=(i == 0))
-        ops.add_rmsnorm(ws.h, ws.res, True, w.norm_f, P, xn=ws.xn)
+        ops.add_rmsnorm(ws.h, ws.res, True, w.norm_f, P, xn=ws.xn, beta=w.norm_f_b)
         if self.mask_nonlinear == "softmax":                      # mamba_masknet.py:133-134 (dim 2 = the N channels)
             score = ops.softmax_mask(ops.gemm(ws.xn, w.w_mask, ws.M, hp.n_spk * N, hp.d_model), None, ws.M, N, hp.n_spk)
         else:
@@ -365,7 +369,7 @@ class MambaTasNetSeparator(_EngineOwner):
         enc = Encoder(hp.kernel_size, hp.enc_dim)
         mask = MaskNet(hp.enc_dim, hp.d_model, n_spk=hp.n_spk, n_mamba=hp.n_mamba, d_model=hp.d_model,
                        d_state=hp.d_state, expand=hp.expand, d_conv=hp.d_conv, mode=mode, bidirectional=hp.bidirectional,
-                       mask_nonlinear=hp.mask_nonlinear)
+                       mask_nonlinear=hp.mask_nonlinear, rms_norm=hp.rms_norm)
         dec = Decoder(hp.enc_dim, 1, hp.kernel_size, hp.stride, bias=False)
         return cls(enc, mask, dec, mode=mode, use_graph=use_graph)
 

@@ -113,17 +113,18 @@ def rowsum_parts(N: int) -> int:
     return int(_lib.load().mtn_gemm_rowsum_parts(N))
 
 
-def add_rmsnorm(h, res, res_valid, g, planes, eps=1e-5, xn=None, out_f32=None):
-    """``out_f32`` (fp32 [M, D]): also (or, with ``xn=False``, only) write the normalised rows in fp32."""
-    _req_cuda(res, g)
+def add_rmsnorm(h, res, res_valid, g, planes, eps=1e-5, xn=None, out_f32=None, beta=None):
+    """``out_f32`` (fp32 [M, D]): also (or, with ``xn=False``, only) write the normalised rows in fp32.
+    ``beta`` ([D]): LayerNorm (mean removed, weight ``g``, bias ``beta``) instead of RMSNorm."""
+    _req_cuda(res, g, beta)
     M, D = res.shape
     if xn is None:
         xn = torch.empty((planes, M, D), dtype=torch.bfloat16, device=res.device)
     elif xn is False:
         assert out_f32 is not None
         xn = None
-    check(_lib.load().mtn_add_rmsnorm_out_fwd(ptr(h), ptr(res), int(res_valid), ptr(g), ptr(xn), ptr(out_f32), M, D, planes,
-                                              eps, _stream()), "mtn_add_rmsnorm_out_fwd")
+    check(_lib.load().mtn_add_norm_fwd(ptr(h), ptr(res), int(res_valid), ptr(g), ptr(beta), ptr(xn), ptr(out_f32), M, D, planes,
+                                       eps, _stream()), "mtn_add_norm_fwd")
     return xn if xn is not None else out_f32
 
 

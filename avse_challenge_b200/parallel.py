@@ -182,7 +182,7 @@ class CudaSeqBackend:
     # ---- per layer
     def pre(self, i: int):
         lw, o, hp = self.w.layers[i], self.ops, self.hp
-        o.add_rmsnorm(self.h, self.res, i > 0, lw["norm"], self.P, xn=self.xn)
+        o.add_rmsnorm(self.h, self.res, i > 0, lw["norm"], self.P, xn=self.xn, beta=lw["norm_b"])
         o.gemm(self.xn, lw["w_in"], self.Lr, 2 * hp.d_inner, hp.d_model, out=self.xz, epilogue=self._lib.EPI_INPROJ,
                epi_param=hp.d_inner, out_bf16=self.xz.dtype == torch.bfloat16)
 
@@ -231,7 +231,7 @@ class CudaSeqBackend:
     # ---- tail
     def head(self):
         hp, w, o = self.hp, self.w, self.ops
-        o.add_rmsnorm(self.h, self.res, True, w.norm_f, self.P, xn=self.xn)
+        o.add_rmsnorm(self.h, self.res, True, w.norm_f, self.P, xn=self.xn, beta=w.norm_f_b)
         o.gemm(self.xn, w.w_mask, self.Lr, hp.n_spk * hp.enc_dim, hp.d_model, out=self.sep_full[1:],
                epilogue=self._lib.EPI_MASK, epi_param=hp.enc_dim, aux=self.mix_w)
 

@@ -140,6 +140,11 @@ int mtn_add_rmsnorm_fwd(const float* h, float* res, int res_valid, const float* 
 int mtn_add_rmsnorm_out_fwd(const float* h, float* res, int res_valid, const float* g, void* xn_planes, float* out_f32,
                             int M, int D, int planes, float eps, mtn_stream_t stream);
 
+/* Same with an optional bias `beta` [D]: beta != NULL selects nn.LayerNorm (mean removed, biased variance, weight g and
+ * bias beta) instead of RMSNorm -- `rms_norm=False` in create_block / norm_f (modules/mamba_blocks.py:36-41,167-169). */
+int mtn_add_norm_fwd(const float* h, float* res, int res_valid, const float* g, const float* beta, void* xn_planes,
+                     float* out_f32, int M, int D, int planes, float eps, mtn_stream_t stream);
+
 /* xs = xz[:, 0:di] (fp32 or bf16, row stride ldxz) -> u planes [P][M][2*di]:
  * u_fwd[t] = silu(b + sum_k w[k]*xs[t-3+k]),  u_bwd[t] = silu(b' + sum_k w'[k]*xs[t+3-k]), zero padded per
  * utterance.  conv_w [2][di][4], conv_b [2][di]. */

@@ -54,11 +54,13 @@ def golden_scan():
                         out_reverse=out_b.numpy())
 
 
-def golden_forward(name, T, batch, seed, tag, own_init, bidirectional=True, mask_nonlinear="relu"):
+def golden_forward(name, T, batch, seed, tag, own_init, bidirectional=True, mask_nonlinear="relu", rms_norm=True):
+    from dataclasses import replace
     hp = CONFIGS[name] if bidirectional else CONFIGS[name].causal()
+    hp = replace(hp, rms_norm=rms_norm)
     ref = ref_shims.load_reference()
     enc, mask, dec = ref_shims.build_reference_model(hp.as_dict(), seed=seed, bidirectional=bidirectional,
-                                                     mask_nonlinear=mask_nonlinear)
+                                                     mask_nonlinear=mask_nonlinear, rms_norm=rms_norm)
     if own_init:  # perturbed ("trained-like") weights, loaded strict into the reference modules
         sds = init_state_dicts(hp, seed)
         enc.load_state_dict(sds["encoder"], strict=True)
@@ -178,6 +180,7 @@ def main():
     _, mask, _ = golden_forward("tiny", T=1203, batch=2, seed=55, tag="tiny_causal", own_init=True, bidirectional=False)
     golden_stream(mask, "tiny_causal")
     golden_forward("tiny", T=803, batch=1, seed=66, tag="tiny_softmax", own_init=True, mask_nonlinear="softmax")
+    golden_forward("tiny", T=803, batch=1, seed=67, tag="tiny_layernorm", own_init=True, rms_norm=False)
     golden_dp("dp_tiny_skip", T=1203, batch=2, seed=91, skip_around_intra=True)
     golden_dp("dp_tiny_noskip", T=811, batch=1, seed=92, skip_around_intra=False)
     golden_dp("dp_tiny_blockskip", T=643, batch=1, seed=93, skip_around_intra=True, skip_n_block=1, n_dp=3)

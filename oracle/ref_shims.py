@@ -321,7 +321,7 @@ def load_reference():
     return _loaded
 
 
-def build_reference_model(hp, seed=1234, bidirectional=True, mask_nonlinear="relu"):
+def build_reference_model(hp, seed=1234, bidirectional=True, mask_nonlinear="relu", rms_norm=True):
     """Construct reference Encoder/MaskNet/Decoder with the reference's own init under a seed.
 
     ``hp`` needs: enc_dim, d_model, n_mamba, kernel_size."""
@@ -331,7 +331,7 @@ def build_reference_model(hp, seed=1234, bidirectional=True, mask_nonlinear="rel
     mask = ref.MaskNet(enc_dim=hp["enc_dim"], bot_dim=hp["d_model"], n_spk=2, n_mamba=hp["n_mamba"],
                        mask_nonlinear=mask_nonlinear,
                        bidirectional=bidirectional, d_model=hp["d_model"], d_state=16, expand=2, d_conv=4,
-                       fused_add_norm=False, rms_norm=True, residual_in_fp32=False)
+                       fused_add_norm=False, rms_norm=rms_norm, residual_in_fp32=False)
     dec = ref.Decoder(in_channels=hp["enc_dim"], out_channels=1, kernel_size=hp["kernel_size"],
                       stride=hp["kernel_size"] // 2, bias=False)
     return enc.eval(), mask.eval(), dec.eval()

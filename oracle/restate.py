@@ -99,6 +99,14 @@ def rmsnorm_fwd(x, w, eps=1e-5):
     return x * torch.rsqrt(x.pow(2).mean(dim=-1, keepdim=True) + eps) * w
 
 
+def block_norm(x, sd, key, eps=1e-5):
+    """The block / final norm: RMSNorm, or ``nn.LayerNorm`` when the state_dict carries a bias for it
+    (``rms_norm=False``, ``modules/mamba_blocks.py:36-41,167-169``)."""
+    if key + ".bias" in sd:
+        return F.layer_norm(x, (x.shape[-1],), sd[key + ".weight"], sd[key + ".bias"], eps)
+    return rmsnorm_fwd(x, sd[key + ".weight"], eps)
+
+
 def causal_conv_silu(xs, w, b, reverse=False):
     """Depthwise causal conv (width 4) + bias + SiLU on ``[B, L, di]``.
     ``causal_conv1d_fwd`` call site ``modules/mamba/selective_scan_interface.py:182``; the backward
@@ -253,12 +261,12 @@ def mamba_stack_fwd(h, sd, n_mamba, prefix="mamba_net.", scan_impl="auto", taps=
     for i in range(n_mamba):
         p = f"{prefix}layers.{i}."
         residual = h if residual is None else h + residual                # bimamba.py:446
-        hn = rmsnorm_fwd(residual, sd[p + "norm.weight"])                  # bimamba.py:447
+        hn = block_norm(residual, sd, p + "norm")                          # bimamba.py:447
         h = mixer_fwd(hn, sd, p + "mixer.", scan_impl, state=None if states is None else states[i])  # bimamba.py:461
         if taps is not None:
             taps.append(h)
     residual = h + residual if residual is not None else h                 # mamba_blocks.py:196
-    return rmsnorm_fwd(residual, sd[prefix + "norm_f.weight"])             # mamba_blocks.py:197
+    return block_norm(residual, sd, prefix + "norm_f")                     # mamba_blocks.py:197
 
 
 def masknet_fwd(mix_w, sd, n_mamba, n_spk=2, scan_impl="auto", taps=None, mask_nonlinear="relu"):

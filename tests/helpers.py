@@ -33,4 +33,4 @@ def hp_from_sds(sds):
     N = m["layer_norm.gamma"].shape[-1]
     D = m["mamba_net.norm_f.weight"].shape[0]
     n = 1 + max(int(k.split(".")[2]) for k in m if k.startswith("mamba_net.layers."))
-    return HParams("golden", N, D, n)
+    return HParams("golden", N, D, n, rms_norm="mamba_net.norm_f.bias" not in m)

@@ -148,6 +148,24 @@ def test_streaming_single_frame_chunks_and_rejects():
         StreamingSeparator(SeparatorEngine(CONFIGS["tiny"], init_state_dicts(CONFIGS["tiny"], 1), device=DEV), 1)
 
 
+def test_causal_bf16_mode_one_shot_and_streaming():
+    """bf16 mode of the causal stack: stated tolerance against the fp32 oracle (as test_bf16_mode_stated_tolerance), and
+    chunked streaming against the one-shot bf16 forward (same kernels, same rounding points -> fp32-class agreement)."""
+    from avse_challenge_b200 import si_snr
+    hp = CONFIGS["S"].causal()
+    sds = init_state_dicts(hp, 1234)
+    mix, src = synth_mixture(2, 8000, seed=7)
+    with torch.no_grad():
+        ref = restate.separate(mix, sds, hp.n_mamba, scan_impl="c")
+    eng = SeparatorEngine(hp, sds, device=DEV, mode="bf16", use_graph=False)
+    one = eng(mix.to(DEV)).cpu()
+    err, fid = rel_max(one, ref), si_snr(one, ref).min().item()
+    print(f"causal S bf16: max-abs/rms {err:.3e}  SI-SNR(est,ref) {fid:.1f} dB")
+    assert err <= 0.15 and fid >= 25.0, (err, fid)
+    got = StreamingSeparator(eng, 2, use_graph=True).separate(mix.to(DEV), 8 * 40).cpu()
+    assert rel_max(got, one) <= 1e-4
+
+
 def test_stack_forward_with_inference_params_matches_reference_cache_golden(golden_dir):
     """`MambaBlocksSequential.forward(x, inference_params)` drop-in: prefill L0 tokens then one token per call, against
     the reference's own streamed outputs and final conv / ssm caches."""

@@ -344,6 +344,28 @@ def test_softmax_mask_nonlinear_matches_reference_golden(golden_dir):
     assert torch.allclose(mask.sum(dim=2), torch.ones_like(mask.sum(dim=2)), atol=1e-4)
 
 
+def test_layernorm_blocks_match_reference_golden(golden_dir):
+    """rms_norm=False (nn.LayerNorm blocks + norm_f): engine and strict state_dict load against the reference's run."""
+    sds, g, _ = load_golden_forward(os.path.join(golden_dir, "forward_tiny_layernorm.npz"))
+    hp = hp_from_sds(sds)
+    assert not hp.rms_norm
+    sep = modules.MambaTasNetSeparator.from_hparams(hp, mode="fp32", use_graph=False)
+    sep.load_reference_state_dicts(sds, strict=True).to(DEV)
+    est = sep(g["mix"].to(DEV)).cpu()
+    err, d_sisnr, fid = _gate(est, g["est"], g["src"])
+    assert err <= 1e-3 and d_sisnr <= 0.01, (err, d_sisnr, fid)
+    # the kernel alone, D = 256 (vector path), against torch
+    gen = torch.Generator().manual_seed(1)
+    M, D = 777, 256
+    h, res = torch.randn(M, D, generator=gen) + 0.7, torch.randn(M, D, generator=gen)
+    w, b = torch.randn(D, generator=gen), torch.randn(D, generator=gen)
+    ref = torch.nn.functional.layer_norm(h + res, (D,), w, b, 1e-5)
+    out = torch.empty(M, D, device=DEV)
+    res_d = res.to(DEV)
+    ops.add_rmsnorm(h.to(DEV), res_d, True, w.to(DEV), 2, xn=False, out_f32=out, beta=b.to(DEV))
+    assert rel_max(out.cpu(), ref) <= 1e-5 and rel_max(res_d.cpu(), h + res) <= 1e-6
+
+
 def test_three_speakers_vs_oracle():
     """num_spks = 3 (the recipes' "set to 3 for wsj0-3mix", hparams/WSJ0Mix/mambatasnet_S.yaml:39): mask conv to 3*N
     channels, three decoder passes."""

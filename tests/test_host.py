@@ -63,7 +63,7 @@ def test_unknown_mask_nonlinear_raises_like_the_reference():
 
 
 @pytest.mark.parametrize("kw", [dict(d_state=8),
-                                dict(d_conv=3), dict(rms_norm=False)])
+                                dict(d_conv=3)])
 def test_unsupported_options_raise(kw):
     with pytest.raises(NotImplementedError):
         modules.MaskNet(64, 64, n_mamba=1, d_model=64, **kw)

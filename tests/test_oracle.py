@@ -178,3 +178,12 @@ def test_softmax_mask_restatement_matches_reference_golden(golden_dir):
     assert (mask.permute(0, 1, 3, 2) - out["est_mask"]).abs().max().item() <= 2e-6
     assert torch.allclose(out["est_mask"].sum(dim=2), torch.ones(2, 1, out["est_mask"].shape[3]), atol=1e-5)
     assert (est - out["est"]).abs().max().item() <= 2e-6
+
+
+def test_layernorm_blocks_restatement_matches_reference_golden(golden_dir):
+    """rms_norm=False: nn.LayerNorm blocks and norm_f (modules/mamba_blocks.py:36-41,167-169), reference's own run."""
+    sds, out, _ = load_golden_forward(os.path.join(golden_dir, "forward_tiny_layernorm.npz"))
+    assert "mamba_net.norm_f.bias" in sds["masknet"]
+    with torch.no_grad():
+        est = restate.separate(out["mix"], sds, 2, scan_impl="c")
+    assert (est - out["est"]).abs().max().item() <= 2e-6
