@@ -362,6 +362,10 @@ def run_b200_arm(a):
                 tj = json.load(open(tp))
                 key = f"{a.hparams}_b{a.batch}_{a.mode}" + ("" if hp.bidirectional else "_causal") + ("_dp" if a.model == "dpmamba" else "")
                 traffic = tj.get(key, {}).get("dram_bytes_per_launch")
+                if traffic is None:   # measured bytes per token of the same hparams / mode, scaled to this launch
+                    per_tok = tj.get("per_token", {}).get(f"{a.hparams}_{a.mode}", {}).get("bytes")
+                    if per_tok is not None:
+                        traffic = int(per_tok * scan_tokens * (1.0 if hp.bidirectional else 0.5))
             except Exception:
                 traffic = None
         sm_mhz = (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
