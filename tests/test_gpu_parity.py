@@ -645,3 +645,28 @@ def test_separator_from_checkpoint_dir(tmp_path):
     est = sep(mix.to(DEV)).cpu()
     ref = SeparatorEngine(hp, sds, device=DEV, mode="fp32", use_graph=False)(mix.to(DEV)).cpu()
     assert torch.equal(est, ref)
+
+
+@pytest.mark.parametrize("scale", [0.0, 1e-6, 30.0])
+def test_degenerate_inputs_stay_finite_and_match_oracle(scale):
+    """Digital silence (zero variance in cLN / GroupNorm: eps-only denominators), near-silence and a clipped-loud mixture
+    through both model families: finite outputs, same values as the oracle."""
+    from dataclasses import replace
+    from avse_challenge_b200 import DP_CONFIGS, init_dp_state_dicts
+    from avse_challenge_b200.dpmamba import DPSeparatorEngine
+    mix, _ = synth_mixture(2, 2400, seed=4)
+    mix = mix * scale
+    hp = CONFIGS["tiny"]
+    sds = init_state_dicts(hp, 8)
+    with torch.no_grad():
+        ref = restate.separate(mix, sds, hp.n_mamba, scan_impl="c")
+    est = SeparatorEngine(hp, sds, device=DEV, mode="fp32", use_graph=False)(mix.to(DEV)).cpu()
+    assert torch.isfinite(est).all()
+    assert (est - ref).abs().max().item() <= 1e-3 * max(ref.pow(2).mean().sqrt().item(), 1e-12) + 1e-12
+    dhp = replace(DP_CONFIGS["tiny"], n_dp=1)
+    dsds = init_dp_state_dicts(dhp, 8)
+    with torch.no_grad():
+        dref = restate.separate_dp(mix, dsds, dhp, scan_impl="c")
+    dest = DPSeparatorEngine(dhp, dsds, device=DEV, mode="fp32", use_graph=False)(mix.to(DEV)).cpu()
+    assert torch.isfinite(dest).all()
+    assert (dest - dref).abs().max().item() <= 1e-3 * max(dref.pow(2).mean().sqrt().item(), 1e-12) + 1e-12
