@@ -248,7 +248,7 @@ __device__ __forceinline__ void scan_pair_recur(const uint8_t* ring, float* slot
 // epilogue (MTN_EPI_XPROJ) and arrive through the TMA ring.  Helper warp w (warp 4 + w) owns TMEM lanes [32 w, +32) =
 // exactly its own channels, so one tcgen05.ld.32x32b.x16 hands every lane its channel's 16 pre-activations: no
 // shuffle, no dot products on the FMA pipe (R FMAs + R/4 LDS.128 per (step, channel) otherwise).
-template <int P, int R, int NDBL, typename ZT, bool WY, bool TC, int ABL>
+template <int P, int R, int NDBL, typename ZT, bool WY, bool TC, int ABL, bool BAL = false>
 __device__ __forceinline__ void scan_pair_helper(uint8_t* ring, float* slots, uint8_t* zbuf_all, uint64_t* full_bar,
                                                  uint64_t* empty_bar, uint64_t* prepped, uint64_t* ydone,
                                                  uint64_t* dtfull, uint8_t* wa, uint32_t tmem_base,
