@@ -53,5 +53,6 @@ for var in a.variants.split(","):
     diff = ((yv - y_ref).abs().max() / y_ref.pow(2).mean().sqrt()).item()
     print(json.dumps({"variant": var, "scan_ms": round(ms, 4), "alg_GBps": round(alg / ms / 1e6, 1),
                       "frac_of_6541": round(alg / ms / 1e6 / 6541.1, 4), "max_abs_diff_vs_first/rms": diff,
+                      "y_checksum": [yv.double().sum().item(), yv.double().abs().sum().item()],
                       "mufu_bound_ms@1965": round(2 * M * di * 16 / (148 * 16 * 1.965e9) * 1e3, 4),
                       "shape": [a.hparams, a.batch, a.L, a.mode]}), flush=True)
