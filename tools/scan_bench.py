@@ -5,7 +5,9 @@
 import argparse, json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from avse_challenge_b200 import CONFIGS, ops
+from avse_challenge_b200 import CONFIGS, ops, _lib
+if os.environ.get("MTN_LIB"):   # dev knob of this tool only: time an experimental build of the library
+    _lib.LIB_PATH = os.path.abspath(os.environ["MTN_LIB"])
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--hparams", default="S"); ap.add_argument("--batch", type=int, default=32)
