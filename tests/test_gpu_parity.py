@@ -499,6 +499,24 @@ def test_full_size_config2_properties():
     assert err <= 1e-3 and d_sisnr <= 0.01, (err, d_sisnr, fid)
 
 
+def test_full_size_config3_properties():
+    """BASELINE config 3 (L hparams, 256 x 4 s @ 8 kHz, bf16 mode) at full size through size-independent properties:
+    finite output, silence in -> silence out, and batch independence -- utterance i of the batch of 256 equals the same
+    utterance run alone, bit for bit (8 192 scan CTAs in several waves, GEMM tiles straddling utterance boundaries)."""
+    hp = CONFIGS["L"]
+    sds = init_state_dicts(hp, 1234)
+    B, T = 256, 32000
+    mix, _ = synth_mixture(B, T, seed=4321)
+    mix[200] = 0.0
+    eng = SeparatorEngine(hp, sds, device=DEV, mode="bf16", use_graph=True)
+    est = eng(mix.to(DEV)).cpu()
+    assert est.shape == (B, T, 2) and torch.isfinite(est).all()
+    assert est[200].abs().max() == 0.0
+    for i in (0, 129, 255):
+        alone = eng(mix[i:i + 1].to(DEV)).cpu()
+        assert torch.equal(alone[0], est[i]), i
+
+
 # --------------------------------------------------------------------------- chunked / sequence-parallel pieces
 def test_conv_silu_halo_equals_slice_of_full_sequence():
     """A time chunk convolved with its neighbours' 3-frame halos == the same rows of the whole-utterance conv."""
