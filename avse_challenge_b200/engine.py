@@ -294,9 +294,10 @@ class SeparatorEngine(LayerPlan):
            tail=ss["ola_tail"])
         return est
 
-    def _run(self, ws: Workspace, taps=None):
+    def _run(self, ws: Workspace, taps=None, stream_state=None):
         if not self.fuse_norm or taps is not None or self.hp.mask_nonlinear != "relu" or not self.hp.rms_norm:
-            return self._run_unfused(ws, taps)
+            return self._run_unfused(ws, taps, stream_state)
+        ss = stream_state
         hp, w, P = self.hp, self.w, self.w.P
         N, D, di, M = hp.enc_dim, hp.d_model, hp.d_inner, ws.M
         op = self._op
@@ -309,14 +310,19 @@ class SeparatorEngine(LayerPlan):
         for i, lw in enumerate(w.layers):
             op("gemm_in_proj", ops.gemm, ws.xn, lw["w_in_g"], M, 2 * di, D, out=ws.xz, epilogue=_lib.EPI_INPROJ,
                epi_param=di, out_bf16=ws.xz.dtype == torch.bfloat16, rowsq=ws.rowsum[cur], **norm)
-            self._mixer_core(ws, lw)
+            self._mixer_core(ws, lw, None if ss is None else ss["layers"][i])
             op("gemm_out_proj", ops.gemm, ws.y, lw["w_out"], M, D, self.ndir * di, out=ws.res, epilogue=_lib.EPI_RESADD,
                epi_param=1, out2=ws.xn, rowsum=ws.rowsum[1 - cur])
             cur = 1 - cur
         op("gemm_mask", ops.gemm, ws.xn, w.w_mask_g, M, hp.n_spk * N, D, out=ws.sep, epilogue=_lib.EPI_MASK, epi_param=N,
            aux=ws.mix_w, rowsq=ws.rowsum[cur], **norm)
-        op("decoder", ops.decoder, ws.sep, w.w_dec, ws.batch, ws.T, ws.L, N, hp.n_spk, est=ws.est, frames=ws.frames)
-        return ws.est
+        if ss is None:
+            op("decoder", ops.decoder, ws.sep, w.w_dec, ws.batch, ws.T, ws.L, N, hp.n_spk, est=ws.est, frames=ws.frames)
+            return ws.est
+        est = ss["est"]   # streaming chunk, as in _run_unfused
+        op("decoder", ops.decoder, ws.sep, w.w_dec, ws.batch, 8 * ws.L, ws.L, N, hp.n_spk, est=est, frames=ws.frames,
+           tail=ss["ola_tail"])
+        return est
 
     def profile_ops(self, batch: int, T: int, steps: int = 1):
         """Eager (no graph) run with CUDA events around every kernel launch, on the launch stream.

@@ -30,8 +30,6 @@ class StreamingSeparator:
     def __init__(self, engine: SeparatorEngine, batch: int, use_graph: bool = True):
         if engine.hp.bidirectional:
             raise NotImplementedError("streaming needs a causal stack: construct the model with bidirectional=False")
-        if engine.fuse_norm:
-            raise NotImplementedError("StreamingSeparator drives the separate add_rmsnorm plan (fuse_norm=False)")
         self.eng, self.batch, self.use_graph = engine, batch, use_graph
         hp, dev = engine.hp, engine.device
         z = lambda *shape: torch.zeros(shape, dtype=torch.float32, device=dev)
@@ -59,7 +57,7 @@ class StreamingSeparator:
     def _run(self, ws, L):
         self.state["est"] = self._est.setdefault(
             L, torch.empty((self.batch, 8 * L, self.eng.hp.n_spk), dtype=torch.float32, device=self.eng.device))
-        return self.eng._run_unfused(ws, stream_state=self.state)
+        return self.eng._run(ws, stream_state=self.state)   # either plan (fuse_norm folds Add -> RMSNorm into the GEMMs)
 
     @torch.no_grad()
     def push(self, chunk: torch.Tensor) -> torch.Tensor:

@@ -52,6 +52,8 @@ def parse():
     ap.add_argument("--mode", default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--fuse-norm", action="store_true",
+                    help="plan with Add -> RMSNorm folded into the GEMM epilogues (one launch fewer per layer)")
     ap.add_argument("--model", default="mambatasnet", choices=["mambatasnet", "dpmamba"],
                     help="dpmamba: the dual-path recipes (hparams/WSJ0Mix/dpmamba_*.yaml), SURVEY 8f rank 1")
     ap.add_argument("--causal", action="store_true",
@@ -292,7 +294,7 @@ def run_b200_arm(a):
     if a.model == "dpmamba":
         eng = DPSeparatorEngine(dhp, sds, device=dev, mode=a.mode, use_graph=not a.no_graph)
     else:
-        eng = SeparatorEngine(hp, sds, device=dev, mode=a.mode, use_graph=not a.no_graph)
+        eng = SeparatorEngine(hp, sds, device=dev, mode=a.mode, use_graph=not a.no_graph, fuse_norm=a.fuse_norm)
     audio_s_per_step = a.batch * T / a.sample_rate
 
     cpu_base = None
@@ -517,7 +519,7 @@ def run_stream_arm(a):
     hp = CONFIGS[a.hparams].causal()
     n = max(16, int(round(a.chunk_ms * 1e-3 * a.sample_rate)) // 8 * 8)     # samples per push
     sds = init_state_dicts(hp, 1234)
-    eng = SeparatorEngine(hp, sds, device=dev, mode=a.mode, use_graph=False)
+    eng = SeparatorEngine(hp, sds, device=dev, mode=a.mode, use_graph=False, fuse_norm=a.fuse_norm)
     st = StreamingSeparator(eng, a.batch, use_graph=not a.no_graph)
     n_chunks = 64
     mix_cpu, _ = synth_mixture(min(a.batch, 8), n * n_chunks, a.sample_rate, seed=1234 + rank)
@@ -579,6 +581,7 @@ def run_stream_arm(a):
         cfg["workload"] = (f"streaming causal Mamba-TasNet {a.hparams} hparams (bidirectional=False), {a.batch} concurrent stream(s) "
                            f"per GPU, {n / a.sample_rate * 1e3:g} ms ({n // 8} frames) per push, {a.mode} mode, CUDA graph per chunk shape")
         cfg["chunk_samples"] = n
+        cfg["plan"] = "fuse_norm (Add -> RMSNorm folded into the GEMM epilogues)" if a.fuse_norm else "separate add_rmsnorm kernel"
         line = {
             "metric": METRIC, "value": audio_s * world / (step_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": a.steps,
             "warmup": max(3, a.warmup), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
@@ -588,7 +591,7 @@ def run_stream_arm(a):
             "latency_ms": {"chunk_audio_ms": n / a.sample_rate * 1e3, "device_ms_per_push": step_ms,
                            "host_observed_median_ms": statistics.median(lat), "host_observed_max_ms": max(lat),
                            "algorithmic_latency_ms": 16 / a.sample_rate * 1e3},
-            "gpu_launches": a.steps * (2 + hp.n_mamba * 6 + 2 + 2),
+            "gpu_launches": a.steps * eng.launches_per_forward,
             "roofline": {"kernel": "launch-latency bound (about 100 launches of a few-frame chunk per push)", "bound": "hbm",
                          "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "peak_source": peak_src, "traffic": None,
                          "note": "per-kernel roofline is reported on the cfg2 workload"},

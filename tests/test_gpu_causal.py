@@ -129,6 +129,22 @@ def test_streaming_equals_one_shot(chunk, use_graph):
     assert e2 <= 1e-3 and d2 <= 0.01
 
 
+@pytest.mark.parametrize("chunk", [16, 8 * 20, 8 * 333])
+def test_streaming_fused_norm_plan_equals_one_shot(chunk):
+    """The plan with Add -> RMSNorm folded into the GEMM epilogues (17 fewer launches per push) streams to the same
+    samples as the one-shot forward of the default plan."""
+    hp = CONFIGS["tiny"].causal()
+    sds = init_state_dicts(hp, 11)
+    B, T = 2, 8 * 1000 + 5
+    mix, _ = synth_mixture(B, T, seed=5)
+    one = SeparatorEngine(hp, sds, device=DEV, mode="fp32", use_graph=False)(mix.to(DEV)).cpu()
+    eng = SeparatorEngine(hp, sds, device=DEV, mode="fp32", use_graph=False, fuse_norm=True)
+    got = StreamingSeparator(eng, B, use_graph=True).separate(mix.to(DEV), chunk).cpu()
+    err = rel_max(got, one)
+    print(f"fused-norm streaming, chunk {chunk}: max-abs/rms vs one-shot {err:.3e}")
+    assert err <= 2e-4, err
+
+
 def test_streaming_single_frame_chunks_and_rejects():
     hp = CONFIGS["tiny"].causal()
     sds = init_state_dicts(hp, 12)
