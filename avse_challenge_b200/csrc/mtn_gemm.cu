@@ -459,6 +459,9 @@ static int dispatch_epi(const mtn_gemm_args* a, cudaStream_t s) {
         if (a->epilogue == MTN_EPI_XPROJ && !a->out_bf16) return launch_gemm<P, BN, MTN_EPI_XPROJ, false>(a, s);
     }
     if (BN == 64) {
+        // in_proj of a single-row-tile problem (streaming chunk): see dispatch_bn
+        if (a->epilogue == MTN_EPI_INPROJ && !a->out_bf16) return launch_gemm<P, BN, MTN_EPI_INPROJ, false>(a, s);
+        if (a->epilogue == MTN_EPI_INPROJ && a->out_bf16) return launch_gemm<P, BN, MTN_EPI_INPROJ, true>(a, s);
         if (a->epilogue == MTN_EPI_RESADD && !a->out_bf16) return launch_gemm<P, BN, MTN_EPI_RESADD, false>(a, s);
         // per-speaker grouped end_conv1x1 of DPMamba at enc_dim = 64 (unit-test sizes)
         if (a->epilogue == MTN_EPI_MASK && !a->out_bf16) return launch_gemm<P, BN, MTN_EPI_MASK, false>(a, s);
@@ -480,7 +483,16 @@ static int tile_n_for(int N) { return N % 256 == 0 ? 256 : N % 128 == 0 ? 128 : 
 template <int P>
 static int dispatch_bn(const mtn_gemm_args* a, cudaStream_t s) {
     const int N = a->N;
-    if (N % 256 == 0) return dispatch_epi<P, 256>(a, s);
+    // A single row tile (M <= 128: a streaming chunk of a few frames) is latency-bound: narrow N tiles put 4x as many
+    // CTAs on the problem and cut each CTA's weight load and epilogue by as much (B200, S hparams, one stream, 20 ms
+    // pushes: 0.733 ms with 256-wide tiles, 0.590 with 128, 0.574 with 64).  Same K order per output element, so the
+    // result is bit-identical.  (RESADD keeps its tile width: the row-sum plane count depends on it.)
+    const bool one_row_tile = a->M <= BM && a->epilogue != MTN_EPI_RESADD;
+    if (one_row_tile && N % 64 == 0 && N > 64 &&
+        (a->epilogue == MTN_EPI_STORE || a->epilogue == MTN_EPI_INPROJ || a->epilogue == MTN_EPI_MASK ||
+         a->epilogue == MTN_EPI_RELU))
+        return dispatch_epi<P, 64>(a, s);
+    if (N % 256 == 0 && !one_row_tile) return dispatch_epi<P, 256>(a, s);
     if (N % 128 == 0) return dispatch_epi<P, 128>(a, s);
     if (N == 64) return dispatch_epi<P, 64>(a, s);
     if (N == 48) return dispatch_epi<P, 48>(a, s);
