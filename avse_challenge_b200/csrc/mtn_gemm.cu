@@ -483,16 +483,21 @@ static int tile_n_for(int N) { return N % 256 == 0 ? 256 : N % 128 == 0 ? 128 : 
 template <int P>
 static int dispatch_bn(const mtn_gemm_args* a, cudaStream_t s) {
     const int N = a->N;
-    // A single row tile (M <= 128: a streaming chunk of a few frames) is latency-bound: narrow N tiles put 4x as many
-    // CTAs on the problem and cut each CTA's weight load and epilogue by as much (B200, S hparams, one stream, 20 ms
-    // pushes: 0.733 ms with 256-wide tiles, 0.590 with 128, 0.574 with 64).  Same K order per output element, so the
-    // result is bit-identical.  (RESADD keeps its tile width: the row-sum plane count depends on it.)
-    const bool one_row_tile = a->M <= BM && a->epilogue != MTN_EPI_RESADD;
-    if (one_row_tile && N % 64 == 0 && N > 64 &&
-        (a->epilogue == MTN_EPI_STORE || a->epilogue == MTN_EPI_INPROJ || a->epilogue == MTN_EPI_MASK ||
-         a->epilogue == MTN_EPI_RELU))
-        return dispatch_epi<P, 64>(a, s);
-    if (N % 256 == 0 && !one_row_tile) return dispatch_epi<P, 256>(a, s);
+    // Under-filled problems (fewer 256-wide tiles than SMs: streaming chunks, short utterances) are latency-bound, not
+    // throughput-bound: narrower N tiles put up to 4x as many CTAs on them and cut each CTA's weight load and epilogue
+    // by as much (B200, S hparams, one stream, 20 ms pushes = one row tile: 0.733 ms per push with 256-wide tiles, 0.590
+    // with 128, 0.574 with 64).  Same K order per output element, so the result is bit-identical.  (RESADD keeps its
+    // tile width: the row-sum plane count depends on it; XPROJ only exists for narrow N.)
+    const bool narrowable = a->epilogue == MTN_EPI_STORE || a->epilogue == MTN_EPI_INPROJ ||
+                            a->epilogue == MTN_EPI_MASK || a->epilogue == MTN_EPI_RELU;
+    const long row_tiles = long((a->M + BM - 1) / BM) * a->groups;
+    const long cap = a->max_ctas > 0 ? a->max_ctas : num_sms();
+    if (narrowable && N > 64) {
+        if (N % 256 == 0 && row_tiles * (N / 256) >= cap) return dispatch_epi<P, 256>(a, s);
+        if (N % 128 == 0 && row_tiles * (N / 128) >= cap) return dispatch_epi<P, 128>(a, s);
+        if (N % 64 == 0) return dispatch_epi<P, 64>(a, s);
+    }
+    if (N % 256 == 0) return dispatch_epi<P, 256>(a, s);
     if (N % 128 == 0) return dispatch_epi<P, 128>(a, s);
     if (N == 64) return dispatch_epi<P, 64>(a, s);
     if (N == 48) return dispatch_epi<P, 48>(a, s);

@@ -423,7 +423,8 @@ def run_longform_arm(a):
     mix_cpu, _ = synth_mixture(1, min(T, 30 * a.sample_rate), a.sample_rate, seed=1234)
     reps = -(-T // mix_cpu.shape[1])
     mix_cpu = mix_cpu.repeat(1, reps)[:, :T].contiguous()            # 30 s of synthetic speech tiled to length
-    sp = SequenceParallelSeparator(hp, sds, device=dev, mode=a.mode, sub_chunks=a.sub_chunks, exchange=a.exchange)
+    sp = SequenceParallelSeparator(hp, sds, device=dev, mode=a.mode, sub_chunks=a.sub_chunks, exchange=a.exchange,
+                                   use_graph=not a.no_graph)   # graph replay on a single rank only (no collective then)
     cpu_base = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         cpu_base, _ = cpu_reference_throughput(a.hparams, a.sample_rate, steps=1, warmup=0, budget_s=30.0, causal=a.causal, model=a.model)

@@ -597,6 +597,26 @@ def test_sequence_parallel_driver_single_gpu(name, T, sub):
     assert err <= 1e-3 and d_sisnr <= 0.01, (err, d_sisnr, fid)
 
 
+def test_single_rank_chunked_plan_graph_replay_is_the_low_latency_path():
+    """One utterance through the chunked-scan plan on a single rank (`SequenceParallelSeparator`, world 1): the forward is
+    captured as one CUDA graph per length; replays with NEW inputs must match the batch plan (same kernels, chunk carries
+    folded in fp32) and an eager run of the same plan bit for bit."""
+    from avse_challenge_b200.parallel import SequenceParallelSeparator
+    hp = CONFIGS["XS"]
+    sds = init_state_dicts(hp, 3)
+    eng = SeparatorEngine(hp, sds, device=DEV, mode="fp32", use_graph=False)
+    sp_g = SequenceParallelSeparator(hp, sds, device=DEV, mode="fp32", sub_chunks=8, use_graph=True)
+    sp_e = SequenceParallelSeparator(hp, sds, device=DEV, mode="fp32", sub_chunks=8, use_graph=False)
+    for seed in (1, 2, 3):   # the first call captures, the next two replay with different samples
+        mix, _ = synth_mixture(1, 8000 + 5, seed=seed)
+        ref = eng(mix.to(DEV)).cpu()
+        got = sp_g(mix.to(DEV)).cpu()
+        assert got.shape == ref.shape
+        assert (got - ref).abs().max() <= 1e-4 * ref.pow(2).mean().sqrt()
+        assert torch.equal(got, sp_e(mix.to(DEV)).cpu())
+    assert len(sp_g._graphs) == 1
+
+
 # --------------------------------------------------------------------------- evaluation front end (SURVEY 8f rank 3)
 @pytest.mark.parametrize("B,T", [(3, 4001), (1, 16), (2, 70001), (5, 32768)])
 def test_si_snr_pit_matches_oracle(B, T, golden_dir):
