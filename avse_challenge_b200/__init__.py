@@ -22,4 +22,10 @@ def __getattr__(name):
     if name == "SeparatorEngine":
         from .engine import SeparatorEngine
         return SeparatorEngine
+    if name in ("ShardedSeparator", "SequenceParallelSeparator"):
+        from . import parallel
+        return getattr(parallel, name)
+    if name == "StreamingSeparator":
+        from .streaming import StreamingSeparator
+        return StreamingSeparator
     raise AttributeError(name)
