@@ -395,6 +395,22 @@ class MambaTasNetSeparator(_EngineOwner):
     def forward(self, mix):
         return self.engine().forward(mix)
 
+    def chunked(self, sub_chunks: int = 16):
+        """The chunked-scan plan over this module's weights (``parallel.SequenceParallelSeparator``): ``[1, T] ->
+        [1, T, n_spk]``.  One utterance at minimum latency on one GPU (the whole forward is one CUDA graph; the scan's
+        serial chain is ``sub_chunks`` times shorter than in the batch plan), or one long recording sharded over the
+        ranks of the default process group.  Bidirectional stacks only."""
+        from .parallel import SequenceParallelSeparator
+        cache = self.__dict__.setdefault("_engine_cache", {})
+        key = ("chunked", sub_chunks)
+        if key not in cache:
+            dev = self.masknet.layer_norm.gamma.device
+            sds = {"encoder": self.encoder.state_dict(), "masknet": self.masknet.state_dict(),
+                   "decoder": self.decoder.state_dict()}
+            cache[key] = SequenceParallelSeparator(self.masknet.hp, sds, device=dev, mode=self.mode,
+                                                   sub_chunks=sub_chunks, use_graph=self.use_graph)
+        return cache[key]
+
 
 # ---------------------------------------------------------------------------------------------------- DPMamba
 class Dual_Computation_Block(nn.Module):

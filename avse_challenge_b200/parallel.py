@@ -266,6 +266,9 @@ class SequenceParallelSeparator:
                  exchange: str = "allgather", group=None, backend=None, use_graph: bool = True):
         if exchange not in ("allgather", "sendrecv"):
             raise ValueError("exchange must be 'allgather' or 'sendrecv'")
+        if not hp.bidirectional:
+            raise NotImplementedError("the chunked-scan plan is built for the bidirectional stack; a causal model "
+                                      "streams through StreamingSeparator instead")
         self.hp, self.sub_chunks, self.exchange = hp, sub_chunks, exchange
         self.comm = Comm(group)
         self.be = backend if backend is not None else CudaSeqBackend(hp, sds, device, mode)

@@ -615,6 +615,10 @@ def test_single_rank_chunked_plan_graph_replay_is_the_low_latency_path():
         assert (got - ref).abs().max() <= 1e-4 * ref.pow(2).mean().sqrt()
         assert torch.equal(got, sp_e(mix.to(DEV)).cpu())
     assert len(sp_g._graphs) == 1
+    # the same plan from the drop-in module
+    from avse_challenge_b200 import MambaTasNetSeparator
+    sep = MambaTasNetSeparator.from_hparams(hp).load_reference_state_dicts(sds).to(DEV)
+    assert torch.equal(sep.chunked(8)(mix.to(DEV)).cpu(), got)
 
 
 # --------------------------------------------------------------------------- evaluation front end
