@@ -262,7 +262,10 @@ class SequenceParallelSeparator:
     ``exchange``: ``"allgather"`` (default: one all-gather of the chunk summaries per layer) or ``"sendrecv"``
     (the folded state is handed down the rank chain with point-to-point send/recv; same numbers)."""
 
-    def __init__(self, hp: HParams, sds: Optional[dict] = None, device="cuda", mode: str = "fp32", sub_chunks: int = 64,
+    # sub_chunks = 74: every chunk is 2 * d_inner / 32 independent warp pairs for the scan (32 for S / M, 64 for L) and a
+    # B200 holds 148 SMs x 8 pairs = 1 184 of them, so 74 chunks are exactly 2 (S) or 4 (L) full waves; 64 chunks left the
+    # second wave 73 % full (config 5 on one GPU: 361 ms at 64, 341 ms at 74, 340 ms at 128-256; DESIGN.md 6)
+    def __init__(self, hp: HParams, sds: Optional[dict] = None, device="cuda", mode: str = "fp32", sub_chunks: int = 74,
                  exchange: str = "allgather", group=None, backend=None, use_graph: bool = True):
         if exchange not in ("allgather", "sendrecv"):
             raise ValueError("exchange must be 'allgather' or 'sendrecv'")

@@ -64,7 +64,8 @@ def parse():
                          "256 x 4 s sharded over the GPUs, bf16 mode, strong scaling.  longform: one 10-minute 16 kHz "
                          "recording, sequence-parallel over the GPUs (S fp32 unless --hparams/--mode given), strong "
                          "scaling.  custom: take --hparams/--batch/--seconds/--sample-rate/--mode as given.")
-    ap.add_argument("--sub-chunks", type=int, default=64, help="longform: time sub-chunks per GPU")
+    ap.add_argument("--sub-chunks", type=int, default=74,
+                    help="longform: time sub-chunks per GPU (74 x 32 warp pairs = two full waves of a 148-SM GPU for S hparams)")
     ap.add_argument("--exchange", default="allgather", choices=["allgather", "sendrecv"])
     a = ap.parse_args()
     explicit = {x.split("=")[0] for x in sys.argv[1:] if x.startswith("--")}
