@@ -83,7 +83,8 @@ def test_shard_slices_cover_and_balance():
             assert max(sizes) - min(sizes) <= 1
 
 
-@pytest.mark.parametrize("L,world,sub", [(101, 2, 3), (3999, 8, 64), (1199999, 8, 64), (24, 8, 4), (50, 1, 7)])
+@pytest.mark.parametrize("L,world,sub", [(101, 2, 3), (3999, 8, 64), (1199999, 8, 64), (24, 8, 4), (50, 1, 7),
+                                         (1199999, 8, 74), (1199999, 1, 74), (3999, 1, 16)])
 def test_seq_plan_is_a_partition(L, world, sub):
     plan = make_seq_plan(L, world, sub)
     assert plan.ranges[0][0] == 0 and plan.ranges[-1][1] == L
@@ -156,3 +157,26 @@ def test_sequence_parallel_single_rank_many_chunks():
         ref = restate.separate(mix, sds, hp.n_mamba, scan_impl="c")
     est = SequenceParallelSeparator(hp, sub_chunks=7, backend=OracleSeqBackend(hp, sds))(mix)
     assert rel_max(est, ref) < 2e-5
+
+
+def test_sequence_parallel_defaults_and_rejections():
+    """Host logic of the driver: default sub-chunk count (whole waves of a 148-SM GPU), the default plan on the
+    oracle backend (no graph without the CUDA backend), causal stacks and bad arguments rejected at construction."""
+    import inspect
+    import avse_challenge_b200 as mtn
+    assert mtn.SequenceParallelSeparator is SequenceParallelSeparator and mtn.ShardedSeparator is ShardedSeparator
+    assert inspect.signature(SequenceParallelSeparator.__init__).parameters["sub_chunks"].default == 74
+    hp = CONFIGS["tiny"]
+    sds = init_state_dicts(hp, 1234)
+    sp = SequenceParallelSeparator(hp, backend=OracleSeqBackend(hp, sds))
+    assert sp.sub_chunks == 74 and sp.use_graph is False
+    mix, _ = synth_mixture(1, 1600, seed=9)          # 199 frames -> 74 chunks of 3 frames (the conv halo's minimum)
+    with torch.no_grad():
+        ref = restate.separate(mix, sds, hp.n_mamba, scan_impl="c")
+    assert rel_max(sp(mix), ref) < 2e-5
+    with pytest.raises(NotImplementedError):
+        SequenceParallelSeparator(hp.causal(), backend=OracleSeqBackend(hp, sds))
+    with pytest.raises(ValueError):
+        SequenceParallelSeparator(hp, exchange="ring", backend=OracleSeqBackend(hp, sds))
+    with pytest.raises(ValueError):
+        sp(torch.zeros(2, 1600))
