@@ -13,12 +13,17 @@ LIB_PATH = os.path.join(_HERE, "libmtn_b200.so")
 
 EPI_STORE, EPI_INPROJ, EPI_MASK, EPI_RELU, EPI_XPROJ, EPI_RESADD = 0, 1, 2, 3, 4, 5
 
+# ABI the ctypes structs below were written for (include/mtn_b200.h: MTN_ABI_VERSION).  A stale or experiment-only build of
+# the library (it is git-ignored and rebuilt on mtimes) must not be handed structs of another layout.
+EXPECTED_ABI = 6
+
 EXPORTS = [
     "mtn_encoder_cln_fwd", "mtn_gemm_fwd", "mtn_gemm_rowsum_parts", "mtn_add_rmsnorm_fwd", "mtn_add_rmsnorm_out_fwd", "mtn_add_norm_fwd", "mtn_conv_silu_fwd", "mtn_conv_silu_halo_fwd", "mtn_conv_silu_dir_fwd", "mtn_decoder_stream_fwd",
     "mtn_scan_fwd", "mtn_fold_states_fwd",
     "mtn_gn_partials_bytes", "mtn_gn_stats_fwd", "mtn_gn_apply_fwd", "mtn_gn_apply_norm_fwd", "mtn_dp_num_chunks", "mtn_dp_segment_fwd",
     "mtn_dp_overadd_prelu_fwd", "mtn_bias_planes_fwd", "mtn_gate_planes_fwd",
     "mtn_decoder_fwd", "mtn_cln_fwd", "mtn_softmax_mask_fwd", "mtn_split_planes", "mtn_si_snr_pit_fwd", "mtn_si_snr_workspace_bytes", "mtn_last_error_string", "mtn_abi_version",
+    "mtn_sizeof_gemm_args", "mtn_sizeof_scan_args", "mtn_sizeof_gn_apply_args",
 ]
 
 
@@ -73,6 +78,12 @@ def load():
     lib.mtn_last_error_string.restype = c_char_p
     lib.mtn_last_error_string.argtypes = []
     lib.mtn_abi_version.restype = c_int
+    lib.mtn_abi_version.argtypes = []
+    abi = int(lib.mtn_abi_version())
+    if abi != EXPECTED_ABI:
+        raise MtnError(f"{LIB_PATH} reports ABI {abi}, this binding was written for ABI {EXPECTED_ABI}: rebuild it with "
+                       "`python -m avse_challenge_b200.build --force` (dev / experiment builds carry ABI + 1000 and load "
+                       "only through tools/ with MTN_LIB set)")
     lib.mtn_encoder_cln_fwd.argtypes = [c_void_p, c_int] + [c_void_p] * 5 + [c_int] * 5 + [c_float, c_void_p]
     lib.mtn_gemm_fwd.argtypes = [POINTER(GemmArgs), c_void_p]
     lib.mtn_gemm_rowsum_parts.argtypes = [c_int]
@@ -107,10 +118,18 @@ def load():
                                              c_void_p]
     lib.mtn_bias_planes_fwd.argtypes = [c_void_p, c_int, c_void_p, c_float, c_void_p, c_int, c_int, c_int, c_int, c_void_p]
     lib.mtn_gate_planes_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]
+    for name, st in (("mtn_sizeof_gemm_args", GemmArgs), ("mtn_sizeof_scan_args", ScanArgs),
+                     ("mtn_sizeof_gn_apply_args", GnApplyArgs)):
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = c_size_t, []
+        if int(fn()) != ctypes.sizeof(st):
+            raise MtnError(f"{name}() = {int(fn())} but ctypes.sizeof({st.__name__}) = {ctypes.sizeof(st)}: the binding "
+                           "and include/mtn_b200.h disagree about the struct layout")
     for name in EXPORTS:
         fn = getattr(lib, name, None)
         if fn is not None and name not in ("mtn_last_error_string", "mtn_abi_version", "mtn_si_snr_workspace_bytes",
-                                           "mtn_gn_partials_bytes"):
+                                           "mtn_gn_partials_bytes", "mtn_sizeof_gemm_args", "mtn_sizeof_scan_args",
+                                           "mtn_sizeof_gn_apply_args"):
             fn.restype = c_int
     lib.mtn_si_snr_workspace_bytes.restype = c_size_t
     lib.mtn_gn_partials_bytes.restype = c_size_t

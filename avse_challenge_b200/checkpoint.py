@@ -20,7 +20,7 @@ from typing import Dict, Optional
 
 import torch
 
-from .hparams import HParams
+from .hparams import DPHParams, HParams
 
 _SCALAR = re.compile(r"^([A-Za-z_][A-Za-z0-9_]*):\s*(.*?)\s*$")
 _REF = re.compile(r"<([A-Za-z_][A-Za-z0-9_]*)>")
@@ -102,33 +102,92 @@ def read_yaml_scalars(path: str) -> Dict[str, object]:
 def _masknet_class(path: str) -> Optional[str]:
     with open(path) as f:
         for line in f:
-            m = re.match(r"^MaskNet:\s*!new:(\S+)", line)
+            m = re.match(r"^MaskNet:\s*(?:&\S+\s+)?!new:(\S+)", line)   # the saved copy carries yaml anchors (&id006)
             if m:
                 return m.group(1)
     return None
 
 
-def read_hparams_yaml(path: str, name: Optional[str] = None) -> HParams:
-    """``HParams`` of a Mamba-TasNet recipe yaml (``hparams/WSJ0Mix/mambatasnet_*.yaml`` or the ``hyperparams.yaml``
-    copy speechbrain stores next to the checkpoints)."""
+def read_object_block(path: str, key: str, scalars: Optional[Dict[str, object]] = None) -> Dict[str, object]:
+    """The ``name: value`` lines nested under a top-level ``key: !new:Class`` entry (constructor keyword arguments, e.g.
+    ``MaskNet: ... mask_nonlinear: softmax``); ``!ref <x>`` values are looked up in ``scalars``, references to other
+    objects (``intra_model: !ref <Mambaintra>``) are returned as the referenced key's name."""
+    scalars = scalars or {}
+    out: Dict[str, object] = {}
+    inside = False
+    with open(path) as f:
+        for line in f:
+            if not inside:
+                inside = re.match(rf"^{re.escape(key)}:\s*(?:&\S+\s+)?!new:", line) is not None
+                continue
+            if line.strip() == "" or line.lstrip().startswith("#"):
+                continue
+            if line[0] not in " \t":
+                break                                   # next top-level entry
+            m = _SCALAR.match(line.strip())
+            if not m:
+                continue
+            val = _strip_comment(m.group(2))
+            if val.startswith("!ref"):
+                names = _REF.findall(val)
+                expr = val[4:].strip()
+                if len(names) == 1 and expr == f"<{names[0]}>":
+                    out[m.group(1)] = scalars.get(names[0], names[0])
+                elif all(n in scalars for n in names):
+                    for n in names:
+                        expr = expr.replace(f"<{n}>", repr(scalars[n]))
+                    if re.fullmatch(r"[0-9eE\.\s\+\-\*/\(\)]*", expr):
+                        out[m.group(1)] = eval(expr, {"__builtins__": {}})   # digits and arithmetic only
+            elif val != "":
+                out[m.group(1)] = _parse_value(val)
+    return out
+
+
+MASKNET_TASNET = ("modules.mamba_masknet.MaskNet",)
+MASKNET_DP = ("speechbrain.lobes.models.dual_path.Dual_Path_Model", "modules.dual_path.Dual_Path_Model_Skip")
+
+
+def read_hparams_yaml(path: str, name: Optional[str] = None):
+    """``HParams`` of a Mamba-TasNet recipe yaml (``hparams/WSJ0Mix/mambatasnet_*.yaml:108-155``) or ``DPHParams`` of a
+    DPMamba one (``hparams/WSJ0Mix/dpmamba_*.yaml:108-174``: ``MaskNet: !new:...Dual_Path_Model`` over two
+    ``MambaBlocksSequential``), also from the ``hyperparams.yaml`` copy speechbrain stores next to the checkpoints.
+    Everything the engines implement is accepted (``rms_norm: False``, ``mask_nonlinear: softmax``, ``num_spks: 3``,
+    ``bidirectional: False``, ``fused_add_norm: True`` -- the latter only picks between two identical reference code paths,
+    ``modules/mamba_blocks.py:195-210``); what they do not implement raises ``NotImplementedError``."""
     cls = _masknet_class(path)
-    if cls is not None and cls != "modules.mamba_masknet.MaskNet":
-        raise NotImplementedError(f"{path}: MaskNet is {cls}; only modules.mamba_masknet.MaskNet (Mamba-TasNet) is built")
+    if cls is not None and cls not in MASKNET_TASNET + MASKNET_DP:
+        raise NotImplementedError(f"{path}: MaskNet is {cls}; built: {MASKNET_TASNET + MASKNET_DP}")
     y = read_yaml_scalars(path)
-    need = ["N_encoder_out", "out_channels", "kernel_size", "n_mamba"]
+    dp = cls in MASKNET_DP
+    need = ["N_encoder_out", "out_channels", "kernel_size"] + (["n_dp", "chunk_size"] if dp else ["n_mamba"])
     missing = [k for k in need if k not in y]
     if missing:
         raise KeyError(f"{path}: missing {missing}")
-    if y.get("fused_add_norm", False) or not y.get("rms_norm", True):
-        raise NotImplementedError("only fused_add_norm: False / rms_norm: True (all shipped recipes) is built")
     stride = y.get("kernel_stride", y["kernel_size"] // 2)
     if stride != y["kernel_size"] // 2:
         raise NotImplementedError(f"kernel_stride {stride} != kernel_size // 2")
-    return HParams(name or os.path.splitext(os.path.basename(path))[0], int(y["N_encoder_out"]), int(y["out_channels"]),
-                   int(y["n_mamba"]), kernel_size=int(y["kernel_size"]), d_state=int(y.get("ssm_dim", 16)),
-                   expand=int(y.get("mamba_expand", 2)), d_conv=int(y.get("mamba_conv", 4)),
-                   n_spk=int(y.get("num_spks", 2)), sample_rate=int(y.get("sample_rate", 8000)),
-                   bidirectional=bool(y.get("bidirectional", True)))
+    blk = read_object_block(path, "MaskNet", y) if cls is not None else {}
+    nm = name or os.path.splitext(os.path.basename(path))[0]
+    common = dict(kernel_size=int(y["kernel_size"]), d_state=int(y.get("ssm_dim", 16)), expand=int(y.get("mamba_expand", 2)),
+                  d_conv=int(y.get("mamba_conv", 4)), n_spk=int(blk.get("num_spks", blk.get("n_spk", y.get("num_spks", 2)))),
+                  sample_rate=int(y.get("sample_rate", 8000)))
+    if not dp:
+        return HParams(nm, int(y["N_encoder_out"]), int(y["out_channels"]), int(y["n_mamba"]),
+                       mask_nonlinear=str(blk.get("mask_nonlinear", "relu")), rms_norm=bool(y.get("rms_norm", True)),
+                       bidirectional=bool(y.get("bidirectional", True)), **common)
+    # speechbrain Dual_Path_Model defaults: norm="ln", linear_layer_after_inter_intra=True, use_global_pos_enc=False
+    if str(blk.get("norm", "ln")) != "ln" or bool(blk.get("linear_layer_after_inter_intra", True)) or \
+            bool(blk.get("use_global_pos_enc", False)):
+        raise NotImplementedError(f"{path}: Dual_Path_Model with norm != ln / linear_layer_after_inter_intra / "
+                                  "use_global_pos_enc is not built")
+    if not y.get("bidirectional", True) or not y.get("rms_norm", True):
+        raise NotImplementedError(f"{path}: the dual-path stacks are built bidirectional with RMSNorm (every shipped recipe)")
+    n_mamba_dp = int(y.get("n_mamba_dp", 2))
+    if n_mamba_dp < 2 or n_mamba_dp % 2:
+        raise NotImplementedError(f"{path}: n_mamba_dp = {n_mamba_dp} (intra and inter stacks take n_mamba_dp // 2 layers each)")
+    return DPHParams(nm, int(y["N_encoder_out"]), int(y["out_channels"]), int(y["n_dp"]), bool(y.get("skip_around_intra", True)),
+                     chunk_size=int(y["chunk_size"]), n_mamba_dp=n_mamba_dp,
+                     skip_n_block=int(y.get("skip_n_block", 0)) if cls == MASKNET_DP[1] else 0, **common)
 
 
 def find_checkpoint_dir(save_folder: str) -> str:
@@ -158,10 +217,11 @@ def save_checkpoint_dir(sds: Dict[str, dict], ckpt_dir: str) -> str:
 
 def separator_from_checkpoint(hparams_yaml: str, ckpt_dir: str, mode: str = "fp32", use_graph: bool = True,
                               device="cuda"):
-    """The reference's ``inference.ipynb`` cells 0-1 in one call: yaml + CKPT dir -> ``MambaTasNetSeparator`` with the
-    weights loaded (``strict=True``) on ``device``."""
-    from .modules import MambaTasNetSeparator
+    """The reference's ``inference.ipynb`` cells 0-1 in one call: yaml + CKPT dir -> ``MambaTasNetSeparator`` (or
+    ``DPMambaSeparator`` for a dpmamba recipe) with the weights loaded (``strict=True``) on ``device``."""
+    from .modules import DPMambaSeparator, MambaTasNetSeparator
     hp = read_hparams_yaml(hparams_yaml)
-    sep = MambaTasNetSeparator.from_hparams(hp, mode=mode, use_graph=use_graph)
+    cls = DPMambaSeparator if isinstance(hp, DPHParams) else MambaTasNetSeparator
+    sep = cls.from_hparams(hp, mode=mode, use_graph=use_graph)
     sep.load_reference_state_dicts(load_checkpoint_dir(ckpt_dir), strict=True)
     return sep.to(device)

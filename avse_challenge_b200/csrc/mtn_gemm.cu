@@ -435,15 +435,8 @@ static int launch_gemm(const mtn_gemm_args* a, cudaStream_t stream) {
     p.tiles_m = (a->M + BM - 1) / BM;
     p.tiles_n = a->N / BN;
     auto kern = gemm_tcgen05_kernel<P, BN, EPI, OUT_BF16>;
-    static bool attr_set = false;  // per template instantiation
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-        if (e != cudaSuccess) {
-            set_error("gemm: cudaFuncSetAttribute(%d B smem) failed: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
-            return MTN_ECUDA;
-        }
-        attr_set = true;
-    }
+    static std::atomic<unsigned long long> attr_done{0};   // per template instantiation, one bit per device
+    if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(kern), Cfg::SMEM_BYTES, attr_done, "gemm")) return rc;
     int total = p.tiles_m * p.tiles_n * p.groups;
     int cap = a->max_ctas > 0 ? a->max_ctas : num_sms();
     int grid = total < cap ? total : cap;

@@ -26,6 +26,21 @@ int num_sms() {
     return cached[dev];
 }
 
+int ensure_dyn_smem(const void* kern, int bytes, std::atomic<unsigned long long>& done_mask, const char* what) {
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = -1;
+    const bool tracked = dev >= 0 && dev < 64;
+    if (tracked && ((done_mask.load(std::memory_order_acquire) >> dev) & 1ull)) return MTN_OK;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) {
+        set_error("%s: cudaFuncSetAttribute(%d B dynamic smem) failed on device %d: %s", what, bytes, dev,
+                  cudaGetErrorString(e));
+        return MTN_ECUDA;
+    }
+    if (tracked) done_mask.fetch_or(1ull << dev, std::memory_order_release);
+    return MTN_OK;
+}
+
 typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -73,4 +88,11 @@ bool encode_tmap(CUtensorMap* map, CUtensorMapDataType dtype, int rank, const vo
 }  // namespace mtn
 
 extern "C" const char* mtn_last_error_string(void) { return mtn::g_err; }
-extern "C" int mtn_abi_version(void) { return 5; }
+#ifdef MTN_SCAN_DEV
+extern "C" int mtn_abi_version(void) { return MTN_ABI_VERSION + 1000; }   // tools/devbuild.sh experiment build
+#else
+extern "C" int mtn_abi_version(void) { return MTN_ABI_VERSION; }
+#endif
+extern "C" size_t mtn_sizeof_gemm_args(void) { return sizeof(mtn_gemm_args); }
+extern "C" size_t mtn_sizeof_scan_args(void) { return sizeof(mtn_scan_args); }
+extern "C" size_t mtn_sizeof_gn_apply_args(void) { return sizeof(mtn_gn_apply_args); }

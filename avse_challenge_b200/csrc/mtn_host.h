@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <atomic>
 #include "../../include/mtn_b200.h"
 
 namespace mtn {
@@ -15,6 +16,11 @@ int num_sms();
 // dims/strides innermost first; strides in BYTES for dims 1..rank-1.
 bool encode_tmap(CUtensorMap* map, CUtensorMapDataType dtype, int rank, const void* base, const uint64_t* dims,
                  const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swizzle);
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) applies to one (function, DEVICE) pair, so the "already set"
+// cache is a per-call-site bit mask over device ordinals (atomic: the C ABI is re-entrant).  Devices >= 64 are
+// simply set on every launch.
+int ensure_dyn_smem(const void* kern, int bytes, std::atomic<unsigned long long>& done_mask, const char* what);
 
 #define MTN_REQUIRE(cond, ...)           \
     do {                                 \

@@ -551,15 +551,8 @@ static int launch_scan(const mtn_scan_args* a, cudaStream_t stream) {
     ScanParams p = make_scan_params(a);
     const int ndirs = p.ndirs;
     auto kern = scan_kernel<P, R, NDBL, ZT, CH, KP, WY>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL);
-        if (e != cudaSuccess) {
-            set_error("scan: cudaFuncSetAttribute(%d B smem) failed: %s", SM::TOTAL, cudaGetErrorString(e));
-            return MTN_ECUDA;
-        }
-        attr_set = true;
-    }
+    static std::atomic<unsigned long long> attr_done{0};   // per template instantiation, one bit per device
+    if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(kern), SM::TOTAL, attr_done, "scan")) return rc;
     dim3 grid(ndirs * (a->di / CH), a->batch, 1);
     kern<<<grid, CH * 2, SM::TOTAL, stream>>>(mapU, mapZ, mapD, p);
     MTN_CUDA_LAUNCH_CHECK("scan");
@@ -1029,15 +1022,8 @@ static int launch_scan_tc(const mtn_scan_args* a, cudaStream_t stream) {
     ScanParams p = make_scan_params(a);
     const int ndirs = p.ndirs;
     auto kern = scan_kernel_tc<P, R, NDBL, ZT, WY>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL);
-        if (e != cudaSuccess) {
-            set_error("scan(tc): cudaFuncSetAttribute(%d B smem) failed: %s", SM::TOTAL, cudaGetErrorString(e));
-            return MTN_ECUDA;
-        }
-        attr_set = true;
-    }
+    static std::atomic<unsigned long long> attr_done{0};   // per template instantiation, one bit per device
+    if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(kern), SM::TOTAL, attr_done, "scan(tc)")) return rc;
     dim3 grid(ndirs * (a->di / SC_CH), a->batch, 1);
     kern<<<grid, 256, SM::TOTAL, stream>>>(mapU, mapZ, mapD, mapT, p);
     MTN_CUDA_LAUNCH_CHECK("scan(tc)");
@@ -1068,6 +1054,23 @@ static int dispatch_scan_variant(const mtn_scan_args* a, cudaStream_t s) {
     if (variant == 7 && a->dtp && a->y) return launch_scan_pair<P, R, NDBL, ZT, true, true>(a, s);  // tensor-core dt_proj
     if (variant == 9 && a->y) return launch_scan_trio<P, R, NDBL, ZT>(a, s);   // recurrence / prep / post warp trios
 #endif
+    // v2 helper (mma.sync dt_proj, packed softplus, row-segment gate): 6; 61 / 62 (dev builds) add 1 / 2 state pairs per
+    // step on the FMA-pipe polynomial exp2
+#ifdef MTN_SCAN_DEV   // timing-only ablations of the v2 kernel (WRONG results)
+    if (variant == 63 && a->y) return launch_scan_pair2<P, R, NDBL, ZT, true, 0, false, 3>(a, s);   // helper: no dt_proj/softplus/gate
+    if (variant == 64 && a->y) return launch_scan_pair2<P, R, NDBL, ZT, true, 0, false, 4>(a, s);   // recurrence: no MUFU
+    if (variant == 67 && a->y) return launch_scan_pair2<P, R, NDBL, ZT, true, 0, false, 7>(a, s);   // both
+    if (variant == 66 && a->y) return launch_scan_pair2<P, R, NDBL, ZT, true, 0, false, 1>(a, s);   // helper: no dt_proj/softplus
+    if (variant == 65 && a->y) return launch_scan_pair2<P, R, NDBL, ZT, true, 0, false, 2>(a, s);   // helper: no gate
+#endif
+    if (variant == 6 || variant == 61 || variant == 62) {
+        if (!a->y) return launch_scan_pair2<P, R, NDBL, ZT, false>(a, s);
+#ifdef MTN_SCAN_DEV
+        if (variant == 61) return launch_scan_pair2<P, R, NDBL, ZT, true, 1>(a, s);
+        if (variant == 62) return launch_scan_pair2<P, R, NDBL, ZT, true, 2>(a, s);
+#endif
+        return launch_scan_pair2<P, R, NDBL, ZT, true>(a, s);
+    }
     // Recurrence / helper warp pairs (mtn_scan_pair.cuh).  Measured on B200 (tools/scan_bench.py): faster
     // than the split mapping for full passes; the summary pass (no y: nothing for the helper to take over) stays on the
     // split mapping.  variant 5 forces it, variant 2/3 force the split mapping.

@@ -58,7 +58,10 @@ __device__ __forceinline__ void sts_f32_nofence(void* p, float v) {
 // One instruction stream serves both directions (with one per direction and role, the four unrolled tile bodies, 80 KB,
 // thrashed the instruction cache: 25 % of the warp samples were stall_no_inst): the slot row pointer and the [B | C] row
 // pointer step by signed strides, everything else has immediate offsets.
-template <int S, int NB, int BOFF, bool WY, int ABL, bool RG = false>
+// DS = slot row stride in floats (32: v1 helper, lane = channel; 36: v2 helper, whose 16-byte row-segment accesses need an
+// odd multiple of 16 bytes to stay bank-conflict free).  KP = state pairs per step whose decay factor is computed by the
+// FMA-pipe polynomial ex2_poly2 instead of MUFU.EX2 (balances the XU against the FMA pipe once the helper is light).
+template <int S, int NB, int BOFF, bool WY, int ABL, bool RG = false, int DS = 32, int KP = 0>
 __device__ __forceinline__ void scan_pair_recur(const uint8_t* ring, float* slots, int stage_bytes, int u_bytes,
                                                 uint64_t* full_bar, uint64_t* empty_bar, uint64_t* prepped,
                                                 uint64_t* ydone, const ScanParams& p, int w, int lane, int d, int b,
@@ -90,15 +93,34 @@ __device__ __forceinline__ void scan_pair_recur(const uint8_t* ring, float* slot
     const float Dv = p.Dskip[pd];
     const int bc_first = dir ? (SC_TT - 1) * NB : 0;   // floats
     const int bc_step = dir ? -NB : NB;
-    const int sl_first = dir ? (SC_TT - 1) * 32 : 0;
-    const int sl_step = dir ? -32 : 32;
+    const int sl_first = dir ? (SC_TT - 1) * DS : 0;
+    const int sl_step = dir ? -DS : DS;
+    constexpr int UOFF = SC_TT * DS;            // u plane of the pair's slot, floats after the delta -> y plane
+    constexpr int PAIRF = 2 * SC_TT * DS;       // floats per pair slot
+    // polynomial exp2 needs delta * A2 >= -126 for its KP pairs: clamp delta for those pairs only (2^-126 ~ 0 either way)
+    float dl_cap = 3.0e38f;
+    if (KP > 0) {
+        float amin = 0.f;
+#pragma unroll
+        for (int q = 0; q < KP; ++q) amin = fminf(amin, fminf(A2[q].x, A2[q].y));
+        dl_cap = amin < 0.f ? -126.f / amin : 3.0e38f;
+    }
+    auto decay = [&](float dl, int q) -> float2 {
+        if (q < KP) {
+            const float dc = fminf(dl, dl_cap);
+            return ex2_poly2(make_float2(dc, dc), A2[q]);
+        }
+        const float2 a = __fmul2_rn(make_float2(dl, dl), A2[q]);
+        return (ABL & 4) ? __ffma2_rn(a, make_float2(0.5f, 0.5f), make_float2(1.f, 1.f))
+                         : make_float2(ex2_approx(a.x), ex2_approx(a.y));
+    };
 
     for (int i = 0; i < ntiles; ++i) {
         const int stg = i % S, sl = i % NSLOT;
         mbar_wait(&prepped[w * NSLOT + sl], uint32_t(i / NSLOT) & 1u);
         mbar_wait(&full_bar[stg], uint32_t(i / S) & 1u);  // complete long ago; orders this warp after the TMA writes
         // row pointer into the pair's slot: delta -> y at [row][32], u fp32 SC_TT*32 floats further
-        float* psl = slots + sl * (4 * 2 * SC_TT * 32) + w * (2 * SC_TT * 32) + lane + sl_first;
+        float* psl = slots + sl * (4 * PAIRF) + w * PAIRF + lane + sl_first;
         const float* pbc = reinterpret_cast<const float*>(ring + stg * stage_bytes + u_bytes) + BOFF + bc_first;
 
         // Ragged tile (only the sequence's last 16-row tile can be one; it is processed first in the backward direction):
@@ -113,21 +135,16 @@ __device__ __forceinline__ void scan_pair_recur(const uint8_t* ring, float* slot
 #pragma unroll 1
             for (int s2 = 0; s2 < nvalid; ++s2) {
                 const int row = dir ? (nvalid - 1 - s2) : s2;
-                float* py = rowbase + row * 32;
-                const float dl = py[0], uu = py[SC_TT * 32];
+                float* py = rowbase + row * DS;
+                const float dl = py[0], uu = py[UOFF];
                 const float* pb = bcbase + row * NB;
-                const float2 d2 = make_float2(dl, dl);
                 const float du = dl * uu;
                 const float2 du2 = make_float2(du, du);
                 float2 ya[4] = {make_float2(Dv * uu, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const float4 Bv = *reinterpret_cast<const float4*>(pb + 4 * q);
-                    const float2 a0 = __fmul2_rn(d2, A2[2 * q]), a1 = __fmul2_rn(d2, A2[2 * q + 1]);
-                    const float2 e0 = (ABL & 4) ? __ffma2_rn(a0, make_float2(0.5f, 0.5f), make_float2(1.f, 1.f))
-                                                : make_float2(ex2_approx(a0.x), ex2_approx(a0.y));
-                    const float2 e1 = (ABL & 4) ? __ffma2_rn(a1, make_float2(0.5f, 0.5f), make_float2(1.f, 1.f))
-                                                : make_float2(ex2_approx(a1.x), ex2_approx(a1.y));
+                    const float2 e0 = decay(dl, 2 * q), e1 = decay(dl, 2 * q + 1);
                     h2[2 * q] = __ffma2_rn(e0, h2[2 * q], __fmul2_rn(du2, make_float2(Bv.x, Bv.y)));
                     h2[2 * q + 1] = __ffma2_rn(e1, h2[2 * q + 1], __fmul2_rn(du2, make_float2(Bv.z, Bv.w)));
                     if (WY) {
@@ -155,20 +172,13 @@ __device__ __forceinline__ void scan_pair_recur(const uint8_t* ring, float* slot
         // queue is fed independently of the state update chain.
         float2 e_c[8], e_n[8];
         float4 Bq[4];
-        float dl_c = psl[0], u_c = psl[SC_TT * 32];
-        float dl_n = psl[sl_step], u_n = psl[sl_step + SC_TT * 32];
+        float dl_c = psl[0], u_c = psl[UOFF];
+        float dl_n = psl[sl_step], u_n = psl[sl_step + UOFF];
         {
-            const float2 d2 = make_float2(dl_c, dl_c), d2n = make_float2(dl_n, dl_n);
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const float2 a = __fmul2_rn(d2, A2[q]);
-                e_c[q] = (ABL & 4) ? __ffma2_rn(a, make_float2(0.5f, 0.5f), make_float2(1.f, 1.f)) : make_float2(ex2_approx(a.x), ex2_approx(a.y));
-            }
+            for (int q = 0; q < 8; ++q) e_c[q] = decay(dl_c, q);
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const float2 a = __fmul2_rn(d2n, A2[q]);
-                e_n[q] = (ABL & 4) ? __ffma2_rn(a, make_float2(0.5f, 0.5f), make_float2(1.f, 1.f)) : make_float2(ex2_approx(a.x), ex2_approx(a.y));
-            }
+            for (int q = 0; q < 8; ++q) e_n[q] = decay(dl_n, q);
 #pragma unroll
             for (int q = 0; q < 4; ++q) Bq[q] = *reinterpret_cast<const float4*>(pbc + 4 * q);
         }
@@ -187,7 +197,7 @@ __device__ __forceinline__ void scan_pair_recur(const uint8_t* ring, float* slot
             float dl_nn = 0.f, u_nn = 0.f;
             if (jj + 2 < SC_TT) {
                 dl_nn = psl[sl_step];
-                u_nn = psl[sl_step + SC_TT * 32];
+                u_nn = psl[sl_step + UOFF];
             }
             const float du = dl_c * u_c;
             const float2 du2 = make_float2(du, du);
@@ -201,15 +211,11 @@ __device__ __forceinline__ void scan_pair_recur(const uint8_t* ring, float* slot
 #pragma unroll
                 for (int q = 0; q < 4; ++q) Bq[q] = *reinterpret_cast<const float4*>(pbc + 4 * q);
             }
-            const float2 dnn2 = make_float2(dl_nn, dl_nn);
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 h2[q] = __ffma2_rn(e_c[q], h2[q], bu[q]);
                 e_c[q] = e_n[q];
-                if (jj + 2 < SC_TT) {
-                    const float2 a = __fmul2_rn(dnn2, A2[q]);
-                    e_n[q] = (ABL & 4) ? __ffma2_rn(a, make_float2(0.5f, 0.5f), make_float2(1.f, 1.f)) : make_float2(ex2_approx(a.x), ex2_approx(a.y));
-                }
+                if (jj + 2 < SC_TT) e_n[q] = decay(dl_nn, q);
             }
             if (WY) {
                 float2 y0 = make_float2(Dv * u_c, 0.f), y1 = make_float2(0.f, 0.f), y2 = y1, y3 = y1;
@@ -628,18 +634,431 @@ static int launch_scan_pair(const mtn_scan_args* a, cudaStream_t stream) {
     }
     ScanParams p = make_scan_params(a);
     auto kern = scan_kernel_pair<P, R, NDBL, ZT, WY, TC, ABL, RG>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL);
-        if (e != cudaSuccess) {
-            set_error("scan(pair): cudaFuncSetAttribute(%d B smem) failed: %s", SM::TOTAL, cudaGetErrorString(e));
-            return MTN_ECUDA;
-        }
-        attr_set = true;
-    }
+    static std::atomic<unsigned long long> attr_done{0};   // per template instantiation, one bit per device
+    if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(kern), SM::TOTAL, attr_done, "scan(pair)")) return rc;
     dim3 grid(p.ndirs * (a->di / SC_CH), a->batch, 1);
     kern<<<grid, 256, SM::TOTAL, stream>>>(mapU, mapD, mapT, p);
     MTN_CUDA_LAUNCH_CHECK("scan(pair)");
+    return MTN_OK;
+}
+
+
+// =====================================================================================================================
+// v2 helper: the same recurrence warp, a helper stripped to ~a third of its instructions.
+//
+// The v1 helper keeps lane = channel for everything and so pays scalar instructions per (step, channel): R FMAs of
+// dt_proj, 13 for softplus, 16-bit loads / stores for u and y, one 4-byte cp.async per gate value -- 72 issue slots per
+// warp-step next to the recurrence warp's 75, on an SM sub-partition that is issue bound.  None of that work cares which
+// lane owns which element, so v2 picks per phase the layout that makes it cheap:
+//   * dt_proj: delta_pre[16 steps, 32 channels] = dt[16, R] x W_dt[32, R]^T as warp-level mma.sync.m16n8k16 (bf16 hi/lo
+//     split of both operands, 4 passes, fp32 accumulate, dt_bias as the C operand): 16 HMMA per tile instead of
+//     224 LDS/FFMA2/FADD.  The accumulator fragment leaves every lane 2 rows x 8 channels; the column -> channel
+//     assignment of the four n-blocks is permuted (channel = col/2 + 4*(2*nb + col%2)) so that the fragment's STS.32
+//     into the slot are bank-conflict free.
+//   * softplus on that fragment in packed form (FFMA2 over the two accumulator columns): 15 slots per 2 elements.
+//   * u planes -> fp32, gate, hi/lo split and the global stores in a (row, 8-channel segment) layout: 128-bit shared
+//     loads / stores, packed converts, y goes from registers straight to global (no staging pass), silu(z) arrives by
+//     16-byte cp.async that each lane issues for exactly the elements it gates itself.
+// Slot rows are DS = 36 floats apart (144 B, an odd multiple of 16 B): the recurrence warp's row reads (lane =
+// channel), the fragment stores and the 16-byte segment accesses are all conflict free.
+constexpr int P2_DS = 36;
+
+template <int P, int NDBL>
+struct ScanSmemPair2 {
+    static constexpr int SLOTS = 3;
+    static constexpr int U_BYTES = P * SC_TT * SC_CH * 2;
+    static constexpr int NB = NDBL;
+    static constexpr int D_BYTES = SC_TT * NB * 4;
+    static constexpr int STAGE_BYTES = U_BYTES + D_BYTES;
+    static constexpr int PAIR_SLOT_BYTES = 2 * SC_TT * P2_DS * 4;        // [delta -> y | u] x 16 rows x 36 floats
+    static constexpr int SLOT_BYTES = 4 * PAIR_SLOT_BYTES;
+    static constexpr int ZBUF_BYTES = 4 * SC_TT * 32 * 4;                 // per pair 2 KB: [chunk j][lane][16 B]
+    static constexpr int BAR_BYTES = (2 * 4 + 2 * 4 * SLOTS) * 8 + 16;
+    static constexpr int FIXED = 128 + SLOTS * SLOT_BYTES + ZBUF_BYTES + BAR_BYTES;
+    static constexpr int PER_CTA_MAX = 233472 / 2 - 1024;                 // two CTAs per SM
+    static constexpr int STAGES = (FIXED + 4 * STAGE_BYTES <= PER_CTA_MAX) ? 4 : 3;
+    static constexpr int TOTAL = FIXED + STAGES * STAGE_BYTES;
+    static_assert(STAGE_BYTES % 128 == 0 && U_BYTES % 128 == 0, "TMA destinations must stay 128-byte aligned");
+    static_assert(TOTAL <= PER_CTA_MAX, "two CTAs per SM must fit");
+};
+
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+// two fp32 -> one bf16x2 word, element 0 in the low half (F2FP on the ALU pipe)
+__device__ __forceinline__ uint32_t pack_bf16x2(float e0, float e1) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(e1), "f"(e0));
+    return r;
+}
+__device__ __forceinline__ float bf16lo_f(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16hi_f(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+// hi / lo bf16 planes of a pair of fp32 values (same rounding as split_bf16)
+__device__ __forceinline__ void split2_bf16(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    hi = pack_bf16x2(x0, x1);
+    lo = pack_bf16x2(x0 - bf16lo_f(hi), x1 - bf16hi_f(hi));
+}
+// D[16x8] = A[16x16] * B[16x8] + C, bf16 operands, fp32 accumulate (legacy warp-level tensor path: HMMA.16816).
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1,
+                                               const float (&c)[4]) {
+    asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%12,%13};"
+        : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(c[0]), "f"(c[1]), "f"(c[2]), "f"(c[3]));
+}
+// softplus_1mufu (mtn_scan.cu) on two values at once: the same operations per element, Horner steps as FFMA2
+__device__ __forceinline__ float2 softplus2_1mufu(float x0, float x1) {
+    const float2 e = make_float2(ex2_approx(-1.4426950408889634f * fabsf(x0)), ex2_approx(-1.4426950408889634f * fabsf(x1)));
+    float2 q = make_float2(0.0051261021414032125f, 0.0051261021414032125f);
+    q = __ffma2_rn(q, e, make_float2(-0.02907406467853027f, -0.02907406467853027f));
+    q = __ffma2_rn(q, e, make_float2(0.07751608674076167f, 0.07751608674076167f));
+    q = __ffma2_rn(q, e, make_float2(-0.13602247622393474f, -0.13602247622393474f));
+    q = __ffma2_rn(q, e, make_float2(0.19076880735651539f, 0.19076880735651539f));
+    q = __ffma2_rn(q, e, make_float2(-0.24835398988480129f, -0.24835398988480129f));
+    q = __ffma2_rn(q, e, make_float2(0.3331812170752912f, 0.3331812170752912f));
+    q = __ffma2_rn(q, e, make_float2(-0.49999444976340335f, -0.49999444976340335f));
+    q = __ffma2_rn(q, e, make_float2(0.9999999659255092f, 0.9999999659255092f));
+    return __ffma2_rn(q, e, make_float2(fmaxf(x0, 0.f), fmaxf(x1, 0.f)));
+}
+
+// n-way bf16 split of a pair of fp32 values: x = p[0] + p[1] (+ p[2]) with 8 mantissa bits per plane (3 planes
+// represent every fp32 value exactly up to its last bit or two)
+template <int NS>
+__device__ __forceinline__ void splitn_bf16(float x0, float x1, uint32_t (&pl)[NS]) {
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        pl[s] = pack_bf16x2(x0, x1);
+        if (s + 1 < NS) {
+            x0 -= bf16lo_f(pl[s]);
+            x1 -= bf16hi_f(pl[s]);
+        }
+    }
+}
+
+// NS = planes of the dt_proj operands: 3 in fp32 mode (products with plane indices i + j <= 2: six MMA passes,
+// error ~2^-24 like the FMA form), 2 in bf16 mode (three passes, ~2^-16; the reference's autocast path rounds this GEMM's
+// operands AND its result to bf16, selective_scan_interface.py:174-176,187).
+// ABL (dev builds, timing only, WRONG results): bit 0 skips the MMA + softplus, bit 1 the gate / store.
+template <int P, int R, int NDBL, typename ZT, bool WY, int ABL = 0>
+__device__ __forceinline__ void scan_pair_helper2(uint8_t* ring, float* slots, uint8_t* zbuf_all, uint64_t* full_bar,
+                                                  uint64_t* empty_bar, uint64_t* prepped, uint64_t* ydone,
+                                                  const ScanParams& p, int w, int lane, int ch0, int b, int dir,
+                                                  int ntiles, int Lb, const CUtensorMap* mapU, const CUtensorMap* mapD) {
+    using SM = ScanSmemPair2<P, NDBL>;
+    constexpr int S = SM::STAGES, NSLOT = SM::SLOTS, NB = SM::NB, DS = P2_DS;
+    constexpr int PLANE = SC_TT * DS, PAIRF = 2 * PLANE;
+    constexpr int KS = (R + 15) / 16;                            // k-steps of the dt_proj MMA (K = 16 each)
+    constexpr int NS = P == 2 ? 3 : 2;
+    constexpr bool ZF = sizeof(ZT) == 4;
+    constexpr int ZCH = ZF ? 2 : 1;                              // 16-byte chunks of silu(z) per (row, 8 channels)
+    const int L = p.L;
+    const int g = lane >> 2, tig = lane & 3;                     // mma fragment coordinates; also (row, segment) of the
+    const int wch0 = ch0 + w * 32;                               // row-segment layout: rows g / g + 8, channels [8 tig, +8)
+    const size_t pdw = size_t(dir) * p.di + wch0;
+
+    // ---- dt_proj operands that never change: W_dt fragments (hi | lo) and the bias accumulator fragment
+    uint32_t bw[KS][4][2][NS];
+    float cb[4][2];
+#pragma unroll
+    for (int nb = 0; nb < 4; ++nb) {
+        const int chn = (g >> 1) + 4 * (2 * nb + (g & 1));       // channel of this lane's B-fragment column (n = g)
+        const float* wrow = p.w_dt + (pdw + chn) * R;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int k = ks * 16 + 2 * tig + 8 * j;
+                const float v0 = k < R ? wrow[k] : 0.f, v1 = k + 1 < R ? wrow[k + 1] : 0.f;
+                splitn_bf16<NS>(v0, v1, bw[ks][nb][j]);
+            }
+        }
+        cb[nb][0] = p.dt_bias[pdw + tig + 8 * nb];               // accumulator columns 2 tig, 2 tig + 1 of n-block nb
+        cb[nb][1] = p.dt_bias[pdw + tig + 8 * nb + 4];
+    }
+    float2 sdl_sum[4];
+#pragma unroll
+    for (int nb = 0; nb < 4; ++nb) sdl_sum[nb] = make_float2(0.f, 0.f);
+
+    const size_t M = size_t(p.batch) * L;
+    const size_t y_plane = M * 2 * p.di;
+    const int ldy = 2 * p.di;                                     // y row stride, bf16 elements
+    __nv_bfloat16* ybase = p.y + size_t(dir) * p.di + (wch0 + tig * 8);
+    uint4* zbuf = reinterpret_cast<uint4*>(zbuf_all + w * (SC_TT * 32 * 4)) + lane;   // chunk j at zbuf[32 * j]
+    const ZT* zsrc = reinterpret_cast<const ZT*>(p.z) + p.z_col0 + wch0 + tig * 8;
+    auto tile_of = [&](int i) { return dir ? (ntiles - 1 - i) : i; };
+    auto issue_tile = [&](int i2) {
+        const int stg = i2 % S;
+        const int row0 = b * L + tile_of(i2) * SC_TT;
+        mbar_arrive_expect_tx(&full_bar[stg], SM::STAGE_BYTES);
+        uint8_t* dst = ring + stg * SM::STAGE_BYTES;
+        tma_load_3d(dst, mapU, &full_bar[stg], dir * p.di + ch0, row0, 0);
+        tma_load_2d(dst + SM::U_BYTES, mapD, &full_bar[stg], dir * p.n_dbl, row0);
+    };
+    if (w == 0) {
+        if (lane == 0) {
+#pragma unroll 1
+            for (int t = 0; t < S; ++t)
+                if (t < ntiles) issue_tile(t);
+        }
+        __syncwarp();
+    }
+
+#pragma unroll 1
+    for (int k = 0; k < ntiles + 2; ++k) {
+        // ---- gate + store the tile the recurrence warp finished two hand-offs ago
+        const int pt = k - 2;
+        if (pt >= 0) {
+            const int sl = pt % NSLOT;
+            mbar_wait_sleep(&ydone[w * NSLOT + sl], uint32_t(pt / NSLOT) & 1u);
+            if (WY && !(ABL & 2)) {
+                const int t0 = tile_of(pt) * SC_TT;
+                const int nvalid = min(SC_TT, Lb - t0);
+                const float* sy = slots + sl * (4 * PAIRF) + w * PAIRF + g * DS + tig * 8;
+                __nv_bfloat16* ytile = ybase + (size_t(b) * L + t0 + g) * size_t(ldy);
+                cp_async_wait_all();   // this lane's own silu(z) chunks, requested one iteration ago
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    if (g + 8 * hh < nvalid) {
+                        const float4 ya = *reinterpret_cast<const float4*>(sy + hh * 8 * DS);
+                        const float4 yb = *reinterpret_cast<const float4*>(sy + hh * 8 * DS + 4);
+                        float zf[8];
+                        if (ZF) {
+                            const uint4 za = zbuf[32 * (2 * hh)], zb = zbuf[32 * (2 * hh + 1)];
+                            zf[0] = __uint_as_float(za.x); zf[1] = __uint_as_float(za.y);
+                            zf[2] = __uint_as_float(za.z); zf[3] = __uint_as_float(za.w);
+                            zf[4] = __uint_as_float(zb.x); zf[5] = __uint_as_float(zb.y);
+                            zf[6] = __uint_as_float(zb.z); zf[7] = __uint_as_float(zb.w);
+                        } else {
+                            const uint4 za = zbuf[32 * hh];
+                            zf[0] = bf16lo_f(za.x); zf[1] = bf16hi_f(za.x); zf[2] = bf16lo_f(za.y); zf[3] = bf16hi_f(za.y);
+                            zf[4] = bf16lo_f(za.z); zf[5] = bf16hi_f(za.z); zf[6] = bf16lo_f(za.w); zf[7] = bf16hi_f(za.w);
+                        }
+                        const float yv[8] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w};
+                        uint32_t hi[4], lo[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            // y * (0.5 * silu(z)), the same two roundings as the v1 helper
+                            const float2 gz = __fmul2_rn(make_float2(zf[2 * q], zf[2 * q + 1]), make_float2(0.5f, 0.5f));
+                            const float2 o = __fmul2_rn(make_float2(yv[2 * q], yv[2 * q + 1]), gz);
+                            if (P == 2) split2_bf16(o.x, o.y, hi[q], lo[q]);
+                            else hi[q] = pack_bf16x2(o.x, o.y);
+                        }
+                        __nv_bfloat16* yrow = ytile + size_t(hh * 8) * size_t(ldy);
+                        *reinterpret_cast<uint4*>(yrow) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                        if (P == 2) *reinterpret_cast<uint4*>(yrow + y_plane) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    }
+                }
+            }
+        }
+        // ---- producer duty of this iteration (rotates over the four helpers): refill the ring stage of tile k-2
+        if ((k & 3) == w) {
+            const bool refill = pt >= 0 && pt + S < ntiles;
+            if (refill) {
+                mbar_wait_sleep(&empty_bar[pt % S], uint32_t(pt / S) & 1u);   // every recurrence warp is done with it
+                if (lane == 0) issue_tile(pt + S);
+            }
+            __syncwarp();
+        }
+        // ---- request silu(z) of the tile gated in the NEXT iteration: 16-byte chunks, each lane its own elements
+        if (WY && !(ABL & 2) && k >= 1 && k - 1 < ntiles) {
+            const int t0 = tile_of(k - 1) * SC_TT;
+            const int nvalid = min(SC_TT, Lb - t0);
+            const ZT* zs = zsrc + (size_t(b) * L + t0 + g) * size_t(p.ldz);
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                if (g + 8 * hh < nvalid) {
+#pragma unroll
+                    for (int c = 0; c < ZCH; ++c)
+                        cp_async_16(zbuf + 32 * (ZCH * hh + c), zs + size_t(hh * 8) * size_t(p.ldz) + c * 4);
+                }
+            }
+        }
+        cp_async_commit();
+        // ---- delta and u of tile k
+        if (k < ntiles) {
+            const int stg = k % S, sl = k % NSLOT;
+            const int t0 = tile_of(k) * SC_TT;
+            const int nvalid = min(SC_TT, Lb - t0);
+            mbar_wait_sleep(&full_bar[stg], uint32_t(k / S) & 1u);
+            const uint8_t* st = ring + stg * SM::STAGE_BYTES;
+            float* slot = slots + sl * (4 * PAIRF) + w * PAIRF;
+            // dt operand fragments: rows g, g + 8 of the staged [dt | B | C] rows, split into bf16 hi | lo
+            const float* sd = reinterpret_cast<const float*>(st + SM::U_BYTES) + g * NB + 2 * tig;
+            float acc[4][4];
+#pragma unroll
+            for (int nb = 0; nb < 4; ++nb) {
+                acc[nb][0] = acc[nb][2] = cb[nb][0];
+                acc[nb][1] = acc[nb][3] = cb[nb][1];
+            }
+            if (!(ABL & 1)) {
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks) {
+                    uint32_t aw[NS][4];
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const float2 v0 = *reinterpret_cast<const float2*>(sd + ks * 16 + 8 * j);
+                        const float2 v1 = *reinterpret_cast<const float2*>(sd + 8 * NB + ks * 16 + 8 * j);
+                        uint32_t p0[NS], p1[NS];
+                        splitn_bf16<NS>(v0.x, v0.y, p0);
+                        splitn_bf16<NS>(v1.x, v1.y, p1);
+#pragma unroll
+                        for (int s2 = 0; s2 < NS; ++s2) {
+                            aw[s2][2 * j] = p0[s2];
+                            aw[s2][2 * j + 1] = p1[s2];
+                        }
+                    }
+                    // smallest products first (plane index sum NS-1 down to 0); the four n-blocks are independent chains
+#pragma unroll
+                    for (int tsum = NS - 1; tsum >= 0; --tsum) {
+#pragma unroll
+                        for (int i = 0; i <= tsum; ++i) {
+#pragma unroll
+                            for (int nb = 0; nb < 4; ++nb)
+                                mma_bf16_16816(acc[nb], aw[i], bw[ks][nb][0][tsum - i], bw[ks][nb][1][tsum - i], acc[nb]);
+                        }
+                    }
+                }
+            }
+            float* sdl = slot + g * DS + tig;
+            const bool v0 = g < nvalid, v1 = g + 8 < nvalid;   // rows past the utterance end: delta = 0 -> state unchanged
+#pragma unroll
+            for (int nb = 0; nb < 4; ++nb) {
+                float2 d0 = (ABL & 1) ? make_float2(acc[nb][0], acc[nb][1]) : softplus2_1mufu(acc[nb][0], acc[nb][1]);
+                float2 d1 = (ABL & 1) ? make_float2(acc[nb][2], acc[nb][3]) : softplus2_1mufu(acc[nb][2], acc[nb][3]);
+                if (nvalid < SC_TT) {
+                    if (!v0) d0 = make_float2(0.f, 0.f);
+                    if (!v1) d1 = make_float2(0.f, 0.f);
+                }
+                sdl_sum[nb] = __fadd2_rn(sdl_sum[nb], __fadd2_rn(d0, d1));
+                sdl[8 * nb] = d0.x;
+                sdl[8 * nb + 4] = d0.y;
+                sdl[8 * DS + 8 * nb] = d1.x;
+                sdl[8 * DS + 8 * nb + 4] = d1.y;
+            }
+            // u planes -> fp32, rows g / g + 8, channels [8 tig, 8 tig + 8) of this warp's 32
+            const __nv_bfloat16* su = reinterpret_cast<const __nv_bfloat16*>(st) + g * SC_CH + w * 32 + tig * 8;
+            float* suo = slot + PLANE + g * DS + tig * 8;
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const uint4 uh = *reinterpret_cast<const uint4*>(su + hh * 8 * SC_CH);
+                const uint32_t hw[4] = {uh.x, uh.y, uh.z, uh.w};
+                float2 f[4];
+                if (P == 2) {
+                    const uint4 ul = *reinterpret_cast<const uint4*>(su + (SC_TT + hh * 8) * SC_CH);
+                    const uint32_t lw[4] = {ul.x, ul.y, ul.z, ul.w};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        f[q] = __fadd2_rn(make_float2(bf16lo_f(hw[q]), bf16hi_f(hw[q])),
+                                          make_float2(bf16lo_f(lw[q]), bf16hi_f(lw[q])));
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) f[q] = make_float2(bf16lo_f(hw[q]), bf16hi_f(hw[q]));
+                }
+                *reinterpret_cast<float4*>(suo + hh * 8 * DS) = make_float4(f[0].x, f[0].y, f[1].x, f[1].y);
+                *reinterpret_cast<float4*>(suo + hh * 8 * DS + 4) = make_float4(f[2].x, f[2].y, f[3].x, f[3].y);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&prepped[w * NSLOT + sl]);
+        }
+    }
+    if (p.sum_delta) {   // per channel: sum over the rows held by the 8 lanes that share tig
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb) {
+#pragma unroll
+            for (int o = 4; o < 32; o <<= 1) {
+                sdl_sum[nb].x += __shfl_xor_sync(0xffffffffu, sdl_sum[nb].x, o);
+                sdl_sum[nb].y += __shfl_xor_sync(0xffffffffu, sdl_sum[nb].y, o);
+            }
+        }
+        if (g == 0) {
+            float* dst = p.sum_delta + (size_t(dir) * p.batch + b) * p.di + wch0 + tig;
+#pragma unroll
+            for (int nb = 0; nb < 4; ++nb) {
+                dst[8 * nb] = sdl_sum[nb].x;
+                dst[8 * nb + 4] = sdl_sum[nb].y;
+            }
+        }
+    }
+}
+
+template <int P, int R, int NDBL, typename ZT, bool WY, bool RG, int KP, int ABL>
+__global__ void __launch_bounds__(256, 2)
+scan_kernel_pair2(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUtensorMap mapD, const ScanParams p) {
+    using SM = ScanSmemPair2<P, NDBL>;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
+    uint8_t* ring = smem;
+    float* slots = reinterpret_cast<float*>(smem + SM::STAGES * SM::STAGE_BYTES);
+    uint8_t* zbuf = smem + SM::STAGES * SM::STAGE_BYTES + SM::SLOTS * SM::SLOT_BYTES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(zbuf + SM::ZBUF_BYTES);
+    uint64_t* empty_bar = full_bar + 4;
+    uint64_t* prepped = empty_bar + 4;
+    uint64_t* ydone = prepped + 4 * SM::SLOTS;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int nchb = p.di / SC_CH;
+    const int ch0 = (blockIdx.x % nchb) * SC_CH;
+    const int dir = p.dir0 + blockIdx.x / nchb;
+    const int b = blockIdx.y;
+    if (tid == 0) {
+        tma_prefetch_desc(&mapU);
+        tma_prefetch_desc(&mapD);
+        for (int s = 0; s < SM::STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 4);
+        }
+        for (int s = 0; s < 4 * SM::SLOTS; ++s) {
+            mbar_init(&prepped[s], 1);
+            mbar_init(&ydone[s], 1);
+        }
+        fence_barrier_init();
+    }
+    __syncthreads();
+    const int Lb = (b == p.batch - 1) ? p.L_last : p.L;
+    const int ntiles = (Lb + SC_TT - 1) / SC_TT;
+    const int w = warp & 3;
+    if (warp < 4)
+        scan_pair_recur<SM::STAGES, SM::NB, R, WY, ABL, RG, P2_DS, KP>(ring, slots, SM::STAGE_BYTES, SM::U_BYTES, full_bar,
+                                                                    empty_bar, prepped, ydone, p, w, lane,
+                                                                    ch0 + w * 32 + lane, b, dir, ntiles, Lb);
+    else
+        scan_pair_helper2<P, R, NDBL, ZT, WY, ABL>(ring, slots, zbuf, full_bar, empty_bar, prepped, ydone, p, w, lane, ch0, b,
+                                              dir, ntiles, Lb, &mapU, &mapD);
+}
+
+template <int P, int R, int NDBL, typename ZT, bool WY, int KP = 0, bool RG = false, int ABL = 0>
+static int launch_scan_pair2(const mtn_scan_args* a, cudaStream_t stream) {
+    // short ragged sequences (many of them: DPMamba's inter model) take the instantiation with the ragged-tile path
+    if (!RG && KP == 0 && ABL == 0 && WY && a->L <= 128 && (a->L % SC_TT) != 0 && a->L_last == 0)
+        return launch_scan_pair2<P, R, NDBL, ZT, WY, KP, true>(a, stream);
+    using SM = ScanSmemPair2<P, NDBL>;
+    MTN_REQUIRE((reinterpret_cast<uintptr_t>(a->z) & 15) == 0 && (a->ldz * sizeof(ZT)) % 16 == 0 &&
+                    (a->z_col0 * sizeof(ZT)) % 16 == 0,
+                "scan(pair2): the gate block must be 16-byte aligned (z=%p ldz=%d z_col0=%d)", a->z, a->ldz, a->z_col0);
+    MTN_REQUIRE(!a->y || (reinterpret_cast<uintptr_t>(a->y) & 15) == 0, "scan(pair2): y must be 16-byte aligned");
+    const uint64_t M = uint64_t(a->batch) * a->L;
+    CUtensorMap mapU, mapD;
+    {
+        uint64_t dims[3] = {uint64_t(2) * a->di, M, uint64_t(P)};
+        uint64_t str[2] = {uint64_t(2) * a->di * 2, M * 2 * a->di * 2};
+        uint32_t box[3] = {uint32_t(SC_CH), SC_TT, uint32_t(P)};
+        if (!encode_tmap(&mapU, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, a->u, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE))
+            return MTN_ECUDA;
+    }
+    {
+        uint64_t dims[2] = {uint64_t(a->ld_dbl), M};
+        uint64_t str[1] = {uint64_t(a->ld_dbl) * 4};
+        uint32_t box[2] = {uint32_t(SM::NB), SC_TT};
+        if (!encode_tmap(&mapD, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, a->dbl, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE))
+            return MTN_ECUDA;
+    }
+    ScanParams p = make_scan_params(a);
+    auto kern = scan_kernel_pair2<P, R, NDBL, ZT, WY, RG, KP, ABL>;
+    static std::atomic<unsigned long long> attr_done{0};   // per template instantiation, one bit per device
+    if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(kern), SM::TOTAL, attr_done, "scan(pair2)")) return rc;
+    dim3 grid(p.ndirs * (a->di / SC_CH), a->batch, 1);
+    kern<<<grid, 256, SM::TOTAL, stream>>>(mapU, mapD, p);
+    MTN_CUDA_LAUNCH_CHECK("scan(pair2)");
     return MTN_OK;
 }
 

@@ -314,15 +314,8 @@ static int launch_scan_trio(const mtn_scan_args* a, cudaStream_t stream) {
     }
     ScanParams p = make_scan_params(a);
     auto kern = scan_kernel_trio<P, R, NDBL, ZT, ABL>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ST::TOTAL);
-        if (e != cudaSuccess) {
-            set_error("scan(trio): cudaFuncSetAttribute(%d B smem) failed: %s", ST::TOTAL, cudaGetErrorString(e));
-            return MTN_ECUDA;
-        }
-        attr_set = true;
-    }
+    static std::atomic<unsigned long long> attr_done{0};   // per template instantiation, one bit per device
+    if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(kern), ST::TOTAL, attr_done, "scan(trio)")) return rc;
     dim3 grid(p.ndirs * (a->di / SC_CH), a->batch, 1);
     kern<<<grid, 384, ST::TOTAL, stream>>>(mapU, mapD, p);
     MTN_CUDA_LAUNCH_CHECK("scan(trio)");

@@ -25,6 +25,7 @@ import copy
 import torch
 
 from . import _lib, ops
+from ._cache import LRUDict
 from .engine import MODES, LayerWorkspace, MambaStack
 from .hparams import DPHParams
 
@@ -102,7 +103,9 @@ class DPSeparatorEngine:
             self.w_og = ops.split_planes(torch.cat([wo, wg] * spk, dim=0).contiguous(), P)       # [P, spk*2D, D]
             self.b_o, self.b_g = f32(m["output.0.bias"]), f32(m["output_gate.0.bias"])
             self.w_end = ops.split_planes(f32(m["end_conv1x1.weight"]).reshape(N, D).repeat(spk, 1).contiguous(), P)
-        self._ws, self._graphs = {}, {}
+        # LRU-bounded like SeparatorEngine's (engine.LRUDict): evicting a workspace drops the graph captured against it
+        self._graphs = LRUDict()
+        self._ws = LRUDict(on_evict=lambda key, ws: self._graphs.pop(key, None))
         self._prof = None
         # encoder, gn x2, conv1d, segment | per block: 2 x (stack 7 + gn 2) | overadd, conv2d, bias, og, gate, end, decoder(2)
         self.launches_per_forward = 5 + hp.n_dp * 2 * (6 * (hp.n_mamba_dp // 2) + 1 + 2) + 8

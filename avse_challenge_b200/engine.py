@@ -25,10 +25,18 @@ from __future__ import annotations
 import torch
 
 from . import _lib, ops
+from ._cache import LRUDict
 from .hparams import HParams
 from .ops import LOG2E, n_dbl_for, rp_for
 
 MODES = {"fp32": dict(planes=2, xz_bf16=False), "bf16": dict(planes=1, xz_bf16=True)}
+
+def resolve_device(device) -> torch.device:
+    """``"cuda"`` -> the current device with an explicit index, so engines can pin their launches to it."""
+    dev = torch.device(device)
+    if dev.type == "cuda" and dev.index is None and torch.cuda.is_available():
+        dev = torch.device("cuda", torch.cuda.current_device())
+    return dev
 
 
 class PackedWeights:
@@ -137,7 +145,7 @@ class LayerPlan:
         if not torch.cuda.is_available():
             raise _lib.MtnError(f"{type(self).__name__} needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         _lib.load()
-        self.hp, self.mode, self.device = hp, mode, torch.device(device)
+        self.hp, self.mode, self.device = hp, mode, resolve_device(device)
         self.P = MODES[mode]["planes"]
         self.n_dbl = n_dbl_for(hp.dt_rank)
         self._prof = None
@@ -214,7 +222,7 @@ class MambaStack(LayerPlan):
             self.layers = [pack_layer(sd, f"{prefix}layers.{i}.", hp, self.P, self.device) for i in range(hp.n_mamba)]
             self.norm_f = f32(sd[prefix + "norm_f.weight"])
             self.norm_f_b = f32(sd[prefix + "norm_f.bias"]) if not hp.rms_norm else None
-        self._ws = {}
+        self._ws = LRUDict()
 
     def workspace(self, batch, L) -> LayerWorkspace:
         key = (batch, L)
@@ -236,10 +244,13 @@ class MambaStack(LayerPlan):
     def forward(self, x: torch.Tensor, states=None) -> torch.Tensor:
         if x.dim() != 3 or x.shape[-1] != self.hp.d_model or not x.is_cuda:
             raise _lib.MtnError(f"MambaStack.forward expects a CUDA tensor [Bseq, L, {self.hp.d_model}]")
+        if x.device != self.device:
+            raise _lib.MtnError(f"input on {x.device}, but this stack was built for {self.device}")
         B, L, D = x.shape
-        ws = self.workspace(B, L)
-        ws.h.copy_(x.reshape(B * L, D))
-        return self.run(ws, torch.empty((B * L, D), dtype=torch.float32, device=x.device), states).view(B, L, D)
+        with torch.cuda.device(self.device):   # launches go to the device the weights live on, whatever is current
+            ws = self.workspace(B, L)
+            ws.h.copy_(x.reshape(B * L, D))
+            return self.run(ws, torch.empty((B * L, D), dtype=torch.float32, device=x.device), states).view(B, L, D)
 
     __call__ = forward
 
@@ -256,8 +267,9 @@ class SeparatorEngine(LayerPlan):
         self.fuse_norm = fuse_norm
         with torch.cuda.device(self.device):
             self.w = PackedWeights(hp, sds, self.device, mode)
-        self._ws = {}
-        self._graphs = {}
+        # a graph replays into the buffers of its workspace: evicting a workspace drops the graph captured against it
+        self._graphs = LRUDict()
+        self._ws = LRUDict(on_evict=lambda key, ws: self._graphs.pop(key, None))
         # enc, bottleneck, layers, (norm_f +) mask, decoder(2); fused: no norm kernels
         self.launches_per_forward = (1 + 1 + hp.n_mamba * 5 + 1 + 2) if fuse_norm else (1 + 1 + hp.n_mamba * 6 + 2 + 2)
 
@@ -348,42 +360,42 @@ class SeparatorEngine(LayerPlan):
         """``mix`` [B, T] fp32 on this engine's device.  Returns a fresh ``[B, T, n_spk]`` tensor."""
         if mix.dim() != 2 or mix.dtype != torch.float32 or not mix.is_cuda:
             raise _lib.MtnError("forward expects a CUDA fp32 tensor of shape [batch, T]")
+        if mix.device != self.device:
+            raise _lib.MtnError(f"mix is on {mix.device}, but this engine was built for {self.device}")
         B, T = mix.shape
         if T < 16:
             raise _lib.MtnError(f"T={T}: need at least one 16-sample frame")
-        ws = self.workspace(B, T)
-        ws.mix[:, :T].copy_(mix, non_blocking=True)
-        if taps is not None or not self.use_graph:
-            return self._run(ws, taps).clone()
-        key = (B, T)
+        with torch.cuda.device(self.device):   # launches go to the engine's device, whatever the caller has current
+            ws = self.workspace(B, T)
+            ws.mix[:, :T].copy_(mix, non_blocking=True)
+            if taps is not None or not self.use_graph:
+                return self._run(ws, taps).clone()
+            self._graph_for(ws, (B, T)).replay()
+            return ws.est.clone()
+
+    __call__ = forward
+
+    def _graph_for(self, ws: Workspace, key):
+        """The whole-forward CUDA graph of this shape (captured on first use, after one eager run that sets the kernels'
+        function attributes and validates the shapes).  Variable-length evaluation loops should build the engine with
+        ``use_graph=False``: every new length otherwise costs an eager run plus a capture."""
         g = self._graphs.get(key)
         if g is None:
-            self._run(ws)  # eager warm-up: sets function attributes, validates shapes before capture
+            self._run(ws)
             torch.cuda.current_stream().synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 self._run(ws)
             self._graphs[key] = g
-        g.replay()
-        return ws.est.clone()
-
-    __call__ = forward
+        return g
 
     def forward_into_workspace(self, batch: int, T: int):
         """Run (graph replay when enabled) on whatever is already in ``workspace(batch, T).mix``; returns the
         workspace's ``est`` buffer without copying.  Used by the benchmark's device-resident timing."""
-        ws = self.workspace(batch, T)
-        key = (batch, T)
-        if self.use_graph:
-            g = self._graphs.get(key)
-            if g is None:
+        with torch.cuda.device(self.device):
+            ws = self.workspace(batch, T)
+            if self.use_graph:
+                self._graph_for(ws, (batch, T)).replay()
+            else:
                 self._run(ws)
-                torch.cuda.current_stream().synchronize()
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    self._run(ws)
-                self._graphs[key] = g
-            g.replay()
-        else:
-            self._run(ws)
-        return ws.est
+            return ws.est

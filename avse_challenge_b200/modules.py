@@ -180,11 +180,17 @@ def _stack_forward(self, x, keep_to=None, inference_params=None):
             _unsupported("inference_params with bidirectional=True (the backward direction needs the future)")
         kv = inference_params.key_value_memory_dict
         di = stack.hp.d_inner
+        # seqlen_offset == 0 is the reference's prefill: it starts from a zero state and OVERWRITES the caches
+        # (bimamba.py:271-304), which is how callers reset a cache object for a new sequence
+        fresh = getattr(inference_params, "seqlen_offset", 0) == 0
         states = []
         for i in range(self.n_mamba):
             if i not in kv:
                 kv[i] = (torch.zeros(B, di, 4, device=dev), torch.zeros(B, di, 16, device=dev))
             cs, ss = kv[i]
+            if fresh:
+                cs.zero_()
+                ss.zero_()
             conv4 = cs.transpose(1, 2).contiguous().float()
             h = torch.zeros(2, B, di, 16, device=dev)
             h[0].copy_(ss)
@@ -293,8 +299,9 @@ class Decoder(nn.ConvTranspose1d):
         sep = x.transpose(1, 2).contiguous().float().view(B * L, N)
         T_est = (L - 1) * 8 + 16
         est = ops.decoder(sep, self.weight.detach().reshape(N, 16).contiguous(), B, T_est, L, N, n_spk=1)
-        est = est.view(B, T_est)
-        return est.squeeze(0) if B == 1 else est  # reference squeezes singleton dims (avse2/model.py:33-36)
+        # speechbrain's Decoder squeezes the channel dim only: [1, 1, T] -> [1, T] (same code as baseline/avse2/model.py:31-36:
+        # squeeze(x).dim() == 1 -> squeeze(x, dim=1)), so compute_forward's `.unsqueeze(-1)` / `[:, :T_origin, :]` work at B = 1
+        return est.view(B, T_est)
 
 
 class MaskNet(_EngineOwner):
@@ -516,9 +523,12 @@ class DPMambaSeparator(_EngineOwner):
     def from_hparams(cls, hp, mode="fp32", use_graph=True):
         mk = lambda: MambaBlocksSequential(hp.n_mamba_dp // 2, bidirectional=True, d_model=hp.d_model, d_state=hp.d_state,
                                            expand=hp.expand, d_conv=hp.d_conv, fused_add_norm=False, rms_norm=True)
-        mask = Dual_Path_Model(hp.enc_dim, hp.d_model, mk(), mk(), num_layers=hp.n_dp, norm="ln", K=hp.chunk_size,
-                               num_spks=hp.n_spk, skip_around_intra=hp.skip_around_intra,
-                               linear_layer_after_inter_intra=False, mode=mode)
+        kw = dict(num_layers=hp.n_dp, norm="ln", K=hp.chunk_size, num_spks=hp.n_spk, skip_around_intra=hp.skip_around_intra,
+                  linear_layer_after_inter_intra=False, mode=mode)
+        if hp.skip_n_block:   # modules/dual_path.py:17-150 (no shipped recipe sets it)
+            mask = Dual_Path_Model_Skip(hp.enc_dim, hp.d_model, mk(), mk(), skip_n_block=hp.skip_n_block, **kw)
+        else:
+            mask = Dual_Path_Model(hp.enc_dim, hp.d_model, mk(), mk(), **kw)
         return cls(Encoder(hp.kernel_size, hp.enc_dim), mask, Decoder(hp.enc_dim, 1, hp.kernel_size, hp.stride, bias=False),
                    mode=mode, use_graph=use_graph)
 

@@ -26,6 +26,7 @@ from typing import List, Optional, Tuple
 import torch
 import torch.distributed as dist
 
+from ._cache import LRUDict
 from .hparams import HParams
 
 
@@ -279,7 +280,7 @@ class SequenceParallelSeparator:
         # per length.  That is also the low-latency plan for ONE short utterance: the scan's serial chain is sub_chunks
         # times shorter than in the batch plan (4 s @ 8 kHz, S: 9.0 ms -> 2.1 ms at 16 sub-chunks).
         self.use_graph = use_graph and backend is None
-        self._graphs = {}
+        self._graphs = LRUDict()   # one whole-forward graph (with its private buffers) per recording length, LRU-bounded
 
     @torch.no_grad()
     def forward(self, mix: torch.Tensor) -> torch.Tensor:

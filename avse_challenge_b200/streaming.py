@@ -20,6 +20,7 @@ from __future__ import annotations
 import torch
 
 from . import _lib
+from ._cache import LRUDict
 from .engine import SeparatorEngine
 
 
@@ -42,8 +43,14 @@ class StreamingSeparator:
         self.started = False
         self.samples_in = 0
         self.samples_out = 0
-        self._est = {}
-        self._graphs = {}
+        # per chunk length: output buffer + (graph, workspace it was captured against).  LRU-bounded; a graph is also
+        # dropped when the engine has meanwhile evicted its workspace (checked at replay)
+        self._est = LRUDict(on_evict=lambda L, buf: self._drop_graphs(L))
+        self._graphs = LRUDict()
+
+    def _drop_graphs(self, L):
+        for key in [k for k, (_, ws) in self._graphs.items() if ws.L == L]:
+            self._graphs.pop(key, None)
 
     def reset(self):
         for st in self.state["layers"]:
@@ -55,8 +62,11 @@ class StreamingSeparator:
         self.samples_in = self.samples_out = 0
 
     def _run(self, ws, L):
-        self.state["est"] = self._est.setdefault(
-            L, torch.empty((self.batch, 8 * L, self.eng.hp.n_spk), dtype=torch.float32, device=self.eng.device))
+        est = self._est.get(L)
+        if est is None:
+            est = self._est[L] = torch.empty((self.batch, 8 * L, self.eng.hp.n_spk), dtype=torch.float32,
+                                             device=self.eng.device)
+        self.state["est"] = est
         return self.eng._run(ws, stream_state=self.state)   # either plan (fuse_norm folds Add -> RMSNorm into the GEMMs)
 
     @torch.no_grad()
@@ -77,8 +87,8 @@ class StreamingSeparator:
         L = ws.L
         key = (T,)
         if self.use_graph:
-            g = self._graphs.get(key)
-            if g is None:
+            g, g_ws = self._graphs.get(key, (None, None))
+            if g is None or g_ws is not ws:   # never captured, or the engine evicted (and re-made) this shape's workspace
                 # capture without running eagerly first: a warm-up run would advance the caches twice
                 snap = self._snapshot()
                 self._run(ws, L)
@@ -87,7 +97,7 @@ class StreamingSeparator:
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
                     self._run(ws, L)
-                self._graphs[key] = g
+                self._graphs[key] = (g, ws)
             g.replay()
             est = self._est[L]
         else:

@@ -46,6 +46,10 @@
 extern "C" {
 #endif
 
+/* Bumped whenever a struct below or an entry point's signature changes; mtn_abi_version() returns the value the library
+ * was built with (experiment builds of tools/devbuild.sh add 1000 so that a product binding refuses them). */
+#define MTN_ABI_VERSION 6
+
 #define MTN_OK 0
 #define MTN_EINVAL (-1)  /* bad shape / alignment / unsupported option */
 #define MTN_ECUDA (-2)   /* CUDA runtime or driver error; see mtn_last_error_string() */
@@ -275,6 +279,11 @@ int mtn_gate_planes_fwd(const float* og, const float* bo, const float* bg, void*
 
 const char* mtn_last_error_string(void);
 int mtn_abi_version(void);
+/* sizeof() of the argument structs as the library was compiled: a binding generated from another revision of this header
+ * (or a hand-copied ctypes / cgo / JNI struct) can check its layout before the first launch (ABI >= 6). */
+size_t mtn_sizeof_gemm_args(void);
+size_t mtn_sizeof_scan_args(void);
+size_t mtn_sizeof_gn_apply_args(void);
 
 #ifdef __cplusplus
 }

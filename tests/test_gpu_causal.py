@@ -209,6 +209,11 @@ def test_stack_forward_with_inference_params_matches_reference_cache_golden(gold
         cs, ss = ip.key_value_memory_dict[i]
         assert rel_max(cs.cpu(), torch.from_numpy(z[f"conv_state/{i}"])) <= 1e-4
         assert rel_max(ss.cpu(), torch.from_numpy(z[f"ssm_state/{i}"])) <= 1e-4
+    # the reference's reset idiom: the SAME cache object with seqlen_offset = 0 starts a new sequence from zero state
+    # (prefill overwrites the caches, bimamba.py:271-304) -- nothing of the previous sequence may leak
+    ip.seqlen_offset = 0
+    again = net(h[:, :L0], inference_params=ip).cpu()
+    assert torch.equal(again, outs[0].cpu())
 
 
 def test_mixer_step_matches_oracle_step():

@@ -382,9 +382,14 @@ def test_three_speakers_vs_oracle():
     m.load_state_dict(sds["masknet"], strict=True)
 
 
-def test_standalone_modules_follow_compute_forward(golden_dir):
-    """The reference's own call sequence (train_wsj0mix.py:86-111) on the three drop-in modules."""
+@pytest.mark.parametrize("rows", [None, 1], ids=["golden-batch", "batch-1"])
+def test_standalone_modules_follow_compute_forward(golden_dir, rows):
+    """The reference's own call sequence (train_wsj0mix.py:86-111) on the three drop-in modules; ``batch-1`` is the
+    reference's default evaluation batch size, where the speechbrain Decoder returns [1, T] (not [T])."""
     sds, g, taps = load_golden_forward(os.path.join(golden_dir, "forward_tiny_trained.npz"))
+    if rows is not None:
+        g = {k: (v[:, :rows] if k == "est_mask" else v[:rows]) if k in ("mix", "mix_w", "est_mask", "est", "src") else v
+             for k, v in g.items()}
     hp = hp_from_sds(sds)
     sep = modules.MambaTasNetSeparator.from_hparams(hp, mode="fp32")
     sep.load_reference_state_dicts(sds).to(DEV)
@@ -397,6 +402,7 @@ def test_standalone_modules_follow_compute_forward(golden_dir):
     mix_w = torch.stack([mix_w] * 2)
     sep_h = mix_w * est_mask
     est_source = torch.cat([Decoder(sep_h[i]).unsqueeze(-1) for i in range(2)], dim=-1)
+    assert est_source.dim() == 3 and est_source.shape[0] == mix.shape[0] and est_source.shape[2] == 2
     T_origin, T_est = mix.size(1), est_source.size(1)
     if T_origin > T_est:
         est_source = torch.nn.functional.pad(est_source, (0, 0, 0, T_origin - T_est))

@@ -117,6 +117,54 @@ def test_struct_layouts_match_header(built_lib):
         assert names == [f[0] for f in cls._fields_], cname
 
 
+def test_integration_stub_matches_the_header(built_lib):
+    """The ctypes stub printed in INTEGRATION.md section 2 is what a maintainer pastes: its struct must have the fields of
+    mtn_scan_args in the header's order and the size the built library reports (a short struct makes the kernel read
+    sum_delta / L_last / dtp from whatever follows it in memory)."""
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    snippet = re.search(r"```python\n(import ctypes, torch.*?)```", doc, re.S).group(1)
+    cls_src = re.search(r"(class MtnScanArgs\(ctypes\.Structure\):.*?)\n\n", snippet, re.S).group(1)
+    ns = {"ctypes": ctypes}
+    exec(cls_src, ns)
+    stub = ns["MtnScanArgs"]
+    assert [f[0] for f in stub._fields_] == [f[0] for f in _lib.ScanArgs._fields_]
+    assert [f[1] for f in stub._fields_] == [f[1] for f in _lib.ScanArgs._fields_]
+    lib = ctypes.CDLL(built_lib)
+    lib.mtn_sizeof_scan_args.restype = ctypes.c_size_t
+    assert ctypes.sizeof(stub) == lib.mtn_sizeof_scan_args() == ctypes.sizeof(_lib.ScanArgs)
+    lib.mtn_abi_version.restype = ctypes.c_int
+    m = re.search(r"mtn_abi_version\(\) == (\d+)", snippet)
+    assert m and int(m.group(1)) == lib.mtn_abi_version() == _lib.EXPECTED_ABI
+    header = open(os.path.join(ROOT, "include", "mtn_b200.h")).read()
+    assert int(re.search(r"#define MTN_ABI_VERSION (\d+)", header).group(1)) == _lib.EXPECTED_ABI
+    # every name the stub's call passes as a keyword is a field
+    call = re.search(r"a = MtnScanArgs\((.*?)\)\n    rc", snippet, re.S).group(1)
+    assert set(re.findall(r"(\w+)=", call)) == {f[0] for f in stub._fields_}
+
+
+def test_loader_refuses_a_library_of_another_abi(built_lib, monkeypatch):
+    """A stale / experiment build (git-ignored .so, rebuilt on mtimes only) must not be handed this binding's structs."""
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "EXPECTED_ABI", _lib.EXPECTED_ABI + 1)
+    with pytest.raises(_lib.MtnError, match="ABI"):
+        _lib.load()
+    monkeypatch.undo()
+    _lib._lib = None
+    assert _lib.load().mtn_abi_version() == _lib.EXPECTED_ABI
+
+
+def test_shape_caches_are_bounded():
+    """per-shape workspaces / graphs must not grow without bound over a variable-length test set."""
+    from avse_challenge_b200._cache import LRUDict
+    evicted = []
+    ws = LRUDict(3, on_evict=lambda k, v: evicted.append(k))
+    for T in range(10):
+        ws[(1, T)] = object()
+        ws.get((1, 0))                      # keep one shape hot
+    assert len(ws) == 3 and (1, 0) in ws and (1, 9) in ws
+    assert evicted == [(1, 1), (1, 2), (1, 3), (1, 4), (1, 5), (1, 6), (1, 7)]
+
+
 def test_synth_is_deterministic_and_scaled():
     mix, src = synth_mixture(2, 4000, seed=5)
     mix2, _ = synth_mixture(2, 4000, seed=5)
