@@ -19,10 +19,10 @@ EXPECTED_ABI = 6
 
 EXPORTS = [
     "mtn_encoder_cln_fwd", "mtn_gemm_fwd", "mtn_gemm_rowsum_parts", "mtn_add_rmsnorm_fwd", "mtn_add_rmsnorm_out_fwd", "mtn_add_norm_fwd", "mtn_conv_silu_fwd", "mtn_conv_silu_halo_fwd", "mtn_conv_silu_dir_fwd", "mtn_decoder_stream_fwd",
-    "mtn_scan_fwd", "mtn_fold_states_fwd",
+    "mtn_scan_fwd", "mtn_fold_states_fwd", "mtn_fold_states_packed_fwd",
     "mtn_gn_partials_bytes", "mtn_gn_stats_fwd", "mtn_gn_apply_fwd", "mtn_gn_apply_norm_fwd", "mtn_dp_num_chunks", "mtn_dp_segment_fwd",
     "mtn_dp_overadd_prelu_fwd", "mtn_bias_planes_fwd", "mtn_gate_planes_fwd",
-    "mtn_decoder_fwd", "mtn_cln_fwd", "mtn_softmax_mask_fwd", "mtn_split_planes", "mtn_si_snr_pit_fwd", "mtn_si_snr_workspace_bytes", "mtn_last_error_string", "mtn_abi_version",
+    "mtn_decoder_fwd", "mtn_cln_fwd", "mtn_softmax_mask_fwd", "mtn_split_planes", "mtn_si_snr_pit_fwd", "mtn_si_snr_workspace_bytes", "mtn_si_snr_pit_n_fwd", "mtn_si_snr_workspace_bytes_n", "mtn_last_error_string", "mtn_abi_version",
     "mtn_sizeof_gemm_args", "mtn_sizeof_scan_args", "mtn_sizeof_gn_apply_args",
 ]
 
@@ -102,12 +102,16 @@ def load():
     lib.mtn_decoder_stream_fwd.argtypes = [c_void_p] * 5 + [c_int] * 5 + [c_void_p]
     lib.mtn_scan_fwd.argtypes = [POINTER(ScanArgs), c_void_p]
     lib.mtn_fold_states_fwd.argtypes = [c_void_p] * 6 + [c_int] * 5 + [c_void_p]
+    lib.mtn_fold_states_packed_fwd.argtypes = [c_void_p] * 5 + [c_int] * 6 + [c_void_p]
     lib.mtn_decoder_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]
     lib.mtn_cln_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p]
     lib.mtn_softmax_mask_fwd.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]
     lib.mtn_split_planes.argtypes = [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p]
     lib.mtn_si_snr_workspace_bytes.argtypes = [c_int, c_int]
     lib.mtn_si_snr_pit_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p, c_void_p]
+    lib.mtn_si_snr_workspace_bytes_n.argtypes = [c_int, c_int, c_int]
+    lib.mtn_si_snr_pit_n_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p,
+                                         c_int, c_void_p]
     lib.mtn_gn_partials_bytes.argtypes = [c_int, c_int, c_int]
     lib.mtn_gn_stats_fwd.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]
     lib.mtn_gn_apply_fwd.argtypes = [POINTER(GnApplyArgs), c_void_p]
@@ -128,10 +132,12 @@ def load():
     for name in EXPORTS:
         fn = getattr(lib, name, None)
         if fn is not None and name not in ("mtn_last_error_string", "mtn_abi_version", "mtn_si_snr_workspace_bytes",
+                                           "mtn_si_snr_workspace_bytes_n",
                                            "mtn_gn_partials_bytes", "mtn_sizeof_gemm_args", "mtn_sizeof_scan_args",
                                            "mtn_sizeof_gn_apply_args"):
             fn.restype = c_int
     lib.mtn_si_snr_workspace_bytes.restype = c_size_t
+    lib.mtn_si_snr_workspace_bytes_n.restype = c_size_t
     lib.mtn_gn_partials_bytes.restype = c_size_t
     _lib = lib
     return lib

@@ -74,6 +74,23 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) 
     }
 }
 
+// Wait of a warp that is a whole tile AHEAD of the one it waits for (the scan's helper warps): every failed try_wait
+// costs ~10 issue slots on a sub-partition that is short of them, and the default 64 ns back-off polled ~47 times per tile
+// (ncu, profiles/r02/scan_v7_pair2_ncu_summary.txt: 600 of the helper's 1 090 instructions per tile were this loop).
+// Sleeping `ns` per poll bounds that to a handful; the slack of the hand-off (two tiles) absorbs the later wake-up.
+__device__ __forceinline__ void mbar_wait_long_sleep(uint64_t* bar, uint32_t parity, uint32_t ns) {
+    uint32_t spins = 0;
+    uint64_t t0 = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        __nanosleep(ns);
+        if ((++spins & 0xFF) == 0) {
+            const uint64_t now = global_timer_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 2000000000ull) __trap();
+        }
+    }
+}
+
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");

@@ -1033,51 +1033,36 @@ static int launch_scan_tc(const mtn_scan_args* a, cudaStream_t stream) {
 
 }  // namespace mtn
 #include "mtn_scan_pair.cuh"
-#ifdef MTN_SCAN_DEV
-#include "mtn_scan_trio.cuh"   // measured and rejected: kept as a dev-build variant only
-#endif
 namespace mtn {
-
-// every measured shape except the widest fp32 one (L hparams, R = 32, two planes: the split mapping with tensor-core dt_proj wins by 4 %)
-static bool pair_wins(const mtn_scan_args* a) { return !(a->R > 16 && a->planes == 2); }
 
 template <int P, int R, int NDBL, typename ZT>
 static int dispatch_scan_variant(const mtn_scan_args* a, cudaStream_t s) {
     int variant = 0;
     if (const char* v = getenv("MTN_SCAN_VARIANT")) variant = atoi(v);
-#ifdef MTN_SCAN_DEV   // experiment variants of the pair mapping (timing-only ablations give WRONG results)
-    if (variant == 15) return launch_scan_pair<P, R, NDBL, ZT, true, false, 1>(a, s);
-    if (variant == 25) return launch_scan_pair<P, R, NDBL, ZT, true, false, 2>(a, s);
-    if (variant == 35) return launch_scan_pair<P, R, NDBL, ZT, true, false, 3>(a, s);
-    if (variant == 75) return launch_scan_pair<P, R, NDBL, ZT, true, false, 7>(a, s);
-    if (variant == 85) return launch_scan_pair<P, R, NDBL, ZT, true, false, 8>(a, s);
-    if (variant == 7 && a->dtp && a->y) return launch_scan_pair<P, R, NDBL, ZT, true, true>(a, s);  // tensor-core dt_proj
-    if (variant == 9 && a->y) return launch_scan_trio<P, R, NDBL, ZT>(a, s);   // recurrence / prep / post warp trios
-#endif
-    // v2 helper (mma.sync dt_proj, packed softplus, row-segment gate): 6; 61 / 62 (dev builds) add 1 / 2 state pairs per
-    // step on the FMA-pipe polynomial exp2
-#ifdef MTN_SCAN_DEV   // timing-only ablations of the v2 kernel (WRONG results)
-    if (variant == 63 && a->y) return launch_scan_pair2<P, R, NDBL, ZT, true, 0, false, 3>(a, s);   // helper: no dt_proj/softplus/gate
-    if (variant == 64 && a->y) return launch_scan_pair2<P, R, NDBL, ZT, true, 0, false, 4>(a, s);   // recurrence: no MUFU
-    if (variant == 67 && a->y) return launch_scan_pair2<P, R, NDBL, ZT, true, 0, false, 7>(a, s);   // both
-    if (variant == 66 && a->y) return launch_scan_pair2<P, R, NDBL, ZT, true, 0, false, 1>(a, s);   // helper: no dt_proj/softplus
-    if (variant == 65 && a->y) return launch_scan_pair2<P, R, NDBL, ZT, true, 0, false, 2>(a, s);   // helper: no gate
-#endif
-    if (variant == 6 || variant == 61 || variant == 62) {
-        if (!a->y) return launch_scan_pair2<P, R, NDBL, ZT, false>(a, s);
-#ifdef MTN_SCAN_DEV
-        if (variant == 61) return launch_scan_pair2<P, R, NDBL, ZT, true, 1>(a, s);
-        if (variant == 62) return launch_scan_pair2<P, R, NDBL, ZT, true, 2>(a, s);
-#endif
-        return launch_scan_pair2<P, R, NDBL, ZT, true>(a, s);
+#ifdef MTN_SCAN_DEV   // experiments on the pair kernel (dev builds of tools/devbuild.sh only)
+    if (a->y) {
+        switch (variant) {
+            case 61: return launch_scan_pair<P, R, NDBL, ZT, true, 1>(a, s);               // 1 state pair on the FMA-pipe exp2
+            case 62: return launch_scan_pair<P, R, NDBL, ZT, true, 2>(a, s);               // 2 state pairs
+            case 68: return launch_scan_pair<P, R, NDBL, ZT, true, 0, false, 32>(a, s);    // 64 ns helper poll (r02 start)
+            // timing-only ablations (WRONG results)
+            case 63: return launch_scan_pair<P, R, NDBL, ZT, true, 0, false, 3>(a, s);     // helper: no dt_proj/softplus/gate
+            case 64: return launch_scan_pair<P, R, NDBL, ZT, true, 0, false, 4>(a, s);     // recurrence: no MUFU
+            case 65: return launch_scan_pair<P, R, NDBL, ZT, true, 0, false, 2>(a, s);     // helper: no gate
+            case 66: return launch_scan_pair<P, R, NDBL, ZT, true, 0, false, 1>(a, s);     // helper: no dt_proj/softplus
+            case 67: return launch_scan_pair<P, R, NDBL, ZT, true, 0, false, 7>(a, s);     // 63 + 64
+            default: break;
+        }
     }
-    // Recurrence / helper warp pairs (mtn_scan_pair.cuh).  Measured on B200 (tools/scan_bench.py): faster
-    // than the split mapping for full passes; the summary pass (no y: nothing for the helper to take over) stays on the
-    // split mapping.  variant 5 forces it, variant 2/3 force the split mapping.
-    const bool pair_default = variant == 0 && a->y != nullptr && pair_wins(a);
-    if (variant == 5 || pair_default) {
-        if (!a->y) return launch_scan_pair<P, R, NDBL, ZT, false, false>(a, s);
-        return launch_scan_pair<P, R, NDBL, ZT, true, false>(a, s);
+#endif
+    // Recurrence / helper warp pairs (mtn_scan_pair.cuh) for every pass that writes y.  Measured on B200
+    // (tools/scan_bench.py, DESIGN.md 4.1, profiles/r02/scan_*.jsonl): faster than the split mapping at every shipped
+    // shape (S fp32 0.90 -> 0.82 ms, L fp32 2.00 -> 1.73, L bf16 3.29 -> 2.82).  The summary pass (no y: nothing for
+    // the helper to take over) measures the same in both mappings (0.72 ms) and stays on the split mapping.
+    // variant 5 / 6 force the pair kernel (also for summary passes), 2 / 3 the split mapping.
+    if (variant == 5 || variant == 6 || (variant == 0 && a->y != nullptr)) {
+        if (!a->y) return launch_scan_pair<P, R, NDBL, ZT, false>(a, s);
+        return launch_scan_pair<P, R, NDBL, ZT, true>(a, s);
     }
     if (a->dtp && (variant == 0 || variant == 3)) {  // split mapping, dt_proj on the tensor cores
         if (!a->y) return launch_scan_tc<P, R, NDBL, ZT, false>(a, s);

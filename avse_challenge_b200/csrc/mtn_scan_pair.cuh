@@ -5,47 +5,23 @@
 // the split mapping of mtn_scan.cu spends 150 issue slots per 32 channel-steps on a serial path with 3 shuffles per
 // step, so it runs at ~58 % of the XU floor.  Here the serial path is stripped to what depends on the state:
 //   * recurrence warp (lane = channel, all 16 states in registers): per step 2 private LDS (delta, u), 8 broadcast
-//     LDS.128 (B_t, C_t), 16 packed multiplies, 16 MUFU, 16 packed FMAs, a 4-op reduction and one STS of y: ~65 issue
+//     LDS.128 (B_t, C_t), 16 packed multiplies, 16 MUFU, 16 packed FMAs, a 4-op reduction and one STS of y: ~75 issue
 //     slots per 128 XU cycles, no shuffles, no global memory access, no conversions.
-//   * helper warp (lane = the same channel, but a whole 16-step tile at once, i.e. time-parallel work): dt_proj +
+//   * helper warp (the same 32 channels, but a whole 16-step tile at once, i.e. time-parallel work): dt_proj +
 //     softplus -> delta, bf16 planes -> fp32 u, written to a pair-private shared-memory slot two tiles ahead of the
-//     recurrence; afterwards gate (0.5 * silu(z), z read straight from global one tile ahead), hi/lo bf16 split and
-//     the global stores of y.  It also owns the TMA ring (duty rotates over the 4 helpers) and sum_delta.
+//     recurrence; afterwards gate (0.5 * silu(z)), hi/lo bf16 split and the global stores of y.  It also owns the
+//     TMA ring (duty rotates over the 4 helpers) and sum_delta.
 // The two warps of a pair share an SM sub-partition (warp w and w + 4), so the helper fills the issue slots the
 // recurrence warp leaves idle while it waits on the XU pipe.  Hand-offs are pair-private mbarriers (prepped / ydone);
 // only the TMA ring (u planes + [dt|B|C] rows) is shared by the CTA.  y overwrites delta in place in the slot.
+//
+// History (profiles/r01, profiles/r02): the first helper kept lane = channel for everything and needed
+// 72 issue slots per warp-step next to the recurrence warp's 75; the helper below needs ~30, and the kernel went from
+// issue-bound (XU 61 % busy) to XU-bound (81 % on the sub-partitions that hold two pairs).
 #pragma once
 
 namespace mtn {
 
-template <int P, int NDBL, bool TC, int RP>
-struct ScanSmemPair {
-    static constexpr int SLOTS = 3;
-    static constexpr int U_BYTES = P * SC_TT * SC_CH * 2;
-    static constexpr int NB = TC ? 2 * SC_NS : NDBL;                      // floats per staged row: [B | C] or [dt | B | C | pad]
-    static constexpr int D_BYTES = SC_TT * NB * 4;
-    static constexpr int DT_BYTES = TC ? 2 * RP * SC_TT * 2 : 0;          // [plane][k8][16 rows][8] bf16, UMMA canonical
-    static constexpr int STAGE_BYTES = U_BYTES + D_BYTES + DT_BYTES;
-    static constexpr int PAIR_SLOT_BYTES = 2 * SC_TT * 32 * 4;           // [delta -> y | u] x 16 rows x 32 lanes fp32
-    static constexpr int SLOT_BYTES = 4 * PAIR_SLOT_BYTES;
-    static constexpr int ZBUF_BYTES = 4 * SC_TT * 32 * 4;                 // per pair: silu(z) of one tile, [16][32] (fp32 or bf16)
-    static constexpr int WA_BYTES = TC ? 2 * RP * SC_CH * 2 : 0;          // [plane][k8][128 rows][8] bf16, UMMA canonical
-    static constexpr int BAR_BYTES = (2 * 4 + 2 * 4 * SLOTS + 4) * 8 + 16;
-    static constexpr int FIXED = 128 + SLOTS * SLOT_BYTES + ZBUF_BYTES + WA_BYTES + BAR_BYTES;
-    static constexpr int PER_CTA_MAX = 233472 / 2 - 1024;                 // two CTAs per SM
-    // tile j: TMA issued at helper iteration j-(STAGES-2), delta/u at j, recurrence ~j+1, refill at j+2
-    static constexpr int STAGES = (FIXED + 4 * STAGE_BYTES <= PER_CTA_MAX) ? 4 : 3;
-    static constexpr int TOTAL = FIXED + STAGES * STAGE_BYTES;
-    static_assert(STAGE_BYTES % 128 == 0 && U_BYTES % 128 == 0 && (U_BYTES + D_BYTES) % 128 == 0,
-                  "TMA destinations must stay 128-byte aligned");
-    static_assert(TOTAL <= PER_CTA_MAX, "two CTAs per SM must fit");
-};
-
-// per-thread asynchronous 4-byte global -> shared copy (LDGSTS): no register, no scoreboard entry, so the global
-// latency of the gate never blocks the helper's instruction stream (a plain LDG did, through scoreboard sharing).
-__device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gsrc) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
-}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
@@ -58,8 +34,8 @@ __device__ __forceinline__ void sts_f32_nofence(void* p, float v) {
 // One instruction stream serves both directions (with one per direction and role, the four unrolled tile bodies, 80 KB,
 // thrashed the instruction cache: 25 % of the warp samples were stall_no_inst): the slot row pointer and the [B | C] row
 // pointer step by signed strides, everything else has immediate offsets.
-// DS = slot row stride in floats (32: v1 helper, lane = channel; 36: v2 helper, whose 16-byte row-segment accesses need an
-// odd multiple of 16 bytes to stay bank-conflict free).  KP = state pairs per step whose decay factor is computed by the
+// DS = slot row stride in floats (36: the helper's 16-byte row-segment accesses need an odd multiple of 16 bytes to stay
+// bank-conflict free, and so do the rows this warp reads lane = channel).  KP = state pairs per step whose decay factor is computed by the
 // FMA-pipe polynomial ex2_poly2 instead of MUFU.EX2 (balances the XU against the FMA pipe once the helper is light).
 template <int S, int NB, int BOFF, bool WY, int ABL, bool RG = false, int DS = 32, int KP = 0>
 __device__ __forceinline__ void scan_pair_recur(const uint8_t* ring, float* slots, int stage_bytes, int u_bytes,
@@ -248,408 +224,9 @@ __device__ __forceinline__ void scan_pair_recur(const uint8_t* ring, float* slot
 }
 
 // --------------------------------------------------------------------------------------------------- helper warp
-// TC: delta_pre = dt . W_dt^T on the tensor cores, once per 16-step tile:
-//     D[128 channels (TMEM lanes), 16 steps (columns)] = W_dt[128, RP] (smem, K-major) x dt_tile[16, RP]^T
-// in split-bf16 form (hi/lo x hi/lo, fp32 accumulate in TMEM).  The dt operand planes are written by the x_proj GEMM
-// epilogue (MTN_EPI_XPROJ) and arrive through the TMA ring.  Helper warp w (warp 4 + w) owns TMEM lanes [32 w, +32) =
-// exactly its own channels, so one tcgen05.ld.32x32b.x16 hands every lane its channel's 16 pre-activations: no
-// shuffle, no dot products on the FMA pipe (R FMAs + R/4 LDS.128 per (step, channel) otherwise).
-template <int P, int R, int NDBL, typename ZT, bool WY, bool TC, int ABL, bool BAL = false>
-__device__ __forceinline__ void scan_pair_helper(uint8_t* ring, float* slots, uint8_t* zbuf_all, uint64_t* full_bar,
-                                                 uint64_t* empty_bar, uint64_t* prepped, uint64_t* ydone,
-                                                 uint64_t* dtfull, uint8_t* wa, uint32_t tmem_base,
-                                                 const ScanParams& p, int w, int lane, int ch0, int d, int b, int dir,
-                                                 int ntiles, int Lb, const CUtensorMap* mapU, const CUtensorMap* mapD,
-                                                 const CUtensorMap* mapT) {
-    constexpr int RP = R <= 16 ? 16 : 32;
-    using SM = ScanSmemPair<P, NDBL, TC, RP>;
-    constexpr int S = SM::STAGES, NSLOT = SM::SLOTS, NB = SM::NB;
-    constexpr bool ZF = sizeof(ZT) == 4;
-    constexpr int RW = TC ? 4 : R;                                // w_dt registers are only needed by the FMA form
-    const int L = p.L;
-    const size_t pd = size_t(dir) * p.di + d;
-    const int chl = w * 32 + lane;
-    float2 wdt2[RW / 2];
-    if (!TC) {
-        const float4* wp = reinterpret_cast<const float4*>(p.w_dt + pd * R);
-#pragma unroll
-        for (int q = 0; q < RW / 4; ++q) {
-            const float4 x = wp[q];
-            wdt2[2 * q] = make_float2(x.x, x.y);
-            wdt2[2 * q + 1] = make_float2(x.z, x.w);
-        }
-    }
-    const float bias = p.dt_bias[pd];
-    float sdl_sum = 0.f;
-    const size_t M = size_t(p.batch) * L;
-    const size_t y_plane = M * 2 * p.di;
-    const int ldy = 2 * p.di;                                     // y row stride, bf16 elements
-    // flush mapping: lane -> (row = lane / 4 (+ 8), 16-byte segment = 8 channels)
-    const int frow = lane >> 2, fseg = lane & 3;
-    __nv_bfloat16* yflush = p.y + size_t(dir) * p.di + (ch0 + w * 32 + fseg * 8);
-    // gate copies (4 bytes each): fp32 z: lane = channel, one row per copy; bf16 z: lane = (row parity, channel pair)
-    ZT* zbuf = reinterpret_cast<ZT*>(zbuf_all + w * (SC_TT * 32 * 4));
-    const int zc_row0 = ZF ? 0 : (lane >> 4);
-    const int zc_col = ZF ? lane : 2 * (lane & 15);
-    const ZT* zsrc = reinterpret_cast<const ZT*>(p.z) + p.z_col0 + ch0 + w * 32 + zc_col;
-    ZT* zdst = zbuf + zc_row0 * 32 + zc_col;
-    constexpr int ZROWS = ZF ? 1 : 2;                             // rows covered by one warp-wide copy
-    const uint32_t taddr = tmem_base + (uint32_t(32 * w) << 16);
-    auto tile_of = [&](int i) { return dir ? (ntiles - 1 - i) : i; };
-    auto issue_tile = [&](int i2) {
-        const int stg = i2 % S;
-        const int row0 = b * L + tile_of(i2) * SC_TT;
-        mbar_arrive_expect_tx(&full_bar[stg], SM::STAGE_BYTES);
-        uint8_t* dst = ring + stg * SM::STAGE_BYTES;
-        tma_load_3d(dst, mapU, &full_bar[stg], dir * p.di + ch0, row0, 0);
-        tma_load_2d(dst + SM::U_BYTES, mapD, &full_bar[stg], dir * p.n_dbl + (TC ? R : 0), row0);
-        if (TC) {
-            uint8_t* dt = dst + SM::U_BYTES + SM::D_BYTES;
-#pragma unroll
-            for (int c = 0; c < 2 * RP / 8; ++c)   // chunk c = plane * (RP/8) + k8 -> one [16 rows][16 B] slab each
-                tma_load_2d(dt + c * (SC_TT * 16), mapT, &full_bar[stg], dir * 2 * RP + c * 8, row0);
-        }
-    };
-    // one elected thread: D[buf] = W_dt x dt_tile(stage)^T, completion signalled on dtfull[buf]
-    auto issue_dt_mma = [&](int stg, int buf) {
-        constexpr uint32_t idesc = make_idesc_bf16(SC_CH, SC_TT);
-        tc_fence_after();
-        const uint32_t a0 = smem_u32(wa);
-        const uint32_t b0 = smem_u32(ring + stg * SM::STAGE_BYTES + SM::U_BYTES + SM::D_BYTES);
-        const uint32_t dcol = tmem_base + buf * SC_TT;
-        constexpr uint32_t A_SLAB = SC_CH * 16, B_SLAB = SC_TT * 16, A_PLANE = (RP / 8) * A_SLAB,
-                           B_PLANE = (RP / 8) * B_SLAB;
-#pragma unroll
-        for (int kk = 0; kk < RP / 16; ++kk) {
-            const uint64_t a_hi = make_smem_desc_nosw(a0 + 2 * kk * A_SLAB, A_SLAB, 128);
-            const uint64_t a_lo = make_smem_desc_nosw(a0 + A_PLANE + 2 * kk * A_SLAB, A_SLAB, 128);
-            const uint64_t b_hi = make_smem_desc_nosw(b0 + 2 * kk * B_SLAB, B_SLAB, 128);
-            const uint64_t b_lo = make_smem_desc_nosw(b0 + B_PLANE + 2 * kk * B_SLAB, B_SLAB, 128);
-            tc_mma_bf16(dcol, a_hi, b_hi, idesc, kk > 0 ? 1u : 0u);
-            tc_mma_bf16(dcol, a_lo, b_hi, idesc, 1u);
-            tc_mma_bf16(dcol, a_hi, b_lo, idesc, 1u);
-            tc_mma_bf16(dcol, a_lo, b_lo, idesc, 1u);
-        }
-        tc_commit(&dtfull[buf]);
-    };
-    if (w == 0) {
-        if (lane == 0) {
-#pragma unroll 1
-            for (int t = 0; t < S; ++t)
-                if (t < ntiles) issue_tile(t);
-        }
-        if (TC) {
-            mbar_wait(&full_bar[0], 0);
-            if (lane == 0) issue_dt_mma(0, 0);
-        }
-        __syncwarp();
-    }
-
-#pragma unroll 1
-    for (int k = 0; k < ntiles + 2; ++k) {
-        // ---- gate + store the tile the recurrence warp finished two hand-offs ago
-        const int pt = k - 2;
-        if (pt >= 0) {
-            const int sl = pt % NSLOT;
-            mbar_wait_sleep(&ydone[w * NSLOT + sl], uint32_t(pt / NSLOT) & 1u);
-            if (WY && !(ABL & 2)) {
-                const int t0 = tile_of(pt) * SC_TT;
-                const int nvalid = min(SC_TT, Lb - t0);
-                float* slot = slots + sl * (4 * 2 * SC_TT * 32) + w * (2 * SC_TT * 32);
-                const float* sy = slot + lane;
-                // the u half of the slot is dead now: stage the gated outputs there as bf16 [P][16 rows][32 ch]
-                uint16_t* stage = reinterpret_cast<uint16_t*>(slot + SC_TT * 32);
-                cp_async_wait_all();   // silu(z) of this tile, requested one iteration ago
-                __syncwarp();
-#pragma unroll 1
-                for (int g = 0; g < SC_TT; g += 8) {   // two passes of 8 rows keep the unrolled code small
-                    float yv[8], zv[8];
-#pragma unroll
-                    for (int r = 0; r < 8; ++r) {
-                        yv[r] = sy[(g + r) * 32];
-                        zv[r] = ldz(zbuf + (g + r) * 32 + lane);
-                    }
-#pragma unroll
-                    for (int r = 0; r < 8; ++r) {
-                        const float y = yv[r] * (0.5f * zv[r]);
-                        const uint32_t hi = f2bf_lo(y);
-                        sts_b16(stage + (g + r) * 32 + lane, hi);
-                        if (P == 2) sts_b16(stage + (SC_TT + g + r) * 32 + lane, f2bf_lo(y - __uint_as_float(hi << 16)));
-                    }
-                }
-                __syncwarp();
-                __nv_bfloat16* ytile = yflush + (size_t(b) * L + t0) * size_t(ldy);
-#pragma unroll
-                for (int pl = 0; pl < P; ++pl) {
-#pragma unroll
-                    for (int hh = 0; hh < 2; ++hh) {
-                        const int row = frow + 8 * hh;
-                        if (row < nvalid) {
-                            const uint4 v = *reinterpret_cast<const uint4*>(stage + (pl * SC_TT + row) * 32 + fseg * 8);
-                            *reinterpret_cast<uint4*>(ytile + pl * y_plane + size_t(row * ldy)) = v;
-                        }
-                    }
-                }
-            }
-        }
-        // ---- producer duty of this iteration (rotates over the four helpers): refill the ring stage of tile k-2 and
-        // start the dt_proj MMA of tile k+1
-        if ((k & 3) == w) {
-            const bool refill = pt >= 0 && pt + S < ntiles;
-            const bool mma = TC && k + 1 < ntiles;
-            if (pt >= 0 && (refill || mma)) {
-                // every recurrence warp is done with tile k-2; hence every helper finished tile k-2's inputs too (its
-                // hand-off preceded the recurrence), incl. the TMEM accumulator that MMA k+1 overwrites (tile k-3's)
-                mbar_wait_sleep(&empty_bar[pt % S], uint32_t(pt / S) & 1u);
-            }
-            if (refill && lane == 0) issue_tile(pt + S);
-            __syncwarp();
-        }
-        // ---- request silu(z) of the tile gated in the NEXT iteration (asynchronous copies into the pair's z buffer)
-        if (WY && !(ABL & 2) && k >= 1 && k - 1 < ntiles) {
-            const int t0 = tile_of(k - 1) * SC_TT;
-            const int nvalid = min(SC_TT, Lb - t0);
-            const ZT* zs = zsrc + (size_t(b) * L + t0 + zc_row0) * size_t(p.ldz);
-            const size_t zstep = size_t(ZROWS) * p.ldz;
-#pragma unroll
-            for (int r = 0; r < SC_TT; r += ZROWS) {
-                if (r + zc_row0 < nvalid) cp_async_4(zdst + r * 32, zs);
-                zs += zstep;
-            }
-        }
-        cp_async_commit();
-        // ---- delta and u of tile k
-        if (k < ntiles) {
-            const int stg = k % S, sl = k % NSLOT;
-            const int t0 = tile_of(k) * SC_TT;
-            const int nvalid = min(SC_TT, Lb - t0);
-            mbar_wait_sleep(&full_bar[stg], uint32_t(k / S) & 1u);
-            const uint8_t* st = ring + stg * SM::STAGE_BYTES;
-            const __nv_bfloat16* su = reinterpret_cast<const __nv_bfloat16*>(st) + chl;
-            const float* sd = reinterpret_cast<const float*>(st + SM::U_BYTES);
-            float* sdl = slots + sl * (4 * 2 * SC_TT * 32) + w * (2 * SC_TT * 32) + lane;
-            // Two passes of 8 rows, each written in lock step over its rows (all dot products, then every softplus stage
-            // for the 8 rows at once): ~8 independent chains in the helper's instruction stream, half the unrolled code.
-            if (TC) {
-                mbar_wait(&dtfull[k & 3], uint32_t(k >> 2) & 1u);
-                tc_fence_after();
-            }
-#pragma unroll 1
-            for (int g = 0; g < SC_TT; g += 8) {
-                float pre[8];
-                if (TC) {
-                    uint32_t raw[8];
-                    tmem_ld_x8(taddr + (k & 3) * SC_TT + g, raw);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int r = 0; r < 8; ++r) pre[r] = bias + __uint_as_float(raw[r]);
-                } else {
-                    float2 pa[8], pb[8];
-#pragma unroll
-                    for (int r = 0; r < 8; ++r) {
-                        pa[r] = make_float2(bias, 0.f);
-                        pb[r] = make_float2(0.f, 0.f);
-                    }
-#pragma unroll
-                    for (int q = 0; q < ((ABL & 8) ? 1 : RW / 4); ++q) {
-#pragma unroll
-                        for (int r = 0; r < 8; ++r) {
-                            const float4 x = *reinterpret_cast<const float4*>(sd + (g + r) * NB + 4 * q);
-                            pa[r] = __ffma2_rn(make_float2(x.x, x.y), wdt2[2 * q], pa[r]);
-                            pb[r] = __ffma2_rn(make_float2(x.z, x.w), wdt2[2 * q + 1], pb[r]);
-                        }
-                    }
-#pragma unroll
-                    for (int r = 0; r < 8; ++r) {
-                        const float2 pab = __fadd2_rn(pa[r], pb[r]);
-                        pre[r] = pab.x + pab.y;
-                    }
-                }
-                float ev[8], qv[8];
-#pragma unroll
-                for (int r = 0; r < 8; ++r) {
-                    ev[r] = (ABL & 1) ? 0.5f : ex2_approx(-1.4426950408889634f * fabsf(pre[r]));
-                    qv[r] = 0.0051261021414032125f;
-                }
-                constexpr float SPC[8] = {-0.02907406467853027f, 0.07751608674076167f, -0.13602247622393474f,
-                                          0.19076880735651539f,  -0.24835398988480129f, 0.3331812170752912f,
-                                          -0.49999444976340335f, 0.9999999659255092f};
-#pragma unroll
-                for (int c = 0; c < ((ABL & 1) ? 1 : 8); ++c) {
-#pragma unroll
-                    for (int r = 0; r < 8; ++r) qv[r] = fmaf(qv[r], ev[r], SPC[c]);
-                }
-#pragma unroll
-                for (int r = 0; r < 8; ++r) {
-                    float dl = fmaf(qv[r], ev[r], fmaxf(pre[r], 0.f));   // softplus_1mufu, see mtn_scan.cu
-                    dl = (g + r < nvalid) ? dl : 0.f;  // rows past the utterance end: exp2(0) = 1, delta*u = 0 -> state unchanged
-                    float uval = bf16_bits_to_float(su + (g + r) * SC_CH);
-                    if (P == 2) uval += bf16_bits_to_float(su + (SC_TT + g + r) * SC_CH);
-                    sdl_sum += dl;
-                    sdl[(g + r) * 32] = dl;
-                    sdl[(SC_TT + g + r) * 32] = uval;
-                }
-            }
-            if (TC) tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&prepped[w * NSLOT + sl]);
-        }
-        // ---- second half of the producer duty, after this warp's own hand-off so that it never delays it: start the
-        // dt_proj MMA of tile k+1 (its operands were requested S-2 iterations ago, or in the prologue)
-        if (TC && (k & 3) == w && k + 1 < ntiles) {
-            const int tl = k + 1;
-            mbar_wait_sleep(&full_bar[tl % S], uint32_t(tl / S) & 1u);
-            if (lane == 0) issue_dt_mma(tl % S, tl & 3);
-            __syncwarp();
-        }
-    }
-    if (p.sum_delta) p.sum_delta[(size_t(dir) * p.batch + b) * p.di + d] = sdl_sum;
-}
-
-template <int P, int R, int NDBL, typename ZT, bool WY, bool TC, int ABL, bool RG>
-__global__ void __launch_bounds__(256, 2)
-scan_kernel_pair(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUtensorMap mapD,
-                 const __grid_constant__ CUtensorMap mapT, const ScanParams p) {
-    constexpr int RP = R <= 16 ? 16 : 32;
-    using SM = ScanSmemPair<P, NDBL, TC, RP>;
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
-    uint8_t* ring = smem;
-    float* slots = reinterpret_cast<float*>(smem + SM::STAGES * SM::STAGE_BYTES);
-    uint8_t* zbuf = smem + SM::STAGES * SM::STAGE_BYTES + SM::SLOTS * SM::SLOT_BYTES;
-    uint8_t* wa = zbuf + SM::ZBUF_BYTES;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(wa + SM::WA_BYTES);
-    uint64_t* empty_bar = full_bar + 4;
-    uint64_t* prepped = empty_bar + 4;
-    uint64_t* ydone = prepped + 4 * SM::SLOTS;
-    uint64_t* dtfull = ydone + 4 * SM::SLOTS;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dtfull + 4);
-
-    const int tid = threadIdx.x;
-    const int warp = tid >> 5, lane = tid & 31;
-    const int nchb = p.di / SC_CH;
-    const int ch0 = (blockIdx.x % nchb) * SC_CH;
-    const int dir = p.dir0 + blockIdx.x / nchb;
-    const int b = blockIdx.y;
-    if (tid == 0) {
-        tma_prefetch_desc(&mapU);
-        tma_prefetch_desc(&mapD);
-        if (TC) tma_prefetch_desc(&mapT);
-        for (int s = 0; s < SM::STAGES; ++s) {
-            mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 4);
-        }
-        for (int s = 0; s < 4 * SM::SLOTS; ++s) {
-            mbar_init(&prepped[s], 1);
-            mbar_init(&ydone[s], 1);
-        }
-        for (int s = 0; s < 4; ++s) mbar_init(&dtfull[s], 1);
-        fence_barrier_init();
-    }
-    uint32_t tmem_base = 0;
-    if (TC) {
-        if (warp == 0) tmem_alloc(tmem_slot, 64);
-        if (tid < SC_CH) {
-            // A operand: row m = channel ch0 + m, W_dt split into hi | lo bf16 planes, K-major canonical (no swizzle)
-            const int m = tid;
-            const size_t pdm = size_t(dir) * p.di + ch0 + m;
-#pragma unroll
-            for (int k8 = 0; k8 < RP / 8; ++k8) {
-                uint32_t hi[4], lo[4];
-#pragma unroll
-                for (int e2 = 0; e2 < 4; ++e2) {
-                    const int k = k8 * 8 + 2 * e2;
-                    const float v0 = k < R ? p.w_dt[pdm * R + k] : 0.f;
-                    const float v1 = k + 1 < R ? p.w_dt[pdm * R + k + 1] : 0.f;
-                    const uint32_t h0 = f2bf_lo(v0), h1 = f2bf_lo(v1);
-                    const uint32_t l0 = f2bf_lo(v0 - __uint_as_float(h0 << 16)), l1 = f2bf_lo(v1 - __uint_as_float(h1 << 16));
-                    hi[e2] = h0 | (h1 << 16);
-                    lo[e2] = l0 | (l1 << 16);
-                }
-                *reinterpret_cast<uint4*>(wa + k8 * (SC_CH * 16) + m * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                *reinterpret_cast<uint4*>(wa + (RP / 8 + k8) * (SC_CH * 16) + m * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-            }
-            fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
-        }
-        tc_fence_before();
-    }
-    __syncthreads();
-    if (TC) {
-        tc_fence_after();
-        tmem_base = *tmem_slot;
-    }
-    const int Lb = (b == p.batch - 1) ? p.L_last : p.L;
-    const int ntiles = (Lb + SC_TT - 1) / SC_TT;
-    const int w = warp & 3;
-    const int d = ch0 + w * 32 + lane;
-    if (warp < 4)
-        scan_pair_recur<SM::STAGES, SM::NB, TC ? 0 : R, WY, ABL, RG>(ring, slots, SM::STAGE_BYTES, SM::U_BYTES, full_bar,
-                                                                    empty_bar, prepped, ydone, p, w, lane, d, b, dir, ntiles,
-                                                                    Lb);
-    else
-        scan_pair_helper<P, R, NDBL, ZT, WY, TC, ABL>(ring, slots, zbuf, full_bar, empty_bar, prepped, ydone, dtfull, wa,
-                                                      tmem_base, p, w, lane, ch0, d, b, dir, ntiles, Lb, &mapU, &mapD,
-                                                      &mapT);
-    if (TC) {
-        tc_fence_before();
-        __syncthreads();
-        if (warp == 0) {
-            tc_fence_after();
-            tmem_dealloc(tmem_base, 64);
-        }
-    }
-}
-
-template <int P, int R, int NDBL, typename ZT, bool WY, bool TC, int ABL = 0, bool RG = false>
-static int launch_scan_pair(const mtn_scan_args* a, cudaStream_t stream) {
-    // short ragged sequences (many of them: DPMamba's inter model) take the instantiation with the ragged-tile path
-    if (!RG && !TC && ABL == 0 && WY && a->L <= 128 && (a->L % SC_TT) != 0 && a->L_last == 0)
-        return launch_scan_pair<P, R, NDBL, ZT, WY, TC, ABL, true>(a, stream);
-    constexpr int RP = R <= 16 ? 16 : 32;
-    using SM = ScanSmemPair<P, NDBL, TC, RP>;
-    const uint64_t M = uint64_t(a->batch) * a->L;
-    CUtensorMap mapU, mapD, mapT;
-    {
-        uint64_t dims[3] = {uint64_t(2) * a->di, M, uint64_t(P)};
-        uint64_t str[2] = {uint64_t(2) * a->di * 2, M * 2 * a->di * 2};
-        uint32_t box[3] = {uint32_t(SC_CH), SC_TT, uint32_t(P)};
-        if (!encode_tmap(&mapU, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, a->u, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE))
-            return MTN_ECUDA;
-    }
-    {
-        uint64_t dims[2] = {uint64_t(a->ld_dbl), M};
-        uint64_t str[1] = {uint64_t(a->ld_dbl) * 4};
-        uint32_t box[2] = {uint32_t(SM::NB), SC_TT};   // TC: [B | C] only (dt comes from TMEM)
-        if (!encode_tmap(&mapD, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, a->dbl, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE))
-            return MTN_ECUDA;
-    }
-    if (TC) {
-        uint64_t dims[2] = {uint64_t(4 * RP), M};           // [dir][plane][RP] per row
-        uint64_t str[1] = {uint64_t(4 * RP) * 2};
-        uint32_t box[2] = {8, SC_TT};                       // one 16-byte K chunk x 16 rows = one canonical slab
-        if (!encode_tmap(&mapT, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->dtp, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE))
-            return MTN_ECUDA;
-    } else {
-        mapT = mapD;
-    }
-    ScanParams p = make_scan_params(a);
-    auto kern = scan_kernel_pair<P, R, NDBL, ZT, WY, TC, ABL, RG>;
-    static std::atomic<unsigned long long> attr_done{0};   // per template instantiation, one bit per device
-    if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(kern), SM::TOTAL, attr_done, "scan(pair)")) return rc;
-    dim3 grid(p.ndirs * (a->di / SC_CH), a->batch, 1);
-    kern<<<grid, 256, SM::TOTAL, stream>>>(mapU, mapD, mapT, p);
-    MTN_CUDA_LAUNCH_CHECK("scan(pair)");
-    return MTN_OK;
-}
-
-
-// =====================================================================================================================
-// v2 helper: the same recurrence warp, a helper stripped to ~a third of its instructions.
-//
-// The v1 helper keeps lane = channel for everything and so pays scalar instructions per (step, channel): R FMAs of
-// dt_proj, 13 for softplus, 16-bit loads / stores for u and y, one 4-byte cp.async per gate value -- 72 issue slots per
-// warp-step next to the recurrence warp's 75, on an SM sub-partition that is issue bound.  None of that work cares which
-// lane owns which element, so v2 picks per phase the layout that makes it cheap:
+// None of the helper's work cares which lane owns which element, so every phase uses the layout that makes it cheap (a
+// lane = channel helper pays scalar instructions per (step, channel): R FMAs of dt_proj, 13 for softplus, 16-bit loads /
+// stores for u and y, one 4-byte cp.async per gate value):
 //   * dt_proj: delta_pre[16 steps, 32 channels] = dt[16, R] x W_dt[32, R]^T as warp-level mma.sync.m16n8k16 (bf16 hi/lo
 //     split of both operands, 4 passes, fp32 accumulate, dt_bias as the C operand): 16 HMMA per tile instead of
 //     224 LDS/FFMA2/FADD.  The accumulator fragment leaves every lane 2 rows x 8 channels; the column -> channel
@@ -664,7 +241,7 @@ static int launch_scan_pair(const mtn_scan_args* a, cudaStream_t stream) {
 constexpr int P2_DS = 36;
 
 template <int P, int NDBL>
-struct ScanSmemPair2 {
+struct ScanSmemPair {
     static constexpr int SLOTS = 3;
     static constexpr int U_BYTES = P * SC_TT * SC_CH * 2;
     static constexpr int NB = NDBL;
@@ -739,11 +316,11 @@ __device__ __forceinline__ void splitn_bf16(float x0, float x1, uint32_t (&pl)[N
 // operands AND its result to bf16, selective_scan_interface.py:174-176,187).
 // ABL (dev builds, timing only, WRONG results): bit 0 skips the MMA + softplus, bit 1 the gate / store.
 template <int P, int R, int NDBL, typename ZT, bool WY, int ABL = 0>
-__device__ __forceinline__ void scan_pair_helper2(uint8_t* ring, float* slots, uint8_t* zbuf_all, uint64_t* full_bar,
+__device__ __forceinline__ void scan_pair_helper(uint8_t* ring, float* slots, uint8_t* zbuf_all, uint64_t* full_bar,
                                                   uint64_t* empty_bar, uint64_t* prepped, uint64_t* ydone,
                                                   const ScanParams& p, int w, int lane, int ch0, int b, int dir,
                                                   int ntiles, int Lb, const CUtensorMap* mapU, const CUtensorMap* mapD) {
-    using SM = ScanSmemPair2<P, NDBL>;
+    using SM = ScanSmemPair<P, NDBL>;
     constexpr int S = SM::STAGES, NSLOT = SM::SLOTS, NB = SM::NB, DS = P2_DS;
     constexpr int PLANE = SC_TT * DS, PAIRF = 2 * PLANE;
     constexpr int KS = (R + 15) / 16;                            // k-steps of the dt_proj MMA (K = 16 each)
@@ -808,7 +385,7 @@ __device__ __forceinline__ void scan_pair_helper2(uint8_t* ring, float* slots, u
         const int pt = k - 2;
         if (pt >= 0) {
             const int sl = pt % NSLOT;
-            mbar_wait_sleep(&ydone[w * NSLOT + sl], uint32_t(pt / NSLOT) & 1u);
+            mbar_wait_long_sleep(&ydone[w * NSLOT + sl], uint32_t(pt / NSLOT) & 1u, (ABL & 32) ? 64u : 500u);
             if (WY && !(ABL & 2)) {
                 const int t0 = tile_of(pt) * SC_TT;
                 const int nvalid = min(SC_TT, Lb - t0);
@@ -836,7 +413,7 @@ __device__ __forceinline__ void scan_pair_helper2(uint8_t* ring, float* slots, u
                         uint32_t hi[4], lo[4];
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            // y * (0.5 * silu(z)), the same two roundings as the v1 helper
+                            // y * (0.5 * silu(z)): two roundings (0.5 * z is exact)
                             const float2 gz = __fmul2_rn(make_float2(zf[2 * q], zf[2 * q + 1]), make_float2(0.5f, 0.5f));
                             const float2 o = __fmul2_rn(make_float2(yv[2 * q], yv[2 * q + 1]), gz);
                             if (P == 2) split2_bf16(o.x, o.y, hi[q], lo[q]);
@@ -982,8 +559,8 @@ __device__ __forceinline__ void scan_pair_helper2(uint8_t* ring, float* slots, u
 
 template <int P, int R, int NDBL, typename ZT, bool WY, bool RG, int KP, int ABL>
 __global__ void __launch_bounds__(256, 2)
-scan_kernel_pair2(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUtensorMap mapD, const ScanParams p) {
-    using SM = ScanSmemPair2<P, NDBL>;
+scan_kernel_pair(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUtensorMap mapD, const ScanParams p) {
+    using SM = ScanSmemPair<P, NDBL>;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
     uint8_t* ring = smem;
@@ -1022,20 +599,20 @@ scan_kernel_pair2(const __grid_constant__ CUtensorMap mapU, const __grid_constan
                                                                     empty_bar, prepped, ydone, p, w, lane,
                                                                     ch0 + w * 32 + lane, b, dir, ntiles, Lb);
     else
-        scan_pair_helper2<P, R, NDBL, ZT, WY, ABL>(ring, slots, zbuf, full_bar, empty_bar, prepped, ydone, p, w, lane, ch0, b,
+        scan_pair_helper<P, R, NDBL, ZT, WY, ABL>(ring, slots, zbuf, full_bar, empty_bar, prepped, ydone, p, w, lane, ch0, b,
                                               dir, ntiles, Lb, &mapU, &mapD);
 }
 
 template <int P, int R, int NDBL, typename ZT, bool WY, int KP = 0, bool RG = false, int ABL = 0>
-static int launch_scan_pair2(const mtn_scan_args* a, cudaStream_t stream) {
+static int launch_scan_pair(const mtn_scan_args* a, cudaStream_t stream) {
     // short ragged sequences (many of them: DPMamba's inter model) take the instantiation with the ragged-tile path
     if (!RG && KP == 0 && ABL == 0 && WY && a->L <= 128 && (a->L % SC_TT) != 0 && a->L_last == 0)
-        return launch_scan_pair2<P, R, NDBL, ZT, WY, KP, true>(a, stream);
-    using SM = ScanSmemPair2<P, NDBL>;
+        return launch_scan_pair<P, R, NDBL, ZT, WY, KP, true>(a, stream);
+    using SM = ScanSmemPair<P, NDBL>;
     MTN_REQUIRE((reinterpret_cast<uintptr_t>(a->z) & 15) == 0 && (a->ldz * sizeof(ZT)) % 16 == 0 &&
                     (a->z_col0 * sizeof(ZT)) % 16 == 0,
-                "scan(pair2): the gate block must be 16-byte aligned (z=%p ldz=%d z_col0=%d)", a->z, a->ldz, a->z_col0);
-    MTN_REQUIRE(!a->y || (reinterpret_cast<uintptr_t>(a->y) & 15) == 0, "scan(pair2): y must be 16-byte aligned");
+                "scan(pair): the gate block must be 16-byte aligned (z=%p ldz=%d z_col0=%d)", a->z, a->ldz, a->z_col0);
+    MTN_REQUIRE(!a->y || (reinterpret_cast<uintptr_t>(a->y) & 15) == 0, "scan(pair): y must be 16-byte aligned");
     const uint64_t M = uint64_t(a->batch) * a->L;
     CUtensorMap mapU, mapD;
     {
@@ -1053,12 +630,12 @@ static int launch_scan_pair2(const mtn_scan_args* a, cudaStream_t stream) {
             return MTN_ECUDA;
     }
     ScanParams p = make_scan_params(a);
-    auto kern = scan_kernel_pair2<P, R, NDBL, ZT, WY, RG, KP, ABL>;
+    auto kern = scan_kernel_pair<P, R, NDBL, ZT, WY, RG, KP, ABL>;
     static std::atomic<unsigned long long> attr_done{0};   // per template instantiation, one bit per device
-    if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(kern), SM::TOTAL, attr_done, "scan(pair2)")) return rc;
+    if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(kern), SM::TOTAL, attr_done, "scan(pair)")) return rc;
     dim3 grid(p.ndirs * (a->di / SC_CH), a->batch, 1);
     kern<<<grid, 256, SM::TOTAL, stream>>>(mapU, mapD, p);
-    MTN_CUDA_LAUNCH_CHECK("scan(pair2)");
+    MTN_CUDA_LAUNCH_CHECK("scan(pair)");
     return MTN_OK;
 }
 

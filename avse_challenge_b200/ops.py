@@ -185,6 +185,18 @@ def fold_states(h_end, sum_delta, A2, g0, n_out, *, h0=None, want_final=False, d
     return h_in, h_final
 
 
+def fold_states_packed(pack, A2, W, cmax, di, g0, n_out, *, h_in=None, h0=None, h_final=None, dir_mask=3):
+    """``fold_states`` over the all-gathered packed summaries (see ``mtn_fold_states_packed_fwd``): ``pack`` fp32
+    ``[W, 2*cmax*di*17]`` -> ``h_in [2, n_out, di, 16]`` (written into the given buffer when passed)."""
+    _req_cuda(pack, A2, h0, h_in, h_final)
+    assert pack.dtype == torch.float32 and pack.is_contiguous() and pack.numel() == W * 2 * cmax * di * 17
+    if h_in is None:
+        h_in = torch.empty((2, n_out, di, 16), dtype=torch.float32, device=pack.device)
+    check(_lib.load().mtn_fold_states_packed_fwd(ptr(pack), ptr(A2), ptr(h0), ptr(h_in), ptr(h_final), W, cmax, di, g0,
+                                                 n_out, dir_mask, _stream()), "mtn_fold_states_packed_fwd")
+    return h_in
+
+
 def decoder(sep, w_dec, batch, T, L, N, n_spk=2, est=None, frames=None, tail=None):
     """``tail`` (fp32 [batch, n_spk, 8], in/out): streaming overlap-add carry (then ``T`` must be ``8 * L``)."""
     _req_cuda(sep, w_dec, tail)

@@ -10,7 +10,8 @@ training, ``Mamba-TasNet/train_wsj0mix.py:718``); both modes here are B200-side 
                                 depthwise conv and the scan is per-token.  Per layer: (1) conv halo = 3 frames of
                                 ``xs`` from each neighbour; (2) scan = reduce-then-scan: a summary pass gives every
                                 chunk's transfer operator ``h -> exp2(A2*sum_delta)*h + h_end``, the summaries are
-                                exchanged (all-gather, or NCCL send/recv of the folded state along the rank chain),
+                                exchanged (ONE all-gather of a packed record per layer, or NCCL send/recv of the folded
+                                state along the rank chain),
                                 ``mtn_fold_states_fwd`` composes them into the state entering each chunk, a second
                                 scan pass seeded with those states writes the output.  The sub-chunks are what fills
                                 148 SMs when the batch is 1 (a rank's chunk alone would occupy 8 CTAs).
@@ -51,14 +52,16 @@ class Comm:
         self.rank = dist.get_rank(group) if self.on else 0
         self.world = dist.get_world_size(group) if self.on else 1
 
-    def all_gather(self, t: torch.Tensor) -> torch.Tensor:
-        """``[*shape]`` on every rank -> ``[world, *shape]`` (same shape required on every rank)."""
+    def all_gather(self, t: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """``[*shape]`` on every rank -> ``[world, *shape]`` (same shape required on every rank).  ``out``: a
+        pre-allocated contiguous ``[world, *shape]`` receive buffer (no allocation on the hot path)."""
         t = t.contiguous()
         if self.world == 1:
             return t.unsqueeze(0)
-        out = torch.empty(self.world * t.numel(), dtype=t.dtype, device=t.device)
-        dist.all_gather_into_tensor(out, t.reshape(-1), group=self.group)
-        return out.view((self.world,) + tuple(t.shape))
+        if out is None:
+            out = torch.empty((self.world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out.view(-1), t.reshape(-1), group=self.group)
+        return out
 
     def send(self, t: torch.Tensor, dst: int):
         dist.send(t.contiguous(), dst, group=self.group)
@@ -134,16 +137,19 @@ def make_seq_plan(L: int, world: int, sub_chunks: int) -> SeqPlan:
 
 # ------------------------------------------------------------------------------------------------ CUDA backend
 class CudaSeqBackend:
-    """The per-rank kernel calls of one sequence-parallel forward (all through the C ABI, see ``ops.py``)."""
+    """The per-rank kernel calls of one sequence-parallel forward (all through the C ABI, see ``ops.py``).
+
+    All activation buffers of a (local length, plan) shape are allocated once and reused (``_Shape``, LRU-bounded), so a
+    forward allocates nothing -- which is also what makes it capturable in a CUDA graph together with its collectives."""
 
     def __init__(self, hp: HParams, sds: dict, device, mode: str = "fp32"):
         from . import _lib, ops
-        from .engine import MODES, PackedWeights
+        from .engine import MODES, PackedWeights, resolve_device
         if not torch.cuda.is_available():
             raise _lib.MtnError("CudaSeqBackend needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         _lib.load()
         self.ops, self._lib = ops, _lib
-        self.hp, self.mode, self.device = hp, mode, torch.device(device)
+        self.hp, self.mode, self.device = hp, mode, resolve_device(device)
         self.P = MODES[mode]["planes"]
         self.xz_dt = torch.bfloat16 if MODES[mode]["xz_bf16"] else torch.float32
         with torch.cuda.device(self.device):
@@ -151,34 +157,69 @@ class CudaSeqBackend:
         self.n_layers = hp.n_mamba
         self.di, self.enc_dim = hp.d_inner, hp.enc_dim
         self.tc_dt = hp.dt_rank >= 32 and mode == "fp32"    # same rule as SeparatorEngine
+        self.cmax, self.world = None, 1
+        self._shapes = LRUDict()
+
+    def set_plan(self, cmax: int, world: int):
+        """Sub-chunks per rank (padded) and the world size: fixes the layout of the packed summary record."""
+        self.cmax, self.world = cmax, world
 
     # ---- chunk set-up: encoder + cLN + bottleneck on this rank's samples
     def begin(self, mix_slice: torch.Tensor, Lr: int, Ls: int, chunks: int, last_len: int):
         hp, P, dev = self.hp, self.P, self.device
         N, D, di = hp.enc_dim, hp.d_model, hp.d_inner
         nd = self.w.n_dbl
-        self.Lr, self.Ls, self.C, self.last_len = Lr, Ls, chunks, last_len
-        rows = chunks * Ls                                   # >= Lr; rows beyond Lr are never valid scan steps
-        e = lambda shape, dt: torch.zeros(shape, dtype=dt, device=dev)
         T_loc = mix_slice.shape[1]
         assert hp.frames(T_loc) == Lr, (T_loc, Lr)
-        self.mix = e((1, (T_loc + 7) // 8 * 8), torch.float32)
-        self.mix[:, :T_loc].copy_(mix_slice.to(dev, non_blocking=True))
-        self.T_loc = T_loc
-        self.mix_w = e((Lr, N), torch.float32)
-        self.yn = e((P, Lr, N), torch.bfloat16)
-        self.h = e((Lr, D), torch.float32)
-        self.res = e((Lr, D), torch.float32)
-        self.xn = e((P, Lr, D), torch.bfloat16)
-        self.xz = e((rows, 2 * di), self.xz_dt)
-        self.u = e((P, rows, 2 * di), torch.bfloat16)
-        self.dbl = e((rows, 2 * nd), torch.float32)
-        self.dtp = e((rows, 2, 2, self.ops.rp_for(hp.dt_rank)), torch.bfloat16)
-        self.y = e((P, rows, 2 * di), torch.bfloat16)
-        self.sep_full = e((Lr + 1, hp.n_spk * N), torch.float32)   # row 0 = last frame of the previous rank
+        cmax = self.cmax if self.cmax is not None else chunks
+        key = (T_loc, Lr, Ls, chunks, last_len, cmax, self.world)
+        ws = self._shapes.get(key)
+        if ws is None:
+            rows = chunks * Ls                                   # >= Lr; rows beyond Lr are never valid scan steps
+            z = lambda shape, dt=torch.float32: torch.zeros(shape, dtype=dt, device=dev)
+            ws = {}
+            ws["mix"] = z((1, (T_loc + 7) // 8 * 8))
+            ws["mix_w"] = z((Lr, N))
+            ws["yn"] = z((P, Lr, N), torch.bfloat16)
+            ws["h"], ws["res"] = z((Lr, D)), z((Lr, D))
+            ws["xn"] = z((P, Lr, D), torch.bfloat16)
+            ws["xz"] = z((rows, 2 * di), self.xz_dt)
+            ws["u"] = z((P, rows, 2 * di), torch.bfloat16)
+            ws["dbl"] = z((rows, 2 * nd))
+            ws["dtp"] = z((rows, 2, 2, self.ops.rp_for(hp.dt_rank)), torch.bfloat16)
+            ws["y"] = z((P, rows, 2 * di), torch.bfloat16)
+            ws["sep_full"] = z((Lr + 1, hp.n_spk * N))         # row 0 = last frame of the previous rank
+            ws["edges"] = z((2, 3, di))
+            ws["edges_all"] = z((self.world, 2, 3, di))
+            # packed chunk summaries: [h_end (2, cmax, di, 16) | sum_delta (2, cmax, di)]; entries past `chunks` stay zero
+            # (identity operators).  The scan writes [2][batch][di][..] with batch = chunks, so it can write the record
+            # in place only when chunks == cmax; otherwise it writes compact buffers that are copied in.
+            rec = 2 * cmax * di * 17
+            ws["pack"] = z((rec,))
+            ws["pack_all"] = z((self.world, rec))
+            ws["h_end"] = ws["pack"][: 2 * cmax * di * 16].view(2, cmax, di, 16)
+            ws["sdl"] = ws["pack"][2 * cmax * di * 16:].view(2, cmax, di)
+            if chunks != cmax:
+                ws["h_end_c"], ws["sdl_c"] = z((2, chunks, di, 16)), z((2, chunks, di))
+            ws["h_in"] = z((2, chunks, di, 16))
+            ws["row"] = z((hp.n_spk * N,))
+            ws["rows_all"] = z((self.world, hp.n_spk * N))
+            Lx = Lr + 1
+            ws["frames"] = z((Lx, hp.n_spk, 16))
+            ws["est"] = z((1, (Lx - 1) * 8 + 16, hp.n_spk))
+            self._shapes[key] = ws
+        self.ws = ws
+        self.Lr, self.Ls, self.C, self.last_len, self.T_loc = Lr, Ls, chunks, last_len, T_loc
+        for k in ("mix", "mix_w", "yn", "h", "res", "xn", "xz", "u", "dbl", "dtp", "y", "sep_full"):
+            setattr(self, k, ws[k])
+        self.mix[:, :T_loc].copy_(mix_slice, non_blocking=True)
         o, w = self.ops, self.w
         o.encoder_cln(self.mix, w.w_enc, w.gamma, w.beta, P, mix_w=self.mix_w, yn=self.yn, T=T_loc)
         o.gemm(self.yn, w.w_bot, Lr, D, N, out=self.h)
+
+    def gather_buffer(self, name: str) -> torch.Tensor:
+        """Pre-allocated ``[world, ...]`` receive buffer of the collective called ``name``."""
+        return self.ws[name]
 
     # ---- per layer
     def pre(self, i: int):
@@ -189,14 +230,16 @@ class CudaSeqBackend:
 
     def xs_edges(self) -> torch.Tensor:
         """First and last three ``xs`` rows of this rank's chunk, fp32 ``[2, 3, di]`` (what the neighbours need)."""
-        di = self.di
-        return torch.stack([self.xz[:3, :di], self.xz[self.Lr - 3:self.Lr, :di]]).float().contiguous()
+        di, e = self.di, self.ws["edges"]
+        e[0].copy_(self.xz[:3, :di])
+        e[1].copy_(self.xz[self.Lr - 3:self.Lr, :di])
+        return e
 
     def conv_xproj(self, i: int, halo_lo: Optional[torch.Tensor], halo_hi: Optional[torch.Tensor]):
         lw, o, hp = self.w.layers[i], self.ops, self.hp
         di, nd = hp.d_inner, self.w.n_dbl
-        lo = halo_lo.reshape(1, 3, di).contiguous() if halo_lo is not None else None
-        hi = halo_hi.reshape(1, 3, di).contiguous() if halo_hi is not None else None
+        lo = halo_lo.reshape(1, 3, di) if halo_lo is not None else None      # contiguous slices of the gather buffer
+        hi = halo_hi.reshape(1, 3, di) if halo_hi is not None else None
         o.conv_silu(self.xz, lw["conv_w"], lw["conv_b"], 1, self.Lr, di, self.P, u=self.u, halo_lo=lo, halo_hi=hi)
         if self.tc_dt:
             o.gemm(self.u, lw["w_x"], self.Lr, nd, di, out=self.dbl, groups=2, out_group_stride=nd,
@@ -211,11 +254,26 @@ class CudaSeqBackend:
 
     def scan_summary(self, i: int):
         """Summary pass: ``(h_end [2, C, di, 16], sum_delta [2, C, di])`` of this rank's sub-chunks, h_in = 0."""
-        di = self.di
-        h_end = torch.zeros((2, self.C, di, 16), dtype=torch.float32, device=self.device)
-        sdl = torch.zeros((2, self.C, di), dtype=torch.float32, device=self.device)
+        ws = self.ws
+        if "h_end_c" in ws:
+            h_end, sdl = ws["h_end_c"], ws["sdl_c"]
+        else:
+            h_end, sdl = ws["h_end"], ws["sdl"]
         self._scan(i, h_out=h_end, sum_delta=sdl, summary_only=True)
         return h_end, sdl
+
+    def scan_summary_packed(self, i: int) -> torch.Tensor:
+        """Summary pass into this rank's packed record ``[2*cmax*di*17]`` (one all-gather moves it)."""
+        ws = self.ws
+        h_end, sdl = self.scan_summary(i)
+        if "h_end_c" in ws:
+            ws["h_end"][:, :self.C].copy_(h_end)
+            ws["sdl"][:, :self.C].copy_(sdl)
+        return ws["pack"]
+
+    def fold_packed(self, i: int, pack_all: torch.Tensor, g0: int, n_out: int) -> torch.Tensor:
+        return self.ops.fold_states_packed(pack_all, self.w.layers[i]["A2"], self.world, self.cmax, self.di, g0, n_out,
+                                           h_in=self.ws["h_in"])
 
     def fold(self, i: int, h_end: torch.Tensor, sdl: torch.Tensor, g0: int, n_out: int, h0=None, want_final=False,
              dir_mask: int = 3):
@@ -237,7 +295,8 @@ class CudaSeqBackend:
                epilogue=self._lib.EPI_MASK, epi_param=hp.enc_dim, aux=self.mix_w)
 
     def sep_last_row(self) -> torch.Tensor:
-        return self.sep_full[self.Lr].clone()
+        self.ws["row"].copy_(self.sep_full[self.Lr])
+        return self.ws["row"]
 
     def set_sep_halo(self, row: Optional[torch.Tensor]):
         if row is None:
@@ -251,7 +310,8 @@ class CudaSeqBackend:
         hp = self.hp
         Lx = self.Lr + 1
         T_x = (Lx - 1) * 8 + 16
-        est = self.ops.decoder(self.sep_full, self.w.w_dec, 1, T_x, Lx, hp.enc_dim, hp.n_spk)
+        est = self.ops.decoder(self.sep_full, self.w.w_dec, 1, T_x, Lx, hp.enc_dim, hp.n_spk, est=self.ws["est"],
+                               frames=self.ws["frames"])
         return est[0]
 
 
@@ -260,8 +320,12 @@ class SequenceParallelSeparator:
     """``forward(mix [1, T]) -> est [1, T, n_spk]`` with time sharded over the ranks of ``group``.
 
     ``mix`` must be the same (replicated) tensor on every rank; the result is assembled on every rank.
-    ``exchange``: ``"allgather"`` (default: one all-gather of the chunk summaries per layer) or ``"sendrecv"``
-    (the folded state is handed down the rank chain with point-to-point send/recv; same numbers)."""
+    ``forward_local(mix_local, T)`` is the sharded form: rank r passes only the samples ``input_range(T)`` it owns and
+    gets back the samples ``output_range(T)`` of the estimate -- no rank ever holds the whole recording (this is what an
+    end-to-end pipeline with host buffers should call: every rank copies 1/world of the audio in and out).
+    ``exchange``: ``"allgather"`` (default: the conv edges and ONE packed record of chunk summaries per layer) or
+    ``"sendrecv"`` (the folded state is handed down the rank chain with point-to-point send/recv; same numbers).
+    Collectives per forward (allgather mode): 2 per layer + 1 (decoder seam); ``collectives_per_forward`` reports it."""
 
     # sub_chunks = 74: every chunk is 2 * d_inner / 32 independent warp pairs for the scan (32 for S / M, 64 for L) and a
     # B200 holds 148 SMs x 8 pairs = 1 184 of them, so 74 chunks are exactly 2 (S) or 4 (L) full waves; 64 chunks left the
@@ -276,76 +340,135 @@ class SequenceParallelSeparator:
         self.hp, self.sub_chunks, self.exchange = hp, sub_chunks, exchange
         self.comm = Comm(group)
         self.be = backend if backend is not None else CudaSeqBackend(hp, sds, device, mode)
-        # On a single rank there is no collective in the path, so the whole chunked forward replays as one CUDA graph
-        # per length.  That is also the low-latency plan for ONE short utterance: the scan's serial chain is sub_chunks
-        # times shorter than in the batch plan (4 s @ 8 kHz, S: 9.0 ms -> 2.1 ms at 16 sub-chunks).
-        self.use_graph = use_graph and backend is None
-        self._graphs = LRUDict()   # one whole-forward graph (with its private buffers) per recording length, LRU-bounded
+        # The whole chunked forward -- collectives included (NCCL >= 2.9 is capturable) -- replays as one CUDA graph per
+        # length.  On one rank that is also the low-latency plan for ONE short utterance: the scan's serial chain is
+        # sub_chunks times shorter than in the batch plan (4 s @ 8 kHz, S: 9.0 ms -> 2.1 ms at 16 sub-chunks).
+        # The point-to-point chain (exchange="sendrecv") stays eager when world > 1.
+        self.use_graph = use_graph and backend is None and (self.comm.world == 1 or exchange == "allgather")
+        self._graphs = LRUDict()   # one whole-forward graph (with its static input / output) per recording length
+        self.graph_failed = None   # set to the error text if a multi-rank capture was refused (the driver then runs eagerly)
+
+    # ---- geometry
+    def plan(self, T: int) -> SeqPlan:
+        return make_seq_plan(self.hp.frames(T), self.comm.world, self.sub_chunks)
+
+    def input_range(self, T: int, rank: Optional[int] = None) -> Tuple[int, int]:
+        """Samples ``[s0, s1)`` of the recording that rank ``rank`` encodes (its frames plus the 8-sample frame overlap)."""
+        f0, f1 = self.plan(T).ranges[self.comm.rank if rank is None else rank]
+        return 8 * f0, 8 * f1 + 8
+
+    def output_range(self, T: int, rank: Optional[int] = None) -> Tuple[int, int]:
+        """Samples ``[o0, o1)`` of the estimate that rank ``rank`` finalises (clipped to T: pad / trim of the reference)."""
+        r = self.comm.rank if rank is None else rank
+        f0, f1 = self.plan(T).ranges[r]
+        hi = 8 * f1 + (8 if r == self.comm.world - 1 else 0)
+        return min(8 * f0, T), (T if r == self.comm.world - 1 else min(hi, T))
+
+    @property
+    def collectives_per_forward(self) -> int:
+        if self.comm.world == 1:
+            return 0
+        per_layer = 2 if self.exchange == "allgather" else 5      # edges + packed summaries | edges + 2 sends + 2 recvs
+        return self.hp.n_mamba * per_layer + 1
+
+    # ---- public API
+    @torch.no_grad()
+    def forward_local(self, mix_local: torch.Tensor, T: int) -> torch.Tensor:
+        """``mix_local`` [1, s1 - s0] = this rank's ``input_range(T)`` of the recording -> ``[o1 - o0, n_spk]`` = this
+        rank's ``output_range(T)`` of the estimate."""
+        s0, s1 = self.input_range(T)
+        if mix_local.dim() != 2 or mix_local.shape[0] != 1 or mix_local.shape[1] != s1 - s0:
+            raise ValueError(f"rank {self.comm.rank} owns samples [{s0}, {s1}) of a {T}-sample recording: expected "
+                             f"[1, {s1 - s0}], got {tuple(mix_local.shape)}")
+        if not (self.use_graph and mix_local.is_cuda and self.graph_failed is None):
+            return self._forward_local(mix_local, T)
+        ent = self._graphs.get(T)
+        if ent is None:
+            static_in = mix_local.clone()
+            out = self._forward_local(static_in, T)      # eager first: workspaces, kernel attributes, shape checks
+            torch.cuda.current_stream().synchronize()
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    static_out = self._forward_local(static_in, T)
+            except Exception as e:                       # pragma: no cover - depends on the NCCL / driver build
+                if self.comm.world == 1:
+                    raise
+                self.graph_failed = f"{type(e).__name__}: {e}"
+                torch.cuda.synchronize()
+                return out
+            ent = self._graphs[T] = (g, static_in, static_out)
+        g, static_in, static_out = ent
+        static_in.copy_(mix_local, non_blocking=True)
+        g.replay()
+        return static_out.clone()
 
     @torch.no_grad()
     def forward(self, mix: torch.Tensor) -> torch.Tensor:
         if mix.dim() != 2 or mix.shape[0] != 1:
             raise ValueError("sequence-parallel mode separates one recording: mix must be [1, T]")
-        if not (self.use_graph and self.comm.world == 1 and mix.is_cuda):
-            return self._forward(mix)
         T = mix.shape[1]
-        ent = self._graphs.get(T)
-        if ent is None:
-            static_in = mix.clone()
-            self._forward(static_in)                     # eager first: workspaces, kernel attributes, shape checks
-            torch.cuda.current_stream().synchronize()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                static_out = self._forward(static_in)
-            ent = self._graphs[T] = (g, static_in, static_out)
-        g, static_in, static_out = ent
-        static_in.copy_(mix, non_blocking=True)
-        g.replay()
-        return static_out.clone()
+        s0, s1 = self.input_range(T)
+        piece = self.forward_local(mix[:, s0:s1].contiguous(), T)
+        W = self.comm.world
+        if W == 1:
+            return piece.unsqueeze(0)
+        ranges = [self.output_range(T, q) for q in range(W)]
+        nmax = max(b - a for a, b in ranges)
+        pad = piece.new_zeros((nmax, piece.shape[1]))
+        pad[: piece.shape[0]] = piece
+        allp = self.comm.all_gather(pad)                                     # result gather (replicated output only)
+        return torch.cat([allp[q, : b - a] for q, (a, b) in enumerate(ranges)], dim=0).unsqueeze(0)
 
-    def _forward(self, mix: torch.Tensor) -> torch.Tensor:
+    __call__ = forward
+
+    def _gather(self, t: torch.Tensor, name: str) -> torch.Tensor:
+        buf = self.be.gather_buffer(name) if hasattr(self.be, "gather_buffer") else None
+        return self.comm.all_gather(t, out=buf)
+
+    def _forward_local(self, mix_local: torch.Tensor, T: int) -> torch.Tensor:
         hp, be, comm = self.hp, self.be, self.comm
         r, W = comm.rank, comm.world
-        T = mix.shape[1]
-        L = hp.frames(T)
-        plan = make_seq_plan(L, W, self.sub_chunks)
+        plan = self.plan(T)
         f0, f1 = plan.ranges[r]
         Lr, C, cmax = f1 - f0, plan.chunks[r], plan.cmax
-        be.begin(mix[:, 8 * f0: 8 * f1 + 8], Lr, plan.Ls, C, plan.last_len[r])
+        packed = self.exchange == "allgather" and hasattr(be, "scan_summary_packed")
+        if hasattr(be, "set_plan"):
+            be.set_plan(cmax, W)
+        be.begin(mix_local, Lr, plan.Ls, C, plan.last_len[r])
         for i in range(be.n_layers):
             be.pre(i)
-            edges = comm.all_gather(be.xs_edges())                           # [W, 2, 3, di]
+            edges = self._gather(be.xs_edges(), "edges_all")                 # [W, 2, 3, di]
             be.conv_xproj(i, edges[r - 1, 1] if r > 0 else None, edges[r + 1, 0] if r < W - 1 else None)
-            h_end, sdl = be.scan_summary(i)                                  # [2, C, di, 16], [2, C, di]
-            if self.exchange == "allgather":
+            if packed:
+                pack_all = self._gather(be.scan_summary_packed(i), "pack_all")   # [W, 2*cmax*di*17]: ONE collective
+                h_in = be.fold_packed(i, pack_all, r * cmax, C)
+            elif self.exchange == "allgather":
+                h_end, sdl = be.scan_summary(i)                              # [2, C, di, 16], [2, C, di]
                 he = h_end.new_zeros((2, cmax) + tuple(h_end.shape[2:]))
                 sd = sdl.new_zeros((2, cmax) + tuple(sdl.shape[2:]))
                 he[:, :C], sd[:, :C] = h_end, sdl                            # padding chunks = identity operators
-                he_all = comm.all_gather(he).transpose(0, 1).reshape((2, W * cmax) + tuple(h_end.shape[2:]))
-                sd_all = comm.all_gather(sd).transpose(0, 1).reshape((2, W * cmax) + tuple(sdl.shape[2:]))
-                h_in, _ = be.fold(i, he_all, sd_all, r * cmax, C)
+                rec = comm.all_gather(torch.cat([he.reshape(-1), sd.reshape(-1)]))   # [W, rec]: one collective
+                n_h = he.numel()
+                he_all = rec[:, :n_h].reshape((W, 2, cmax) + tuple(h_end.shape[2:])).transpose(0, 1)
+                sd_all = rec[:, n_h:].reshape((W, 2, cmax) + tuple(sdl.shape[2:])).transpose(0, 1)
+                h_in, _ = be.fold(i, he_all.reshape((2, W * cmax) + tuple(h_end.shape[2:])),
+                                  sd_all.reshape((2, W * cmax) + tuple(sdl.shape[2:])), r * cmax, C)
             else:
+                h_end, sdl = be.scan_summary(i)
                 h_in = self._fold_chain(i, h_end, sdl, C)
             be.scan_seeded(i, h_in)
             be.out_proj(i)
         be.head()
-        rows = comm.all_gather(be.sep_last_row())                            # [W, n_spk*N]
+        rows = self._gather(be.sep_last_row(), "rows_all")                   # [W, n_spk*N]
         be.set_sep_halo(rows[r - 1] if r > 0 else None)
         est_x = be.decode()                                                  # samples 8*(f0-1) .. 8*(f1+1)
-        n_keep = 8 * Lr + (8 if r == W - 1 else 0)
-        piece = est_x[8: 8 + n_keep]
-        nmax = 8 * max(b - a for a, b in plan.ranges) + 8
-        pad = piece.new_zeros((nmax, piece.shape[1]))
-        pad[:n_keep] = piece
-        allp = comm.all_gather(pad)                                          # result gather
-        parts = [allp[q, : 8 * (b - a) + (8 if q == W - 1 else 0)] for q, (a, b) in enumerate(plan.ranges)]
-        est = torch.cat(parts, dim=0)                                        # T_est = 8*L + 8 samples
-        out = est.new_zeros((T, est.shape[1]))                               # pad / trim (train_wsj0mix.py:104-109)
-        n = min(T, est.shape[0])
-        out[:n] = est[:n]
-        return out.unsqueeze(0)
-
-    __call__ = forward
+        o0, o1 = self.output_range(T)
+        n_keep = 8 * Lr + (8 if r == W - 1 else 0)                           # what this rank's frames finalise
+        piece = est_x[8: 8 + min(n_keep, o1 - o0)]
+        if piece.shape[0] < o1 - o0:                                         # T beyond the last frame: zero pad
+            piece = torch.cat([piece, piece.new_zeros((o1 - o0 - piece.shape[0], piece.shape[1]))], dim=0)
+        return piece
 
     def _fold_chain(self, i, h_end, sdl, C):
         """Point-to-point variant: rank r receives the state entering its chunk from its neighbour, folds its own

@@ -11,6 +11,10 @@ BASELINE config 2: S hparams, 32 x 4 s @ 8 kHz per GPU, fp32 mode.  N > 1: one p
 its own batch (utterances are independent: batch sharding, no collective on the data path; weak scaling).
 
 One JSON line on rank 0:
+  also       (default workload only; --no-also skips it) the two multi-GPU splits BASELINE.json names, a few steps each,
+             in the same launch: config 3 (L, bf16 mode, global batch 256 sharded over the ranks: strong scaling) and
+             config 5 (one 10-minute 16 kHz recording, sequence-parallel over the ranks) -- each with value / e2e /
+             ms_per_step, a parity record measured in this run across the ranks that ran it, and the collectives per forward
   value      whole-job audio-s/s, inputs resident in HBM, CUDA-graph replay, device-timed, max over ranks
   e2e        same metric through the public API with HOST buffers (pinned H2D of the mixtures + D2H of the estimates
              inside the timed region)
@@ -18,7 +22,9 @@ One JSON line on rank 0:
              with CUDA events on the launch stream, vs MEASURED_PEAKS.json hbm_gbs
   cpu_baseline  the oracle port of the reference CPU path (torch loop selective_scan_ref), bounded sample, N=1 only
 --impl reference times that CPU path alone (the reference is Python and needs /root/reference + third-party
-packages that are absent on the GPU box; the oracle port is the same algorithm, see oracle/restate.py).
+packages that are absent on the GPU box; the oracle port is the same algorithm, see oracle/restate.py).  Its
+config.workload names the BOUNDED SAMPLE it really timed (a CPU forward of the full 32 x 4 s batch takes minutes per
+step); config.sample_of names the workload the sample was cut from.
 """
 from __future__ import annotations
 
@@ -67,6 +73,8 @@ def parse():
     ap.add_argument("--sub-chunks", type=int, default=74,
                     help="longform: time sub-chunks per GPU (74 x 32 warp pairs = two full waves of a 148-SM GPU for S hparams)")
     ap.add_argument("--exchange", default="allgather", choices=["allgather", "sendrecv"])
+    ap.add_argument("--no-also", action="store_true", help="default workload: skip the config-3 / config-5 side runs")
+    ap.add_argument("--also-steps", type=int, default=3, help="timed steps of each side run")
     a = ap.parse_args()
     explicit = {x.split("=")[0] for x in sys.argv[1:] if x.startswith("--")}
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -166,7 +174,7 @@ def cpu_reference_throughput(hparams: str, sample_rate: int, steps: int, warmup:
         t, s = run(seconds)
         times.append(t)
     dt = sum(times) / len(times)
-    return {"value": s / dt, "unit": UNIT, "cores": cores, "kind": "port",
+    return {"value": s / dt, "unit": UNIT, "cores": cores, "kind": "port", "sample_seconds": seconds,
             "sample": f"1 utterance x {seconds:g} s @ {sample_rate} Hz, {hparams} hparams, fp32, torch {torch.get_num_threads()} threads, "
                       f"{len(times)} timed run(s) of {dt:.2f} s"}, dt
 
@@ -176,11 +184,17 @@ def run_reference_arm(a):
     if rank != 0:
         return
     base, dt = cpu_reference_throughput(a.hparams, a.sample_rate, a.steps, a.warmup, budget_s=150.0, causal=a.causal, model=a.model)
+    cfg = workload_config(a, a.gpus)
+    # say what was really timed: a bounded sample of the workload (one short utterance), not the batch the GPU arm runs
+    cfg["sample_of"] = cfg["workload"]
+    cfg["workload"] = f"BOUNDED SAMPLE ({base['sample']}) of: {cfg['sample_of']}"
+    cfg["batch_per_gpu"], cfg["global_batch"], cfg["seconds"] = 1, 1, base["sample_seconds"]
+    cfg["parallelism"] = f"CPU, torch with {base['cores']} threads, no GPU"
     line = {
         "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": a.gpus,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": scaling_kind(a),
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(a, a.gpus),
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
         "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -256,23 +270,97 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)", {}
 
 
-def run_b200_arm(a):
-    import torch
-    import torch.distributed as dist
+def scan_source_hash() -> str:
+    """Hash of the sources the scan kernel is compiled from: a committed DRAM-traffic figure (tools/scan_traffic.py) is
+    only quoted while it belongs to this code."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("mtn_scan.cu", "mtn_scan_pair.cuh", "mtn_ptx.cuh"):
+        with open(os.path.join(ROOT, "avse_challenge_b200", "csrc", f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+def measured_traffic(key: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one scan launch of this workload, from the ncu capture that
+    tools/scan_traffic.py wrote to profiles/scan_traffic.json -- or None when no capture of THIS kernel source exists."""
+    tp = os.path.join(ROOT, "profiles", "scan_traffic.json")
+    try:
+        tj = json.load(open(tp))
+    except Exception:
+        return None, "no profiles/scan_traffic.json"
+    if tj.get("source_hash") != scan_source_hash():
+        return None, "stale: profiles/scan_traffic.json was captured for another revision of the scan sources"
+    ent = tj.get("launches", {}).get(key)
+    if ent is None:
+        return None, f"no capture of {key}"
+    return int(ent["dram_bytes_per_launch"]), ent.get("source", "tools/scan_traffic.py")
+
+
+class Ctx:
+    """Process-group plumbing shared by the timed arms of one bench.py process."""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback for the product path)"
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, *vals):
+        t = self.torch.tensor(list(vals), dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return t.tolist()
+
+    def gather(self, t):
+        """[*shape] on every rank -> [world, *shape] on every rank."""
+        if self.world == 1:
+            return t.unsqueeze(0)
+        out = self.torch.empty((self.world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+        self.dist.all_gather_into_tensor(out.view(-1), t.contiguous().view(-1))
+        return out
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def timed(ctx, fn, steps, warmup):
+    """`warmup` untimed calls, then exactly `steps` calls between CUDA events on the launch stream, barrier + synchronize on
+    both sides; returns the max over ranks of the elapsed ms."""
+    torch = ctx.torch
+    for _ in range(warmup):
+        fn()
+    ctx.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    ctx.barrier()
+    return e0.elapsed_time(e1)
+
+
+def measure_batch(a, ctx, steps, warmup, cpu_baseline=True, parity=False, sampler=None):
+    """One batch-sharded workload (configs 2 / 3 / 4 / custom): every rank separates its own `a.batch` utterances."""
+    torch = ctx.torch
     from avse_challenge_b200 import CONFIGS, init_state_dicts, synth_mixture
     from avse_challenge_b200.engine import SeparatorEngine
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback for the product path)"
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-
+    rank, world, dev = ctx.rank, ctx.world, ctx.dev
     T = int(round(a.seconds * a.sample_rate)) // 8 * 8
     if a.model == "dpmamba":
         from avse_challenge_b200 import DP_CONFIGS, init_dp_state_dicts
@@ -299,29 +387,31 @@ def run_b200_arm(a):
     audio_s_per_step = a.batch * T / a.sample_rate
 
     cpu_base = None
-    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+    if cpu_baseline and rank == 0 and world == 1 and not a.no_cpu_baseline:
         cpu_base, _ = cpu_reference_throughput(a.hparams, a.sample_rate, steps=1, warmup=0, budget_s=30.0, causal=a.causal, model=a.model)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    sampler = ClockSampler(local) if rank == 0 else None
+    # ---- parity record of this run: the SAME two utterances on every rank -> identical results across the GPUs, and
+    # inside the full batch == run alone (utterances are independent, so any difference is a kernel / sharding bug)
+    par = None
+    if parity:
+        pmix, _ = synth_mixture(2, T, a.sample_rate, seed=4321)
+        alone = eng.forward(pmix.to(dev))
+        ws0 = eng.workspace(a.batch, T)
+        ws0.mix[:, :T].copy_(mix_cpu.to(dev))
+        ws0.mix[:2, :T].copy_(pmix.to(dev))
+        inside = eng.forward_into_workspace(a.batch, T)[:2].clone()
+        rms = alone.pow(2).mean().sqrt().clamp(min=1e-30)
+        d_batch = ((inside - alone).abs().max() / rms).item()
+        allr = ctx.gather(alone)
+        d_ranks = ((allr - allr[0:1]).abs().max() / rms).item()
+        par = {"max_abs_over_rms": max(d_batch, d_ranks), "across_ranks": d_ranks, "batch_vs_alone": d_batch, "world": world,
+               "check": "the same 2 utterances separated by every rank's engine, compared across the ranks and, on each "
+                        "rank, inside the full batch against run alone"}
 
     # ---- device-resident timing (value): inputs already in HBM, graph replay
     ws = eng.workspace(a.batch, T)
     ws.mix[:, :T].copy_(mix_cpu.to(dev))
-    for _ in range(max(3, a.warmup)):
-        eng.forward_into_workspace(a.batch, T)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(a.steps):
-        eng.forward_into_workspace(a.batch, T)
-    e1.record()
-    barrier()
-    ms_total = e0.elapsed_time(e1)
+    ms_total = timed(ctx, lambda: eng.forward_into_workspace(a.batch, T), steps, max(3, warmup))
 
     # ---- end-to-end through the public API with host buffers
     pin_in = mix_cpu.pin_memory()
@@ -333,91 +423,61 @@ def run_b200_arm(a):
         est = eng.forward(dmix)
         pin_out.copy_(est, non_blocking=True)
 
-    for _ in range(3):
-        e2e_step()
-    barrier()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record()
-    for _ in range(a.steps):
-        e2e_step()
-    f1.record()
-    barrier()
-    ms_e2e = f0.elapsed_time(f1)
+    ms_e2e = timed(ctx, e2e_step, steps, 3)
 
     # ---- per-kernel timing in situ (CUDA events around every launch, eager mode), for the roofline
-    prof = eng.profile_ops(a.batch, T, steps=max(2, min(a.steps, 5)))
+    prof = eng.profile_ops(a.batch, T, steps=max(1, min(steps, 5)))
     clocks = sampler.stop() if sampler else None
-
-    t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, ms_e2e = t.tolist()
-
-    if rank == 0:
-        peak, peak_src, peaks = load_peaks()
-        scan_ms = prof["scan"]["ms"]
-        alg = scan_algorithmic_bytes(hp, 1, scan_tokens, a.mode, 2 if hp.bidirectional else 1)
-        achieved = alg / (scan_ms * 1e-3) / 1e9
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "scan_traffic.json")
-        if os.path.exists(tp):
-            try:
-                tj = json.load(open(tp))
-                key = f"{a.hparams}_b{a.batch}_{a.mode}" + ("" if hp.bidirectional else "_causal") + ("_dp" if a.model == "dpmamba" else "")
-                traffic = tj.get(key, {}).get("dram_bytes_per_launch")
-                if traffic is None:   # measured bytes per token of the same hparams / mode, scaled to this launch
-                    per_tok = tj.get("per_token", {}).get(f"{a.hparams}_{a.mode}", {}).get("bytes")
-                    if per_tok is not None:
-                        traffic = int(per_tok * scan_tokens * (1.0 if hp.bidirectional else 0.5))
-            except Exception:
-                traffic = None
-        sm_mhz = (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
-        n_exp = (2 if hp.bidirectional else 1) * scan_tokens * hp.d_inner * hp.d_state
-        mufu_ms = n_exp / (148 * 16 * sm_mhz * 1e6) * 1e3
-        step_ms = ms_total / a.steps
-        total_prof = sum(v["ms_per_forward"] for v in prof.values())
-        line = {
-            "metric": METRIC, "value": audio_s_per_step * world / (step_ms * 1e-3), "unit": UNIT, "n_gpus": world,
-            "steps": a.steps, "warmup": max(3, a.warmup), "ms_per_step": step_ms, "higher_is_better": True,
-            "scaling": scaling_kind(a), "vs_baseline": None, "dtype": "f32" if a.mode == "fp32" else "bf16",
-            "data": "synthetic", "config": workload_config(a, world),
-            "e2e": {"value": audio_s_per_step * world / (ms_e2e / a.steps * 1e-3), "unit": UNIT,
-                    "h2d_bytes_per_step": a.batch * T * 4, "d2h_bytes_per_step": a.batch * T * hp.n_spk * 4,
-                    "ms_per_step": ms_e2e / a.steps},
-            "gpu_launches": a.steps * sum(v["launches"] for v in prof.values()) + a.steps,  # +1: decoder = 2 kernels
-            "launches_per_step": sum(v["launches"] for v in prof.values()) + 1,
-            "roofline": {"kernel": "mtn::scan_kernel_pair / scan_kernel (selective scan, both directions per launch)", "bound": "hbm",
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "peak_source": peak_src, "traffic": traffic, "algorithmic_bytes_per_launch": alg,
-                         "ms_per_launch": scan_ms, "launches_per_step": prof["scan"]["launches"],
-                         "share_of_step": prof["scan"]["ms_per_forward"] / total_prof,
-                         "mufu_bound_ms": mufu_ms, "mufu_frac": mufu_ms / scan_ms},
-            "kernels_ms_per_step": {k: round(v["ms_per_forward"], 4) for k, v in sorted(prof.items())},
-            "clocks": clocks,
-        }
-        if cpu_base is not None:
-            line["cpu_baseline"] = cpu_base
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    ms_total, ms_e2e = ctx.max_over_ranks(ms_total, ms_e2e)
+    del eng, ws, dmix
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    peak, peak_src, peaks = load_peaks()
+    scan_ms = prof["scan"]["ms"]
+    alg = scan_algorithmic_bytes(hp, 1, scan_tokens, a.mode, 2 if hp.bidirectional else 1)
+    achieved = alg / (scan_ms * 1e-3) / 1e9
+    tkey = f"{a.hparams}_b{a.batch}_L{L}_{a.mode}" + ("" if hp.bidirectional else "_causal") + ("_dp" if a.model == "dpmamba" else "")
+    traffic, traffic_src = measured_traffic(tkey)
+    sm_mhz = (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
+    n_exp = (2 if hp.bidirectional else 1) * scan_tokens * hp.d_inner * hp.d_state
+    mufu_ms = n_exp / (148 * 16 * sm_mhz * 1e6) * 1e3
+    step_ms = ms_total / steps
+    total_prof = sum(v["ms_per_forward"] for v in prof.values())
+    line = {
+        "metric": METRIC, "value": audio_s_per_step * world / (step_ms * 1e-3), "unit": UNIT, "n_gpus": world,
+        "steps": steps, "warmup": max(3, warmup), "ms_per_step": step_ms, "higher_is_better": True,
+        "scaling": scaling_kind(a), "vs_baseline": None, "dtype": "f32" if a.mode == "fp32" else "bf16",
+        "data": "synthetic", "config": workload_config(a, world),
+        "e2e": {"value": audio_s_per_step * world / (ms_e2e / steps * 1e-3), "unit": UNIT,
+                "h2d_bytes_per_step": a.batch * T * 4, "d2h_bytes_per_step": a.batch * T * hp.n_spk * 4,
+                "ms_per_step": ms_e2e / steps},
+        "gpu_launches": steps * sum(v["launches"] for v in prof.values()) + steps,  # +1: decoder = 2 kernels
+        "launches_per_step": sum(v["launches"] for v in prof.values()) + 1,
+        "roofline": {"kernel": "mtn::scan_kernel_pair (selective scan, both directions per launch)", "bound": "hbm",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "peak_source": peak_src, "traffic": traffic, "traffic_source": traffic_src,
+                     "algorithmic_bytes_per_launch": alg,
+                     "ms_per_launch": scan_ms, "launches_per_step": prof["scan"]["launches"],
+                     "share_of_step": prof["scan"]["ms_per_forward"] / total_prof,
+                     "mufu_bound_ms": mufu_ms, "mufu_frac": mufu_ms / scan_ms},
+        "kernels_ms_per_step": {k: round(v["ms_per_forward"], 4) for k, v in sorted(prof.items())},
+        "clocks": clocks,
+    }
+    if par is not None:
+        line["parity"] = par
+        line["collectives_per_forward"] = 0
+    if cpu_base is not None:
+        line["cpu_baseline"] = cpu_base
+    return line
 
 
-def run_longform_arm(a):
+def measure_longform(a, ctx, steps, warmup, cpu_baseline=True, parity=False, sampler=None):
     """BASELINE config 5: one long recording, sequence-parallel over the ranks (strong scaling)."""
-    import torch
-    import torch.distributed as dist
+    torch = ctx.torch
     from avse_challenge_b200 import CONFIGS, init_state_dicts, synth_mixture
     from avse_challenge_b200.parallel import SequenceParallelSeparator
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback for the product path)"
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+    rank, world, dev = ctx.rank, ctx.world, ctx.dev
     hp = CONFIGS[a.hparams]
     T = int(round(a.seconds * a.sample_rate)) // 8 * 8
     sds = init_state_dicts(hp, 1234)
@@ -425,78 +485,125 @@ def run_longform_arm(a):
     reps = -(-T // mix_cpu.shape[1])
     mix_cpu = mix_cpu.repeat(1, reps)[:, :T].contiguous()            # 30 s of synthetic speech tiled to length
     sp = SequenceParallelSeparator(hp, sds, device=dev, mode=a.mode, sub_chunks=a.sub_chunks, exchange=a.exchange,
-                                   use_graph=not a.no_graph)   # graph replay on a single rank only (no collective then)
+                                   use_graph=not a.no_graph)
     cpu_base = None
-    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+    if cpu_baseline and rank == 0 and world == 1 and not a.no_cpu_baseline:
         cpu_base, _ = cpu_reference_throughput(a.hparams, a.sample_rate, steps=1, warmup=0, budget_s=30.0, causal=a.causal, model=a.model)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    # ---- parity record of this run: a short clip through the sequence-parallel path on all ranks (collectives and all)
+    # against the single-GPU batch plan (SeparatorEngine, itself oracle-tested) on every rank
+    par = None
+    if parity:
+        from avse_challenge_b200.engine import SeparatorEngine
+        Tp = min(T, 12 * a.sample_rate) // 8 * 8
+        clip = mix_cpu[:, :Tp].contiguous().to(dev)
+        got = sp(clip)
+        ref = SeparatorEngine(hp, sds, device=dev, mode=a.mode, use_graph=False)(clip)
+        rms = ref.pow(2).mean().sqrt().clamp(min=1e-30)
+        err = ((got - ref).abs().max() / rms).item()
+        err, = ctx.max_over_ranks(err)
+        par = {"max_abs_over_rms": err, "world": world, "clip_seconds": Tp / a.sample_rate,
+               "check": "sequence-parallel forward of a short clip over all ranks (replicated output) against the one-GPU "
+                        "batch plan (SeparatorEngine) on each rank, max over ranks"}
+        del ref, got
+        torch.cuda.empty_cache()
 
-    sampler = ClockSampler(local) if rank == 0 else None
-    mix_d = mix_cpu.to(dev)
-    for _ in range(max(3, a.warmup)):
-        sp(mix_d)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(a.steps):
-        sp(mix_d)
-    e1.record()
-    barrier()
-    ms_total = e0.elapsed_time(e1)
-    pin_in = mix_cpu.pin_memory()
-    pin_out = torch.empty((1, T, hp.n_spk), dtype=torch.float32).pin_memory()
-    dmix = torch.empty((1, T), dtype=torch.float32, device=dev)
+    # ---- sharded timing: every rank holds only its slice of the recording and produces only its slice of the estimate
+    s0, s1 = sp.input_range(T)
+    o0, o1 = sp.output_range(T)
+    mix_loc = mix_cpu[:, s0:s1].contiguous()
+    mix_d = mix_loc.to(dev)
+    ms_total = timed(ctx, lambda: sp.forward_local(mix_d, T), steps, max(3, warmup))
+    pin_in = mix_loc.pin_memory()
+    pin_out = torch.empty((o1 - o0, hp.n_spk), dtype=torch.float32).pin_memory()
+    dmix = torch.empty((1, s1 - s0), dtype=torch.float32, device=dev)
 
     def e2e_step():
         dmix.copy_(pin_in, non_blocking=True)
-        pin_out.copy_(sp(dmix), non_blocking=True)
+        pin_out.copy_(sp.forward_local(dmix, T), non_blocking=True)
 
-    for _ in range(2):
-        e2e_step()
-    barrier()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record()
-    for _ in range(a.steps):
-        e2e_step()
-    f1.record()
-    barrier()
-    ms_e2e = f0.elapsed_time(f1)
+    ms_e2e = timed(ctx, e2e_step, steps, 2)
     clocks = sampler.stop() if sampler else None
-    t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, ms_e2e = t.tolist()
-    if rank == 0:
-        from avse_challenge_b200.parallel import make_seq_plan
-        peak, peak_src, _ = load_peaks()
-        audio_s = T / a.sample_rate
-        L = hp.frames(T)
-        plan = make_seq_plan(L, world, a.sub_chunks)
-        step_ms = ms_total / a.steps
-        per_fwd = 4 + hp.n_mamba * 8                 # enc, bottleneck, (norm, in_proj, conv, x_proj, scan A, fold, scan B, out_proj) x layers, norm_f+mask, decoder(2)
-        line = {
-            "metric": METRIC, "value": audio_s / (step_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": a.steps,
-            "warmup": max(3, a.warmup), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f32" if a.mode == "fp32" else "bf16", "data": "synthetic",
-            "config": dict(workload_config(a, world), frames=L, frames_per_gpu=plan.ranges[0][1] - plan.ranges[0][0],
-                           sub_chunk_frames=plan.Ls),
-            "e2e": {"value": audio_s / (ms_e2e / a.steps * 1e-3), "unit": UNIT, "h2d_bytes_per_step": T * 4,
-                    "d2h_bytes_per_step": T * hp.n_spk * 4, "ms_per_step": ms_e2e / a.steps},
-            "gpu_launches": a.steps * (per_fwd + 1),
-            "roofline": {"kernel": "mtn::scan_kernel (summary pass + seeded pass per layer)", "bound": "hbm",
-                         "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "peak_source": peak_src,
-                         "traffic": None, "note": "per-kernel roofline is reported on the cfg2 workload"},
-            "clocks": clocks,
-        }
-        if cpu_base is not None:
-            line["cpu_baseline"] = cpu_base
+    ms_total, ms_e2e = ctx.max_over_ranks(ms_total, ms_e2e)
+    graphed = bool(sp.use_graph and sp.graph_failed is None)
+    graph_note = sp.graph_failed
+    ncoll = sp.collectives_per_forward
+    del sp, dmix, mix_d
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    from avse_challenge_b200.parallel import make_seq_plan
+    peak, peak_src, _ = load_peaks()
+    audio_s = T / a.sample_rate
+    L = hp.frames(T)
+    plan = make_seq_plan(L, world, a.sub_chunks)
+    step_ms = ms_total / steps
+    per_fwd = 4 + hp.n_mamba * 10     # enc, bottleneck, (norm, in_proj, 2 edge copies, conv, x_proj, scan A, fold, scan B, out_proj) x layers, norm_f+mask, decoder(2)
+    line = {
+        "metric": METRIC, "value": audio_s / (step_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps,
+        "warmup": max(3, warmup), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32" if a.mode == "fp32" else "bf16", "data": "synthetic",
+        "config": dict(workload_config(a, world), frames=L, frames_per_gpu=plan.ranges[0][1] - plan.ranges[0][0],
+                       sub_chunk_frames=plan.Ls),
+        "e2e": {"value": audio_s / (ms_e2e / steps * 1e-3), "unit": UNIT, "h2d_bytes_per_step": (s1 - s0) * 4,
+                "d2h_bytes_per_step": (o1 - o0) * hp.n_spk * 4, "ms_per_step": ms_e2e / steps,
+                "note": "per rank: every rank copies only its own slice of the recording in and of the estimate out"},
+        "gpu_launches": steps * (per_fwd + 1),
+        "collectives_per_forward": ncoll, "cuda_graph": graphed,
+        "roofline": {"kernel": "mtn::scan_kernel (summary pass) + mtn::scan_kernel_pair (seeded pass) per layer", "bound": "hbm",
+                     "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "peak_source": peak_src,
+                     "traffic": None, "note": "per-kernel roofline is reported on the batch workloads"},
+        "clocks": clocks,
+    }
+    if graph_note:
+        line["cuda_graph_note"] = graph_note
+    if par is not None:
+        line["parity"] = par
+    if cpu_base is not None:
+        line["cpu_baseline"] = cpu_base
+    return line
+
+
+def side_args(a, workload):
+    """argparse namespace of a side run (`also`): the named BASELINE config with its defaults."""
+    import copy
+    b = copy.copy(a)
+    b.workload = workload
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    b.model, b.causal, b.fuse_norm = "mambatasnet", False, False
+    if workload == "cfg3":
+        b.hparams, b.mode, b.batch, b.seconds, b.sample_rate = "L", "bf16", max(1, 256 // world), 4.0, 8000
+    else:
+        b.hparams, b.mode, b.batch, b.seconds, b.sample_rate = "S", "fp32", 1, 600.0, 16000
+    return b
+
+
+def run_b200_arm(a):
+    ctx = Ctx()
+    sampler = ClockSampler(ctx.local) if ctx.rank == 0 else None
+    line = measure_batch(a, ctx, a.steps, a.warmup, sampler=sampler, parity=(ctx.world > 1))
+    if a.workload == "cfg2" and a.model == "mambatasnet" and not a.causal and not a.no_also:
+        also = []
+        for wl, fn in (("cfg3", measure_batch), ("longform", measure_longform)):
+            try:
+                sub = fn(side_args(a, wl), ctx, max(1, a.also_steps), 1, cpu_baseline=False, parity=True)
+            except Exception as e:   # a side run must never take the headline line down with it
+                sub = {"config": {"workload": wl}, "error": f"{type(e).__name__}: {e}"}
+            also.append(sub)
+        if ctx.rank == 0:
+            line["also"] = also
+    if ctx.rank == 0:
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    ctx.close()
+
+
+def run_longform_arm(a):
+    ctx = Ctx()
+    sampler = ClockSampler(ctx.local) if ctx.rank == 0 else None
+    line = measure_longform(a, ctx, a.steps, a.warmup, sampler=sampler, parity=True)
+    if ctx.rank == 0:
+        print(json.dumps(line), flush=True)
+    ctx.close()
 
 
 def run_stream_arm(a):

@@ -182,6 +182,12 @@ int mtn_scan_fwd(const mtn_scan_args* args, mtn_stream_t stream);
 int mtn_fold_states_fwd(const float* h_end, const float* sum_delta, const float* A2, const float* h0, float* h_in,
                         float* h_final, int G, int di, int g0, int n_out, int dir_mask, mtn_stream_t stream);
 
+/* The same composition over the summaries exactly as ONE all-gather delivers them (ABI >= 6): `pack` fp32 [W][rec], rank w's
+ * record rec = [ h_end [2][cmax][di][16] | sum_delta [2][cmax][di] ] (cmax sub-chunks per rank, unused ones zero = identity
+ * operators); global chunk g = w * cmax + c.  h0 / h_in / h_final / g0 / n_out / dir_mask as above. */
+int mtn_fold_states_packed_fwd(const float* pack, const float* A2, const float* h0, float* h_in, float* h_final, int W,
+                               int cmax, int di, int g0, int n_out, int dir_mask, mtn_stream_t stream);
+
 /* sep fp32 [batch*L][n_spk*N] (speaker-major channels) -> est [batch][T][n_spk] fp32:
  * est[b, 8l+k, s] = sum over frames/taps of sum_n w_dec[n][k] * sep[b,l,s*N+n]; zero-padded / trimmed to T.
  * frames: scratch fp32 [batch*L][n_spk][16]. */
@@ -216,6 +222,14 @@ int mtn_split_planes(const float* src, int ld, void* dst_planes, int rows, int c
 size_t mtn_si_snr_workspace_bytes(int batch, int T);
 int mtn_si_snr_pit_fwd(const float* est, const float* src, const float* mix, int ld_mix, int batch, int T,
                        void* workspace, size_t workspace_bytes, float* out, mtn_stream_t stream);
+/* The same for n_spk = 1..4 speakers (`num_spks: 3` is the wsj0-3mix setting of every recipe,
+ * hparams/WSJ0Mix/mambatasnet_S.yaml:39; save_results appends s3_sig then, train_wsj0mix.py:537-538) (ABI >= 6).
+ * est, src fp32 [batch][T][n_spk].  out fp32 [batch][out_stride >= 4 + n^2]: { si_snr (best of the n! assignments, mean
+ * over speakers), si_snr_i, lexicographic rank of the best assignment, si_snr of the mixture, pair matrix [est i][src j] }
+ * and, when out_stride >= 4 + n^2 + n, the assignment itself (entry i = source matched to estimate i). */
+size_t mtn_si_snr_workspace_bytes_n(int batch, int T, int n_spk);
+int mtn_si_snr_pit_n_fwd(const float* est, const float* src, const float* mix, int ld_mix, int batch, int T, int n_spk,
+                         void* workspace, size_t workspace_bytes, float* out, int out_stride, mtn_stream_t stream);
 
 /* ---- DPMamba (dual-path) glue, SURVEY 8f rank 1 ------------------------------------------------------------------
  * The mask network of the dpmamba_* recipes is speechbrain 1.0.0 `Dual_Path_Model` [third party, not vendored]

@@ -54,7 +54,13 @@ def golden_scan():
                         out_reverse=out_b.numpy())
 
 
-def golden_forward(name, T, batch, seed, tag, own_init, bidirectional=True, mask_nonlinear="relu", rms_norm=True):
+def golden_forward(name, T, batch, seed, tag, own_init, bidirectional=True, mask_nonlinear="relu", rms_norm=True,
+                   autocast=False):
+    """``autocast``: run the reference's modules the way its recipes do by default (``precision: bf16``,
+    hparams/WSJ0Mix/mambatasnet_S.yaml:38; ``torch.autocast`` region train_wsj0mix.py:161-164) -- on the CPU autocast
+    backend here, whose op policy for this path (conv / linear / matmul in bf16, everything else in the dtype it is
+    given) matches the CUDA one.  The outputs are stored as fp32 copies of the bf16 results."""
+    import contextlib
     from dataclasses import replace
     hp = CONFIGS[name] if bidirectional else CONFIGS[name].causal()
     hp = replace(hp, rms_norm=rms_norm)
@@ -71,18 +77,24 @@ def golden_forward(name, T, batch, seed, tag, own_init, bidirectional=True, mask
 
     def hook(key):
         def fn(_m, _i, o):
-            taps[key] = (o[0] if isinstance(o, tuple) else o).detach().numpy()
+            taps[key] = (o[0] if isinstance(o, tuple) else o).detach().float().numpy()
         return fn
 
     mask.mamba_net.layers[0].mixer.register_forward_hook(hook("mixer0_out"))
     mask.mamba_net.register_forward_hook(hook("stack_out"))
     mask.bottleneck_conv1x1.register_forward_hook(hook("bottleneck_out"))
-    with torch.no_grad():
+    ctx = torch.autocast("cpu", dtype=torch.bfloat16) if autocast else contextlib.nullcontext()
+    with torch.no_grad(), ctx:
         mix_w = enc(mix)
         est_mask = mask(mix_w)
         est = ref.compute_forward(enc, mask, dec, mix)
-    arrs = {"mix": mix.numpy(), "src": src.numpy(), "est": est.numpy(), "mix_w": mix_w.numpy(),
-            "est_mask": est_mask.numpy(), "T": np.int64(T), "batch": np.int64(batch)}
+    if autocast:
+        assert est.dtype == torch.bfloat16 and est_mask.dtype == torch.bfloat16
+        taps = {k: v.astype(np.float32) if v.dtype != np.float32 else v for k, v in
+                ((k, torch.as_tensor(v).float().numpy() if not isinstance(v, np.ndarray) else v) for k, v in taps.items())}
+    f32 = lambda t: t.float().numpy()
+    arrs = {"mix": mix.numpy(), "src": src.numpy(), "est": f32(est), "mix_w": f32(mix_w),
+            "est_mask": f32(est_mask), "T": np.int64(T), "batch": np.int64(batch)}
     arrs.update({f"tap/{k}": v for k, v in taps.items()})
     arrs.update(_np(enc.state_dict(), "encoder"))
     arrs.update(_np(mask.state_dict(), "masknet"))
@@ -170,6 +182,37 @@ def golden_si_snr():
     print("si_snr_ref.npz", (-neg[0]).tolist())
 
 
+def golden_results_csv():
+    """``test_results.csv`` exactly as ``Separation.save_results`` writes it (``Mamba-TasNet/train_wsj0mix.py:517-597``):
+    the writer statements of the reference restated verbatim over fixed per-utterance metrics (the metrics themselves are
+    pinned elsewhere), so that the product's writer can be compared byte for byte."""
+    import csv
+    g = np.random.default_rng(7)
+    ids = ["440c0206_1.8_446o030c_-1.8", "22ga010b_0.5_050a050f_-0.5", "421a0108_2.1_01zo030f_-2.1"]
+    sdr, sdr_i = g.normal(15, 3, 3), g.normal(15, 3, 3)
+    sisnr, sisnr_i = g.normal(-14, 3, 3), g.normal(-14, 3, 3)      # the reference holds NEGATIVE si-snr (loss) here
+    path = os.path.join(OUT, "test_results_ref.csv")
+    all_sdrs, all_sdrs_i, all_sisnrs, all_sisnrs_i = [], [], [], []
+    csv_columns = ["snt_id", "sdr", "sdr_i", "si-snr", "si-snr_i"]                      # :517
+    with open(path, "w") as results_csv:                                                # :523
+        writer = csv.DictWriter(results_csv, fieldnames=csv_columns)
+        writer.writeheader()
+        for i in range(3):
+            row = {"snt_id": ids[i], "sdr": sdr[i], "sdr_i": sdr_i[i], "si-snr": -float(sisnr[i]),
+                   "si-snr_i": -float(sisnr_i[i])}                                      # :577-583
+            writer.writerow(row)
+            all_sdrs.append(sdr[i])
+            all_sdrs_i.append(sdr_i[i])
+            all_sisnrs.append(-float(sisnr[i]))
+            all_sisnrs_i.append(-float(sisnr_i[i]))
+        row = {"snt_id": "avg", "sdr": np.array(all_sdrs).mean(), "sdr_i": np.array(all_sdrs_i).mean(),
+               "si-snr": np.array(all_sisnrs).mean(), "si-snr_i": np.array(all_sisnrs_i).mean()}   # :591-597
+        writer.writerow(row)
+    np.savez(os.path.join(OUT, "test_results_ref_inputs.npz"), ids=np.array(ids), sdr=sdr, sdr_i=sdr_i,
+             si_snr=-sisnr, si_snr_i=-sisnr_i)
+    print("test_results_ref.csv", open(path).read().count("\n"), "lines")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
@@ -177,10 +220,12 @@ def main():
     golden_forward("tiny", T=2000, batch=2, seed=1234, tag="tiny_refinit", own_init=False)
     golden_forward("tiny", T=1003, batch=3, seed=77, tag="tiny_trained", own_init=True)
     golden_si_snr()
+    golden_results_csv()
     _, mask, _ = golden_forward("tiny", T=1203, batch=2, seed=55, tag="tiny_causal", own_init=True, bidirectional=False)
     golden_stream(mask, "tiny_causal")
     golden_forward("tiny", T=803, batch=1, seed=66, tag="tiny_softmax", own_init=True, mask_nonlinear="softmax")
     golden_forward("tiny", T=803, batch=1, seed=67, tag="tiny_layernorm", own_init=True, rms_norm=False)
+    golden_forward("tiny", T=1003, batch=2, seed=78, tag="tiny_autocast", own_init=True, autocast=True)
     golden_dp("dp_tiny_skip", T=1203, batch=2, seed=91, skip_around_intra=True)
     golden_dp("dp_tiny_noskip", T=811, batch=1, seed=92, skip_around_intra=False)
     golden_dp("dp_tiny_blockskip", T=643, batch=1, seed=93, skip_around_intra=True, skip_n_block=1, n_dp=3)

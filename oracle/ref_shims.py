@@ -48,11 +48,19 @@ def reference_available() -> bool:
 
 
 # --------------------------------------------------------------------------- leaves
+def _no_autocast():
+    """The third-party kernels compute in fp32 whatever dtype they are handed and round ONCE on output; their stand-ins
+    must not be re-cast by a surrounding autocast region (the bf16 golden run of oracle/make_golden.py)."""
+    return torch.autocast("cpu", enabled=False)
+
+
 def _causal_conv1d_fwd(x, weight, bias, seq_idx, silu):
-    # x [B, D, L]; weight [D, W]
+    # x [B, D, L]; weight [D, W].  causal-conv1d 1.1.3.post1: fp32 accumulation, output in x.dtype.
     d, w = weight.shape
-    y = F.conv1d(x, weight[:, None, :], bias, padding=w - 1, groups=d)[..., : x.shape[-1]]
-    return F.silu(y) if silu else y
+    with _no_autocast():
+        y = F.conv1d(x.float(), weight.float()[:, None, :], None if bias is None else bias.float(), padding=w - 1,
+                     groups=d)[..., : x.shape[-1]]
+        return (F.silu(y) if silu else y).to(x.dtype)
 
 
 class _RMSNorm(nn.Module):
@@ -63,9 +71,10 @@ class _RMSNorm(nn.Module):
         self.register_parameter("bias", None)
 
     def forward(self, x):
-        xf = x.float()
-        y = xf * torch.rsqrt(xf.pow(2).mean(dim=-1, keepdim=True) + self.eps) * self.weight.float()
-        return y.to(x.dtype)
+        with _no_autocast():
+            xf = x.float()
+            y = xf * torch.rsqrt(xf.pow(2).mean(dim=-1, keepdim=True) + self.eps) * self.weight.float()
+            return y.to(x.dtype)
 
 
 class _ChannelwiseLayerNorm(nn.Module):
@@ -234,7 +243,10 @@ def load_reference():
     from modules.mamba import selective_scan_interface as ssi  # noqa: E402
 
     def _fwd(u, delta, A, B, C, D, z, delta_bias, delta_softplus):
-        out_z, last = ssi.selective_scan_ref(u, delta, A, B, C, D, z, delta_bias, delta_softplus, True)
+        with _no_autocast():   # selective_scan_ref floats u / delta / B / C and returns out.to(u.dtype), like the kernel;
+            # z is the one input it does not float (ssi.py:155 would take silu in bf16), while the kernel gates in fp32
+            out_z, last = ssi.selective_scan_ref(u, delta, A, B, C, D, None if z is None else z.float(), delta_bias,
+                                                 delta_softplus, True)
         # `x` = the kernel's per-chunk running states [B, D, n_chunks, 2*Ns]; SelectiveScanFn.forward reads the final
         # state from x[:, :, -1, 1::2] (selective_scan_interface.py:46)
         x = torch.zeros(last.shape[0], last.shape[1], 1, 2 * last.shape[2], dtype=last.dtype)

@@ -45,8 +45,47 @@ def _clib():
     return _CLIB
 
 
-# ----------------------------------------------------------------------------- GEMM rounding model
+# ----------------------------------------------------------------------------- precision models
+# "fp32"          the reference's fp32 path (selective_scan_ref in fp32): the oracle of BASELINE configs 1-2.
+# "product_bf16"  rounds to bf16 exactly where the CUDA path's bf16 mode stores bf16: both operands of
+#                 every dense contraction (xn / yn / u / y planes, weights), the x half and the silu(z) half of in_proj's
+#                 output, the conv output u, the gated scan output y.  Residual stream, [dt|B|C], delta, the SSM state,
+#                 mix_w, the mask product and the decoder stay fp32.  This is the checker of configs 3-4: the product
+#                 must agree with it far more tightly than with the fp32 oracle.
+# "autocast_ref"  rounds where the REFERENCE's mixed-precision path rounds (``precision: bf16`` is the recipes' default,
+#                 hparams/WSJ0Mix/mambatasnet_S.yaml:38; autocast region train_wsj0mix.py:161-164): every conv / linear /
+#                 matmul takes bf16 operands and returns bf16 (incl. x_proj and dt_proj, whose weights
+#                 selective_scan_interface.py:174-176 casts), the depthwise conv and the scan kernels take bf16 and return
+#                 bf16 with fp32 arithmetic inside (A, D, delta_bias and the state stay fp32: bimamba.py:200,232-233),
+#                 RMSNorm returns bf16, and the residual stream is bf16 (residual_in_fp32: False).  Pinned against a run
+#                 of the reference's own modules under torch.autocast (tests/golden/forward_tiny_autocast.npz).
+_PREC = "fp32"
 _GEMM_MODE = "fp32"
+
+
+def set_precision(mode: str):
+    """Select one of the three precision models above (also sets the GEMM operand rounding)."""
+    global _PREC
+    assert mode in ("fp32", "product_bf16", "autocast_ref")
+    _PREC = mode
+    set_gemm_mode("fp32" if mode == "fp32" else "bf16")
+
+
+def _r(x):
+    """Round to bf16 (round-to-nearest-even), keep the container dtype."""
+    return x.to(torch.bfloat16).to(x.dtype)
+
+
+def _r_ref(x):
+    return _r(x) if _PREC == "autocast_ref" else x
+
+
+def _r_prod(x):
+    return _r(x) if _PREC == "product_bf16" else x
+
+
+def _r_any(x):
+    return _r(x) if _PREC != "fp32" else x
 
 
 def set_gemm_mode(mode: str):
@@ -69,7 +108,7 @@ def _mm(x, w):
     if _GEMM_MODE == "fp32":
         return x @ w.t()
     if _GEMM_MODE == "bf16":
-        return x.to(torch.bfloat16).to(x.dtype) @ w.to(torch.bfloat16).to(w.dtype).t()
+        return _r_ref(_r(x) @ _r(w).t())          # autocast: the output is bf16 too; the CUDA path keeps fp32 outputs
     if _GEMM_MODE == "tf32":
         r = lambda t: ((t.float().view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32).to(t.dtype)
         return r(x) @ r(w).t()
@@ -83,12 +122,20 @@ def encoder_fwd(mix, w_enc):
     """``relu(conv1d(mix[:,None,:], W[N,1,K], stride K//2))`` -> ``[B, L, N]``.
     speechbrain ``dual_path.Encoder`` == ``baseline/avse2/model.py:14-24``."""
     k = w_enc.shape[-1]
+    if _PREC == "autocast_ref":   # conv1d is an autocast op: bf16 operands, bf16 result
+        return F.relu(_r(F.conv1d(_r(mix).unsqueeze(1), _r(w_enc), stride=k // 2))).transpose(1, 2).contiguous()
     return F.relu(F.conv1d(mix.unsqueeze(1), w_enc, stride=k // 2)).transpose(1, 2).contiguous()
 
 
 def cln_fwd(y, gamma, beta, eps=1e-8):
     """ChannelwiseLayerNorm over the channel axis, biased variance, eps 1e-8
     (speechbrain ``conv_tasnet.ChannelwiseLayerNorm``; ctor ``modules/mamba_masknet.py:73``)."""
+    if _PREC == "autocast_ref":
+        # y is bf16: mean / var / (y - mean) / var + eps / pow are bf16 ops (fp32 inside, one rounding each); the products
+        # with the fp32 parameters gamma / beta promote to fp32 (type promotion with a dimensioned fp32 tensor)
+        mean = _r(y.mean(dim=-1, keepdim=True))
+        var = _r(y.var(dim=-1, keepdim=True, unbiased=False))
+        return gamma.reshape(-1) * _r(y - mean) / _r(torch.sqrt(_r(var + eps))) + beta.reshape(-1)
     mean = y.mean(dim=-1, keepdim=True)
     var = y.var(dim=-1, keepdim=True, unbiased=False)
     return gamma.reshape(-1) * (y - mean) / torch.sqrt(var + eps) + beta.reshape(-1)
@@ -103,8 +150,10 @@ def block_norm(x, sd, key, eps=1e-5):
     """The block / final norm: RMSNorm, or ``nn.LayerNorm`` when the state_dict carries a bias for it
     (``rms_norm=False``, ``modules/mamba_blocks.py:36-41,167-169``)."""
     if key + ".bias" in sd:
+        if _PREC == "autocast_ref":
+            raise NotImplementedError("autocast_ref models the shipped recipes (rms_norm: True)")
         return F.layer_norm(x, (x.shape[-1],), sd[key + ".weight"], sd[key + ".bias"], eps)
-    return rmsnorm_fwd(x, sd[key + ".weight"], eps)
+    return _r_ref(rmsnorm_fwd(x, sd[key + ".weight"], eps))   # the Triton RMSNorm returns the input dtype
 
 
 def causal_conv_silu(xs, w, b, reverse=False):
@@ -115,7 +164,7 @@ def causal_conv_silu(xs, w, b, reverse=False):
     if reverse:
         x = x.flip(-1)
     di, _, width = w.shape
-    y = F.silu(F.conv1d(x, w, b, padding=width - 1, groups=di)[..., : x.shape[-1]])
+    y = _r_any(F.silu(F.conv1d(x, w, b, padding=width - 1, groups=di)[..., : x.shape[-1]]))   # bf16 modes: u is stored bf16
     if reverse:
         y = y.flip(-1)
     return y.transpose(1, 2).contiguous()
@@ -184,6 +233,7 @@ def mixer_fwd(x, sd, prefix, scan_impl="auto", state=None):
     di = W_in.shape[0] // 2
     xz = _mm(x, W_in)                                                       # bimamba.py:192-196
     xs, z = xz[..., :di], xz[..., di:]                                     # ssi.py:180 (x first, z last)
+    xs = _r_prod(xs)          # product bf16 mode: xz is a bf16 buffer, x half as is, z half already activated
     bidir = (p + "A_b_log") in sd
     if state is not None and bidir:
         raise ValueError("streaming state exists only for the unidirectional mixer")
@@ -206,16 +256,29 @@ def mixer_fwd(x, sd, prefix, scan_impl="auto", state=None):
         else:
             u = causal_conv_silu(xs, conv_w, conv_b, reverse=rev)         # ssi.py:182
         dbl = _mm(u, W_x)                                                  # ssi.py:186
-        delta_pre = dbl[..., :R] @ W_dt.t()                                # ssi.py:187 (bias NOT added here)
+        if _PREC == "autocast_ref":   # delta_proj_weight is cast to the autocast dtype (ssi.py:174-176), bf16 matmul
+            delta_pre = _r(_r(dbl[..., :R]) @ _r(W_dt).t())
+        else:
+            delta_pre = dbl[..., :R] @ W_dt.t()                            # ssi.py:187 (bias NOT added here)
         Bm, Cm = dbl[..., R:R + Ns], dbl[..., R + Ns:]                     # ssi.py:193,205
-        y, h_last = selective_scan(u, delta_pre, A.to(u.dtype), Bm, Cm, D.to(u.dtype), z,
-                                   b_dt.to(u.dtype), reverse=rev, impl=scan_impl, h_in=h_in)  # ssi.py:218-220
+        if _PREC == "fp32":
+            y, h_last = selective_scan(u, delta_pre, A.to(u.dtype), Bm, Cm, D.to(u.dtype), z,
+                                       b_dt.to(u.dtype), reverse=rev, impl=scan_impl, h_in=h_in)  # ssi.py:218-220
+        else:
+            y, h_last = selective_scan(u, delta_pre, A.to(u.dtype), Bm, Cm, D.to(u.dtype), None,
+                                       b_dt.to(u.dtype), reverse=rev, impl=scan_impl, h_in=h_in, gate=False)
+            if _PREC == "autocast_ref":
+                y = _r(y * F.silu(z))          # the kernel gates in fp32 and returns bf16 (ssi.py:155, out_z)
+            else:
+                y = y * _r(F.silu(z))          # the in_proj epilogue stored silu(z) as bf16; y is rounded when stored (below)
         if state is not None:
             state["ssm"].copy_(h_last)                                     # bimamba.py:302-304, :357
         outs.append(y)
     if not bidir:
         return _mm(outs[0], sd[p + "out_proj.weight"])                    # bimamba.py:306
-    return _mm(0.5 * outs[0] + 0.5 * outs[1], sd[p + "out_proj.weight"])  # bimamba.py:253
+    if _PREC == "product_bf16":   # each direction's 0.5 * y is its own bf16 buffer; out_proj sums them along K
+        return _mm(0.5 * outs[0], sd[p + "out_proj.weight"]) + _mm(0.5 * outs[1], sd[p + "out_proj.weight"])
+    return _mm(_r_ref(0.5 * outs[0] + 0.5 * outs[1]), sd[p + "out_proj.weight"])  # bimamba.py:253 (bf16 add under autocast)
 
 
 def mixer_step(x_t, sd, prefix, conv_state, ssm_state):
@@ -260,12 +323,12 @@ def mamba_stack_fwd(h, sd, n_mamba, prefix="mamba_net.", scan_impl="auto", taps=
     residual = None
     for i in range(n_mamba):
         p = f"{prefix}layers.{i}."
-        residual = h if residual is None else h + residual                # bimamba.py:446
+        residual = h if residual is None else _r_ref(h + residual)        # bimamba.py:446 (bf16 stream when residual_in_fp32 False)
         hn = block_norm(residual, sd, p + "norm")                          # bimamba.py:447
         h = mixer_fwd(hn, sd, p + "mixer.", scan_impl, state=None if states is None else states[i])  # bimamba.py:461
         if taps is not None:
             taps.append(h)
-    residual = h + residual if residual is not None else h                 # mamba_blocks.py:196
+    residual = _r_ref(h + residual) if residual is not None else h         # mamba_blocks.py:196
     return block_norm(residual, sd, prefix + "norm_f")                     # mamba_blocks.py:197
 
 
@@ -287,6 +350,8 @@ def decoder_fwd(sep_h, w_dec):
     """``conv_transpose1d(sep_h, W[N,1,K], stride K//2)`` on channel-last ``[B,L,N]`` -> ``[B,T_est]``
     (speechbrain ``dual_path.Decoder`` == ``baseline/avse2/model.py:27-37``)."""
     k = w_dec.shape[-1]
+    if _PREC == "autocast_ref":   # conv_transpose1d is an autocast op: bf16 operands, bf16 result
+        return _r(F.conv_transpose1d(_r(sep_h).transpose(1, 2), _r(w_dec), stride=k // 2)[:, 0, :])
     return F.conv_transpose1d(sep_h.transpose(1, 2), w_dec, stride=k // 2)[:, 0, :]
 
 
@@ -294,7 +359,7 @@ def separate(mix, sds, n_mamba, n_spk=2, scan_impl="auto", taps=None, mask_nonli
     """``Separation.compute_forward`` (``Mamba-TasNet/train_wsj0mix.py:86-111``): ``[B,T] -> [B,T,n_spk]``."""
     mix_w = encoder_fwd(mix, sds["encoder"]["conv1d.weight"])              # :89
     mask = masknet_fwd(mix_w, sds["masknet"], n_mamba, n_spk, scan_impl, taps, mask_nonlinear)  # :90
-    est = torch.stack([decoder_fwd(mix_w * mask[s], sds["decoder"]["weight"]) for s in range(n_spk)],
+    est = torch.stack([decoder_fwd(_r_ref(mix_w * mask[s]), sds["decoder"]["weight"]) for s in range(n_spk)],
                       dim=-1)                                              # :91-101
     T, T_est = mix.shape[1], est.shape[1]
     if T > T_est:                                                          # :104-109
@@ -370,9 +435,15 @@ def dp_masknet_fwd(mix_w, sd, n_dp, K, skip_around_intra, n_mamba_stack=1, n_spk
         x = inter + intra
     x = torch.where(x >= 0, x, sd["prelu.weight"] * x)                     # dp.py:126
     w2 = sd["conv2d.weight"][:, :, 0, 0]
-    x = _mm(x, w2) + sd["conv2d.bias"]                                     # dp.py:131  [B, S, K, spk*D]
-    x = x.reshape(B, S, K, n_spk, D).permute(0, 3, 1, 2, 4).reshape(B * n_spk, S, K, D)   # dp.py:137 (view B*spks)
-    x = dp_over_add(x, gap)                                                # dp.py:140  [B*spk, L, D]
+    if _PREC == "product_bf16":
+        # the CUDA path applies the 1x1 conv2d AFTER the overlap-add (the same linear map on half the rows, its bias then
+        # counts twice: mtn_dp_overadd_prelu_fwd), so the bf16 operand of that GEMM is the overlap-added frame
+        x = _mm(dp_over_add(x, gap), w2) + 2.0 * sd["conv2d.bias"]         # [B, L, spk*D]
+        x = x.reshape(B, L, n_spk, D).permute(0, 2, 1, 3).reshape(B * n_spk, L, D)
+    else:
+        x = _mm(x, w2) + sd["conv2d.bias"]                                 # dp.py:131  [B, S, K, spk*D]
+        x = x.reshape(B, S, K, n_spk, D).permute(0, 3, 1, 2, 4).reshape(B * n_spk, S, K, D)   # dp.py:137 (view B*spks)
+        x = dp_over_add(x, gap)                                            # dp.py:140  [B*spk, L, D]
     o = torch.tanh(_mm(x, sd["output.0.weight"][:, :, 0]) + sd["output.0.bias"])
     g = torch.sigmoid(_mm(x, sd["output_gate.0.weight"][:, :, 0]) + sd["output_gate.0.bias"])
     x = _mm(o * g, sd["end_conv1x1.weight"][:, :, 0])                      # dp.py:141-146
@@ -410,16 +481,17 @@ def cal_si_snr(source, estimate):
 
 def pit_si_snr_improvement(est, src, mix):
     """What ``save_results`` writes per utterance (``Mamba-TasNet/train_wsj0mix.py:548-558``): PIT SI-SNR of the
-    estimates, of the unprocessed mixture, and their difference.  The PIT wrapper [3P speechbrain
-    ``get_si_snr_with_pitwrapper``, published behaviour] takes the permutation with the smallest mean loss, i.e. the
-    largest mean SI-SNR over the speakers.  Returns (si_snr [B], si_snr_i [B], perm [B], pairs [B, 2, 2])."""
-    B = est.shape[0]
-    pairs = torch.stack([torch.stack([cal_si_snr(src[..., j:j + 1], est[..., i:i + 1])[:, 0] for j in range(2)], dim=-1)
-                         for i in range(2)], dim=1)                          # [B, est i, src j]
-    direct = 0.5 * (pairs[:, 0, 0] + pairs[:, 1, 1])
-    swapped = 0.5 * (pairs[:, 0, 1] + pairs[:, 1, 0])
-    perm = (swapped > direct).long()
-    best = torch.where(perm.bool(), swapped, direct)
-    mixture = torch.stack([mix] * 2, dim=-1)                                 # train_wsj0mix.py:551-553
+    estimates, of the unprocessed mixture, and their difference, for any number of speakers (``num_spks: 3`` adds
+    ``s3_sig``, ``:537-538``).  The PIT wrapper [3P speechbrain ``get_si_snr_with_pitwrapper``, published behaviour] takes
+    the permutation with the smallest mean loss, i.e. the largest mean SI-SNR over the speakers (first one on ties, like
+    argmin over permutations in lexicographic order).  Returns (si_snr [B], si_snr_i [B], perm [B] = lexicographic rank of
+    the best assignment (2 speakers: 0 direct, 1 swapped), pairs [B, n, n] = est i vs src j)."""
+    import itertools
+    n = est.shape[-1]
+    pairs = torch.stack([torch.stack([cal_si_snr(src[..., j:j + 1], est[..., i:i + 1])[:, 0] for j in range(n)], dim=-1)
+                         for i in range(n)], dim=1)                          # [B, est i, src j]
+    cands = torch.stack([sum(pairs[:, i, p[i]] for i in range(n)) / n for p in itertools.permutations(range(n))], dim=1)
+    best, perm = cands.max(dim=1)                                            # max returns the first maximum
+    mixture = torch.stack([mix] * n, dim=-1)                                 # train_wsj0mix.py:551-553
     base = cal_si_snr(src, mixture).mean(dim=-1)
     return best, best - base, perm, pairs

@@ -483,6 +483,60 @@ def test_bf16_mode_stated_tolerance():
     assert err <= 0.15 and fid >= 25.0, (err, fid)
 
 
+@pytest.mark.parametrize("name,B,T", [("S", 2, 8000), ("L", 2, 32000)])
+def test_bf16_mode_against_matched_rounding_oracle(name, B, T):
+    """bf16 mode against the oracle evaluated with the product's own rounding points (``restate.set_precision(
+    "product_bf16")``: bf16 GEMM operands, bf16 xz / u / y, everything else fp32).  ``L`` with B = 2, T = 32 000 is BASELINE
+    config 3's own hparams and utterance length.  Gate: max-abs <= 1.5e-2 * rms and SI-SNR(est, matched oracle) >= 40 dB --
+    ten times tighter than the gate against the fp32 oracle (test_bf16_mode_stated_tolerance); what is left is bf16
+    roundings flipped by fp32-level differences (accumulation order, ex2.approx, the 1-MUFU SiLU).  The distance to the fp32
+    oracle is printed beside it."""
+    hp = CONFIGS[name]
+    sds = init_state_dicts(hp, 1234)
+    mix, src = synth_mixture(B, T, seed=7)
+    restate.set_precision("product_bf16")
+    try:
+        with torch.no_grad():
+            ref_m = restate.separate(mix, sds, hp.n_mamba, scan_impl="c")
+    finally:
+        restate.set_precision("fp32")
+    with torch.no_grad():
+        ref32 = restate.separate(mix, sds, hp.n_mamba, scan_impl="c")
+    est = SeparatorEngine(hp, sds, device=DEV, mode="bf16", use_graph=False)(mix.to(DEV)).cpu()
+    err_m, d_m, fid_m = _gate(est, ref_m, src)
+    err32, d32, fid32 = _gate(est, ref32, src)
+    err_o, _, _ = _gate(ref_m, ref32, src)
+    print(f"bf16 {name} B={B} T={T}: vs matched oracle max-abs/rms {err_m:.3e} dSI-SNR {d_m:.2e} dB fidelity {fid_m:.1f} dB | "
+          f"vs fp32 oracle {err32:.3e} / {d32:.2e} dB / {fid32:.1f} dB | matched oracle vs fp32 oracle {err_o:.3e}")
+    assert err_m <= 1.5e-2 and fid_m >= 40.0, (err_m, fid_m)
+    assert err32 <= 0.15 and fid32 >= 25.0, (err32, fid32)
+
+
+def test_bf16_mode_causal_and_reference_autocast_distance():
+    """Causal S stack in bf16 mode against the matched-rounding oracle (same gate), and -- for the record -- how far the
+    REFERENCE's own bf16 path (``autocast_ref`` model, pinned to a run of the reference under torch.autocast) sits from the
+    fp32 oracle on the same input: the product's bf16 mode must not be further away than that."""
+    hp = CONFIGS["S"].causal()
+    sds = init_state_dicts(hp, 99)
+    mix, src = synth_mixture(2, 8000, seed=17)
+    outs = {}
+    for mode in ("product_bf16", "autocast_ref", "fp32"):
+        restate.set_precision(mode)
+        try:
+            with torch.no_grad():
+                outs[mode] = restate.separate(mix, sds, hp.n_mamba, scan_impl="c")
+        finally:
+            restate.set_precision("fp32")
+    est = SeparatorEngine(hp, sds, device=DEV, mode="bf16", use_graph=False)(mix.to(DEV)).cpu()
+    err_m, _, fid_m = _gate(est, outs["product_bf16"], src)
+    err32, _, _ = _gate(est, outs["fp32"], src)
+    err_ref, _, _ = _gate(outs["autocast_ref"], outs["fp32"], src)
+    print(f"bf16 causal S: vs matched oracle {err_m:.3e} ({fid_m:.1f} dB) | vs fp32 oracle {err32:.3e} | reference autocast "
+          f"model vs fp32 oracle {err_ref:.3e}")
+    assert err_m <= 1.5e-2 and fid_m >= 40.0, (err_m, fid_m)
+    assert err32 <= 1.25 * err_ref, (err32, err_ref)
+
+
 def test_full_size_config2_properties():
     """BASELINE config 2 (S, 32 x 4 s @ 8 kHz) at full size through size-independent properties:
     (a) batch independence: utterance i of the batch of 32 == the same utterance run alone (bit-exact),
@@ -651,12 +705,73 @@ def test_si_snr_pit_matches_oracle(B, T, golden_dir):
         assert (got["pairs"].cpu()[:, [0, 1], [0, 1]].double() - torch.from_numpy(z["si_snr"]).double()).abs().max() < 2e-3
 
 
+@pytest.mark.parametrize("n,B,T", [(3, 4, 8001), (3, 1, 40000), (1, 2, 500), (4, 2, 3000)])
+def test_si_snr_pit_n_speakers_matches_oracle(n, B, T):
+    """``num_spks: 3`` (wsj0-3mix, mambatasnet_S.yaml:39; save_results appends s3_sig, train_wsj0mix.py:537-538): all n!
+    assignments on the device against the oracle's itertools.permutations PIT; the estimates are permuted copies of the
+    sources so that every utterance has a different best assignment."""
+    import itertools
+    from avse_challenge_b200 import scoring
+    g = torch.Generator().manual_seed(100 * n + B)
+    src = torch.randn(B, T, n, generator=g) * torch.linspace(0.5, 1.5, n)
+    perms = list(itertools.permutations(range(n)))
+    est = torch.stack([src[b][:, list(perms[(3 * b + 1) % len(perms)])] for b in range(B)])
+    est = est * 0.8 + torch.randn(est.shape, generator=g) * 0.05
+    mix = src.sum(-1)
+    got = scoring.si_snr_pit(est.to(DEV), src.to(DEV), mix.to(DEV))
+    best, imp, perm, pairs = restate.pit_si_snr_improvement(est, src, mix)
+    assert torch.equal(got["perm"].cpu(), perm)
+    assert (got["pairs"].cpu().double() - pairs).abs().max() < 2e-3      # dB
+    assert (got["si_snr"].cpu().double() - best).abs().max() < 2e-3
+    assert (got["si_snr_i"].cpu().double() - imp).abs().max() < 2e-3
+    for b in range(B):          # the assignment row is the permutation itself: estimate i came from source perms[k][i]
+        assert tuple(got["assignment"][b].tolist()) == perms[int(perm[b])]
+
+
+def test_save_results_end_to_end_from_wav_files(tmp_path):
+    """The reference's evaluation loop (train_wsj0mix.py:503-604) on top of the drop-in separator: wav files on disk in,
+    one utterance at a time with every length different, ``test_results.csv`` + ``audio_results/*.wav`` out.  The CSV's
+    SI-SNR columns must equal what the oracle's forward + oracle PIT give for the same files."""
+    import csv
+    from avse_challenge_b200 import scoring, wavio
+    from avse_challenge_b200.modules import MambaTasNetSeparator
+    hp = CONFIGS["tiny"]
+    sds = init_state_dicts(hp, 77)
+    sep = MambaTasNetSeparator.from_hparams(hp, use_graph=False).load_reference_state_dicts(sds).to(DEV)
+    items, refs = [], []
+    for k, T in enumerate((1603, 2000, 811)):
+        mix, src = synth_mixture(1, T, seed=50 + k)
+        paths = []
+        for name, sig in (("mix", mix[0]), ("s1", src[0, :, 0]), ("s2", src[0, :, 1])):
+            p = str(tmp_path / f"utt{k}_{name}.wav")
+            wavio.write_wav(p, sig, 8000)
+            paths.append(p)
+        items.append({"id": f"utt{k}", "mix": paths[0], "sources": paths[1:]})
+        with torch.no_grad():
+            ref = restate.separate(mix, sds, hp.n_mamba, scan_impl="c")
+        b, i, _, _ = restate.pit_si_snr_improvement(ref, src, mix)
+        refs.append((b.item(), i.item()))
+    avg = scoring.save_results(sep, items, str(tmp_path / "out"), num_spks=2, device=DEV, n_audio_files=1)
+    rows = list(csv.DictReader(open(tmp_path / "out" / "test_results.csv")))
+    assert [r["snt_id"] for r in rows] == ["utt0", "utt1", "utt2", "avg"]
+    for r, (b, i) in zip(rows[:3], refs):
+        assert r["sdr"] == "" and abs(float(r["si-snr"]) - b) < 5e-3 and abs(float(r["si-snr_i"]) - i) < 5e-3
+    assert abs(float(rows[3]["si-snr"]) - sum(b for b, _ in refs) / 3) < 5e-3 and abs(avg["si-snr_i"] - float(rows[3]["si-snr_i"])) < 1e-9
+    assert sorted(os.listdir(tmp_path / "out" / "audio_results")) == ["itemutt0_mix.wav", "itemutt0_source1.wav",
+                                                                      "itemutt0_source1hat.wav", "itemutt0_source2.wav",
+                                                                      "itemutt0_source2hat.wav"]
+    # an SDR backend plugs in through sdr_fn (mir_eval's bss_eval_sources in the reference, :564-572)
+    avg2 = scoring.save_results(sep, items[:1], str(tmp_path / "out2"), device=DEV,
+                                sdr_fn=lambda r, e: np.array([1.0, 3.0]) if e.std() > 0 else np.zeros(2))
+    assert avg2["sdr"] == 2.0 and avg2["sdr_i"] == 0.0
+
+
 def test_si_snr_pit_rejects_cpu_and_bad_shapes():
     from avse_challenge_b200 import scoring
     with pytest.raises(_lib.MtnError):
         scoring.si_snr_pit(torch.zeros(1, 100, 2), torch.zeros(1, 100, 2), torch.zeros(1, 100))
     with pytest.raises(_lib.MtnError):
-        scoring.si_snr_pit(torch.zeros(1, 100, 3, device=DEV), torch.zeros(1, 100, 3, device=DEV),
+        scoring.si_snr_pit(torch.zeros(1, 100, 5, device=DEV), torch.zeros(1, 100, 5, device=DEV),
                            torch.zeros(1, 100, device=DEV))
 
 
