@@ -18,6 +18,7 @@
 //    SiLU(z) gate / relu(mask)*mix_w fused in.
 #include "mtn_ptx.cuh"
 #include "mtn_host.h"
+#include <stdlib.h>
 
 namespace mtn {
 
@@ -43,10 +44,14 @@ struct GemmParams {
     int rowsq_parts;
 };
 
-template <int P, int BN>
+// CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA pair (2-CTA cluster, cta_group::2) per 256 x BN tile: each CTA stages its
+// own 128 rows of A and HALF of the B tile per k-block, so a stage is 2/3 of the one-CTA stage (64 KB instead of 96 KB at
+// P = 2, BN = 256: three stages instead of two) and each SM pulls a third less operand data through the crossbar -- the
+// wide fp32-mode GEMMs sat at 55 % / 72 % tensor-pipe utilisation with a two-deep ring (profiles/r01/gemm_ncu_metrics.txt).
+template <int P, int BN, int CG = 1>
 struct GemmCfg {
     static constexpr int A_BYTES = BM * BK * 2;
-    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int B_BYTES = (BN / CG) * BK * 2;       // bytes of B this CTA stages per plane
     static constexpr int STAGE_BYTES = P * (A_BYTES + B_BYTES);
     static constexpr int STAGING_BYTES = EPI_WARPS * 32 * STG_LD * 4;
     static constexpr int BAR_BYTES = 256;
@@ -60,11 +65,11 @@ struct GemmCfg {
     static_assert(B_BYTES % 1024 == 0, "B tile must keep 1024B alignment for SWIZZLE_128B");
 };
 
-template <int P, int BN, int EPI, bool OUT_BF16>
+template <int P, int BN, int EPI, bool OUT_BF16, int CG = 1>
 __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                     const GemmParams p) {
-    using Cfg = GemmCfg<P, BN>;
+    using Cfg = GemmCfg<P, BN, CG>;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-B align inside the shared window without leaving the shared address space (keeps LDS/STS)
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -77,49 +82,65 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const int crank = CG == 2 ? int(cluster_ctarank()) : 0;   // 0 = the pair's leader (issues the MMAs)
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&mapA);
         tma_prefetch_desc(&mapB);
         for (int s = 0; s < Cfg::STAGES; ++s) {
-            mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
+            mbar_init(&full_bar[s], 1);            // CG 2: only the leader's is used (both CTAs' loads signal it)
+            mbar_init(&empty_bar[s], 1);           // CG 2: the leader's commit arrives on both CTAs' barriers
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull_bar[a], 1);
-            mbar_init(&tempty_bar[a], EPI_WARPS);  // one arrive per epilogue warp
+            mbar_init(&tempty_bar[a], CG * EPI_WARPS);  // one arrive per epilogue warp (CG 2: of both CTAs, on the leader's)
         }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    if (warp == 1) {
+        if (CG == 2) tmem_alloc_2sm(tmem_slot, Cfg::TMEM_COLS);
+        else tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    }
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all();   // the peer's barriers must be initialised before anything is signalled on them
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     const int kblocks = p.K / BK;
-    const int tiles_per_group = p.tiles_m * p.tiles_n;
+    // CG 2: the tile loop runs over PAIR tiles of 256 rows; CTA `crank` owns rows [mt * 256 + crank * 128, +128)
+    const int tiles_m = CG == 2 ? (p.tiles_m + 1) / 2 : p.tiles_m;
+    const int tiles_per_group = tiles_m * p.tiles_n;
     const int total_tiles = tiles_per_group * p.groups;
+    const int tile0 = CG == 2 ? int(blockIdx.x) / 2 : int(blockIdx.x);
+    const int tile_step = CG == 2 ? int(gridDim.x) / 2 : int(gridDim.x);
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer (one thread)
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int tile = tile0; tile < total_tiles; tile += tile_step) {
                 const int g = tile / tiles_per_group;
                 const int r = tile - g * tiles_per_group;
                 const int mt = r / p.tiles_n;
                 const int nt = r - mt * p.tiles_n;
+                const int arow = (mt * CG + crank) * BM;                  // rows past M are zero-filled by TMA
+                const int brow = g * p.N + nt * BN + crank * (BN / CG);   // this CTA's share of the B tile
                 for (int kb = 0; kb < kblocks; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                    if (CG == 1 || crank == 0) mbar_arrive_expect_tx(&full_bar[stage], CG * Cfg::STAGE_BYTES);
                     uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
                     uint8_t* sb = sa + P * Cfg::A_BYTES;
 #pragma unroll
                     for (int pl = 0; pl < P; ++pl) {
-                        tma_load_3d(sa + pl * Cfg::A_BYTES, &mapA, &full_bar[stage], g * p.K + kb * BK, mt * BM, pl);
-                        tma_load_3d(sb + pl * Cfg::B_BYTES, &mapB, &full_bar[stage], kb * BK, g * p.N + nt * BN, pl);
+                        if (CG == 2) {
+                            tma_load_3d_2sm(sa + pl * Cfg::A_BYTES, &mapA, &full_bar[stage], g * p.K + kb * BK, arow, pl);
+                            tma_load_3d_2sm(sb + pl * Cfg::B_BYTES, &mapB, &full_bar[stage], kb * BK, brow, pl);
+                        } else {
+                            tma_load_3d(sa + pl * Cfg::A_BYTES, &mapA, &full_bar[stage], g * p.K + kb * BK, arow, pl);
+                            tma_load_3d(sb + pl * Cfg::B_BYTES, &mapB, &full_bar[stage], kb * BK, brow, pl);
+                        }
                     }
                     if (++stage == Cfg::STAGES) {
                         stage = 0;
@@ -131,13 +152,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         __syncwarp();
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer (one thread)
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+        if (lane == 0 && crank == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(CG * BM, BN);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int tile = tile0; tile < total_tiles; tile += tile_step) {
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_COLS;
@@ -150,21 +171,28 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                     for (int kk = 0; kk < BK / 16; ++kk) {
                         const uint64_t a_hi = make_smem_desc_sw128(sa + kk * 32);
                         const uint64_t b_hi = make_smem_desc_sw128(sb + kk * 32);
-                        tc_mma_bf16(d_tmem, a_hi, b_hi, idesc, (kb | kk) != 0 ? 1u : 0u);
+                        auto mma = [&](uint64_t da, uint64_t db, uint32_t accum) {
+                            if (CG == 2) tc_mma_bf16_2sm(d_tmem, da, db, idesc, accum);
+                            else tc_mma_bf16(d_tmem, da, db, idesc, accum);
+                        };
+                        mma(a_hi, b_hi, (kb | kk) != 0 ? 1u : 0u);
                         if (P == 2) {
                             const uint64_t a_lo = make_smem_desc_sw128(sa + Cfg::A_BYTES + kk * 32);
                             const uint64_t b_lo = make_smem_desc_sw128(sb + Cfg::B_BYTES + kk * 32);
-                            tc_mma_bf16(d_tmem, a_lo, b_hi, idesc, 1u);
-                            tc_mma_bf16(d_tmem, a_hi, b_lo, idesc, 1u);
+                            mma(a_lo, b_hi, 1u);
+                            mma(a_hi, b_lo, 1u);
                         }
                     }
-                    tc_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+                    // smem slot reusable once these MMAs retire (CG 2: in both CTAs)
+                    if (CG == 2) tc_commit_2sm(&empty_bar[stage]);
+                    else tc_commit(&empty_bar[stage]);
                     if (++stage == Cfg::STAGES) {
                         stage = 0;
                         phase ^= 1;
                     }
                 }
-                tc_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+                if (CG == 2) tc_commit_2sm(&tfull_bar[acc]);   // accumulator complete -> both CTAs' epilogues
+                else tc_commit(&tfull_bar[acc]);
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;
             }
@@ -184,7 +212,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         auto load_ss = [&](int tile2) {  // sum of the partial-sum planes (fixed order) for this lane's 4 rows of tile2
             if (tile2 >= total_tiles) return;
             const int r2 = tile2 % tiles_per_group;
-            const int rowb = (r2 / p.tiles_n) * BM + q * 32 + (lane >> 2);
+            const int rowb = ((r2 / p.tiles_n) * CG + crank) * BM + q * 32 + (lane >> 2);
 #pragma unroll
             for (int it = 0; it < 4; ++it) {
                 const int grow = rowb + it * 8;
@@ -204,12 +232,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                               : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         };
-        if (p.rowsq) load_ss(blockIdx.x);
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        auto release_acc = [&](int acc_) {   // hand the accumulator back to the (leader's) MMA thread
+            if (CG == 2 && crank != 0) mbar_arrive_remote(&tempty_bar[acc_], 0);
+            else mbar_arrive(&tempty_bar[acc_]);
+        };
+        if (p.rowsq) load_ss(tile0);
+        for (int tile = tile0; tile < total_tiles; tile += tile_step) {
             const int g = tile / tiles_per_group;
             const int r = tile - g * tiles_per_group;
-            const int mt = r / p.tiles_n;
-            const int nt = r - mt * p.tiles_n;
+            const int mt = (r / p.tiles_n) * CG + crank;     // this CTA's 128-row tile
+            const int nt = r - (r / p.tiles_n) * p.tiles_n;
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_base = tmem_base + acc * Cfg::ACC_COLS + (uint32_t(q * 32) << 16);
@@ -222,7 +254,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             if (p.rowsq) {
 #pragma unroll
                 for (int it = 0; it < 4; ++it) rstd[it] = rsqrtf(fmaf(ss_next[it], p.rowsq_scale, p.rowsq_eps));
-                load_ss(tile + gridDim.x);
+                load_ss(tile + tile_step);
             }
             float4 auxn[4];  // RESADD: residual rows of the warp's next chunk, requested one chunk ahead
             if (EPI == MTN_EPI_RESADD) load_res(auxn, row0, nt * BN + 16 * chalf);
@@ -236,7 +268,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                     // last TMEM read of this accumulator by this warp: hand it back to the MMA warp early
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                    if (lane == 0) release_acc(acc);
                     released = true;
                 }
                 // registers (thread = row) -> padded smem
@@ -379,7 +411,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             if (!released) {  // a warp with no chunk of its own (cannot happen for BN >= 32) still has to release
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                if (lane == 0) release_acc(acc);
             }
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
@@ -387,16 +419,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all();   // neither CTA may leave (or free TMEM) while the pair's MMAs / remote arrives are in flight
+    else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+        if (CG == 2) tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
+        else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
     }
 }
 
-template <int P, int BN, int EPI, bool OUT_BF16>
+template <int P, int BN, int EPI, bool OUT_BF16, int CG = 1>
 static int launch_gemm(const mtn_gemm_args* a, cudaStream_t stream) {
-    using Cfg = GemmCfg<P, BN>;
+    using Cfg = GemmCfg<P, BN, CG>;
     CUtensorMap mapA, mapB;
     {
         uint64_t dims[3] = {(uint64_t)a->lda, (uint64_t)a->a_rows, (uint64_t)P};
@@ -409,7 +443,7 @@ static int launch_gemm(const mtn_gemm_args* a, cudaStream_t stream) {
         uint64_t rows = (uint64_t)a->groups * a->N;
         uint64_t dims[3] = {(uint64_t)a->K, rows, (uint64_t)P};
         uint64_t str[2] = {(uint64_t)a->K * 2, rows * a->K * 2};
-        uint32_t box[3] = {BK, BN, 1};
+        uint32_t box[3] = {BK, BN / CG, 1};
         if (!encode_tmap(&mapB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, a->w, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B))
             return MTN_ECUDA;
     }
@@ -434,19 +468,66 @@ static int launch_gemm(const mtn_gemm_args* a, cudaStream_t stream) {
     p.rowsq_parts = a->rowsq_parts;
     p.tiles_m = (a->M + BM - 1) / BM;
     p.tiles_n = a->N / BN;
-    auto kern = gemm_tcgen05_kernel<P, BN, EPI, OUT_BF16>;
+    auto kern = gemm_tcgen05_kernel<P, BN, EPI, OUT_BF16, CG>;
     static std::atomic<unsigned long long> attr_done{0};   // per template instantiation, one bit per device
     if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(kern), Cfg::SMEM_BYTES, attr_done, "gemm")) return rc;
-    int total = p.tiles_m * p.tiles_n * p.groups;
     int cap = a->max_ctas > 0 ? a->max_ctas : num_sms();
+    if (CG == 2) {
+        // one CTA pair (a 2-CTA cluster: both SMs of a TPC) per 256-row tile; persistent over at most cap / 2 pairs
+        const int pairs_total = ((p.tiles_m + 1) / 2) * p.tiles_n * p.groups;
+        int pairs = cap / 2 < pairs_total ? cap / 2 : pairs_total;
+        if (pairs < 1) pairs = 1;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * pairs, 1, 1);
+        cfg.blockDim = dim3(64 + 32 * EPI_WARPS, 1, 1);
+        cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, kern, mapA, mapB, p);
+        if (e != cudaSuccess) {
+            set_error("gemm(2cta): cluster launch failed: %s", cudaGetErrorString(e));
+            return MTN_ECUDA;
+        }
+        return MTN_OK;
+    }
+    int total = p.tiles_m * p.tiles_n * p.groups;
     int grid = total < cap ? total : cap;
     kern<<<grid, 64 + 32 * EPI_WARPS, Cfg::SMEM_BYTES, stream>>>(mapA, mapB, p);
     MTN_CUDA_LAUNCH_CHECK("gemm");
     return MTN_OK;
 }
 
+// CTA pairs (cta_group::2) for the mainloop-bound GEMMs: 256-wide N tiles, K >= 512 and at least one 256-row pair tile per
+// SM pair.  Measured on B200 (tools/gemm_bench.py --ab, profiles/r02/gemm_2cta_ab_*.jsonl; outputs bit-identical):
+// out_proj (K = 1024) 0.177 -> 0.156 ms = 94 % of the sustained bf16 tensor peak, L bf16 out_proj (K = 2048) 0.489 -> 0.445;
+// but in_proj (K = 256: four k-blocks per tile) 0.206 -> 0.227 and mask 0.195 -> 0.216 -- with so short a main loop the
+// accumulator hand-off between MMA and epilogue is paid per tile, and in a pair it crosses two SMs.  Hence the K rule.
+// MTN_GEMM_2CTA = 0 / 1 / 2 in the environment: never / by this rule (default) / whenever the shape allows (A/B runs).
+static bool use_cta_pairs(const mtn_gemm_args* a, int bn) {
+    if (bn != 256 || a->groups != 1) return false;
+    int mode = 1;
+    if (const char* v = getenv("MTN_GEMM_2CTA")) mode = atoi(v);
+    if (mode == 0) return false;
+    if (mode == 1 && a->K < 512) return false;
+    const long pair_tiles = long((a->M + 2 * BM - 1) / (2 * BM)) * (a->N / bn);
+    const long cap = a->max_ctas > 0 ? a->max_ctas : num_sms();
+    return pair_tiles >= cap / 2;
+}
+
 template <int P, int BN>
 static int dispatch_epi(const mtn_gemm_args* a, cudaStream_t s) {
+    if (BN == 256 && use_cta_pairs(a, BN)) {
+        if (a->epilogue == MTN_EPI_STORE && !a->out_bf16) return launch_gemm<P, BN, MTN_EPI_STORE, false, 2>(a, s);
+        if (a->epilogue == MTN_EPI_INPROJ && !a->out_bf16) return launch_gemm<P, BN, MTN_EPI_INPROJ, false, 2>(a, s);
+        if (a->epilogue == MTN_EPI_INPROJ && a->out_bf16) return launch_gemm<P, BN, MTN_EPI_INPROJ, true, 2>(a, s);
+        if (a->epilogue == MTN_EPI_MASK && !a->out_bf16) return launch_gemm<P, BN, MTN_EPI_MASK, false, 2>(a, s);
+    }
     if (a->epilogue == MTN_EPI_STORE && !a->out_bf16) return launch_gemm<P, BN, MTN_EPI_STORE, false>(a, s);
     if (BN <= 64) {
         if (a->epilogue == MTN_EPI_XPROJ && !a->out_bf16) return launch_gemm<P, BN, MTN_EPI_XPROJ, false>(a, s);

@@ -1045,6 +1045,7 @@ static int dispatch_scan_variant(const mtn_scan_args* a, cudaStream_t s) {
             case 61: return launch_scan_pair<P, R, NDBL, ZT, true, 1>(a, s);               // 1 state pair on the FMA-pipe exp2
             case 62: return launch_scan_pair<P, R, NDBL, ZT, true, 2>(a, s);               // 2 state pairs
             case 68: return launch_scan_pair<P, R, NDBL, ZT, true, 0, false, 32>(a, s);    // 64 ns helper poll (r02 start)
+            case 69: return launch_scan_pair<P, R, NDBL, ZT, true, 0, false, 64>(a, s);    // the other softplus form
             // timing-only ablations (WRONG results)
             case 63: return launch_scan_pair<P, R, NDBL, ZT, true, 0, false, 3>(a, s);     // helper: no dt_proj/softplus/gate
             case 64: return launch_scan_pair<P, R, NDBL, ZT, true, 0, false, 4>(a, s);     // recurrence: no MUFU
@@ -1094,8 +1095,9 @@ static int dispatch_scan_variant(const mtn_scan_args* a, cudaStream_t s) {
 
 template <int P, typename ZT>
 static int dispatch_scan_r(const mtn_scan_args* a, cudaStream_t s) {
-#ifdef MTN_SCAN_DEV  // fast-iteration build: BASELINE config 2 instantiation only
+#ifdef MTN_SCAN_DEV  // fast-iteration build: BASELINE config 2 / 3 instantiations only
     if (a->R == 16 && a->n_dbl == 48) return dispatch_scan_variant<P, 16, 48, ZT>(a, s);
+    if (a->R == 32 && a->n_dbl == 64) return dispatch_scan_variant<P, 32, 64, ZT>(a, s);
     set_error("scan: MTN_SCAN_DEV build");
     return MTN_EINVAL;
 #else
@@ -1131,8 +1133,8 @@ extern "C" int mtn_scan_fwd(const mtn_scan_args* a, mtn_stream_t stream) {
     MTN_REQUIRE(!a->dtp || (reinterpret_cast<uintptr_t>(a->dtp) & 15) == 0, "scan: dtp must be 16-byte aligned");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     if (a->planes == 2 && !a->z_bf16) return dispatch_scan_r<2, float>(a, s);
-#ifndef MTN_SCAN_DEV
     if (a->planes == 1 && a->z_bf16) return dispatch_scan_r<1, __nv_bfloat16>(a, s);
+#ifndef MTN_SCAN_DEV
     if (a->planes == 1 && !a->z_bf16) return dispatch_scan_r<1, float>(a, s);
 #endif
     set_error("scan: unsupported planes=%d z_bf16=%d", a->planes, a->z_bf16);

@@ -315,6 +315,15 @@ __device__ __forceinline__ void splitn_bf16(float x0, float x1, uint32_t (&pl)[N
 // error ~2^-24 like the FMA form), 2 in bf16 mode (three passes, ~2^-16; the reference's autocast path rounds this GEMM's
 // operands AND its result to bf16, selective_scan_interface.py:174-176,187).
 // ABL (dev builds, timing only, WRONG results): bit 0 skips the MMA + softplus, bit 1 the gate / store.
+// softplus with TWO MUFU ops and no polynomial: max(x,0) + ln2 * lg2(1 + exp(-|x|)).  1 + e rounds e to 2^-24 absolute,
+// so tiny deltas lose RELATIVE accuracy (6e-8 absolute on delta) -- irrelevant once the activations around the scan are
+// bf16 (bf16 mode), where it saves 64 of the helper's FMA-pipe instructions per tile; fp32 mode keeps softplus2_1mufu.
+__device__ __forceinline__ float2 softplus2_2mufu(float x0, float x1) {
+    const float e0 = ex2_approx(-1.4426950408889634f * fabsf(x0)), e1 = ex2_approx(-1.4426950408889634f * fabsf(x1));
+    const float2 l = make_float2(lg2_approx(1.0f + e0), lg2_approx(1.0f + e1));
+    return __ffma2_rn(l, make_float2(0.6931471805599453f, 0.6931471805599453f), make_float2(fmaxf(x0, 0.f), fmaxf(x1, 0.f)));
+}
+
 template <int P, int R, int NDBL, typename ZT, bool WY, int ABL = 0>
 __device__ __forceinline__ void scan_pair_helper(uint8_t* ring, float* slots, uint8_t* zbuf_all, uint64_t* full_bar,
                                                   uint64_t* empty_bar, uint64_t* prepped, uint64_t* ydone,
@@ -499,8 +508,11 @@ __device__ __forceinline__ void scan_pair_helper(uint8_t* ring, float* slots, ui
             const bool v0 = g < nvalid, v1 = g + 8 < nvalid;   // rows past the utterance end: delta = 0 -> state unchanged
 #pragma unroll
             for (int nb = 0; nb < 4; ++nb) {
-                float2 d0 = (ABL & 1) ? make_float2(acc[nb][0], acc[nb][1]) : softplus2_1mufu(acc[nb][0], acc[nb][1]);
-                float2 d1 = (ABL & 1) ? make_float2(acc[nb][2], acc[nb][3]) : softplus2_1mufu(acc[nb][2], acc[nb][3]);
+                constexpr bool SP2 = (P == 1) != bool(ABL & 64);   // ABL bit 6 (dev builds): the other form, for A/B timing
+                float2 d0 = (ABL & 1) ? make_float2(acc[nb][0], acc[nb][1])
+                            : SP2     ? softplus2_2mufu(acc[nb][0], acc[nb][1]) : softplus2_1mufu(acc[nb][0], acc[nb][1]);
+                float2 d1 = (ABL & 1) ? make_float2(acc[nb][2], acc[nb][3])
+                            : SP2     ? softplus2_2mufu(acc[nb][2], acc[nb][3]) : softplus2_1mufu(acc[nb][2], acc[nb][3]);
                 if (nvalid < SC_TT) {
                     if (!v0) d0 = make_float2(0.f, 0.f);
                     if (!v1) d1 = make_float2(0.f, 0.f);

@@ -258,13 +258,24 @@ class MambaStack(LayerPlan):
 class SeparatorEngine(LayerPlan):
     """mix [B, T] fp32 (CUDA) -> est_source [B, T, n_spk] fp32, all in hand-written sm_100a kernels."""
 
+    # Batches this small are bound by the scan's serial chain, not by throughput (B = 1, 4 s @ 8 kHz, S: 64 warp pairs on
+    # 148 SMs walk 3 999 steps: 8.2 of the batch plan's 9.0 ms).  The chunked-scan plan (parallel.SequenceParallelSeparator
+    # on this process alone: summary pass -> fold -> seeded pass over SMALL_BATCH_CHUNKS time chunks) cuts that chain and
+    # takes 2.06 ms per utterance as one CUDA graph, so up to SMALL_BATCH_MAX utterances run through it one after the other.
+    SMALL_BATCH_MAX = 3
+    SMALL_BATCH_CHUNKS = 16
+    SMALL_BATCH_MIN_FRAMES = 1024
+
     def __init__(self, hp: HParams, sds: dict, device="cuda", mode: str = "fp32", use_graph: bool = True,
-                 fuse_norm: bool = False):
+                 fuse_norm: bool = False, small_batch_plan: bool = True):
         self._init_plan(hp, mode, device)
         if hp.mask_nonlinear not in ("relu", "softmax"):
             raise ValueError("Unsupported mask non-linear function")      # mamba_masknet.py:138
         self.use_graph = use_graph
         self.fuse_norm = fuse_norm
+        self.small_batch_plan = (small_batch_plan and hp.bidirectional and hp.mask_nonlinear == "relu"
+                                 and not self.tc_dt)   # what the chunked driver implements
+        self._chunked = None
         with torch.cuda.device(self.device):
             self.w = PackedWeights(hp, sds, self.device, mode)
         # a graph replays into the buffers of its workspace: evicting a workspace drops the graph captured against it
@@ -366,6 +377,8 @@ class SeparatorEngine(LayerPlan):
         if T < 16:
             raise _lib.MtnError(f"T={T}: need at least one 16-sample frame")
         with torch.cuda.device(self.device):   # launches go to the engine's device, whatever the caller has current
+            if taps is None and self.plan_for(B, T) == "chunked":
+                return torch.cat([self._chunked_plan()(mix[b:b + 1]) for b in range(B)], dim=0)
             ws = self.workspace(B, T)
             ws.mix[:, :T].copy_(mix, non_blocking=True)
             if taps is not None or not self.use_graph:
@@ -374,6 +387,21 @@ class SeparatorEngine(LayerPlan):
             return ws.est.clone()
 
     __call__ = forward
+
+    def plan_for(self, batch: int, T: int) -> str:
+        """``"chunked"`` (per-utterance chunked-scan plan, small batches of long utterances) or ``"batch"``."""
+        if (self.small_batch_plan and batch <= self.SMALL_BATCH_MAX and T >= 16
+                and self.hp.frames(T) >= self.SMALL_BATCH_MIN_FRAMES):
+            return "chunked"
+        return "batch"
+
+    def _chunked_plan(self):
+        if self._chunked is None:
+            from .parallel import CudaSeqBackend, SequenceParallelSeparator
+            be = CudaSeqBackend(self.hp, None, self.device, self.mode, weights=self.w)      # shares the packed weights
+            self._chunked = SequenceParallelSeparator(self.hp, backend=be, sub_chunks=self.SMALL_BATCH_CHUNKS, group="local",
+                                                      use_graph=self.use_graph)
+        return self._chunked
 
     def _graph_for(self, ws: Workspace, key):
         """The whole-forward CUDA graph of this shape (captured on first use, after one eager run that sets the kernels'

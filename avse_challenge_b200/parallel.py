@@ -48,7 +48,7 @@ class Comm:
 
     def __init__(self, group=None):
         self.group = group
-        self.on = dist.is_available() and dist.is_initialized()
+        self.on = group != "local" and dist.is_available() and dist.is_initialized()   # "local": this process alone
         self.rank = dist.get_rank(group) if self.on else 0
         self.world = dist.get_world_size(group) if self.on else 1
 
@@ -142,7 +142,9 @@ class CudaSeqBackend:
     All activation buffers of a (local length, plan) shape are allocated once and reused (``_Shape``, LRU-bounded), so a
     forward allocates nothing -- which is also what makes it capturable in a CUDA graph together with its collectives."""
 
-    def __init__(self, hp: HParams, sds: dict, device, mode: str = "fp32"):
+    def __init__(self, hp: HParams, sds: Optional[dict], device, mode: str = "fp32", weights=None):
+        """``weights``: an already packed ``engine.PackedWeights`` of the same hparams / mode / device (shares the device
+        copies with a ``SeparatorEngine``); otherwise packed here from ``sds``."""
         from . import _lib, ops
         from .engine import MODES, PackedWeights, resolve_device
         if not torch.cuda.is_available():
@@ -152,8 +154,11 @@ class CudaSeqBackend:
         self.hp, self.mode, self.device = hp, mode, resolve_device(device)
         self.P = MODES[mode]["planes"]
         self.xz_dt = torch.bfloat16 if MODES[mode]["xz_bf16"] else torch.float32
-        with torch.cuda.device(self.device):
-            self.w = PackedWeights(hp, sds, self.device, mode)
+        if weights is not None:
+            self.w = weights
+        else:
+            with torch.cuda.device(self.device):
+                self.w = PackedWeights(hp, sds, self.device, mode)
         self.n_layers = hp.n_mamba
         self.di, self.enc_dim = hp.d_inner, hp.enc_dim
         self.tc_dt = hp.dt_rank >= 32 and mode == "fp32"    # same rule as SeparatorEngine
@@ -344,9 +349,22 @@ class SequenceParallelSeparator:
         # length.  On one rank that is also the low-latency plan for ONE short utterance: the scan's serial chain is
         # sub_chunks times shorter than in the batch plan (4 s @ 8 kHz, S: 9.0 ms -> 2.1 ms at 16 sub-chunks).
         # The point-to-point chain (exchange="sendrecv") stays eager when world > 1.
-        self.use_graph = use_graph and backend is None and (self.comm.world == 1 or exchange == "allgather")
+        cuda_be = backend is None or isinstance(backend, CudaSeqBackend)
+        self.use_graph = use_graph and cuda_be and (self.comm.world == 1 or exchange == "allgather")
         self._graphs = LRUDict()   # one whole-forward graph (with its static input / output) per recording length
         self.graph_failed = None   # set to the error text if a multi-rank capture was refused (the driver then runs eagerly)
+
+    def close(self):
+        """Drop the captured graphs.  Call this (or delete the object) BEFORE ``dist.destroy_process_group()``: a live CUDA
+        graph that holds captured NCCL collectives keeps the communicator busy and the teardown waits for it forever
+        (observed on B200 / NCCL 2.28: tools/seqpar_check.py hung at exit until it released the driver first)."""
+        self._graphs.clear()
+
+    def __del__(self):
+        try:
+            self._graphs.clear()
+        except Exception:
+            pass
 
     # ---- geometry
     def plan(self, T: int) -> SeqPlan:

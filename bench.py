@@ -498,7 +498,7 @@ def measure_longform(a, ctx, steps, warmup, cpu_baseline=True, parity=False, sam
         Tp = min(T, 12 * a.sample_rate) // 8 * 8
         clip = mix_cpu[:, :Tp].contiguous().to(dev)
         got = sp(clip)
-        ref = SeparatorEngine(hp, sds, device=dev, mode=a.mode, use_graph=False)(clip)
+        ref = SeparatorEngine(hp, sds, device=dev, mode=a.mode, use_graph=False, small_batch_plan=False)(clip)
         rms = ref.pow(2).mean().sqrt().clamp(min=1e-30)
         err = ((got - ref).abs().max() / rms).item()
         err, = ctx.max_over_ranks(err)

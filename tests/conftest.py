@@ -10,6 +10,18 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "small_batch_plan: keep SeparatorEngine's chunked plan for batches <= 3 enabled")
+
+
+@pytest.fixture(autouse=True)
+def _batch_plan_unless_asked(request, monkeypatch):
+    """The parity tests run small batches (1-3 utterances) to keep the CPU oracle affordable, but what they pin is the
+    BATCH plan of ``SeparatorEngine`` -- the one every benchmark configuration runs.  The engine would route such batches
+    through its per-utterance chunked-scan plan, so that plan is switched off here and has its own tests
+    (``@pytest.mark.small_batch_plan``)."""
+    if "small_batch_plan" not in request.keywords:
+        from avse_challenge_b200.engine import SeparatorEngine
+        monkeypatch.setattr(SeparatorEngine, "SMALL_BATCH_MAX", 0)
 
 
 @pytest.fixture(scope="session")

@@ -11,6 +11,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--hparams", default="S"); ap.add_argument("--batch", type=int, default=32)
 ap.add_argument("--L", type=int, default=3999); ap.add_argument("--mode", default="fp32")
 ap.add_argument("--iters", type=int, default=20); ap.add_argument("--only", default="")
+ap.add_argument("--ab", action="store_true", help="time every case with MTN_GEMM_2CTA=0 (one CTA per tile) and =2 (CTA pairs wherever the shape allows) and compare the outputs")
 a = ap.parse_args()
 hp = CONFIGS[a.hparams]; D, N, di, R = hp.d_model, hp.enc_dim, hp.d_inner, hp.dt_rank; nd = ops.n_dbl_for(R)
 P = 2 if a.mode == "fp32" else 1
@@ -40,15 +41,24 @@ for name, (A, W, m, n, k, kw, nbytes) in cases.items():
     if a.only and name not in a.only.split(","):
         continue
     run = lambda: ops.gemm(A, W, m, n, k, **kw)
-    for _ in range(3): run()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(a.iters): run()
-    e1.record(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / a.iters
-    groups = kw.get("groups", 1)
-    flops = 2.0 * m * n * k * groups * (3 if P == 2 else 1)
-    print(json.dumps({"gemm": name, "M": m, "N": n, "K": k, "groups": groups, "planes": P, "ms": round(ms, 4),
-                      "GBps_algorithmic": round(nbytes / ms / 1e6, 1), "frac_hbm_6541": round(nbytes / ms / 1e6 / 6541.1, 3),
-                      "TFLOPs_issued": round(flops / ms / 1e9, 1), "frac_bf16_1622": round(flops / ms / 1e9 / 1622.0, 3)}), flush=True)
+    ref_out = None
+    for pairs in (("0", "2") if a.ab else (os.environ.get("MTN_GEMM_2CTA", "1"),)):
+        os.environ["MTN_GEMM_2CTA"] = pairs          # read by the library at every call
+        kw["out"].zero_()
+        for _ in range(3): run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(a.iters): run()
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / a.iters
+        groups = kw.get("groups", 1)
+        flops = 2.0 * m * n * k * groups * (3 if P == 2 else 1)
+        rec = {"gemm": name, "cta_pairs": pairs, "M": m, "N": n, "K": k, "groups": groups, "planes": P, "ms": round(ms, 4),
+               "GBps_algorithmic": round(nbytes / ms / 1e6, 1), "frac_hbm_6541": round(nbytes / ms / 1e6 / 6541.1, 3),
+               "TFLOPs_issued": round(flops / ms / 1e9, 1), "frac_bf16_sustained_1372": round(flops / ms / 1e9 / 1371.8, 3)}
+        if ref_out is None:
+            ref_out = kw["out"].float().clone()
+        else:
+            rec["max_abs_diff_vs_one_cta"] = (kw["out"].float() - ref_out).abs().max().item()
+        print(json.dumps(rec), flush=True)

@@ -44,9 +44,12 @@ if world > 1:
 out = {"world": world, "hparams": a.hparams, "T": T, "frames": hp.frames(T), "sub_chunks": a.sub_chunks,
        "exchange": a.exchange, "mode": a.mode, "s_per_forward": t.item(), "audio_s_per_s": T / a.sample_rate / t.item()}
 if rank == 0 and not a.no_check:
-    one = SeparatorEngine(hp, sds, device=dev, mode=a.mode, use_graph=False)(mix_d)
+    one = SeparatorEngine(hp, sds, device=dev, mode=a.mode, use_graph=False, small_batch_plan=False)(mix_d)
     out["max_abs_diff_vs_unchunked/rms"] = ((est - one).abs().max() / one.pow(2).mean().sqrt()).item()
 if rank == 0:
     print(json.dumps(out), flush=True)
+sp.close()          # captured NCCL graphs must go before the process group does
+del sp
+torch.cuda.synchronize()
 if world > 1:
     dist.destroy_process_group()

@@ -34,7 +34,7 @@ def timed(fn):
     return e0.elapsed_time(e1) / a.iters
 
 
-eng = SeparatorEngine(hp, sds, device="cuda", mode=a.mode)
+eng = SeparatorEngine(hp, sds, device="cuda", mode=a.mode, small_batch_plan=False)   # the batch plan, for comparison
 ref = eng(mix)
 res = {"shape": [a.hparams, 1, T, a.mode], "batch_plan_ms": round(timed(lambda: eng(mix)), 3), "chunked": []}
 rms = ref.pow(2).mean().sqrt()
