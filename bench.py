@@ -395,7 +395,15 @@ def measure_batch(a, ctx, steps, warmup, cpu_baseline=True, parity=False, sample
     par = None
     if parity:
         pmix, _ = synth_mixture(2, T, a.sample_rate, seed=4321)
+        sbp = getattr(eng, "small_batch_plan", False)
+        if sbp:
+            eng.small_batch_plan = False          # "alone" = the batch plan at B = 2, the kernels the full batch runs
         alone = eng.forward(pmix.to(dev))
+        d_chunked = None
+        if sbp:
+            eng.small_batch_plan = True           # what forward() picks for so small a batch: the chunked-scan plan
+            chunked = eng.forward(pmix.to(dev))
+            d_chunked = ((chunked - alone).abs().max() / alone.pow(2).mean().sqrt().clamp(min=1e-30)).item()
         ws0 = eng.workspace(a.batch, T)
         ws0.mix[:, :T].copy_(mix_cpu.to(dev))
         ws0.mix[:2, :T].copy_(pmix.to(dev))
@@ -406,7 +414,9 @@ def measure_batch(a, ctx, steps, warmup, cpu_baseline=True, parity=False, sample
         d_ranks = ((allr - allr[0:1]).abs().max() / rms).item()
         par = {"max_abs_over_rms": max(d_batch, d_ranks), "across_ranks": d_ranks, "batch_vs_alone": d_batch, "world": world,
                "check": "the same 2 utterances separated by every rank's engine, compared across the ranks and, on each "
-                        "rank, inside the full batch against run alone"}
+                        "rank, inside the full batch against run alone (batch plan both times)"}
+        if d_chunked is not None:
+            par["small_batch_chunked_plan_vs_batch_plan"] = d_chunked
 
     # ---- device-resident timing (value): inputs already in HBM, graph replay
     ws = eng.workspace(a.batch, T)
