@@ -1046,6 +1046,12 @@ static int dispatch_scan_variant(const mtn_scan_args* a, cudaStream_t s) {
             case 62: return launch_scan_pair<P, R, NDBL, ZT, true, 2>(a, s);               // 2 state pairs
             case 68: return launch_scan_pair<P, R, NDBL, ZT, true, 0, false, 32>(a, s);    // 64 ns helper poll (r02 start)
             case 69: return launch_scan_pair<P, R, NDBL, ZT, true, 0, false, 64>(a, s);    // the other softplus form
+            case 70: return launch_scan_duo<P, R, NDBL, ZT>(a, s);                          // two 8-state recurrence warps per group
+            case 71: return launch_scan_duo<P, R, NDBL, ZT, 4>(a, s);                       // ... timing only: no MUFU
+            case 74: return launch_scan_pair<P, R, NDBL, ZT, true, 0, false, 128>(a, s);   // recurrence warps = the higher warp ids
+            case 75: return launch_scan_duo<P, R, NDBL, ZT, 128>(a, s);                     // duo, helper = the lowest warp ids
+            case 72: return launch_scan_duo<P, R, NDBL, ZT, 3>(a, s);                       // ... timing only: idle helper
+            case 73: return launch_scan_duo<P, R, NDBL, ZT, 7>(a, s);                       // ... timing only: idle helper, no MUFU
             // timing-only ablations (WRONG results)
             case 63: return launch_scan_pair<P, R, NDBL, ZT, true, 0, false, 3>(a, s);     // helper: no dt_proj/softplus/gate
             case 64: return launch_scan_pair<P, R, NDBL, ZT, true, 0, false, 4>(a, s);     // recurrence: no MUFU

@@ -240,14 +240,18 @@ __device__ __forceinline__ void scan_pair_recur(const uint8_t* ring, float* slot
 // channel), the fragment stores and the 16-byte segment accesses are all conflict free.
 constexpr int P2_DS = 36;
 
-template <int P, int NDBL>
+// DUO (mtn "duo" mapping below): TWO recurrence warps per 32 channels, 8 states each.  The pair slot then holds three planes
+// [delta copy of half 0 -> y0 | delta copy of half 1 -> y1 | u] (each half overwrites ITS OWN delta copy with its partial y, so
+// the halves never have to wait for each other inside a tile) and there are two slots instead of three.
+template <int P, int NDBL, bool DUO = false>
 struct ScanSmemPair {
-    static constexpr int SLOTS = 3;
+    static constexpr int SLOTS = DUO ? 2 : 3;
+    static constexpr int PLANES = DUO ? 3 : 2;
     static constexpr int U_BYTES = P * SC_TT * SC_CH * 2;
     static constexpr int NB = NDBL;
     static constexpr int D_BYTES = SC_TT * NB * 4;
     static constexpr int STAGE_BYTES = U_BYTES + D_BYTES;
-    static constexpr int PAIR_SLOT_BYTES = 2 * SC_TT * P2_DS * 4;        // [delta -> y | u] x 16 rows x 36 floats
+    static constexpr int PAIR_SLOT_BYTES = PLANES * SC_TT * P2_DS * 4;   // [delta -> y | u] x 16 rows x 36 floats
     static constexpr int SLOT_BYTES = 4 * PAIR_SLOT_BYTES;
     static constexpr int ZBUF_BYTES = 4 * SC_TT * 32 * 4;                 // per pair 2 KB: [chunk j][lane][16 B]
     static constexpr int BAR_BYTES = (2 * 4 + 2 * 4 * SLOTS) * 8 + 16;
@@ -324,14 +328,14 @@ __device__ __forceinline__ float2 softplus2_2mufu(float x0, float x1) {
     return __ffma2_rn(l, make_float2(0.6931471805599453f, 0.6931471805599453f), make_float2(fmaxf(x0, 0.f), fmaxf(x1, 0.f)));
 }
 
-template <int P, int R, int NDBL, typename ZT, bool WY, int ABL = 0>
+template <int P, int R, int NDBL, typename ZT, bool WY, int ABL = 0, bool DUO = false>
 __device__ __forceinline__ void scan_pair_helper(uint8_t* ring, float* slots, uint8_t* zbuf_all, uint64_t* full_bar,
                                                   uint64_t* empty_bar, uint64_t* prepped, uint64_t* ydone,
                                                   const ScanParams& p, int w, int lane, int ch0, int b, int dir,
                                                   int ntiles, int Lb, const CUtensorMap* mapU, const CUtensorMap* mapD) {
-    using SM = ScanSmemPair<P, NDBL>;
+    using SM = ScanSmemPair<P, NDBL, DUO>;
     constexpr int S = SM::STAGES, NSLOT = SM::SLOTS, NB = SM::NB, DS = P2_DS;
-    constexpr int PLANE = SC_TT * DS, PAIRF = 2 * PLANE;
+    constexpr int PLANE = SC_TT * DS, PAIRF = SM::PLANES * PLANE, UPL = (SM::PLANES - 1) * PLANE;
     constexpr int KS = (R + 15) / 16;                            // k-steps of the dt_proj MMA (K = 16 each)
     constexpr int NS = P == 2 ? 3 : 2;
     constexpr bool ZF = sizeof(ZT) == 4;
@@ -404,8 +408,18 @@ __device__ __forceinline__ void scan_pair_helper(uint8_t* ring, float* slots, ui
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh) {
                     if (g + 8 * hh < nvalid) {
-                        const float4 ya = *reinterpret_cast<const float4*>(sy + hh * 8 * DS);
-                        const float4 yb = *reinterpret_cast<const float4*>(sy + hh * 8 * DS + 4);
+                        float4 ya = *reinterpret_cast<const float4*>(sy + hh * 8 * DS);
+                        float4 yb = *reinterpret_cast<const float4*>(sy + hh * 8 * DS + 4);
+                        if (DUO) {   // y = (states 0-7 + D * u) + (states 8-15), the two recurrence warps' partial sums
+                            const float4 yc = *reinterpret_cast<const float4*>(sy + PLANE + hh * 8 * DS);
+                            const float4 yd = *reinterpret_cast<const float4*>(sy + PLANE + hh * 8 * DS + 4);
+                            const float2 s0 = __fadd2_rn(make_float2(ya.x, ya.y), make_float2(yc.x, yc.y));
+                            const float2 s1 = __fadd2_rn(make_float2(ya.z, ya.w), make_float2(yc.z, yc.w));
+                            const float2 s2 = __fadd2_rn(make_float2(yb.x, yb.y), make_float2(yd.x, yd.y));
+                            const float2 s3 = __fadd2_rn(make_float2(yb.z, yb.w), make_float2(yd.z, yd.w));
+                            ya = make_float4(s0.x, s0.y, s1.x, s1.y);
+                            yb = make_float4(s2.x, s2.y, s3.x, s3.y);
+                        }
                         float zf[8];
                         if (ZF) {
                             const uint4 za = zbuf[32 * (2 * hh)], zb = zbuf[32 * (2 * hh + 1)];
@@ -522,10 +536,16 @@ __device__ __forceinline__ void scan_pair_helper(uint8_t* ring, float* slots, ui
                 sdl[8 * nb + 4] = d0.y;
                 sdl[8 * DS + 8 * nb] = d1.x;
                 sdl[8 * DS + 8 * nb + 4] = d1.y;
+                if (DUO) {   // the second recurrence warp's own copy
+                    sdl[PLANE + 8 * nb] = d0.x;
+                    sdl[PLANE + 8 * nb + 4] = d0.y;
+                    sdl[PLANE + 8 * DS + 8 * nb] = d1.x;
+                    sdl[PLANE + 8 * DS + 8 * nb + 4] = d1.y;
+                }
             }
             // u planes -> fp32, rows g / g + 8, channels [8 tig, 8 tig + 8) of this warp's 32
             const __nv_bfloat16* su = reinterpret_cast<const __nv_bfloat16*>(st) + g * SC_CH + w * 32 + tig * 8;
-            float* suo = slot + PLANE + g * DS + tig * 8;
+            float* suo = slot + UPL + g * DS + tig * 8;
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
                 const uint4 uh = *reinterpret_cast<const uint4*>(su + hh * 8 * SC_CH);
@@ -569,6 +589,213 @@ __device__ __forceinline__ void scan_pair_helper(uint8_t* ring, float* slots, ui
     }
 }
 
+// ------------------------------------------------------------------------------------------------ "duo" mapping
+// Two recurrence warps per 32 channels, 8 states each (HS = 0: states 0-7 and the D * u skip term, HS = 1: states 8-15), and
+// the same helper warp: 12 warps per CTA, warps w / w + 4 / w + 8 of a channel group on one SM sub-partition.
+// Why: with one recurrence warp per group a sub-partition holds at most two of them (registers), and two in-order warps
+// cannot keep the XU fed -- config 2 ran 392 cycles per step of a sub-partition's two groups against 256 cycles of MUFU work
+// (profiles/r02/scan_v7_pair2_ncu_summary.txt: XU 70 %, issue 55 %, 27 % of the recurrence warps' samples in fixed-latency
+// `wait`; without any MUFU the recurrence still took 0.59 ms).  Halving the state per warp doubles the independent
+// instruction streams at the same total MUFU / FMA work; it costs the duplicated per-step scalars (delta, u, delta * u,
+// pointer steps: ~8 issue slots per step) and one extra add per element in the helper's gate.  No shuffles, no atomics:
+// each half owns a delta copy in the slot and overwrites it in place with its partial y.
+template <int HS, int S, int NB, int BOFF, int ABL, int DS>
+__device__ __forceinline__ void scan_duo_recur(const uint8_t* ring, float* slots, int stage_bytes, int u_bytes,
+                                               uint64_t* full_bar, uint64_t* empty_bar, uint64_t* prepped,
+                                               uint64_t* ydone, const ScanParams& p, int w, int lane, int d, int b,
+                                               int dir, int ntiles) {
+    constexpr int NSLOT = 2;
+    constexpr int PLANE = SC_TT * DS, PAIRF = 3 * PLANE;
+    constexpr int UOFF = (2 - HS) * PLANE;      // u plane relative to this half's delta -> y plane
+    constexpr int SOFF = 8 * HS;                // first state of this half
+    const size_t pd = size_t(dir) * p.di + d;
+    float2 h2[4], A2[4];
+    {
+        const float4* ap = reinterpret_cast<const float4*>(p.A2 + pd * SC_NS + SOFF);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const float4 a = ap[q];
+            A2[2 * q] = make_float2(a.x, a.y);
+            A2[2 * q + 1] = make_float2(a.z, a.w);
+        }
+        if (p.h_in) {
+            const float4* hp = reinterpret_cast<const float4*>(p.h_in + ((size_t(dir) * p.batch + b) * p.di + d) * SC_NS + SOFF);
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const float4 a = hp[q];
+                h2[2 * q] = make_float2(a.x, a.y);
+                h2[2 * q + 1] = make_float2(a.z, a.w);
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) h2[q] = make_float2(0.f, 0.f);
+        }
+    }
+    const float Dv = HS == 0 ? p.Dskip[pd] : 0.f;
+    const int bc_first = dir ? (SC_TT - 1) * NB : 0;   // floats
+    const int bc_step = dir ? -NB : NB;
+    const int sl_first = dir ? (SC_TT - 1) * DS : 0;
+    const int sl_step = dir ? -DS : DS;
+    auto decay = [&](float dl, int q) -> float2 {
+        const float2 a = __fmul2_rn(make_float2(dl, dl), A2[q]);
+        return (ABL & 4) ? __ffma2_rn(a, make_float2(0.5f, 0.5f), make_float2(1.f, 1.f))
+                         : make_float2(ex2_approx(a.x), ex2_approx(a.y));
+    };
+    for (int i = 0; i < ntiles; ++i) {
+        const int stg = i % S, sl = i % NSLOT;
+        mbar_wait(&prepped[w * NSLOT + sl], uint32_t(i / NSLOT) & 1u);
+        mbar_wait(&full_bar[stg], uint32_t(i / S) & 1u);  // complete long ago; orders this warp after the TMA writes
+        float* psl = slots + sl * (4 * PAIRF) + w * PAIRF + HS * PLANE + lane + sl_first;
+        const float* pbc = reinterpret_cast<const float*>(ring + stg * stage_bytes + u_bytes) + BOFF + SOFF + bc_first;
+        // decay factors two steps ahead in their own registers (see scan_pair_recur)
+        float2 e_c[4], e_n[4];
+        float4 Bq[2];
+        float dl_c = psl[0], u_c = psl[UOFF];
+        float dl_n = psl[sl_step], u_n = psl[sl_step + UOFF];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) e_c[q] = decay(dl_c, q);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) e_n[q] = decay(dl_n, q);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) Bq[q] = *reinterpret_cast<const float4*>(pbc + 4 * q);
+#pragma unroll
+        for (int jj = 0; jj < SC_TT; ++jj) {
+            float4 Cq[2];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) Cq[q] = *reinterpret_cast<const float4*>(pbc + SC_NS + 4 * q);
+            pbc += bc_step;
+            float* py = psl;
+            psl += sl_step;
+            float dl_nn = 0.f, u_nn = 0.f;
+            if (jj + 2 < SC_TT) {
+                dl_nn = psl[sl_step];
+                u_nn = psl[sl_step + UOFF];
+            }
+            const float du = dl_c * u_c;
+            const float2 du2 = make_float2(du, du);
+            float2 bu[4];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                bu[2 * q] = __fmul2_rn(du2, make_float2(Bq[q].x, Bq[q].y));
+                bu[2 * q + 1] = __fmul2_rn(du2, make_float2(Bq[q].z, Bq[q].w));
+            }
+            if (jj + 1 < SC_TT) {
+#pragma unroll
+                for (int q = 0; q < 2; ++q) Bq[q] = *reinterpret_cast<const float4*>(pbc + 4 * q);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                h2[q] = __ffma2_rn(e_c[q], h2[q], bu[q]);
+                e_c[q] = e_n[q];
+                if (jj + 2 < SC_TT) e_n[q] = decay(dl_nn, q);
+            }
+            float2 y0 = make_float2(HS == 0 ? Dv * u_c : 0.f, 0.f), y1 = make_float2(0.f, 0.f);
+            y0 = __ffma2_rn(h2[0], make_float2(Cq[0].x, Cq[0].y), y0);
+            y1 = __ffma2_rn(h2[1], make_float2(Cq[0].z, Cq[0].w), y1);
+            y0 = __ffma2_rn(h2[2], make_float2(Cq[1].x, Cq[1].y), y0);
+            y1 = __ffma2_rn(h2[3], make_float2(Cq[1].z, Cq[1].w), y1);
+            const float2 sy = __fadd2_rn(y0, y1);
+            sts_f32_nofence(py, sy.x + sy.y);
+            dl_c = dl_n;
+            u_c = u_n;
+            dl_n = dl_nn;
+            u_n = u_nn;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            mbar_arrive(&ydone[w * NSLOT + sl]);
+            mbar_arrive(&empty_bar[stg]);
+        }
+    }
+    if (p.h_out) {
+        float4* hp = reinterpret_cast<float4*>(p.h_out + ((size_t(dir) * p.batch + b) * p.di + d) * SC_NS + SOFF);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) hp[q] = make_float4(h2[2 * q].x, h2[2 * q].y, h2[2 * q + 1].x, h2[2 * q + 1].y);
+    }
+}
+
+template <int P, int R, int NDBL, typename ZT, int ABL>
+__global__ void __launch_bounds__(384, 2)
+scan_kernel_duo(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUtensorMap mapD, const ScanParams p) {
+    using SM = ScanSmemPair<P, NDBL, true>;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
+    uint8_t* ring = smem;
+    float* slots = reinterpret_cast<float*>(smem + SM::STAGES * SM::STAGE_BYTES);
+    uint8_t* zbuf = smem + SM::STAGES * SM::STAGE_BYTES + SM::SLOTS * SM::SLOT_BYTES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(zbuf + SM::ZBUF_BYTES);
+    uint64_t* empty_bar = full_bar + 4;
+    uint64_t* prepped = empty_bar + 4;
+    uint64_t* ydone = prepped + 4 * SM::SLOTS;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int nchb = p.di / SC_CH;
+    const int ch0 = (blockIdx.x % nchb) * SC_CH;
+    const int dir = p.dir0 + blockIdx.x / nchb;
+    const int b = blockIdx.y;
+    if (tid == 0) {
+        tma_prefetch_desc(&mapU);
+        tma_prefetch_desc(&mapD);
+        for (int s = 0; s < SM::STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 8);     // both halves of the four channel groups
+        }
+        for (int s = 0; s < 4 * SM::SLOTS; ++s) {
+            mbar_init(&prepped[s], 1);
+            mbar_init(&ydone[s], 2);         // both halves
+        }
+        fence_barrier_init();
+    }
+    __syncthreads();
+    const int Lb = (b == p.batch - 1) ? p.L_last : p.L;
+    const int ntiles = (Lb + SC_TT - 1) / SC_TT;
+    const int w = warp & 3;
+    const int role = (ABL & 128) ? (warp < 4 ? 2 : (warp < 8 ? 0 : 1)) : (warp >> 2);   // bit 7: helper = the LOWEST warp ids
+    if (role == 0)
+        scan_duo_recur<0, SM::STAGES, SM::NB, R, ABL, P2_DS>(ring, slots, SM::STAGE_BYTES, SM::U_BYTES, full_bar, empty_bar,
+                                                            prepped, ydone, p, w, lane, ch0 + w * 32 + lane, b, dir, ntiles);
+    else if (role == 1)
+        scan_duo_recur<1, SM::STAGES, SM::NB, R, ABL, P2_DS>(ring, slots, SM::STAGE_BYTES, SM::U_BYTES, full_bar, empty_bar,
+                                                            prepped, ydone, p, w, lane, ch0 + w * 32 + lane, b, dir, ntiles);
+    else
+        scan_pair_helper<P, R, NDBL, ZT, true, ABL, true>(ring, slots, zbuf, full_bar, empty_bar, prepped, ydone, p, w, lane,
+                                                          ch0, b, dir, ntiles, Lb, &mapU, &mapD);
+}
+
+template <int P, int R, int NDBL, typename ZT, int ABL = 0>
+static int launch_scan_duo(const mtn_scan_args* a, cudaStream_t stream) {
+    using SM = ScanSmemPair<P, NDBL, true>;
+    MTN_REQUIRE((reinterpret_cast<uintptr_t>(a->z) & 15) == 0 && (a->ldz * sizeof(ZT)) % 16 == 0 &&
+                    (a->z_col0 * sizeof(ZT)) % 16 == 0,
+                "scan(duo): the gate block must be 16-byte aligned (z=%p ldz=%d z_col0=%d)", a->z, a->ldz, a->z_col0);
+    MTN_REQUIRE(a->y && (reinterpret_cast<uintptr_t>(a->y) & 15) == 0, "scan(duo): y must be 16-byte aligned");
+    const uint64_t M = uint64_t(a->batch) * a->L;
+    CUtensorMap mapU, mapD;
+    {
+        uint64_t dims[3] = {uint64_t(2) * a->di, M, uint64_t(P)};
+        uint64_t str[2] = {uint64_t(2) * a->di * 2, M * 2 * a->di * 2};
+        uint32_t box[3] = {uint32_t(SC_CH), SC_TT, uint32_t(P)};
+        if (!encode_tmap(&mapU, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, a->u, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE))
+            return MTN_ECUDA;
+    }
+    {
+        uint64_t dims[2] = {uint64_t(a->ld_dbl), M};
+        uint64_t str[1] = {uint64_t(a->ld_dbl) * 4};
+        uint32_t box[2] = {uint32_t(SM::NB), SC_TT};
+        if (!encode_tmap(&mapD, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, a->dbl, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE))
+            return MTN_ECUDA;
+    }
+    ScanParams p = make_scan_params(a);
+    auto kern = scan_kernel_duo<P, R, NDBL, ZT, ABL>;
+    static std::atomic<unsigned long long> attr_done{0};   // per template instantiation, one bit per device
+    if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(kern), SM::TOTAL, attr_done, "scan(duo)")) return rc;
+    dim3 grid(p.ndirs * (a->di / SC_CH), a->batch, 1);
+    kern<<<grid, 384, SM::TOTAL, stream>>>(mapU, mapD, p);
+    MTN_CUDA_LAUNCH_CHECK("scan(duo)");
+    return MTN_OK;
+}
+
 template <int P, int R, int NDBL, typename ZT, bool WY, bool RG, int KP, int ABL>
 __global__ void __launch_bounds__(256, 2)
 scan_kernel_pair(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUtensorMap mapD, const ScanParams p) {
@@ -606,7 +833,7 @@ scan_kernel_pair(const __grid_constant__ CUtensorMap mapU, const __grid_constant
     const int Lb = (b == p.batch - 1) ? p.L_last : p.L;
     const int ntiles = (Lb + SC_TT - 1) / SC_TT;
     const int w = warp & 3;
-    if (warp < 4)
+    if ((ABL & 128) ? warp >= 4 : warp < 4)   // ABL bit 7 (dev builds): roles swapped, recurrence = the HIGHER warp ids
         scan_pair_recur<SM::STAGES, SM::NB, R, WY, ABL, RG, P2_DS, KP>(ring, slots, SM::STAGE_BYTES, SM::U_BYTES, full_bar,
                                                                     empty_bar, prepped, ydone, p, w, lane,
                                                                     ch0 + w * 32 + lane, b, dir, ntiles, Lb);
