@@ -15,7 +15,7 @@ EPI_STORE, EPI_INPROJ, EPI_MASK, EPI_RELU, EPI_XPROJ, EPI_RESADD = 0, 1, 2, 3, 4
 
 # ABI the ctypes structs below were written for (include/mtn_b200.h: MTN_ABI_VERSION).  A stale or experiment-only build of
 # the library (it is git-ignored and rebuilt on mtimes) must not be handed structs of another layout.
-EXPECTED_ABI = 6
+EXPECTED_ABI = 7
 
 EXPORTS = [
     "mtn_encoder_cln_fwd", "mtn_gemm_fwd", "mtn_gemm_rowsum_parts", "mtn_add_rmsnorm_fwd", "mtn_add_rmsnorm_out_fwd", "mtn_add_norm_fwd", "mtn_conv_silu_fwd", "mtn_conv_silu_halo_fwd", "mtn_conv_silu_dir_fwd", "mtn_decoder_stream_fwd",
@@ -24,6 +24,7 @@ EXPORTS = [
     "mtn_dp_overadd_prelu_fwd", "mtn_bias_planes_fwd", "mtn_gate_planes_fwd",
     "mtn_decoder_fwd", "mtn_cln_fwd", "mtn_softmax_mask_fwd", "mtn_split_planes", "mtn_si_snr_pit_fwd", "mtn_si_snr_workspace_bytes", "mtn_si_snr_pit_n_fwd", "mtn_si_snr_workspace_bytes_n", "mtn_last_error_string", "mtn_abi_version",
     "mtn_sizeof_gemm_args", "mtn_sizeof_scan_args", "mtn_sizeof_gn_apply_args",
+    "mtn_stream_push_fwd", "mtn_sizeof_stream_push_args",
 ]
 
 
@@ -55,6 +56,18 @@ class GnApplyArgs(Structure):
         ("out_a", c_void_p), ("out_a2", c_void_p), ("out_t", c_void_p), ("planes", c_void_p),
         ("batch", c_int), ("S", c_int), ("K", c_int), ("C", c_int), ("x_transposed", c_int),
         ("n_planes", c_int), ("plane_rows", c_int), ("eps", c_float), ("blend", c_void_p),
+    ]
+
+
+class StreamPushArgs(Structure):
+    _fields_ = [
+        ("mix", c_void_p), ("in_tail", c_void_p), ("est", c_void_p), ("halo", c_void_p), ("h", c_void_p), ("ola_tail", c_void_p),
+        ("head", c_void_p), ("bot_frag", c_void_p), ("mask_frag", c_void_p), ("layer_vec", c_void_p),
+        ("layer_frag", c_void_p),
+        ("h_layer_stride", c_size_t), ("layer_vec_stride", c_size_t), ("layer_frag_stride", c_size_t),
+        ("B", c_int), ("F", c_int), ("N", c_int), ("D", c_int), ("di", c_int), ("R", c_int), ("n_spk", c_int),
+        ("n_layers", c_int), ("ld_mix", c_int), ("first", c_int), ("eps_cln", c_float), ("eps_rms", c_float),
+        ("timeline", c_void_p),
     ]
 
 
@@ -122,8 +135,9 @@ def load():
                                              c_void_p]
     lib.mtn_bias_planes_fwd.argtypes = [c_void_p, c_int, c_void_p, c_float, c_void_p, c_int, c_int, c_int, c_int, c_void_p]
     lib.mtn_gate_planes_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]
+    lib.mtn_stream_push_fwd.argtypes = [POINTER(StreamPushArgs), c_void_p]
     for name, st in (("mtn_sizeof_gemm_args", GemmArgs), ("mtn_sizeof_scan_args", ScanArgs),
-                     ("mtn_sizeof_gn_apply_args", GnApplyArgs)):
+                     ("mtn_sizeof_gn_apply_args", GnApplyArgs), ("mtn_sizeof_stream_push_args", StreamPushArgs)):
         fn = getattr(lib, name)
         fn.restype, fn.argtypes = c_size_t, []
         if int(fn()) != ctypes.sizeof(st):
@@ -134,7 +148,7 @@ def load():
         if fn is not None and name not in ("mtn_last_error_string", "mtn_abi_version", "mtn_si_snr_workspace_bytes",
                                            "mtn_si_snr_workspace_bytes_n",
                                            "mtn_gn_partials_bytes", "mtn_sizeof_gemm_args", "mtn_sizeof_scan_args",
-                                           "mtn_sizeof_gn_apply_args"):
+                                           "mtn_sizeof_gn_apply_args", "mtn_sizeof_stream_push_args"):
             fn.restype = c_int
     lib.mtn_si_snr_workspace_bytes.restype = c_size_t
     lib.mtn_si_snr_workspace_bytes_n.restype = c_size_t

@@ -1,0 +1,653 @@
+// One-launch streaming push of the causal Mamba-TasNet separator (sm_100a).
+//
+// A streaming chunk is a handful of frames (a 20 ms push at 8 kHz = 20 frames): every GEMM of the path has M <= 32 rows and
+// the ~100-kernel chain of the batch plan is pure launch latency there (0.56 ms per push, profiles/r01/stream_push_*).
+// This kernel runs the WHOLE push -- encoder + cLN + bottleneck, every Mamba block (Add -> RMSNorm -> in_proj -> causal
+// conv + SiLU -> x_proj -> dt_proj + softplus -> selective-scan steps -> gate -> out_proj), norm_f, mask, decoder
+// overlap-add -- as ONE launch: one thread-block CLUSTER per stream, the channels of d_inner cut over the CTAs of the
+// cluster (64 per CTA; cluster size = d_model / 32: 8 for the S recipe), weights streamed from L2 exactly once per CTA.
+//
+// Replaces, for chunks of <= 32 frames, the reference's token-at-a-time `Mamba.step` + `inference_params` caches
+// (Mamba-TasNet/modules/mamba/bimamba.py:320-372, caches :374-404) driven through `MambaBlocksSequential.forward(x,
+// inference_params)` (modules/mamba_blocks.py:186-197), plus the Encoder / MaskNet / Decoder calls around it
+// (train_wsj0mix.py:86-111).
+//
+// Arithmetic: the contractions run on warp-level mma.sync.m16n8k16 (bf16 hi/lo split of both operands, three passes,
+// fp32 accumulate = the same fp32-class operand model as the batch plan's tcgen05 GEMMs).  The WEIGHT is the M-side
+// operand (16 output channels per tile, fragments pre-packed per lane at load time so a warp reads 512 contiguous bytes per
+// k-step straight from L2 into registers) and the FRAMES are the N side (8 per tile: F = 20 costs 24 rows, not 32).
+// Everything else (norms, conv, dt_proj, the recurrence, overlap-add) is fp32 SIMT on shared memory.
+//
+// Cluster dataflow per block (rank r owns d_inner channels [64r, 64r+64) and d_model columns [32r, 32r+32)):
+//   [A] every CTA gathers the residual slices of all ranks -> RMSNorm of all rows -> in_proj (its x / z columns) -> conv +
+//   SiLU -> x_proj partial over its 64 channels [B] sum of the partials of all ranks -> dt_proj + softplus -> scan (its
+//   channels, 16 states, state in / out of the cache) -> gate -> out_proj partial over its 64 channels [C] sum of its 32
+//   columns over all ranks, residual slice += that -> next block.
+// The three exchanges per block are reads of the peers' shared memory (DSMEM, ld.shared::cluster) behind a cluster barrier:
+// a first version that exchanged through global memory spent 2.2 us per dependent read of a line another SM had just
+// written (tools/stream_push_timeline.py), ten times the DSMEM latency.  Every exchanged buffer is rewritten only after a
+// later cluster barrier, so nothing is double-buffered.
+#include "mtn_ptx.cuh"
+#include "mtn_host.h"
+
+namespace mtn {
+
+constexpr int SP_THREADS = 512;
+constexpr int SP_WARPS = SP_THREADS / 32;
+constexpr int SP_DSL = 64;   // d_inner channels per CTA
+constexpr int SP_CSL = 32;   // d_model columns per CTA
+constexpr int SP_MSL = 64;   // mask columns per CTA (n_spk * N / CL with N == D, n_spk == 2)
+constexpr int SP_PAD = 8;    // bf16 row padding of the operand planes: row stride = 4 (mod 32) words, conflict-free fragments
+
+// Shared-memory carve-up (bytes), compile-time per (frame tiles, d_model): every buffer is `smem + constant`, which keeps ~30
+// pointers out of the register file (a run-time layout spilled 1.4 KB per thread).  Identical in every CTA of a cluster:
+// peers address each other's buffers by the same offsets.
+constexpr int sp_al16(int bytes) { return (bytes + 15) / 16 * 16; }
+constexpr int sp_max(int a, int b) { return a > b ? a : b; }
+template <int NTF, int D>
+struct SpL {
+    static constexpr int R = D / 16, NXp = (R + 32 + 15) / 16 * 16, CL = D / 32;
+    static constexpr int Fp = 8 * NTF, lda = D + SP_PAD, ldu = SP_DSL + SP_PAD;
+    static constexpr int act_hi = 0;
+    static constexpr int act_lo = act_hi + sp_al16(Fp * lda * 2);
+    static constexpr int su_hi = act_lo + sp_al16(Fp * lda * 2);
+    static constexpr int su_lo = su_hi + sp_al16(Fp * ldu * 2);
+    static constexpr int planes_end = su_lo + sp_al16(Fp * ldu * 2);
+    static constexpr int xs = planes_end;
+    static constexpr int zs = xs + sp_al16((Fp + 3) * SP_DSL * 4);
+    static constexpr int us = zs + sp_al16(Fp * SP_DSL * 4);
+    static constexpr int dl = us + sp_al16(Fp * SP_DSL * 4);
+    static constexpr int dbl = dl + sp_al16(Fp * SP_DSL * 4);
+    static constexpr int xd = dbl + sp_al16(Fp * NXp * 4);        // x_proj partial of this CTA (read by every peer)
+    static constexpr int res = xd + sp_al16(Fp * NXp * 4);        // residual slice (read by every peer)
+    static constexpr int mixw = res + sp_al16(Fp * SP_CSL * 4);
+    static constexpr int frs = mixw + sp_al16(Fp * SP_MSL * 4);   // decoder frames: this CTA's partial (read by rank 0)
+    static constexpr int lvec = frs + sp_al16(Fp * 16 * 4);       // this CTA's slice of the layer's small vectors
+    static constexpr int norm = lvec + sp_al16(SP_DSL * (23 + R) * 4);   // RMSNorm weights, double-buffered one layer ahead
+    // K-split partial sums of one GEMM: the widest user is in_proj (2 x 128 columns), out_proj (D columns; plane 0 is read by
+    // every peer) or the bottleneck (8 x 32 columns)
+    static constexpr int widest = sp_max(sp_max(2 * (2 * SP_DSL + 4), D + 4), 8 * (SP_CSL + 4));
+    static constexpr int red = norm + sp_al16(2 * D * 4);
+    static constexpr int total = red + sp_al16(Fp * widest * 4);
+};
+
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint4& a, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ void put_planes(__nv_bfloat16* hi, __nv_bfloat16* lo, int idx, float v) {
+    __nv_bfloat16 h, l;
+    split_bf16(v, h, l);
+    hi[idx] = h;
+    lo[idx] = l;
+}
+
+// ---- distributed shared memory: the same offset in cluster rank `rank`'s shared memory
+__device__ __forceinline__ uint32_t dsmem_addr(const void* local, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(local)), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ float ld_dsmem(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ float4 ld_dsmem4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+// sum over the cluster ranks of the float4 at the same shared-memory address: eight loads in flight before the first add
+template <int CL>
+__device__ __forceinline__ float4 rank_sum4(const float* local) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int r0 = 0; r0 < CL; r0 += 8) {
+        constexpr int NB = CL < 8 ? CL : 8;
+        float4 v[NB];
+#pragma unroll
+        for (int r = 0; r < NB; ++r) v[r] = ld_dsmem4(dsmem_addr(local, r0 + r));
+#pragma unroll
+        for (int r = 0; r < NB; ++r) { s.x += v[r].x; s.y += v[r].y; s.z += v[r].z; s.w += v[r].w; }
+    }
+    return s;
+}
+
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+#define SP_MARK(k)                                                                                                          \
+    do {                                                                                                                    \
+        if (a.timeline && blockIdx.x == 0 && tid == 0) a.timeline[size_t(tl_row) * 16 + (k)] = global_timer_ns();          \
+    } while (0)
+
+// One warp: C[16 channels of tile][8*NTF frames] += W_frag[ksteps] x act[frames][k0 + 16*ksteps].
+// wf -> this unit's fragments: per k-step 2 planes (hi, lo) x 32 lanes x 16 B.  Up to PF k-steps of weights are in flight.
+template <int NTF>
+__device__ __forceinline__ void mma_unit(const uint4* __restrict__ wf, int ksteps, const __nv_bfloat16* ahi,
+                                         const __nv_bfloat16* alo, int lda, int k0, float (&acc)[NTF][4], int lane) {
+    constexpr int PF = 8;
+    const int g = lane >> 2, t = lane & 3;
+    uint4 wh[PF], wl[PF];
+#pragma unroll
+    for (int i = 0; i < PF; ++i)
+        if (i < ksteps) {
+            wh[i] = __ldg(wf + (i * 2) * 32 + lane);
+            wl[i] = __ldg(wf + (i * 2 + 1) * 32 + lane);
+        }
+    const __nv_bfloat16* bh = ahi + g * lda + k0 + 2 * t;
+    const __nv_bfloat16* bl = alo + g * lda + k0 + 2 * t;
+    for (int s = 0; s < ksteps; s += PF) {
+#pragma unroll
+        for (int i = 0; i < PF; ++i) {
+            if (s + i < ksteps) {
+                const uint4 ah = wh[i], al = wl[i];
+                if (s + i + PF < ksteps) {
+                    wh[i] = __ldg(wf + ((s + i + PF) * 2) * 32 + lane);
+                    wl[i] = __ldg(wf + ((s + i + PF) * 2 + 1) * 32 + lane);
+                }
+                const int ko = (s + i) * 16;
+#pragma unroll
+                for (int j = 0; j < NTF; ++j) {
+                    const uint32_t h0 = *reinterpret_cast<const uint32_t*>(bh + j * 8 * lda + ko);
+                    const uint32_t h1 = *reinterpret_cast<const uint32_t*>(bh + j * 8 * lda + ko + 8);
+                    const uint32_t l0 = *reinterpret_cast<const uint32_t*>(bl + j * 8 * lda + ko);
+                    const uint32_t l1 = *reinterpret_cast<const uint32_t*>(bl + j * 8 * lda + ko + 8);
+                    mma16816(acc[j], ah, h0, h1);
+                    mma16816(acc[j], al, h0, h1);
+                    mma16816(acc[j], ah, l0, l1);
+                }
+            }
+        }
+    }
+}
+
+// CTA-wide GEMM on fragments: CT tiles of 16 output channels, `ksteps` k-steps of 16; when there are fewer tiles than warps
+// the k range is cut KS ways and the partial sums land in red[ks][frame][ldr] (ldr = 16*CT + 4).  Returns KS.
+template <int NTF>
+__device__ __forceinline__ int gemm_frag(const uint4* __restrict__ wfrag, int CT, int ksteps, const __nv_bfloat16* ahi,
+                                         const __nv_bfloat16* alo, int lda, float* red, int warp, int lane) {
+    constexpr int Fp = 8 * NTF;
+    int KS = 1;
+    while (KS * 2 * CT <= SP_WARPS && KS * 2 <= ksteps && ksteps % (KS * 2) == 0) KS *= 2;
+    const int kper = ksteps / KS;
+    const int ldr = 16 * CT + 4;
+    const int g = lane >> 2, t = lane & 3;
+    for (int unit = warp; unit < CT * KS; unit += SP_WARPS) {
+        const int ct = unit / KS, ks = unit % KS;
+        float acc[NTF][4];
+#pragma unroll
+        for (int j = 0; j < NTF; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+        mma_unit<NTF>(wfrag + (size_t(ct) * ksteps + size_t(ks) * kper) * 64, kper, ahi, alo, lda, ks * kper * 16, acc, lane);
+        float* r = red + size_t(ks) * Fp * ldr + ct * 16 + g;
+#pragma unroll
+        for (int j = 0; j < NTF; ++j) {
+            const int f0 = j * 8 + 2 * t;
+            r[f0 * ldr] = acc[j][0];
+            r[(f0 + 1) * ldr] = acc[j][1];
+            r[f0 * ldr + 8] = acc[j][2];
+            r[(f0 + 1) * ldr + 8] = acc[j][3];
+        }
+    }
+    return KS;
+}
+
+__device__ __forceinline__ float red_sum(const float* red, int KS, int Fp, int ldr, int f, int c) {
+    float v = red[f * ldr + c];
+    for (int ks = 1; ks < KS; ++ks) v += red[(size_t(ks) * Fp + f) * ldr + c];
+    return v;
+}
+
+// RMSNorm of all F rows of the residual, whose 32-column slices live in the `res` buffers of the cluster's CTAs, under the
+// weight g (shared memory) -> operand planes.  Lane = column inside a slice, so a warp reads 128 contiguous bytes per peer.
+template <int CL>
+__device__ __forceinline__ void rmsnorm_rows(const float* res_local, const float* g, int F, float eps, __nv_bfloat16* ahi,
+                                             __nv_bfloat16* alo, int lda, int warp, int lane) {
+    constexpr int D = 32 * CL;
+    for (int f = warp; f < F; f += SP_WARPS) {
+        float v[CL];
+        float sq = 0.f;
+#pragma unroll
+        for (int r = 0; r < CL; ++r) v[r] = ld_dsmem(dsmem_addr(res_local + f * SP_CSL + lane, r));
+#pragma unroll
+        for (int r = 0; r < CL; ++r) sq = fmaf(v[r], v[r], sq);
+        const float rstd = rsqrtf(warp_sum(sq) * (1.0f / D) + eps);
+#pragma unroll
+        for (int r = 0; r < CL; ++r) put_planes(ahi, alo, f * lda + 32 * r + lane, v[r] * rstd * g[32 * r + lane]);
+    }
+}
+
+template <int NTF, int D>
+__global__ void __launch_bounds__(SP_THREADS, 1) stream_push_kernel(const mtn_stream_push_args a) {
+    using L = SpL<NTF, D>;
+    constexpr int Fp = 8 * NTF, N = D, di = 2 * D, R = L::R, NXp = L::NXp, CL = L::CL, lda = L::lda, ldu = L::ldu;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int rank = int(cluster_ctarank());
+    const int b = blockIdx.x / CL;
+    const int F = a.F;
+    __nv_bfloat16* const act_hi = reinterpret_cast<__nv_bfloat16*>(smem + L::act_hi);
+    __nv_bfloat16* const act_lo = reinterpret_cast<__nv_bfloat16*>(smem + L::act_lo);
+    __nv_bfloat16* const su_hi = reinterpret_cast<__nv_bfloat16*>(smem + L::su_hi);
+    __nv_bfloat16* const su_lo = reinterpret_cast<__nv_bfloat16*>(smem + L::su_lo);
+    float* const xs = reinterpret_cast<float*>(smem + L::xs);
+    float* const zs = reinterpret_cast<float*>(smem + L::zs);
+    float* const us = reinterpret_cast<float*>(smem + L::us);
+    float* const dl = reinterpret_cast<float*>(smem + L::dl);
+    float* const dbl = reinterpret_cast<float*>(smem + L::dbl);
+    float* const xd = reinterpret_cast<float*>(smem + L::xd);
+    float* const res = reinterpret_cast<float*>(smem + L::res);
+    float* const mixw = reinterpret_cast<float*>(smem + L::mixw);
+    float* const frs = reinterpret_cast<float*>(smem + L::frs);
+    float* const lvec = reinterpret_cast<float*>(smem + L::lvec);
+    float* const s_norm = reinterpret_cast<float*>(smem + L::norm);
+    float* const red = reinterpret_cast<float*>(smem + L::red);
+    int tl_row = 0;
+
+    // head blob: w_enc_t [16][N] | gamma [N] | beta [N] | norm_f [D] | w_dec [N][16]
+    const float* w_enc_t = a.head;
+    const float* gamma = w_enc_t + 16 * N;
+    const float* beta = gamma + N;
+    const float* norm_f = beta + N;
+    const float* w_dec = norm_f + D;
+
+    // rows >= F of the operand planes are multiplied too (their results are never read): keep them finite
+    for (int i = tid; i < L::planes_end / 4; i += SP_THREADS) reinterpret_cast<uint32_t*>(smem)[i] = 0u;
+    // RMSNorm weight of the first block
+    for (int i = tid; i < D / 4; i += SP_THREADS) cp_async16(s_norm + 4 * i, a.layer_vec + 4 * i);
+    cp_async_commit();
+    __syncthreads();
+
+    // ------------------------------------------------------------------ encoder + cLN (every CTA, all rows)
+    {
+        constexpr int nj = N / 32;
+        const int m0 = (rank * SP_MSL) % N;   // first encoder channel of this CTA's mask columns
+        // the encoder sees [8 carried samples | chunk]; the very first push has no carried samples
+        const float* mixb = a.mix + size_t(b) * a.ld_mix;
+        const float* tl = a.in_tail + size_t(b) * 8;
+        const int shift = a.first ? 0 : 8;
+        for (int f = warp; f < F; f += SP_WARPS) {
+            float x[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const int j = 8 * f + k - shift;
+                x[k] = j >= 0 ? __ldg(mixb + j) : tl[j + 8];
+            }
+            float v[16];
+            float s = 0.f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (j < nj) {
+                    float acc = 0.f;
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) acc = fmaf(__ldg(w_enc_t + k * N + lane + 32 * j), x[k], acc);
+                    v[j] = fmaxf(acc, 0.f);
+                    s += v[j];
+                }
+            const float mean = warp_sum(s) * (1.0f / N);
+            float sq = 0.f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (j < nj) {
+                    const float d = v[j] - mean;
+                    sq = fmaf(d, d, sq);
+                }
+            const float rstd = rsqrtf(warp_sum(sq) * (1.0f / N) + a.eps_cln);
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (j < nj) {
+                    const int n = lane + 32 * j;
+                    put_planes(act_hi, act_lo, f * lda + n, fmaf(__ldg(gamma + n) * (v[j] - mean), rstd, __ldg(beta + n)));
+                    if (n >= m0 && n < m0 + SP_MSL) mixw[f * SP_MSL + n - m0] = v[j];
+                }
+        }
+    }
+    __syncthreads();
+
+    // ------------------------------------------------------------------ bottleneck: this CTA's 32 columns of h; residual := h
+    {
+        const uint4* wf = reinterpret_cast<const uint4*>(a.bot_frag) + size_t(rank) * (SP_CSL / 16) * (N / 16) * 64;
+        const int KS = gemm_frag<NTF>(wf, SP_CSL / 16, N / 16, act_hi, act_lo, lda, red, warp, lane);
+        __syncthreads();
+        for (int i = tid; i < F * SP_CSL; i += SP_THREADS) res[i] = red_sum(red, KS, Fp, SP_CSL + 4, i / SP_CSL, i % SP_CSL);
+    }
+    cp_async_wait_all();
+    cluster_sync_all();   // [A]
+
+    // ------------------------------------------------------------------ Mamba blocks
+    constexpr int ct_in = 2 * SP_DSL / 16, ks_d = D / 16, ct_x = NXp / 16, ks_c = SP_DSL / 16, ct_o = D / 16;
+    constexpr size_t in_units = size_t(ct_in) * ks_d, x_units = size_t(ct_x) * ks_c, o_units = size_t(ct_o) * ks_c;
+    const int ch0 = rank * SP_DSL;
+    // this CTA's slice of a layer's small vectors in shared memory:
+    // conv_w [64][4] | conv_b [64] | w_dt^T [R][64] | dt_bias [64] | A2 [64][16] | D [64]
+    float* s_conv_w = lvec;
+    float* s_conv_b = s_conv_w + SP_DSL * 4;
+    float* s_w_dt = s_conv_b + SP_DSL;
+    float* s_dt_bias = s_w_dt + SP_DSL * R;
+    float* s_A2 = s_dt_bias + SP_DSL;
+    float* s_D = s_A2 + SP_DSL * 16;
+    SP_MARK(0);
+    for (int layer = 0; layer < a.n_layers; ++layer) {
+        tl_row = 1 + layer;
+        // layer vector blob: norm [D] | conv_w [di][4] | conv_b [di] | w_dt^T [R][di] | dt_bias [di] | A2 [di][16] | Dskip [di]
+        const float* lv = a.layer_vec + size_t(layer) * a.layer_vec_stride;
+        // layer fragment blob: in_proj [CL][ct_in][ks_d] | x_proj [CL][ct_x][ks_c] | out_proj [CL][ct_o][ks_c], 1 KiB each
+        const uint4* lf = reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(a.layer_frag) +
+                                                         size_t(layer) * a.layer_frag_stride);
+        float* halo = a.halo + (size_t(layer) * a.B + b) * 3 * di + ch0;
+        float* hst = a.h + size_t(layer) * a.h_layer_stride + (size_t(b) * di + ch0) * 16;
+
+        // small vectors of this layer + the NEXT norm weight: asynchronous copies, waited for before the conv (their previous
+        // readers are at least one cluster barrier back)
+        {
+            const float* conv_w = lv + D;
+            const float* conv_b = conv_w + size_t(di) * 4;
+            const float* w_dt = conv_b + di;
+            const float* dt_bias = w_dt + size_t(di) * R;
+            const float* A2 = dt_bias + di;
+            const float* Dskip = A2 + size_t(di) * 16;
+            const float* next_norm = layer + 1 < a.n_layers ? lv + a.layer_vec_stride : norm_f;
+            constexpr int q_cw = SP_DSL, q_v = SP_DSL / 4, q_wd = R * (SP_DSL / 4), q_a2 = SP_DSL * 4, q_n = D / 4;   // 16-byte chunks
+            for (int i = tid; i < q_cw + 3 * q_v + q_wd + q_a2 + q_n; i += SP_THREADS) {
+                int j = i;
+                if (j < q_cw) { cp_async16(s_conv_w + 4 * j, conv_w + size_t(ch0) * 4 + 4 * j); continue; }
+                j -= q_cw;
+                if (j < q_v) { cp_async16(s_conv_b + 4 * j, conv_b + ch0 + 4 * j); continue; }
+                j -= q_v;
+                if (j < q_wd) { cp_async16(s_w_dt + 4 * j, w_dt + size_t(j / (SP_DSL / 4)) * di + ch0 + 4 * (j % (SP_DSL / 4))); continue; }
+                j -= q_wd;
+                if (j < q_v) { cp_async16(s_dt_bias + 4 * j, dt_bias + ch0 + 4 * j); continue; }
+                j -= q_v;
+                if (j < q_a2) { cp_async16(s_A2 + 4 * j, A2 + size_t(ch0) * 16 + 4 * j); continue; }
+                j -= q_a2;
+                if (j < q_v) { cp_async16(s_D + 4 * j, Dskip + ch0 + 4 * j); continue; }
+                j -= q_v;
+                cp_async16(s_norm + ((layer + 1) & 1) * D + 4 * j, next_norm + 4 * j);
+            }
+            cp_async_commit();
+        }
+
+        // Add -> RMSNorm (bimamba.py:446-447): all rows, every CTA
+        rmsnorm_rows<CL>(res, s_norm + (layer & 1) * D, F, a.eps_rms, act_hi, act_lo, lda, warp, lane);
+        __syncthreads();
+        SP_MARK(1);
+
+        // in_proj: x columns [ch0, ch0+64) and z columns di + [ch0, ch0+64)
+        {
+            const int KS = gemm_frag<NTF>(lf + size_t(rank) * in_units * 64, ct_in, ks_d, act_hi, act_lo, lda, red, warp, lane);
+            if (tid < 3 * SP_DSL) xs[tid] = halo[(tid / SP_DSL) * di + tid % SP_DSL];   // conv history = rows -3..-1
+            __syncthreads();
+            SP_MARK(2);
+            for (int i = tid; i < F * 2 * SP_DSL; i += SP_THREADS) {
+                const int f = i / (2 * SP_DSL), c = i % (2 * SP_DSL);
+                const float v = red_sum(red, KS, Fp, 2 * SP_DSL + 4, f, c);
+                if (c < SP_DSL) xs[(3 + f) * SP_DSL + c] = v;
+                else zs[f * SP_DSL + c - SP_DSL] = silu_f(v);
+            }
+        }
+        cp_async_wait_all();
+        __syncthreads();
+        SP_MARK(3);
+
+        // causal depthwise conv (width 4) + bias + SiLU (ssi.py:182); new history = last three conv inputs
+        for (int i = tid; i < F * SP_DSL; i += SP_THREADS) {
+            const int f = i / SP_DSL, c = i % SP_DSL;
+            const float4 w = *reinterpret_cast<const float4*>(s_conv_w + 4 * c);
+            const float* x = xs + f * SP_DSL + c;
+            const float pre = fmaf(w.x, x[0], fmaf(w.y, x[SP_DSL], fmaf(w.z, x[2 * SP_DSL], fmaf(w.w, x[3 * SP_DSL], s_conv_b[c]))));
+            const float u = silu_f(pre);
+            us[i] = u;
+            put_planes(su_hi, su_lo, f * ldu + c, u);
+        }
+        if (tid < 3 * SP_DSL) halo[(tid / SP_DSL) * di + tid % SP_DSL] = xs[(F + tid / SP_DSL) * SP_DSL + tid % SP_DSL];
+        __syncthreads();
+        SP_MARK(4);
+
+        // x_proj over this CTA's 64 channels: partial [dt | B | C] rows, left in xd for the peers
+        {
+            const int KS = gemm_frag<NTF>(lf + (size_t(CL) * in_units + size_t(rank) * x_units) * 64, ct_x, ks_c, su_hi, su_lo, ldu,
+                                          red, warp, lane);
+            __syncthreads();
+            for (int i = tid; i < F * NXp; i += SP_THREADS) xd[i] = red_sum(red, KS, Fp, NXp + 4, i / NXp, i % NXp);
+        }
+        SP_MARK(5);
+        cluster_sync_all();   // [B]
+        SP_MARK(6);
+        for (int i = tid; i < F * NXp / 4; i += SP_THREADS)
+            *reinterpret_cast<float4*>(dbl + 4 * i) = rank_sum4<CL>(xd + 4 * i);
+        __syncthreads();
+        SP_MARK(7);
+
+        // dt_proj + softplus (ssi.py:187, delta_softplus of :218)
+        for (int i = tid; i < F * SP_DSL; i += SP_THREADS) {
+            const int f = i / SP_DSL, c = i % SP_DSL;
+            float acc = s_dt_bias[c];
+#pragma unroll
+            for (int r = 0; r < R; ++r) acc = fmaf(dbl[f * NXp + r], s_w_dt[r * SP_DSL + c], acc);
+            dl[i] = softplus_f(acc);
+        }
+        __syncthreads();
+        SP_MARK(8);
+
+        // selective-scan steps: 8 threads per channel, 2 of the 16 states each (selective_scan_ref, ssi.py:91-157);
+        // y = (sum_n C h + D u) * silu(z) -> operand planes of out_proj (over the u planes, which x_proj is done with).
+        // Eight steps of operands are fetched before their recurrence runs and the eight results are stored after it (the
+        // compiler cannot move shared loads across the plane stores of an earlier step).
+        {
+            const int c = tid >> 3, sp = tid & 7;
+            const float A0 = s_A2[c * 16 + 2 * sp], A1 = s_A2[c * 16 + 2 * sp + 1];
+            const float Dp = s_D[c];
+            float2 h = *reinterpret_cast<const float2*>(hst + c * 16 + 2 * sp);
+            const float* bc = dbl + R + 2 * sp;
+#pragma unroll
+            for (int f0 = 0; f0 < Fp; f0 += 8) {
+                if (f0 < F) {
+                    float d[8], u[8], yv[8];
+                    float2 Bv[8], Cv[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const int f = f0 + k < F ? f0 + k : F - 1;
+                        d[k] = dl[f * SP_DSL + c];
+                        u[k] = us[f * SP_DSL + c];
+                        Bv[k] = *reinterpret_cast<const float2*>(bc + f * NXp);
+                        Cv[k] = *reinterpret_cast<const float2*>(bc + f * NXp + 16);
+                    }
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        if (f0 + k < F) {
+                            const float du = d[k] * u[k];
+                            h.x = fmaf(ex2_approx(d[k] * A0), h.x, du * Bv[k].x);
+                            h.y = fmaf(ex2_approx(d[k] * A1), h.y, du * Bv[k].y);
+                        }
+                        float yp = fmaf(Cv[k].x, h.x, Cv[k].y * h.y);
+                        yp += __shfl_xor_sync(0xffffffffu, yp, 1);
+                        yp += __shfl_xor_sync(0xffffffffu, yp, 2);
+                        yp += __shfl_xor_sync(0xffffffffu, yp, 4);
+                        yv[k] = fmaf(Dp, u[k], yp);
+                    }
+                    // lane sp of the channel's eight finishes step f0 + sp
+                    float mine = yv[0];
+#pragma unroll
+                    for (int k = 1; k < 8; ++k) mine = sp == k ? yv[k] : mine;
+                    if (f0 + sp < F) put_planes(su_hi, su_lo, (f0 + sp) * ldu + c, mine * zs[(f0 + sp) * SP_DSL + c]);
+                }
+            }
+            *reinterpret_cast<float2*>(hst + c * 16 + 2 * sp) = h;
+        }
+        __syncthreads();
+        SP_MARK(9);
+
+        // out_proj over this CTA's 64 channels: partial h [F][D], left in plane 0 of red for the peers
+        {
+            const int KS = gemm_frag<NTF>(lf + (size_t(CL) * (in_units + x_units) + size_t(rank) * o_units) * 64, ct_o, ks_c, su_hi,
+                                          su_lo, ldu, red, warp, lane);
+            if (KS > 1) {
+                __syncthreads();
+                for (int i = tid; i < F * D; i += SP_THREADS) {
+                    const int f = i / D, c = i % D;
+                    red[f * (D + 4) + c] = red_sum(red, KS, Fp, D + 4, f, c);   // each element has one owner: in place
+                }
+            }
+        }
+        SP_MARK(10);
+        cluster_sync_all();   // [C]
+        SP_MARK(11);
+        for (int i = tid; i < F * SP_CSL / 4; i += SP_THREADS) {
+            const int f = i / (SP_CSL / 4), c = 4 * (i % (SP_CSL / 4));
+            const float4 v = rank_sum4<CL>(red + f * (D + 4) + rank * SP_CSL + c);
+            float4 r = *reinterpret_cast<float4*>(res + f * SP_CSL + c);
+            r.x += v.x; r.y += v.y; r.z += v.z; r.w += v.w;
+            *reinterpret_cast<float4*>(res + f * SP_CSL + c) = r;
+        }
+        SP_MARK(12);
+        cluster_sync_all();   // [A] of the next block / of norm_f
+        SP_MARK(13);
+    }
+    tl_row = 1 + a.n_layers;
+    SP_MARK(0);
+
+    // ------------------------------------------------------------------ norm_f -> mask conv + ReLU -> mask * mix_w
+    rmsnorm_rows<CL>(res, s_norm + (a.n_layers & 1) * D, F, a.eps_rms, act_hi, act_lo, lda, warp, lane);
+    __syncthreads();
+    {
+        const uint4* wf = reinterpret_cast<const uint4*>(a.mask_frag) + size_t(rank) * (SP_MSL / 16) * (D / 16) * 64;
+        const int KS = gemm_frag<NTF>(wf, SP_MSL / 16, D / 16, act_hi, act_lo, lda, red, warp, lane);
+        __syncthreads();
+        for (int i = tid; i < F * SP_MSL; i += SP_THREADS) {
+            const int f = i / SP_MSL, c = i % SP_MSL;
+            us[i] = fmaxf(red_sum(red, KS, Fp, SP_MSL + 4, f, c), 0.f) * mixw[i];   // sep slice (train_wsj0mix.py:91-92)
+        }
+    }
+    __syncthreads();
+    // decoder frames (ConvTranspose1d k=16 s=8): partial over this CTA's 64 encoder channels of ONE speaker
+    {
+        const int m0 = (rank * SP_MSL) % N;
+        for (int i = tid; i < F * 16; i += SP_THREADS) {
+            const int f = i >> 4, j = i & 15;
+            float acc = 0.f;
+#pragma unroll 8
+            for (int c = 0; c < SP_MSL; ++c) acc = fmaf(us[f * SP_MSL + c], __ldg(w_dec + (m0 + c) * 16 + j), acc);
+            frs[i] = acc;
+        }
+    }
+    SP_MARK(1);
+    cluster_sync_all();   // [D]
+    // overlap-add on rank 0: frame f finalises samples [8f, 8f+8) together with the second half of frame f-1 (or the
+    // carried tail); the second half of the last frame becomes the new tail
+    if (rank == 0) {
+        constexpr int Sn = 2, rps = N / SP_MSL;   // ranks per speaker
+        float* tail = a.ola_tail + size_t(b) * Sn * 8;
+        float* fsum = red;   // [Sn][F][16]
+        for (int i = tid; i < Sn * F * 16; i += SP_THREADS) {
+            const int s = i / (F * 16), fj = i % (F * 16);
+            float v = 0.f;
+            for (int r = s * rps; r < (s + 1) * rps; ++r) v += ld_dsmem(dsmem_addr(frs + fj, r));
+            fsum[i] = v;
+        }
+        __syncthreads();
+        float* est = a.est + size_t(b) * (8 * F) * Sn;
+        for (int i = tid; i < 8 * F * Sn; i += SP_THREADS) {
+            const int s = i % Sn, t = i / Sn, f = t >> 3, k = t & 7;
+            float v = fsum[(s * F + f) * 16 + k];
+            v += f >= 1 ? fsum[(s * F + f - 1) * 16 + 8 + k] : tail[s * 8 + k];
+            est[i] = v;
+        }
+        __syncthreads();
+        if (tid < Sn * 8) tail[tid] = fsum[((tid >> 3) * F + F - 1) * 16 + 8 + (tid & 7)];
+        // the last 8 samples of this chunk open the next push's first frame (every CTA of the cluster is past its encoder)
+        if (tid >= 32 && tid < 40)
+            a.in_tail[size_t(b) * 8 + tid - 32] = a.mix[size_t(b) * a.ld_mix + (a.first ? 8 * F + 8 : 8 * F) - 8 + tid - 32];
+        SP_MARK(2);
+    }
+    cluster_sync_all();   // [E] peers keep their shared memory alive until rank 0 has read the frames
+}
+
+}  // namespace mtn
+
+using namespace mtn;
+
+extern "C" size_t mtn_sizeof_stream_push_args(void) { return sizeof(mtn_stream_push_args); }
+
+extern "C" int mtn_stream_push_fwd(const mtn_stream_push_args* args, mtn_stream_t stream) {
+    MTN_REQUIRE(args, "stream_push: null args");
+    const mtn_stream_push_args& a = *args;
+    MTN_REQUIRE(a.mix && a.in_tail && a.est && a.halo && a.h && a.ola_tail && a.head && a.bot_frag && a.mask_frag &&
+                    a.layer_vec && a.layer_frag, "stream_push: null pointer");
+    MTN_REQUIRE(a.B >= 1 && a.F >= 1 && a.F <= 32, "stream_push: B=%d F=%d (1 <= F <= 32 frames per push)", a.B, a.F);
+    MTN_REQUIRE(a.N == a.D && a.di == 2 * a.D && a.n_spk == 2, "stream_push: needs enc_dim == d_model, expand 2, 2 speakers");
+    MTN_REQUIRE(a.D == 64 || a.D == 128 || a.D == 256 || a.D == 512, "stream_push: d_model=%d (64, 128, 256 or 512)", a.D);
+    MTN_REQUIRE(a.n_layers >= 1, "stream_push: layers=%d", a.n_layers);
+    MTN_REQUIRE(a.ld_mix >= 8 * a.F + (a.first ? 8 : 0), "stream_push: ld_mix=%d shorter than the chunk", a.ld_mix);
+    MTN_REQUIRE(a.layer_vec_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(a.layer_vec) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(a.layer_frag) & 15) == 0 && a.layer_frag_stride % 16 == 0 &&
+                    (reinterpret_cast<uintptr_t>(a.head) & 15) == 0,
+                "stream_push: weight blobs must be 16-byte aligned");
+    const int CL = a.D / 32;
+    const int NTF = (a.F + 7) / 8;
+    MTN_REQUIRE(a.R == a.D / 16, "stream_push: dt_rank=%d, the recipes' ceil(d_model / 16) = %d is compiled in", a.R, a.D / 16);
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const void* kern = nullptr;
+    int smem_bytes = 0;
+    static std::atomic<unsigned long long> done[16];
+#define SP_PICK(NTF_, D_)                                                              \
+    do {                                                                               \
+        kern = reinterpret_cast<const void*>(&stream_push_kernel<NTF_, D_>);           \
+        smem_bytes = SpL<NTF_, D_>::total;                                             \
+    } while (0)
+#define SP_PICK_D(NTF_)                                   \
+    switch (a.D) {                                        \
+        case 64: SP_PICK(NTF_, 64); break;                \
+        case 128: SP_PICK(NTF_, 128); break;              \
+        case 256: SP_PICK(NTF_, 256); break;              \
+        default: SP_PICK(NTF_, 512); break;               \
+    }
+    switch (NTF) {
+        case 1: SP_PICK_D(1) break;
+        case 2: SP_PICK_D(2) break;
+        case 3: SP_PICK_D(3) break;
+        default: SP_PICK_D(4) break;
+    }
+#undef SP_PICK_D
+#undef SP_PICK
+    MTN_REQUIRE(smem_bytes <= 227 * 1024, "stream_push: %d B of shared memory needed", smem_bytes);
+    const int slot = (NTF - 1) * 4 + (a.D == 64 ? 0 : a.D == 128 ? 1 : a.D == 256 ? 2 : 3);
+    {
+        int dev = -1;
+        cudaGetDevice(&dev);
+        const bool tracked = dev >= 0 && dev < 64;
+        if (!tracked || !((done[slot].load(std::memory_order_acquire) >> dev) & 1ull)) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+            if (e != cudaSuccess) {
+                set_error("stream_push: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+                return MTN_ECUDA;
+            }
+            if (tracked) done[slot].fetch_or(1ull << dev, std::memory_order_release);
+        }
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(unsigned(a.B) * CL, 1, 1);
+    cfg.blockDim = dim3(SP_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = size_t(smem_bytes);
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = unsigned(CL);
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    void* kargs[1] = {const_cast<mtn_stream_push_args*>(args)};
+    cudaError_t e = cudaLaunchKernelExC(&cfg, kern, kargs);
+    if (e != cudaSuccess) {
+        set_error("stream_push: launch failed (cluster of %d CTAs, %d B smem): %s", CL, smem_bytes, cudaGetErrorString(e));
+        return MTN_ECUDA;
+    }
+    return MTN_OK;
+}

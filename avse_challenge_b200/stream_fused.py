@@ -1,0 +1,91 @@
+"""Weights and launch glue of the one-launch streaming push (``mtn_stream_push_fwd``, ``csrc/mtn_stream.cu``).
+
+A streaming chunk of a few frames makes every GEMM of the causal separator a 20-row problem; the batch plan's ~100 kernel
+launches are then pure latency.  ``FusedPush`` repacks the engine's weights once into the layouts that kernel reads
+(fp32 vectors + per-lane ``mma.sync`` fragments, one slab per cluster rank, see ``include/mtn_b200.h``) and launches the
+whole push -- encoder to overlap-add -- as one cluster kernel per call.  It works on the same carried state as the chunked
+batch plan (the reference's ``conv_state`` / ``ssm_state`` caches, ``modules/mamba/bimamba.py:374-404``, plus the encoder
+overlap and the decoder tail), so a stream may mix short pushes (this path) and long ones (batch plan).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib, ops
+from .hparams import HParams
+
+MAX_FRAMES = 32
+
+
+def eligible(hp: HParams, mode: str) -> bool:
+    """What ``mtn_stream_push_fwd`` implements (everything else streams through the batch plan)."""
+    return (not hp.bidirectional and mode == "fp32" and hp.enc_dim == hp.d_model and hp.d_model in (64, 128, 256, 512)
+            and hp.expand == 2 and hp.d_state == 16 and hp.d_conv == 4 and hp.n_spk == 2 and hp.kernel_size == 16
+            and hp.rms_norm and hp.mask_nonlinear == "relu")
+
+
+def pack_fragments(W: torch.Tensor, rows: torch.Tensor, ks: torch.Tensor) -> torch.Tensor:
+    """``W`` fp32 ``[n_out, K]`` -> the ``mma.sync.m16n8k16`` A-operand fragments of ``W[rows][:, ks]`` (both multiples of
+    16 long), bf16 ``[tiles of 16 rows][k-steps of 16][hi | lo][lane][8]``: lane (g, t) = (lane / 4, lane % 4) holds
+    a0 = (row g, k 2t..2t+1), a1 = (row g+8, same k), a2 = (row g, k 2t+8..), a3 = (row g+8, k 2t+8..)."""
+    Wt = W.index_select(0, rows).index_select(1, ks)
+    C, K = Wt.shape
+    assert C % 16 == 0 and K % 16 == 0, (C, K)
+    hi = Wt.to(torch.bfloat16)
+    lo = (Wt - hi.float()).to(torch.bfloat16)
+
+    def frag(P):   # [C, K] -> [ct, row half h, g, ks, k half q, t, e] -> [ct, ks, g, t, (q, h), e]
+        T = P.reshape(C // 16, 2, 8, K // 16, 2, 4, 2)
+        return T.permute(0, 3, 2, 5, 4, 1, 6).reshape(C // 16, K // 16, 32, 8)
+
+    return torch.stack([frag(hi), frag(lo)], dim=2).contiguous()
+
+
+class FusedPush:
+    """Packed weights of the fused push for one engine; ``run`` launches one push."""
+
+    def __init__(self, engine):
+        hp, w = engine.hp, engine.w
+        if not eligible(hp, engine.mode):
+            raise _lib.MtnError("the fused streaming push does not implement this configuration")
+        self.hp, self.device = hp, engine.device
+        N, D, di, R = hp.enc_dim, hp.d_model, hp.d_inner, hp.dt_rank
+        CL = D // 32
+        self.CL = CL
+        dev = self.device
+        f32 = lambda planes: planes.float().sum(dim=0)           # hi + lo: exact, re-splits to the same planes
+        ar = lambda a, b: torch.arange(a, b, device=dev)
+        with torch.cuda.device(dev):
+            self.head = torch.cat([w.w_enc.t().contiguous().reshape(-1), w.gamma, w.beta, w.norm_f,
+                                   w.w_dec.reshape(-1)]).contiguous()
+            w_bot, w_mask = f32(w.w_bot), f32(w.w_mask)           # [D, N], [2N, D]
+            self.bot_frag = torch.stack([pack_fragments(w_bot, ar(32 * r, 32 * r + 32), ar(0, N)) for r in range(CL)]).contiguous()
+            self.mask_frag = torch.stack([pack_fragments(w_mask, ar(64 * r, 64 * r + 64), ar(0, D)) for r in range(CL)]).contiguous()
+            vecs, frags = [], []
+            for lw in w.layers:
+                w_in, w_x = f32(lw["w_in"]), f32(lw["w_x"])       # [2di, D], [n_dbl, di] (rows dt | B | C | zero pad)
+                w_out = 0.5 * f32(lw["w_out"])                    # the batch plan packs 2 * W_out for causal stacks
+                assert w_x.shape[0] % 16 == 0
+                vecs.append(torch.cat([lw["norm"], lw["conv_w"][0].reshape(-1), lw["conv_b"][0], lw["w_dt"][0].t().reshape(-1),
+                                       lw["dt_bias"][0], lw["A2"][0].reshape(-1), lw["D"][0]]))
+                f_in = [pack_fragments(w_in, torch.cat([ar(64 * r, 64 * r + 64), ar(di + 64 * r, di + 64 * r + 64)]), ar(0, D))
+                        for r in range(CL)]
+                f_x = [pack_fragments(w_x, ar(0, w_x.shape[0]), ar(64 * r, 64 * r + 64)) for r in range(CL)]
+                f_o = [pack_fragments(w_out, ar(0, D), ar(64 * r, 64 * r + 64)) for r in range(CL)]
+                frags.append(torch.cat([t.reshape(-1) for t in (*f_in, *f_x, *f_o)]))
+            self.layer_vec = torch.stack(vecs).contiguous()       # [n_layers, floats]
+            self.layer_frag = torch.stack(frags).contiguous()     # [n_layers, bf16 elements]
+
+    def run(self, chunk: torch.Tensor, in_tail: torch.Tensor, first: bool, halo: torch.Tensor, h: torch.Tensor,
+            ola_tail: torch.Tensor, timeline=None) -> torch.Tensor:
+        """``chunk`` [B, 8F] (first push of a stream: [B, 8F + 8]) -> a fresh ``est`` [B, 8F, 2].  Carried state, read and
+        updated in place: ``in_tail`` [B, 8] (last samples of the previous chunk), ``halo`` [n_layers, B, 3, di], ``h``
+        [n_layers, 2, B, di, 16] (direction 0 is used), ``ola_tail`` [B, 2, 8]."""
+        hp = self.hp
+        B, n = chunk.shape
+        F = n // 8 - (1 if first else 0)
+        est = torch.empty((B, 8 * F, hp.n_spk), dtype=torch.float32, device=self.device)
+        ops.stream_push(chunk, in_tail, est, halo, h, ola_tail, self.head, self.bot_frag, self.mask_frag, self.layer_vec,
+                        self.layer_frag, B=B, F=F, N=hp.enc_dim, D=hp.d_model, di=hp.d_inner,
+                        R=hp.dt_rank, n_spk=hp.n_spk, n_layers=hp.n_mamba, first=first, timeline=timeline)
+        return est

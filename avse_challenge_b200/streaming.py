@@ -19,7 +19,7 @@ from __future__ import annotations
 
 import torch
 
-from . import _lib
+from . import _lib, stream_fused
 from ._cache import LRUDict
 from .engine import SeparatorEngine
 
@@ -28,14 +28,23 @@ class StreamingSeparator:
     """``push(chunk [B, 8*F]) -> est [B, 8*F', n_spk]`` with F' = F (F - 1 for the very first chunk, whose first frame
     needs 16 samples); ``flush()`` returns the last 8 samples (the tail of the final frame)."""
 
-    def __init__(self, engine: SeparatorEngine, batch: int, use_graph: bool = True):
+    def __init__(self, engine: SeparatorEngine, batch: int, use_graph: bool = True, fused: bool | None = None):
+        """``fused``: chunks of <= 32 frames go through the one-launch cluster kernel (``mtn_stream_push_fwd``) instead of
+        the batch plan's ~100 launches.  None = whenever that kernel implements the configuration; True = require it."""
         if engine.hp.bidirectional:
             raise NotImplementedError("streaming needs a causal stack: construct the model with bidirectional=False")
         self.eng, self.batch, self.use_graph = engine, batch, use_graph
         hp, dev = engine.hp, engine.device
+        can_fuse = stream_fused.eligible(hp, engine.mode) and not engine.fuse_norm
+        if fused and not can_fuse:
+            raise _lib.MtnError("fused=True: the one-launch push does not implement this configuration / plan")
+        self._fused = stream_fused.FusedPush(engine) if (can_fuse if fused is None else fused) else None
         z = lambda *shape: torch.zeros(shape, dtype=torch.float32, device=dev)
+        # one tensor per kind of cache (the fused kernel indexes it by layer); the batch plan sees per-layer views
+        self._halo = z(hp.n_mamba, batch, 3, hp.d_inner)
+        self._h = z(hp.n_mamba, 2, batch, hp.d_inner, 16)
         self.state = {
-            "layers": [{"halo": z(batch, 3, hp.d_inner), "h": z(2, batch, hp.d_inner, 16)} for _ in range(hp.n_mamba)],
+            "layers": [{"halo": self._halo[i], "h": self._h[i]} for i in range(hp.n_mamba)],
             "ola_tail": z(batch, hp.n_spk, 8),
             "est": None,
         }
@@ -77,6 +86,16 @@ class StreamingSeparator:
         if n % 8 != 0 or n == 0 or (not self.started and n < 16):
             raise _lib.MtnError(f"chunk of {n} samples: need a positive multiple of the hop (8), and >= 16 for the first chunk")
         T = n if not self.started else n + 8          # samples the encoder sees: [carried 8 | chunk]
+        L = self.eng.hp.frames(T)
+        if self._fused is not None and L <= stream_fused.MAX_FRAMES:
+            # one cluster-kernel launch: it reads the chunk and the carried samples in place and updates every cache
+            if chunk.stride(1) != 1:
+                chunk = chunk.contiguous()
+            est = self._fused.run(chunk, self.in_tail, not self.started, self._halo, self._h, self.state["ola_tail"])
+            self.started = True
+            self.samples_in += n
+            self.samples_out += 8 * L
+            return est
         ws = self.eng.workspace(self.batch, T)
         if self.started:
             ws.mix[:, :8].copy_(self.in_tail)
@@ -84,7 +103,6 @@ class StreamingSeparator:
         else:
             ws.mix[:, :T].copy_(chunk)
         self.in_tail.copy_(chunk[:, n - 8:])
-        L = ws.L
         key = (T,)
         if self.use_graph:
             g, g_ws = self._graphs.get(key, (None, None))

@@ -65,6 +65,8 @@ def parse():
     ap.add_argument("--causal", action="store_true",
                     help="unidirectional stack (bidirectional=False, mamba_blocks.py:128): one scan direction per layer")
     ap.add_argument("--chunk-ms", type=float, default=20.0, help="stream: audio per push() call")
+    ap.add_argument("--no-fused-push", action="store_true",
+                    help="stream: run short chunks through the batch plan (~100 launches) instead of the one-launch cluster kernel")
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "longform", "stream", "custom"],
                     help="cfg2 (default): S, 32 x 4 s @ 8 kHz per GPU, fp32 mode, weak scaling.  cfg3: L, global batch "
                          "256 x 4 s sharded over the GPUs, bf16 mode, strong scaling.  longform: one 10-minute 16 kHz "
@@ -639,7 +641,8 @@ def run_stream_arm(a):
     n = max(16, int(round(a.chunk_ms * 1e-3 * a.sample_rate)) // 8 * 8)     # samples per push
     sds = init_state_dicts(hp, 1234)
     eng = SeparatorEngine(hp, sds, device=dev, mode=a.mode, use_graph=False, fuse_norm=a.fuse_norm)
-    st = StreamingSeparator(eng, a.batch, use_graph=not a.no_graph)
+    st = StreamingSeparator(eng, a.batch, use_graph=not a.no_graph, fused=False if a.no_fused_push else None)
+    fused = st._fused is not None and n // 8 <= 32
     n_chunks = 64
     mix_cpu, _ = synth_mixture(min(a.batch, 8), n * n_chunks, a.sample_rate, seed=1234 + rank)
     mix_cpu = mix_cpu.repeat(-(-a.batch // mix_cpu.shape[0]), 1)[: a.batch].contiguous()
@@ -698,7 +701,8 @@ def run_stream_arm(a):
         step_ms = ms_total / a.steps
         cfg = workload_config(a, world)
         cfg["workload"] = (f"streaming causal Mamba-TasNet {a.hparams} hparams (bidirectional=False), {a.batch} concurrent stream(s) "
-                           f"per GPU, {n / a.sample_rate * 1e3:g} ms ({n // 8} frames) per push, {a.mode} mode, CUDA graph per chunk shape")
+                           f"per GPU, {n / a.sample_rate * 1e3:g} ms ({n // 8} frames) per push, {a.mode} mode, "
+                           + ("one cluster-kernel launch per push (mtn_stream_push_fwd)" if fused else "CUDA graph per chunk shape"))
         cfg["chunk_samples"] = n
         cfg["plan"] = "fuse_norm (Add -> RMSNorm folded into the GEMM epilogues)" if a.fuse_norm else "separate add_rmsnorm kernel"
         line = {
@@ -710,8 +714,10 @@ def run_stream_arm(a):
             "latency_ms": {"chunk_audio_ms": n / a.sample_rate * 1e3, "device_ms_per_push": step_ms,
                            "host_observed_median_ms": statistics.median(lat), "host_observed_max_ms": max(lat),
                            "algorithmic_latency_ms": 16 / a.sample_rate * 1e3},
-            "gpu_launches": a.steps * eng.launches_per_forward,
-            "roofline": {"kernel": "launch-latency bound (about 100 launches of a few-frame chunk per push)", "bound": "hbm",
+            "gpu_launches": a.steps * (1 if fused else eng.launches_per_forward),
+            "roofline": {"kernel": ("mtn::stream_push_kernel: one cluster per stream, bound by streaming the weights (fp32-equivalent bytes "
+                                    "of every GEMM weight once per cluster) from L2 and by its cluster barriers, not by HBM") if fused
+                         else "launch-latency bound (about 100 launches of a few-frame chunk per push)", "bound": "hbm",
                          "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "peak_source": peak_src, "traffic": None,
                          "note": "per-kernel roofline is reported on the cfg2 workload"},
             "clocks": clocks,

@@ -48,7 +48,7 @@ extern "C" {
 
 /* Bumped whenever a struct below or an entry point's signature changes; mtn_abi_version() returns the value the library
  * was built with (experiment builds of tools/devbuild.sh add 1000 so that a product binding refuses them). */
-#define MTN_ABI_VERSION 6
+#define MTN_ABI_VERSION 7
 
 #define MTN_OK 0
 #define MTN_EINVAL (-1)  /* bad shape / alignment / unsupported option */
@@ -290,6 +290,47 @@ int mtn_bias_planes_fwd(const float* x, int ldx, const float* bias, float bias_s
  * tanh(o + bo) * sigmoid(g + bg). */
 int mtn_gate_planes_fwd(const float* og, const float* bo, const float* bg, void* planes, int plane_rows, int rows, int groups,
                         int D, int n_planes, mtn_stream_t stream);
+
+/* ---- one-launch streaming push (ABI >= 7) ------------------------------------------------------------------------------
+ * The whole causal separator for one chunk of F <= 32 frames per stream, as ONE kernel launch: a thread-block cluster of
+ * d_model / 32 CTAs per stream (64 d_inner channels each), contractions on warp-level mma.sync with the same split-bf16
+ * operand model as mtn_gemm_fwd.  Replaces, for short chunks, the reference's per-token `Mamba.step` + `inference_params`
+ * caches (Mamba-TasNet/modules/mamba/bimamba.py:320-372, :374-404) under `MambaBlocksSequential.forward(x,
+ * inference_params)` (modules/mamba_blocks.py:186-197) together with the Encoder / MaskNet / Decoder calls around the
+ * stack (train_wsj0mix.py:86-111); same carried state as the chunked batch plan (conv history, SSM state, overlap-add
+ * tail).  Needs enc_dim == d_model in {64, 128, 256, 512}, expand 2, d_state 16, d_conv 4, RMSNorm blocks, ReLU mask,
+ * 2 speakers, unidirectional mixers, fp32 mode.  Weight blobs are packed once by the caller (layouts below; the Python
+ * packer is avse_challenge_b200/stream_fused.py):
+ *   head       fp32: w_enc^T [16][N] | cLN gamma [N] | beta [N] | norm_f [D] | w_dec [N][16]
+ *   layer_vec  fp32 per layer: norm [D] | conv_w [di][4] | conv_b [di] | w_dt^T [R][di] | dt_bias [di] | A2 [di][16] | D [di]
+ *   *_frag     mma.sync A-operand fragments, bf16: [cluster rank][16-column tile][k-step of 16][plane hi|lo][lane][8]:
+ *              bot_frag (rank r: bottleneck rows 32r..32r+31), mask_frag (rank r: mask rows 64r..64r+63), per layer
+ *              in_proj (rank r: rows 64r.. of x then di + 64r.. of z; K = D) | x_proj (rows dt|B|C padded to a multiple of
+ *              16; K = channels 64r..64r+63) | out_proj (all D rows; K = channels 64r..64r+63) */
+typedef struct {
+    const float* mix;       /* [B][ld_mix]: this push's chunk, 8*F samples (first push: 8*F + 8) */
+    float* in_tail;         /* in/out [B][8]: the last 8 samples of the previous chunk (the encoder window overlaps it);
+                               ignored on input when first != 0, always updated */
+    float* est;             /* [B][8*F][n_spk] */
+    float* halo;            /* in/out [n_layers][B][3][di]: last three conv inputs (the reference's conv_state) */
+    float* h;               /* in/out: layer l, stream b at h + l*h_layer_stride + b*di*16: [di][16] (ssm_state) */
+    float* ola_tail;        /* in/out [B][n_spk][8]: second half of the last decoder frame */
+    const float* head;
+    const void* bot_frag;
+    const void* mask_frag;
+    const float* layer_vec;
+    const void* layer_frag;
+    size_t h_layer_stride;  /* floats */
+    size_t layer_vec_stride;  /* floats */
+    size_t layer_frag_stride; /* bytes */
+    int B, F, N, D, di, R, n_spk, n_layers, ld_mix;
+    int first;              /* != 0: first push of a stream (no carried samples; the chunk holds F + 1 hops) */
+    float eps_cln, eps_rms;
+    unsigned long long* timeline; /* nullable debug aid: [n_layers + 2][16] globaltimer stamps of stream 0, rank 0 */
+} mtn_stream_push_args;
+
+int mtn_stream_push_fwd(const mtn_stream_push_args* args, mtn_stream_t stream);
+size_t mtn_sizeof_stream_push_args(void);
 
 const char* mtn_last_error_string(void);
 int mtn_abi_version(void);

@@ -1,0 +1,116 @@
+"""GPU (-m gpu): the one-launch streaming push (``mtn_stream_push_fwd``, one thread-block cluster per stream) against the
+one-shot causal forward, the chunked batch plan and the CPU oracle.  It replaces, for chunks of <= 32 frames, the
+reference's ``Mamba.step`` / ``inference_params`` streaming (``modules/mamba/bimamba.py:320-372``).
+Gates: streaming == one-shot within 5e-5 x rms (two fp32-class summation orders of the same arithmetic); against the oracle
+the north-star gate 1e-3 x rms, |dSI-SNR| <= 0.01 dB.
+"""
+import os
+
+import pytest
+import torch
+
+from avse_challenge_b200 import CONFIGS, init_state_dicts, synth_mixture, pit_si_snr
+from avse_challenge_b200 import _lib
+from avse_challenge_b200.engine import SeparatorEngine
+from avse_challenge_b200.streaming import StreamingSeparator
+from oracle import restate
+from tests.helpers import load_golden_forward, rel_max, hp_from_sds
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _stream(eng, mix, cuts, fused):
+    st = StreamingSeparator(eng, mix.shape[0], use_graph=False, fused=fused)
+    outs, pos = [], 0
+    for c in cuts:
+        outs.append(st.push(mix[:, pos:pos + c].contiguous()))
+        pos += c
+    assert pos == mix.shape[1]
+    outs.append(st.flush())
+    return torch.cat(outs, dim=1)
+
+
+@pytest.mark.parametrize("chunk", [16, 8 * 3, 8 * 20, 8 * 32])
+def test_fused_push_equals_one_shot_tiny(chunk):
+    hp = CONFIGS["tiny"].causal()          # cluster of 2 CTAs, dt_rank 4
+    sds = init_state_dicts(hp, 11)
+    B, T = 2, 8 * 640
+    mix, src = synth_mixture(B, T, seed=5)
+    eng = SeparatorEngine(hp, sds, device=DEV, mode="fp32", use_graph=False)
+    one = eng(mix.to(DEV)).cpu()
+    first = chunk if chunk >= 16 else 16
+    cuts = [first] + [chunk] * ((T - first) // chunk)
+    cuts = cuts + ([T - sum(cuts)] if sum(cuts) < T else [])
+    got = _stream(eng, mix.to(DEV), cuts, fused=True).cpu()
+    assert got.shape == one.shape
+    err = rel_max(got, one)
+    print(f"fused push, chunk {chunk}: max-abs/rms vs one-shot {err:.3e}")
+    assert err <= 5e-5, err
+    with torch.no_grad():
+        ref = restate.separate(mix, sds, hp.n_mamba, scan_impl="c")
+    e2 = rel_max(got, ref)
+    d2 = (pit_si_snr(got, src) - pit_si_snr(ref, src)).abs().max().item()
+    assert e2 <= 1e-3 and d2 <= 0.01, (e2, d2)
+
+
+def test_fused_and_batch_plan_share_one_stream_state():
+    """Short pushes (cluster kernel) and long ones (batch plan) interleave on the same carried state."""
+    hp = CONFIGS["tiny"].causal()
+    sds = init_state_dicts(hp, 12)
+    B = 3
+    cuts = [160, 1000, 16, 8, 256, 2664, 64, 8 * 31]
+    T = sum(cuts)
+    mix, _ = synth_mixture(B, T, seed=6)
+    eng = SeparatorEngine(hp, sds, device=DEV, mode="fp32", use_graph=False)
+    one = eng(mix.to(DEV)).cpu()
+    mixed = _stream(eng, mix.to(DEV), cuts, fused=None).cpu()
+    plain = _stream(eng, mix.to(DEV), cuts, fused=False).cpu()
+    e1, e2 = rel_max(mixed, one), rel_max(plain, one)
+    print(f"mixed fused/batch pushes vs one-shot {e1:.3e}; batch plan only {e2:.3e}")
+    assert e1 <= 5e-5 and e2 <= 5e-5
+
+
+@pytest.mark.parametrize("name,B,frames", [("XS", 2, 20), ("S", 3, 20), ("S", 1, 7), ("L", 1, 24)])
+def test_fused_push_shipped_sizes_vs_oracle(name, B, frames):
+    """Cluster sizes 4 / 8 / 16 (the non-portable size needs the opt-in attribute), dt_rank 8 / 16 / 32."""
+    hp = CONFIGS[name].causal()
+    sds = init_state_dicts(hp, 1234)
+    T = 8 * frames * 6 + 8
+    mix, src = synth_mixture(B, T, seed=7)
+    eng = SeparatorEngine(hp, sds, device=DEV, mode="fp32", use_graph=False)
+    one = eng(mix.to(DEV)).cpu()
+    cuts = [8 * frames + 8] + [8 * frames] * 5
+    got = _stream(eng, mix.to(DEV), cuts, fused=True).cpu()
+    err = rel_max(got, one)
+    with torch.no_grad():
+        ref = restate.separate(mix, sds, hp.n_mamba, scan_impl="c")
+    e2 = rel_max(got, ref)
+    d2 = (pit_si_snr(got, src) - pit_si_snr(ref, src)).abs().max().item()
+    print(f"{hp.name} B={B} F={frames}: vs one-shot {err:.3e}, vs oracle {e2:.3e}, dSI-SNR {d2:.2e}")
+    assert err <= 5e-5 and e2 <= 1e-3 and d2 <= 0.01, (err, e2, d2)
+
+
+def test_fused_push_matches_reference_streaming_golden(golden_dir):
+    """The reference's own inference_params run (prefill + step per token) of the tiny causal model."""
+    sds, g, _ = load_golden_forward(os.path.join(golden_dir, "forward_tiny_causal.npz"))
+    hp = hp_from_sds(sds).causal()
+    eng = SeparatorEngine(hp, sds, device=DEV, mode="fp32", use_graph=False)
+    mix = g["mix"]
+    T = mix.shape[1] // 8 * 8
+    cuts = [64] + [40] * ((T - 64) // 40)
+    cuts += [T - sum(cuts)] if sum(cuts) < T else []
+    got = _stream(eng, mix[:, :T].contiguous().to(DEV), cuts, fused=True).cpu()
+    ref = g["est"][:, :got.shape[1]]
+    err = rel_max(got[:, :ref.shape[1]], ref)
+    print(f"fused push vs reference causal golden: {err:.3e}")
+    assert err <= 1e-3, err
+
+
+def test_fused_push_rejects_what_it_does_not_implement():
+    hp = CONFIGS["tiny"].causal()
+    sds = init_state_dicts(hp, 3)
+    eng = SeparatorEngine(hp, sds, device=DEV, mode="bf16", use_graph=False)
+    with pytest.raises(_lib.MtnError):
+        StreamingSeparator(eng, 1, fused=True)
+    assert StreamingSeparator(eng, 1)._fused is None      # auto: falls back to the batch plan's chunk kernels

@@ -173,3 +173,34 @@ def test_synth_is_deterministic_and_scaled():
     assert torch.allclose(mix, src.sum(-1))
     s = pit_si_snr(src.flip(-1) * 1.7, src)
     assert (s > 60).all()
+
+
+def test_stream_fragment_packer_matches_mma_layout():
+    """stream_fused.pack_fragments lays a weight slice out as mma.sync.m16n8k16 A fragments (row-major 16 x 16 tile: lane
+    (g, t) holds a0 = (g, 2t..2t+1), a1 = (g+8, 2t..), a2 = (g, 2t+8..), a3 = (g+8, 2t+8..)); rebuild the tiles from the packed
+    tensor exactly as the tensor core reads them and compare with hi + lo of the weight."""
+    from avse_challenge_b200.stream_fused import pack_fragments, eligible
+    from avse_challenge_b200 import CONFIGS
+    g = torch.Generator().manual_seed(0)
+    W = torch.randn(96, 80, generator=g)
+    rows = torch.cat([torch.arange(16, 48), torch.arange(64, 96)])
+    ks = torch.arange(16, 80)
+    fr = pack_fragments(W, rows, ks)                          # [ct, ks, 2, 32, 8]
+    assert fr.dtype == torch.bfloat16 and tuple(fr.shape) == (4, 4, 2, 32, 8)
+    Wt = W[rows][:, ks]
+    hi = Wt.to(torch.bfloat16)
+    lo = (Wt - hi.float()).to(torch.bfloat16)
+    for plane, want in ((0, hi), (1, lo)):
+        for ct in range(4):
+            for s in range(4):
+                tile = torch.zeros(16, 16, dtype=torch.bfloat16)
+                for lane in range(32):
+                    gg, t = lane // 4, lane % 4
+                    regs = fr[ct, s, plane, lane].view(4, 2)
+                    tile[gg, 2 * t:2 * t + 2] = regs[0]
+                    tile[gg + 8, 2 * t:2 * t + 2] = regs[1]
+                    tile[gg, 2 * t + 8:2 * t + 10] = regs[2]
+                    tile[gg + 8, 2 * t + 8:2 * t + 10] = regs[3]
+                assert torch.equal(tile, want[16 * ct:16 * ct + 16, 16 * s:16 * s + 16])
+    assert eligible(CONFIGS["S"].causal(), "fp32") and eligible(CONFIGS["tiny"].causal(), "fp32")
+    assert not eligible(CONFIGS["S"], "fp32") and not eligible(CONFIGS["S"].causal(), "bf16")
