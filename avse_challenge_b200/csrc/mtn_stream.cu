@@ -100,16 +100,18 @@ __device__ __forceinline__ float4 ld_dsmem4(uint32_t addr) {
     asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
     return v;
 }
-// sum over the cluster ranks of the float4 at the same shared-memory address: eight loads in flight before the first add
+// sum over the cluster ranks of the float4 at the same shared-memory address: eight loads in flight before the first add.
+// Rank `rank` starts with its right-hand neighbour, so the eight CTAs never queue on the same peer's shared-memory port; the
+// order of the additions therefore differs from rank to rank (and is fixed for a rank: results are reproducible).
 template <int CL>
-__device__ __forceinline__ float4 rank_sum4(const float* local) {
+__device__ __forceinline__ float4 rank_sum4(const float* local, int rank) {
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int r0 = 0; r0 < CL; r0 += 8) {
         constexpr int NB = CL < 8 ? CL : 8;
         float4 v[NB];
 #pragma unroll
-        for (int r = 0; r < NB; ++r) v[r] = ld_dsmem4(dsmem_addr(local, r0 + r));
+        for (int r = 0; r < NB; ++r) v[r] = ld_dsmem4(dsmem_addr(local, (rank + 1 + r0 + r) & (CL - 1)));
 #pragma unroll
         for (int r = 0; r < NB; ++r) { s.x += v[r].x; s.y += v[r].y; s.z += v[r].z; s.w += v[r].w; }
     }
@@ -127,75 +129,111 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
         if (a.timeline && blockIdx.x == 0 && tid == 0) a.timeline[size_t(tl_row) * 16 + (k)] = global_timer_ns();          \
     } while (0)
 
-// One warp: C[16 channels of tile][8*NTF frames] += W_frag[ksteps] x act[frames][k0 + 16*ksteps].
-// wf -> this unit's fragments: per k-step 2 planes (hi, lo) x 32 lanes x 16 B.  Up to PF k-steps of weights are in flight.
-template <int NTF>
-__device__ __forceinline__ void mma_unit(const uint4* __restrict__ wf, int ksteps, const __nv_bfloat16* ahi,
-                                         const __nv_bfloat16* alo, int lda, int k0, float (&acc)[NTF][4], int lane) {
-    constexpr int PF = 8;
-    const int g = lane >> 2, t = lane & 3;
-    uint4 wh[PF], wl[PF];
+// ---- CTA-wide GEMM on pre-packed weight fragments.
+// CT tiles of 16 output channels x KSTEPS k-steps of 16.  With fewer tiles than warps the k range is cut KS ways (partial sums
+// in red[ks][frame][ldr], ldr = 16*CT + 4); a warp works on units (tile, k part) warp, warp + 16, ...  The weights of a
+// warp's FIRST unit (up to 8 k-steps = 64 registers) can be requested long before the operand planes exist (`issue`), so the
+// L2 round trip and the 512 B / k-step / warp stream hide behind the phase in between.
+template <int CT, int KSTEPS>
+struct GemmShape {
+    static constexpr int ks_() {
+        int KS = 1;
+        while (KS * 2 * CT <= SP_WARPS && KS * 2 <= KSTEPS && KSTEPS % (KS * 2) == 0) KS *= 2;
+        return KS;
+    }
+    static constexpr int KS = ks_(), KPER = KSTEPS / KS, UNITS = CT * KS, NPRE = KPER < 8 ? KPER : 8, LDR = 16 * CT + 4;
+};
+
+__device__ __forceinline__ uint4 ld_weights(const uint4* p) {   // volatile: stays where it is issued
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
+template <int NB>
+struct WFrag {
+    uint4 h[NB], l[NB];
+};
+
+template <int NB>
+__device__ __forceinline__ void wfrag_load(WFrag<NB>& w, const uint4* __restrict__ wf, int lane) {
 #pragma unroll
-    for (int i = 0; i < PF; ++i)
-        if (i < ksteps) {
-            wh[i] = __ldg(wf + (i * 2) * 32 + lane);
-            wl[i] = __ldg(wf + (i * 2 + 1) * 32 + lane);
-        }
-    const __nv_bfloat16* bh = ahi + g * lda + k0 + 2 * t;
-    const __nv_bfloat16* bl = alo + g * lda + k0 + 2 * t;
-    for (int s = 0; s < ksteps; s += PF) {
+    for (int i = 0; i < NB; ++i) {
+        w.h[i] = ld_weights(wf + (i * 2) * 32 + lane);
+        w.l[i] = ld_weights(wf + (i * 2 + 1) * 32 + lane);
+    }
+}
+
+template <int CT, int KSTEPS>
+__device__ __forceinline__ void gemm_issue(WFrag<GemmShape<CT, KSTEPS>::NPRE>& w, const uint4* __restrict__ wfrag, int warp, int lane) {
+    using G = GemmShape<CT, KSTEPS>;
+    if (warp < G::UNITS) wfrag_load<G::NPRE>(w, wfrag + (size_t(warp / G::KS) * KSTEPS + size_t(warp % G::KS) * G::KPER) * 64, lane);
+}
+
+// acc += W[NB k-steps] x act rows (bh / bl point at this lane's element of k-step 0)
+template <int NTF, int NB>
+__device__ __forceinline__ void mma_batch(const WFrag<NB>& w, const __nv_bfloat16* bh, const __nv_bfloat16* bl, int lda,
+                                          float (&acc)[NTF][4]) {
 #pragma unroll
-        for (int i = 0; i < PF; ++i) {
-            if (s + i < ksteps) {
-                const uint4 ah = wh[i], al = wl[i];
-                if (s + i + PF < ksteps) {
-                    wh[i] = __ldg(wf + ((s + i + PF) * 2) * 32 + lane);
-                    wl[i] = __ldg(wf + ((s + i + PF) * 2 + 1) * 32 + lane);
-                }
-                const int ko = (s + i) * 16;
+    for (int i = 0; i < NB; ++i) {
 #pragma unroll
-                for (int j = 0; j < NTF; ++j) {
-                    const uint32_t h0 = *reinterpret_cast<const uint32_t*>(bh + j * 8 * lda + ko);
-                    const uint32_t h1 = *reinterpret_cast<const uint32_t*>(bh + j * 8 * lda + ko + 8);
-                    const uint32_t l0 = *reinterpret_cast<const uint32_t*>(bl + j * 8 * lda + ko);
-                    const uint32_t l1 = *reinterpret_cast<const uint32_t*>(bl + j * 8 * lda + ko + 8);
-                    mma16816(acc[j], ah, h0, h1);
-                    mma16816(acc[j], al, h0, h1);
-                    mma16816(acc[j], ah, l0, l1);
-                }
-            }
+        for (int j = 0; j < NTF; ++j) {
+            const uint32_t h0 = *reinterpret_cast<const uint32_t*>(bh + j * 8 * lda + i * 16);
+            const uint32_t h1 = *reinterpret_cast<const uint32_t*>(bh + j * 8 * lda + i * 16 + 8);
+            const uint32_t l0 = *reinterpret_cast<const uint32_t*>(bl + j * 8 * lda + i * 16);
+            const uint32_t l1 = *reinterpret_cast<const uint32_t*>(bl + j * 8 * lda + i * 16 + 8);
+            mma16816(acc[j], w.h[i], h0, h1);
+            mma16816(acc[j], w.l[i], h0, h1);
+            mma16816(acc[j], w.h[i], l0, l1);
         }
     }
 }
 
-// CTA-wide GEMM on fragments: CT tiles of 16 output channels, `ksteps` k-steps of 16; when there are fewer tiles than warps
-// the k range is cut KS ways and the partial sums land in red[ks][frame][ldr] (ldr = 16*CT + 4).  Returns KS.
-template <int NTF>
-__device__ __forceinline__ int gemm_frag(const uint4* __restrict__ wfrag, int CT, int ksteps, const __nv_bfloat16* ahi,
-                                         const __nv_bfloat16* alo, int lda, float* red, int warp, int lane) {
+template <int NTF, int CT, int KSTEPS>
+__device__ __forceinline__ void gemm_run(const WFrag<GemmShape<CT, KSTEPS>::NPRE>& pre, const uint4* __restrict__ wfrag,
+                                         const __nv_bfloat16* ahi, const __nv_bfloat16* alo, int lda, float* red, int warp, int lane) {
+    using G = GemmShape<CT, KSTEPS>;
     constexpr int Fp = 8 * NTF;
-    int KS = 1;
-    while (KS * 2 * CT <= SP_WARPS && KS * 2 <= ksteps && ksteps % (KS * 2) == 0) KS *= 2;
-    const int kper = ksteps / KS;
-    const int ldr = 16 * CT + 4;
     const int g = lane >> 2, t = lane & 3;
-    for (int unit = warp; unit < CT * KS; unit += SP_WARPS) {
-        const int ct = unit / KS, ks = unit % KS;
+#pragma unroll 1
+    for (int unit = warp; unit < G::UNITS; unit += SP_WARPS) {
+        const int ct = unit / G::KS, ks = unit % G::KS;
+        const uint4* wf = wfrag + (size_t(ct) * KSTEPS + size_t(ks) * G::KPER) * 64;
+        const __nv_bfloat16* bh = ahi + g * lda + ks * G::KPER * 16 + 2 * t;
+        const __nv_bfloat16* bl = alo + g * lda + ks * G::KPER * 16 + 2 * t;
         float acc[NTF][4];
 #pragma unroll
         for (int j = 0; j < NTF; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
-        mma_unit<NTF>(wfrag + (size_t(ct) * ksteps + size_t(ks) * kper) * 64, kper, ahi, alo, lda, ks * kper * 16, acc, lane);
-        float* r = red + size_t(ks) * Fp * ldr + ct * 16 + g;
+        if (unit == warp) {
+            mma_batch<NTF, G::NPRE>(pre, bh, bl, lda, acc);
+            if constexpr (G::KPER > G::NPRE) {
+                static_assert(G::KPER <= G::NPRE || (G::KPER - G::NPRE) % 4 == 0, "k-step remainder in batches of four");
+#pragma unroll 1
+                for (int k = G::NPRE; k < G::KPER; k += 4) {
+                    WFrag<4> w;
+                    wfrag_load<4>(w, wf + size_t(k) * 64, lane);
+                    mma_batch<NTF, 4>(w, bh + k * 16, bl + k * 16, lda, acc);
+                }
+            }
+        } else {
+            constexpr int NB = G::KPER % 4 == 0 ? 4 : (G::KPER % 2 == 0 ? 2 : 1);
+#pragma unroll 1
+            for (int k = 0; k < G::KPER; k += NB) {
+                WFrag<NB> w;
+                wfrag_load<NB>(w, wf + size_t(k) * 64, lane);
+                mma_batch<NTF, NB>(w, bh + k * 16, bl + k * 16, lda, acc);
+            }
+        }
+        float* r = red + size_t(ks) * Fp * G::LDR + ct * 16 + g;
 #pragma unroll
         for (int j = 0; j < NTF; ++j) {
             const int f0 = j * 8 + 2 * t;
-            r[f0 * ldr] = acc[j][0];
-            r[(f0 + 1) * ldr] = acc[j][1];
-            r[f0 * ldr + 8] = acc[j][2];
-            r[(f0 + 1) * ldr + 8] = acc[j][3];
+            r[f0 * G::LDR] = acc[j][0];
+            r[(f0 + 1) * G::LDR] = acc[j][1];
+            r[f0 * G::LDR + 8] = acc[j][2];
+            r[(f0 + 1) * G::LDR + 8] = acc[j][3];
         }
     }
-    return KS;
 }
 
 __device__ __forceinline__ float red_sum(const float* red, int KS, int Fp, int ldr, int f, int c) {
@@ -206,22 +244,41 @@ __device__ __forceinline__ float red_sum(const float* red, int KS, int Fp, int l
 
 // RMSNorm of all F rows of the residual, whose 32-column slices live in the `res` buffers of the cluster's CTAs, under the
 // weight g (shared memory) -> operand planes.  Lane = column inside a slice, so a warp reads 128 contiguous bytes per peer.
-template <int CL>
-__device__ __forceinline__ void rmsnorm_rows(const float* res_local, const float* g, int F, float eps, __nv_bfloat16* ahi,
-                                             __nv_bfloat16* alo, int lda, int warp, int lane) {
-    constexpr int D = 32 * CL;
-    for (int f = warp; f < F; f += SP_WARPS) {
-        float v[CL];
-        float sq = 0.f;
+// Split in two so that the caller can put its weight requests BETWEEN the peer reads and their use: issued first, 128 KB of
+// weight loads per CTA queue in front of the DSMEM reads in the load pipe and delay the norm by a microsecond.
+template <int CL, int ROWS>   // ROWS = rows per warp (1 for F <= 16, 2 for F <= 32)
+struct NormRows {
+    float v[ROWS][CL];
+    __device__ __forceinline__ void gather(const float* res_local, int F, int warp, int lane, int rank) {
 #pragma unroll
-        for (int r = 0; r < CL; ++r) v[r] = ld_dsmem(dsmem_addr(res_local + f * SP_CSL + lane, r));
+        for (int i = 0; i < ROWS; ++i) {
+            const int f = warp + i * SP_WARPS;
+            if (f < F) {
 #pragma unroll
-        for (int r = 0; r < CL; ++r) sq = fmaf(v[r], v[r], sq);
-        const float rstd = rsqrtf(warp_sum(sq) * (1.0f / D) + eps);
-#pragma unroll
-        for (int r = 0; r < CL; ++r) put_planes(ahi, alo, f * lda + 32 * r + lane, v[r] * rstd * g[32 * r + lane]);
+                for (int r = 0; r < CL; ++r) v[i][r] = ld_dsmem(dsmem_addr(res_local + f * SP_CSL + lane, (rank + r) & (CL - 1)));
+            }
+        }
     }
-}
+    __device__ __forceinline__ void finish(const float* g, int F, float eps, __nv_bfloat16* ahi, __nv_bfloat16* alo, int lda, int warp,
+                                           int lane, int rank) {
+        constexpr int D = 32 * CL;
+#pragma unroll
+        for (int i = 0; i < ROWS; ++i) {
+            const int f = warp + i * SP_WARPS;
+            if (f < F) {
+                float sq = 0.f;
+#pragma unroll
+                for (int r = 0; r < CL; ++r) sq = fmaf(v[i][r], v[i][r], sq);
+                const float rstd = rsqrtf(warp_sum(sq) * (1.0f / D) + eps);
+#pragma unroll
+                for (int r = 0; r < CL; ++r) {
+                    const int col = 32 * ((rank + r) & (CL - 1)) + lane;
+                    put_planes(ahi, alo, f * lda + col, v[i][r] * rstd * g[col]);
+                }
+            }
+        }
+    }
+};
 
 template <int NTF, int D>
 __global__ void __launch_bounds__(SP_THREADS, 1) stream_push_kernel(const mtn_stream_push_args a) {
@@ -263,6 +320,10 @@ __global__ void __launch_bounds__(SP_THREADS, 1) stream_push_kernel(const mtn_st
     for (int i = tid; i < D / 4; i += SP_THREADS) cp_async16(s_norm + 4 * i, a.layer_vec + 4 * i);
     cp_async_commit();
     __syncthreads();
+
+    // bottleneck weights: requested now, used after the encoder
+    WFrag<GemmShape<SP_CSL / 16, N / 16>::NPRE> w_bot;
+    gemm_issue<SP_CSL / 16, N / 16>(w_bot, reinterpret_cast<const uint4*>(a.bot_frag) + size_t(rank) * (SP_CSL / 16) * (N / 16) * 64, warp, lane);
 
     // ------------------------------------------------------------------ encoder + cLN (every CTA, all rows)
     {
@@ -312,10 +373,11 @@ __global__ void __launch_bounds__(SP_THREADS, 1) stream_push_kernel(const mtn_st
 
     // ------------------------------------------------------------------ bottleneck: this CTA's 32 columns of h; residual := h
     {
+        using G = GemmShape<SP_CSL / 16, N / 16>;
         const uint4* wf = reinterpret_cast<const uint4*>(a.bot_frag) + size_t(rank) * (SP_CSL / 16) * (N / 16) * 64;
-        const int KS = gemm_frag<NTF>(wf, SP_CSL / 16, N / 16, act_hi, act_lo, lda, red, warp, lane);
+        gemm_run<NTF, SP_CSL / 16, N / 16>(w_bot, wf, act_hi, act_lo, lda, red, warp, lane);
         __syncthreads();
-        for (int i = tid; i < F * SP_CSL; i += SP_THREADS) res[i] = red_sum(red, KS, Fp, SP_CSL + 4, i / SP_CSL, i % SP_CSL);
+        for (int i = tid; i < F * SP_CSL; i += SP_THREADS) res[i] = red_sum(red, G::KS, Fp, G::LDR, i / SP_CSL, i % SP_CSL);
     }
     cp_async_wait_all();
     cluster_sync_all();   // [A]
@@ -332,64 +394,81 @@ __global__ void __launch_bounds__(SP_THREADS, 1) stream_push_kernel(const mtn_st
     float* s_dt_bias = s_w_dt + SP_DSL * R;
     float* s_A2 = s_dt_bias + SP_DSL;
     float* s_D = s_A2 + SP_DSL * 16;
+    using GI = GemmShape<ct_in, ks_d>;
+    using GX = GemmShape<ct_x, ks_c>;
+    using GO = GemmShape<ct_o, ks_c>;
+    // asynchronous copy of a layer's small vectors (this CTA's slices) + the norm weight of the layer after it
+    auto prefetch_vectors = [&](int layer) {
+        const float* lv = a.layer_vec + size_t(layer) * a.layer_vec_stride;
+        const float* conv_w = lv + D;
+        const float* conv_b = conv_w + size_t(di) * 4;
+        const float* w_dt = conv_b + di;
+        const float* dt_bias = w_dt + size_t(di) * R;
+        const float* A2 = dt_bias + di;
+        const float* Dskip = A2 + size_t(di) * 16;
+        const float* next_norm = layer + 1 < a.n_layers ? lv + a.layer_vec_stride : norm_f;
+        constexpr int q_cw = SP_DSL, q_v = SP_DSL / 4, q_wd = R * (SP_DSL / 4), q_a2 = SP_DSL * 4, q_n = D / 4;   // 16-byte chunks
+        for (int i = tid; i < q_cw + 3 * q_v + q_wd + q_a2 + q_n; i += SP_THREADS) {
+            int j = i;
+            if (j < q_cw) { cp_async16(s_conv_w + 4 * j, conv_w + size_t(ch0) * 4 + 4 * j); continue; }
+            j -= q_cw;
+            if (j < q_v) { cp_async16(s_conv_b + 4 * j, conv_b + ch0 + 4 * j); continue; }
+            j -= q_v;
+            if (j < q_wd) { cp_async16(s_w_dt + 4 * j, w_dt + size_t(j / (SP_DSL / 4)) * di + ch0 + 4 * (j % (SP_DSL / 4))); continue; }
+            j -= q_wd;
+            if (j < q_v) { cp_async16(s_dt_bias + 4 * j, dt_bias + ch0 + 4 * j); continue; }
+            j -= q_v;
+            if (j < q_a2) { cp_async16(s_A2 + 4 * j, A2 + size_t(ch0) * 16 + 4 * j); continue; }
+            j -= q_a2;
+            if (j < q_v) { cp_async16(s_D + 4 * j, Dskip + ch0 + 4 * j); continue; }
+            j -= q_v;
+            cp_async16(s_norm + ((layer + 1) & 1) * D + 4 * j, next_norm + 4 * j);
+        }
+        cp_async_commit();
+    };
+    prefetch_vectors(0);
     SP_MARK(0);
     for (int layer = 0; layer < a.n_layers; ++layer) {
         tl_row = 1 + layer;
-        // layer vector blob: norm [D] | conv_w [di][4] | conv_b [di] | w_dt^T [R][di] | dt_bias [di] | A2 [di][16] | Dskip [di]
-        const float* lv = a.layer_vec + size_t(layer) * a.layer_vec_stride;
         // layer fragment blob: in_proj [CL][ct_in][ks_d] | x_proj [CL][ct_x][ks_c] | out_proj [CL][ct_o][ks_c], 1 KiB each
         const uint4* lf = reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(a.layer_frag) +
                                                          size_t(layer) * a.layer_frag_stride);
+        const uint4* f_in = lf + size_t(rank) * in_units * 64;
+        const uint4* f_x = lf + (size_t(CL) * in_units + size_t(rank) * x_units) * 64;
+        const uint4* f_o = lf + (size_t(CL) * (in_units + x_units) + size_t(rank) * o_units) * 64;
         float* halo = a.halo + (size_t(layer) * a.B + b) * 3 * di + ch0;
         float* hst = a.h + size_t(layer) * a.h_layer_stride + (size_t(b) * di + ch0) * 16;
 
-        // small vectors of this layer + the NEXT norm weight: asynchronous copies, waited for before the conv (their previous
-        // readers are at least one cluster barrier back)
+        // Add -> RMSNorm (bimamba.py:446-447), all rows in every CTA.  Order of the requests: the peers' residual slices, then
+        // everything that does not depend on this layer's activations (in_proj weights of this warp's unit, the SSM state of
+        // this thread's (channel, state pair), the conv history), then the norm itself.
+        NormRows<CL, (NTF + 1) / 2> nr;
+        nr.gather(res, F, warp, lane, rank);
+        WFrag<GI::NPRE> w_in;
+        gemm_issue<ct_in, ks_d>(w_in, f_in, warp, lane);
+        float2 h;
         {
-            const float* conv_w = lv + D;
-            const float* conv_b = conv_w + size_t(di) * 4;
-            const float* w_dt = conv_b + di;
-            const float* dt_bias = w_dt + size_t(di) * R;
-            const float* A2 = dt_bias + di;
-            const float* Dskip = A2 + size_t(di) * 16;
-            const float* next_norm = layer + 1 < a.n_layers ? lv + a.layer_vec_stride : norm_f;
-            constexpr int q_cw = SP_DSL, q_v = SP_DSL / 4, q_wd = R * (SP_DSL / 4), q_a2 = SP_DSL * 4, q_n = D / 4;   // 16-byte chunks
-            for (int i = tid; i < q_cw + 3 * q_v + q_wd + q_a2 + q_n; i += SP_THREADS) {
-                int j = i;
-                if (j < q_cw) { cp_async16(s_conv_w + 4 * j, conv_w + size_t(ch0) * 4 + 4 * j); continue; }
-                j -= q_cw;
-                if (j < q_v) { cp_async16(s_conv_b + 4 * j, conv_b + ch0 + 4 * j); continue; }
-                j -= q_v;
-                if (j < q_wd) { cp_async16(s_w_dt + 4 * j, w_dt + size_t(j / (SP_DSL / 4)) * di + ch0 + 4 * (j % (SP_DSL / 4))); continue; }
-                j -= q_wd;
-                if (j < q_v) { cp_async16(s_dt_bias + 4 * j, dt_bias + ch0 + 4 * j); continue; }
-                j -= q_v;
-                if (j < q_a2) { cp_async16(s_A2 + 4 * j, A2 + size_t(ch0) * 16 + 4 * j); continue; }
-                j -= q_a2;
-                if (j < q_v) { cp_async16(s_D + 4 * j, Dskip + ch0 + 4 * j); continue; }
-                j -= q_v;
-                cp_async16(s_norm + ((layer + 1) & 1) * D + 4 * j, next_norm + 4 * j);
-            }
-            cp_async_commit();
+            const float* hp = hst + (tid >> 3) * 16 + 2 * (tid & 7);
+            asm volatile("ld.global.v2.f32 {%0,%1}, [%2];" : "=f"(h.x), "=f"(h.y) : "l"(hp));
         }
-
-        // Add -> RMSNorm (bimamba.py:446-447): all rows, every CTA
-        rmsnorm_rows<CL>(res, s_norm + (layer & 1) * D, F, a.eps_rms, act_hi, act_lo, lda, warp, lane);
+        float halo_v = 0.f;
+        if (tid < 3 * SP_DSL) asm volatile("ld.global.f32 %0, [%1];" : "=f"(halo_v) : "l"(halo + (tid / SP_DSL) * di + tid % SP_DSL));
+        nr.finish(s_norm + (layer & 1) * D, F, a.eps_rms, act_hi, act_lo, lda, warp, lane, rank);
         __syncthreads();
         SP_MARK(1);
 
         // in_proj: x columns [ch0, ch0+64) and z columns di + [ch0, ch0+64)
-        {
-            const int KS = gemm_frag<NTF>(lf + size_t(rank) * in_units * 64, ct_in, ks_d, act_hi, act_lo, lda, red, warp, lane);
-            if (tid < 3 * SP_DSL) xs[tid] = halo[(tid / SP_DSL) * di + tid % SP_DSL];   // conv history = rows -3..-1
-            __syncthreads();
-            SP_MARK(2);
-            for (int i = tid; i < F * 2 * SP_DSL; i += SP_THREADS) {
-                const int f = i / (2 * SP_DSL), c = i % (2 * SP_DSL);
-                const float v = red_sum(red, KS, Fp, 2 * SP_DSL + 4, f, c);
-                if (c < SP_DSL) xs[(3 + f) * SP_DSL + c] = v;
-                else zs[f * SP_DSL + c - SP_DSL] = silu_f(v);
-            }
+        gemm_run<NTF, ct_in, ks_d>(w_in, f_in, act_hi, act_lo, lda, red, warp, lane);
+        if (tid < 3 * SP_DSL) xs[tid] = halo_v;   // conv history = rows -3..-1
+        WFrag<GX::NPRE> w_x;
+        gemm_issue<ct_x, ks_c>(w_x, f_x, warp, lane);
+        __syncthreads();
+        SP_MARK(2);
+        for (int i = tid; i < F * 2 * SP_DSL; i += SP_THREADS) {
+            const int f = i / (2 * SP_DSL), c = i % (2 * SP_DSL);
+            const float v = red_sum(red, GI::KS, Fp, GI::LDR, f, c);
+            if (c < SP_DSL) xs[(3 + f) * SP_DSL + c] = v;
+            else zs[f * SP_DSL + c - SP_DSL] = silu_f(v);
         }
         cp_async_wait_all();
         __syncthreads();
@@ -410,17 +489,16 @@ __global__ void __launch_bounds__(SP_THREADS, 1) stream_push_kernel(const mtn_st
         SP_MARK(4);
 
         // x_proj over this CTA's 64 channels: partial [dt | B | C] rows, left in xd for the peers
-        {
-            const int KS = gemm_frag<NTF>(lf + (size_t(CL) * in_units + size_t(rank) * x_units) * 64, ct_x, ks_c, su_hi, su_lo, ldu,
-                                          red, warp, lane);
-            __syncthreads();
-            for (int i = tid; i < F * NXp; i += SP_THREADS) xd[i] = red_sum(red, KS, Fp, NXp + 4, i / NXp, i % NXp);
-        }
+        gemm_run<NTF, ct_x, ks_c>(w_x, f_x, su_hi, su_lo, ldu, red, warp, lane);
+        WFrag<GO::NPRE> w_o;
+        gemm_issue<ct_o, ks_c>(w_o, f_o, warp, lane);   // out_proj weights travel while the partials are summed and the scan runs
+        __syncthreads();
+        for (int i = tid; i < F * NXp; i += SP_THREADS) xd[i] = red_sum(red, GX::KS, Fp, GX::LDR, i / NXp, i % NXp);
         SP_MARK(5);
         cluster_sync_all();   // [B]
         SP_MARK(6);
         for (int i = tid; i < F * NXp / 4; i += SP_THREADS)
-            *reinterpret_cast<float4*>(dbl + 4 * i) = rank_sum4<CL>(xd + 4 * i);
+            *reinterpret_cast<float4*>(dbl + 4 * i) = rank_sum4<CL>(xd + 4 * i, rank);
         __syncthreads();
         SP_MARK(7);
 
@@ -443,7 +521,6 @@ __global__ void __launch_bounds__(SP_THREADS, 1) stream_push_kernel(const mtn_st
             const int c = tid >> 3, sp = tid & 7;
             const float A0 = s_A2[c * 16 + 2 * sp], A1 = s_A2[c * 16 + 2 * sp + 1];
             const float Dp = s_D[c];
-            float2 h = *reinterpret_cast<const float2*>(hst + c * 16 + 2 * sp);
             const float* bc = dbl + R + 2 * sp;
 #pragma unroll
             for (int f0 = 0; f0 < Fp; f0 += 8) {
@@ -465,16 +542,27 @@ __global__ void __launch_bounds__(SP_THREADS, 1) stream_push_kernel(const mtn_st
                             h.x = fmaf(ex2_approx(d[k] * A0), h.x, du * Bv[k].x);
                             h.y = fmaf(ex2_approx(d[k] * A1), h.y, du * Bv[k].y);
                         }
-                        float yp = fmaf(Cv[k].x, h.x, Cv[k].y * h.y);
-                        yp += __shfl_xor_sync(0xffffffffu, yp, 1);
-                        yp += __shfl_xor_sync(0xffffffffu, yp, 2);
-                        yp += __shfl_xor_sync(0xffffffffu, yp, 4);
-                        yv[k] = fmaf(Dp, u[k], yp);
+                        yv[k] = fmaf(Cv[k].x, h.x, Cv[k].y * h.y);
                     }
-                    // lane sp of the channel's eight finishes step f0 + sp
-                    float mine = yv[0];
+                    // reduce-scatter over the channel's eight lanes: 4 + 2 + 1 independent shuffles instead of 8 x 3 dependent
+                    // ones; lane sp ends up with the state sum of step f0 + sp
+                    float k4[4], k2[2];
+                    const bool b2 = sp & 4, b1 = sp & 2, b0 = sp & 1;
 #pragma unroll
-                    for (int k = 1; k < 8; ++k) mine = sp == k ? yv[k] : mine;
+                    for (int i = 0; i < 4; ++i) {
+                        const float recv = __shfl_xor_sync(0xffffffffu, b2 ? yv[i] : yv[i + 4], 4);
+                        k4[i] = (b2 ? yv[i + 4] : yv[i]) + recv;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const float recv = __shfl_xor_sync(0xffffffffu, b1 ? k4[i] : k4[i + 2], 2);
+                        k2[i] = (b1 ? k4[i + 2] : k4[i]) + recv;
+                    }
+                    const float recv = __shfl_xor_sync(0xffffffffu, b0 ? k2[0] : k2[1], 1);
+                    float um = u[0];
+#pragma unroll
+                    for (int k = 1; k < 8; ++k) um = sp == k ? u[k] : um;
+                    const float mine = fmaf(Dp, um, (b0 ? k2[1] : k2[0]) + recv);
                     if (f0 + sp < F) put_planes(su_hi, su_lo, (f0 + sp) * ldu + c, mine * zs[(f0 + sp) * SP_DSL + c]);
                 }
             }
@@ -482,17 +570,15 @@ __global__ void __launch_bounds__(SP_THREADS, 1) stream_push_kernel(const mtn_st
         }
         __syncthreads();
         SP_MARK(9);
+        if (layer + 1 < a.n_layers) prefetch_vectors(layer + 1);   // this layer's readers of the vector slices are done
 
         // out_proj over this CTA's 64 channels: partial h [F][D], left in plane 0 of red for the peers
-        {
-            const int KS = gemm_frag<NTF>(lf + (size_t(CL) * (in_units + x_units) + size_t(rank) * o_units) * 64, ct_o, ks_c, su_hi,
-                                          su_lo, ldu, red, warp, lane);
-            if (KS > 1) {
-                __syncthreads();
-                for (int i = tid; i < F * D; i += SP_THREADS) {
-                    const int f = i / D, c = i % D;
-                    red[f * (D + 4) + c] = red_sum(red, KS, Fp, D + 4, f, c);   // each element has one owner: in place
-                }
+        gemm_run<NTF, ct_o, ks_c>(w_o, f_o, su_hi, su_lo, ldu, red, warp, lane);
+        if constexpr (GO::KS > 1) {
+            __syncthreads();
+            for (int i = tid; i < F * D; i += SP_THREADS) {
+                const int f = i / D, c = i % D;
+                red[f * (D + 4) + c] = red_sum(red, GO::KS, Fp, GO::LDR, f, c);   // each element has one owner: in place
             }
         }
         SP_MARK(10);
@@ -500,7 +586,7 @@ __global__ void __launch_bounds__(SP_THREADS, 1) stream_push_kernel(const mtn_st
         SP_MARK(11);
         for (int i = tid; i < F * SP_CSL / 4; i += SP_THREADS) {
             const int f = i / (SP_CSL / 4), c = 4 * (i % (SP_CSL / 4));
-            const float4 v = rank_sum4<CL>(red + f * (D + 4) + rank * SP_CSL + c);
+            const float4 v = rank_sum4<CL>(red + f * (D + 4) + rank * SP_CSL + c, rank);
             float4 r = *reinterpret_cast<float4*>(res + f * SP_CSL + c);
             r.x += v.x; r.y += v.y; r.z += v.z; r.w += v.w;
             *reinterpret_cast<float4*>(res + f * SP_CSL + c) = r;
@@ -513,15 +599,22 @@ __global__ void __launch_bounds__(SP_THREADS, 1) stream_push_kernel(const mtn_st
     SP_MARK(0);
 
     // ------------------------------------------------------------------ norm_f -> mask conv + ReLU -> mask * mix_w
-    rmsnorm_rows<CL>(res, s_norm + (a.n_layers & 1) * D, F, a.eps_rms, act_hi, act_lo, lda, warp, lane);
+    const uint4* f_mask = reinterpret_cast<const uint4*>(a.mask_frag) + size_t(rank) * (SP_MSL / 16) * (D / 16) * 64;
+    WFrag<GemmShape<SP_MSL / 16, D / 16>::NPRE> w_mask;
+    {
+        NormRows<CL, (NTF + 1) / 2> nr;
+        nr.gather(res, F, warp, lane, rank);
+        gemm_issue<SP_MSL / 16, D / 16>(w_mask, f_mask, warp, lane);
+        nr.finish(s_norm + (a.n_layers & 1) * D, F, a.eps_rms, act_hi, act_lo, lda, warp, lane, rank);
+    }
     __syncthreads();
     {
-        const uint4* wf = reinterpret_cast<const uint4*>(a.mask_frag) + size_t(rank) * (SP_MSL / 16) * (D / 16) * 64;
-        const int KS = gemm_frag<NTF>(wf, SP_MSL / 16, D / 16, act_hi, act_lo, lda, red, warp, lane);
+        using G = GemmShape<SP_MSL / 16, D / 16>;
+        gemm_run<NTF, SP_MSL / 16, D / 16>(w_mask, f_mask, act_hi, act_lo, lda, red, warp, lane);
         __syncthreads();
         for (int i = tid; i < F * SP_MSL; i += SP_THREADS) {
             const int f = i / SP_MSL, c = i % SP_MSL;
-            us[i] = fmaxf(red_sum(red, KS, Fp, SP_MSL + 4, f, c), 0.f) * mixw[i];   // sep slice (train_wsj0mix.py:91-92)
+            us[i] = fmaxf(red_sum(red, G::KS, Fp, G::LDR, f, c), 0.f) * mixw[i];   // sep slice (train_wsj0mix.py:91-92)
         }
     }
     __syncthreads();
