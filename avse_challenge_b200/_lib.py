@@ -24,7 +24,7 @@ EXPORTS = [
     "mtn_dp_overadd_prelu_fwd", "mtn_bias_planes_fwd", "mtn_gate_planes_fwd",
     "mtn_decoder_fwd", "mtn_cln_fwd", "mtn_softmax_mask_fwd", "mtn_split_planes", "mtn_si_snr_pit_fwd", "mtn_si_snr_workspace_bytes", "mtn_si_snr_pit_n_fwd", "mtn_si_snr_workspace_bytes_n", "mtn_last_error_string", "mtn_abi_version",
     "mtn_sizeof_gemm_args", "mtn_sizeof_scan_args", "mtn_sizeof_gn_apply_args",
-    "mtn_stream_push_fwd", "mtn_sizeof_stream_push_args",
+    "mtn_stream_push_fwd", "mtn_sizeof_stream_push_args", "mtn_conv_xproj_fwd",
 ]
 
 
@@ -112,6 +112,8 @@ def load():
                                            c_void_p, c_int, c_int, c_int, c_int, c_void_p]
     lib.mtn_conv_silu_dir_fwd.argtypes = [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
                                           c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]
+    lib.mtn_conv_xproj_fwd.argtypes = [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int,
+                                       c_int, c_int, c_int, c_int, c_int, c_void_p]
     lib.mtn_decoder_stream_fwd.argtypes = [c_void_p] * 5 + [c_int] * 5 + [c_void_p]
     lib.mtn_scan_fwd.argtypes = [POINTER(ScanArgs), c_void_p]
     lib.mtn_fold_states_fwd.argtypes = [c_void_p] * 6 + [c_int] * 5 + [c_void_p]

@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmtn_b200.so")
-SOURCES = ["mtn_host.cu", "mtn_gemm.cu", "mtn_elem.cu", "mtn_scan.cu", "mtn_seq.cu", "mtn_score.cu", "mtn_dp.cu", "mtn_stream.cu"]
+SOURCES = ["mtn_host.cu", "mtn_gemm.cu", "mtn_elem.cu", "mtn_scan.cu", "mtn_seq.cu", "mtn_score.cu", "mtn_dp.cu", "mtn_stream.cu", "mtn_convx.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "--use_fast_math", *(["-DMTN_SCAN_ABLATIONS"] if os.environ.get("MTN_SCAN_ABLATIONS") else []), "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-Xptxas", "-v",

@@ -503,18 +503,20 @@ static int launch_gemm(const mtn_gemm_args* a, cudaStream_t stream) {
     return MTN_OK;
 }
 
-// CTA pairs (cta_group::2) for the mainloop-bound GEMMs: 256-wide N tiles, K >= 512 and at least one 256-row pair tile per
+// CTA pairs (cta_group::2) for the mainloop-bound GEMMs: 256-wide N tiles, K >= 1024 and at least one 256-row pair tile per
 // SM pair.  Measured on B200 (tools/gemm_bench.py --ab, profiles/r02/gemm_2cta_ab_*.jsonl; outputs bit-identical):
 // out_proj (K = 1024) 0.177 -> 0.156 ms = 94 % of the sustained bf16 tensor peak, L bf16 out_proj (K = 2048) 0.489 -> 0.445;
 // but in_proj (K = 256: four k-blocks per tile) 0.206 -> 0.227 and mask 0.195 -> 0.216 -- with so short a main loop the
-// accumulator hand-off between MMA and epilogue is paid per tile, and in a pair it crosses two SMs.  Hence the K rule.
+// accumulator hand-off between MMA and epilogue is paid per tile, and in a pair it crosses two SMs.  Hence the K rule; it
+// was K >= 512 at first, which also paired the L recipe's in_proj / bottleneck (K = 512, eight k-blocks): 0.636 -> 0.707 ms and
+// 0.175 -> 0.203 ms in bf16 mode (gemm_2cta_ab_L_bf16.jsonl), so the bar is sixteen k-blocks.
 // MTN_GEMM_2CTA = 0 / 1 / 2 in the environment: never / by this rule (default) / whenever the shape allows (A/B runs).
 static bool use_cta_pairs(const mtn_gemm_args* a, int bn) {
     if (bn != 256 || a->groups != 1) return false;
     int mode = 1;
     if (const char* v = getenv("MTN_GEMM_2CTA")) mode = atoi(v);
     if (mode == 0) return false;
-    if (mode == 1 && a->K < 512) return false;
+    if (mode == 1 && a->K < 1024) return false;
     const long pair_tiles = long((a->M + 2 * BM - 1) / (2 * BM)) * (a->N / bn);
     const long cap = a->max_ctas > 0 ? a->max_ctas : num_sms();
     return pair_tiles >= cap / 2;

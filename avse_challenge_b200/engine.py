@@ -155,6 +155,10 @@ class LayerPlan:
         self.tc_dt = hp.dt_rank >= 32 and mode == "fp32" and hp.bidirectional
         self.ndir = 2 if hp.bidirectional else 1
         self.dir_mask = 3 if hp.bidirectional else 1
+        # conv + x_proj as one kernel (mtn_conv_xproj_fwd: u is written once and never re-read by a GEMM) wherever that
+        # kernel applies: both directions, whole sequences (no halo rows: not the streaming / sequence-parallel chunks),
+        # plain x_proj epilogue.  Bit-identical to the two-kernel plan; `fuse_convx = False` keeps the latter.
+        self.fuse_convx = hp.bidirectional and not self.tc_dt and hp.d_inner % 64 == 0
 
     def _op(self, name, fn, *a, **k):
         """Launch one kernel; when a profiler is attached, bracket it with CUDA events on the launch stream."""
@@ -176,6 +180,14 @@ class LayerPlan:
         di, R, nd, M = hp.d_inner, hp.dt_rank, self.n_dbl, ws.M
         op = self._op
         ndir = self.ndir
+        # the fused kernel works on 128-frame tiles of one sequence: short sequences (DPMamba's inter-chunk model: 34 frames)
+        # would leave most of a tile empty
+        if self.fuse_convx and st is None and ws.L >= 0.75 * (-(-ws.L // 128) * 128):
+            op("conv_xproj", ops.conv_xproj, ws.xz, lw["conv_w"], lw["conv_b"], lw["w_x"], ws.batch, ws.L, di, P, nd, u=ws.u,
+               dbl=ws.dbl)
+            op("scan", ops.scan, ws.u, ws.dbl, ws.xz, di, lw["w_dt"], lw["dt_bias"], lw["A2"], lw["D"], ws.batch, ws.L, di, R,
+               y=ws.y, dir_mask=self.dir_mask)
+            return
         op("conv_silu", ops.conv_silu, ws.xz, lw["conv_w"], lw["conv_b"], ws.batch, ws.L, di, P, u=ws.u,
            halo_lo=None if st is None else st["halo"], dir_mask=self.dir_mask)
         if st is not None:   # new conv history = last 3 conv inputs (pure data movement; fp32 like the kernel's halo operand)
@@ -282,7 +294,8 @@ class SeparatorEngine(LayerPlan):
         self._graphs = LRUDict()
         self._ws = LRUDict(on_evict=lambda key, ws: self._graphs.pop(key, None))
         # enc, bottleneck, layers, (norm_f +) mask, decoder(2); fused: no norm kernels
-        self.launches_per_forward = (1 + 1 + hp.n_mamba * 5 + 1 + 2) if fuse_norm else (1 + 1 + hp.n_mamba * 6 + 2 + 2)
+        per_layer = (5 if fuse_norm else 6) - (1 if self.fuse_convx else 0)
+        self.launches_per_forward = (1 + 1 + hp.n_mamba * per_layer + 1 + 2) if fuse_norm else (1 + 1 + hp.n_mamba * per_layer + 2 + 2)
 
     # ------------------------------------------------------------------ building blocks
     def workspace(self, batch, T) -> Workspace:

@@ -145,6 +145,22 @@ def conv_silu(xz, conv_w, conv_b, batch, L, di, planes, u=None, halo_lo=None, ha
     return u
 
 
+def conv_xproj(xz, conv_w, conv_b, w_x, batch, L, di, planes, n_dbl, u=None, dbl=None):
+    """``conv_silu`` of both directions fused with the two-group x_proj GEMM (``mtn_conv_xproj_fwd``): xz [M, >= di] ->
+    (u planes [P, M, 2*di], dbl fp32 [M, 2*n_dbl]); ``w_x`` bf16 planes [P, 2*n_dbl, di].  Whole sequences only (no halos)."""
+    _req_cuda(xz, conv_w, conv_b, w_x, u, dbl)
+    M = batch * L
+    assert tuple(w_x.shape) == (planes, 2 * n_dbl, di) and w_x.is_contiguous(), tuple(w_x.shape)
+    if u is None:
+        u = torch.empty((planes, M, 2 * di), dtype=torch.bfloat16, device=xz.device)
+    if dbl is None:
+        dbl = torch.empty((M, 2 * n_dbl), dtype=torch.float32, device=xz.device)
+    check(_lib.load().mtn_conv_xproj_fwd(ptr(xz), xz.stride(0), int(xz.dtype == torch.bfloat16), ptr(conv_w), ptr(conv_b), ptr(u),
+                                         u.shape[1], ptr(w_x), ptr(dbl), dbl.stride(0), n_dbl, batch, L, di, planes, _stream()),
+          "mtn_conv_xproj_fwd")
+    return u, dbl
+
+
 def scan(u, dbl, z, z_col0, w_dt, dt_bias, A2, Dskip, batch, L, di, R, *, y=None, h_in=None, h_out=None, dir_mask=3,
          sum_delta=None, L_last=0, summary_only=False, dtp=None):
     """Both-direction selective scan; see ``mtn_scan_args`` in include/mtn_b200.h.

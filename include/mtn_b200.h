@@ -171,6 +171,16 @@ int mtn_conv_silu_dir_fwd(const void* xz, int ldxz, int xz_bf16, const float* co
                           void* u_planes, int u_rows, const float* halo_lo, const float* halo_hi, int batch, int L,
                           int di, int planes, int dir_mask, mtn_stream_t stream);
 
+/* conv_silu (both directions) fused with the x_proj contraction (ABI >= 7): one pass over xs writes u (for the scan) and
+ * dbl = [dt | B | C] of both directions; u is never re-read by a GEMM.  Bit-identical to mtn_conv_silu_fwd followed by
+ * mtn_gemm_fwd(groups = 2) on the same inputs.  Replaces causal_conv1d_fwd x 2 + F.linear(x_proj) x 2
+ * (modules/mamba/selective_scan_interface.py:182-186, modules/mamba/bimamba.py:237).  wx_planes: bf16 [planes][2*n_dbl][di]
+ * (rows dt | B | C | zero pad per direction, as for mtn_gemm_fwd); dbl: fp32 [batch*L][ld_dbl], direction d at columns
+ * d*n_dbl; di % 64 == 0; n_dbl 48 or 64; no halo rows (whole sequences only). */
+int mtn_conv_xproj_fwd(const void* xz, int ldxz, int xz_bf16, const float* conv_w, const float* conv_b, void* u_planes,
+                       int u_rows, const void* wx_planes, float* dbl, int ld_dbl, int n_dbl, int batch, int L, int di,
+                       int planes, mtn_stream_t stream);
+
 int mtn_scan_fwd(const mtn_scan_args* args, mtn_stream_t stream);
 
 /* Chunked scan, step 2 of 3 (summary pass -> fold -> seeded pass): compose the per-chunk operators

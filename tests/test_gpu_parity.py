@@ -881,3 +881,45 @@ def test_degenerate_inputs_stay_finite_and_match_oracle(scale):
     dest = DPSeparatorEngine(dhp, dsds, device=DEV, mode="fp32", use_graph=False)(mix.to(DEV)).cpu()
     assert torch.isfinite(dest).all()
     assert (dest - dref).abs().max().item() <= 1e-3 * max(dref.pow(2).mean().sqrt().item(), 1e-12) + 1e-12
+
+
+@pytest.mark.parametrize("name,B,L,mode", [("S", 3, 1000, "fp32"), ("S", 2, 257, "bf16"), ("tiny", 4, 130, "fp32"),
+                                             ("L", 2, 500, "bf16"), ("XS", 2, 3999, "fp32")])
+def test_conv_xproj_fused_is_bit_identical_to_conv_then_gemm(name, B, L, mode):
+    """mtn_conv_xproj_fwd (conv + SiLU of both directions feeding tcgen05 x_proj MMAs from shared memory) against the
+    two-kernel plan it replaces (selective_scan_interface.py:182-186): same fmaf nesting, same MMA order -> equal bits,
+    including ragged last tiles (L % 128 != 0) and sequence boundaries inside the batch."""
+    hp = CONFIGS[name]
+    di, R = hp.d_inner, hp.dt_rank
+    nd = ops.n_dbl_for(R)
+    P = 2 if mode == "fp32" else 1
+    g = torch.Generator().manual_seed(17)
+    M = B * L
+    xz = torch.randn(M, 2 * di, generator=g).to(DEV)
+    if P == 1:
+        xz = xz.to(torch.bfloat16)
+    conv_w = (torch.randn(2, di, 4, generator=g) * 0.5).to(DEV)
+    conv_b = (torch.randn(2, di, generator=g) * 0.1).to(DEV)
+    wx = torch.zeros(2 * nd, di)
+    for d in range(2):
+        wx[d * nd: d * nd + R + 32] = torch.randn(R + 32, di, generator=g) / di ** 0.5
+    w_x = ops.split_planes(wx.to(DEV), P)
+    u_ref = ops.conv_silu(xz, conv_w, conv_b, B, L, di, P)
+    dbl_ref = ops.gemm(u_ref, w_x, M, nd, di, groups=2, out_group_stride=nd)
+    u = torch.full_like(u_ref, 3.0)
+    dbl = torch.full_like(dbl_ref, -7.0)
+    ops.conv_xproj(xz, conv_w, conv_b, w_x, B, L, di, P, nd, u=u, dbl=dbl)
+    torch.cuda.synchronize()
+    assert torch.equal(u, u_ref)
+    assert torch.equal(dbl, dbl_ref), (dbl - dbl_ref).abs().max().item()
+
+
+def test_engine_fused_conv_xproj_plan_equals_two_kernel_plan():
+    hp = CONFIGS["S"]
+    sds = init_state_dicts(hp, 1234)
+    mix, _ = synth_mixture(4, 8000, seed=3)
+    a = SeparatorEngine(hp, sds, device=DEV, mode="fp32", use_graph=False, small_batch_plan=False)
+    b = SeparatorEngine(hp, sds, device=DEV, mode="fp32", use_graph=False, small_batch_plan=False)
+    assert a.fuse_convx
+    b.fuse_convx = False
+    assert torch.equal(a(mix.to(DEV)), b(mix.to(DEV)))
