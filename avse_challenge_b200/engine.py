@@ -155,10 +155,14 @@ class LayerPlan:
         self.tc_dt = hp.dt_rank >= 32 and mode == "fp32" and hp.bidirectional
         self.ndir = 2 if hp.bidirectional else 1
         self.dir_mask = 3 if hp.bidirectional else 1
-        # conv + x_proj as one kernel (mtn_conv_xproj_fwd: u is written once and never re-read by a GEMM) wherever that
-        # kernel applies: both directions, whole sequences (no halo rows: not the streaming / sequence-parallel chunks),
-        # plain x_proj epilogue.  Bit-identical to the two-kernel plan; `fuse_convx = False` keeps the latter.
-        self.fuse_convx = hp.bidirectional and not self.tc_dt and hp.d_inner % 64 == 0
+        # conv + x_proj as one kernel (mtn_conv_xproj_fwd: u is written once and never re-read by a GEMM): built, bit-identical
+        # to the two-kernel plan -- and measured SLOWER on B200 (tools/convx_bench.py, profiles/r02/convx_*.json: S fp32 0.323
+        # against 0.267 ms per layer, L bf16 1.03 against 0.60): its eight conv warps per SM (two per sub-partition, 168
+        # registers) cannot hide the conv's load / MUFU latencies the way the full-occupancy conv kernel does, so the saved
+        # 4 KB / token of HBM reads are paid back in issue stalls.  Off by default; `engine.fuse_convx = True` selects it
+        # (whole bidirectional sequences only: no halo rows, plain x_proj epilogue).
+        self.can_fuse_convx = hp.bidirectional and not self.tc_dt and hp.d_inner % 64 == 0
+        self.fuse_convx = False
 
     def _op(self, name, fn, *a, **k):
         """Launch one kernel; when a profiler is attached, bracket it with CUDA events on the launch stream."""
@@ -182,7 +186,7 @@ class LayerPlan:
         ndir = self.ndir
         # the fused kernel works on 128-frame tiles of one sequence: short sequences (DPMamba's inter-chunk model: 34 frames)
         # would leave most of a tile empty
-        if self.fuse_convx and st is None and ws.L >= 0.75 * (-(-ws.L // 128) * 128):
+        if self.fuse_convx and self.can_fuse_convx and st is None and ws.L >= 0.75 * (-(-ws.L // 128) * 128):
             op("conv_xproj", ops.conv_xproj, ws.xz, lw["conv_w"], lw["conv_b"], lw["w_x"], ws.batch, ws.L, di, P, nd, u=ws.u,
                dbl=ws.dbl)
             op("scan", ops.scan, ws.u, ws.dbl, ws.xz, di, lw["w_dt"], lw["dt_bias"], lw["A2"], lw["D"], ws.batch, ws.L, di, R,
@@ -294,7 +298,7 @@ class SeparatorEngine(LayerPlan):
         self._graphs = LRUDict()
         self._ws = LRUDict(on_evict=lambda key, ws: self._graphs.pop(key, None))
         # enc, bottleneck, layers, (norm_f +) mask, decoder(2); fused: no norm kernels
-        per_layer = (5 if fuse_norm else 6) - (1 if self.fuse_convx else 0)
+        per_layer = 5 if fuse_norm else 6
         self.launches_per_forward = (1 + 1 + hp.n_mamba * per_layer + 1 + 2) if fuse_norm else (1 + 1 + hp.n_mamba * per_layer + 2 + 2)
 
     # ------------------------------------------------------------------ building blocks
