@@ -91,7 +91,8 @@ class StreamingSeparator:
             # one cluster-kernel launch: it reads the chunk and the carried samples in place and updates every cache
             if chunk.stride(1) != 1:
                 chunk = chunk.contiguous()
-            est = self._fused.run(chunk, self.in_tail, not self.started, self._halo, self._h, self.state["ola_tail"])
+            with torch.cuda.device(self.eng.device):   # launches go to the engine's device, whatever the caller has current
+                est = self._fused.run(chunk, self.in_tail, not self.started, self._halo, self._h, self.state["ola_tail"])
             self.started = True
             self.samples_in += n
             self.samples_out += 8 * L
