@@ -427,6 +427,8 @@ __global__ void __launch_bounds__(SP_THREADS, 1) stream_push_kernel(const mtn_st
         cp_async_commit();
     };
     prefetch_vectors(0);
+    float2 h_prev = make_float2(0.f, 0.f);
+    float* hst_prev = nullptr;
     SP_MARK(0);
     for (int layer = 0; layer < a.n_layers; ++layer) {
         tl_row = 1 + layer;
@@ -444,8 +446,6 @@ __global__ void __launch_bounds__(SP_THREADS, 1) stream_push_kernel(const mtn_st
         // this thread's (channel, state pair), the conv history), then the norm itself.
         NormRows<CL, (NTF + 1) / 2> nr;
         nr.gather(res, F, warp, lane, rank);
-        WFrag<GI::NPRE> w_in;
-        gemm_issue<ct_in, ks_d>(w_in, f_in, warp, lane);
         float2 h;
         {
             const float* hp = hst + (tid >> 3) * 16 + 2 * (tid & 7);
@@ -453,6 +453,11 @@ __global__ void __launch_bounds__(SP_THREADS, 1) stream_push_kernel(const mtn_st
         }
         float halo_v = 0.f;
         if (tid < 3 * SP_DSL) asm volatile("ld.global.f32 %0, [%1];" : "=f"(halo_v) : "l"(halo + (tid / SP_DSL) * di + tid % SP_DSL));
+        // the previous block's final SSM state goes out here, a whole phase away from the next cluster barrier: a global store
+        // still in flight at `barrier.cluster.arrive.release` makes every thread sit in its memory barrier
+        if (layer > 0) *reinterpret_cast<float2*>(hst_prev + (tid >> 3) * 16 + 2 * (tid & 7)) = h_prev;
+        WFrag<GI::NPRE> w_in;
+        gemm_issue<ct_in, ks_d>(w_in, f_in, warp, lane);
         nr.finish(s_norm + (layer & 1) * D, F, a.eps_rms, act_hi, act_lo, lda, warp, lane, rank);
         __syncthreads();
         SP_MARK(1);
@@ -464,27 +469,34 @@ __global__ void __launch_bounds__(SP_THREADS, 1) stream_push_kernel(const mtn_st
         gemm_issue<ct_x, ks_c>(w_x, f_x, warp, lane);
         __syncthreads();
         SP_MARK(2);
-        for (int i = tid; i < F * 2 * SP_DSL; i += SP_THREADS) {
-            const int f = i / (2 * SP_DSL), c = i % (2 * SP_DSL);
-            const float v = red_sum(red, GI::KS, Fp, GI::LDR, f, c);
-            if (c < SP_DSL) xs[(3 + f) * SP_DSL + c] = v;
-            else zs[f * SP_DSL + c - SP_DSL] = silu_f(v);
+#pragma unroll
+        for (int it = 0; it < Fp * 2 * SP_DSL / SP_THREADS; ++it) {   // a thread's iterations are independent: unrolled for ILP
+            const int i = tid + it * SP_THREADS;
+            if (i < F * 2 * SP_DSL) {
+                const int f = i / (2 * SP_DSL), c = i % (2 * SP_DSL);
+                const float v = red_sum(red, GI::KS, Fp, GI::LDR, f, c);
+                if (c < SP_DSL) xs[(3 + f) * SP_DSL + c] = v;
+                else zs[f * SP_DSL + c - SP_DSL] = silu_f(v);
+            }
         }
         cp_async_wait_all();
         __syncthreads();
         SP_MARK(3);
 
         // causal depthwise conv (width 4) + bias + SiLU (ssi.py:182); new history = last three conv inputs
-        for (int i = tid; i < F * SP_DSL; i += SP_THREADS) {
-            const int f = i / SP_DSL, c = i % SP_DSL;
-            const float4 w = *reinterpret_cast<const float4*>(s_conv_w + 4 * c);
-            const float* x = xs + f * SP_DSL + c;
-            const float pre = fmaf(w.x, x[0], fmaf(w.y, x[SP_DSL], fmaf(w.z, x[2 * SP_DSL], fmaf(w.w, x[3 * SP_DSL], s_conv_b[c]))));
-            const float u = silu_f(pre);
-            us[i] = u;
-            put_planes(su_hi, su_lo, f * ldu + c, u);
+#pragma unroll
+        for (int it = 0; it < Fp * SP_DSL / SP_THREADS; ++it) {
+            const int i = tid + it * SP_THREADS;
+            if (i < F * SP_DSL) {
+                const int f = i / SP_DSL, c = i % SP_DSL;
+                const float4 w = *reinterpret_cast<const float4*>(s_conv_w + 4 * c);
+                const float* x = xs + f * SP_DSL + c;
+                const float pre = fmaf(w.x, x[0], fmaf(w.y, x[SP_DSL], fmaf(w.z, x[2 * SP_DSL], fmaf(w.w, x[3 * SP_DSL], s_conv_b[c]))));
+                const float u = silu_f(pre);
+                us[i] = u;
+                put_planes(su_hi, su_lo, f * ldu + c, u);
+            }
         }
-        if (tid < 3 * SP_DSL) halo[(tid / SP_DSL) * di + tid % SP_DSL] = xs[(F + tid / SP_DSL) * SP_DSL + tid % SP_DSL];
         __syncthreads();
         SP_MARK(4);
 
@@ -497,18 +509,28 @@ __global__ void __launch_bounds__(SP_THREADS, 1) stream_push_kernel(const mtn_st
         SP_MARK(5);
         cluster_sync_all();   // [B]
         SP_MARK(6);
+        // new conv history = last three conv inputs (xs is not touched again before the next block's in_proj epilogue); stored
+        // here, right behind a barrier, for the reason given at the state store above
+        if (tid < 3 * SP_DSL) halo[(tid / SP_DSL) * di + tid % SP_DSL] = xs[(F + tid / SP_DSL) * SP_DSL + tid % SP_DSL];
         for (int i = tid; i < F * NXp / 4; i += SP_THREADS)
             *reinterpret_cast<float4*>(dbl + 4 * i) = rank_sum4<CL>(xd + 4 * i, rank);
         __syncthreads();
         SP_MARK(7);
 
         // dt_proj + softplus (ssi.py:187, delta_softplus of :218)
-        for (int i = tid; i < F * SP_DSL; i += SP_THREADS) {
-            const int f = i / SP_DSL, c = i % SP_DSL;
-            float acc = s_dt_bias[c];
 #pragma unroll
-            for (int r = 0; r < R; ++r) acc = fmaf(dbl[f * NXp + r], s_w_dt[r * SP_DSL + c], acc);
-            dl[i] = softplus_f(acc);
+        for (int it = 0; it < Fp * SP_DSL / SP_THREADS; ++it) {
+            const int i = tid + it * SP_THREADS;
+            if (i < F * SP_DSL) {
+                const int f = i / SP_DSL, c = i % SP_DSL;
+                float acc0 = s_dt_bias[c], acc1 = 0.f;   // two chains halve the dependent-FMA depth
+#pragma unroll
+                for (int r = 0; r < R; r += 2) {
+                    acc0 = fmaf(dbl[f * NXp + r], s_w_dt[r * SP_DSL + c], acc0);
+                    acc1 = fmaf(dbl[f * NXp + r + 1], s_w_dt[(r + 1) * SP_DSL + c], acc1);
+                }
+                dl[i] = softplus_f(acc0 + acc1);
+            }
         }
         __syncthreads();
         SP_MARK(8);
@@ -566,7 +588,8 @@ __global__ void __launch_bounds__(SP_THREADS, 1) stream_push_kernel(const mtn_st
                     if (f0 + sp < F) put_planes(su_hi, su_lo, (f0 + sp) * ldu + c, mine * zs[(f0 + sp) * SP_DSL + c]);
                 }
             }
-            *reinterpret_cast<float2*>(hst + c * 16 + 2 * sp) = h;
+            h_prev = h;
+            hst_prev = hst;
         }
         __syncthreads();
         SP_MARK(9);
@@ -595,6 +618,7 @@ __global__ void __launch_bounds__(SP_THREADS, 1) stream_push_kernel(const mtn_st
         cluster_sync_all();   // [A] of the next block / of norm_f
         SP_MARK(13);
     }
+    *reinterpret_cast<float2*>(hst_prev + (tid >> 3) * 16 + 2 * (tid & 7)) = h_prev;   // last block's final state
     tl_row = 1 + a.n_layers;
     SP_MARK(0);
 
