@@ -67,7 +67,8 @@ class StreamPushArgs(Structure):
         ("h_layer_stride", c_size_t), ("layer_vec_stride", c_size_t), ("layer_frag_stride", c_size_t),
         ("B", c_int), ("F", c_int), ("N", c_int), ("D", c_int), ("di", c_int), ("R", c_int), ("n_spk", c_int),
         ("n_layers", c_int), ("ld_mix", c_int), ("first", c_int), ("eps_cln", c_float), ("eps_rms", c_float),
-        ("timeline", c_void_p),
+        ("timeline", c_void_p), ("halo_stream_stride", c_size_t), ("halo_layer_stride", c_size_t),
+        ("halo_rows", c_int), ("stack_x", c_void_p), ("stack_out", c_void_p),
     ]
 
 

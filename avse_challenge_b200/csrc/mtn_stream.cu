@@ -259,6 +259,21 @@ struct NormRows {
             }
         }
     }
+    // stack-only mode: the normalised rows ARE the result; every CTA has all of them, rank r stores its 32 columns
+    __device__ __forceinline__ void finish_out(const float* g, int F, float eps, float* out, int warp, int lane, int rank) {
+        constexpr int D = 32 * CL;
+#pragma unroll
+        for (int i = 0; i < ROWS; ++i) {
+            const int f = warp + i * SP_WARPS;
+            if (f < F) {
+                float sq = 0.f;
+#pragma unroll
+                for (int r = 0; r < CL; ++r) sq = fmaf(v[i][r], v[i][r], sq);
+                const float rstd = rsqrtf(warp_sum(sq) * (1.0f / D) + eps);
+                out[size_t(f) * D + 32 * rank + lane] = v[i][0] * rstd * g[32 * rank + lane];   // r = 0 is this rank's own slice
+            }
+        }
+    }
     __device__ __forceinline__ void finish(const float* g, int F, float eps, __nv_bfloat16* ahi, __nv_bfloat16* alo, int lda, int warp,
                                            int lane, int rank) {
         constexpr int D = 32 * CL;
@@ -321,6 +336,12 @@ __global__ void __launch_bounds__(SP_THREADS, 1) stream_push_kernel(const mtn_st
     cp_async_commit();
     __syncthreads();
 
+    const bool stack_only = a.stack_x != nullptr;   // MambaBlocksSequential.forward(x, inference_params): no encoder / mask / decoder
+    if (stack_only) {
+        // the stack's input rows are the first residual (bimamba.py:446 with residual None): this CTA keeps its 32 columns
+        const float* xb = a.stack_x + size_t(b) * F * D + rank * SP_CSL;
+        for (int i = tid; i < F * SP_CSL; i += SP_THREADS) res[i] = __ldg(xb + size_t(i / SP_CSL) * D + i % SP_CSL);
+    } else {
     // bottleneck weights: requested now, used after the encoder
     WFrag<GemmShape<SP_CSL / 16, N / 16>::NPRE> w_bot;
     gemm_issue<SP_CSL / 16, N / 16>(w_bot, reinterpret_cast<const uint4*>(a.bot_frag) + size_t(rank) * (SP_CSL / 16) * (N / 16) * 64, warp, lane);
@@ -379,6 +400,7 @@ __global__ void __launch_bounds__(SP_THREADS, 1) stream_push_kernel(const mtn_st
         __syncthreads();
         for (int i = tid; i < F * SP_CSL; i += SP_THREADS) res[i] = red_sum(red, G::KS, Fp, G::LDR, i / SP_CSL, i % SP_CSL);
     }
+    }   // !stack_only
     cp_async_wait_all();
     cluster_sync_all();   // [A]
 
@@ -438,7 +460,7 @@ __global__ void __launch_bounds__(SP_THREADS, 1) stream_push_kernel(const mtn_st
         const uint4* f_in = lf + size_t(rank) * in_units * 64;
         const uint4* f_x = lf + (size_t(CL) * in_units + size_t(rank) * x_units) * 64;
         const uint4* f_o = lf + (size_t(CL) * (in_units + x_units) + size_t(rank) * o_units) * 64;
-        float* halo = a.halo + (size_t(layer) * a.B + b) * 3 * di + ch0;
+        float* halo = a.halo + size_t(layer) * a.halo_layer_stride + size_t(b) * a.halo_stream_stride + ch0;
         float* hst = a.h + size_t(layer) * a.h_layer_stride + (size_t(b) * di + ch0) * 16;
 
         // Add -> RMSNorm (bimamba.py:446-447), all rows in every CTA.  Order of the requests: the peers' residual slices, then
@@ -452,7 +474,9 @@ __global__ void __launch_bounds__(SP_THREADS, 1) stream_push_kernel(const mtn_st
             asm volatile("ld.global.v2.f32 {%0,%1}, [%2];" : "=f"(h.x), "=f"(h.y) : "l"(hp));
         }
         float halo_v = 0.f;
-        if (tid < 3 * SP_DSL) asm volatile("ld.global.f32 %0, [%1];" : "=f"(halo_v) : "l"(halo + (tid / SP_DSL) * di + tid % SP_DSL));
+        // a.halo_rows = 4: the buffer is the reference's 4-wide conv_state (row 0 = the oldest input, never read: bimamba.py:274-277)
+        if (tid < 3 * SP_DSL)
+            asm volatile("ld.global.f32 %0, [%1];" : "=f"(halo_v) : "l"(halo + (a.halo_rows - 3 + tid / SP_DSL) * di + tid % SP_DSL));
         // the previous block's final SSM state goes out here, a whole phase away from the next cluster barrier: a global store
         // still in flight at `barrier.cluster.arrive.release` makes every thread sit in its memory barrier
         if (layer > 0) *reinterpret_cast<float2*>(hst_prev + (tid >> 3) * 16 + 2 * (tid & 7)) = h_prev;
@@ -511,7 +535,8 @@ __global__ void __launch_bounds__(SP_THREADS, 1) stream_push_kernel(const mtn_st
         SP_MARK(6);
         // new conv history = last three conv inputs (xs is not touched again before the next block's in_proj epilogue); stored
         // here, right behind a barrier, for the reason given at the state store above
-        if (tid < 3 * SP_DSL) halo[(tid / SP_DSL) * di + tid % SP_DSL] = xs[(F + tid / SP_DSL) * SP_DSL + tid % SP_DSL];
+        if (tid < a.halo_rows * SP_DSL)
+            halo[(tid / SP_DSL) * di + tid % SP_DSL] = xs[(F + 3 - a.halo_rows + tid / SP_DSL) * SP_DSL + tid % SP_DSL];
         for (int i = tid; i < F * NXp / 4; i += SP_THREADS)
             *reinterpret_cast<float4*>(dbl + 4 * i) = rank_sum4<CL>(xd + 4 * i, rank);
         __syncthreads();
@@ -622,6 +647,13 @@ __global__ void __launch_bounds__(SP_THREADS, 1) stream_push_kernel(const mtn_st
     tl_row = 1 + a.n_layers;
     SP_MARK(0);
 
+    if (stack_only) {   // norm_f (modules/mamba_blocks.py:196-197) is the output
+        NormRows<CL, (NTF + 1) / 2> nr;
+        nr.gather(res, F, warp, lane, rank);
+        nr.finish_out(s_norm + (a.n_layers & 1) * D, F, a.eps_rms, a.stack_out + size_t(b) * F * D, warp, lane, rank);
+        cluster_sync_all();   // peers keep their residual slices alive until every CTA has gathered them
+        return;
+    }
     // ------------------------------------------------------------------ norm_f -> mask conv + ReLU -> mask * mix_w
     const uint4* f_mask = reinterpret_cast<const uint4*>(a.mask_frag) + size_t(rank) * (SP_MSL / 16) * (D / 16) * 64;
     WFrag<GemmShape<SP_MSL / 16, D / 16>::NPRE> w_mask;
@@ -694,13 +726,17 @@ extern "C" size_t mtn_sizeof_stream_push_args(void) { return sizeof(mtn_stream_p
 extern "C" int mtn_stream_push_fwd(const mtn_stream_push_args* args, mtn_stream_t stream) {
     MTN_REQUIRE(args, "stream_push: null args");
     const mtn_stream_push_args& a = *args;
-    MTN_REQUIRE(a.mix && a.in_tail && a.est && a.halo && a.h && a.ola_tail && a.head && a.bot_frag && a.mask_frag &&
-                    a.layer_vec && a.layer_frag, "stream_push: null pointer");
+    MTN_REQUIRE(a.halo && a.h && a.head && a.layer_vec && a.layer_frag, "stream_push: null pointer");
+    if (a.stack_x) MTN_REQUIRE(a.stack_out, "stream_push: stack_x without stack_out");
+    else MTN_REQUIRE(a.mix && a.in_tail && a.est && a.ola_tail && a.bot_frag && a.mask_frag, "stream_push: null pointer");
+    MTN_REQUIRE(a.halo_rows == 3 || a.halo_rows == 4, "stream_push: halo_rows=%d (3, or 4 = the reference's conv_state)", a.halo_rows);
+    MTN_REQUIRE(a.halo_stream_stride >= size_t(a.halo_rows) * size_t(a.di) && a.halo_layer_stride >= a.halo_stream_stride * a.B,
+                "stream_push: halo strides (floats): stream >= 3*di, layer >= B*stream");
     MTN_REQUIRE(a.B >= 1 && a.F >= 1 && a.F <= 32, "stream_push: B=%d F=%d (1 <= F <= 32 frames per push)", a.B, a.F);
     MTN_REQUIRE(a.N == a.D && a.di == 2 * a.D && a.n_spk == 2, "stream_push: needs enc_dim == d_model, expand 2, 2 speakers");
     MTN_REQUIRE(a.D == 64 || a.D == 128 || a.D == 256 || a.D == 512, "stream_push: d_model=%d (64, 128, 256 or 512)", a.D);
     MTN_REQUIRE(a.n_layers >= 1, "stream_push: layers=%d", a.n_layers);
-    MTN_REQUIRE(a.ld_mix >= 8 * a.F + (a.first ? 8 : 0), "stream_push: ld_mix=%d shorter than the chunk", a.ld_mix);
+    MTN_REQUIRE(a.stack_x || a.ld_mix >= 8 * a.F + (a.first ? 8 : 0), "stream_push: ld_mix=%d shorter than the chunk", a.ld_mix);
     MTN_REQUIRE(a.layer_vec_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(a.layer_vec) & 15) == 0 &&
                     (reinterpret_cast<uintptr_t>(a.layer_frag) & 15) == 0 && a.layer_frag_stride % 16 == 0 &&
                     (reinterpret_cast<uintptr_t>(a.head) & 15) == 0,

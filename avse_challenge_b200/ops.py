@@ -228,25 +228,36 @@ def decoder(sep, w_dec, batch, T, L, N, n_spk=2, est=None, frames=None, tail=Non
 
 
 def stream_push(mix, in_tail, est, halo, h, ola_tail, head, bot_frag, mask_frag, layer_vec, layer_frag, *, B, F, N, D,
-                di, R, n_spk, n_layers, first, eps_cln=1e-8, eps_rms=1e-5, timeline=None):
+                di, R, n_spk, n_layers, first, eps_cln=1e-8, eps_rms=1e-5, timeline=None, halo_strides=None, halo_rows=3,
+                stack_x=None, stack_out=None):
     """One streaming chunk of ``F <= 32`` frames per stream through the whole causal separator in one launch
-    (``mtn_stream_push_fwd``; weight layouts in include/mtn_b200.h, packer in stream_fused.py)."""
-    _req_cuda(mix, in_tail, est, halo, h, ola_tail, head, bot_frag, mask_frag, layer_vec, layer_frag, timeline)
-    assert mix.dtype == torch.float32 and mix.stride(1) == 1 and est.is_contiguous() and tuple(est.shape) == (B, 8 * F, n_spk)
-    assert mix.shape[1] == 8 * F + (8 if first else 0) and in_tail.is_contiguous() and tuple(in_tail.shape) == (B, 8)
-    assert timeline is None or (timeline.dtype == torch.int64 and timeline.numel() >= (n_layers + 2) * 16)
-    assert halo.is_contiguous() and tuple(halo.shape) == (n_layers, B, 3, di)
+    (``mtn_stream_push_fwd``; weight layouts in include/mtn_b200.h, packer in stream_fused.py).  ``stack_x`` / ``stack_out``
+    (fp32 [B, F, D]): stack-only mode = ``MambaBlocksSequential.forward(x, inference_params)``; mix / est / tails are unused.
+    ``halo_strides`` = (stream, layer) strides of ``halo`` in floats when it is not a dense [n_layers, B, 3, di] tensor."""
+    _req_cuda(mix, in_tail, est, halo, h, ola_tail, head, bot_frag, mask_frag, layer_vec, layer_frag, timeline, stack_x, stack_out)
+    if stack_x is None:
+        assert mix.dtype == torch.float32 and mix.stride(1) == 1 and est.is_contiguous() and tuple(est.shape) == (B, 8 * F, n_spk)
+        assert mix.shape[1] == 8 * F + (8 if first else 0) and in_tail.is_contiguous() and tuple(in_tail.shape) == (B, 8)
+        assert ola_tail.is_contiguous() and tuple(ola_tail.shape) == (B, n_spk, 8)
+    else:
+        assert stack_x.dtype == torch.float32 and stack_x.is_contiguous() and tuple(stack_x.shape) == (B, F, D)
+        assert stack_out.dtype == torch.float32 and stack_out.is_contiguous() and tuple(stack_out.shape) == (B, F, D)
+    if halo_strides is None:
+        assert halo.is_contiguous() and tuple(halo.shape) == (n_layers, B, 3, di)
+        halo_strides = (3 * di, B * 3 * di)
     assert h.is_contiguous() and h.shape[0] == n_layers and tuple(h.shape[-3:]) == (B, di, 16)
-    assert ola_tail.is_contiguous() and tuple(ola_tail.shape) == (B, n_spk, 8)
+    assert timeline is None or (timeline.dtype == torch.int64 and timeline.numel() >= (n_layers + 2) * 16)
     assert layer_vec.is_contiguous() and layer_frag.is_contiguous()
-    args = StreamPushArgs(mix=ptr(mix), in_tail=ptr(in_tail), first=int(bool(first)), timeline=ptr(timeline), est=ptr(est), halo=ptr(halo), h=ptr(h), ola_tail=ptr(ola_tail), head=ptr(head),
+    args = StreamPushArgs(mix=ptr(mix), in_tail=ptr(in_tail), first=int(bool(first)), timeline=ptr(timeline), est=ptr(est),
+                          halo=ptr(halo), h=ptr(h), ola_tail=ptr(ola_tail), head=ptr(head),
                           bot_frag=ptr(bot_frag), mask_frag=ptr(mask_frag), layer_vec=ptr(layer_vec),
                           layer_frag=ptr(layer_frag), h_layer_stride=h.stride(0),
                           layer_vec_stride=layer_vec.stride(0), layer_frag_stride=layer_frag.stride(0) * layer_frag.element_size(),
-                          B=B, F=F, N=N, D=D, di=di, R=R, n_spk=n_spk, n_layers=n_layers, ld_mix=mix.stride(0),
-                          eps_cln=eps_cln, eps_rms=eps_rms)
+                          B=B, F=F, N=N, D=D, di=di, R=R, n_spk=n_spk, n_layers=n_layers, ld_mix=(mix.stride(0) if mix is not None else 0),
+                          eps_cln=eps_cln, eps_rms=eps_rms, halo_stream_stride=halo_strides[0], halo_layer_stride=halo_strides[1], halo_rows=halo_rows,
+                          stack_x=ptr(stack_x), stack_out=ptr(stack_out))
     check(_lib.load().mtn_stream_push_fwd(args, _stream()), "mtn_stream_push_fwd")
-    return est
+    return est if stack_x is None else stack_out
 
 
 # ---------------------------------------------------------------------------------------------------- DPMamba glue

@@ -41,6 +41,57 @@ def pack_fragments(W: torch.Tensor, rows: torch.Tensor, ks: torch.Tensor) -> tor
     return torch.stack([frag(hi), frag(lo)], dim=2).contiguous()
 
 
+def _pack_layers(layers, hp: HParams, CL: int, dev):
+    """Per layer: the fp32 vector blob and the fragment blob (in_proj | x_proj | out_proj slabs per cluster rank) of
+    ``mtn_stream_push_args`` from ``engine.pack_layer`` dicts."""
+    D, di = hp.d_model, hp.d_inner
+    f32 = lambda planes: planes.float().sum(dim=0)           # hi + lo: exact, re-splits to the same planes
+    ar = lambda a, b: torch.arange(a, b, device=dev)
+    vecs, frags = [], []
+    for lw in layers:
+        w_in, w_x = f32(lw["w_in"]), f32(lw["w_x"])       # [2di, D], [n_dbl, di] (rows dt | B | C | zero pad)
+        w_out = 0.5 * f32(lw["w_out"])                    # the batch plan packs 2 * W_out for causal stacks
+        assert w_x.shape[0] % 16 == 0
+        vecs.append(torch.cat([lw["norm"], lw["conv_w"][0].reshape(-1), lw["conv_b"][0], lw["w_dt"][0].t().reshape(-1),
+                               lw["dt_bias"][0], lw["A2"][0].reshape(-1), lw["D"][0]]))
+        f_in = [pack_fragments(w_in, torch.cat([ar(64 * r, 64 * r + 64), ar(di + 64 * r, di + 64 * r + 64)]), ar(0, D))
+                for r in range(CL)]
+        f_x = [pack_fragments(w_x, ar(0, w_x.shape[0]), ar(64 * r, 64 * r + 64)) for r in range(CL)]
+        f_o = [pack_fragments(w_out, ar(0, D), ar(64 * r, 64 * r + 64)) for r in range(CL)]
+        frags.append(torch.cat([t.reshape(-1) for t in (*f_in, *f_x, *f_o)]))
+    return torch.stack(vecs).contiguous(), torch.stack(frags).contiguous()
+
+
+class FusedStack:
+    """The Mamba stack alone through the one-launch kernel (its stack-only mode): ``MambaBlocksSequential.forward(x,
+    inference_params)`` for <= 32 tokens per call, i.e. the reference's decode loop (``bimamba.py:320-372`` under
+    ``modules/mamba_blocks.py:186-197``) at one kernel launch per call.  The caches are the reference's own tensors, stacked:
+    ``conv [n_layers, B, 4, di]`` (time-major ``conv_state``) and ``ssm [n_layers, B, di, 16]``, updated in place."""
+
+    def __init__(self, stack):
+        hp = stack.hp
+        if not eligible(hp, stack.mode):
+            raise _lib.MtnError("the fused streaming kernel does not implement this stack")
+        self.hp, self.device = hp, stack.device
+        D = hp.d_model
+        with torch.cuda.device(self.device):
+            z = lambda n: torch.zeros(n, dtype=torch.float32, device=self.device)
+            # head blob layout of the separator kernel; only norm_f is read in stack-only mode
+            self.head = torch.cat([z(16 * D), z(D), z(D), stack.norm_f, z(16 * D)]).contiguous()
+            self.layer_vec, self.layer_frag = _pack_layers(stack.layers, hp, D // 32, self.device)
+
+    def run(self, x: torch.Tensor, conv: torch.Tensor, ssm: torch.Tensor) -> torch.Tensor:
+        hp = self.hp
+        B, F, D = x.shape
+        di = hp.d_inner
+        assert tuple(conv.shape) == (hp.n_mamba, B, 4, di) and conv.is_contiguous() and conv.dtype == torch.float32
+        out = torch.empty_like(x)
+        ops.stream_push(None, None, None, conv, ssm, None, self.head, None, None, self.layer_vec, self.layer_frag, B=B, F=F,
+                        N=D, D=D, di=di, R=hp.dt_rank, n_spk=hp.n_spk, n_layers=hp.n_mamba, first=False,
+                        halo_strides=(4 * di, B * 4 * di), halo_rows=4, stack_x=x, stack_out=out)
+        return out
+
+
 class FusedPush:
     """Packed weights of the fused push for one engine; ``run`` launches one push."""
 
@@ -61,20 +112,7 @@ class FusedPush:
             w_bot, w_mask = f32(w.w_bot), f32(w.w_mask)           # [D, N], [2N, D]
             self.bot_frag = torch.stack([pack_fragments(w_bot, ar(32 * r, 32 * r + 32), ar(0, N)) for r in range(CL)]).contiguous()
             self.mask_frag = torch.stack([pack_fragments(w_mask, ar(64 * r, 64 * r + 64), ar(0, D)) for r in range(CL)]).contiguous()
-            vecs, frags = [], []
-            for lw in w.layers:
-                w_in, w_x = f32(lw["w_in"]), f32(lw["w_x"])       # [2di, D], [n_dbl, di] (rows dt | B | C | zero pad)
-                w_out = 0.5 * f32(lw["w_out"])                    # the batch plan packs 2 * W_out for causal stacks
-                assert w_x.shape[0] % 16 == 0
-                vecs.append(torch.cat([lw["norm"], lw["conv_w"][0].reshape(-1), lw["conv_b"][0], lw["w_dt"][0].t().reshape(-1),
-                                       lw["dt_bias"][0], lw["A2"][0].reshape(-1), lw["D"][0]]))
-                f_in = [pack_fragments(w_in, torch.cat([ar(64 * r, 64 * r + 64), ar(di + 64 * r, di + 64 * r + 64)]), ar(0, D))
-                        for r in range(CL)]
-                f_x = [pack_fragments(w_x, ar(0, w_x.shape[0]), ar(64 * r, 64 * r + 64)) for r in range(CL)]
-                f_o = [pack_fragments(w_out, ar(0, D), ar(64 * r, 64 * r + 64)) for r in range(CL)]
-                frags.append(torch.cat([t.reshape(-1) for t in (*f_in, *f_x, *f_o)]))
-            self.layer_vec = torch.stack(vecs).contiguous()       # [n_layers, floats]
-            self.layer_frag = torch.stack(frags).contiguous()     # [n_layers, bf16 elements]
+            self.layer_vec, self.layer_frag = _pack_layers(w.layers, hp, CL, dev)
 
     def run(self, chunk: torch.Tensor, in_tail: torch.Tensor, first: bool, halo: torch.Tensor, h: torch.Tensor,
             ola_tail: torch.Tensor, timeline=None) -> torch.Tensor:

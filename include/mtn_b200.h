@@ -337,6 +337,16 @@ typedef struct {
     int first;              /* != 0: first push of a stream (no carried samples; the chunk holds F + 1 hops) */
     float eps_cln, eps_rms;
     unsigned long long* timeline; /* nullable debug aid: [n_layers + 2][16] globaltimer stamps of stream 0, rank 0 */
+    /* conv history addressing (floats): layer l, stream b at halo + l*halo_layer_stride + b*halo_stream_stride: [3][di].
+     * Dense = {halo_rows*di, B*halo_rows*di}. */
+    size_t halo_stream_stride, halo_layer_stride;
+    int halo_rows;          /* 3, or 4: each [halo_rows][di] block is the reference's conv_state (time-major): rows 1..3 are read
+                               as the history, all four are rewritten with the last four conv inputs */
+    /* stack-only mode (both nullable together): `MambaBlocksSequential.forward(x, inference_params)` itself --
+     * stack_x [B][F][D] fp32 is the stack's input, stack_out [B][F][D] = norm_f(blocks(x)); the encoder / mask / decoder
+     * arguments (mix, in_tail, est, ola_tail, bot_frag, mask_frag) are then unused and may be NULL. */
+    const float* stack_x;
+    float* stack_out;
 } mtn_stream_push_args;
 
 int mtn_stream_push_fwd(const mtn_stream_push_args* args, mtn_stream_t stream);

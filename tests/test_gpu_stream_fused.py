@@ -114,3 +114,44 @@ def test_fused_push_rejects_what_it_does_not_implement():
     with pytest.raises(_lib.MtnError):
         StreamingSeparator(eng, 1, fused=True)
     assert StreamingSeparator(eng, 1)._fused is None      # auto: falls back to the batch plan's chunk kernels
+
+
+@pytest.mark.parametrize("name,B", [("tiny", 3), ("S", 2)])
+def test_stack_decode_calls_take_the_one_launch_kernel_and_share_the_reference_caches(name, B):
+    """`MambaBlocksSequential.forward(x, inference_params)` (modules/mamba_blocks.py:186-197 over bimamba.py:320-372): calls of
+    <= 32 tokens run as one cluster-kernel launch on the reference's own cache tensors (kv[i] = (conv_state [B, di, 4],
+    ssm_state [B, di, 16]), here views of two stacked buffers); longer calls take the chunk kernels on the same caches.  Any
+    split of the sequence reproduces the one-call forward."""
+    import types
+    from avse_challenge_b200 import modules
+    hp = CONFIGS[name].causal()
+    m = init_state_dicts(hp, 5)["masknet"]
+    net = modules.MambaBlocksSequential(hp.n_mamba, bidirectional=False, d_model=hp.d_model, fused_add_norm=False, rms_norm=True)
+    net.load_state_dict({k[len("mamba_net."):]: v for k, v in m.items() if k.startswith("mamba_net.")}, strict=True)
+    net.to(DEV)
+    g = torch.Generator().manual_seed(9)
+    cuts = [40, 1, 1, 7, 32, 50, 1, 20]          # 40 and 50: chunk kernels; the rest: the one-launch kernel
+    x = torch.randn(B, sum(cuts), hp.d_model, generator=g).to(DEV)
+    full = net(x)
+    ip = types.SimpleNamespace(seqlen_offset=0, key_value_memory_dict={})
+    outs, pos = [], 0
+    for c in cuts:
+        outs.append(net(x[:, pos:pos + c], inference_params=ip))
+        pos += c
+        ip.seqlen_offset = pos
+    got = torch.cat(outs, dim=1)
+    err = rel_max(got.cpu(), full.cpu())
+    print(f"{hp.name}: split decode vs one call {err:.3e}")
+    assert err <= 5e-5, err
+    kv = ip.key_value_memory_dict
+    cs, ss = kv[hp.n_mamba - 1]
+    assert tuple(cs.shape) == (B, hp.d_inner, 4) and tuple(ss.shape) == (B, hp.d_inner, 16)
+    assert cs.data_ptr() == kv["_mtn_b200"]["conv"][hp.n_mamba - 1].data_ptr()      # views of the stacked buffers
+    # caches a caller allocated itself (Mamba.allocate_inference_cache) are adopted, not ignored
+    ip2 = types.SimpleNamespace(seqlen_offset=pos - 20, key_value_memory_dict={})
+    ipa = types.SimpleNamespace(seqlen_offset=0, key_value_memory_dict={})
+    net(x[:, :pos - 20], inference_params=ipa)                                      # long call: chunk kernels, plain tensors
+    for i in range(hp.n_mamba):
+        ip2.key_value_memory_dict[i] = tuple(t.clone() for t in ipa.key_value_memory_dict[i])
+    last = net(x[:, pos - 20:], inference_params=ip2)
+    assert rel_max(last.cpu(), full[:, pos - 20:].cpu()) <= 5e-5
