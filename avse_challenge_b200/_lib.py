@@ -24,7 +24,7 @@ EXPORTS = [
     "mtn_dp_overadd_prelu_fwd", "mtn_bias_planes_fwd", "mtn_gate_planes_fwd",
     "mtn_decoder_fwd", "mtn_cln_fwd", "mtn_softmax_mask_fwd", "mtn_split_planes", "mtn_si_snr_pit_fwd", "mtn_si_snr_workspace_bytes", "mtn_si_snr_pit_n_fwd", "mtn_si_snr_workspace_bytes_n", "mtn_last_error_string", "mtn_abi_version",
     "mtn_sizeof_gemm_args", "mtn_sizeof_scan_args", "mtn_sizeof_gn_apply_args",
-    "mtn_stream_push_fwd", "mtn_sizeof_stream_push_args", "mtn_conv_xproj_fwd",
+    "mtn_stream_push_fwd", "mtn_sizeof_stream_push_args", "mtn_stream_push_smem_bytes", "mtn_conv_xproj_fwd",
 ]
 
 
@@ -68,7 +68,7 @@ class StreamPushArgs(Structure):
         ("B", c_int), ("F", c_int), ("N", c_int), ("D", c_int), ("di", c_int), ("R", c_int), ("n_spk", c_int),
         ("n_layers", c_int), ("ld_mix", c_int), ("first", c_int), ("eps_cln", c_float), ("eps_rms", c_float),
         ("timeline", c_void_p), ("halo_stream_stride", c_size_t), ("halo_layer_stride", c_size_t),
-        ("halo_rows", c_int), ("stack_x", c_void_p), ("stack_out", c_void_p),
+        ("halo_rows", c_int), ("stack_x", c_void_p), ("stack_out", c_void_p), ("dsl", c_int),
     ]
 
 
@@ -139,6 +139,8 @@ def load():
     lib.mtn_bias_planes_fwd.argtypes = [c_void_p, c_int, c_void_p, c_float, c_void_p, c_int, c_int, c_int, c_int, c_void_p]
     lib.mtn_gate_planes_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]
     lib.mtn_stream_push_fwd.argtypes = [POINTER(StreamPushArgs), c_void_p]
+    lib.mtn_stream_push_smem_bytes.argtypes = [c_int, c_int, c_int]
+    lib.mtn_stream_push_smem_bytes.restype = c_size_t
     for name, st in (("mtn_sizeof_gemm_args", GemmArgs), ("mtn_sizeof_scan_args", ScanArgs),
                      ("mtn_sizeof_gn_apply_args", GnApplyArgs), ("mtn_sizeof_stream_push_args", StreamPushArgs)):
         fn = getattr(lib, name)
@@ -151,7 +153,8 @@ def load():
         if fn is not None and name not in ("mtn_last_error_string", "mtn_abi_version", "mtn_si_snr_workspace_bytes",
                                            "mtn_si_snr_workspace_bytes_n",
                                            "mtn_gn_partials_bytes", "mtn_sizeof_gemm_args", "mtn_sizeof_scan_args",
-                                           "mtn_sizeof_gn_apply_args", "mtn_sizeof_stream_push_args"):
+                                           "mtn_sizeof_gn_apply_args", "mtn_sizeof_stream_push_args",
+                                           "mtn_stream_push_smem_bytes"):
             fn.restype = c_int
     lib.mtn_si_snr_workspace_bytes.restype = c_size_t
     lib.mtn_si_snr_workspace_bytes_n.restype = c_size_t

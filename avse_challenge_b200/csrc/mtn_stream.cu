@@ -34,39 +34,52 @@ namespace mtn {
 
 constexpr int SP_THREADS = 512;
 constexpr int SP_WARPS = SP_THREADS / 32;
-constexpr int SP_DSL = 64;   // d_inner channels per CTA
-constexpr int SP_CSL = 32;   // d_model columns per CTA
-constexpr int SP_MSL = 64;   // mask columns per CTA (n_spk * N / CL with N == D, n_spk == 2)
+// Channels of d_inner per CTA (DSL, a template parameter: 32, 64 or 128) fix the partition: cluster size CL = 2 * d_model / DSL,
+// d_model columns per CTA CSL = DSL / 2, mask columns per CTA MSL = DSL (n_spk * N / CL with N == d_model, 2 speakers).  Small
+// DSL = more CTAs per stream = lower latency; large DSL = more streams resident at once.
 constexpr int SP_PAD = 8;    // bf16 row padding of the operand planes: row stride = 4 (mod 32) words, conflict-free fragments
 
 // Shared-memory carve-up (bytes), compile-time per (frame tiles, d_model): every buffer is `smem + constant`, which keeps ~30
 // pointers out of the register file (a run-time layout spilled 1.4 KB per thread).  Identical in every CTA of a cluster:
 // peers address each other's buffers by the same offsets.
+template <int CT, int KSTEPS>
+struct GemmShape {
+    static constexpr int ks_() {
+        int KS = 1;
+        while (KS * 2 * CT <= SP_WARPS && KS * 2 <= KSTEPS && KSTEPS % (KS * 2) == 0) KS *= 2;
+        return KS;
+    }
+    static constexpr int KS = ks_(), KPER = KSTEPS / KS, UNITS = CT * KS, NPRE = KPER < 8 ? KPER : 8, LDR = 16 * CT + 4;
+};
+
 constexpr int sp_al16(int bytes) { return (bytes + 15) / 16 * 16; }
 constexpr int sp_max(int a, int b) { return a > b ? a : b; }
-template <int NTF, int D>
+template <int NTF, int D, int DSL>
 struct SpL {
-    static constexpr int R = D / 16, NXp = (R + 32 + 15) / 16 * 16, CL = D / 32;
-    static constexpr int Fp = 8 * NTF, lda = D + SP_PAD, ldu = SP_DSL + SP_PAD;
+    static constexpr int R = D / 16, NXp = (R + 32 + 15) / 16 * 16, CL = 2 * D / DSL, CSL = DSL / 2, MSL = DSL;
+    static constexpr int Fp = 8 * NTF, lda = D + SP_PAD, ldu = DSL + SP_PAD;
     static constexpr int act_hi = 0;
     static constexpr int act_lo = act_hi + sp_al16(Fp * lda * 2);
     static constexpr int su_hi = act_lo + sp_al16(Fp * lda * 2);
     static constexpr int su_lo = su_hi + sp_al16(Fp * ldu * 2);
     static constexpr int planes_end = su_lo + sp_al16(Fp * ldu * 2);
     static constexpr int xs = planes_end;
-    static constexpr int zs = xs + sp_al16((Fp + 3) * SP_DSL * 4);
-    static constexpr int us = zs + sp_al16(Fp * SP_DSL * 4);
-    static constexpr int dl = us + sp_al16(Fp * SP_DSL * 4);
-    static constexpr int dbl = dl + sp_al16(Fp * SP_DSL * 4);
+    static constexpr int zs = xs + sp_al16((Fp + 3) * DSL * 4);
+    static constexpr int us = zs + sp_al16(Fp * DSL * 4);
+    static constexpr int dl = us + sp_al16(Fp * DSL * 4);
+    static constexpr int dbl = dl + sp_al16(Fp * DSL * 4);
     static constexpr int xd = dbl + sp_al16(Fp * NXp * 4);        // x_proj partial of this CTA (read by every peer)
     static constexpr int res = xd + sp_al16(Fp * NXp * 4);        // residual slice (read by every peer)
-    static constexpr int mixw = res + sp_al16(Fp * SP_CSL * 4);
-    static constexpr int frs = mixw + sp_al16(Fp * SP_MSL * 4);   // decoder frames: this CTA's partial (read by rank 0)
+    static constexpr int mixw = res + sp_al16(Fp * CSL * 4);
+    static constexpr int frs = mixw + sp_al16(Fp * MSL * 4);      // decoder frames: this CTA's partial (read by rank 0)
     static constexpr int lvec = frs + sp_al16(Fp * 16 * 4);       // this CTA's slice of the layer's small vectors
-    static constexpr int norm = lvec + sp_al16(SP_DSL * (23 + R) * 4);   // RMSNorm weights, double-buffered one layer ahead
-    // K-split partial sums of one GEMM: the widest user is in_proj (2 x 128 columns), out_proj (D columns; plane 0 is read by
-    // every peer) or the bottleneck (8 x 32 columns)
-    static constexpr int widest = sp_max(sp_max(2 * (2 * SP_DSL + 4), D + 4), 8 * (SP_CSL + 4));
+    static constexpr int norm = lvec + sp_al16(DSL * (23 + R) * 4);   // RMSNorm weights, double-buffered one layer ahead
+    // K-split partial sums of one GEMM (plane 0 of out_proj's is read by every peer): the widest of the five contractions
+    template <int CT, int KSTEPS>
+    static constexpr int width() { return GemmShape<CT, KSTEPS>::KS * GemmShape<CT, KSTEPS>::LDR; }
+    static constexpr int widest = sp_max(sp_max(sp_max(width<2 * DSL / 16, D / 16>(), width<NXp / 16, DSL / 16>()),
+                                                sp_max(width<D / 16, DSL / 16>(), width<CSL / 16, D / 16>())),
+                                         sp_max(width<MSL / 16, D / 16>(), 2 * 16 + 4));
     static constexpr int red = norm + sp_al16(2 * D * 4);
     static constexpr int total = red + sp_al16(Fp * widest * 4);
 };
@@ -134,15 +147,6 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // in red[ks][frame][ldr], ldr = 16*CT + 4); a warp works on units (tile, k part) warp, warp + 16, ...  The weights of a
 // warp's FIRST unit (up to 8 k-steps = 64 registers) can be requested long before the operand planes exist (`issue`), so the
 // L2 round trip and the 512 B / k-step / warp stream hide behind the phase in between.
-template <int CT, int KSTEPS>
-struct GemmShape {
-    static constexpr int ks_() {
-        int KS = 1;
-        while (KS * 2 * CT <= SP_WARPS && KS * 2 <= KSTEPS && KSTEPS % (KS * 2) == 0) KS *= 2;
-        return KS;
-    }
-    static constexpr int KS = ks_(), KPER = KSTEPS / KS, UNITS = CT * KS, NPRE = KPER < 8 ? KPER : 8, LDR = 16 * CT + 4;
-};
 
 __device__ __forceinline__ uint4 ld_weights(const uint4* p) {   // volatile: stays where it is issued
     uint4 v;
@@ -246,59 +250,87 @@ __device__ __forceinline__ float red_sum(const float* red, int KS, int Fp, int l
 // weight g (shared memory) -> operand planes.  Lane = column inside a slice, so a warp reads 128 contiguous bytes per peer.
 // Split in two so that the caller can put its weight requests BETWEEN the peer reads and their use: issued first, 128 KB of
 // weight loads per CTA queue in front of the DSMEM reads in the load pipe and delay the norm by a microsecond.
-template <int CL, int ROWS>   // ROWS = rows per warp (1 for F <= 16, 2 for F <= 32)
+template <int D, int CSL, int ROWS>   // ROWS = rows per warp (1 for F <= 16, 2 for F <= 32); CSL = residual columns per rank
 struct NormRows {
-    float v[ROWS][CL];
+    static constexpr int NL = D / 32;   // loads per row: lane = column inside a 32-column block
+    float v[ROWS][NL];
+    // block j of this rank's rotation (every rank starts at its own columns, so the peers' ports are hit evenly)
+    __device__ __forceinline__ static int block_of(int j, int rank) { return (j + rank * CSL / 32) & (NL - 1); }
     __device__ __forceinline__ void gather(const float* res_local, int F, int warp, int lane, int rank) {
 #pragma unroll
         for (int i = 0; i < ROWS; ++i) {
             const int f = warp + i * SP_WARPS;
             if (f < F) {
 #pragma unroll
-                for (int r = 0; r < CL; ++r) v[i][r] = ld_dsmem(dsmem_addr(res_local + f * SP_CSL + lane, (rank + r) & (CL - 1)));
+                for (int j = 0; j < NL; ++j) {
+                    const int col = 32 * block_of(j, rank) + lane;
+                    v[i][j] = ld_dsmem(dsmem_addr(res_local + f * CSL + col % CSL, col / CSL));
+                }
             }
         }
     }
-    // stack-only mode: the normalised rows ARE the result; every CTA has all of them, rank r stores its 32 columns
+    // stack-only mode: the normalised rows ARE the result; every CTA has all of them, rank r stores its own columns
     __device__ __forceinline__ void finish_out(const float* g, int F, float eps, float* out, int warp, int lane, int rank) {
-        constexpr int D = 32 * CL;
 #pragma unroll
         for (int i = 0; i < ROWS; ++i) {
             const int f = warp + i * SP_WARPS;
             if (f < F) {
                 float sq = 0.f;
 #pragma unroll
-                for (int r = 0; r < CL; ++r) sq = fmaf(v[i][r], v[i][r], sq);
+                for (int j = 0; j < NL; ++j) sq = fmaf(v[i][j], v[i][j], sq);
                 const float rstd = rsqrtf(warp_sum(sq) * (1.0f / D) + eps);
-                out[size_t(f) * D + 32 * rank + lane] = v[i][0] * rstd * g[32 * rank + lane];   // r = 0 is this rank's own slice
+#pragma unroll
+                for (int j = 0; j < NL; ++j) {
+                    const int col = 32 * block_of(j, rank) + lane;
+                    if (col / CSL == rank) out[size_t(f) * D + col] = v[i][j] * rstd * g[col];
+                }
             }
         }
     }
     __device__ __forceinline__ void finish(const float* g, int F, float eps, __nv_bfloat16* ahi, __nv_bfloat16* alo, int lda, int warp,
                                            int lane, int rank) {
-        constexpr int D = 32 * CL;
 #pragma unroll
         for (int i = 0; i < ROWS; ++i) {
             const int f = warp + i * SP_WARPS;
             if (f < F) {
                 float sq = 0.f;
 #pragma unroll
-                for (int r = 0; r < CL; ++r) sq = fmaf(v[i][r], v[i][r], sq);
+                for (int j = 0; j < NL; ++j) sq = fmaf(v[i][j], v[i][j], sq);
                 const float rstd = rsqrtf(warp_sum(sq) * (1.0f / D) + eps);
 #pragma unroll
-                for (int r = 0; r < CL; ++r) {
-                    const int col = 32 * ((rank + r) & (CL - 1)) + lane;
-                    put_planes(ahi, alo, f * lda + col, v[i][r] * rstd * g[col]);
+                for (int j = 0; j < NL; ++j) {
+                    const int col = 32 * block_of(j, rank) + lane;
+                    put_planes(ahi, alo, f * lda + col, v[i][j] * rstd * g[col]);
                 }
             }
         }
     }
 };
 
-template <int NTF, int D>
+// sum of v[k] over the TPC lanes that share a channel, scattered: lane sp returns the total of element sp.
+// log2(TPC) rounds of TPC/2, TPC/4, ... independent shuffles instead of TPC x log2(TPC) dependent ones.
+template <int TPC>
+__device__ __forceinline__ float reduce_scatter(float (&v)[TPC], int sp) {
+#pragma unroll
+    for (int half = TPC / 2; half >= 1; half >>= 1) {
+        const bool up = sp & half;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const float keep = up ? v[i + half] : v[i];
+            const float send = up ? v[i] : v[i + half];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+        }
+    }
+    return v[0];
+}
+
+template <int NTF, int D, int DSL>
 __global__ void __launch_bounds__(SP_THREADS, 1) stream_push_kernel(const mtn_stream_push_args a) {
-    using L = SpL<NTF, D>;
+    using L = SpL<NTF, D, DSL>;
     constexpr int Fp = 8 * NTF, N = D, di = 2 * D, R = L::R, NXp = L::NXp, CL = L::CL, lda = L::lda, ldu = L::ldu;
+    constexpr int SP_DSL = DSL, SP_CSL = L::CSL, SP_MSL = L::MSL;   // d_inner channels / d_model columns / mask columns per CTA
+    constexpr int TPC = SP_THREADS / DSL, SPT = 16 / TPC;           // scan: threads per channel, states per thread
+    using Norm = NormRows<D, SP_CSL, (NTF + 1) / 2>;
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int rank = int(cluster_ctarank());
@@ -449,7 +481,7 @@ __global__ void __launch_bounds__(SP_THREADS, 1) stream_push_kernel(const mtn_st
         cp_async_commit();
     };
     prefetch_vectors(0);
-    float2 h_prev = make_float2(0.f, 0.f);
+    float h_prev[SPT] = {};
     float* hst_prev = nullptr;
     SP_MARK(0);
     for (int layer = 0; layer < a.n_layers; ++layer) {
@@ -466,20 +498,25 @@ __global__ void __launch_bounds__(SP_THREADS, 1) stream_push_kernel(const mtn_st
         // Add -> RMSNorm (bimamba.py:446-447), all rows in every CTA.  Order of the requests: the peers' residual slices, then
         // everything that does not depend on this layer's activations (in_proj weights of this warp's unit, the SSM state of
         // this thread's (channel, state pair), the conv history), then the norm itself.
-        NormRows<CL, (NTF + 1) / 2> nr;
+        Norm nr;
         nr.gather(res, F, warp, lane, rank);
-        float2 h;
+        float h[SPT];
         {
-            const float* hp = hst + (tid >> 3) * 16 + 2 * (tid & 7);
-            asm volatile("ld.global.v2.f32 {%0,%1}, [%2];" : "=f"(h.x), "=f"(h.y) : "l"(hp));
+            const float* hp = hst + (tid / TPC) * 16 + SPT * (tid % TPC);
+#pragma unroll
+            for (int q = 0; q < SPT; ++q) asm volatile("ld.global.f32 %0, [%1];" : "=f"(h[q]) : "l"(hp + q));
         }
         float halo_v = 0.f;
         // a.halo_rows = 4: the buffer is the reference's 4-wide conv_state (row 0 = the oldest input, never read: bimamba.py:274-277)
+        static_assert(4 * SP_DSL <= SP_THREADS, "one thread per element of the conv history");
         if (tid < 3 * SP_DSL)
             asm volatile("ld.global.f32 %0, [%1];" : "=f"(halo_v) : "l"(halo + (a.halo_rows - 3 + tid / SP_DSL) * di + tid % SP_DSL));
         // the previous block's final SSM state goes out here, a whole phase away from the next cluster barrier: a global store
         // still in flight at `barrier.cluster.arrive.release` makes every thread sit in its memory barrier
-        if (layer > 0) *reinterpret_cast<float2*>(hst_prev + (tid >> 3) * 16 + 2 * (tid & 7)) = h_prev;
+        if (layer > 0) {
+#pragma unroll
+            for (int q = 0; q < SPT; ++q) hst_prev[(tid / TPC) * 16 + SPT * (tid % TPC) + q] = h_prev[q];
+        }
         WFrag<GI::NPRE> w_in;
         gemm_issue<ct_in, ks_d>(w_in, f_in, warp, lane);
         nr.finish(s_norm + (layer & 1) * D, F, a.eps_rms, act_hi, act_lo, lda, warp, lane, rank);
@@ -494,7 +531,7 @@ __global__ void __launch_bounds__(SP_THREADS, 1) stream_push_kernel(const mtn_st
         __syncthreads();
         SP_MARK(2);
 #pragma unroll
-        for (int it = 0; it < Fp * 2 * SP_DSL / SP_THREADS; ++it) {   // a thread's iterations are independent: unrolled for ILP
+        for (int it = 0; it < (Fp * 2 * SP_DSL + SP_THREADS - 1) / SP_THREADS; ++it) {   // a thread's iterations are independent: unrolled for ILP
             const int i = tid + it * SP_THREADS;
             if (i < F * 2 * SP_DSL) {
                 const int f = i / (2 * SP_DSL), c = i % (2 * SP_DSL);
@@ -509,7 +546,7 @@ __global__ void __launch_bounds__(SP_THREADS, 1) stream_push_kernel(const mtn_st
 
         // causal depthwise conv (width 4) + bias + SiLU (ssi.py:182); new history = last three conv inputs
 #pragma unroll
-        for (int it = 0; it < Fp * SP_DSL / SP_THREADS; ++it) {
+        for (int it = 0; it < (Fp * SP_DSL + SP_THREADS - 1) / SP_THREADS; ++it) {
             const int i = tid + it * SP_THREADS;
             if (i < F * SP_DSL) {
                 const int f = i / SP_DSL, c = i % SP_DSL;
@@ -544,7 +581,7 @@ __global__ void __launch_bounds__(SP_THREADS, 1) stream_push_kernel(const mtn_st
 
         // dt_proj + softplus (ssi.py:187, delta_softplus of :218)
 #pragma unroll
-        for (int it = 0; it < Fp * SP_DSL / SP_THREADS; ++it) {
+        for (int it = 0; it < (Fp * SP_DSL + SP_THREADS - 1) / SP_THREADS; ++it) {
             const int i = tid + it * SP_THREADS;
             if (i < F * SP_DSL) {
                 const int f = i / SP_DSL, c = i % SP_DSL;
@@ -560,60 +597,52 @@ __global__ void __launch_bounds__(SP_THREADS, 1) stream_push_kernel(const mtn_st
         __syncthreads();
         SP_MARK(8);
 
-        // selective-scan steps: 8 threads per channel, 2 of the 16 states each (selective_scan_ref, ssi.py:91-157);
+        // selective-scan steps: TPC threads per channel, SPT of the 16 states each (selective_scan_ref, ssi.py:91-157);
         // y = (sum_n C h + D u) * silu(z) -> operand planes of out_proj (over the u planes, which x_proj is done with).
-        // Eight steps of operands are fetched before their recurrence runs and the eight results are stored after it (the
-        // compiler cannot move shared loads across the plane stores of an earlier step).
+        // TPC steps of operands are fetched before their recurrence runs and the TPC results are stored after it (the
+        // compiler cannot move shared loads across the plane stores of an earlier step); the state sums of those steps are
+        // reduce-scattered over the channel's lanes, so lane sp finishes step f0 + sp.
         {
-            const int c = tid >> 3, sp = tid & 7;
-            const float A0 = s_A2[c * 16 + 2 * sp], A1 = s_A2[c * 16 + 2 * sp + 1];
+            const int c = tid / TPC, sp = tid % TPC;
+            float A[SPT];
+#pragma unroll
+            for (int q = 0; q < SPT; ++q) A[q] = s_A2[c * 16 + SPT * sp + q];
             const float Dp = s_D[c];
-            const float* bc = dbl + R + 2 * sp;
+            const float* bc = dbl + R + SPT * sp;
+#pragma unroll 1
+            for (int f0 = 0; f0 < F; f0 += TPC) {
+                float d[TPC], u[TPC], yv[TPC], Bv[TPC][SPT], Cv[TPC][SPT];
 #pragma unroll
-            for (int f0 = 0; f0 < Fp; f0 += 8) {
-                if (f0 < F) {
-                    float d[8], u[8], yv[8];
-                    float2 Bv[8], Cv[8];
+                for (int k = 0; k < TPC; ++k) {
+                    const int f = f0 + k < F ? f0 + k : F - 1;
+                    d[k] = dl[f * SP_DSL + c];
+                    u[k] = us[f * SP_DSL + c];
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const int f = f0 + k < F ? f0 + k : F - 1;
-                        d[k] = dl[f * SP_DSL + c];
-                        u[k] = us[f * SP_DSL + c];
-                        Bv[k] = *reinterpret_cast<const float2*>(bc + f * NXp);
-                        Cv[k] = *reinterpret_cast<const float2*>(bc + f * NXp + 16);
+                    for (int q = 0; q < SPT; ++q) {
+                        Bv[k][q] = bc[f * NXp + q];
+                        Cv[k][q] = bc[f * NXp + 16 + q];
                     }
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        if (f0 + k < F) {
-                            const float du = d[k] * u[k];
-                            h.x = fmaf(ex2_approx(d[k] * A0), h.x, du * Bv[k].x);
-                            h.y = fmaf(ex2_approx(d[k] * A1), h.y, du * Bv[k].y);
-                        }
-                        yv[k] = fmaf(Cv[k].x, h.x, Cv[k].y * h.y);
-                    }
-                    // reduce-scatter over the channel's eight lanes: 4 + 2 + 1 independent shuffles instead of 8 x 3 dependent
-                    // ones; lane sp ends up with the state sum of step f0 + sp
-                    float k4[4], k2[2];
-                    const bool b2 = sp & 4, b1 = sp & 2, b0 = sp & 1;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float recv = __shfl_xor_sync(0xffffffffu, b2 ? yv[i] : yv[i + 4], 4);
-                        k4[i] = (b2 ? yv[i + 4] : yv[i]) + recv;
-                    }
-#pragma unroll
-                    for (int i = 0; i < 2; ++i) {
-                        const float recv = __shfl_xor_sync(0xffffffffu, b1 ? k4[i] : k4[i + 2], 2);
-                        k2[i] = (b1 ? k4[i + 2] : k4[i]) + recv;
-                    }
-                    const float recv = __shfl_xor_sync(0xffffffffu, b0 ? k2[0] : k2[1], 1);
-                    float um = u[0];
-#pragma unroll
-                    for (int k = 1; k < 8; ++k) um = sp == k ? u[k] : um;
-                    const float mine = fmaf(Dp, um, (b0 ? k2[1] : k2[0]) + recv);
-                    if (f0 + sp < F) put_planes(su_hi, su_lo, (f0 + sp) * ldu + c, mine * zs[(f0 + sp) * SP_DSL + c]);
                 }
+#pragma unroll
+                for (int k = 0; k < TPC; ++k) {
+                    const bool live = f0 + k < F;
+                    const float du = d[k] * u[k];
+                    float y = 0.f;
+#pragma unroll
+                    for (int q = 0; q < SPT; ++q) {
+                        if (live) h[q] = fmaf(ex2_approx(d[k] * A[q]), h[q], du * Bv[k][q]);
+                        y = fmaf(Cv[k][q], h[q], y);
+                    }
+                    yv[k] = y;
+                }
+                const float ysum = reduce_scatter<TPC>(yv, sp);
+                float um = u[0];
+#pragma unroll
+                for (int k = 1; k < TPC; ++k) um = sp == k ? u[k] : um;
+                if (f0 + sp < F) put_planes(su_hi, su_lo, (f0 + sp) * ldu + c, fmaf(Dp, um, ysum) * zs[(f0 + sp) * SP_DSL + c]);
             }
-            h_prev = h;
+#pragma unroll
+            for (int q = 0; q < SPT; ++q) h_prev[q] = h[q];
             hst_prev = hst;
         }
         __syncthreads();
@@ -643,12 +672,13 @@ __global__ void __launch_bounds__(SP_THREADS, 1) stream_push_kernel(const mtn_st
         cluster_sync_all();   // [A] of the next block / of norm_f
         SP_MARK(13);
     }
-    *reinterpret_cast<float2*>(hst_prev + (tid >> 3) * 16 + 2 * (tid & 7)) = h_prev;   // last block's final state
+#pragma unroll
+    for (int q = 0; q < SPT; ++q) hst_prev[(tid / TPC) * 16 + SPT * (tid % TPC) + q] = h_prev[q];   // last block's final state
     tl_row = 1 + a.n_layers;
     SP_MARK(0);
 
     if (stack_only) {   // norm_f (modules/mamba_blocks.py:196-197) is the output
-        NormRows<CL, (NTF + 1) / 2> nr;
+        Norm nr;
         nr.gather(res, F, warp, lane, rank);
         nr.finish_out(s_norm + (a.n_layers & 1) * D, F, a.eps_rms, a.stack_out + size_t(b) * F * D, warp, lane, rank);
         cluster_sync_all();   // peers keep their residual slices alive until every CTA has gathered them
@@ -658,7 +688,7 @@ __global__ void __launch_bounds__(SP_THREADS, 1) stream_push_kernel(const mtn_st
     const uint4* f_mask = reinterpret_cast<const uint4*>(a.mask_frag) + size_t(rank) * (SP_MSL / 16) * (D / 16) * 64;
     WFrag<GemmShape<SP_MSL / 16, D / 16>::NPRE> w_mask;
     {
-        NormRows<CL, (NTF + 1) / 2> nr;
+        Norm nr;
         nr.gather(res, F, warp, lane, rank);
         gemm_issue<SP_MSL / 16, D / 16>(w_mask, f_mask, warp, lane);
         nr.finish(s_norm + (a.n_layers & 1) * D, F, a.eps_rms, act_hi, act_lo, lda, warp, lane, rank);
@@ -723,6 +753,34 @@ using namespace mtn;
 
 extern "C" size_t mtn_sizeof_stream_push_args(void) { return sizeof(mtn_stream_push_args); }
 
+namespace {
+template <int NTF>
+size_t sp_smem_ntf(int D, int dsl) {
+#define SP_SZ(D_)                                                     \
+    if (D == D_) {                                                    \
+        if (dsl == 64) return SpL<NTF, D_, 64>::total;                \
+        if (dsl == 128) return SpL<NTF, D_, 128>::total;              \
+        if constexpr (D_ <= 256) { if (dsl == 32) return SpL<NTF, D_, 32>::total; } \
+        return 0;                                                     \
+    }
+    SP_SZ(64) SP_SZ(128) SP_SZ(256) SP_SZ(512)
+#undef SP_SZ
+    return 0;
+}
+}  // namespace
+
+// Dynamic shared memory one CTA of the push kernel needs for F frames at d_model D and dsl channels per CTA; 0 = that
+// combination does not exist (cluster size 2 * D / dsl outside 2..16).  A launch needs <= 227 KiB.
+extern "C" size_t mtn_stream_push_smem_bytes(int F, int D, int dsl) {
+    if (F < 1 || F > 32 || dsl <= 0 || 2 * D / dsl > 16 || D < dsl) return 0;
+    switch ((F + 7) / 8) {
+        case 1: return sp_smem_ntf<1>(D, dsl);
+        case 2: return sp_smem_ntf<2>(D, dsl);
+        case 3: return sp_smem_ntf<3>(D, dsl);
+        default: return sp_smem_ntf<4>(D, dsl);
+    }
+}
+
 extern "C" int mtn_stream_push_fwd(const mtn_stream_push_args* args, mtn_stream_t stream) {
     MTN_REQUIRE(args, "stream_push: null args");
     const mtn_stream_push_args& a = *args;
@@ -741,24 +799,34 @@ extern "C" int mtn_stream_push_fwd(const mtn_stream_push_args* args, mtn_stream_
                     (reinterpret_cast<uintptr_t>(a.layer_frag) & 15) == 0 && a.layer_frag_stride % 16 == 0 &&
                     (reinterpret_cast<uintptr_t>(a.head) & 15) == 0,
                 "stream_push: weight blobs must be 16-byte aligned");
-    const int CL = a.D / 32;
+    const int DSL = a.dsl ? a.dsl : 64;
+    MTN_REQUIRE(DSL == 32 || DSL == 64 || DSL == 128, "stream_push: dsl=%d channels per CTA (32, 64 or 128; 0 = 64)", a.dsl);
+    const int CL = 2 * a.D / DSL;
+    // CL >= 2: a CTA's mask columns (dsl of them) must lie inside one speaker's enc_dim = d_model columns
+    MTN_REQUIRE(CL >= 2 && CL <= 16, "stream_push: d_model %d at %d channels per CTA needs a cluster of %d CTAs (2..16)", a.D, DSL, CL);
     const int NTF = (a.F + 7) / 8;
     MTN_REQUIRE(a.R == a.D / 16, "stream_push: dt_rank=%d, the recipes' ceil(d_model / 16) = %d is compiled in", a.R, a.D / 16);
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     const void* kern = nullptr;
     int smem_bytes = 0;
-    static std::atomic<unsigned long long> done[16];
-#define SP_PICK(NTF_, D_)                                                              \
+    static std::atomic<unsigned long long> done[4 * 4 * 3];
+#define SP_PICK(NTF_, D_, DSL_)                                                        \
     do {                                                                               \
-        kern = reinterpret_cast<const void*>(&stream_push_kernel<NTF_, D_>);           \
-        smem_bytes = SpL<NTF_, D_>::total;                                             \
+        kern = reinterpret_cast<const void*>(&stream_push_kernel<NTF_, D_, DSL_>);     \
+        smem_bytes = SpL<NTF_, D_, DSL_>::total;                                       \
+    } while (0)
+#define SP_PICK_DSL(NTF_, D_)                                                          \
+    do {                                                                               \
+        if (DSL == 64) SP_PICK(NTF_, D_, 64);                                          \
+        else if (DSL == 128) SP_PICK(NTF_, D_, 128);                                   \
+        else if constexpr (D_ <= 256) SP_PICK(NTF_, D_, 32);                           \
     } while (0)
 #define SP_PICK_D(NTF_)                                   \
     switch (a.D) {                                        \
-        case 64: SP_PICK(NTF_, 64); break;                \
-        case 128: SP_PICK(NTF_, 128); break;              \
-        case 256: SP_PICK(NTF_, 256); break;              \
-        default: SP_PICK(NTF_, 512); break;               \
+        case 64: SP_PICK_DSL(NTF_, 64); break;            \
+        case 128: SP_PICK_DSL(NTF_, 128); break;          \
+        case 256: SP_PICK_DSL(NTF_, 256); break;          \
+        default: SP_PICK_DSL(NTF_, 512); break;           \
     }
     switch (NTF) {
         case 1: SP_PICK_D(1) break;
@@ -767,9 +835,11 @@ extern "C" int mtn_stream_push_fwd(const mtn_stream_push_args* args, mtn_stream_
         default: SP_PICK_D(4) break;
     }
 #undef SP_PICK_D
+#undef SP_PICK_DSL
 #undef SP_PICK
+    MTN_REQUIRE(kern, "stream_push: no kernel for d_model %d at %d channels per CTA", a.D, DSL);
     MTN_REQUIRE(smem_bytes <= 227 * 1024, "stream_push: %d B of shared memory needed", smem_bytes);
-    const int slot = (NTF - 1) * 4 + (a.D == 64 ? 0 : a.D == 128 ? 1 : a.D == 256 ? 2 : 3);
+    const int slot = ((NTF - 1) * 4 + (a.D == 64 ? 0 : a.D == 128 ? 1 : a.D == 256 ? 2 : 3)) * 3 + (DSL == 32 ? 0 : DSL == 64 ? 1 : 2);
     {
         int dev = -1;
         cudaGetDevice(&dev);

@@ -229,7 +229,7 @@ def decoder(sep, w_dec, batch, T, L, N, n_spk=2, est=None, frames=None, tail=Non
 
 def stream_push(mix, in_tail, est, halo, h, ola_tail, head, bot_frag, mask_frag, layer_vec, layer_frag, *, B, F, N, D,
                 di, R, n_spk, n_layers, first, eps_cln=1e-8, eps_rms=1e-5, timeline=None, halo_strides=None, halo_rows=3,
-                stack_x=None, stack_out=None):
+                stack_x=None, stack_out=None, dsl=64):
     """One streaming chunk of ``F <= 32`` frames per stream through the whole causal separator in one launch
     (``mtn_stream_push_fwd``; weight layouts in include/mtn_b200.h, packer in stream_fused.py).  ``stack_x`` / ``stack_out``
     (fp32 [B, F, D]): stack-only mode = ``MambaBlocksSequential.forward(x, inference_params)``; mix / est / tails are unused.
@@ -255,7 +255,7 @@ def stream_push(mix, in_tail, est, halo, h, ola_tail, head, bot_frag, mask_frag,
                           layer_vec_stride=layer_vec.stride(0), layer_frag_stride=layer_frag.stride(0) * layer_frag.element_size(),
                           B=B, F=F, N=N, D=D, di=di, R=R, n_spk=n_spk, n_layers=n_layers, ld_mix=(mix.stride(0) if mix is not None else 0),
                           eps_cln=eps_cln, eps_rms=eps_rms, halo_stream_stride=halo_strides[0], halo_layer_stride=halo_strides[1], halo_rows=halo_rows,
-                          stack_x=ptr(stack_x), stack_out=ptr(stack_out))
+                          stack_x=ptr(stack_x), stack_out=ptr(stack_out), dsl=dsl)
     check(_lib.load().mtn_stream_push_fwd(args, _stream()), "mtn_stream_push_fwd")
     return est if stack_x is None else stack_out
 

@@ -41,10 +41,31 @@ def pack_fragments(W: torch.Tensor, rows: torch.Tensor, ks: torch.Tensor) -> tor
     return torch.stack([frag(hi), frag(lo)], dim=2).contiguous()
 
 
-def _pack_layers(layers, hp: HParams, CL: int, dev):
+# Measured on a B200 (tools/stream_grid.py, profiles/r02/stream/stream_grid_S_f{20,2}.jsonl; S causal, 20-frame pushes): a
+# cluster of 16 CTAs takes 0.22 ms per push and 4 of them are resident at once, 8 CTAs 0.24 ms / 12 resident, 4 CTAs 0.34 ms /
+# 32 resident; beyond that the clusters queue in waves.  Relative time per wave and resident clusters by cluster size:
+_WAVE_TIME = {32: 0.93, 64: 1.0, 128: 1.41}
+_RESIDENT = {16: 4, 8: 12, 4: 32, 2: 64}
+
+
+def channels_per_cta(batch: int, d_model: int, frames: int = MAX_FRAMES) -> int:
+    """d_inner channels one CTA of a stream's cluster owns (``mtn_stream_push_args.dsl``): cluster size = 2 * d_model / dsl.
+    Few streams: small slices (most CTAs per stream = lowest latency).  Many streams: larger slices, so that every stream's
+    cluster is resident at once instead of queueing in waves -- as far as the kernel's shared memory for ``frames`` rows
+    allows.  Picks the candidate with the smallest (waves x time per wave) from the measured table above."""
+    fits = lambda dsl: 0 < int(_lib.load().mtn_stream_push_smem_bytes(frames, d_model, dsl)) <= 227 * 1024
+    cands = [dsl for dsl in (32, 64, 128) if fits(dsl)]
+    if not cands:
+        raise _lib.MtnError(f"no streaming push kernel for d_model {d_model} at {frames} frames")
+    cost = lambda dsl: -(-batch // _RESIDENT[2 * d_model // dsl]) * _WAVE_TIME[dsl]
+    return min(cands, key=cost)
+
+
+def _pack_layers(layers, hp: HParams, dsl: int, dev):
     """Per layer: the fp32 vector blob and the fragment blob (in_proj | x_proj | out_proj slabs per cluster rank) of
-    ``mtn_stream_push_args`` from ``engine.pack_layer`` dicts."""
+    ``mtn_stream_push_args`` from ``engine.pack_layer`` dicts, for ``dsl`` channels per CTA."""
     D, di = hp.d_model, hp.d_inner
+    CL = di // dsl
     f32 = lambda planes: planes.float().sum(dim=0)           # hi + lo: exact, re-splits to the same planes
     ar = lambda a, b: torch.arange(a, b, device=dev)
     vecs, frags = [], []
@@ -54,10 +75,10 @@ def _pack_layers(layers, hp: HParams, CL: int, dev):
         assert w_x.shape[0] % 16 == 0
         vecs.append(torch.cat([lw["norm"], lw["conv_w"][0].reshape(-1), lw["conv_b"][0], lw["w_dt"][0].t().reshape(-1),
                                lw["dt_bias"][0], lw["A2"][0].reshape(-1), lw["D"][0]]))
-        f_in = [pack_fragments(w_in, torch.cat([ar(64 * r, 64 * r + 64), ar(di + 64 * r, di + 64 * r + 64)]), ar(0, D))
+        f_in = [pack_fragments(w_in, torch.cat([ar(dsl * r, dsl * r + dsl), ar(di + dsl * r, di + dsl * r + dsl)]), ar(0, D))
                 for r in range(CL)]
-        f_x = [pack_fragments(w_x, ar(0, w_x.shape[0]), ar(64 * r, 64 * r + 64)) for r in range(CL)]
-        f_o = [pack_fragments(w_out, ar(0, D), ar(64 * r, 64 * r + 64)) for r in range(CL)]
+        f_x = [pack_fragments(w_x, ar(0, w_x.shape[0]), ar(dsl * r, dsl * r + dsl)) for r in range(CL)]
+        f_o = [pack_fragments(w_out, ar(0, D), ar(dsl * r, dsl * r + dsl)) for r in range(CL)]
         frags.append(torch.cat([t.reshape(-1) for t in (*f_in, *f_x, *f_o)]))
     return torch.stack(vecs).contiguous(), torch.stack(frags).contiguous()
 
@@ -72,23 +93,31 @@ class FusedStack:
         hp = stack.hp
         if not eligible(hp, stack.mode):
             raise _lib.MtnError("the fused streaming kernel does not implement this stack")
-        self.hp, self.device = hp, stack.device
+        self.hp, self.device, self.stack = hp, stack.device, stack
         D = hp.d_model
         with torch.cuda.device(self.device):
             z = lambda n: torch.zeros(n, dtype=torch.float32, device=self.device)
             # head blob layout of the separator kernel; only norm_f is read in stack-only mode
             self.head = torch.cat([z(16 * D), z(D), z(D), stack.norm_f, z(16 * D)]).contiguous()
-            self.layer_vec, self.layer_frag = _pack_layers(stack.layers, hp, D // 32, self.device)
+        self._packed = {}    # dsl -> (layer_vec, layer_frag), packed on first use
 
-    def run(self, x: torch.Tensor, conv: torch.Tensor, ssm: torch.Tensor) -> torch.Tensor:
+    def packed(self, dsl: int):
+        if dsl not in self._packed:
+            with torch.cuda.device(self.device):
+                self._packed[dsl] = _pack_layers(self.stack.layers, self.hp, dsl, self.device)
+        return self._packed[dsl]
+
+    def run(self, x: torch.Tensor, conv: torch.Tensor, ssm: torch.Tensor, dsl: int | None = None) -> torch.Tensor:
         hp = self.hp
         B, F, D = x.shape
         di = hp.d_inner
         assert tuple(conv.shape) == (hp.n_mamba, B, 4, di) and conv.is_contiguous() and conv.dtype == torch.float32
+        dsl = dsl or channels_per_cta(B, D, F)
+        layer_vec, layer_frag = self.packed(dsl)
         out = torch.empty_like(x)
-        ops.stream_push(None, None, None, conv, ssm, None, self.head, None, None, self.layer_vec, self.layer_frag, B=B, F=F,
+        ops.stream_push(None, None, None, conv, ssm, None, self.head, None, None, layer_vec, layer_frag, B=B, F=F,
                         N=D, D=D, di=di, R=hp.dt_rank, n_spk=hp.n_spk, n_layers=hp.n_mamba, first=False,
-                        halo_strides=(4 * di, B * 4 * di), halo_rows=4, stack_x=x, stack_out=out)
+                        halo_strides=(4 * di, B * 4 * di), halo_rows=4, stack_x=x, stack_out=out, dsl=dsl)
         return out
 
 
@@ -96,34 +125,44 @@ class FusedPush:
     """Packed weights of the fused push for one engine; ``run`` launches one push."""
 
     def __init__(self, engine):
-        hp, w = engine.hp, engine.w
+        hp = engine.hp
         if not eligible(hp, engine.mode):
             raise _lib.MtnError("the fused streaming push does not implement this configuration")
-        self.hp, self.device = hp, engine.device
-        N, D, di, R = hp.enc_dim, hp.d_model, hp.d_inner, hp.dt_rank
-        CL = D // 32
-        self.CL = CL
-        dev = self.device
-        f32 = lambda planes: planes.float().sum(dim=0)           # hi + lo: exact, re-splits to the same planes
-        ar = lambda a, b: torch.arange(a, b, device=dev)
-        with torch.cuda.device(dev):
+        self.hp, self.device, self.w = hp, engine.device, engine.w
+        w = engine.w
+        with torch.cuda.device(self.device):
             self.head = torch.cat([w.w_enc.t().contiguous().reshape(-1), w.gamma, w.beta, w.norm_f,
                                    w.w_dec.reshape(-1)]).contiguous()
-            w_bot, w_mask = f32(w.w_bot), f32(w.w_mask)           # [D, N], [2N, D]
-            self.bot_frag = torch.stack([pack_fragments(w_bot, ar(32 * r, 32 * r + 32), ar(0, N)) for r in range(CL)]).contiguous()
-            self.mask_frag = torch.stack([pack_fragments(w_mask, ar(64 * r, 64 * r + 64), ar(0, D)) for r in range(CL)]).contiguous()
-            self.layer_vec, self.layer_frag = _pack_layers(w.layers, hp, CL, dev)
+        self._packed = {}    # dsl -> (bot_frag, mask_frag, layer_vec, layer_frag), packed on first use
+
+    def packed(self, dsl: int):
+        if dsl not in self._packed:
+            hp, w, dev = self.hp, self.w, self.device
+            N, D = hp.enc_dim, hp.d_model
+            CL = hp.d_inner // dsl
+            f32 = lambda planes: planes.float().sum(dim=0)
+            ar = lambda a, b: torch.arange(a, b, device=dev)
+            with torch.cuda.device(dev):
+                w_bot, w_mask = f32(w.w_bot), f32(w.w_mask)           # [D, N], [2N, D]
+                c = dsl // 2
+                bot = torch.stack([pack_fragments(w_bot, ar(c * r, c * r + c), ar(0, N)) for r in range(CL)]).contiguous()
+                mask = torch.stack([pack_fragments(w_mask, ar(dsl * r, dsl * r + dsl), ar(0, D)) for r in range(CL)]).contiguous()
+                self._packed[dsl] = (bot, mask) + _pack_layers(w.layers, hp, dsl, dev)
+        return self._packed[dsl]
 
     def run(self, chunk: torch.Tensor, in_tail: torch.Tensor, first: bool, halo: torch.Tensor, h: torch.Tensor,
-            ola_tail: torch.Tensor, timeline=None) -> torch.Tensor:
+            ola_tail: torch.Tensor, timeline=None, dsl: int | None = None) -> torch.Tensor:
         """``chunk`` [B, 8F] (first push of a stream: [B, 8F + 8]) -> a fresh ``est`` [B, 8F, 2].  Carried state, read and
         updated in place: ``in_tail`` [B, 8] (last samples of the previous chunk), ``halo`` [n_layers, B, 3, di], ``h``
-        [n_layers, 2, B, di, 16] (direction 0 is used), ``ola_tail`` [B, 2, 8]."""
+        [n_layers, 2, B, di, 16] (direction 0 is used), ``ola_tail`` [B, 2, 8].  ``dsl``: d_inner channels per CTA (None =
+        ``channels_per_cta(B, d_model)``)."""
         hp = self.hp
         B, n = chunk.shape
         F = n // 8 - (1 if first else 0)
+        dsl = dsl or channels_per_cta(B, hp.d_model, F)
+        bot_frag, mask_frag, layer_vec, layer_frag = self.packed(dsl)
         est = torch.empty((B, 8 * F, hp.n_spk), dtype=torch.float32, device=self.device)
-        ops.stream_push(chunk, in_tail, est, halo, h, ola_tail, self.head, self.bot_frag, self.mask_frag, self.layer_vec,
-                        self.layer_frag, B=B, F=F, N=hp.enc_dim, D=hp.d_model, di=hp.d_inner,
-                        R=hp.dt_rank, n_spk=hp.n_spk, n_layers=hp.n_mamba, first=first, timeline=timeline)
+        ops.stream_push(chunk, in_tail, est, halo, h, ola_tail, self.head, bot_frag, mask_frag, layer_vec,
+                        layer_frag, B=B, F=F, N=hp.enc_dim, D=hp.d_model, di=hp.d_inner,
+                        R=hp.dt_rank, n_spk=hp.n_spk, n_layers=hp.n_mamba, first=first, timeline=timeline, dsl=dsl)
         return est

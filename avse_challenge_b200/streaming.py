@@ -28,12 +28,14 @@ class StreamingSeparator:
     """``push(chunk [B, 8*F]) -> est [B, 8*F', n_spk]`` with F' = F (F - 1 for the very first chunk, whose first frame
     needs 16 samples); ``flush()`` returns the last 8 samples (the tail of the final frame)."""
 
-    def __init__(self, engine: SeparatorEngine, batch: int, use_graph: bool = True, fused: bool | None = None):
+    def __init__(self, engine: SeparatorEngine, batch: int, use_graph: bool = True, fused: bool | None = None,
+                 channels_per_cta: int | None = None):
         """``fused``: chunks of <= 32 frames go through the one-launch cluster kernel (``mtn_stream_push_fwd``) instead of
         the batch plan's ~100 launches.  None = whenever that kernel implements the configuration; True = require it."""
         if engine.hp.bidirectional:
             raise NotImplementedError("streaming needs a causal stack: construct the model with bidirectional=False")
         self.eng, self.batch, self.use_graph = engine, batch, use_graph
+        self.channels_per_cta = channels_per_cta    # fused push: 32 / 64 / 128 d_inner channels per CTA; None = by batch size
         hp, dev = engine.hp, engine.device
         can_fuse = stream_fused.eligible(hp, engine.mode) and not engine.fuse_norm
         if fused and not can_fuse:
@@ -92,7 +94,8 @@ class StreamingSeparator:
             if chunk.stride(1) != 1:
                 chunk = chunk.contiguous()
             with torch.cuda.device(self.eng.device):   # launches go to the engine's device, whatever the caller has current
-                est = self._fused.run(chunk, self.in_tail, not self.started, self._halo, self._h, self.state["ola_tail"])
+                est = self._fused.run(chunk, self.in_tail, not self.started, self._halo, self._h, self.state["ola_tail"],
+                                      dsl=self.channels_per_cta)
             self.started = True
             self.samples_in += n
             self.samples_out += 8 * L

@@ -303,7 +303,7 @@ int mtn_gate_planes_fwd(const float* og, const float* bo, const float* bg, void*
 
 /* ---- one-launch streaming push (ABI >= 7) ------------------------------------------------------------------------------
  * The whole causal separator for one chunk of F <= 32 frames per stream, as ONE kernel launch: a thread-block cluster of
- * d_model / 32 CTAs per stream (64 d_inner channels each), contractions on warp-level mma.sync with the same split-bf16
+ * 2 * d_model / dsl CTAs per stream (dsl = 32, 64 or 128 d_inner channels each), contractions on warp-level mma.sync with the same split-bf16
  * operand model as mtn_gemm_fwd.  Replaces, for short chunks, the reference's per-token `Mamba.step` + `inference_params`
  * caches (Mamba-TasNet/modules/mamba/bimamba.py:320-372, :374-404) under `MambaBlocksSequential.forward(x,
  * inference_params)` (modules/mamba_blocks.py:186-197) together with the Encoder / MaskNet / Decoder calls around the
@@ -314,9 +314,9 @@ int mtn_gate_planes_fwd(const float* og, const float* bo, const float* bg, void*
  *   head       fp32: w_enc^T [16][N] | cLN gamma [N] | beta [N] | norm_f [D] | w_dec [N][16]
  *   layer_vec  fp32 per layer: norm [D] | conv_w [di][4] | conv_b [di] | w_dt^T [R][di] | dt_bias [di] | A2 [di][16] | D [di]
  *   *_frag     mma.sync A-operand fragments, bf16: [cluster rank][16-column tile][k-step of 16][plane hi|lo][lane][8]:
- *              bot_frag (rank r: bottleneck rows 32r..32r+31), mask_frag (rank r: mask rows 64r..64r+63), per layer
- *              in_proj (rank r: rows 64r.. of x then di + 64r.. of z; K = D) | x_proj (rows dt|B|C padded to a multiple of
- *              16; K = channels 64r..64r+63) | out_proj (all D rows; K = channels 64r..64r+63) */
+ *              with c = dsl: bot_frag (rank r: bottleneck rows (c/2)r..), mask_frag (rank r: mask rows c*r..), per layer
+ *              in_proj (rank r: c rows from c*r of x, then c rows from di + c*r of z; K = D) | x_proj (rows dt|B|C padded to a
+ *              multiple of 16; K = channels c*r..c*r+c-1) | out_proj (all D rows; K = the same channels) */
 typedef struct {
     const float* mix;       /* [B][ld_mix]: this push's chunk, 8*F samples (first push: 8*F + 8) */
     float* in_tail;         /* in/out [B][8]: the last 8 samples of the previous chunk (the encoder window overlaps it);
@@ -347,10 +347,15 @@ typedef struct {
      * arguments (mix, in_tail, est, ola_tail, bot_frag, mask_frag) are then unused and may be NULL. */
     const float* stack_x;
     float* stack_out;
+    int dsl;                /* d_inner channels per CTA: 32, 64 or 128 (0 = 64).  Cluster size = 2 * D / dsl (2..16); the weight
+                               fragments must have been packed for the same value.  32: lowest latency; 128: most streams
+                               resident at once */
 } mtn_stream_push_args;
 
 int mtn_stream_push_fwd(const mtn_stream_push_args* args, mtn_stream_t stream);
 size_t mtn_sizeof_stream_push_args(void);
+/* dynamic shared memory per CTA for F frames, d_model D, dsl channels per CTA; 0 = no such kernel; a launch needs <= 227 KiB */
+size_t mtn_stream_push_smem_bytes(int F, int D, int dsl);
 
 const char* mtn_last_error_string(void);
 int mtn_abi_version(void);

@@ -155,3 +155,39 @@ def test_stack_decode_calls_take_the_one_launch_kernel_and_share_the_reference_c
         ip2.key_value_memory_dict[i] = tuple(t.clone() for t in ipa.key_value_memory_dict[i])
     last = net(x[:, pos - 20:], inference_params=ip2)
     assert rel_max(last.cpu(), full[:, pos - 20:].cpu()) <= 5e-5
+
+
+@pytest.mark.parametrize("name,B,frames,dsl", [("tiny", 2, 20, 32), ("tiny", 2, 9, 64), ("XS", 2, 20, 32), ("XS", 1, 32, 128),
+                                               ("S", 2, 20, 32), ("S", 3, 20, 128), ("S", 1, 2, 32), ("L", 1, 12, 128)])
+def test_fused_push_channels_per_cta_variants(name, B, frames, dsl):
+    """The same kernel cut 32 / 64 / 128 d_inner channels per CTA (cluster size 2 * d_model / dsl: 16-CTA clusters for the
+    lowest latency, 4-CTA clusters to keep many streams resident): each equals the one-shot forward and the oracle."""
+    hp = CONFIGS[name].causal()
+    sds = init_state_dicts(hp, 1234)
+    T = 8 * frames * 5 + 8
+    mix, src = synth_mixture(B, T, seed=7)
+    eng = SeparatorEngine(hp, sds, device=DEV, mode="fp32", use_graph=False)
+    one = eng(mix.to(DEV)).cpu()
+    st = StreamingSeparator(eng, B, use_graph=False, fused=True, channels_per_cta=dsl)
+    outs, pos = [], 0
+    for c in [8 * frames + 8] + [8 * frames] * 4:
+        outs.append(st.push(mix[:, pos:pos + c].contiguous().to(DEV)))
+        pos += c
+    outs.append(st.flush())
+    got = torch.cat(outs, dim=1).cpu()
+    err = rel_max(got, one)
+    with torch.no_grad():
+        ref = restate.separate(mix, sds, hp.n_mamba, scan_impl="c")
+    e2 = rel_max(got, ref)
+    print(f"{hp.name} dsl={dsl} B={B} F={frames}: vs one-shot {err:.3e}, vs oracle {e2:.3e}")
+    assert err <= 5e-5 and e2 <= 1e-3, (err, e2)
+
+
+def test_channels_per_cta_policy():
+    from avse_challenge_b200.stream_fused import channels_per_cta
+    assert channels_per_cta(1, 256) == 32 and channels_per_cta(4, 256) == 32       # 16-CTA clusters while all of them are resident
+    assert channels_per_cta(8, 256) == 64 and channels_per_cta(12, 256) == 64
+    assert channels_per_cta(16, 256) == 128 and channels_per_cta(32, 256) == 128 and channels_per_cta(64, 256) == 128
+    assert channels_per_cta(1, 512) == 64                                          # d_model 512: 32 would need 32 CTAs
+    assert channels_per_cta(32, 512, 32) == 64 and channels_per_cta(32, 512, 8) == 128   # shared memory decides at 32 frames
+    assert channels_per_cta(1, 64) == 32 and channels_per_cta(64, 64) == 64        # d_model 64: 128 would span both speakers
