@@ -5,7 +5,8 @@
 // This kernel runs the WHOLE push -- encoder + cLN + bottleneck, every Mamba block (Add -> RMSNorm -> in_proj -> causal
 // conv + SiLU -> x_proj -> dt_proj + softplus -> selective-scan steps -> gate -> out_proj), norm_f, mask, decoder
 // overlap-add -- as ONE launch: one thread-block CLUSTER per stream, the channels of d_inner cut over the CTAs of the
-// cluster (64 per CTA; cluster size = d_model / 32: 8 for the S recipe), weights streamed from L2 exactly once per CTA.
+// cluster (DSL = 32, 64 or 128 per CTA, a template parameter: clusters of 16 / 8 / 4 CTAs for the S recipe, picked by the
+// caller from the number of streams), weights streamed from L2 exactly once per CTA.
 //
 // Replaces, for chunks of <= 32 frames, the reference's token-at-a-time `Mamba.step` + `inference_params` caches
 // (Mamba-TasNet/modules/mamba/bimamba.py:320-372, caches :374-404) driven through `MambaBlocksSequential.forward(x,
@@ -18,10 +19,10 @@
 // k-step straight from L2 into registers) and the FRAMES are the N side (8 per tile: F = 20 costs 24 rows, not 32).
 // Everything else (norms, conv, dt_proj, the recurrence, overlap-add) is fp32 SIMT on shared memory.
 //
-// Cluster dataflow per block (rank r owns d_inner channels [64r, 64r+64) and d_model columns [32r, 32r+32)):
+// Cluster dataflow per block (rank r owns d_inner channels [DSL r, DSL r + DSL) and d_model columns [DSL/2 r, DSL/2 r + DSL/2)):
 //   [A] every CTA gathers the residual slices of all ranks -> RMSNorm of all rows -> in_proj (its x / z columns) -> conv +
-//   SiLU -> x_proj partial over its 64 channels [B] sum of the partials of all ranks -> dt_proj + softplus -> scan (its
-//   channels, 16 states, state in / out of the cache) -> gate -> out_proj partial over its 64 channels [C] sum of its 32
+//   SiLU -> x_proj partial over its channels [B] sum of the partials of all ranks -> dt_proj + softplus -> scan (its
+//   channels, 16 states, state in / out of the cache) -> gate -> out_proj partial over its channels [C] sum of its
 //   columns over all ranks, residual slice += that -> next block.
 // The three exchanges per block are reads of the peers' shared memory (DSMEM, ld.shared::cluster) behind a cluster barrier:
 // a first version that exchanged through global memory spent 2.2 us per dependent read of a line another SM had just
