@@ -20,6 +20,8 @@ __global__ void k(float* out, long long* cyc, float seed) {
     float2 h[8], e[8], b[8];
     for (int q = 0; q < 8; ++q) { h[q] = make_float2(seed * q, seed); e[q] = make_float2(0.999f - 0.01f * q * seed, 0.998f - 0.013f * q * seed); b[q] = make_float2(1e-3f * threadIdx.x + q * seed, 1e-3f * q + seed); }
     float s = seed;
+    float2 a2[8];
+    for (int q = 0; q < 8; ++q) a2[q] = make_float2(-0.01f * (2 * q + 1) * seed, -0.01f * (2 * q + 2) * seed);
     __syncthreads();
     long long t0 = clock64();
 #pragma unroll 1
@@ -72,6 +74,34 @@ __global__ void k(float* out, long long* cyc, float seed) {
             }
             if (T == 13) { const float2 sy = make_float2(y0.x + y1.x + y2.x + y3.x, y0.y + y1.y + y2.y + y3.y); sm[600 + (it & 15) * 32 + (threadIdx.x & 31)] = sy.x + sy.y; }
             s = s * 0.999f + (y0.x + y1.x + y2.x + y3.x + y0.y + y1.y + y2.y + y3.y) * 1e-30f;
+        } else if (T == 15) {  // the same step, software-pipelined the way the kernel is: the decay factors of step it+1 (8 FMUL2 + 16 MUFU)
+                               // do not depend on the state, so they are issued among the state updates of step it; two steps per
+                               // iteration so that no register moves are needed.  Nothing feeds back from y into the next step.
+            float4 Bv[4], Cv[4];
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                float2* cur = half ? b : e;     // e / b double as the (current, next) decay registers
+                float2* nxt = half ? e : b;
+                const int row = ((2 * it + half) & 15) * 32;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { Bv[q] = *reinterpret_cast<float4*>(&sm[row + 4 * q]); Cv[q] = *reinterpret_cast<float4*>(&sm[row + 16 + 4 * q]); }
+                const float sn = sm[512 + row + (threadIdx.x & 31)];
+                const float du = sm[768 + (row >> 1) + (threadIdx.x & 15)];
+                float2 y0 = make_float2(0.f, 0.f), y1 = y0, y2 = y0, y3 = y0;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    float2 x = fmul2(make_float2(sn, sn), a2[q]);
+                    x.x = ex2a(x.x); x.y = ex2a(x.y);
+                    nxt[q] = x;
+                    const float2 bq = (q & 1) ? make_float2(Bv[q >> 1].z, Bv[q >> 1].w) : make_float2(Bv[q >> 1].x, Bv[q >> 1].y);
+                    const float2 cq = (q & 1) ? make_float2(Cv[q >> 1].z, Cv[q >> 1].w) : make_float2(Cv[q >> 1].x, Cv[q >> 1].y);
+                    h[q] = ffma2(cur[q], h[q], fmul2(make_float2(du, du), bq));
+                    if ((q & 3) == 0) y0 = ffma2(h[q], cq, y0); else if ((q & 3) == 1) y1 = ffma2(h[q], cq, y1);
+                    else if ((q & 3) == 2) y2 = ffma2(h[q], cq, y2); else y3 = ffma2(h[q], cq, y3);
+                }
+                const float2 sy = make_float2(y0.x + y1.x + y2.x + y3.x, y0.y + y1.y + y2.y + y3.y);
+                sm[600 + ((row >> 1) & 127) + (threadIdx.x & 31)] = sy.x + sy.y;
+            }
         } else if (T == 8) {   // FFMA2 with an immediate-like constant third operand: h = e*h + const
 #pragma unroll
             for (int r = 0; r < 2; ++r)
@@ -128,6 +158,7 @@ int main() {
     run<12>("step + 8 LDS.128 + 1 LDS (57) again", 57);
     run<13>("step + 8 LDS.128 + 1 LDS + y reduce + STS (~62)", 62);
     run<14>("16 FFMA2 d=a*b+c, d distinct", 16);
+    run<15>("2 pipelined steps + LDS + y reduce + STS (~124)", 124);
     cudaError_t e = cudaGetLastError(); if (e != cudaSuccess) printf("CUDA error %s\n", cudaGetErrorString(e));
     return 0;
 }
