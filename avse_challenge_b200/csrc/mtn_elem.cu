@@ -235,7 +235,11 @@ __device__ __forceinline__ float4 load_x4<__nv_bfloat16>(const __nv_bfloat16* p)
 
 constexpr int CONV_TT = 32;
 
-template <int P, typename XT, int DIRS>   // DIRS: 3 = both directions, 1 = forward only (compile time: keeps the hot both-direction code branch-free)
+// NX rows are requested together per iteration: 8 for both directions from fp32 rows (128 B in flight per thread).  Measured on
+// B200 at BASELINE config 2 (tools/conv_bench.py, profiles/r02/conv_variants_S_fp32.jsonl, all bit-identical): (time tile, NX) =
+// (32, 4) 0.158 ms = 76 % of the HBM peak, **(32, 8) 0.142 ms = 85 %**, (64, 8) 0.143, (128, 8) 0.148, (24, 12) 0.150, (32, 16)
+// 0.178 (182 registers).
+template <int P, typename XT, int DIRS, int NX = (DIRS == 3 && sizeof(XT) == 4) ? 8 : 4>   // DIRS: 3 = both directions, 1 = forward only (compile time: keeps the hot both-direction code branch-free)
 __global__ void __launch_bounds__(256)
 conv_silu_kernel(const XT* __restrict__ xz, int ldxz, const float* __restrict__ conv_w, const float* __restrict__ conv_b,
                  __nv_bfloat16* __restrict__ u, size_t u_rows, const float* __restrict__ halo_lo,
@@ -277,12 +281,12 @@ conv_silu_kernel(const XT* __restrict__ xz, int ldxz, const float* __restrict__ 
     };
     // window w[i] = x[t - 3 + i], i = 0..6
     float4 w0 = ld(t0 - 3), w1 = ld(t0 - 2), w2 = ld(t0 - 1), w3 = ld(t0), w4 = ld(t0 + 1), w5 = ld(t0 + 2), w6;
-    for (int t = t0; t < t1; t += 4) {
-        float4 nx[4];
+    for (int t = t0; t < t1; t += NX) {
+        float4 nx[NX];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) nx[i] = ld(t + 3 + i);
+        for (int i = 0; i < NX; ++i) nx[i] = ld(t + 3 + i);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < NX; ++i) {
             w6 = nx[i];
             if (t + i < t1) {
                 float4 f, r;
@@ -311,7 +315,11 @@ conv_silu_kernel(const XT* __restrict__ xz, int ldxz, const float* __restrict__ 
 // kernel above moves 8 bytes per access there and reached only 2.1 TB/s at BASELINE config 3).  One direction per CTA
 // (blockIdx.z: low bit = direction when both are requested) keeps the register footprint at 32 weights + a 4-row fp32
 // window; the second read of xs hits L1/L2.  Same fmaf nesting as conv_silu_kernel -> identical results.
-constexpr int CONV8_TT = 32;
+// Time tile 64: the per-CTA start-up (32 weight rows, bias, three halo rows per thread) is paid half as often as with 32 rows.
+// Measured on B200 (L hparams, 64 x 3999, profiles/r02/conv_variants_L_bf16.jsonl, bit-identical): 32 rows 0.411 ms, **64 rows
+// 0.381 ms** (63 % of the HBM peak; ncu: issue 59 %, ALU pipe 46 %, 16 resident warps per SM at 128 registers); 16 rows in flight
+// instead of 8 (184 registers) 0.73 ms, double-buffered row blocks 0.39 ms -- neither the bytes in flight nor load latency bound it.
+constexpr int CONV8_TT = 64;
 
 __device__ __forceinline__ void unpack_bf16x8(const uint4 raw, float (&v)[8]) {
     const uint32_t r[4] = {raw.x, raw.y, raw.z, raw.w};

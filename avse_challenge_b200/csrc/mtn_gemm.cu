@@ -48,10 +48,16 @@ struct GemmParams {
 // own 128 rows of A and HALF of the B tile per k-block, so a stage is 2/3 of the one-CTA stage (64 KB instead of 96 KB at
 // P = 2, BN = 256: three stages instead of two) and each SM pulls a third less operand data through the crossbar -- the
 // wide fp32-mode GEMMs sat at 55 % / 72 % tensor-pipe utilisation with a two-deep ring (profiles/r01/gemm_ncu_metrics.txt).
-template <int P, int BN, int CG = 1>
+// BKT = K extent of one pipeline stage: 64 (rows of 128 B, SWIZZLE_128B) or 32 (rows of 64 B, SWIZZLE_64B).  Half-depth stages
+// make the ring twice as deep in the same shared memory: at P = 2, BN = 256 a 64-deep stage is 96 KB, so only two fit and the
+// TMA request for k-block k + 2 goes out when k-block k retires -- one k-block (1 536 tensor-pipe cycles) before its data is
+// needed, less than a 96 KB load takes under load (in_proj: tensor pipe 55 % active).  With 32-deep stages (48 KB, four of them)
+// the request leads by three stages.
+template <int P, int BN, int CG = 1, int BKT = BK>
 struct GemmCfg {
-    static constexpr int A_BYTES = BM * BK * 2;
-    static constexpr int B_BYTES = (BN / CG) * BK * 2;       // bytes of B this CTA stages per plane
+    static_assert(BKT == 64 || BKT == 32, "stage depth: 64 (SWIZZLE_128B) or 32 (SWIZZLE_64B) bf16 elements");
+    static constexpr int A_BYTES = BM * BKT * 2;
+    static constexpr int B_BYTES = (BN / CG) * BKT * 2;      // bytes of B this CTA stages per plane
     static constexpr int STAGE_BYTES = P * (A_BYTES + B_BYTES);
     static constexpr int STAGING_BYTES = EPI_WARPS * 32 * STG_LD * 4;
     static constexpr int BAR_BYTES = 256;
@@ -65,11 +71,11 @@ struct GemmCfg {
     static_assert(B_BYTES % 1024 == 0, "B tile must keep 1024B alignment for SWIZZLE_128B");
 };
 
-template <int P, int BN, int EPI, bool OUT_BF16, int CG = 1>
+template <int P, int BN, int EPI, bool OUT_BF16, int CG = 1, int BKT = BK>
 __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                     const GemmParams p) {
-    using Cfg = GemmCfg<P, BN, CG>;
+    using Cfg = GemmCfg<P, BN, CG, BKT>;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-B align inside the shared window without leaving the shared address space (keeps LDS/STS)
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -107,7 +113,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int kblocks = p.K / BK;
+    const int kblocks = p.K / BKT;
     // CG 2: the tile loop runs over PAIR tiles of 256 rows; CTA `crank` owns rows [mt * 256 + crank * 128, +128)
     const int tiles_m = CG == 2 ? (p.tiles_m + 1) / 2 : p.tiles_m;
     const int tiles_per_group = tiles_m * p.tiles_n;
@@ -135,11 +141,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
 #pragma unroll
                     for (int pl = 0; pl < P; ++pl) {
                         if (CG == 2) {
-                            tma_load_3d_2sm(sa + pl * Cfg::A_BYTES, &mapA, &full_bar[stage], g * p.K + kb * BK, arow, pl);
-                            tma_load_3d_2sm(sb + pl * Cfg::B_BYTES, &mapB, &full_bar[stage], kb * BK, brow, pl);
+                            tma_load_3d_2sm(sa + pl * Cfg::A_BYTES, &mapA, &full_bar[stage], g * p.K + kb * BKT, arow, pl);
+                            tma_load_3d_2sm(sb + pl * Cfg::B_BYTES, &mapB, &full_bar[stage], kb * BKT, brow, pl);
                         } else {
-                            tma_load_3d(sa + pl * Cfg::A_BYTES, &mapA, &full_bar[stage], g * p.K + kb * BK, arow, pl);
-                            tma_load_3d(sb + pl * Cfg::B_BYTES, &mapB, &full_bar[stage], kb * BK, brow, pl);
+                            tma_load_3d(sa + pl * Cfg::A_BYTES, &mapA, &full_bar[stage], g * p.K + kb * BKT, arow, pl);
+                            tma_load_3d(sb + pl * Cfg::B_BYTES, &mapB, &full_bar[stage], kb * BKT, brow, pl);
                         }
                     }
                     if (++stage == Cfg::STAGES) {
@@ -168,17 +174,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                     const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
                     const uint32_t sb = sa + P * Cfg::A_BYTES;
 #pragma unroll
-                    for (int kk = 0; kk < BK / 16; ++kk) {
-                        const uint64_t a_hi = make_smem_desc_sw128(sa + kk * 32);
-                        const uint64_t b_hi = make_smem_desc_sw128(sb + kk * 32);
+                    for (int kk = 0; kk < BKT / 16; ++kk) {
+                        auto make_desc = [](uint32_t addr) { return BKT == 64 ? make_smem_desc_sw128(addr) : make_smem_desc_sw64(addr); };
+                        const uint64_t a_hi = make_desc(sa + kk * 32);
+                        const uint64_t b_hi = make_desc(sb + kk * 32);
                         auto mma = [&](uint64_t da, uint64_t db, uint32_t accum) {
                             if (CG == 2) tc_mma_bf16_2sm(d_tmem, da, db, idesc, accum);
                             else tc_mma_bf16(d_tmem, da, db, idesc, accum);
                         };
                         mma(a_hi, b_hi, (kb | kk) != 0 ? 1u : 0u);
                         if (P == 2) {
-                            const uint64_t a_lo = make_smem_desc_sw128(sa + Cfg::A_BYTES + kk * 32);
-                            const uint64_t b_lo = make_smem_desc_sw128(sb + Cfg::B_BYTES + kk * 32);
+                            const uint64_t a_lo = make_desc(sa + Cfg::A_BYTES + kk * 32);
+                            const uint64_t b_lo = make_desc(sb + Cfg::B_BYTES + kk * 32);
                             mma(a_lo, b_hi, 1u);
                             mma(a_hi, b_lo, 1u);
                         }
@@ -428,23 +435,24 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     }
 }
 
-template <int P, int BN, int EPI, bool OUT_BF16, int CG = 1>
+template <int P, int BN, int EPI, bool OUT_BF16, int CG = 1, int BKT = BK>
 static int launch_gemm(const mtn_gemm_args* a, cudaStream_t stream) {
-    using Cfg = GemmCfg<P, BN, CG>;
+    using Cfg = GemmCfg<P, BN, CG, BKT>;
+    constexpr CUtensorMapSwizzle swz = BKT == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     CUtensorMap mapA, mapB;
     {
         uint64_t dims[3] = {(uint64_t)a->lda, (uint64_t)a->a_rows, (uint64_t)P};
         uint64_t str[2] = {(uint64_t)a->lda * 2, (uint64_t)a->a_rows * a->lda * 2};
-        uint32_t box[3] = {BK, BM, 1};
-        if (!encode_tmap(&mapA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, a->a, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B))
+        uint32_t box[3] = {BKT, BM, 1};
+        if (!encode_tmap(&mapA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, a->a, dims, str, box, swz))
             return MTN_ECUDA;
     }
     {
         uint64_t rows = (uint64_t)a->groups * a->N;
         uint64_t dims[3] = {(uint64_t)a->K, rows, (uint64_t)P};
         uint64_t str[2] = {(uint64_t)a->K * 2, rows * a->K * 2};
-        uint32_t box[3] = {BK, BN / CG, 1};
-        if (!encode_tmap(&mapB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, a->w, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B))
+        uint32_t box[3] = {BKT, BN / CG, 1};
+        if (!encode_tmap(&mapB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, a->w, dims, str, box, swz))
             return MTN_ECUDA;
     }
     GemmParams p;
@@ -468,7 +476,7 @@ static int launch_gemm(const mtn_gemm_args* a, cudaStream_t stream) {
     p.rowsq_parts = a->rowsq_parts;
     p.tiles_m = (a->M + BM - 1) / BM;
     p.tiles_n = a->N / BN;
-    auto kern = gemm_tcgen05_kernel<P, BN, EPI, OUT_BF16, CG>;
+    auto kern = gemm_tcgen05_kernel<P, BN, EPI, OUT_BF16, CG, BKT>;
     static std::atomic<unsigned long long> attr_done{0};   // per template instantiation, one bit per device
     if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(kern), Cfg::SMEM_BYTES, attr_done, "gemm")) return rc;
     int cap = a->max_ctas > 0 ? a->max_ctas : num_sms();
@@ -522,6 +530,12 @@ static bool use_cta_pairs(const mtn_gemm_args* a, int bn) {
     return pair_tiles >= cap / 2;
 }
 
+// MTN_GEMM_HALF_STAGES = 0 in the environment: keep 64-deep stages everywhere (A/B runs of tools/gemm_bench.py).
+static bool half_depth_stages() {
+    if (const char* v = getenv("MTN_GEMM_HALF_STAGES")) return atoi(v) != 0;
+    return true;
+}
+
 template <int P, int BN>
 static int dispatch_epi(const mtn_gemm_args* a, cudaStream_t s) {
     if (BN == 256 && use_cta_pairs(a, BN)) {
@@ -529,6 +543,11 @@ static int dispatch_epi(const mtn_gemm_args* a, cudaStream_t s) {
         if (a->epilogue == MTN_EPI_INPROJ && !a->out_bf16) return launch_gemm<P, BN, MTN_EPI_INPROJ, false, 2>(a, s);
         if (a->epilogue == MTN_EPI_INPROJ && a->out_bf16) return launch_gemm<P, BN, MTN_EPI_INPROJ, true, 2>(a, s);
         if (a->epilogue == MTN_EPI_MASK && !a->out_bf16) return launch_gemm<P, BN, MTN_EPI_MASK, false, 2>(a, s);
+    }
+    if (P == 2 && BN == 256 && half_depth_stages()) {   // 96 KB stages: only two fit (see GemmCfg)
+        if (a->epilogue == MTN_EPI_STORE && !a->out_bf16) return launch_gemm<P, BN, MTN_EPI_STORE, false, 1, 32>(a, s);
+        if (a->epilogue == MTN_EPI_INPROJ && !a->out_bf16) return launch_gemm<P, BN, MTN_EPI_INPROJ, false, 1, 32>(a, s);
+        if (a->epilogue == MTN_EPI_MASK && !a->out_bf16) return launch_gemm<P, BN, MTN_EPI_MASK, false, 1, 32>(a, s);
     }
     if (a->epilogue == MTN_EPI_STORE && !a->out_bf16) return launch_gemm<P, BN, MTN_EPI_STORE, false>(a, s);
     if (BN <= 64) {

@@ -218,6 +218,13 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr) {
            (uint64_t(1) << 46) | (uint64_t(2) << 61);
 }
 
+// The same for rows of 64 B with the 64-byte swizzle (a TMA SWIZZLE_64B box of 32 bf16 x rows): 8-row groups are 512 B apart,
+// layout = 4 (SWIZZLE_64B); the tile base must be 512-byte aligned.
+__device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t saddr) {
+    return uint64_t((saddr & 0x3FFFF) >> 4) | (uint64_t(1) << 16) | (uint64_t(512 >> 4) << 32) |
+           (uint64_t(1) << 46) | (uint64_t(4) << 61);
+}
+
 // ---------------------------------------------------------------- small math helpers
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;

@@ -6,12 +6,15 @@ import argparse, json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from avse_challenge_b200 import CONFIGS, ops, _lib
+if os.environ.get("MTN_LIB"):   # dev knob of this tool only: time an experimental build of the library
+    _lib.LIB_PATH = os.path.abspath(os.environ["MTN_LIB"])
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--hparams", default="S"); ap.add_argument("--batch", type=int, default=32)
 ap.add_argument("--L", type=int, default=3999); ap.add_argument("--mode", default="fp32")
 ap.add_argument("--iters", type=int, default=20); ap.add_argument("--only", default="")
 ap.add_argument("--ab", action="store_true", help="time every case with MTN_GEMM_2CTA=0 (one CTA per tile) and =2 (CTA pairs wherever the shape allows) and compare the outputs")
+ap.add_argument("--ab-stages", action="store_true", help="time every case with MTN_GEMM_HALF_STAGES=0 (64-deep stages) and =1 (32-deep stages where the dispatcher uses them) and compare the outputs")
 a = ap.parse_args()
 hp = CONFIGS[a.hparams]; D, N, di, R = hp.d_model, hp.enc_dim, hp.d_inner, hp.dt_rank; nd = ops.n_dbl_for(R)
 P = 2 if a.mode == "fp32" else 1
@@ -42,8 +45,11 @@ for name, (A, W, m, n, k, kw, nbytes) in cases.items():
         continue
     run = lambda: ops.gemm(A, W, m, n, k, **kw)
     ref_out = None
-    for pairs in (("0", "2") if a.ab else (os.environ.get("MTN_GEMM_2CTA", "1"),)):
-        os.environ["MTN_GEMM_2CTA"] = pairs          # read by the library at every call
+    for pairs in (("0", "2") if a.ab else ("s0", "s1") if a.ab_stages else (os.environ.get("MTN_GEMM_2CTA", "1"),)):
+        if pairs.startswith("s"):
+            os.environ["MTN_GEMM_HALF_STAGES"] = pairs[1]   # read by the library at every call
+        else:
+            os.environ["MTN_GEMM_2CTA"] = pairs          # read by the library at every call
         kw["out"].zero_()
         for _ in range(3): run()
         torch.cuda.synchronize()
