@@ -53,13 +53,14 @@ struct GemmParams {
 // TMA request for k-block k + 2 goes out when k-block k retires -- one k-block (1 536 tensor-pipe cycles) before its data is
 // needed, less than a 96 KB load takes under load (in_proj: tensor pipe 55 % active).  With 32-deep stages (48 KB, four of them)
 // the request leads by three stages.
-template <int P, int BN, int CG = 1, int BKT = BK>
+template <int P, int BN, int CG = 1, int BKT = BK, int EW = EPI_WARPS>
 struct GemmCfg {
+    static_assert(EW == 8 || EW == 16, "epilogue warps: two or four per TMEM lane quarter");
     static_assert(BKT == 64 || BKT == 32, "stage depth: 64 (SWIZZLE_128B) or 32 (SWIZZLE_64B) bf16 elements");
     static constexpr int A_BYTES = BM * BKT * 2;
     static constexpr int B_BYTES = (BN / CG) * BKT * 2;      // bytes of B this CTA stages per plane
     static constexpr int STAGE_BYTES = P * (A_BYTES + B_BYTES);
-    static constexpr int STAGING_BYTES = EPI_WARPS * 32 * STG_LD * 4;
+    static constexpr int STAGING_BYTES = EW * 32 * STG_LD * 4;
     static constexpr int BAR_BYTES = 256;
     static constexpr int BUDGET = 227 * 1024 - 1024 - STAGING_BYTES - BAR_BYTES;
     static constexpr int STAGES_RAW = BUDGET / STAGE_BYTES;
@@ -71,11 +72,13 @@ struct GemmCfg {
     static_assert(B_BYTES % 1024 == 0, "B tile must keep 1024B alignment for SWIZZLE_128B");
 };
 
-template <int P, int BN, int EPI, bool OUT_BF16, int CG = 1, int BKT = BK>
-__global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
+template <int P, int BN, int EPI, bool OUT_BF16, int CG = 1, int BKT = BK, int EW = EPI_WARPS>
+__global__ void __launch_bounds__(64 + 32 * EW, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                     const GemmParams p) {
-    using Cfg = GemmCfg<P, BN, CG, BKT>;
+    using Cfg = GemmCfg<P, BN, CG, BKT, EW>;
+    constexpr int ESPLIT = EW / 4;   // epilogue warps per TMEM lane quarter: each takes every ESPLIT-th 16-column chunk
+    static_assert(EPI != MTN_EPI_RESADD || EW == 8, "the row-sum planes of the resadd epilogue are laid out for two warps per quarter");
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-B align inside the shared window without leaving the shared address space (keeps LDS/STS)
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -86,7 +89,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     uint64_t* tempty_bar = tfull_bar + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = __shfl_sync(0xffffffffu, int(threadIdx.x >> 5), 0);   // warp-uniform for the compiler too (role / chunk tests)
     const int lane = threadIdx.x & 31;
     const int crank = CG == 2 ? int(cluster_ctarank()) : 0;   // 0 = the pair's leader (issues the MMAs)
 
@@ -99,7 +102,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull_bar[a], 1);
-            mbar_init(&tempty_bar[a], CG * EPI_WARPS);  // one arrive per epilogue warp (CG 2: of both CTAs, on the leader's)
+            mbar_init(&tempty_bar[a], CG * EW);  // one arrive per epilogue warp (CG 2: of both CTAs, on the leader's)
         }
         fence_barrier_init();
     }
@@ -265,13 +268,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             }
             float4 auxn[4];  // RESADD: residual rows of the warp's next chunk, requested one chunk ahead
             if (EPI == MTN_EPI_RESADD) load_res(auxn, row0, nt * BN + 16 * chalf);
+            // Control flow below is warp-uniform on purpose (chunk index, activation / dt-column tests per CHUNK, row validity
+            // only as a predicate on the memory accesses): per-lane `if (row < M) { ... }` / `if (col >= split)` blocks had cost
+            // ~15 branch / convergence-barrier / predicate instructions per 16-byte store (ncu source page, in_proj: 3.5 M BRA,
+            // 2.4 M BSSY + 2.4 M BSYNC, 2.6 M ISETP, 2.3 M R2UR for 1.0 M STG), in warps that run latency-bound.  Rows past M hold
+            // zeros (TMA zero-fills the A rows, guarded aux loads return zeros), so computing them is harmless.
+            constexpr int NCH = BN / 16;
 #pragma unroll
-            for (int c0 = 0; c0 < BN; c0 += 16) {
-                if (((c0 >> 4) & 1) != chalf) continue;
+            for (int j = 0; j < (NCH + ESPLIT - 1) / ESPLIT; ++j) {
+                const int ch = j * ESPLIT + chalf;      // this warp's j-th 16-column chunk
+                if (NCH % ESPLIT != 0 && ch >= NCH) break;
+                const int c0 = ch * 16;
                 uint32_t v[16];
                 tmem_ld_x16(t_base + c0, v);
                 tmem_ld_wait();
-                if (c0 + 32 >= BN) {
+                if (ch + ESPLIT >= NCH) {
                     // last TMEM read of this accumulator by this warp: hand it back to the MMA warp early
                     tc_fence_before();
                     __syncwarp();
@@ -280,20 +291,24 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                 }
                 // registers (thread = row) -> padded smem
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    *reinterpret_cast<float4*>(&stg[lane * STG_LD + 4 * j]) =
-                        make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
-                                    __uint_as_float(v[4 * j + 3]));
+                for (int jj = 0; jj < 4; ++jj)
+                    *reinterpret_cast<float4*>(&stg[lane * STG_LD + 4 * jj]) =
+                        make_float4(__uint_as_float(v[4 * jj]), __uint_as_float(v[4 * jj + 1]), __uint_as_float(v[4 * jj + 2]),
+                                    __uint_as_float(v[4 * jj + 3]));
                 __syncwarp();
                 // smem -> global, row-contiguous: 4 lanes cover one 64-byte row segment, 8 rows per pass
                 const int rsub = lane >> 2;
                 const int c4 = lane & 3;
-                const int gcol = nt * BN + c0 + c4 * 4;  // column within the group's N
+                const int ccol = nt * BN + c0;           // first column of the chunk within the group's N (warp-uniform)
+                const int gcol = ccol + c4 * 4;
+                const bool chunk_flag = EPI == MTN_EPI_INPROJ ? ccol >= p.epi_param      // SiLU half (split is a multiple of 16)
+                                      : EPI == MTN_EPI_XPROJ ? ccol < p.epi_param        // dt columns (RP = 16 or 32)
+                                                             : false;
                 float4 aux[4];
                 if (EPI == MTN_EPI_RESADD) {
 #pragma unroll
                     for (int it = 0; it < 4; ++it) aux[it] = auxn[it];
-                    if (c0 + 32 < BN) load_res(auxn, row0, nt * BN + c0 + 32);
+                    if (ch + ESPLIT < NCH) load_res(auxn, row0, ccol + 16 * ESPLIT);
                 }
                 if (EPI == MTN_EPI_MASK) {  // issue the four mix_w loads together (they were the epilogue's critical path)
 #pragma unroll
@@ -308,97 +323,98 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                 for (int it = 0; it < 4; ++it) {
                     const int rr = it * 8 + rsub;
                     const int grow = row0 + rr;
+                    const bool ok = grow < p.M;
                     float4 f = *reinterpret_cast<const float4*>(&stg[rr * STG_LD + c4 * 4]);
-                    if (grow < p.M) {
-                        if (p.rowsq) {  // RMSNorm of the A operand's rows, applied after the contraction
-                            f.x *= rstd[it];
-                            f.y *= rstd[it];
-                            f.z *= rstd[it];
-                            f.w *= rstd[it];
+                    if (p.rowsq) {  // RMSNorm of the A operand's rows, applied after the contraction
+                        f.x *= rstd[it];
+                        f.y *= rstd[it];
+                        f.z *= rstd[it];
+                        f.w *= rstd[it];
+                    }
+                    if (EPI == MTN_EPI_RESADD) {
+                        f.x += aux[it].x;
+                        f.y += aux[it].y;
+                        f.z += aux[it].z;
+                        f.w += aux[it].w;
+                        // the planes of the updated residual: A operand of the next in_proj / mask GEMM
+                        __nv_bfloat16* pr = p.out2 + size_t(grow) * p.ldo2 + gcol;
+                        __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
+                        if (P == 2) {
+                            split_bf16(f.x, h0, l0);
+                            split_bf16(f.y, h1, l1);
+                            split_bf16(f.z, h2, l2);
+                            split_bf16(f.w, h3, l3);
+                        } else {
+                            h0 = __float2bfloat16_rn(f.x);
+                            h1 = __float2bfloat16_rn(f.y);
+                            h2 = __float2bfloat16_rn(f.z);
+                            h3 = __float2bfloat16_rn(f.w);
                         }
-                        if (EPI == MTN_EPI_RESADD) {
-                            f.x += aux[it].x;
-                            f.y += aux[it].y;
-                            f.z += aux[it].z;
-                            f.w += aux[it].w;
-                            // the planes of the updated residual: A operand of the next in_proj / mask GEMM
-                            __nv_bfloat16* pr = p.out2 + size_t(grow) * p.ldo2 + gcol;
+                        __nv_bfloat162 a2 = __halves2bfloat162(h0, h1), b2 = __halves2bfloat162(h2, h3);
+                        uint2 ph;
+                        ph.x = *reinterpret_cast<uint32_t*>(&a2);
+                        ph.y = *reinterpret_cast<uint32_t*>(&b2);
+                        if (ok) *reinterpret_cast<uint2*>(pr) = ph;
+                        if (P == 2) {
+                            __nv_bfloat162 c2 = __halves2bfloat162(l0, l1), d2 = __halves2bfloat162(l2, l3);
+                            uint2 pl;
+                            pl.x = *reinterpret_cast<uint32_t*>(&c2);
+                            pl.y = *reinterpret_cast<uint32_t*>(&d2);
+                            if (ok) *reinterpret_cast<uint2*>(pr + p.plane2) = pl;
+                        }
+                        sqacc[it] = fmaf(f.x, f.x, fmaf(f.y, f.y, fmaf(f.z, f.z, fmaf(f.w, f.w, sqacc[it]))));
+                    }
+                    if (EPI == MTN_EPI_INPROJ) {
+                        if (chunk_flag) {
+                            f.x = silu_sel<OUT_BF16>(f.x);   // bf16 output: 1-MUFU form (rounded to bf16 right below)
+                            f.y = silu_sel<OUT_BF16>(f.y);
+                            f.z = silu_sel<OUT_BF16>(f.z);
+                            f.w = silu_sel<OUT_BF16>(f.w);
+                        }
+                    } else if (EPI == MTN_EPI_RELU) {
+                        f.x = fmaxf(f.x, 0.f);
+                        f.y = fmaxf(f.y, 0.f);
+                        f.z = fmaxf(f.z, 0.f);
+                        f.w = fmaxf(f.w, 0.f);
+                    } else if (EPI == MTN_EPI_MASK) {
+                        f.x = fmaxf(f.x, 0.f) * aux[it].x;
+                        f.y = fmaxf(f.y, 0.f) * aux[it].y;
+                        f.z = fmaxf(f.z, 0.f) * aux[it].z;
+                        f.w = fmaxf(f.w, 0.f) * aux[it].w;
+                    }
+                    if (EPI == MTN_EPI_XPROJ) {
+                        // dt columns also go out as hi | lo bf16 planes: the B operand of the scan's dt_proj MMA
+                        if (chunk_flag) {
+                            __nv_bfloat16* drow = reinterpret_cast<__nv_bfloat16*>(const_cast<float*>(p.aux)) +
+                                                  (size_t(grow) * p.groups + g) * 2 * p.epi_param + gcol;
                             __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
-                            if (P == 2) {
-                                split_bf16(f.x, h0, l0);
-                                split_bf16(f.y, h1, l1);
-                                split_bf16(f.z, h2, l2);
-                                split_bf16(f.w, h3, l3);
-                            } else {
-                                h0 = __float2bfloat16_rn(f.x);
-                                h1 = __float2bfloat16_rn(f.y);
-                                h2 = __float2bfloat16_rn(f.z);
-                                h3 = __float2bfloat16_rn(f.w);
-                            }
+                            split_bf16(f.x, h0, l0);
+                            split_bf16(f.y, h1, l1);
+                            split_bf16(f.z, h2, l2);
+                            split_bf16(f.w, h3, l3);
                             __nv_bfloat162 a2 = __halves2bfloat162(h0, h1), b2 = __halves2bfloat162(h2, h3);
-                            uint2 ph;
+                            __nv_bfloat162 c2 = __halves2bfloat162(l0, l1), d2 = __halves2bfloat162(l2, l3);
+                            uint2 ph, pl;
                             ph.x = *reinterpret_cast<uint32_t*>(&a2);
                             ph.y = *reinterpret_cast<uint32_t*>(&b2);
-                            *reinterpret_cast<uint2*>(pr) = ph;
-                            if (P == 2) {
-                                __nv_bfloat162 c2 = __halves2bfloat162(l0, l1), d2 = __halves2bfloat162(l2, l3);
-                                uint2 pl;
-                                pl.x = *reinterpret_cast<uint32_t*>(&c2);
-                                pl.y = *reinterpret_cast<uint32_t*>(&d2);
-                                *reinterpret_cast<uint2*>(pr + p.plane2) = pl;
-                            }
-                            sqacc[it] = fmaf(f.x, f.x, fmaf(f.y, f.y, fmaf(f.z, f.z, fmaf(f.w, f.w, sqacc[it]))));
-                        }
-                        if (EPI == MTN_EPI_INPROJ) {
-                            if (gcol >= p.epi_param) {
-                                f.x = silu_sel<OUT_BF16>(f.x);   // bf16 output: 1-MUFU form (rounded to bf16 right below)
-                                f.y = silu_sel<OUT_BF16>(f.y);
-                                f.z = silu_sel<OUT_BF16>(f.z);
-                                f.w = silu_sel<OUT_BF16>(f.w);
-                            }
-                        } else if (EPI == MTN_EPI_RELU) {
-                            f.x = fmaxf(f.x, 0.f);
-                            f.y = fmaxf(f.y, 0.f);
-                            f.z = fmaxf(f.z, 0.f);
-                            f.w = fmaxf(f.w, 0.f);
-                        } else if (EPI == MTN_EPI_MASK) {
-                            f.x = fmaxf(f.x, 0.f) * aux[it].x;
-                            f.y = fmaxf(f.y, 0.f) * aux[it].y;
-                            f.z = fmaxf(f.z, 0.f) * aux[it].z;
-                            f.w = fmaxf(f.w, 0.f) * aux[it].w;
-                        }
-                        if (EPI == MTN_EPI_XPROJ) {
-                            // dt columns also go out as hi | lo bf16 planes: the B operand of the scan's dt_proj MMA
-                            if (gcol < p.epi_param) {
-                                __nv_bfloat16* drow = reinterpret_cast<__nv_bfloat16*>(const_cast<float*>(p.aux)) +
-                                                      (size_t(grow) * p.groups + g) * 2 * p.epi_param + gcol;
-                                __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
-                                split_bf16(f.x, h0, l0);
-                                split_bf16(f.y, h1, l1);
-                                split_bf16(f.z, h2, l2);
-                                split_bf16(f.w, h3, l3);
-                                __nv_bfloat162 a2 = __halves2bfloat162(h0, h1), b2 = __halves2bfloat162(h2, h3);
-                                __nv_bfloat162 c2 = __halves2bfloat162(l0, l1), d2 = __halves2bfloat162(l2, l3);
-                                uint2 ph, pl;
-                                ph.x = *reinterpret_cast<uint32_t*>(&a2);
-                                ph.y = *reinterpret_cast<uint32_t*>(&b2);
-                                pl.x = *reinterpret_cast<uint32_t*>(&c2);
-                                pl.y = *reinterpret_cast<uint32_t*>(&d2);
+                            pl.x = *reinterpret_cast<uint32_t*>(&c2);
+                            pl.y = *reinterpret_cast<uint32_t*>(&d2);
+                            if (ok) {
                                 *reinterpret_cast<uint2*>(drow) = ph;
                                 *reinterpret_cast<uint2*>(drow + p.epi_param) = pl;
                             }
                         }
-                        const size_t off = size_t(grow) * p.ldo + size_t(g) * p.out_group_stride + gcol;
-                        if (OUT_BF16) {
-                            __nv_bfloat162 lo2 = __floats2bfloat162_rn(f.x, f.y);
-                            __nv_bfloat162 hi2 = __floats2bfloat162_rn(f.z, f.w);
-                            uint2 pk;
-                            pk.x = *reinterpret_cast<uint32_t*>(&lo2);
-                            pk.y = *reinterpret_cast<uint32_t*>(&hi2);
-                            *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off) = pk;
-                        } else {
-                            *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off) = f;
-                        }
+                    }
+                    const size_t off = size_t(grow) * p.ldo + size_t(g) * p.out_group_stride + gcol;
+                    if (OUT_BF16) {
+                        __nv_bfloat162 lo2 = __floats2bfloat162_rn(f.x, f.y);
+                        __nv_bfloat162 hi2 = __floats2bfloat162_rn(f.z, f.w);
+                        uint2 pk;
+                        pk.x = *reinterpret_cast<uint32_t*>(&lo2);
+                        pk.y = *reinterpret_cast<uint32_t*>(&hi2);
+                        if (ok) *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off) = pk;
+                    } else {
+                        if (ok) *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off) = f;
                     }
                 }
                 __syncwarp();
@@ -435,9 +451,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     }
 }
 
-template <int P, int BN, int EPI, bool OUT_BF16, int CG = 1, int BKT = BK>
+template <int P, int BN, int EPI, bool OUT_BF16, int CG = 1, int BKT = BK, int EW = EPI_WARPS>
 static int launch_gemm(const mtn_gemm_args* a, cudaStream_t stream) {
-    using Cfg = GemmCfg<P, BN, CG, BKT>;
+    using Cfg = GemmCfg<P, BN, CG, BKT, EW>;
     constexpr CUtensorMapSwizzle swz = BKT == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     CUtensorMap mapA, mapB;
     {
@@ -476,7 +492,7 @@ static int launch_gemm(const mtn_gemm_args* a, cudaStream_t stream) {
     p.rowsq_parts = a->rowsq_parts;
     p.tiles_m = (a->M + BM - 1) / BM;
     p.tiles_n = a->N / BN;
-    auto kern = gemm_tcgen05_kernel<P, BN, EPI, OUT_BF16, CG, BKT>;
+    auto kern = gemm_tcgen05_kernel<P, BN, EPI, OUT_BF16, CG, BKT, EW>;
     static std::atomic<unsigned long long> attr_done{0};   // per template instantiation, one bit per device
     if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(kern), Cfg::SMEM_BYTES, attr_done, "gemm")) return rc;
     int cap = a->max_ctas > 0 ? a->max_ctas : num_sms();
@@ -487,7 +503,7 @@ static int launch_gemm(const mtn_gemm_args* a, cudaStream_t stream) {
         if (pairs < 1) pairs = 1;
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(2 * pairs, 1, 1);
-        cfg.blockDim = dim3(64 + 32 * EPI_WARPS, 1, 1);
+        cfg.blockDim = dim3(64 + 32 * EW, 1, 1);
         cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
         cfg.stream = stream;
         cudaLaunchAttribute attr[1];
@@ -506,7 +522,7 @@ static int launch_gemm(const mtn_gemm_args* a, cudaStream_t stream) {
     }
     int total = p.tiles_m * p.tiles_n * p.groups;
     int grid = total < cap ? total : cap;
-    kern<<<grid, 64 + 32 * EPI_WARPS, Cfg::SMEM_BYTES, stream>>>(mapA, mapB, p);
+    kern<<<grid, 64 + 32 * EW, Cfg::SMEM_BYTES, stream>>>(mapA, mapB, p);
     MTN_CUDA_LAUNCH_CHECK("gemm");
     return MTN_OK;
 }
@@ -530,10 +546,10 @@ static bool use_cta_pairs(const mtn_gemm_args* a, int bn) {
     return pair_tiles >= cap / 2;
 }
 
-// MTN_GEMM_HALF_STAGES = 0 in the environment: keep 64-deep stages everywhere (A/B runs of tools/gemm_bench.py).
-static bool half_depth_stages() {
-    if (const char* v = getenv("MTN_GEMM_HALF_STAGES")) return atoi(v) != 0;
-    return true;
+// MTN_GEMM_HALF_STAGES in the environment (A/B runs of tools/gemm_bench.py): see dispatch_epi.  Unset = -1 = the shipped rule.
+static int half_depth_stages() {
+    if (const char* v = getenv("MTN_GEMM_HALF_STAGES")) return atoi(v);
+    return -1;
 }
 
 template <int P, int BN>
@@ -544,10 +560,29 @@ static int dispatch_epi(const mtn_gemm_args* a, cudaStream_t s) {
         if (a->epilogue == MTN_EPI_INPROJ && a->out_bf16) return launch_gemm<P, BN, MTN_EPI_INPROJ, true, 2>(a, s);
         if (a->epilogue == MTN_EPI_MASK && !a->out_bf16) return launch_gemm<P, BN, MTN_EPI_MASK, false, 2>(a, s);
     }
-    if (P == 2 && BN == 256 && half_depth_stages()) {   // 96 KB stages: only two fit (see GemmCfg)
-        if (a->epilogue == MTN_EPI_STORE && !a->out_bf16) return launch_gemm<P, BN, MTN_EPI_STORE, false, 1, 32>(a, s);
-        if (a->epilogue == MTN_EPI_INPROJ && !a->out_bf16) return launch_gemm<P, BN, MTN_EPI_INPROJ, false, 1, 32>(a, s);
-        if (a->epilogue == MTN_EPI_MASK && !a->out_bf16) return launch_gemm<P, BN, MTN_EPI_MASK, false, 1, 32>(a, s);
+    if constexpr (P == 2 && BN == 256) {
+        // Mask GEMM (fp32 mode): its epilogue waits on four global mix_w loads per chunk, so it runs with sixteen epilogue warps
+        // (four per TMEM lane quarter) and, to make room for their staging buffers, half-depth stages: 0.195 -> 0.139 ms at
+        // BASELINE config 2 (profiles/r02/gemm_epilogue_variants_S_fp32.jsonl).  in_proj / bottleneck do not gain from either
+        // (0.201 -> 0.209 / 0.211 ms): MTN_GEMM_HALF_STAGES = 1 / 2 selects them there for A/B runs, 0 switches the mask rule off.
+        const int hs = half_depth_stages();
+        if (a->epilogue == MTN_EPI_MASK && !a->out_bf16 && hs != 0) return launch_gemm<P, BN, MTN_EPI_MASK, false, 1, 32, 16>(a, s);
+        if (hs == 2) {
+            if (a->epilogue == MTN_EPI_STORE && !a->out_bf16) return launch_gemm<P, BN, MTN_EPI_STORE, false, 1, 32, 16>(a, s);
+            if (a->epilogue == MTN_EPI_INPROJ && !a->out_bf16) return launch_gemm<P, BN, MTN_EPI_INPROJ, false, 1, 32, 16>(a, s);
+        } else if (hs == 1) {
+            if (a->epilogue == MTN_EPI_STORE && !a->out_bf16) return launch_gemm<P, BN, MTN_EPI_STORE, false, 1, 32>(a, s);
+            if (a->epilogue == MTN_EPI_INPROJ && !a->out_bf16) return launch_gemm<P, BN, MTN_EPI_INPROJ, false, 1, 32>(a, s);
+        }
+    }
+    if constexpr (P == 1 && BN == 256) {
+        // bf16 mode: 48 KB stages, three of them fit beside sixteen warps' staging buffers, and the output-heavy GEMMs are
+        // epilogue-bound there (one tensor pass per k-step): L hparams, 64 x 3999 (profiles/r02/gemm_ew16_L_bf16.jsonl), in_proj
+        // 0.563 -> 0.518 ms, mask 0.682 -> 0.446 ms, bit-identical.  MTN_GEMM_HALF_STAGES = 0 keeps eight warps (A/B runs).
+        if (half_depth_stages() != 0) {
+            if (a->epilogue == MTN_EPI_MASK && !a->out_bf16) return launch_gemm<P, BN, MTN_EPI_MASK, false, 1, 64, 16>(a, s);
+            if (a->epilogue == MTN_EPI_INPROJ && a->out_bf16) return launch_gemm<P, BN, MTN_EPI_INPROJ, true, 1, 64, 16>(a, s);
+        }
     }
     if (a->epilogue == MTN_EPI_STORE && !a->out_bf16) return launch_gemm<P, BN, MTN_EPI_STORE, false>(a, s);
     if (BN <= 64) {
@@ -619,7 +654,7 @@ extern "C" int mtn_gemm_fwd(const mtn_gemm_args* a, mtn_stream_t stream) {
     if (a->epilogue == MTN_EPI_MASK)
         MTN_REQUIRE(a->aux && a->epi_param > 0 && a->epi_param % 4 == 0 && a->ld_aux % 4 == 0,
                     "gemm: mask epilogue needs aux / enc_dim");
-    if (a->epilogue == MTN_EPI_INPROJ) MTN_REQUIRE(a->epi_param % 4 == 0, "gemm: inproj split must be a multiple of 4");
+    if (a->epilogue == MTN_EPI_INPROJ) MTN_REQUIRE(a->epi_param % 16 == 0, "gemm: inproj split must be a multiple of 16");
     if (a->rowsq) MTN_REQUIRE(a->rowsq_parts >= 1 && a->rowsq_parts <= 64, "gemm: rowsq_parts=%d", a->rowsq_parts);
     if (a->epilogue == MTN_EPI_RESADD)
         MTN_REQUIRE(a->out2 && a->rowsum && !a->out_bf16 && a->groups == 1 && a->ldo2 % 4 == 0 && a->a2_rows >= a->M &&

@@ -29,6 +29,8 @@ cases = {
     "in_proj": (planes(M, D), planes(2 * di, D), M, 2 * di, D,
                 dict(epilogue=_lib.EPI_INPROJ, epi_param=di, out_bf16=P == 1, out=torch.empty(M, 2 * di, device=dev, dtype=xz_dt)),
                 M * D * 2 * P + M * 2 * di * (4 if P == 2 else 2)),
+    "in_proj_plain_store": (planes(M, D), planes(2 * di, D), M, 2 * di, D,      # in_proj's shape without the SiLU epilogue (diagnostic)
+                            dict(out=torch.empty(M, 2 * di, device=dev)), M * D * 2 * P + M * 2 * di * 4),
     "x_proj": (planes(M, 2 * di), planes(2 * nd, di), M, nd, di,
                dict(groups=2, out_group_stride=nd, out=torch.empty(M, 2 * nd, device=dev)),
                M * 2 * di * 2 * P + M * 2 * nd * 4),
@@ -45,7 +47,7 @@ for name, (A, W, m, n, k, kw, nbytes) in cases.items():
         continue
     run = lambda: ops.gemm(A, W, m, n, k, **kw)
     ref_out = None
-    for pairs in (("0", "2") if a.ab else ("s0", "s1") if a.ab_stages else (os.environ.get("MTN_GEMM_2CTA", "1"),)):
+    for pairs in (("0", "2") if a.ab else ("s0", "s1", "s2") if a.ab_stages else (os.environ.get("MTN_GEMM_2CTA", "1"),)):
         if pairs.startswith("s"):
             os.environ["MTN_GEMM_HALF_STAGES"] = pairs[1]   # read by the library at every call
         else:
