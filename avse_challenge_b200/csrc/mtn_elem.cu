@@ -34,42 +34,67 @@ encoder_cln_kernel(const float* __restrict__ mix, const float* __restrict__ w_en
         g[j] = gamma[lane + 32 * j];
         bt[j] = beta[lane + 32 * j];
     }
-    for (size_t tok = size_t(blockIdx.x) * warps_per_block + (threadIdx.x >> 5); tok < tokens;
-         tok += size_t(gridDim.x) * warps_per_block) {
-        const int b = int(tok / L), l = int(tok % L);
-        const float4* xp = reinterpret_cast<const float4*>(mix + size_t(b) * ld_mix + size_t(l) * 8);
-        float x[16];
+    // TPI tokens per warp iteration: every filter tap fetched from shared memory is used TPI times (one token at a time the
+    // kernel was paced by its 16 x NJ scalar LDS per token: 0.109 ms at BASELINE config 2 against 0.04 ms of HBM time).
+    constexpr int TPI = NJ >= 16 ? 2 : 4;
+    const size_t groups = (tokens + TPI - 1) / TPI;
+    for (size_t grp = size_t(blockIdx.x) * warps_per_block + (threadIdx.x >> 5); grp < groups;
+         grp += size_t(gridDim.x) * warps_per_block) {
+        const size_t tok0 = grp * TPI;
+        float x[TPI][16];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const float4 f = __ldg(xp + q);
-            x[4 * q] = f.x;
-            x[4 * q + 1] = f.y;
-            x[4 * q + 2] = f.z;
-            x[4 * q + 3] = f.w;
+        for (int i = 0; i < TPI; ++i) {
+            const size_t tok = tok0 + i < tokens ? tok0 + i : tokens - 1;   // tail: recompute the last token, store nothing
+            const int b = int(tok / L), l = int(tok % L);
+            const float4* xp = reinterpret_cast<const float4*>(mix + size_t(b) * ld_mix + size_t(l) * 8);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 f = __ldg(xp + q);
+                x[i][4 * q] = f.x;
+                x[i][4 * q + 1] = f.y;
+                x[i][4 * q + 2] = f.z;
+                x[i][4 * q + 3] = f.w;
+            }
         }
-        float v[NJ];
-        float s = 0.f;
+        float v[TPI][NJ];
+        float s[TPI];
+#pragma unroll
+        for (int i = 0; i < TPI; ++i) s[i] = 0.f;
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
-            float acc = 0.f;
+            float acc[TPI];
 #pragma unroll
-            for (int k = 0; k < 16; ++k) acc = fmaf(s_w[k * N + lane + 32 * j], x[k], acc);
-            v[j] = fmaxf(acc, 0.f);
-            s += v[j];
+            for (int i = 0; i < TPI; ++i) acc[i] = 0.f;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const float w = s_w[k * N + lane + 32 * j];
+#pragma unroll
+                for (int i = 0; i < TPI; ++i) acc[i] = fmaf(w, x[i][k], acc[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < TPI; ++i) {
+                v[i][j] = fmaxf(acc[i], 0.f);
+                s[i] += v[i][j];
+            }
         }
-        const float mean = warp_sum(s) * (1.0f / N);
-        float sq = 0.f;
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) {
-            const float d = v[j] - mean;
-            sq = fmaf(d, d, sq);
-        }
-        const float rstd = rsqrtf(warp_sum(sq) * (1.0f / N) + eps);
+        for (int i = 0; i < TPI; ++i) {
+            const float mean = warp_sum(s[i]) * (1.0f / N);
+            float sq = 0.f;
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) {
-            const size_t off = tok * N + lane + 32 * j;
-            mix_w[off] = v[j];
-            store_planes1<P>(yn, plane_stride, off, fmaf(g[j] * (v[j] - mean), rstd, bt[j]));
+            for (int j = 0; j < NJ; ++j) {
+                const float d = v[i][j] - mean;
+                sq = fmaf(d, d, sq);
+            }
+            const float rstd = rsqrtf(warp_sum(sq) * (1.0f / N) + eps);
+            if (tok0 + i < tokens) {
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) {
+                    const size_t off = (tok0 + i) * N + lane + 32 * j;
+                    mix_w[off] = v[i][j];
+                    store_planes1<P>(yn, plane_stride, off, fmaf(g[j] * (v[i][j] - mean), rstd, bt[j]));
+                }
+            }
         }
     }
 }
@@ -448,36 +473,51 @@ decoder_frames_kernel(const float* __restrict__ sep, const float* __restrict__ w
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int warps_per_block = blockDim.x >> 5;
-    // one warp per (token, speaker)
-    for (size_t item = size_t(blockIdx.x) * warps_per_block + (threadIdx.x >> 5); item < items;
-         item += size_t(gridDim.x) * warps_per_block) {
-        const float* row = sep + item * N;  // sep[token][s*N + n] -> contiguous in (token, s)
-        float acc[16];
+    // One warp per PAIR of (token, speaker) rows: the filter taps are read from shared memory once for both, and the 2 x 16
+    // per-lane partial sums are reduced by a transposing butterfly (offsets 16, 8, 4, 2, 1; every step halves the values a lane
+    // keeps) -- 31 shuffles per pair instead of 80 per row, the same summation tree as a plain warp sum (bit-identical), and
+    // lane l ends up with tap l & 15 of row l >> 4: one coalesced 128-byte store.
+    const size_t pairs = (items + 1) / 2;
+    for (size_t pr = size_t(blockIdx.x) * warps_per_block + (threadIdx.x >> 5); pr < pairs;
+         pr += size_t(gridDim.x) * warps_per_block) {
+        const size_t item0 = 2 * pr;
+        const bool two = item0 + 1 < items;
+        const float* row0 = sep + item0 * N;  // sep[token][s*N + n] -> contiguous in (token, s)
+        const float* row1 = two ? row0 + N : row0;
+        float a0[16], a1[16];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) acc[k] = 0.f;
+        for (int k = 0; k < 16; ++k) a0[k] = a1[k] = 0.f;
 #pragma unroll 2
         for (int j = 0; j < NJ; ++j) {
             const int n = lane + 32 * j;
-            const float v = row[n];
+            const float v0 = row0[n], v1 = row1[n];
             const float4* wp = reinterpret_cast<const float4*>(&s_w[n * DEC_WLD]);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const float4 w = wp[q];
-                acc[4 * q] = fmaf(v, w.x, acc[4 * q]);
-                acc[4 * q + 1] = fmaf(v, w.y, acc[4 * q + 1]);
-                acc[4 * q + 2] = fmaf(v, w.z, acc[4 * q + 2]);
-                acc[4 * q + 3] = fmaf(v, w.w, acc[4 * q + 3]);
+                a0[4 * q] = fmaf(v0, w.x, a0[4 * q]);
+                a0[4 * q + 1] = fmaf(v0, w.y, a0[4 * q + 1]);
+                a0[4 * q + 2] = fmaf(v0, w.z, a0[4 * q + 2]);
+                a0[4 * q + 3] = fmaf(v0, w.w, a0[4 * q + 3]);
+                a1[4 * q] = fmaf(v1, w.x, a1[4 * q]);
+                a1[4 * q + 1] = fmaf(v1, w.y, a1[4 * q + 1]);
+                a1[4 * q + 2] = fmaf(v1, w.z, a1[4 * q + 2]);
+                a1[4 * q + 3] = fmaf(v1, w.w, a1[4 * q + 3]);
             }
         }
+        const bool up16 = lane & 16, up8 = lane & 8, up4 = lane & 4, up2 = lane & 2, up1 = lane & 1;
+        float x[16], y[8], z[4], u2[2];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) acc[k] = warp_sum(acc[k]);
-        if (lane < 16) {
-            float mine = 0.f;
+        for (int k = 0; k < 16; ++k)   // lanes 0..15 keep row 0, lanes 16..31 row 1
+            x[k] = (up16 ? a1[k] : a0[k]) + __shfl_xor_sync(0xffffffffu, up16 ? a0[k] : a1[k], 16);
 #pragma unroll
-            for (int k = 0; k < 16; ++k)
-                if (lane == k) mine = acc[k];
-            frames[item * 16 + lane] = mine;
-        }
+        for (int k = 0; k < 8; ++k) y[k] = (up8 ? x[8 + k] : x[k]) + __shfl_xor_sync(0xffffffffu, up8 ? x[k] : x[8 + k], 8);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) z[k] = (up4 ? y[4 + k] : y[k]) + __shfl_xor_sync(0xffffffffu, up4 ? y[k] : y[4 + k], 4);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) u2[k] = (up2 ? z[2 + k] : z[k]) + __shfl_xor_sync(0xffffffffu, up2 ? z[k] : z[2 + k], 2);
+        const float mine = (up1 ? u2[1] : u2[0]) + __shfl_xor_sync(0xffffffffu, up1 ? u2[0] : u2[1], 1);
+        if (two || lane < 16) frames[item0 * 16 + lane] = mine;
     }
 }
 
