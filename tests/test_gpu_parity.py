@@ -114,6 +114,44 @@ def test_gemm_resadd_and_folded_rmsnorm(M, N, K, P):
     assert rel_max(out.cpu(), exp2) < tol * 2
 
 
+@pytest.mark.parametrize("P", [2, 1], ids=["fp32-mode", "bf16-mode"])
+def test_gemm_wide_tile_variants(P, monkeypatch):
+    """Problems big enough for 256-wide tiles (>= one tile per SM) take the sixteen-epilogue-warp kernels -- fp32 mode: mask over
+    half-depth SWIZZLE_64B stages; bf16 mode: in_proj / mask -- and, with MTN_GEMM_HALF_STAGES = 1 / 2, the half-depth in_proj
+    variants.  All of them must match fp64 and be bit-identical to the eight-warp, 64-deep-stage kernel (same K order)."""
+    g = torch.Generator().manual_seed(11 + P)
+    M, K, di, enc = 21000, 256, 256, 256          # 165 row tiles x 2 column tiles of 256; M % 128 != 0 (ragged last tile)
+    a = torch.randn(M, K, generator=g)
+    w = torch.randn(2 * di, K, generator=g) / K ** 0.5
+    mixw = torch.rand(M, enc, generator=g).to(DEV)
+    ap, wp = ops.split_planes(a.to(DEV), P), ops.split_planes(w.to(DEV), P)
+    ref = _planes_value(ap).double() @ _planes_value(wp).double().t()
+    exp_in = ref.clone()
+    exp_in[:, di:] = torch.nn.functional.silu(exp_in[:, di:])
+    exp_mask = ref.clamp(min=0) * torch.cat([mixw.cpu(), mixw.cpu()], 1).double()
+    tol = 5e-5 if P == 2 else 5e-6
+    outs = {}
+    for hs in ("0", "", "1", "2"):               # "" = the shipped rule
+        if hs:
+            monkeypatch.setenv("MTN_GEMM_HALF_STAGES", hs)
+        else:
+            monkeypatch.delenv("MTN_GEMM_HALF_STAGES", raising=False)
+        o_in = ops.gemm(ap, wp, M, 2 * di, K, epilogue=_lib.EPI_INPROJ, epi_param=di, out_bf16=(P == 1))
+        o_mask = ops.gemm(ap, wp, M, 2 * enc, K, epilogue=_lib.EPI_MASK, epi_param=enc, aux=mixw)
+        o_store = ops.gemm(ap, wp, M, 2 * di, K)
+        torch.cuda.synchronize()
+        outs[hs] = (o_in, o_mask, o_store)
+        if P == 2:
+            assert rel_max(o_in.cpu(), exp_in) < tol
+        else:
+            assert rel_mixed(o_in.float().cpu(), exp_in) < 2 ** -8
+        assert rel_max(o_mask.cpu(), exp_mask) < tol
+        assert rel_max(o_store.cpu(), ref) < tol
+    for hs in ("", "1", "2"):
+        for got, base in zip(outs[hs], outs["0"]):
+            assert torch.equal(got, base), f"MTN_GEMM_HALF_STAGES={hs!r} differs from the eight-warp kernel"
+
+
 def test_gemm_rejects_bad_shapes():
     ap = torch.zeros(2, 128, 64, dtype=torch.bfloat16, device=DEV)
     wp = torch.zeros(2, 40, 64, dtype=torch.bfloat16, device=DEV)
