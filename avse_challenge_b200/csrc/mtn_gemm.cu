@@ -19,6 +19,7 @@
 #include "mtn_ptx.cuh"
 #include "mtn_host.h"
 #include <stdlib.h>
+#include <string.h>
 
 namespace mtn {
 
@@ -53,14 +54,15 @@ struct GemmParams {
 // TMA request for k-block k + 2 goes out when k-block k retires -- one k-block (1 536 tensor-pipe cycles) before its data is
 // needed, less than a 96 KB load takes under load (in_proj: tensor pipe 55 % active).  With 32-deep stages (48 KB, four of them)
 // the request leads by three stages.
-template <int P, int BN, int CG = 1, int BKT = BK, int EW = EPI_WARPS>
+template <int P, int BN, int CG = 1, int BKT = BK, int EW = EPI_WARPS, bool TS = false>
 struct GemmCfg {
     static_assert(EW == 8 || EW == 16, "epilogue warps: two or four per TMEM lane quarter");
     static_assert(BKT == 64 || BKT == 32, "stage depth: 64 (SWIZZLE_128B) or 32 (SWIZZLE_64B) bf16 elements");
     static constexpr int A_BYTES = BM * BKT * 2;
     static constexpr int B_BYTES = (BN / CG) * BKT * 2;      // bytes of B this CTA stages per plane
     static constexpr int STAGE_BYTES = P * (A_BYTES + B_BYTES);
-    static constexpr int STAGING_BYTES = EW * 32 * STG_LD * 4;
+    // TS (bulk tensor stores): two dense 32 x 16 boxes (2 KB each, 512-byte aligned for the swizzle) per epilogue warp
+    static constexpr int STAGING_BYTES = TS ? EW * 4096 : EW * 32 * STG_LD * 4;
     static constexpr int BAR_BYTES = 256;
     static constexpr int BUDGET = 227 * 1024 - 1024 - STAGING_BYTES - BAR_BYTES;
     static constexpr int STAGES_RAW = BUDGET / STAGE_BYTES;
@@ -72,11 +74,12 @@ struct GemmCfg {
     static_assert(B_BYTES % 1024 == 0, "B tile must keep 1024B alignment for SWIZZLE_128B");
 };
 
-template <int P, int BN, int EPI, bool OUT_BF16, int CG = 1, int BKT = BK, int EW = EPI_WARPS>
+template <int P, int BN, int EPI, bool OUT_BF16, int CG = 1, int BKT = BK, int EW = EPI_WARPS, bool TS = false>
 __global__ void __launch_bounds__(64 + 32 * EW, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-                    const GemmParams p) {
-    using Cfg = GemmCfg<P, BN, CG, BKT, EW>;
+                    const __grid_constant__ CUtensorMap mapO, const GemmParams p) {
+    using Cfg = GemmCfg<P, BN, CG, BKT, EW, TS>;
+    static_assert(!TS || EPI == MTN_EPI_STORE || EPI == MTN_EPI_INPROJ, "bulk-store epilogue: plain store and in_proj only");
     constexpr int ESPLIT = EW / 4;   // epilogue warps per TMEM lane quarter: each takes every ESPLIT-th 16-column chunk
     static_assert(EPI != MTN_EPI_RESADD || EW == 8, "the row-sum planes of the resadd epilogue are laid out for two warps per quarter");
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -219,6 +222,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         int acc = 0;
         uint32_t acc_phase = 0;
         float ss_next[4] = {0.f, 0.f, 0.f, 0.f};
+        uint32_t nstore = 0;   // TS: bulk stores issued by this warp so far (selects the staging box)
         auto load_ss = [&](int tile2) {  // sum of the partial-sum planes (fixed order) for this lane's 4 rows of tile2
             if (tile2 >= total_tiles) return;
             const int r2 = tile2 % tiles_per_group;
@@ -274,6 +278,59 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             // 2.4 M BSSY + 2.4 M BSYNC, 2.6 M ISETP, 2.3 M R2UR for 1.0 M STG), in warps that run latency-bound.  Rows past M hold
             // zeros (TMA zero-fills the A rows, guarded aux loads return zeros), so computing them is harmless.
             constexpr int NCH = BN / 16;
+            if constexpr (TS) {
+                // Bulk-store epilogue (plain store / in_proj, no folded norm): the thread that read row `lane` of the chunk from
+                // TMEM applies the activation in registers, writes its 16 values (64 B fp32 / 32 B bf16) into a dense, swizzled
+                // 32 x 16 box in shared memory, and one lane hands the box to the TMA unit -- no transposing read-back, no
+                // per-row address arithmetic, no global store instructions in the warp.  Rows past M are clipped by the tensor map.
+                uint8_t* sbox = reinterpret_cast<uint8_t*>(staging) + e * 4096;   // two boxes, used alternately (nstore)
+#pragma unroll
+                for (int j = 0; j < (NCH + ESPLIT - 1) / ESPLIT; ++j) {
+                    const int ch = j * ESPLIT + chalf;
+                    if (NCH % ESPLIT != 0 && ch >= NCH) break;
+                    const int c0 = ch * 16;
+                    uint32_t v[16];
+                    tmem_ld_x16(t_base + c0, v);
+                    tmem_ld_wait();
+                    if (ch + ESPLIT >= NCH) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) release_acc(acc);
+                        released = true;
+                    }
+                    const int ccol = nt * BN + c0;
+                    if (EPI == MTN_EPI_INPROJ && ccol >= p.epi_param) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(silu_sel<OUT_BF16>(__uint_as_float(v[i])));
+                    }
+                    uint8_t* box = sbox + (nstore++ & 1) * 2048;
+                    if (lane == 0) bulk_wait_group_read<1>();   // the store issued from this buffer two chunks ago has read it
+                    __syncwarp();
+                    if (OUT_BF16) {     // rows of 32 B, SWIZZLE_32B: 16-byte chunk c of row r sits at c ^ ((r >> 2) & 1)
+                        uint32_t pk[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+                            pk[i] = *reinterpret_cast<const uint32_t*>(&h2);
+                        }
+#pragma unroll
+                        for (int c = 0; c < 2; ++c)
+                            *reinterpret_cast<uint4*>(box + lane * 32 + ((c ^ ((lane >> 2) & 1)) << 4)) =
+                                make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+                    } else {            // rows of 64 B, SWIZZLE_64B: chunk c of row r sits at c ^ ((r >> 1) & 3)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            *reinterpret_cast<uint4*>(box + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4)) =
+                                make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&mapO, box, g * p.out_group_stride + ccol, row0);
+                        bulk_commit_group();
+                    }
+                }
+            } else
 #pragma unroll
             for (int j = 0; j < (NCH + ESPLIT - 1) / ESPLIT; ++j) {
                 const int ch = j * ESPLIT + chalf;      // this warp's j-th 16-column chunk
@@ -441,6 +498,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         }
     }
 
+    if (TS && warp >= 2 && lane == 0) bulk_wait_group_all();   // this lane's bulk stores have left shared memory and are performed
     tc_fence_before();
     if (CG == 2) cluster_sync_all();   // neither CTA may leave (or free TMEM) while the pair's MMAs / remote arrives are in flight
     else __syncthreads();
@@ -451,9 +509,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     }
 }
 
-template <int P, int BN, int EPI, bool OUT_BF16, int CG = 1, int BKT = BK, int EW = EPI_WARPS>
+template <int P, int BN, int EPI, bool OUT_BF16, int CG = 1, int BKT = BK, int EW = EPI_WARPS, bool TS = false>
 static int launch_gemm(const mtn_gemm_args* a, cudaStream_t stream) {
-    using Cfg = GemmCfg<P, BN, CG, BKT, EW>;
+    using Cfg = GemmCfg<P, BN, CG, BKT, EW, TS>;
     constexpr CUtensorMapSwizzle swz = BKT == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     CUtensorMap mapA, mapB;
     {
@@ -469,6 +527,16 @@ static int launch_gemm(const mtn_gemm_args* a, cudaStream_t stream) {
         uint64_t str[2] = {(uint64_t)a->K * 2, rows * a->K * 2};
         uint32_t box[3] = {BKT, BN / CG, 1};
         if (!encode_tmap(&mapB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, a->w, dims, str, box, swz))
+            return MTN_ECUDA;
+    }
+    CUtensorMap mapO;
+    memset(&mapO, 0, sizeof(mapO));
+    if (TS) {   // output as a 2-D tensor [M][ldo]; one box = 32 rows x 16 columns of a chunk
+        uint64_t dims[2] = {(uint64_t)a->ldo, (uint64_t)a->M};
+        uint64_t str[1] = {(uint64_t)a->ldo * (OUT_BF16 ? 2 : 4)};
+        uint32_t box[2] = {16, 32};
+        if (!encode_tmap(&mapO, OUT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, a->out, dims, str,
+                         box, OUT_BF16 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B))
             return MTN_ECUDA;
     }
     GemmParams p;
@@ -492,7 +560,7 @@ static int launch_gemm(const mtn_gemm_args* a, cudaStream_t stream) {
     p.rowsq_parts = a->rowsq_parts;
     p.tiles_m = (a->M + BM - 1) / BM;
     p.tiles_n = a->N / BN;
-    auto kern = gemm_tcgen05_kernel<P, BN, EPI, OUT_BF16, CG, BKT, EW>;
+    auto kern = gemm_tcgen05_kernel<P, BN, EPI, OUT_BF16, CG, BKT, EW, TS>;
     static std::atomic<unsigned long long> attr_done{0};   // per template instantiation, one bit per device
     if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(kern), Cfg::SMEM_BYTES, attr_done, "gemm")) return rc;
     int cap = a->max_ctas > 0 ? a->max_ctas : num_sms();
@@ -513,7 +581,7 @@ static int launch_gemm(const mtn_gemm_args* a, cudaStream_t stream) {
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, kern, mapA, mapB, p);
+        cudaError_t e = cudaLaunchKernelEx(&cfg, kern, mapA, mapB, mapO, p);
         if (e != cudaSuccess) {
             set_error("gemm(2cta): cluster launch failed: %s", cudaGetErrorString(e));
             return MTN_ECUDA;
@@ -522,7 +590,7 @@ static int launch_gemm(const mtn_gemm_args* a, cudaStream_t stream) {
     }
     int total = p.tiles_m * p.tiles_n * p.groups;
     int grid = total < cap ? total : cap;
-    kern<<<grid, 64 + 32 * EW, Cfg::SMEM_BYTES, stream>>>(mapA, mapB, p);
+    kern<<<grid, 64 + 32 * EW, Cfg::SMEM_BYTES, stream>>>(mapA, mapB, mapO, p);
     MTN_CUDA_LAUNCH_CHECK("gemm");
     return MTN_OK;
 }
@@ -552,6 +620,14 @@ static int half_depth_stages() {
     return -1;
 }
 
+// Bulk-store epilogue (GemmCfg TS): plain-store and in_proj GEMMs without the folded norm, output rows 16-byte aligned.
+// MTN_GEMM_TMA_STORE = 0 in the environment keeps the register -> shared -> STG epilogue (A/B runs).
+static bool bulk_store_ok(const mtn_gemm_args* a) {
+    if (a->rowsq || (a->epilogue != MTN_EPI_STORE && a->epilogue != MTN_EPI_INPROJ)) return false;
+    if (const char* v = getenv("MTN_GEMM_TMA_STORE")) if (atoi(v) == 0) return false;
+    return (size_t(a->ldo) * (a->out_bf16 ? 2 : 4)) % 16 == 0;
+}
+
 template <int P, int BN>
 static int dispatch_epi(const mtn_gemm_args* a, cudaStream_t s) {
     if (BN == 256 && use_cta_pairs(a, BN)) {
@@ -559,6 +635,14 @@ static int dispatch_epi(const mtn_gemm_args* a, cudaStream_t s) {
         if (a->epilogue == MTN_EPI_INPROJ && !a->out_bf16) return launch_gemm<P, BN, MTN_EPI_INPROJ, false, 2>(a, s);
         if (a->epilogue == MTN_EPI_INPROJ && a->out_bf16) return launch_gemm<P, BN, MTN_EPI_INPROJ, true, 2>(a, s);
         if (a->epilogue == MTN_EPI_MASK && !a->out_bf16) return launch_gemm<P, BN, MTN_EPI_MASK, false, 2>(a, s);
+    }
+    if constexpr (P == 2 && BN == 256) {
+        // fp32-mode in_proj / bottleneck: the bulk-store epilogue (B200, S 32 x 3 999, profiles/r02/gemm_tma_store_*.jsonl, bit-identical):
+        // in_proj 0.202 -> 0.192 ms, bottleneck 0.058 -> 0.056; no gain for x_proj's narrow tiles or the bf16-mode GEMMs (not wired).
+        if (bulk_store_ok(a)) {
+            if (a->epilogue == MTN_EPI_STORE && !a->out_bf16) return launch_gemm<P, BN, MTN_EPI_STORE, false, 1, BK, 8, true>(a, s);
+            if (a->epilogue == MTN_EPI_INPROJ && !a->out_bf16) return launch_gemm<P, BN, MTN_EPI_INPROJ, false, 1, BK, 8, true>(a, s);
+        }
     }
     if constexpr (P == 2 && BN == 256) {
         // Mask GEMM (fp32 mode): its epilogue waits on four global mix_w loads per chunk, so it runs with sixteen epilogue warps

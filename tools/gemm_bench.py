@@ -15,6 +15,7 @@ ap.add_argument("--L", type=int, default=3999); ap.add_argument("--mode", defaul
 ap.add_argument("--iters", type=int, default=20); ap.add_argument("--only", default="")
 ap.add_argument("--ab", action="store_true", help="time every case with MTN_GEMM_2CTA=0 (one CTA per tile) and =2 (CTA pairs wherever the shape allows) and compare the outputs")
 ap.add_argument("--ab-stages", action="store_true", help="time every case with MTN_GEMM_HALF_STAGES=0 (64-deep stages) and =1 (32-deep stages where the dispatcher uses them) and compare the outputs")
+ap.add_argument("--ab-env", default="", help="NAME=v0,v1,...: time every case with the library knob NAME set to each value and compare the outputs (e.g. MTN_GEMM_TMA_STORE=0,1)")
 a = ap.parse_args()
 hp = CONFIGS[a.hparams]; D, N, di, R = hp.d_model, hp.enc_dim, hp.d_inner, hp.dt_rank; nd = ops.n_dbl_for(R)
 P = 2 if a.mode == "fp32" else 1
@@ -47,8 +48,11 @@ for name, (A, W, m, n, k, kw, nbytes) in cases.items():
         continue
     run = lambda: ops.gemm(A, W, m, n, k, **kw)
     ref_out = None
-    for pairs in (("0", "2") if a.ab else ("s0", "s1", "s2") if a.ab_stages else (os.environ.get("MTN_GEMM_2CTA", "1"),)):
-        if pairs.startswith("s"):
+    env_name, env_vals = (a.ab_env.split("=")[0], a.ab_env.split("=")[1].split(",")) if a.ab_env else ("", [])
+    for pairs in (("0", "2") if a.ab else ("s0", "s1", "s2") if a.ab_stages else ["e" + v for v in env_vals] if env_vals else (os.environ.get("MTN_GEMM_2CTA", "1"),)):
+        if pairs.startswith("e"):
+            os.environ[env_name] = pairs[1:]                # read by the library at every call
+        elif pairs.startswith("s"):
             os.environ["MTN_GEMM_HALF_STAGES"] = pairs[1]   # read by the library at every call
         else:
             os.environ["MTN_GEMM_2CTA"] = pairs          # read by the library at every call
