@@ -296,7 +296,9 @@ class SeparatorEngine(LayerPlan):
             self.w = PackedWeights(hp, sds, self.device, mode)
         # a graph replays into the buffers of its workspace: evicting a workspace drops the graph captured against it
         self._graphs = LRUDict()
-        self._ws = LRUDict(on_evict=lambda key, ws: self._graphs.pop(key, None))
+        self._ws = LRUDict(on_evict=lambda key, ws: (self._graphs.pop(key, None), self._host_io.pop(key, None)))
+        self._host_io = {}     # forward_host staging per (batch, T); dropped together with the shape's workspace
+        self._host_done = None
         # enc, bottleneck, layers, (norm_f +) mask, decoder(2); fused: no norm kernels
         per_layer = 5 if fuse_norm else 6
         self.launches_per_forward = (1 + 1 + hp.n_mamba * per_layer + 1 + 2) if fuse_norm else (1 + 1 + hp.n_mamba * per_layer + 2 + 2)
@@ -433,6 +435,78 @@ class SeparatorEngine(LayerPlan):
                 self._run(ws)
             self._graphs[key] = g
         return g
+
+    # ------------------------------------------------------------------ host buffers, pipelined
+    @torch.no_grad()
+    def forward_host(self, mix_host: torch.Tensor, out_host: torch.Tensor = None):
+        """Host -> host separation for serving loops: ``mix_host`` [B, T] fp32 in pinned memory -> ``out_host`` [B, T, n_spk]
+        (pinned; allocated when omitted).  Returns ``(out_host, done)``; ``out_host`` may be read after ``done.synchronize()``
+        (or after ``wait_host()``).  The copies ride two side streams and two staging buffers per shape, so in a loop of calls the
+        H2D copy of call i + 1 and the D2H copy of call i - 1 run under the kernels of call i; the result is the same as
+        ``forward(mix_host.cuda()).cpu()``.  ``mix_host`` must not be modified until ``done`` (it is read asynchronously)."""
+        if mix_host.dim() != 2 or mix_host.dtype != torch.float32 or mix_host.is_cuda or not mix_host.is_pinned():
+            raise _lib.MtnError("forward_host expects a pinned CPU fp32 tensor of shape [batch, T]")
+        B, T = mix_host.shape
+        if T < 16:
+            raise _lib.MtnError(f"T={T}: need at least one 16-sample frame")
+        if out_host is None:
+            out_host = torch.empty((B, T, self.hp.n_spk), dtype=torch.float32).pin_memory()
+        if tuple(out_host.shape) != (B, T, self.hp.n_spk) or out_host.dtype != torch.float32 or not out_host.is_pinned():
+            raise _lib.MtnError(f"out_host must be a pinned fp32 tensor of shape {(B, T, self.hp.n_spk)}")
+        with torch.cuda.device(self.device):
+            if self.plan_for(B, T) == "chunked":      # latency plan of tiny batches: nothing to overlap with, plain copies
+                out_host.copy_(self.forward(mix_host.to(self.device, non_blocking=True)), non_blocking=True)
+                done = torch.cuda.Event()
+                done.record()
+                self._host_done = done
+                return out_host, done
+            io = self._host_io.get((B, T))
+            if io is None:
+                io = {"k": 0, "s_in": torch.cuda.Stream(device=self.device), "s_out": torch.cuda.Stream(device=self.device),
+                      "mix": [torch.empty((B, T), dtype=torch.float32, device=self.device) for _ in range(2)],
+                      "est": [torch.empty((B, T, self.hp.n_spk), dtype=torch.float32, device=self.device) for _ in range(2)],
+                      "consumed": [None, None], "copied_out": [None, None]}
+                self._host_io[(B, T)] = io
+            k = io["k"]
+            io["k"] = 1 - k
+            cur = torch.cuda.current_stream()
+            ws = self.workspace(B, T)
+            # H2D into staging buffer k (free once the copy into the workspace two calls ago has read it)
+            if io["consumed"][k] is not None:
+                io["s_in"].wait_event(io["consumed"][k])
+            with torch.cuda.stream(io["s_in"]):
+                io["mix"][k].copy_(mix_host, non_blocking=True)
+                arrived = torch.cuda.Event()
+                arrived.record()
+            cur.wait_event(arrived)
+            ws.mix[:, :T].copy_(io["mix"][k], non_blocking=True)
+            io["consumed"][k] = torch.cuda.Event()
+            io["consumed"][k].record(cur)
+            if self.use_graph:
+                self._graph_for(ws, (B, T)).replay()
+            else:
+                self._run(ws)
+            # the workspace's estimate is overwritten by the next call: park it in est[k] (free once its D2H two calls ago is done)
+            if io["copied_out"][k] is not None:
+                cur.wait_event(io["copied_out"][k])
+            io["est"][k].copy_(ws.est, non_blocking=True)
+            parked = torch.cuda.Event()
+            parked.record(cur)
+            io["s_out"].wait_event(parked)
+            with torch.cuda.stream(io["s_out"]):
+                out_host.copy_(io["est"][k], non_blocking=True)
+                done = torch.cuda.Event()
+                done.record()
+            io["copied_out"][k] = done
+            self._host_done = done
+            return out_host, done
+
+    def wait_host(self):
+        """Make the current stream wait for the last ``forward_host`` result copy (and return its event)."""
+        done = getattr(self, "_host_done", None)
+        if done is not None:
+            torch.cuda.current_stream(self.device).wait_event(done)
+        return done
 
     def forward_into_workspace(self, batch: int, T: int):
         """Run (graph replay when enabled) on whatever is already in ``workspace(batch, T).mix``; returns the
