@@ -296,7 +296,7 @@ class SeparatorEngine(LayerPlan):
             self.w = PackedWeights(hp, sds, self.device, mode)
         # a graph replays into the buffers of its workspace: evicting a workspace drops the graph captured against it
         self._graphs = LRUDict()
-        self._ws = LRUDict(on_evict=lambda key, ws: (self._graphs.pop(key, None), self._host_io.pop(key, None)))
+        self._ws = LRUDict(on_evict=self._drop_shape)
         self._host_io = {}     # forward_host staging per (batch, T); dropped together with the shape's workspace
         self._host_done = None
         # enc, bottleneck, layers, (norm_f +) mask, decoder(2); fused: no norm kernels
@@ -304,6 +304,15 @@ class SeparatorEngine(LayerPlan):
         self.launches_per_forward = (1 + 1 + hp.n_mamba * per_layer + 1 + 2) if fuse_norm else (1 + 1 + hp.n_mamba * per_layer + 2 + 2)
 
     # ------------------------------------------------------------------ building blocks
+    def _drop_shape(self, key, ws):
+        """LRU eviction of a (batch, T) shape: its graph replays into the evicted buffers, and its host-staging buffers may still
+        be in use on the copy streams (they are not known to the caching allocator there), so those drain first."""
+        self._graphs.pop(key, None)
+        io = self._host_io.pop(key, None)
+        if io is not None:
+            io["s_in"].synchronize()
+            io["s_out"].synchronize()
+
     def workspace(self, batch, T) -> Workspace:
         key = (batch, T)
         if key not in self._ws:
