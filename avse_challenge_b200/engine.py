@@ -277,8 +277,12 @@ class SeparatorEngine(LayerPlan):
     # Batches this small are bound by the scan's serial chain, not by throughput (B = 1, 4 s @ 8 kHz, S: 64 warp pairs on
     # 148 SMs walk 3 999 steps: 8.2 of the batch plan's 9.0 ms).  The chunked-scan plan (parallel.SequenceParallelSeparator
     # on this process alone: summary pass -> fold -> seeded pass over SMALL_BATCH_CHUNKS time chunks) cuts that chain and
-    # takes 2.06 ms per utterance as one CUDA graph, so up to SMALL_BATCH_MAX utterances run through it one after the other.
-    SMALL_BATCH_MAX = 3
+    # takes 1.9 ms per utterance as one CUDA graph; up to SMALL_BATCH_STREAMS utterances run through their own plan instance
+    # at the same time (each one alone leaves most of the GPU idle).  Measured on B200 (tools/small_batch_latency.py,
+    # profiles/r02/small_batch_latency_S.jsonl; S, 4 s utterances, batch plan -> this plan): B = 1 8.7 -> 1.9 ms, 2 9.0 -> 3.0,
+    # 3 9.4 -> 4.0, 4 9.6 -> 5.1, 6 10.4 -> 7.6, 8 11.0 -> 10.0, 12 12.4 -> 15.1: used up to SMALL_BATCH_MAX utterances.
+    SMALL_BATCH_MAX = 6
+    SMALL_BATCH_STREAMS = 8
     SMALL_BATCH_CHUNKS = 16
     SMALL_BATCH_MIN_FRAMES = 1024
 
@@ -406,7 +410,7 @@ class SeparatorEngine(LayerPlan):
             raise _lib.MtnError(f"T={T}: need at least one 16-sample frame")
         with torch.cuda.device(self.device):   # launches go to the engine's device, whatever the caller has current
             if taps is None and self.plan_for(B, T) == "chunked":
-                return torch.cat([self._chunked_plan()(mix[b:b + 1]) for b in range(B)], dim=0)
+                return self._forward_chunked(mix)
             ws = self.workspace(B, T)
             ws.mix[:, :T].copy_(mix, non_blocking=True)
             if taps is not None or not self.use_graph:
@@ -423,13 +427,43 @@ class SeparatorEngine(LayerPlan):
             return "chunked"
         return "batch"
 
-    def _chunked_plan(self):
+    def _chunked_plan(self, k: int = 0):
+        """The k-th chunked-scan plan instance (own workspaces and CUDA graph, shared packed weights)."""
         if self._chunked is None:
+            self._chunked = []
+        while len(self._chunked) <= k:
             from .parallel import CudaSeqBackend, SequenceParallelSeparator
             be = CudaSeqBackend(self.hp, None, self.device, self.mode, weights=self.w)      # shares the packed weights
-            self._chunked = SequenceParallelSeparator(self.hp, backend=be, sub_chunks=self.SMALL_BATCH_CHUNKS, group="local",
-                                                      use_graph=self.use_graph)
-        return self._chunked
+            self._chunked.append((SequenceParallelSeparator(self.hp, backend=be, sub_chunks=self.SMALL_BATCH_CHUNKS,
+                                                            group="local", use_graph=self.use_graph),
+                                  torch.cuda.Stream(device=self.device)))
+        return self._chunked[k][0]
+
+    def _forward_chunked(self, mix: torch.Tensor) -> torch.Tensor:
+        """Small batches through the chunked-scan plan: one utterance occupies a fraction of the GPU (16 sub-chunks = 64 scan
+        CTAs on 148 SMs), so up to SMALL_BATCH_STREAMS utterances run at the same time, each through its own plan instance
+        (workspaces + whole-forward CUDA graph) on its own stream; per utterance the result is that of the single-utterance plan."""
+        B, T = mix.shape
+        if B == 1:
+            return self._chunked_plan(0)(mix)
+        n = min(B, self.SMALL_BATCH_STREAMS)
+        for k in range(n):
+            self._chunked_plan(k)
+        out = torch.empty((B, T, self.hp.n_spk), dtype=torch.float32, device=self.device)
+        cur = torch.cuda.current_stream()
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        for b in range(B):
+            plan, st = self._chunked[b % n]
+            if b < n:
+                st.wait_event(ready)
+            with torch.cuda.stream(st):
+                out[b:b + 1].copy_(plan(mix[b:b + 1]), non_blocking=True)
+        for k in range(n):
+            done = torch.cuda.Event()
+            done.record(self._chunked[k][1])
+            cur.wait_event(done)
+        return out
 
     def _graph_for(self, ws: Workspace, key):
         """The whole-forward CUDA graph of this shape (captured on first use, after one eager run that sets the kernels'
