@@ -150,6 +150,19 @@ def test_gemm_wide_tile_variants(P, monkeypatch):
     for hs in ("", "1", "2"):
         for got, base in zip(outs[hs], outs["0"]):
             assert torch.equal(got, base), f"MTN_GEMM_HALF_STAGES={hs!r} differs from the eight-warp kernel"
+    # the bulk-store epilogue (fp32-mode plain store / in_proj: cp.async.bulk.tensor of swizzled boxes, rows past M clipped by
+    # the tensor map) against the register -> shared -> STG epilogue
+    monkeypatch.delenv("MTN_GEMM_HALF_STAGES", raising=False)
+    monkeypatch.setenv("MTN_GEMM_TMA_STORE", "0")
+    guard = torch.full((M + 64, 2 * di), 7.0, device=DEV)            # rows past M must stay untouched by either epilogue
+    o_in = ops.gemm(ap, wp, M, 2 * di, K, epilogue=_lib.EPI_INPROJ, epi_param=di, out_bf16=(P == 1))
+    o_store = ops.gemm(ap, wp, M, 2 * di, K)
+    monkeypatch.delenv("MTN_GEMM_TMA_STORE", raising=False)
+    assert torch.equal(o_in, outs[""][0]) and torch.equal(o_store, outs[""][2])
+    if P == 2:
+        ops.gemm(ap, wp, M, 2 * di, K, out=guard[:M])
+        torch.cuda.synchronize()
+        assert torch.equal(guard[:M], o_store) and bool((guard[M:] == 7.0).all())
 
 
 def test_gemm_rejects_bad_shapes():
