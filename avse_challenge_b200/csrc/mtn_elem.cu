@@ -473,51 +473,62 @@ decoder_frames_kernel(const float* __restrict__ sep, const float* __restrict__ w
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int warps_per_block = blockDim.x >> 5;
-    // One warp per PAIR of (token, speaker) rows: the filter taps are read from shared memory once for both, and the 2 x 16
-    // per-lane partial sums are reduced by a transposing butterfly (offsets 16, 8, 4, 2, 1; every step halves the values a lane
+    // One warp per group of RPW = 4 (token, speaker) rows: every filter tap read from shared memory serves four rows (the kernel
+    // is paced by those 64-byte-per-lane reads: 16 shared-memory wavefronts per 32 channels), and the 16 per-lane partial sums of
+    // each PAIR of rows are reduced by a transposing butterfly (offsets 16, 8, 4, 2, 1; every step halves the values a lane
     // keeps) -- 31 shuffles per pair instead of 80 per row, the same summation tree as a plain warp sum (bit-identical), and
-    // lane l ends up with tap l & 15 of row l >> 4: one coalesced 128-byte store.
-    const size_t pairs = (items + 1) / 2;
-    for (size_t pr = size_t(blockIdx.x) * warps_per_block + (threadIdx.x >> 5); pr < pairs;
-         pr += size_t(gridDim.x) * warps_per_block) {
-        const size_t item0 = 2 * pr;
-        const bool two = item0 + 1 < items;
-        const float* row0 = sep + item0 * N;  // sep[token][s*N + n] -> contiguous in (token, s)
-        const float* row1 = two ? row0 + N : row0;
-        float a0[16], a1[16];
+    // lane l ends up with tap l & 15 of row l >> 4 of the pair: one coalesced 128-byte store per pair.
+    constexpr int RPW = 4;
+    const size_t groups = (items + RPW - 1) / RPW;
+    for (size_t grp = size_t(blockIdx.x) * warps_per_block + (threadIdx.x >> 5); grp < groups;
+         grp += size_t(gridDim.x) * warps_per_block) {
+        const size_t item0 = RPW * grp;
+        const float* row[RPW];   // sep[token][s*N + n] -> contiguous in (token, s); rows past the end repeat the first one
 #pragma unroll
-        for (int k = 0; k < 16; ++k) a0[k] = a1[k] = 0.f;
+        for (int i = 0; i < RPW; ++i) row[i] = sep + (item0 + i < items ? item0 + i : item0) * N;
+        float a[RPW][16];
+#pragma unroll
+        for (int i = 0; i < RPW; ++i)
+#pragma unroll
+            for (int k = 0; k < 16; ++k) a[i][k] = 0.f;
 #pragma unroll 2
         for (int j = 0; j < NJ; ++j) {
             const int n = lane + 32 * j;
-            const float v0 = row0[n], v1 = row1[n];
+            float v[RPW];
+#pragma unroll
+            for (int i = 0; i < RPW; ++i) v[i] = row[i][n];
             const float4* wp = reinterpret_cast<const float4*>(&s_w[n * DEC_WLD]);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const float4 w = wp[q];
-                a0[4 * q] = fmaf(v0, w.x, a0[4 * q]);
-                a0[4 * q + 1] = fmaf(v0, w.y, a0[4 * q + 1]);
-                a0[4 * q + 2] = fmaf(v0, w.z, a0[4 * q + 2]);
-                a0[4 * q + 3] = fmaf(v0, w.w, a0[4 * q + 3]);
-                a1[4 * q] = fmaf(v1, w.x, a1[4 * q]);
-                a1[4 * q + 1] = fmaf(v1, w.y, a1[4 * q + 1]);
-                a1[4 * q + 2] = fmaf(v1, w.z, a1[4 * q + 2]);
-                a1[4 * q + 3] = fmaf(v1, w.w, a1[4 * q + 3]);
+#pragma unroll
+                for (int i = 0; i < RPW; ++i) {
+                    a[i][4 * q] = fmaf(v[i], w.x, a[i][4 * q]);
+                    a[i][4 * q + 1] = fmaf(v[i], w.y, a[i][4 * q + 1]);
+                    a[i][4 * q + 2] = fmaf(v[i], w.z, a[i][4 * q + 2]);
+                    a[i][4 * q + 3] = fmaf(v[i], w.w, a[i][4 * q + 3]);
+                }
             }
         }
         const bool up16 = lane & 16, up8 = lane & 8, up4 = lane & 4, up2 = lane & 2, up1 = lane & 1;
-        float x[16], y[8], z[4], u2[2];
 #pragma unroll
-        for (int k = 0; k < 16; ++k)   // lanes 0..15 keep row 0, lanes 16..31 row 1
-            x[k] = (up16 ? a1[k] : a0[k]) + __shfl_xor_sync(0xffffffffu, up16 ? a0[k] : a1[k], 16);
+        for (int pq = 0; pq < RPW / 2; ++pq) {
+            const float(&a0)[16] = a[2 * pq];
+            const float(&a1)[16] = a[2 * pq + 1];
+            float x[16], y[8], z[4], u2[2];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) y[k] = (up8 ? x[8 + k] : x[k]) + __shfl_xor_sync(0xffffffffu, up8 ? x[k] : x[8 + k], 8);
+            for (int k = 0; k < 16; ++k)   // lanes 0..15 keep the pair's first row, lanes 16..31 its second
+                x[k] = (up16 ? a1[k] : a0[k]) + __shfl_xor_sync(0xffffffffu, up16 ? a0[k] : a1[k], 16);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) z[k] = (up4 ? y[4 + k] : y[k]) + __shfl_xor_sync(0xffffffffu, up4 ? y[k] : y[4 + k], 4);
+            for (int k = 0; k < 8; ++k) y[k] = (up8 ? x[8 + k] : x[k]) + __shfl_xor_sync(0xffffffffu, up8 ? x[k] : x[8 + k], 8);
 #pragma unroll
-        for (int k = 0; k < 2; ++k) u2[k] = (up2 ? z[2 + k] : z[k]) + __shfl_xor_sync(0xffffffffu, up2 ? z[k] : z[2 + k], 2);
-        const float mine = (up1 ? u2[1] : u2[0]) + __shfl_xor_sync(0xffffffffu, up1 ? u2[0] : u2[1], 1);
-        if (two || lane < 16) frames[item0 * 16 + lane] = mine;
+            for (int k = 0; k < 4; ++k) z[k] = (up4 ? y[4 + k] : y[k]) + __shfl_xor_sync(0xffffffffu, up4 ? y[k] : y[4 + k], 4);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) u2[k] = (up2 ? z[2 + k] : z[k]) + __shfl_xor_sync(0xffffffffu, up2 ? z[k] : z[2 + k], 2);
+            const float mine = (up1 ? u2[1] : u2[0]) + __shfl_xor_sync(0xffffffffu, up1 ? u2[0] : u2[1], 1);
+            const size_t it0 = item0 + 2 * pq;
+            if (it0 + (lane >> 4) < items) frames[it0 * 16 + lane] = mine;
+        }
     }
 }
 
