@@ -280,8 +280,8 @@ class SeparatorEngine(LayerPlan):
     # takes 1.9 ms per utterance as one CUDA graph; up to SMALL_BATCH_STREAMS utterances run through their own plan instance
     # at the same time (each one alone leaves most of the GPU idle).  Measured on B200 (tools/small_batch_latency.py,
     # profiles/r02/small_batch_latency_S.jsonl; S, 4 s utterances, batch plan -> this plan): B = 1 8.7 -> 1.9 ms, 2 9.0 -> 3.0,
-    # 3 9.4 -> 4.0, 4 9.6 -> 5.1, 6 10.4 -> 7.6, 8 11.0 -> 10.0, 12 12.4 -> 15.1: used up to SMALL_BATCH_MAX utterances.
-    SMALL_BATCH_MAX = 6
+    # 3 9.4 -> 4.0, 4 9.6 -> 5.1, 6 10.4 -> 7.6, 7 10.5 -> 8.8, 8 10.8 -> 10.0, 9 11.1 -> 12.0: used up to SMALL_BATCH_MAX utterances.
+    SMALL_BATCH_MAX = 8
     SMALL_BATCH_STREAMS = 8
     SMALL_BATCH_CHUNKS = 16
     SMALL_BATCH_MIN_FRAMES = 1024
@@ -448,7 +448,13 @@ class SeparatorEngine(LayerPlan):
             return self._chunked_plan(0)(mix)
         n = min(B, self.SMALL_BATCH_STREAMS)
         for k in range(n):
-            self._chunked_plan(k)
+            plan = self._chunked_plan(k)
+            # first use of an instance at this length = eager run + CUDA-graph capture: done here, alone on the device, because
+            # a capture must not overlap work in flight on the other instances' streams (allocator events invalidate it)
+            if self.use_graph and plan._graphs.get(T) is None:
+                torch.cuda.synchronize(self.device)
+                plan(mix[:1])
+                torch.cuda.synchronize(self.device)
         out = torch.empty((B, T, self.hp.n_spk), dtype=torch.float32, device=self.device)
         cur = torch.cuda.current_stream()
         ready = torch.cuda.Event()
