@@ -532,6 +532,8 @@ class SeparatorEngine(LayerPlan):
             io["consumed"][k] = torch.cuda.Event()
             io["consumed"][k].record(cur)
             if self.use_graph:
+                if self._graphs.get((B, T)) is None:
+                    torch.cuda.synchronize(self.device)   # a first-use capture must not overlap copies in flight on other streams
                 self._graph_for(ws, (B, T)).replay()
             else:
                 self._run(ws)
