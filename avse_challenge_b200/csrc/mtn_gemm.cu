@@ -518,7 +518,13 @@ static int launch_gemm(const mtn_gemm_args* a, cudaStream_t stream) {
         uint64_t dims[3] = {(uint64_t)a->lda, (uint64_t)a->a_rows, (uint64_t)P};
         uint64_t str[2] = {(uint64_t)a->lda * 2, (uint64_t)a->a_rows * a->lda * 2};
         uint32_t box[3] = {BKT, BM, 1};
-        if (!encode_tmap(&mapA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, a->a, dims, str, box, swz))
+        // Narrow-N fp32-mode GEMMs (x_proj) stream A once from HBM, 128 B of every row per k-block: promoting those requests to
+        // 256 B brings the next k-block's piece of the row along.  B200, S 32 x 3 999: x_proj 0.1056 -> 0.0982 ms (83 -> 89 % of
+        // the HBM peak), bit-identical; neutral to -4 % for the wide tiles and the bf16-mode x_proj (97 % already), so only here
+        // (profiles/r02/gemm_l2_promotion_S_fp32.jsonl).
+        const CUtensorMapL2promotion promoA =
+            (P == 2 && BN <= 64) ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+        if (!encode_tmap(&mapA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, a->a, dims, str, box, swz, promoA))
             return MTN_ECUDA;
     }
     {

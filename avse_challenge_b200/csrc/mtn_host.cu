@@ -60,7 +60,8 @@ static encode_tiled_fn get_encode() {
 }
 
 bool encode_tmap(CUtensorMap* map, CUtensorMapDataType dtype, int rank, const void* base, const uint64_t* dims,
-                 const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swizzle) {
+                 const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swizzle,
+                 CUtensorMapL2promotion l2_promotion) {
     encode_tiled_fn fn = get_encode();
     if (!fn) return false;
     cuuint64_t gdim[5];
@@ -74,7 +75,7 @@ bool encode_tmap(CUtensorMap* map, CUtensorMapDataType dtype, int rank, const vo
     }
     for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
     CUresult r = fn(map, dtype, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, l2_promotion,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed (CUresult %d): rank %d dims [%llu,%llu,%llu] box [%u,%u,%u]", (int)r,

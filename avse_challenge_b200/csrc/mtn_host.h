@@ -15,7 +15,8 @@ int num_sms();
 // cuTensorMapEncodeTiled through the runtime's driver-entry-point query (no -lcuda link).
 // dims/strides innermost first; strides in BYTES for dims 1..rank-1.
 bool encode_tmap(CUtensorMap* map, CUtensorMapDataType dtype, int rank, const void* base, const uint64_t* dims,
-                 const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swizzle);
+                 const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swizzle,
+                 CUtensorMapL2promotion l2_promotion = CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
 
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) applies to one (function, DEVICE) pair, so the "already set"
 // cache is a per-call-site bit mask over device ordinals (atomic: the C ABI is re-entrant).  Devices >= 64 are
