@@ -36,6 +36,7 @@ struct GemmParams {
     int groups, out_group_stride;
     int epi_param;
     int tiles_m, tiles_n;
+    int desc;        // 1: row tiles are walked from the last to the first (see launch_gemm)
     __nv_bfloat16* out2;
     float* rowsum;
     const float* rowsq;
@@ -135,8 +136,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             for (int tile = tile0; tile < total_tiles; tile += tile_step) {
                 const int g = tile / tiles_per_group;
                 const int r = tile - g * tiles_per_group;
-                const int mt = r / p.tiles_n;
-                const int nt = r - mt * p.tiles_n;
+                const int mq = r / p.tiles_n;
+                const int nt = r - mq * p.tiles_n;
+                const int mt = p.desc ? tiles_m - 1 - mq : mq;
                 const int arow = (mt * CG + crank) * BM;                  // rows past M are zero-filled by TMA
                 const int brow = g * p.N + nt * BN + crank * (BN / CG);   // this CTA's share of the B tile
                 for (int kb = 0; kb < kblocks; ++kb) {
@@ -226,7 +228,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         auto load_ss = [&](int tile2) {  // sum of the partial-sum planes (fixed order) for this lane's 4 rows of tile2
             if (tile2 >= total_tiles) return;
             const int r2 = tile2 % tiles_per_group;
-            const int rowb = ((r2 / p.tiles_n) * CG + crank) * BM + q * 32 + (lane >> 2);
+            const int mq2 = r2 / p.tiles_n;
+            const int rowb = ((p.desc ? tiles_m - 1 - mq2 : mq2) * CG + crank) * BM + q * 32 + (lane >> 2);
 #pragma unroll
             for (int it = 0; it < 4; ++it) {
                 const int grow = rowb + it * 8;
@@ -254,8 +257,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         for (int tile = tile0; tile < total_tiles; tile += tile_step) {
             const int g = tile / tiles_per_group;
             const int r = tile - g * tiles_per_group;
-            const int mt = (r / p.tiles_n) * CG + crank;     // this CTA's 128-row tile
-            const int nt = r - (r / p.tiles_n) * p.tiles_n;
+            const int mq = r / p.tiles_n;
+            const int mt = (p.desc ? tiles_m - 1 - mq : mq) * CG + crank;     // this CTA's 128-row tile
+            const int nt = r - mq * p.tiles_n;
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_base = tmem_base + acc * Cfg::ACC_COLS + (uint32_t(q * 32) << 16);
@@ -566,6 +570,13 @@ static int launch_gemm(const mtn_gemm_args* a, cudaStream_t stream) {
     p.rowsq_parts = a->rowsq_parts;
     p.tiles_m = (a->M + BM - 1) / BM;
     p.tiles_n = a->N / BN;
+    // Row tiles are walked from the LAST to the first.  Every other kernel of the layer (norm, conv, scan, decoder) walks the
+    // tokens upwards, and each kernel's input is what the previous one has just written or read, 0.1 - 0.5 GB against 126 MB of
+    // L2: walking the same way, a consumer starts at the rows that were evicted first and pushes out the newest ones before it
+    // reaches them; walking the opposite way it starts on whatever part of the stream is still in L2.  MTN_GEMM_ORDER = 0 in
+    // the environment restores ascending order (A/B runs).
+    p.desc = 1;
+    if (const char* v = getenv("MTN_GEMM_ORDER")) p.desc = atoi(v) != 0;
     auto kern = gemm_tcgen05_kernel<P, BN, EPI, OUT_BF16, CG, BKT, EW, TS>;
     static std::atomic<unsigned long long> attr_done{0};   // per template instantiation, one bit per device
     if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(kern), Cfg::SMEM_BYTES, attr_done, "gemm")) return rc;
