@@ -8,7 +8,8 @@ import torch
 from avse_challenge_b200 import CONFIGS, ops, _lib
 if os.environ.get("MTN_LIB"):   # dev knob of this tool only: time an experimental build of the library
     _lib.LIB_PATH = os.path.abspath(os.environ["MTN_LIB"])
-    _lib.EXPECTED_ABI += 1000     # tools/devbuild.sh experiment builds identify themselves this way
+    if os.environ["MTN_LIB"].endswith("_dev.so"):
+        _lib.EXPECTED_ABI += 1000     # tools/devbuild.sh experiment builds identify themselves this way
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--hparams", default="S"); ap.add_argument("--batch", type=int, default=32)
