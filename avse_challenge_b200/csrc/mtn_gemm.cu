@@ -397,7 +397,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                         f.y += aux[it].y;
                         f.z += aux[it].z;
                         f.w += aux[it].w;
-                        // the planes of the updated residual: A operand of the next in_proj / mask GEMM
+                        // the planes of the updated residual: A operand of the next in_proj / mask GEMM (optional: without out2
+                        // and rowsum the epilogue is just `res += result`, the residual add of bimamba.py:446 moved into out_proj)
+                        if (p.out2 != nullptr) {
                         __nv_bfloat16* pr = p.out2 + size_t(grow) * p.ldo2 + gcol;
                         __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
                         if (P == 2) {
@@ -422,6 +424,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                             pl.x = *reinterpret_cast<uint32_t*>(&c2);
                             pl.y = *reinterpret_cast<uint32_t*>(&d2);
                             if (ok) *reinterpret_cast<uint2*>(pr + p.plane2) = pl;
+                        }
                         }
                         sqacc[it] = fmaf(f.x, f.x, fmaf(f.y, f.y, fmaf(f.z, f.z, fmaf(f.w, f.w, sqacc[it]))));
                     }
@@ -480,7 +483,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                 }
                 __syncwarp();
             }
-            if (EPI == MTN_EPI_RESADD) {
+            if (EPI == MTN_EPI_RESADD && p.rowsum != nullptr) {
                 // row sums of squares: 4 lanes share a row; every (N tile, warp half) owns one partial-sum plane, so the
                 // sums are plain stores (nothing to zero, bit-reproducible); the consumer adds the planes in order
 #pragma unroll
@@ -652,6 +655,7 @@ static int dispatch_epi(const mtn_gemm_args* a, cudaStream_t s) {
         if (a->epilogue == MTN_EPI_INPROJ && !a->out_bf16) return launch_gemm<P, BN, MTN_EPI_INPROJ, false, 2>(a, s);
         if (a->epilogue == MTN_EPI_INPROJ && a->out_bf16) return launch_gemm<P, BN, MTN_EPI_INPROJ, true, 2>(a, s);
         if (a->epilogue == MTN_EPI_MASK && !a->out_bf16) return launch_gemm<P, BN, MTN_EPI_MASK, false, 2>(a, s);
+        if (a->epilogue == MTN_EPI_RESADD && !a->out_bf16) return launch_gemm<P, BN, MTN_EPI_RESADD, false, 2>(a, s);
     }
     if constexpr (P == 2 && BN == 256) {
         // fp32-mode in_proj / bottleneck: the bulk-store epilogue (B200, S 32 x 3 999, profiles/r02/gemm_tma_store_*.jsonl, bit-identical):
@@ -758,9 +762,11 @@ extern "C" int mtn_gemm_fwd(const mtn_gemm_args* a, mtn_stream_t stream) {
     if (a->epilogue == MTN_EPI_INPROJ) MTN_REQUIRE(a->epi_param % 16 == 0, "gemm: inproj split must be a multiple of 16");
     if (a->rowsq) MTN_REQUIRE(a->rowsq_parts >= 1 && a->rowsq_parts <= 64, "gemm: rowsq_parts=%d", a->rowsq_parts);
     if (a->epilogue == MTN_EPI_RESADD)
-        MTN_REQUIRE(a->out2 && a->rowsum && !a->out_bf16 && a->groups == 1 && a->ldo2 % 4 == 0 && a->a2_rows >= a->M &&
-                        (reinterpret_cast<uintptr_t>(a->out2) & 7) == 0,
-                    "gemm: resadd epilogue needs fp32 out, out2 planes (8-byte aligned, ldo2 %% 4 == 0, a2_rows >= M), rowsum");
+        MTN_REQUIRE(!a->out_bf16 && a->groups == 1 &&
+                        ((!a->out2 && !a->rowsum) || (a->out2 && a->rowsum && a->ldo2 % 4 == 0 && a->a2_rows >= a->M &&
+                                                      (reinterpret_cast<uintptr_t>(a->out2) & 7) == 0)),
+                    "gemm: resadd epilogue needs fp32 out and either no out2 / rowsum (plain `out += result`) or both (out2 planes "
+                    "8-byte aligned, ldo2 %% 4 == 0, a2_rows >= M)");
     if (a->epilogue == MTN_EPI_XPROJ)
         MTN_REQUIRE(a->aux && (a->epi_param == 16 || a->epi_param == 32) && a->epi_param <= a->N &&
                         (reinterpret_cast<uintptr_t>(a->aux) & 15) == 0,

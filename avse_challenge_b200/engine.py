@@ -211,15 +211,29 @@ class LayerPlan:
         op("scan", ops.scan, ws.u, ws.dbl, ws.xz, di, lw["w_dt"], lw["dt_bias"], lw["A2"], lw["D"], ws.batch, ws.L, di, R,
            y=ws.y, dtp=ws.dtp if self.tc_dt else None, dir_mask=self.dir_mask, h_in=h, h_out=h)
 
-    def _layer(self, ws: Workspace, lw: dict, first: bool, taps=None, st=None, prenormed: bool = False):
+    def _layer(self, ws: Workspace, lw: dict, first: bool, taps=None, st=None, prenormed: bool = False,
+               res_in_gemm: bool = False, input_in_h: bool = False):
+        """``res_in_gemm``: the residual stream lives in ``ws.res`` only -- the caller has put the stack input there (or in ``ws.h``:
+        ``input_in_h``, then the first block's norm kernel copies it over), the norm
+        kernel reads it without adding anything, and out_proj adds its result to it in its epilogue (``MTN_EPI_RESADD`` without
+        planes / row sums).  Same fp32 additions as Add -> Norm (bimamba.py:446-447), so the result is bit-identical, but the
+        block output ``h`` never makes its round trip through HBM (1 KB written + 1 KB read per token and layer at D = 256)."""
         hp, P = self.hp, self.P
         D, di, M = hp.d_model, hp.d_inner, ws.M
         op = self._op
-        if not prenormed:   # prenormed: the producer already wrote ws.res and ws.xn = RMSNorm(res) * lw["norm"]
+        if prenormed:         # the producer already wrote ws.res and ws.xn = RMSNorm(res) * lw["norm"]
+            pass
+        elif res_in_gemm and not (first and input_in_h):
+            op("add_rmsnorm", ops.add_rmsnorm, None, ws.res, True, lw["norm"], P, xn=ws.xn, beta=lw["norm_b"])
+        else:                 # first block of a stack whose input sits in ws.h: residual := h (bimamba.py:446, residual None)
             op("add_rmsnorm", ops.add_rmsnorm, ws.h, ws.res, not first, lw["norm"], P, xn=ws.xn, beta=lw["norm_b"])
         op("gemm_in_proj", ops.gemm, ws.xn, lw["w_in"], M, 2 * di, D, out=ws.xz, epilogue=_lib.EPI_INPROJ, epi_param=di,
            out_bf16=ws.xz.dtype == torch.bfloat16)
         self._mixer_core(ws, lw, st)
+        if res_in_gemm:
+            op("gemm_out_proj", ops.gemm, ws.y, lw["w_out"], M, D, self.ndir * di, out=ws.res, epilogue=_lib.EPI_RESADD,
+               epi_param=1)
+            return
         op("gemm_out_proj", ops.gemm, ws.y, lw["w_out"], M, D, self.ndir * di, out=ws.h)
         if taps is not None:
             taps.append(ws.h.clone())
@@ -251,8 +265,9 @@ class MambaStack(LayerPlan):
         (``{"halo", "h"}``, unidirectional only).  ``prenormed``: the caller has already filled ``ws.res`` with the input
         and ``ws.xn`` with its RMSNorm under ``self.layers[0]["norm"]`` (fused producer), so the first launch is skipped."""
         for i, lw in enumerate(self.layers):
-            self._layer(ws, lw, first=(i == 0), st=None if states is None else states[i], prenormed=(prenormed and i == 0))
-        self._op("add_rmsnorm", ops.add_rmsnorm, ws.h, ws.res, True, self.norm_f, self.P, xn=False, out_f32=out,
+            self._layer(ws, lw, first=(i == 0), st=None if states is None else states[i], prenormed=(prenormed and i == 0),
+                        res_in_gemm=True, input_in_h=True)
+        self._op("add_rmsnorm", ops.add_rmsnorm, None, ws.res, True, self.norm_f, self.P, xn=False, out_f32=out,
                  beta=self.norm_f_b)
         return out
 
@@ -293,6 +308,7 @@ class SeparatorEngine(LayerPlan):
             raise ValueError("Unsupported mask non-linear function")      # mamba_masknet.py:138
         self.use_graph = use_graph
         self.fuse_norm = fuse_norm
+        self.res_in_gemm = True    # residual add in the out_proj epilogue (see LayerPlan._layer); False = separate Add -> Norm
         self.small_batch_plan = (small_batch_plan and hp.bidirectional and hp.mask_nonlinear == "relu"
                                  and not self.tc_dt)   # what the chunked driver implements
         self._chunked = None
@@ -331,10 +347,11 @@ class SeparatorEngine(LayerPlan):
         op = self._op
         ss = stream_state
         op("encoder_cln", ops.encoder_cln, ws.mix, w.w_enc, w.gamma, w.beta, P, mix_w=ws.mix_w, yn=ws.yn, T=ws.T)
-        op("gemm_bottleneck", ops.gemm, ws.yn, w.w_bot, M, D, N, out=ws.h)
+        rg = self.res_in_gemm and taps is None      # taps want every block's own output tensor
+        op("gemm_bottleneck", ops.gemm, ws.yn, w.w_bot, M, D, N, out=ws.res if rg else ws.h)
         for i, lw in enumerate(w.layers):
-            self._layer(ws, lw, first=(i == 0), taps=taps, st=None if ss is None else ss["layers"][i])
-        op("add_rmsnorm", ops.add_rmsnorm, ws.h, ws.res, True, w.norm_f, P, xn=ws.xn, beta=w.norm_f_b)
+            self._layer(ws, lw, first=(i == 0), taps=taps, st=None if ss is None else ss["layers"][i], res_in_gemm=rg)
+        op("add_rmsnorm", ops.add_rmsnorm, None if rg else ws.h, ws.res, True, w.norm_f, P, xn=ws.xn, beta=w.norm_f_b)
         if hp.mask_nonlinear == "softmax":   # mamba_masknet.py:133-134 + train_wsj0mix.py:91-92
             op("gemm_mask", ops.gemm, ws.xn, w.w_mask, M, hp.n_spk * N, D, out=ws.sep)
             op("softmax_mask", ops.softmax_mask, ws.sep, ws.mix_w, M, N, hp.n_spk)

@@ -220,7 +220,7 @@ class CudaSeqBackend:
         self.mix[:, :T_loc].copy_(mix_slice, non_blocking=True)
         o, w = self.ops, self.w
         o.encoder_cln(self.mix, w.w_enc, w.gamma, w.beta, P, mix_w=self.mix_w, yn=self.yn, T=T_loc)
-        o.gemm(self.yn, w.w_bot, Lr, D, N, out=self.h)
+        o.gemm(self.yn, w.w_bot, Lr, D, N, out=self.res)   # the residual stream starts here; out_proj adds to it in place
 
     def gather_buffer(self, name: str) -> torch.Tensor:
         """Pre-allocated ``[world, ...]`` receive buffer of the collective called ``name``."""
@@ -229,7 +229,7 @@ class CudaSeqBackend:
     # ---- per layer
     def pre(self, i: int):
         lw, o, hp = self.w.layers[i], self.ops, self.hp
-        o.add_rmsnorm(self.h, self.res, i > 0, lw["norm"], self.P, xn=self.xn, beta=lw["norm_b"])
+        o.add_rmsnorm(None, self.res, True, lw["norm"], self.P, xn=self.xn, beta=lw["norm_b"])
         o.gemm(self.xn, lw["w_in"], self.Lr, 2 * hp.d_inner, hp.d_model, out=self.xz, epilogue=self._lib.EPI_INPROJ,
                epi_param=hp.d_inner, out_bf16=self.xz.dtype == torch.bfloat16)
 
@@ -290,12 +290,15 @@ class CudaSeqBackend:
 
     def out_proj(self, i: int):
         lw, hp = self.w.layers[i], self.hp
-        self.ops.gemm(self.y, lw["w_out"], self.Lr, hp.d_model, 2 * hp.d_inner, out=self.h)
+        # residual add in the epilogue (MTN_EPI_RESADD without planes / row sums): same additions as Add -> Norm, bit-identical,
+        # and the block output never makes its round trip through HBM (engine.LayerPlan._layer)
+        self.ops.gemm(self.y, lw["w_out"], self.Lr, hp.d_model, 2 * hp.d_inner, out=self.res, epilogue=self._lib.EPI_RESADD,
+                      epi_param=1)
 
     # ---- tail
     def head(self):
         hp, w, o = self.hp, self.w, self.ops
-        o.add_rmsnorm(self.h, self.res, True, w.norm_f, self.P, xn=self.xn, beta=w.norm_f_b)
+        o.add_rmsnorm(None, self.res, True, w.norm_f, self.P, xn=self.xn, beta=w.norm_f_b)
         o.gemm(self.xn, w.w_mask, self.Lr, hp.n_spk * hp.enc_dim, hp.d_model, out=self.sep_full[1:],
                epilogue=self._lib.EPI_MASK, epi_param=hp.enc_dim, aux=self.mix_w)
 
