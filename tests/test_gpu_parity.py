@@ -165,6 +165,28 @@ def test_gemm_wide_tile_variants(P, monkeypatch):
         assert torch.equal(guard[:M], o_store) and bool((guard[M:] == 7.0).all())
 
 
+@pytest.mark.parametrize("M,N,K,P", [(21000, 256, 1024, 2), (700, 256, 512, 2), (21000, 512, 2048, 1)],
+                         ids=["cta-pairs-fp32", "one-cta", "cta-pairs-bf16"])
+def test_gemm_resadd_without_planes_is_out_plus_result(M, N, K, P):
+    """``MTN_EPI_RESADD`` without ``out2`` / ``rowsum`` is the residual add of bimamba.py:446 inside out_proj: ``out += A W^T``
+    with exactly the fp32 additions of a plain store followed by an add (bit-identical), on the CTA-pair kernel too."""
+    g = torch.Generator().manual_seed(M + K)
+    a = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) / K ** 0.5
+    res0 = torch.randn(M, N, generator=g).to(DEV)
+    ap, wp = ops.split_planes(a.to(DEV), P), ops.split_planes(w.to(DEV), P)
+    plain = ops.gemm(ap, wp, M, N, K)
+    res = res0.clone()
+    ops.gemm(ap, wp, M, N, K, out=res, epilogue=_lib.EPI_RESADD, epi_param=1)
+    torch.cuda.synchronize()
+    assert torch.equal(res, plain + res0)
+    over = torch.full((M, N), float("nan"), device=DEV)          # epi_param = 0: out := result, whatever it held
+    ops.gemm(ap, wp, M, N, K, out=over, epilogue=_lib.EPI_RESADD, epi_param=0)
+    assert torch.equal(over, plain)
+    ref = _planes_value(ap).double() @ _planes_value(wp).double().t() + res0.cpu().double()
+    assert rel_max(res.cpu(), ref) < (5e-5 if P == 2 else 2e-5)   # P = 1: fp32 accumulation over K = 2048 only
+
+
 def test_gemm_rejects_bad_shapes():
     ap = torch.zeros(2, 128, 64, dtype=torch.bfloat16, device=DEV)
     wp = torch.zeros(2, 40, 64, dtype=torch.bfloat16, device=DEV)
