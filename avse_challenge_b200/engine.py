@@ -7,12 +7,12 @@ per-direction tensors, ``A2 = -exp(A_log) * log2(e)``), (b) per-shape activation
 every activation channel-last, nothing executed by torch except buffer allocation.
 
 Per layer (reference call stack SURVEY.md 3.1):
-    add_rmsnorm   res += h ; xn = RMSNorm(res) * g              (bimamba.py:446-447)
+    add_rmsnorm   xn = RMSNorm(res) * g                          (bimamba.py:447; the add of :446 sits in out_proj's epilogue)
     gemm(in_proj) xz = xn @ W_in^T ; z-half stored as silu(z)   (bimamba.py:192-196, ssi.py:155)
     conv_silu     u_f, u_b = silu(conv1d(xs)) both directions   (ssi.py:182, bimamba.py:237)
     gemm(x_proj)  [dt|B|C]_f, [dt|B|C]_b (2 groups)             (ssi.py:186)
     scan          dt_proj + softplus + recurrence + D-skip + gate, x0.5, both directions (ssi.py:187,218-220)
-    gemm(out_proj) h = [y_f | y_b] @ [W_out | W_out]^T          (bimamba.py:253)
+    gemm(out_proj) res += [y_f | y_b] @ [W_out | W_out]^T       (bimamba.py:253 + the next block's residual add, :446)
 Optional plan without the add_rmsnorm kernel: RMSNorm(res) * g = rstd[row] * res * g[col], so g is folded
 into the consuming weight at load time, the residual add + sum of squares live in the producer GEMM's epilogue
 (MTN_EPI_RESADD) and rstd scales the consumer GEMM's accumulator rows (``fuse_norm=True``).  Measured on B200 at BASELINE

@@ -84,8 +84,11 @@ typedef struct {
      * the contraction.  So the producer GEMM (out_proj / bottleneck, MTN_EPI_RESADD) adds its result to the residual,
      * stores it as fp32 AND as operand planes and accumulates sum(res^2) per row; the consumer GEMM (in_proj / mask)
      * reads those planes and scales its accumulator rows by rsqrt(rowsq * rowsq_scale + rowsq_eps) before its own
-     * epilogue.  No separate add/norm kernel, no round trip of the mixer output through HBM. */
-    void* out2;          /* MTN_EPI_RESADD: bf16 planes [planes][a2_rows][ldo2] of the updated residual (next GEMM's A) */
+     * epilogue.  No separate add/norm kernel, no round trip of the mixer output through HBM.
+     * MTN_EPI_RESADD with out2 == NULL and rowsum == NULL is the residual add alone: out (fp32, in/out) += result (epi_param 1)
+     * or := result (epi_param 0) -- the default plan's out_proj: the norm kernel then reads the residual stream only. */
+    void* out2;          /* MTN_EPI_RESADD: bf16 planes [planes][a2_rows][ldo2] of the updated residual (next GEMM's A); nullable
+                            together with rowsum */
     float* rowsum;       /* MTN_EPI_RESADD: fp32 [parts][M], parts = mtn_gemm_rowsum_parts(N): plane k holds the sum of
                             res^2 over the columns one epilogue warp group of one N tile owns (plain stores: nothing to
                             zero, bit-reproducible) */
