@@ -37,6 +37,8 @@ cases = {
                M * 2 * di * 2 * P + M * 2 * nd * 4),
     "out_proj": (planes(M, 2 * di), planes(D, 2 * di), M, D, 2 * di, dict(out=torch.empty(M, D, device=dev)),
                  M * 2 * di * 2 * P + M * D * 4),
+    "out_proj_resadd": (planes(M, 2 * di), planes(D, 2 * di), M, D, 2 * di,        # the default plan's out_proj: res += result
+                        dict(out=rnd(M, D), epilogue=_lib.EPI_RESADD, epi_param=1), M * 2 * di * 2 * P + 2 * M * D * 4),
     "bottleneck": (planes(M, N), planes(D, N), M, D, N, dict(out=torch.empty(M, D, device=dev)),
                    M * N * 2 * P + M * D * 4),
     "mask": (planes(M, D), planes(2 * N, D), M, 2 * N, D,
