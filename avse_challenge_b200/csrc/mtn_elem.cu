@@ -7,6 +7,26 @@
 
 namespace mtn {
 
+// Operand-plane store of four consecutive values with PACKED conversions (F2FP.BF16.PACK_AB on the ALU pipe): the scalar
+// __float2bfloat16_rn of store_planes4 compiles to F2F, which shares the XU pipe with the SiLU's MUFUs -- in the fp32-mode conv
+// 8 of 24 XU operations per (4 channels, step) were conversions.  Same roundings, bit-identical planes.
+template <int P>
+__device__ __forceinline__ void store_planes4_packed(__nv_bfloat16* base, size_t plane_stride, size_t off, float4 v) {
+    const __nv_bfloat162 h01 = __floats2bfloat162_rn(v.x, v.y), h23 = __floats2bfloat162_rn(v.z, v.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<const uint32_t*>(&h01);
+    pk.y = *reinterpret_cast<const uint32_t*>(&h23);
+    *reinterpret_cast<uint2*>(base + off) = pk;
+    if (P == 2) {
+        const __nv_bfloat162 l01 = __floats2bfloat162_rn(v.x - __uint_as_float(pk.x << 16), v.y - __uint_as_float(pk.x & 0xffff0000u));
+        const __nv_bfloat162 l23 = __floats2bfloat162_rn(v.z - __uint_as_float(pk.y << 16), v.w - __uint_as_float(pk.y & 0xffff0000u));
+        uint2 pl;
+        pl.x = *reinterpret_cast<const uint32_t*>(&l01);
+        pl.y = *reinterpret_cast<const uint32_t*>(&l23);
+        *reinterpret_cast<uint2*>(base + plane_stride + off) = pl;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Encoder (Conv1d 1->N, k=16, s=8, no bias, ReLU) + ChannelwiseLayerNorm.  One warp per frame.
 // Reference: speechbrain dual_path.Encoder == baseline/avse2/model.py:14-24; cLN call
@@ -199,7 +219,7 @@ add_rmsnorm_kernel(const float* __restrict__ h, float* __restrict__ res, int res
                 o.z = r[j].z * rstd * gg.z;
                 o.w = r[j].w * rstd * gg.w;
                 }
-                if (xn) store_planes4<P>(xn, plane_stride, off, o);
+                if (xn) store_planes4_packed<P>(xn, plane_stride, off, o);
                 if (out_f32) *reinterpret_cast<float4*>(out_f32 + off) = o;
             }
         } else {
@@ -328,8 +348,8 @@ conv_silu_kernel(const XT* __restrict__ xz, int ldxz, const float* __restrict__ 
                 if (do_f) f = make_float4(silu_sel<FS>(f.x), silu_sel<FS>(f.y), silu_sel<FS>(f.z), silu_sel<FS>(f.w));
                 if (do_b) r = make_float4(silu_sel<FS>(r.x), silu_sel<FS>(r.y), silu_sel<FS>(r.z), silu_sel<FS>(r.w));
                 const size_t off = (size_t(b) * L + (t + i)) * (2 * di) + c;
-                if (do_f) store_planes4<P>(u, plane_stride, off, f);
-                if (do_b) store_planes4<P>(u, plane_stride, off + di, r);
+                if (do_f) store_planes4_packed<P>(u, plane_stride, off, f);
+                if (do_b) store_planes4_packed<P>(u, plane_stride, off + di, r);
             }
             w0 = w1; w1 = w2; w2 = w3; w3 = w4; w4 = w5; w5 = w6;
         }
@@ -395,13 +415,19 @@ __device__ __forceinline__ void conv_silu_bf16x8_body(const __nv_bfloat16* __res
     // forward: out[t] = sum_k w[k] x[t-3+k] -> window rows r[k] = x[t-3+k]; backward: out[t] = sum_k w[k] x[t+3-k] ->
     // r[k] = x[t+3-k].  Either way the window slides by one row per step in the direction of increasing t: forward drops
     // r[0] and appends x[t] as r[3]; backward drops r[3] and prepends x[t+3] as r[0].
+    // The four live rows sit in a ring of four register rows addressed by compile-time indices (the row loop is unrolled PF = 8
+    // steps, a multiple of the ring size, so the assignment repeats every outer iteration): forward, x[t0 - 3 + m] lives in
+    // slot m & 3, step j appends x[t] to slot (j + 3) & 3 and tap k reads slot (j + k) & 3; backward, x[t0 + m] lives in slot
+    // m & 3, step j appends x[t + 3] to slot (j + 3) & 3 and tap k reads slot (j + 3 - k) & 3.  (Shifting a 4 x 8 window by
+    // register moves cost 24 MOV per row next to 40 FFMA: 373 of the kernel's ~2 300 instructions.)
     float r[4][8];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) ld(dir ? (t0 + 2 - k) : (t0 - 3 + k), r[dir ? k + 1 : k]);
+    for (int k = 0; k < 3; ++k) ld(dir ? (t0 + k) : (t0 - 3 + k), r[k]);
     __nv_bfloat16* ubase = u + (size_t(b) * L) * (2 * size_t(di)) + size_t(dir) * di + c;
     // PF rows are requested together (PF x 16 B in flight per thread: with 16 resident warps per SM a single outstanding
     // load per thread left the kernel latency-bound at 2.2 TB/s), then consumed one step at a time.
     constexpr int PF = 8;
+    static_assert(PF % 4 == 0 && CONV8_TT % PF == 0, "the register ring needs whole periods per outer iteration");
     constexpr int shift = dir ? 3 : 0;                 // the new row of step t is x[t + shift]
 #pragma unroll 1
     for (int tb = t0; tb < t1; tb += PF) {
@@ -417,34 +443,32 @@ __device__ __forceinline__ void conv_silu_bf16x8_body(const __nv_bfloat16* __res
             const int t = tb + j;
             if (t < t1) {
                 const int tr = t + shift;
-                if (tr < L) unpack_bf16x8(raw[j], r[dir ? 0 : 3]);
-                else ld_halo(tr, r[dir ? 0 : 3]);
+                float(&rn)[8] = r[(j + 3) & 3];
+                if (tr < L) unpack_bf16x8(raw[j], rn);
+                else ld_halo(tr, rn);
+                const float(&r0)[8] = r[dir ? (j + 3) & 3 : j & 3];            // tap 0 .. tap 3 rows
+                const float(&r1)[8] = r[dir ? (j + 2) & 3 : (j + 1) & 3];
+                const float(&r2)[8] = r[dir ? (j + 1) & 3 : (j + 2) & 3];
+                const float(&r3)[8] = r[dir ? j & 3 : (j + 3) & 3];
                 uint32_t pk[4];
 #pragma unroll
                 for (int i = 0; i < 8; i += 2) {
-                    float f0 = fmaf(w[0][i], r[0][i], fmaf(w[1][i], r[1][i], fmaf(w[2][i], r[2][i], fmaf(w[3][i], r[3][i], bias[i]))));
-                    float f1 = fmaf(w[0][i + 1], r[0][i + 1],
-                                    fmaf(w[1][i + 1], r[1][i + 1], fmaf(w[2][i + 1], r[2][i + 1], fmaf(w[3][i + 1], r[3][i + 1], bias[i + 1]))));
+                    float f0 = fmaf(w[0][i], r0[i], fmaf(w[1][i], r1[i], fmaf(w[2][i], r2[i], fmaf(w[3][i], r3[i], bias[i]))));
+                    float f1 = fmaf(w[0][i + 1], r0[i + 1],
+                                    fmaf(w[1][i + 1], r1[i + 1], fmaf(w[2][i + 1], r2[i + 1], fmaf(w[3][i + 1], r3[i + 1], bias[i + 1]))));
                     f0 = silu_bf16_f(f0);
                     f1 = silu_bf16_f(f1);
                     const __nv_bfloat162 h2 = __floats2bfloat162_rn(f0, f1);
                     pk[i / 2] = *reinterpret_cast<const uint32_t*>(&h2);
                 }
                 *reinterpret_cast<uint4*>(ubase + size_t(t) * (2 * size_t(di))) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                if (dir) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) { r[3][i] = r[2][i]; r[2][i] = r[1][i]; r[1][i] = r[0][i]; }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) { r[0][i] = r[1][i]; r[1][i] = r[2][i]; r[2][i] = r[3][i]; }
-                }
             }
         }
     }
 }
 
 template <bool BOTH>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 conv_silu_bf16x8_kernel(const __nv_bfloat16* __restrict__ xz, int ldxz, const float* __restrict__ conv_w,
                         const float* __restrict__ conv_b, __nv_bfloat16* __restrict__ u, const float* __restrict__ halo_lo,
                         const float* __restrict__ halo_hi, int L, int di) {
