@@ -1030,3 +1030,25 @@ def test_engine_fused_conv_xproj_plan_equals_two_kernel_plan():
     assert a.can_fuse_convx and not b.fuse_convx     # the fused kernel is opt-in (measured slower)
     a.fuse_convx = True
     assert torch.equal(a(mix.to(DEV)), b(mix.to(DEV)))
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_one_process_two_devices(mode):
+    """One process driving two GPUs: the dynamic-shared-memory opt-in (`cudaFuncSetAttribute`) is per device, and an engine
+    launches on the device its weights live on whatever device is current.  cuda:1's engine runs FIRST on no device the
+    process has touched, with cuda:0 current, and must agree bit for bit with cuda:0's engine; inputs on another device are
+    refused."""
+    hp = CONFIGS["S"]
+    sds = init_state_dicts(hp, 1234)
+    mix, _ = synth_mixture(12, 8000, seed=77)                         # B > 8: the batch plan (scan + GEMM > 48 KB smem)
+    torch.cuda.set_device(0)
+    eng1 = SeparatorEngine(hp, sds, device="cuda:1", mode=mode, use_graph=False)
+    est1 = eng1(mix.to("cuda:1"))
+    assert est1.device == torch.device("cuda:1") and torch.cuda.current_device() == 0
+    eng0 = SeparatorEngine(hp, sds, device="cuda:0", mode=mode, use_graph=True)
+    est0 = eng0(mix.to("cuda:0"))
+    assert torch.equal(est0.cpu(), est1.cpu())
+    assert torch.equal(eng1(mix[:2, :4000].to("cuda:1")).cpu(), eng0(mix[:2, :4000].to("cuda:0")).cpu())   # chunked-free short plan
+    with pytest.raises(_lib.MtnError):
+        eng1(mix.to("cuda:0"))
