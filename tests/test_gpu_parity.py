@@ -703,6 +703,32 @@ def test_full_size_config3_properties():
         assert torch.equal(alone[0], est[i]), i
 
 
+def test_full_size_config5_properties():
+    """BASELINE config 5 (S hparams, ONE 600 s @ 16 kHz recording, fp32 mode) at full size through size-independent
+    properties: the chunked / sequence-parallel plan is invariant to where time is cut -- 74 sub-chunks (the shipped default,
+    two whole waves of scan CTAs) against 148 and against the UNCUT batch plan (one 1.2 M-step scan chain per channel, the
+    plan the oracle restates) within fp32 re-association across the seams; a silent recording gives a silent estimate."""
+    from avse_challenge_b200.parallel import SequenceParallelSeparator
+    hp = CONFIGS["S"]
+    sds = init_state_dicts(hp, 1234)
+    T = 600 * 16000
+    mix, _ = synth_mixture(1, T, sample_rate=16000, seed=55)
+    sp74 = SequenceParallelSeparator(hp, sds, device=DEV, mode="fp32", sub_chunks=74)
+    est74 = sp74(mix).cpu()
+    assert est74.shape == (1, T, 2) and torch.isfinite(est74).all()
+    assert sp74(torch.zeros_like(mix)).abs().max() == 0.0
+    del sp74
+    est148 = SequenceParallelSeparator(hp, sds, device=DEV, mode="fp32", sub_chunks=148)(mix).cpu()
+    assert rel_max(est148, est74) < 1e-4, rel_max(est148, est74)
+    del est148
+    torch.cuda.empty_cache()
+    eng = SeparatorEngine(hp, sds, device=DEV, mode="fp32", use_graph=False, small_batch_plan=False)
+    assert eng.plan_for(1, T) == "batch"
+    est_one = eng(mix.to(DEV)).cpu()
+    print(f"config 5 full size: 74 sub-chunks vs the uncut batch plan {rel_max(est74, est_one):.3e} x rms")
+    assert rel_max(est74, est_one) < 1e-4, rel_max(est74, est_one)
+
+
 # --------------------------------------------------------------------------- chunked / sequence-parallel pieces
 def test_conv_silu_halo_equals_slice_of_full_sequence():
     """A time chunk convolved with its neighbours' 3-frame halos == the same rows of the whole-utterance conv."""
