@@ -703,6 +703,25 @@ def test_full_size_config3_properties():
         assert torch.equal(alone[0], est[i]), i
 
 
+def test_full_size_config4_properties():
+    """BASELINE config 4 at its per-GPU size (AVSEC-4-shaped: 64 x 6 s @ 16 kHz mono mixtures, L = 11 999, S hparams, bf16
+    mode) through size-independent properties: finite output, silence in -> silence out, and batch independence -- utterance
+    i of the batch of 64 equals the same utterance run alone through the same (batch) plan, bit for bit.  The oracle
+    comparison at this shape is `test_config4_shape_and_M_hparams_vs_oracle`."""
+    hp = CONFIGS["S"]
+    sds = init_state_dicts(hp, 1234)
+    B, T = 64, 96000
+    mix, _ = synth_mixture(B, T, sample_rate=16000, seed=404)
+    mix[40] = 0.0
+    eng = SeparatorEngine(hp, sds, device=DEV, mode="bf16", use_graph=True, small_batch_plan=False)
+    est = eng(mix.to(DEV)).cpu()
+    assert est.shape == (B, T, 2) and torch.isfinite(est).all()
+    assert est[40].abs().max() == 0.0
+    for i in (0, 33, 63):
+        alone = eng(mix[i:i + 1].to(DEV)).cpu()
+        assert torch.equal(alone[0], est[i]), i
+
+
 def test_full_size_config5_properties():
     """BASELINE config 5 (S hparams, ONE 600 s @ 16 kHz recording, fp32 mode) at full size through size-independent
     properties: the chunked / sequence-parallel plan is invariant to where time is cut -- 74 sub-chunks (the shipped default,
