@@ -552,6 +552,33 @@ def measure_longform(a, ctx, steps, warmup, cpu_baseline=True, parity=False, sam
         pin_out.copy_(sp.forward_local(dmix, T), non_blocking=True)
 
     ms_e2e = timed(ctx, e2e_step, steps, 2)
+    # ---- the two scan passes timed in situ: one eager forward on every rank (the collectives need all of them) with CUDA
+    # events around the summary pass and the seeded pass of every layer
+    be, spans = sp.be, {"summary": [], "seeded": []}
+
+    def _spanned(fn, key):
+        def call(*args, **kw):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = fn(*args, **kw)
+            e1.record()
+            spans[key].append((e0, e1))
+            return out
+        return call
+
+    orig = (be.scan_summary, be.scan_seeded)
+    be.scan_summary, be.scan_seeded = _spanned(orig[0], "summary"), _spanned(orig[1], "seeded")
+    try:
+        for it in range(2):                                               # first pass warms the eager path up
+            for v in spans.values():
+                v.clear()
+            sp._forward_local(mix_d, T)
+            torch.cuda.synchronize()
+    finally:
+        be.scan_summary, be.scan_seeded = orig
+    scan_ms = {k: sum(e0.elapsed_time(e1) for e0, e1 in v) for k, v in spans.items()}
+    n_scan_layers = len(spans["seeded"])
+    scan_sum_ms, scan_seed_ms = ctx.max_over_ranks(scan_ms["summary"], scan_ms["seeded"])
     clocks = sampler.stop() if sampler else None
     ms_total, ms_e2e = ctx.max_over_ranks(ms_total, ms_e2e)
     graphed = bool(sp.use_graph and sp.graph_failed is None)
@@ -567,6 +594,9 @@ def measure_longform(a, ctx, steps, warmup, cpu_baseline=True, parity=False, sam
     L = hp.frames(T)
     plan = make_seq_plan(L, world, a.sub_chunks)
     step_ms = ms_total / steps
+    alg = scan_algorithmic_bytes(hp, 1, plan.ranges[0][1] - plan.ranges[0][0], a.mode, 2 if hp.bidirectional else 1)
+    per_layer_ms = (scan_sum_ms + scan_seed_ms) / max(1, n_scan_layers)
+    achieved = alg / (per_layer_ms * 1e-3) / 1e9
     per_fwd = 4 + hp.n_mamba * 10     # enc, bottleneck, (norm, in_proj, 2 edge copies, conv, x_proj, scan A, fold, scan B, out_proj) x layers, norm_f+mask, decoder(2)
     line = {
         "metric": METRIC, "value": audio_s / (step_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps,
@@ -580,8 +610,14 @@ def measure_longform(a, ctx, steps, warmup, cpu_baseline=True, parity=False, sam
         "gpu_launches": steps * (per_fwd + 1),
         "collectives_per_forward": ncoll, "cuda_graph": graphed,
         "roofline": {"kernel": "mtn::scan_kernel (summary pass) + mtn::scan_kernel_pair (seeded pass) per layer", "bound": "hbm",
-                     "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "peak_source": peak_src,
-                     "traffic": None, "note": "per-kernel roofline is reported on the batch workloads"},
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                     "traffic": None, "algorithmic_bytes_per_launch": alg, "ms_per_launch": per_layer_ms,
+                     "ms_summary_pass": scan_sum_ms / max(1, n_scan_layers), "ms_seeded_pass": scan_seed_ms / max(1, n_scan_layers),
+                     "launches_per_step": 2 * n_scan_layers, "share_of_step": (scan_sum_ms + scan_seed_ms) / step_ms,
+                     "note": "algorithmic bytes = op-boundary bytes of ONE scan over this rank's frames (the summary pass is "
+                             "the plan's overhead, not algorithmic traffic) / (summary + seeded pass time of one layer), timed "
+                             "with CUDA events in one eager forward, max over ranks; share_of_step relates those eager "
+                             "durations to the graph-replayed step"},
         "clocks": clocks,
     }
     if graph_note:
